@@ -1,0 +1,312 @@
+"""ctypes access to libraries that export HPMPC's C symbols, and to the batched hpmpc_b200 C ABI.
+
+The same `HpmpcLib` class drives
+  * the product  : hpmpc_b200/lib/libhpmpc_b200.so (CUDA; raises if it is missing -- there is no CPU fallback),
+  * the reference: oracle/_ref/libhpmpc_ref_{c99,avx2}.so (test infrastructure only),
+so a parity test calls the *same function name with the same arguments* on both.
+This module is harness code: it moves pointers around and never computes a solution.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Sequence
+
+import numpy as np
+
+from .problems import Ocp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "lib", "libhpmpc_b200.so")
+
+c_dpp = C.POINTER(C.c_void_p)
+BS, NCL = 4, 2
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+def aligned_zeros(n: int, align: int = 64) -> np.ndarray:
+    raw = np.zeros(n + align // 8 + 1, dtype=np.float64)
+    off = (-raw.ctypes.data % align) // 8
+    return raw[off:off + n]
+
+
+def ptr_array(arrs: Sequence[np.ndarray]):
+    """double** (or int**) from a list of numpy arrays; the list must outlive the call."""
+    n = max(len(arrs), 1)
+    out = (C.c_void_p * n)()
+    for i, a in enumerate(arrs):
+        out[i] = a.ctypes.data if a is not None else None
+    return out
+
+
+def int_array(v: Sequence[int]):
+    return (C.c_int * max(len(v), 1))(*[int(x) for x in v])
+
+
+def to_pmat(M: np.ndarray) -> np.ndarray:
+    """Dense matrix -> the reference's lib4 panel-major storage (auxiliary/d_aux_lib4.c:1310), 64-byte aligned."""
+    rows, cols = M.shape
+    pr, sda = _rup(max(rows, 1), BS), _rup(max(cols, 1), NCL)
+    p = aligned_zeros(pr * sda + 8)
+    if rows and cols:
+        I, J = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+        p[(I // BS) * BS * sda + I % BS + BS * J] = M
+    return p
+
+
+class HpmpcLib:
+    """A shared library exporting HPMPC's hot-path symbols (reference build or libhpmpc_b200.so)."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not found -- build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.path = path
+        self.lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        L = self.lib
+        for name in ("fortran_order_d_ip_ocp_hard_tv", "c_order_d_ip_ocp_hard_tv"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 5 \
+                + [C.c_int, C.c_int] + [C.c_void_p] * 18 + [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes.restype = C.c_int
+        L.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+        for name in ("d_back_ric_rec_sv_tv_work_space_size_bytes", "d_back_ric_rec_sv_tv_memory_space_size_bytes",
+                     "d_ip2_res_mpc_hard_tv_work_space_size_bytes"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_int] + [C.c_void_p] * 4
+        L.d_back_ric_rec_sv_tv_res.restype = None
+        L.d_back_ric_rec_sv_tv_res.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int] \
+            + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.d_back_ric_rec_trf_tv_res.restype = None
+        L.d_back_ric_rec_trf_tv_res.argtypes = [C.c_int] + [C.c_void_p] * 12
+        L.d_back_ric_rec_trs_tv_res.restype = None
+        L.d_back_ric_rec_trs_tv_res.argtypes = [C.c_int] + [C.c_void_p] * 11 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.d_ip2_res_mpc_hard_tv.restype = C.c_int
+        L.d_ip2_res_mpc_hard_tv.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p,
+                                            C.c_int] + [C.c_void_p] * 10 + [C.c_int] + [C.c_void_p] * 4
+
+    # ---------------------------------------------------------------- high level
+    def ip_ocp_hard_tv(self, p: Ocp, *, order: str = "fortran", k_max: int = 40, mu0: float = 2.0, mu_tol: float = 1e-8,
+                       warm_start: int = 0, x_init=None, u_init=None):
+        """{c,fortran}_order_d_ip_ocp_hard_tv (reference include/c_interface.h:62,65)."""
+        N = p.N
+        conv = (lambda M: np.ascontiguousarray(M)) if order == "c" else (lambda M: np.asfortranarray(M))
+        A = [conv(M) for M in p.A]; B = [conv(M) for M in p.B]
+        Q = [conv(M) for M in p.Q]; S = [conv(M) for M in p.S]; R = [conv(M) for M in p.R]
+        # numpy keeps 0-sized arrays valid; HPMPC never dereferences them
+        b = [np.ascontiguousarray(v) for v in p.b]; q = [np.ascontiguousarray(v) for v in p.q]; r = [np.ascontiguousarray(v) for v in p.r]
+        lb = [np.ascontiguousarray(v) for v in p.lb]; ub = [np.ascontiguousarray(v) for v in p.ub]
+        x = [np.zeros(max(n, 1)) for n in p.nx]; u = [np.zeros(max(n, 1)) for n in p.nu[:N]]
+        if x_init is not None:
+            for n in range(N + 1): x[n][:p.nx[n]] = x_init[n]
+            for n in range(N): u[n][:p.nu[n]] = u_init[n]
+        pi = [np.zeros(max(p.nx[n + 1], 1)) for n in range(N)]
+        lam = [np.zeros(max(2 * nb, 1)) for nb in p.nb]
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) for v in p.idxb]
+        nx, nu, nb, ng = int_array(p.nx), int_array(p.nu), int_array(p.nb), int_array([0] * (N + 1))
+        empty = [np.zeros(1) for _ in range(N + 1)]
+        wsz = self.lib.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N)
+        work = aligned_zeros(wsz // 8 + 16)
+        res = np.zeros(8); stat = np.zeros(5 * k_max + 5)
+        kk = C.c_int(0)
+        keep = [A, B, b, Q, S, R, q, r, lb, ub, x, u, pi, lam, idxb, empty]
+        fn = self.lib.c_order_d_ip_ocp_hard_tv if order == "c" else self.lib.fortran_order_d_ip_ocp_hard_tv
+        pa = ptr_array
+        arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(empty), pa(empty), pa(empty), pa(empty),
+                pa(x), pa(u), pa(pi), pa(lam)]
+        pidx = pa(idxb)
+        status = fn(C.byref(kk), k_max, mu0, mu_tol, N, nx, nu, nb, pidx, ng, N, warm_start, *arrs,
+                    res.ctypes.data, work.ctypes.data, stat.ctypes.data)
+        del keep
+        return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)],
+                    u=[u[n][:p.nu[n]].copy() for n in range(N)], pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
+                    lam=[lam[n][:2 * p.nb[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(),
+                    stat=stat[:5 * kk.value].reshape(-1, 5).copy())
+
+    # ---------------------------------------------------------------- low level (panel-major)
+    def _pm_problem(self, p: Ocp):
+        N = p.N
+        BAbt, RSQ = [], []
+        for n in range(N + 1):
+            nx, nu = p.nx[n], p.nu[n]
+            nux = nx + nu
+            if n < N:
+                nx1 = p.nx[n + 1]
+                M = np.vstack([p.B[n].T.reshape(nu, nx1), p.A[n].T.reshape(nx, nx1), p.b[n].reshape(1, nx1)])
+                BAbt.append(to_pmat(M))
+            H = np.zeros((nux + 1, nux))
+            H[:nu, :nu] = p.R[n]; H[nu:nux, :nu] = p.S[n].T; H[:nu, nu:nux] = p.S[n]; H[nu:nux, nu:nux] = p.Q[n]
+            H[nux, :nu] = p.r[n]; H[nux, nu:] = p.q[n]
+            RSQ.append(to_pmat(H))
+        return BAbt, RSQ
+
+    def _sizes(self, p: Ocp):
+        N = p.N
+        nx, nu, nb, ng = int_array(p.nx), int_array(p.nu), int_array(p.nb), int_array([0] * (N + 1))
+        return nx, nu, nb, ng
+
+    def ric(self, p: Ocp, mode: str = "sv"):
+        """d_back_ric_rec_sv_tv_res, or trf followed by trs (reference include/lqcp_solvers.h:41-45); unconstrained."""
+        N = p.N
+        nx, nu, nb0, ng = self._sizes(p)
+        nb = int_array([0] * (N + 1))
+        BAbt, RSQ = self._pm_problem(p)
+        wsz = self.lib.d_back_ric_rec_sv_tv_work_space_size_bytes(N, nx, nu, nb, ng)
+        msz = self.lib.d_back_ric_rec_sv_tv_memory_space_size_bytes(N, nx, nu, nb, ng)
+        work, mem = aligned_zeros(wsz // 8 + 16), aligned_zeros(msz // 8 + 16)
+        hux = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        hpi = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        hPb = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        idxb = [np.zeros(1, dtype=np.int32) for _ in range(N + 1)]
+        dummy = [aligned_zeros(8) for _ in range(N + 1)]
+        pa = ptr_array
+        pBAbt, pRSQ, pux, ppi, pPb, pidx, pd = pa(BAbt), pa(RSQ), pa(hux), pa(hpi), pa(hPb), pa(idxb), pa(dummy)
+        if mode == "sv":
+            self.lib.d_back_ric_rec_sv_tv_res(N, nx, nu, nb, pidx, ng, 0, pBAbt, pd, 0, pRSQ, pd, pd, pd, pd, pd,
+                                              pux, 1, ppi, 1, pPb, mem.ctypes.data, work.ctypes.data)
+        else:
+            hb = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+            hq = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+            for n in range(N):
+                hb[n][:p.nx[n + 1]] = p.b[n]
+            for n in range(N + 1):
+                hq[n][:p.nu[n]] = p.r[n]; hq[n][p.nu[n]:p.nu[n] + p.nx[n]] = p.q[n]
+            phb, phq = pa(hb), pa(hq)
+            self.lib.d_back_ric_rec_trf_tv_res(N, nx, nu, nb, pidx, ng, pBAbt, pRSQ, pd, pd, pd, mem.ctypes.data, work.ctypes.data)
+            self.lib.d_back_ric_rec_trs_tv_res(N, nx, nu, nb, pidx, ng, pBAbt, phb, phq, pd, pd, pux, 1, ppi, 1, pPb,
+                                               mem.ctypes.data, work.ctypes.data)
+        return dict(u=[hux[n][:p.nu[n]].copy() for n in range(N)],
+                    x=[hux[n][p.nu[n]:p.nu[n] + p.nx[n]].copy() for n in range(N + 1)],
+                    pi=[hpi[n][:p.nx[n + 1]].copy() for n in range(N)],
+                    Pb=[hPb[n][:p.nx[n + 1]].copy() for n in range(N)])
+
+    def ip2_res_mpc_hard_tv(self, p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, alpha_min=1e-8, warm_start=0):
+        """d_ip2_res_mpc_hard_tv on panel-major data (reference include/mpc_solvers.h:42)."""
+        N = p.N
+        nx, nu, nb, ng = self._sizes(p)
+        BAbt, RSQ = self._pm_problem(p)
+        pnb = [_rup(v, BS) for v in p.nb]
+        d = [aligned_zeros(2 * pnb[n] + 4) for n in range(N + 1)]
+        for n in range(N + 1):
+            d[n][:p.nb[n]] = p.lb[n]; d[n][pnb[n]:pnb[n] + p.nb[n]] = p.ub[n]
+        ux = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        pi = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        lam = [aligned_zeros(2 * pnb[n] + 4) for n in range(N + 1)]
+        t = [aligned_zeros(2 * pnb[n] + 4) for n in range(N + 1)]
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        dummy = [aligned_zeros(8) for _ in range(N + 1)]
+        wsz = self.lib.d_ip2_res_mpc_hard_tv_work_space_size_bytes(N, nx, nu, nb, ng)
+        work = aligned_zeros(wsz // 8 + 16)
+        stat = np.zeros(5 * k_max + 5)
+        kk = C.c_int(0)
+        pa = ptr_array
+        keep = (pa(BAbt), pa(RSQ), pa(dummy), pa(d), pa(ux), pa(pi), pa(lam), pa(t), pa(idxb))
+        status = self.lib.d_ip2_res_mpc_hard_tv(C.byref(kk), k_max, mu0, mu_tol, alpha_min, warm_start, stat.ctypes.data, N,
+                                                nx, nu, nb, keep[8], ng, keep[0], keep[1], keep[2], keep[3], keep[4], 1,
+                                                keep[5], keep[6], keep[7], work.ctypes.data)
+        return dict(status=status, kk=kk.value, u=[ux[n][:p.nu[n]].copy() for n in range(N)],
+                    x=[ux[n][p.nu[n]:p.nu[n] + p.nx[n]].copy() for n in range(N + 1)],
+                    pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
+                    lam=[np.concatenate([lam[n][:p.nb[n]], lam[n][pnb[n]:pnb[n] + p.nb[n]]]) for n in range(N + 1)],
+                    t=[np.concatenate([t[n][:p.nb[n]], t[n][pnb[n]:pnb[n] + p.nb[n]]]) for n in range(N + 1)],
+                    stat=stat[:5 * kk.value].reshape(-1, 5).copy())
+
+
+# ------------------------------------------------------------------------------------------- batched C ABI
+class Sizes(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in ("in_stride", "ux_stride", "pi_stride", "lam_stride", "L_stride", "ipm_work_stride")] \
+        + [(n, C.c_int) for n in ("N", "nzM", "nxM", "nbtot", "grid", "warps_per_cta", "n_slots", "smem_per_cta")]
+
+
+_product = None
+
+
+def product() -> C.CDLL:
+    """libhpmpc_b200.so, loaded once.  Raises if the library is missing: there is no fallback path."""
+    global _product
+    if _product is None:
+        if not os.path.exists(PRODUCT_LIB):
+            raise RuntimeError(f"{PRODUCT_LIB} is missing; run __graft_entry__.build() -- hpmpc_b200 has no CPU fallback")
+        L = C.CDLL(PRODUCT_LIB, mode=C.RTLD_GLOBAL)
+        L.hpmpc_b200_ocp_create.restype = C.c_int
+        L.hpmpc_b200_ocp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hpmpc_b200_ocp_destroy.argtypes = [C.c_void_p]
+        L.hpmpc_b200_ocp_set_launch.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hpmpc_b200_ocp_sizes.argtypes = [C.c_void_p, C.POINTER(Sizes)]
+        L.hpmpc_b200_ocp_stage_offsets.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 7
+        L.hpmpc_b200_pack_instance.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
+        L.hpmpc_b200_d_back_ric_rec_sv_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 5
+        L.hpmpc_b200_d_back_ric_rec_trf_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
+        L.hpmpc_b200_d_back_ric_rec_trs_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 5
+        L.hpmpc_b200_d_ip2_res_mpc_hard_batch.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                                         C.c_double, C.c_int] + [C.c_void_p] * 6
+        L.hpmpc_b200_d_back_ric_rec_sv_batch_host.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
+        L.hpmpc_b200_d_ip2_res_mpc_hard_batch_host.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                                              C.c_double, C.c_int] + [C.c_void_p] * 5
+        L.hpmpc_b200_fp64_peak_tflops.restype = C.c_double
+        L.hpmpc_b200_fp64_peak_tflops.argtypes = [C.c_int]
+        L.hpmpc_b200_version.restype = C.c_char_p
+        _product = L
+    return _product
+
+
+class BatchOcp:
+    """Handle on a size pattern (hpmpc_b200_ocp_create) plus numpy-side packing helpers."""
+
+    def __init__(self, p: Ocp, device: int = 0):
+        L = product()
+        self.L, self.p, self.device = L, p, device
+        self.h = C.c_void_p()
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        self._keep = idxb
+        rc = L.hpmpc_b200_ocp_create(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb), device)
+        if rc != 0:
+            raise RuntimeError(f"hpmpc_b200_ocp_create failed ({rc})")
+        self.refresh()
+        self.off = []
+        for n in range(p.N + 1):
+            v = [C.c_int() for _ in range(7)]
+            L.hpmpc_b200_ocp_stage_offsets(self.h, n, *[C.byref(x) for x in v])
+            self.off.append(dict(zip(("BAbt", "RSQ", "d", "ux", "pi", "lam", "L"), [x.value for x in v])))
+
+    def refresh(self):
+        self.sz = Sizes()
+        self.L.hpmpc_b200_ocp_sizes(self.h, C.byref(self.sz))
+
+    def set_launch(self, ctas_per_sm: int, warps: int):
+        rc = self.L.hpmpc_b200_ocp_set_launch(self.h, ctas_per_sm, warps)
+        self.refresh()
+        return rc
+
+    def close(self):
+        if self.h:
+            self.L.hpmpc_b200_ocp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def pack(self, p: Ocp) -> np.ndarray:
+        """One instance -> native packed block (hpmpc_b200_pack_instance, row-major inputs)."""
+        blk = np.zeros(self.sz.in_stride)
+        c = np.ascontiguousarray
+        arrs = [[c(M) for M in L] for L in (p.A, p.B, p.b, p.Q, p.S, p.R, p.q, p.r, p.lb, p.ub)]
+        ptrs = [ptr_array(a) for a in arrs]
+        rc = self.L.hpmpc_b200_pack_instance(self.h, 1, *ptrs, blk.ctypes.data)
+        assert rc == 0
+        return blk
+
+    def split_ux(self, ux: np.ndarray):
+        p = self.p
+        u = [ux[self.off[n]["ux"]:self.off[n]["ux"] + p.nu[n]].copy() for n in range(p.N)]
+        x = [ux[self.off[n]["ux"] + p.nu[n]:self.off[n]["ux"] + p.nu[n] + p.nx[n]].copy() for n in range(p.N + 1)]
+        return u, x
+
+    def split_pi(self, pi: np.ndarray):
+        p = self.p
+        return [pi[self.off[n]["pi"]:self.off[n]["pi"] + p.nx[n + 1]].copy() for n in range(p.N)]
+
+    def split_lam(self, lam: np.ndarray):
+        p = self.p
+        return [lam[self.off[n]["lam"]:self.off[n]["lam"] + 2 * p.nb[n]].copy() for n in range(p.N + 1)]

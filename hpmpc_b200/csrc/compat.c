@@ -1,0 +1,404 @@
+/*
+ * compat.c -- HPMPC's own C symbols, exported by libhpmpc_b200.so so that existing callers link unchanged.
+ *
+ * Each function below has the reference's exact signature (cited per function) and runs the problem as a
+ * batch of ONE through the CUDA engine: unpack the caller's arrays into the native packed block, copy in,
+ * launch, copy out.  This path exists for link compatibility and for the parity tests; throughput comes
+ * from the batched entry points of hpmpc_b200.h.  Nothing here computes the solution on the CPU, and a
+ * missing / failing GPU is reported on stderr and turned into an error return (or abort() for the void
+ * reference signatures, mirroring the reference's own printf+exit(1) on bad sizes, c_order_interface.c:103-110).
+ *
+ * Storage conventions accepted (reference include/block_size.h, auxiliary/d_aux_lib4.c:1310):
+ *   low-level symbols : "lib4" panel-major matrices, bs = 4, column padding ncl = 2:
+ *                       element (i,j) of a matrix with sda padded columns is p[(i/4)*4*sda + i%4 + 4*j];
+ *                       bound-like vectors d, lam, t are [lower(pnb) upper(pnb)], pnb = nb rounded up to 4
+ *   high-level symbols: dense row-major (c_order_) or column-major (fortran_order_) stage arrays
+ * Deliberate differences (documented in INTEGRATION.md): the caller's matrices are never modified
+ * (lib4 writes q / b / diagonal updates into them and restores them later, d_ip2_res_hard.c:721-732);
+ * `work` is not used; `memory` holds the factor in the layout of layout.h; ng must be 0; N2 is ignored.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <pthread.h>
+#include <cuda_runtime_api.h>
+#include "layout.h"
+#include "../../include/hpmpc_b200.h"
+#include "../../include/hpmpc_compat.h"
+
+#define BS 4
+#define NCL 2
+#define PM(p, sda, i, j) ((p)[((i)/BS)*BS*(sda) + (i)%BS + BS*(j)])
+#define RUP(x, m) (((x)+(m)-1)/(m)*(m))
+
+/* ---- one cached single-instance context, rebuilt when the size pattern changes ---- */
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static struct
+	{
+	hpmpc_b200_ocp *ocp;
+	int N, *nx, *nu, *nb, **idxb;
+	hpmpc_b200_sizes sz;
+	int k_max_alloc;
+	double *h_in, *h_ux, *h_pi, *h_Pb, *h_lam, *h_t, *h_info;
+	double *d_in, *d_ux, *d_pi, *d_Pb, *d_L, *d_lam, *d_t, *d_info;
+	} G;
+
+static void fatal(const char *what)
+	{
+	fprintf(stderr, "hpmpc_b200: %s -- no CPU fallback exists, aborting\n", what);
+	abort();
+	}
+
+static int same_pattern(int N, const int *nx, const int *nu, const int *nb, int *const *idxb)
+	{
+	int n, j;
+	if(!G.ocp || G.N!=N) return 0;
+	for(n=0; n<=N; n++)
+		{
+		int nun = n<N ? nu[n] : 0, nbn = nb ? nb[n] : 0;
+		if(G.nx[n]!=nx[n] || G.nu[n]!=nun || G.nb[n]!=nbn) return 0;
+		for(j=0; j<nbn; j++) if(G.idxb[n][j]!=idxb[n][j]) return 0;
+		}
+	return 1;
+	}
+
+static void ctx_free(void)
+	{
+	int n;
+	if(!G.ocp) return;
+	hpmpc_b200_ocp_destroy(G.ocp);
+	for(n=0; n<=G.N; n++) free(G.idxb[n]);
+	free(G.idxb); free(G.nx); free(G.nu); free(G.nb);
+	free(G.h_in); free(G.h_ux); free(G.h_pi); free(G.h_Pb); free(G.h_lam); free(G.h_t); free(G.h_info);
+	cudaFree(G.d_in); cudaFree(G.d_ux); cudaFree(G.d_pi); cudaFree(G.d_Pb); cudaFree(G.d_L); cudaFree(G.d_lam); cudaFree(G.d_t); cudaFree(G.d_info);
+	memset(&G, 0, sizeof(G));
+	}
+
+static int ctx_get(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *ng, int k_max)
+	{
+	int n, j, dev = 0;
+	if(ng) for(n=0; n<=N; n++) if(ng[n]>0) { fprintf(stderr, "hpmpc_b200: general constraints (ng>0) are not supported\n"); return -1; }
+	if(!same_pattern(N, nx, nu, nb, idxb))
+		{
+		ctx_free();
+		const char *e = getenv("HPMPC_B200_DEVICE");
+		if(e) dev = atoi(e); else if(cudaGetDevice(&dev)!=cudaSuccess) { fprintf(stderr, "hpmpc_b200: no CUDA device available\n"); return -1; }
+		if(hpmpc_b200_ocp_create(&G.ocp, N, nx, nu, nb, idxb, dev)) { G.ocp = NULL; return -1; }
+		G.N = N;
+		G.nx = malloc((N+1)*sizeof(int)); G.nu = malloc((N+1)*sizeof(int)); G.nb = malloc((N+1)*sizeof(int)); G.idxb = calloc(N+1, sizeof(int*));
+		for(n=0; n<=N; n++)
+			{
+			G.nx[n] = nx[n]; G.nu[n] = n<N ? nu[n] : 0; G.nb[n] = nb ? nb[n] : 0;
+			G.idxb[n] = malloc((G.nb[n]+1)*sizeof(int));
+			for(j=0; j<G.nb[n]; j++) G.idxb[n][j] = idxb[n][j];
+			}
+		hpmpc_b200_ocp_sizes(G.ocp, &G.sz);
+		size_t lam = (size_t)(G.sz.lam_stride>0 ? G.sz.lam_stride : 2);
+		G.h_in = calloc(G.sz.in_stride, sizeof(double)); G.h_ux = calloc(G.sz.ux_stride, sizeof(double));
+		G.h_pi = calloc(G.sz.pi_stride+2, sizeof(double)); G.h_Pb = calloc(G.sz.pi_stride+2, sizeof(double));
+		G.h_lam = calloc(lam, sizeof(double)); G.h_t = calloc(lam, sizeof(double));
+		if(cudaMalloc((void**)&G.d_in, sizeof(double)*G.sz.in_stride)!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_ux, sizeof(double)*G.sz.ux_stride)!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_pi, sizeof(double)*(G.sz.pi_stride+2))!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_Pb, sizeof(double)*(G.sz.pi_stride+2))!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_L, sizeof(double)*G.sz.L_stride)!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_lam, sizeof(double)*lam)!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_t, sizeof(double)*lam)!=cudaSuccess)
+			{ fprintf(stderr, "hpmpc_b200: device allocation failed\n"); return -1; }
+		}
+	if(k_max>G.k_max_alloc)
+		{
+		free(G.h_info); if(G.d_info) cudaFree(G.d_info);
+		G.h_info = calloc(HB_IPM_INFO_HEAD+5*k_max, sizeof(double));
+		if(cudaMalloc((void**)&G.d_info, sizeof(double)*(HB_IPM_INFO_HEAD+5*k_max))!=cudaSuccess) return -1;
+		G.k_max_alloc = k_max;
+		}
+	return 0;
+	}
+
+static int h2d(double *d, const double *h, size_t n) { return cudaMemcpy(d, h, sizeof(double)*n, cudaMemcpyHostToDevice)!=cudaSuccess; }
+static int d2h(double *h, const double *d, size_t n) { return cudaMemcpy(h, d, sizeof(double)*n, cudaMemcpyDeviceToHost)!=cudaSuccess; }
+
+/* panel-major problem data -> native block (G.h_in) */
+static void pack_from_pmat(int N, const int *nx, const int *nu, const int *nb, double **hpBAbt, double **hpRSQrq, double **hd)
+	{
+	int n, i, j;
+	memset(G.h_in, 0, sizeof(double)*G.sz.in_stride);
+	for(n=0; n<=N; n++)
+		{
+		int oB, oH, oD;
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, &oB, &oH, &oD, NULL, NULL, NULL, NULL);
+		int nun = n<N ? nu[n] : 0, nux = nun+nx[n];
+		if(n<N)
+			{
+			int nx1 = nx[n+1], cnx1 = RUP(nx1, NCL);
+			double *M = G.h_in + oB;
+			for(i=0; i<=nux; i++) for(j=0; j<nx1; j++) M[i*nx1+j] = PM(hpBAbt[n], cnx1, i, j);
+			}
+		int cnux = RUP(nux, NCL);
+		double *H = G.h_in + oH;
+		for(i=0; i<nux; i++) for(j=0; j<=i; j++) H[HB_TRI(i)+j] = PM(hpRSQrq[n], cnux, i, j);
+		for(j=0; j<nux; j++) H[HB_TRI(nux)+j] = PM(hpRSQrq[n], cnux, nux, j);
+		if(hd && nb && nb[n]>0)
+			{
+			int pnb = RUP(nb[n], BS);
+			for(j=0; j<nb[n]; j++) { G.h_in[oD+j] = hd[n][j]; G.h_in[oD+nb[n]+j] = hd[n][pnb+j]; }
+			}
+		}
+	}
+
+/* optional vector overrides of the Riccati entry points, folded into the packed block */
+static void fold_updates(int N, const int *nx, const int *nu, const int *nb, int **idxb, int update_b, double **b,
+		int update_q, double **q, double **bd, double **Qx, double **qx)
+	{
+	int n, j;
+	for(n=0; n<=N; n++)
+		{
+		int oB, oH;
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, &oB, &oH, NULL, NULL, NULL, NULL, NULL);
+		int nun = n<N ? nu[n] : 0, nux = nun+nx[n];
+		double *H = G.h_in + oH;
+		if(update_b && n<N) for(j=0; j<nx[n+1]; j++) G.h_in[oB+nux*nx[n+1]+j] = b[n][j];
+		if(update_q) for(j=0; j<nux; j++) H[HB_TRI(nux)+j] = q[n][j];
+		if(nb && nb[n]>0)
+			for(j=0; j<nb[n]; j++)
+				{
+				int id = idxb[n][j];
+				if(Qx) H[HB_TRI(id)+id] = (bd ? bd[n][j] : H[HB_TRI(id)+id]) + Qx[n][j];   /* ddiaadin_libsp: bd + Qx */
+				if(qx) H[HB_TRI(nux)+id] += qx[n][j];                                        /* drowad_libsp */
+				}
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* reference include/lqcp_solvers.h:37-45                                                             */
+/* ------------------------------------------------------------------------------------------------ */
+int d_back_ric_rec_sv_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int *ng)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)ng;
+	return 64;     /* the engine keeps its scratch on the device */
+	}
+
+int d_back_ric_rec_sv_tv_memory_space_size_bytes(int N, int *nx, int *nu, int *nb, int *ng)
+	{
+	(void)nb; (void)ng;
+	long long d = 0; int n;
+	for(n=0; n<=N; n++) { int nux = (n<N ? nu[n] : 0) + nx[n]; d += HB_EVEN(HB_TRI(nux)+2*nux); }
+	return (int)((d*sizeof(double)+63)/64*64);
+	}
+
+void d_back_ric_rec_sv_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, int update_b, double **hpBAbt, double **b,
+		int update_q, double **hpRSQrq, double **q, double **bd, double **hpDCt, double **Qx, double **qx, double **hux,
+		int compute_pi, double **hpi, int compute_Pb, double **hPb, double *memory, double *work)
+	{
+	(void)hpDCt; (void)work;
+	int n, i;
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu, nb, idxb, ng, 0)) fatal("d_back_ric_rec_sv_tv_res: GPU context unavailable");
+	pack_from_pmat(N, nx, nu, nb, hpBAbt, hpRSQrq, NULL);
+	fold_updates(N, nx, nu, nb, idxb, update_b, b, update_q, q, bd, Qx, qx);
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride)) fatal("copy to device failed");
+	/* factor kept per instance (d_L) so that a later trs call can reuse it through `memory` */
+	if(hpmpc_b200_d_back_ric_rec_sv_batch(G.ocp, 1, G.d_in, G.d_ux, G.d_pi, G.d_Pb, NULL)) fatal("sv launch failed");
+	if(cudaDeviceSynchronize()!=cudaSuccess) fatal("sv kernel failed");
+	if(d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_Pb, G.d_Pb, G.sz.pi_stride)) fatal("copy from device failed");
+	if(memory)
+		{
+		/* slot 0 of the engine's stash holds this instance's factor */
+		extern int hpmpc_b200_internal_copy_stash(hpmpc_b200_ocp *p, double *h_dst);
+		if(hpmpc_b200_internal_copy_stash(G.ocp, memory)) fatal("copy of the factor failed");
+		}
+	for(n=0; n<=N; n++)
+		{
+		int oU, oP, nun = n<N ? nu[n] : 0;
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, NULL, NULL);
+		for(i=0; i<nun+nx[n]; i++) hux[n][i] = G.h_ux[oU+i];
+		if(n<N && compute_pi) for(i=0; i<nx[n+1]; i++) hpi[n][i] = G.h_pi[oP+i];
+		if(n<N && compute_Pb) for(i=0; i<nx[n+1]; i++) hPb[n][i] = G.h_Pb[oP+i];
+		}
+	pthread_mutex_unlock(&g_lock);
+	}
+
+void d_back_ric_rec_trf_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hpRSQrq,
+		double **hpDCt, double **Qx, double **bd, double *memory, double *work)
+	{
+	(void)hpDCt; (void)work;
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu, nb, idxb, ng, 0)) fatal("d_back_ric_rec_trf_tv_res: GPU context unavailable");
+	pack_from_pmat(N, nx, nu, nb, hpBAbt, hpRSQrq, NULL);
+	fold_updates(N, nx, nu, nb, idxb, 0, NULL, 0, NULL, bd, Qx, NULL);
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride)) fatal("copy to device failed");
+	if(hpmpc_b200_d_back_ric_rec_trf_batch(G.ocp, 1, G.d_in, G.d_L, NULL)) fatal("trf launch failed");
+	if(cudaDeviceSynchronize()!=cudaSuccess) fatal("trf kernel failed");
+	if(d2h(memory, G.d_L, G.sz.L_stride)) fatal("copy from device failed");
+	pthread_mutex_unlock(&g_lock);
+	}
+
+void d_back_ric_rec_trs_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hb, double **hq,
+		double **hpDCt, double **qx, double **hux, int compute_pi, double **hpi, int compute_Pb, double **hPb, double *memory, double *work)
+	{
+	(void)hpDCt; (void)work; (void)compute_Pb; (void)hPb;
+	int n, i, j;
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu, nb, idxb, ng, 0)) fatal("d_back_ric_rec_trs_tv_res: GPU context unavailable");
+	/* only [B A]', b and the gradient are read by the solve; the Hessian part of the block is unused */
+	memset(G.h_in, 0, sizeof(double)*G.sz.in_stride);
+	for(n=0; n<=N; n++)
+		{
+		int oB, oH, nun = n<N ? nu[n] : 0, nux = nun+nx[n];
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, &oB, &oH, NULL, NULL, NULL, NULL, NULL);
+		if(n<N)
+			{
+			int nx1 = nx[n+1], cnx1 = RUP(nx1, NCL);
+			for(i=0; i<nux; i++) for(j=0; j<nx1; j++) G.h_in[oB+i*nx1+j] = PM(hpBAbt[n], cnx1, i, j);
+			for(j=0; j<nx1; j++) G.h_in[oB+nux*nx1+j] = hb[n][j];
+			}
+		for(j=0; j<nux; j++) G.h_in[oH+HB_TRI(nux)+j] = hq[n][j];
+		if(nb && nb[n]>0 && qx) for(j=0; j<nb[n]; j++) G.h_in[oH+HB_TRI(nux)+idxb[n][j]] += qx[n][j];
+		}
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride) || h2d(G.d_L, memory, G.sz.L_stride)) fatal("copy to device failed");
+	if(hpmpc_b200_d_back_ric_rec_trs_batch(G.ocp, 1, G.d_in, G.d_L, G.d_ux, G.d_pi, NULL)) fatal("trs launch failed");
+	if(cudaDeviceSynchronize()!=cudaSuccess) fatal("trs kernel failed");
+	if(d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride)) fatal("copy from device failed");
+	for(n=0; n<=N; n++)
+		{
+		int oU, oP, nun = n<N ? nu[n] : 0;
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, NULL, NULL);
+		for(i=0; i<nun+nx[n]; i++) hux[n][i] = G.h_ux[oU+i];
+		if(n<N && compute_pi) for(i=0; i<nx[n+1]; i++) hpi[n][i] = G.h_pi[oP+i];
+		}
+	pthread_mutex_unlock(&g_lock);
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* reference include/mpc_solvers.h:41-42                                                              */
+/* ------------------------------------------------------------------------------------------------ */
+int d_ip2_res_mpc_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int *ng)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)ng;
+	return 64;
+	}
+
+static int run_ipm_single(int *kk, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start, double *stat)
+	{
+	int i;
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride)) return -1;
+	if(warm_start && h2d(G.d_ux, G.h_ux, G.sz.ux_stride)) return -1;
+	if(cudaMemset(G.d_info, 0, sizeof(double)*(HB_IPM_INFO_HEAD+5*k_max))!=cudaSuccess) return -1;
+	if(hpmpc_b200_d_ip2_res_mpc_hard_batch(G.ocp, 1, G.d_in, k_max, mu0, mu_tol, alpha_min, warm_start,
+			G.d_ux, G.d_pi, G.d_lam, G.d_t, G.d_info, NULL)) return -1;
+	if(cudaDeviceSynchronize()!=cudaSuccess) return -1;
+	if(d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_info, G.d_info, HB_IPM_INFO_HEAD+5*k_max)) return -1;
+	if(G.sz.lam_stride>0 && (d2h(G.h_lam, G.d_lam, G.sz.lam_stride) || d2h(G.h_t, G.d_t, G.sz.lam_stride))) return -1;
+	*kk = (int)G.h_info[0];
+	if(stat) for(i=0; i<5*(*kk); i++) stat[i] = G.h_info[HB_IPM_INFO_HEAD+i];
+	return 0;
+	}
+
+int d_ip2_res_mpc_hard_tv(int *kk, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start, double *stat, int N,
+		int *nx, int *nu_N, int *nb, int **idxb, int *ng, double **pBAbt, double **pQ, double **pDCt, double **d, double **ux,
+		int compute_mult, double **pi, double **lam, double **t, double *double_work_memory)
+	{
+	(void)pDCt; (void)double_work_memory; (void)compute_mult;
+	int n, i, status;
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu_N, nb, idxb, ng, k_max)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_ip2_res_mpc_hard_tv: GPU context unavailable\n"); return -1; }
+	pack_from_pmat(N, nx, nu_N, nb, pBAbt, pQ, d);
+	if(warm_start)
+		for(n=0; n<=N; n++)
+			{
+			int oU, nun = n<N ? nu_N[n] : 0;
+			hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, NULL, NULL, NULL);
+			for(i=0; i<nun+nx[n]; i++) G.h_ux[oU+i] = ux[n][i];
+			}
+	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_ip2_res_mpc_hard_tv: GPU execution failed\n"); return -1; }
+	status = (int)G.h_info[1];
+	for(n=0; n<=N; n++)
+		{
+		int oU, oP, oLm, nun = n<N ? nu_N[n] : 0, nbn = nb[n], pnb = RUP(nbn, BS);
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, &oLm, NULL);
+		for(i=0; i<nun+nx[n]; i++) ux[n][i] = G.h_ux[oU+i];
+		if(n<N) for(i=0; i<nx[n+1]; i++) pi[n][i] = G.h_pi[oP+i];
+		for(i=0; i<nbn; i++)
+			{
+			lam[n][i] = G.h_lam[oLm+i]; lam[n][pnb+i] = G.h_lam[oLm+nbn+i];
+			t[n][i] = G.h_t[oLm+i]; t[n][pnb+i] = G.h_t[oLm+nbn+i];
+			}
+		}
+	pthread_mutex_unlock(&g_lock);
+	return status;
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* reference include/c_interface.h:59-67                                                              */
+/* ------------------------------------------------------------------------------------------------ */
+int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)hidxb; (void)ng; (void)N2;
+	return 64;     /* callers may keep passing their (larger) buffer; it is not touched */
+	}
+
+static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb,
+		int *ng, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q,
+		double **r, double **lb, double **ub, double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *stat)
+	{
+	int n, i, j, l, status;
+	const double alpha_min = 1e-8;       /* c_order_interface.c:141 */
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu, nb, hidxb, ng, k_max)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU context unavailable\n"); return -1; }
+	hpmpc_b200_pack_instance(G.ocp, c_order, A, B, b, Q, S, R, q, r, lb, ub, G.h_in);
+	/* mu0 estimate when the caller passes mu0 <= 0: signed maximum over the cost entries
+	 * (c_order_interface.c:318-331 / fortran_order_interface.c:318-331) */
+	if(mu0<=0)
+		{
+		for(n=0; n<=N; n++)
+			{
+			int nun = n<N ? nu[n] : 0;
+			if(n<N)
+				{
+				for(j=0; j<nun*nun; j++) mu0 = fmax(mu0, R[n][j]);
+				for(j=0; j<nx[n]*nun; j++) mu0 = fmax(mu0, S[n][j]);
+				for(j=0; j<nun; j++) mu0 = fmax(mu0, r[n][j]);
+				}
+			for(j=0; j<nx[n]; j++) for(l=0; l<nx[n]; l++) mu0 = fmax(mu0, Q[n][j*nx[n]+l]);
+			for(j=0; j<nx[n]; j++) mu0 = fmax(mu0, q[n][j]);
+			}
+		}
+	if(warm_start)
+		for(n=0; n<=N; n++)
+			{
+			int oU, nun = n<N ? nu[n] : 0;
+			hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, NULL, NULL, NULL);
+			for(i=0; i<nun; i++) G.h_ux[oU+i] = u[n][i];
+			for(i=0; i<nx[n]; i++) G.h_ux[oU+nun+i] = x[n][i];
+			}
+	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU execution failed\n"); return -1; }
+	status = (int)G.h_info[1];
+	hpmpc_b200_unpack_solution(G.ocp, G.h_ux, G.h_pi, G.h_lam, x, u, pi, lam);
+	/* inputs fixed by lb == ub are returned exactly on the bound (c_order_interface.c:599-608) */
+	for(n=0; n<N; n++)
+		for(j=0; j<nb[n] && hidxb[n][j]<nu[n]; j++)
+			if(lb[n][j]==ub[n][j]) u[n][hidxb[n][j]] = lb[n][j];
+	for(i=0; i<4; i++) inf_norm_res[i] = G.h_info[2+i];
+	pthread_mutex_unlock(&g_lock);
+	return status;
+	}
+
+int c_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb, int *ng,
+		int N2, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q, double **r,
+		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
+		double **lam, double *inf_norm_res, void *work0, double *stat)
+	{
+	(void)N2; (void)C; (void)D; (void)lg; (void)ug; (void)work0;
+	return high_level(1, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, x, u, pi, lam, inf_norm_res, stat);
+	}
+
+int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb, int *ng,
+		int N2, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q, double **r,
+		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
+		double **lam, double *inf_norm_res, void *work0, double *stat)
+	{
+	(void)N2; (void)C; (void)D; (void)lg; (void)ug; (void)work0;
+	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, x, u, pi, lam, inf_norm_res, stat);
+	}

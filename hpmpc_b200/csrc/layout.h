@@ -1,0 +1,80 @@
+/*
+ * layout.h -- internal POD descriptors shared by the C host shim and the sm_100a kernels.
+ *
+ * Device data layout ("native packed layout", one contiguous block of doubles per OCP instance):
+ *
+ *   for n = 0..N :   [ BAbt_n ]  (nu_n+nx_n+1) x nx_{n+1}, row-major, ld = nx_{n+1}      (n < N only)
+ *                                rows 0..nu-1 = B_n' , rows nu..nux-1 = A_n' , row nux = b_n'
+ *                    [ RSQrq_n ] packed lower triangle by rows of the (nux+1) x nux trapezoid
+ *                                [R S';S Q ; r' q'] : row i holds columns 0..min(i,nux-1),
+ *                                element (i,k) at i*(i+1)/2 + k ; row nux (gradient) has nux entries
+ *                    [ d_n ]     lb (nb) then ub (nb)
+ *   every sub-block starts on a 16-byte boundary (sizes padded to an even number of doubles) so a
+ *   stage can be moved with 16-byte vector loads or a 1-D bulk (TMA) copy.
+ *
+ * This replaces the reference's panel-major (bs=4) hpBAbt / hpRSQrq / hd arrays
+ * (reference auxiliary/d_aux_lib4.c:1310, interfaces/c/fortran_order_interface.c:176-380): only the
+ * unique Hessian entries are stored (SURVEY.md section 8d "algorithmic bytes").
+ *
+ * The Riccati factor L_n uses the same packed-trapezoid layout as RSQrq_n (the triangular row
+ * offsets i*(i+1)/2 are a complete residue system mod 16, so one-row-per-lane accesses in shared memory
+ * are bank-conflict free), followed by the nux inverse diagonal entries.
+ */
+#ifndef HPMPC_B200_LAYOUT_H
+#define HPMPC_B200_LAYOUT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_stage
+	{
+	int nx, nu, nb, nx1;        /* nx1 = nx[n+1], 0 at n = N */
+	int off_BAbt, off_RSQ, off_d;   /* into the instance input block (doubles) */
+	int off_ux;                 /* into ux-like vectors (sum of nux over earlier stages) */
+	int off_pi;                 /* into pi-like vectors, edge n -> length nx1 */
+	int off_c;                  /* constraint offset: sum of nb over earlier stages */
+	int off_L;                  /* into the factor stash: packed L_n then dinv_n */
+	int pad;
+	} hb_stage;
+
+typedef struct hb_dims
+	{
+	int N;
+	int nzM;                    /* max over stages of nu+nx+1 */
+	int nxM;                    /* max over stages of nx      */
+	int nbtot;                  /* sum of nb                  */
+	long long in_stride;        /* doubles per instance: inputs        */
+	long long ux_stride;        /* doubles per instance: ux            */
+	long long pi_stride;        /* doubles per instance: pi / Pb / b   */
+	long long L_stride;         /* doubles per instance: factor stash  */
+	const hb_stage *st;         /* [N+1]  (device pointer in kernel launches) */
+	const int *idxb;            /* [nbtot] bound index within its stage's ux */
+	const int *c_ux;            /* [nbtot] flat index into the instance's ux vector */
+	} hb_dims;
+
+/* packed trapezoid helpers */
+#define HB_TRI(i) (((i)*((i)+1))>>1)
+#define HB_EVEN(x) (((x)+1)&~1)
+
+/* per-instance IPM result record (doubles) : kk, status, inf_norm_res[4], then stat[5*k_max] */
+#define HB_IPM_INFO_HEAD 6
+
+/* launchers implemented in ric_kernels.cu ; all pointers are device pointers, stream is a cudaStream_t */
+int hb_launch_ric_sv(const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi, double *Pb,
+		double *stash, int n_slots, int grid, int warps, void *stream);
+int hb_launch_ric_trf(const hb_dims *dims, long long n_inst, const double *in, double *L, int grid, int warps, void *stream);
+int hb_launch_ric_trs(const hb_dims *dims, long long n_inst, const double *in, const double *L, double *ux, double *pi,
+		double *work, int n_slots, int grid, int warps, void *stream);
+int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
+		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, void *stream);
+long long hb_ipm_work_doubles(const hb_dims *dims);
+int hb_smem_bytes_per_warp(const hb_dims *dims);
+int hb_device_sm_count(int device);
+double hb_fp64_peak_probe(int device, int iters, void *stream);   /* measured DFMA TFLOP/s */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

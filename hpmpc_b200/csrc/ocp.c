@@ -1,0 +1,401 @@
+/*
+ * ocp.c -- host side (plain C) of the batched engine: size pattern -> device layout, packing from the
+ * reference's stage-wise arrays, scratch-slot management, the device- and host-buffer entry points of
+ * include/hpmpc_b200.h.  No solver arithmetic happens here; it all runs in ric_kernels.cu.
+ *
+ * Packing restates what the reference's wrapper does before calling its solver
+ * (interfaces/c/fortran_order_interface.c:262-380 / c_order_interface.c:262-380): B', A', b into one
+ * [B A b]' block, [R S'; S Q] and [r q] into one Hessian block, [lb ub] into one bound vector -- but
+ * into the packed-trapezoid layout of layout.h instead of panel-major.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_runtime_api.h>
+#include "layout.h"
+#include "../../include/hpmpc_b200.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if(e_!=cudaSuccess) { fprintf(stderr, "hpmpc_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while(0)
+
+struct hpmpc_b200_ocp
+	{
+	int device;
+	int N;
+	int *nx, *nu, *nb;       /* [N+1] */
+	int **idxb;              /* [N+1] */
+	hb_stage *st;            /* host copy [N+1] */
+	int *h_idxb, *h_cux;     /* flat [nbtot] */
+	hb_dims dims;            /* st / idxb / c_ux are DEVICE pointers */
+	long long lam_stride;
+	/* launch shape */
+	int sms, grid, warps, n_slots, smem_cta;
+	/* scratch (device), grown on demand */
+	double *scratch; size_t scratch_bytes;
+	int *counter;
+	/* staging for the host-buffer entry points */
+	cudaStream_t s_copy[2];
+	double *stage_in[2], *stage_out[2]; size_t stage_in_bytes, stage_out_bytes;
+	cudaEvent_t ev[2];
+	};
+
+static int ensure_scratch(hpmpc_b200_ocp *p, size_t bytes)
+	{
+	if(bytes<=p->scratch_bytes) return 0;
+	if(p->scratch) CK(cudaFree(p->scratch));
+	p->scratch = NULL; p->scratch_bytes = 0;
+	CK(cudaMalloc((void**)&p->scratch, bytes));
+	p->scratch_bytes = bytes;
+	return 0;
+	}
+
+static void default_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps)
+	{
+	int smem_warp = hb_smem_bytes_per_warp(&p->dims);
+	if(warps<=0)
+		{
+		warps = 4;
+		while(warps>1 && warps*smem_warp>200*1024) warps--;
+		}
+	int smem_cta = warps*smem_warp;
+	if(ctas_per_sm<=0)
+		{
+		ctas_per_sm = (220*1024)/(smem_cta+1024);
+		if(ctas_per_sm<1) ctas_per_sm = 1;
+		int cap = 16/warps; if(cap<1) cap = 1;          /* <= 16 resident warps per SM by default */
+		if(ctas_per_sm>cap) ctas_per_sm = cap;
+		}
+	p->warps = warps;
+	p->grid = p->sms*ctas_per_sm;
+	p->n_slots = p->grid*p->warps;
+	p->smem_cta = smem_cta;
+	}
+
+int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, int device)
+	{
+	int n, j;
+	*out = NULL;
+	if(N<1) { fprintf(stderr, "hpmpc_b200: N must be >= 1\n"); return -2; }
+	hpmpc_b200_ocp *p = (hpmpc_b200_ocp*)calloc(1, sizeof(*p));
+	p->device = device; p->N = N;
+	p->nx = malloc((N+1)*sizeof(int)); p->nu = malloc((N+1)*sizeof(int)); p->nb = malloc((N+1)*sizeof(int));
+	p->idxb = calloc(N+1, sizeof(int*));
+	p->st = calloc(N+1, sizeof(hb_stage));
+	int nbtot = 0, nzM = 1, nxM = 1;
+	for(n=0; n<=N; n++)
+		{
+		p->nx[n] = nx[n]; p->nu[n] = n<N ? nu[n] : 0; p->nb[n] = nb ? nb[n] : 0;
+		if(p->nb[n]>p->nu[n]+p->nx[n])
+			{
+			/* the reference prints this and exit(1)s (c_order_interface.c:103-110); we return an error */
+			fprintf(stderr, "hpmpc_b200: stage %d: nb=%d larger than nu+nx=%d\n", n, p->nb[n], p->nu[n]+p->nx[n]);
+			return -2;
+			}
+		nbtot += p->nb[n];
+		if(p->nu[n]+p->nx[n]+1>nzM) nzM = p->nu[n]+p->nx[n]+1;
+		if(p->nx[n]>nxM) nxM = p->nx[n];
+		}
+	p->h_idxb = malloc((nbtot+1)*sizeof(int)); p->h_cux = malloc((nbtot+1)*sizeof(int));
+	long long o_in = 0, o_ux = 0, o_pi = 0, o_L = 0; int o_c = 0;
+	for(n=0; n<=N; n++)
+		{
+		hb_stage *s = &p->st[n];
+		int nux = p->nu[n]+p->nx[n];
+		s->nx = p->nx[n]; s->nu = p->nu[n]; s->nb = p->nb[n]; s->nx1 = n<N ? p->nx[n+1] : 0;
+		s->off_BAbt = (int)o_in; o_in += HB_EVEN((nux+1)*s->nx1);
+		s->off_RSQ = (int)o_in;  o_in += HB_EVEN(HB_TRI(nux)+nux);
+		s->off_d = (int)o_in;    o_in += HB_EVEN(2*s->nb);
+		s->off_ux = (int)o_ux;   o_ux += nux;
+		s->off_pi = (int)o_pi;   o_pi += s->nx1;
+		s->off_c = o_c;
+		s->off_L = (int)o_L;     o_L += HB_EVEN(HB_TRI(nux)+2*nux);
+		p->idxb[n] = malloc((s->nb+1)*sizeof(int));
+		for(j=0; j<s->nb; j++)
+			{
+			int id = hidxb[n][j];
+			if(id<0 || id>=nux) { fprintf(stderr, "hpmpc_b200: stage %d: idxb[%d]=%d out of range\n", n, j, id); return -2; }
+			p->idxb[n][j] = id;
+			p->h_idxb[o_c+j] = id;
+			p->h_cux[o_c+j] = s->off_ux + id;
+			}
+		o_c += s->nb;
+		}
+	p->dims.N = N; p->dims.nzM = nzM; p->dims.nxM = nxM; p->dims.nbtot = nbtot;
+	p->dims.in_stride = o_in; p->dims.ux_stride = HB_EVEN(o_ux); p->dims.pi_stride = HB_EVEN(o_pi); p->dims.L_stride = o_L;
+	p->lam_stride = 2*(long long)nbtot;
+	if(nzM>64) { fprintf(stderr, "hpmpc_b200: nu+nx+1 = %d > 64 is not supported yet\n", nzM); return -2; }
+
+	CK(cudaSetDevice(device));
+	hb_stage *d_st; int *d_idxb, *d_cux;
+	CK(cudaMalloc((void**)&d_st, (N+1)*sizeof(hb_stage)));
+	CK(cudaMalloc((void**)&d_idxb, (nbtot+1)*sizeof(int)));
+	CK(cudaMalloc((void**)&d_cux, (nbtot+1)*sizeof(int)));
+	CK(cudaMemcpy(d_st, p->st, (N+1)*sizeof(hb_stage), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_idxb, p->h_idxb, (nbtot+1)*sizeof(int), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_cux, p->h_cux, (nbtot+1)*sizeof(int), cudaMemcpyHostToDevice));
+	p->dims.st = d_st; p->dims.idxb = d_idxb; p->dims.c_ux = d_cux;
+	CK(cudaMalloc((void**)&p->counter, 64));
+	p->sms = hb_device_sm_count(device);
+	if(p->sms<=0) { fprintf(stderr, "hpmpc_b200: no CUDA device %d\n", device); return -1; }
+	default_launch(p, 0, 0);
+	*out = p;
+	return 0;
+	}
+
+void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p)
+	{
+	int n, k;
+	if(!p) return;
+	cudaSetDevice(p->device);
+	for(k=0; k<2; k++)
+		{
+		if(p->stage_in[k]) cudaFree(p->stage_in[k]);
+		if(p->stage_out[k]) cudaFree(p->stage_out[k]);
+		if(p->s_copy[k]) cudaStreamDestroy(p->s_copy[k]);
+		if(p->ev[k]) cudaEventDestroy(p->ev[k]);
+		}
+	if(p->scratch) cudaFree(p->scratch);
+	if(p->counter) cudaFree(p->counter);
+	cudaFree((void*)p->dims.st); cudaFree((void*)p->dims.idxb); cudaFree((void*)p->dims.c_ux);
+	for(n=0; n<=p->N; n++) free(p->idxb[n]);
+	free(p->idxb); free(p->nx); free(p->nu); free(p->nb); free(p->st); free(p->h_idxb); free(p->h_cux);
+	free(p);
+	}
+
+int hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_cta)
+	{
+	default_launch(p, ctas_per_sm, warps_per_cta);
+	if(p->smem_cta>227*1024) { fprintf(stderr, "hpmpc_b200: %d warps need %d bytes of shared memory\n", p->warps, p->smem_cta); default_launch(p, 0, 0); return -2; }
+	return 0;
+	}
+
+void hpmpc_b200_ocp_sizes(const hpmpc_b200_ocp *p, hpmpc_b200_sizes *o)
+	{
+	o->in_stride = p->dims.in_stride; o->ux_stride = p->dims.ux_stride; o->pi_stride = p->dims.pi_stride;
+	o->lam_stride = p->lam_stride; o->L_stride = p->dims.L_stride; o->ipm_work_stride = hb_ipm_work_doubles(&p->dims);
+	o->N = p->N; o->nzM = p->dims.nzM; o->nxM = p->dims.nxM; o->nbtot = p->dims.nbtot;
+	o->grid = p->grid; o->warps_per_cta = p->warps; o->n_slots = p->n_slots; o->smem_per_cta = p->smem_cta;
+	}
+
+void hpmpc_b200_ocp_stage_offsets(const hpmpc_b200_ocp *p, int n, int *off_BAbt, int *off_RSQ, int *off_d,
+		int *off_ux, int *off_pi, int *off_lam, int *off_L)
+	{
+	const hb_stage *s = &p->st[n];
+	if(off_BAbt) *off_BAbt = s->off_BAbt;
+	if(off_RSQ) *off_RSQ = s->off_RSQ;
+	if(off_d) *off_d = s->off_d;
+	if(off_ux) *off_ux = s->off_ux;
+	if(off_pi) *off_pi = s->off_pi;
+	if(off_lam) *off_lam = 2*s->off_c;
+	if(off_L) *off_L = s->off_L;
+	}
+
+/* element (i,j) of an m x n matrix with leading dimension ld given in column- or row-major order */
+#define EL(M, i, j, rows, cols, c_order) ((c_order) ? (M)[(size_t)(i)*(cols)+(j)] : (M)[(i)+(size_t)(j)*(rows)])
+
+int hpmpc_b200_pack_instance(const hpmpc_b200_ocp *p, int c_order, double *const *A, double *const *B, double *const *b,
+		double *const *Q, double *const *S, double *const *R, double *const *q, double *const *r,
+		double *const *lb, double *const *ub, double *blk)
+	{
+	int n, i, j;
+	memset(blk, 0, sizeof(double)*p->dims.in_stride);
+	for(n=0; n<=p->N; n++)
+		{
+		const hb_stage *s = &p->st[n];
+		int nx = s->nx, nu = s->nu, nux = nx+nu, nx1 = s->nx1;
+		if(n<p->N)
+			{
+			double *M = blk + s->off_BAbt;                     /* (nux+1) x nx1 row-major */
+			for(i=0; i<nu; i++) for(j=0; j<nx1; j++) M[i*nx1+j] = EL(B[n], j, i, nx1, nu, c_order);
+			for(i=0; i<nx; i++) for(j=0; j<nx1; j++) M[(nu+i)*nx1+j] = EL(A[n], j, i, nx1, nx, c_order);
+			for(j=0; j<nx1; j++) M[nux*nx1+j] = b[n][j];
+			}
+		double *H = blk + s->off_RSQ;                          /* packed lower trapezoid */
+		for(i=0; i<nu; i++) for(j=0; j<=i; j++) H[HB_TRI(i)+j] = EL(R[n], i, j, nu, nu, c_order);
+		for(i=0; i<nx; i++)
+			{
+			for(j=0; j<nu; j++) H[HB_TRI(nu+i)+j] = EL(S[n], j, i, nu, nx, c_order);      /* S is nu x nx */
+			for(j=0; j<=i; j++) H[HB_TRI(nu+i)+nu+j] = EL(Q[n], i, j, nx, nx, c_order);
+			}
+		for(j=0; j<nu; j++) H[HB_TRI(nux)+j] = r[n][j];
+		for(j=0; j<nx; j++) H[HB_TRI(nux)+nu+j] = q[n][j];
+		double *d = blk + s->off_d;
+		for(j=0; j<s->nb; j++) { d[j] = lb[n][j]; d[s->nb+j] = ub[n][j]; }
+		}
+	return 0;
+	}
+
+void hpmpc_b200_unpack_solution(const hpmpc_b200_ocp *p, const double *ux, const double *pi, const double *lam,
+		double **x, double **u, double **pi_out, double **lam_out)
+	{
+	int n, i;
+	for(n=0; n<=p->N; n++)
+		{
+		const hb_stage *s = &p->st[n];
+		if(u && n<p->N) for(i=0; i<s->nu; i++) u[n][i] = ux[s->off_ux+i];
+		if(x) for(i=0; i<s->nx; i++) x[n][i] = ux[s->off_ux+s->nu+i];
+		if(pi_out && pi && n<p->N) for(i=0; i<s->nx1; i++) pi_out[n][i] = pi[s->off_pi+i];
+		if(lam_out && lam) for(i=0; i<2*s->nb; i++) lam_out[n][i] = lam[2*s->off_c+i];
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* device-pointer entry points                                                                       */
+/* ------------------------------------------------------------------------------------------------ */
+static int grid_for(const hpmpc_b200_ocp *p, long long n_inst)
+	{
+	long long need = (n_inst + p->warps - 1)/p->warps;
+	return (int)(need<p->grid ? (need<1 ? 1 : need) : p->grid);
+	}
+
+int hpmpc_b200_d_back_ric_rec_sv_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in,
+		double *d_ux, double *d_pi, double *d_Pb, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	CK(cudaSetDevice(p->device));
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*p->dims.L_stride)) return -1;
+	return hb_launch_ric_sv(&p->dims, n_inst, d_in, d_ux, d_pi, d_Pb, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
+	}
+
+int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_L, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	CK(cudaSetDevice(p->device));
+	return hb_launch_ric_trf(&p->dims, n_inst, d_in, d_L, grid_for(p, n_inst), p->warps, stream);
+	}
+
+int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_L,
+		double *d_ux, double *d_pi, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	CK(cudaSetDevice(p->device));
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*(p->dims.ux_stride+2*p->dims.pi_stride))) return -1;
+	return hb_launch_ric_trs(&p->dims, n_inst, d_in, d_L, d_ux, d_pi, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
+	}
+
+int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t,
+		double *d_info, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	CK(cudaSetDevice(p->device));
+	long long ws = hb_ipm_work_doubles(&p->dims);
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*ws)) return -1;
+	return hb_launch_ipm(&p->dims, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
+			p->scratch, ws, p->n_slots, grid_for(p, n_inst), p->warps, p->counter, stream);
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* host-buffer entry points: two staging buffers, copy-in / solve / copy-out of chunk k overlaps k+1  */
+/* ------------------------------------------------------------------------------------------------ */
+static int ensure_staging(hpmpc_b200_ocp *p, size_t in_bytes, size_t out_bytes)
+	{
+	int k;
+	for(k=0; k<2; k++)
+		{
+		if(!p->s_copy[k]) CK(cudaStreamCreateWithFlags(&p->s_copy[k], cudaStreamNonBlocking));
+		if(!p->ev[k]) CK(cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming));
+		}
+	if(in_bytes>p->stage_in_bytes)
+		{
+		for(k=0; k<2; k++) { if(p->stage_in[k]) CK(cudaFree(p->stage_in[k])); p->stage_in[k] = NULL; CK(cudaMalloc((void**)&p->stage_in[k], in_bytes)); }
+		p->stage_in_bytes = in_bytes;
+		}
+	if(out_bytes>p->stage_out_bytes)
+		{
+		for(k=0; k<2; k++) { if(p->stage_out[k]) CK(cudaFree(p->stage_out[k])); p->stage_out[k] = NULL; CK(cudaMalloc((void**)&p->stage_out[k], out_bytes)); }
+		p->stage_out_bytes = out_bytes;
+		}
+	return 0;
+	}
+
+static long long chunk_size(const hpmpc_b200_ocp *p, long long n_inst)
+	{
+	/* a chunk should fill the persistent grid a few times over, and stay below ~512 MiB of input */
+	long long c = 8LL*p->n_slots;
+	long long cap = (512LL<<20)/(long long)(sizeof(double)*p->dims.in_stride);
+	if(cap<1) cap = 1;
+	if(c>cap) c = cap;
+	if(c>n_inst) c = n_inst;
+	return c;
+	}
+
+int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in, double *h_ux, double *h_pi)
+	{
+	if(n_inst<=0) return 0;
+	CK(cudaSetDevice(p->device));
+	const long long cs = chunk_size(p, n_inst);
+	const size_t in_b = sizeof(double)*(size_t)cs*p->dims.in_stride;
+	const size_t ux_b = sizeof(double)*(size_t)cs*p->dims.ux_stride, pi_b = sizeof(double)*(size_t)cs*p->dims.pi_stride;
+	if(ensure_staging(p, in_b, ux_b+pi_b)) return -1;
+	/* each stream owns its own slice of the scratch slots: both chunks can be in flight */
+	if(ensure_scratch(p, sizeof(double)*(size_t)2*p->n_slots*p->dims.L_stride)) return -1;
+	long long done; int k = 0;
+	for(done=0; done<n_inst; done+=cs, k^=1)
+		{
+		long long m = n_inst-done<cs ? n_inst-done : cs;
+		cudaStream_t st = p->s_copy[k];
+		double *d_in = p->stage_in[k], *d_ux = p->stage_out[k], *d_pi = d_ux + (size_t)cs*p->dims.ux_stride;
+		CK(cudaMemcpyAsync(d_in, h_in + (size_t)done*p->dims.in_stride, sizeof(double)*(size_t)m*p->dims.in_stride, cudaMemcpyHostToDevice, st));
+		if(hb_launch_ric_sv(&p->dims, m, d_in, d_ux, d_pi, NULL, p->scratch + (size_t)k*p->n_slots*p->dims.L_stride,
+				p->n_slots, grid_for(p, m), p->warps, st)) return -1;
+		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));
+		}
+	CK(cudaStreamSynchronize(p->s_copy[0]));
+	CK(cudaStreamSynchronize(p->s_copy[1]));
+	return 0;
+	}
+
+int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *h_ux, double *h_pi, double *h_lam, double *h_t, double *h_info)
+	{
+	if(n_inst<=0) return 0;
+	CK(cudaSetDevice(p->device));
+	const long long cs = chunk_size(p, n_inst);
+	const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max, lam_len = p->lam_stride>0 ? p->lam_stride : 2;
+	const size_t in_b = sizeof(double)*(size_t)cs*p->dims.in_stride;
+	const size_t out_d = (size_t)cs*(p->dims.ux_stride + p->dims.pi_stride + 2*lam_len + info_len);
+	if(ensure_staging(p, in_b, sizeof(double)*out_d)) return -1;
+	const long long ws = hb_ipm_work_doubles(&p->dims);
+	if(ensure_scratch(p, sizeof(double)*(size_t)2*p->n_slots*ws)) return -1;
+	long long done; int k = 0;
+	for(done=0; done<n_inst; done+=cs, k^=1)
+		{
+		long long m = n_inst-done<cs ? n_inst-done : cs;
+		cudaStream_t st = p->s_copy[k];
+		double *d_in = p->stage_in[k];
+		double *d_ux = p->stage_out[k], *d_pi = d_ux + (size_t)cs*p->dims.ux_stride, *d_lam = d_pi + (size_t)cs*p->dims.pi_stride;
+		double *d_t = d_lam + (size_t)cs*lam_len, *d_info = d_t + (size_t)cs*lam_len;
+		CK(cudaMemcpyAsync(d_in, h_in + (size_t)done*p->dims.in_stride, sizeof(double)*(size_t)m*p->dims.in_stride, cudaMemcpyHostToDevice, st));
+		if(warm_start) CK(cudaMemcpyAsync(d_ux, h_ux + (size_t)done*p->dims.ux_stride, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(d_info, 0, sizeof(double)*(size_t)m*info_len, st));
+		if(hb_launch_ipm(&p->dims, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
+				p->scratch + (size_t)k*p->n_slots*ws, ws, p->n_slots, grid_for(p, m), p->warps, p->counter + 8*k, st)) return -1;
+		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));
+		if(p->lam_stride>0)
+			{
+			CK(cudaMemcpyAsync(h_lam + (size_t)done*p->lam_stride, d_lam, sizeof(double)*(size_t)m*p->lam_stride, cudaMemcpyDeviceToHost, st));
+			if(h_t) CK(cudaMemcpyAsync(h_t + (size_t)done*p->lam_stride, d_t, sizeof(double)*(size_t)m*p->lam_stride, cudaMemcpyDeviceToHost, st));
+			}
+		CK(cudaMemcpyAsync(h_info + (size_t)done*info_len, d_info, sizeof(double)*(size_t)m*info_len, cudaMemcpyDeviceToHost, st));
+		}
+	CK(cudaStreamSynchronize(p->s_copy[0]));
+	CK(cudaStreamSynchronize(p->s_copy[1]));
+	return 0;
+	}
+
+double hpmpc_b200_fp64_peak_tflops(int device)
+	{
+	if(cudaSetDevice(device)!=cudaSuccess) return -1.0;
+	return hb_fp64_peak_probe(device, 1<<16, NULL);
+	}
+
+const char *hpmpc_b200_version(void) { return "hpmpc_b200 0.1 (sm_100a)"; }
+
+/* used by compat.c only: the factor of a batch-of-one sv call sits in scratch slot 0 */
+int hpmpc_b200_internal_copy_stash(hpmpc_b200_ocp *p, double *h_dst)
+	{
+	CK(cudaMemcpy(h_dst, p->scratch, sizeof(double)*(size_t)p->dims.L_stride, cudaMemcpyDeviceToHost));
+	return 0;
+	}

@@ -1,0 +1,85 @@
+/*
+ * hpmpc_b200.h -- batched C ABI of the B200-native Riccati / box-IPM engine.
+ *
+ * The reference (HPMPC) solves ONE optimal-control problem per call on one CPU thread:
+ *     d_back_ric_rec_{sv,trf,trs}_tv_res      reference include/lqcp_solvers.h:37-45
+ *     d_ip2_res_mpc_hard_tv                   reference include/mpc_solvers.h:41-42
+ *     {c,fortran}_order_d_ip_ocp_hard_tv      reference include/c_interface.h:59-67
+ * Those symbols are exported unchanged by this library (see hpmpc_compat.h) as a batch of one.
+ * The entry points below are the same operations with a leading instance dimension: n_inst independent
+ * problems that share one size pattern (N, nx[], nu[], nb[], idxb[][]) and differ in their numbers.
+ *
+ * All pointers are plain C; "d_" arguments are device pointers on the handle's device, "h_" arguments are
+ * host pointers (pinned memory makes the copies asynchronous).  `stream` is a cudaStream_t passed as void*
+ * (NULL = default stream).  Every function returns 0 on success, a negative value on error
+ * (and prints the reason to stderr); nothing falls back to the CPU.
+ *
+ * Native packed instance layout: see hpmpc_b200/csrc/layout.h; offsets are queried with
+ * hpmpc_b200_ocp_stage_offsets().  Outputs per instance:
+ *     ux  [ux_stride]   u_n then x_n for n = 0..N        (reference hux[n], d_back_ric_rec.c:341)
+ *     pi  [pi_stride]   multiplier of x_{n+1} = ..., n = 0..N-1   (reference hpi[n], edge-indexed)
+ *     lam [lam_stride]  per stage [lower(nb) upper(nb)]  (reference lam ordering, c_order_interface.c:662-671)
+ *     t   [lam_stride]  slacks, same ordering
+ *     info[6+5*k_max]   kk, status(0 converged /1 k_max /2 alpha_min /-1), ||rq||inf, ||rb||inf, ||rd||inf, mu,
+ *                       then the reference's stat table (sigma, alpha_aff, mu_aff, alpha, mu) per iteration
+ */
+#ifndef HPMPC_B200_H
+#define HPMPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hpmpc_b200_ocp hpmpc_b200_ocp;
+
+typedef struct hpmpc_b200_sizes
+	{
+	long long in_stride, ux_stride, pi_stride, lam_stride, L_stride, ipm_work_stride;
+	int N, nzM, nxM, nbtot;
+	int grid, warps_per_cta, n_slots, smem_per_cta;
+	} hpmpc_b200_sizes;
+
+/* nu has N entries (nu[N] is taken as 0, like the reference high-level API, c_order_interface.c:78-81);
+ * nb / hidxb may be NULL for an unconstrained problem; hidxb[n][j] indexes [u_n ; x_n] */
+int  hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb,
+                           int *const *hidxb, int device);
+void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p);
+/* ctas_per_sm <= 0 or warps_per_cta <= 0 selects the default for the problem size */
+int  hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_cta);
+void hpmpc_b200_ocp_sizes(const hpmpc_b200_ocp *p, hpmpc_b200_sizes *out);
+void hpmpc_b200_ocp_stage_offsets(const hpmpc_b200_ocp *p, int n, int *off_BAbt, int *off_RSQ, int *off_d,
+                                  int *off_ux, int *off_pi, int *off_lam, int *off_L);
+
+/* host-side packing of one instance from the reference's stage-wise arrays (c_order = 0: column-major as
+ * fortran_order_d_ip_ocp_hard_tv takes them; 1: row-major as c_order_d_ip_ocp_hard_tv).  lb/ub may be NULL. */
+int  hpmpc_b200_pack_instance(const hpmpc_b200_ocp *p, int c_order, double *const *A, double *const *B, double *const *b,
+                              double *const *Q, double *const *S, double *const *R, double *const *q, double *const *r,
+                              double *const *lb, double *const *ub, double *block);
+void hpmpc_b200_unpack_solution(const hpmpc_b200_ocp *p, const double *ux, const double *pi, const double *lam,
+                                double **x, double **u, double **pi_out, double **lam_out);
+
+/* ---- data resident in HBM ---- */
+int hpmpc_b200_d_back_ric_rec_sv_batch (hpmpc_b200_ocp *p, long long n_inst, const double *d_in,
+                                        double *d_ux, double *d_pi, double *d_Pb /* may be NULL */, void *stream);
+int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_L, void *stream);
+int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_L,
+                                        double *d_ux, double *d_pi, void *stream);
+int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
+                                        double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi,
+                                        double *d_lam, double *d_t, double *d_info, void *stream);
+
+/* ---- data in host memory: copies in, solves, copies out (chunked so copies overlap the kernels) ---- */
+int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in,
+                                            double *h_ux, double *h_pi);
+int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in, int k_max, double mu0,
+                                             double mu_tol, double alpha_min, int warm_start, double *h_ux, double *h_pi,
+                                             double *h_lam, double *h_t, double *h_info);
+
+/* measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator) */
+double hpmpc_b200_fp64_peak_tflops(int device);
+const char *hpmpc_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

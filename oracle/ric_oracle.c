@@ -1,0 +1,835 @@
+/*
+ * oracle/ric_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C, single-threaded, dense column-major restatement of the HPMPC hot path:
+ * backward Riccati recursion (factor / solve / factor+solve) and the two-phase Mehrotra
+ * predictor-corrector IPM for box-constrained OCPs.  Nothing under hpmpc_b200/ may include,
+ * link or call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg do,
+ * and only as the checker.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function here against
+ * the real reference (oracle/_ref/libhpmpc_ref_c99.so, built from /root/reference by oracle/Makefile)
+ * on seeded mass-spring problems, and tests/golden/ holds vectors produced by that reference build
+ * (tests/golden/make_golden.py).
+ *
+ * Reference lines followed (paths relative to /root/reference):
+ *   chol_mn            kernel/c99/kernel_dpotrf_c99_lib4.c:553-640 (pivot rule >1e-15, inverse diagonal
+ *                      multiplied), blas/blas_d_lib4.c:3622 (dsyrk_dpotrf_lib: m x n trapezoid)
+ *   orc_ric_backward   lqcp_solvers/d_back_ric_rec.c:184-333 (sv), :470-556 (trf);
+ *                      readable twin lqcp_solvers/d_back_ric_rec_libstr.c:89-181
+ *   orc_ric_forward    lqcp_solvers/d_back_ric_rec.c:341-397 ; _libstr.c:187-221
+ *   orc_ric_trs        lqcp_solvers/d_back_ric_rec.c:564-791 ; _libstr.c:309-424
+ *   IPM element-wise   mpc_solvers/c99/d_aux_ip_hard_lib4.c:43 (init), :217 (update_hessian), :387
+ *                      (update_gradient), :489 (compute_alpha), :618 (update_var), :715 (compute_mu),
+ *                      :954 (update_hessian_gradient_res), :1180 (compute_alpha_res), :1382
+ *                      (backup_update_var_res), :1453 (compute_mu_res), :1512 (centering), :1550
+ *   residuals          mpc_solvers/c99/d_res_ip_res_hard.c:39 ; exit residuals mpc_solvers/d_res_ip_hard.c:38
+ *   IPM driver         mpc_solvers/d_ip2_res_hard.c:116-1345
+ *   high-level wrapper interfaces/c/fortran_order_interface.c:53-688 (packing, mu0 estimate, u=lb if lb==ub,
+ *                      inf_norm_res, lam ordering [lb ub])
+ *
+ * Scope: ng == 0 (no general constraints), N2 >= N (no partial condensing) -- SURVEY.md section 8 rows f1, f3.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+/* ------------------------------------------------------------------------------------------- */
+/* problem container: everything dense, column-major                                            */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+	int N;
+	int *nx, *nu, *nb;      /* [N+1], nu[N] = 0 */
+	int **idxb;             /* [N+1][nb]        */
+	double **BAbt;          /* [N]   (nux+1) x nx1, ld = nux+1 ; rows: B' , A' , b'   */
+	double **RSQrq;         /* [N+1] (nux+1) x nux, ld = nux+1 ; [R S';S Q] lower + last row [r' q'] */
+	double **d;             /* [N+1] [lb(nb) ; ub(nb)] */
+	/* factorization memory */
+	double **L;             /* [N+1] (nux+1) x nux, ld = nux+1 */
+	double **dinv;          /* [N+1] nux : inverse diagonal of L */
+	int nzM, nxM;
+	double *W;              /* scratch (nzM x nxM) */
+	double *tmp;            /* scratch 2*nzM */
+} orc_prob;
+
+static int nux_(const orc_prob *P, int n) { return P->nu[n] + P->nx[n]; }
+
+orc_prob *orc_prob_create(int N, const int *nx, const int *nu, const int *nb, int *const *idxb)
+	{
+	orc_prob *P = calloc(1, sizeof(orc_prob));
+	int n, j;
+	P->N = N;
+	P->nx = malloc((N+1)*sizeof(int)); P->nu = malloc((N+1)*sizeof(int)); P->nb = malloc((N+1)*sizeof(int));
+	for(n=0; n<=N; n++) { P->nx[n] = nx[n]; P->nu[n] = n<N ? nu[n] : 0; P->nb[n] = nb ? nb[n] : 0; }
+	P->idxb = calloc(N+1, sizeof(int*));
+	for(n=0; n<=N; n++)
+		{
+		P->idxb[n] = malloc((P->nb[n]+1)*sizeof(int));
+		for(j=0; j<P->nb[n]; j++) P->idxb[n][j] = idxb[n][j];
+		}
+	P->BAbt = calloc(N+1, sizeof(double*)); P->RSQrq = calloc(N+1, sizeof(double*)); P->d = calloc(N+1, sizeof(double*));
+	P->L = calloc(N+1, sizeof(double*)); P->dinv = calloc(N+1, sizeof(double*));
+	P->nzM = 1; P->nxM = 1;
+	for(n=0; n<=N; n++)
+		{
+		int nux = nux_(P, n), nz = nux+1;
+		if(nz>P->nzM) P->nzM = nz;
+		if(P->nx[n]>P->nxM) P->nxM = P->nx[n];
+		if(n<N) P->BAbt[n] = calloc((size_t)nz*(P->nx[n+1]+1), sizeof(double));
+		P->RSQrq[n] = calloc((size_t)nz*(nux+1), sizeof(double));
+		P->L[n] = calloc((size_t)nz*(nux+1), sizeof(double));
+		P->dinv[n] = calloc(nux+1, sizeof(double));
+		P->d[n] = calloc(2*P->nb[n]+1, sizeof(double));
+		}
+	P->W = calloc((size_t)P->nzM*P->nxM, sizeof(double));
+	P->tmp = calloc(4*P->nzM, sizeof(double));
+	return P;
+	}
+
+void orc_prob_free(orc_prob *P)
+	{
+	int n;
+	for(n=0; n<=P->N; n++)
+		{ free(P->idxb[n]); free(P->BAbt[n]); free(P->RSQrq[n]); free(P->L[n]); free(P->dinv[n]); free(P->d[n]); }
+	free(P->idxb); free(P->BAbt); free(P->RSQrq); free(P->L); free(P->dinv); free(P->d);
+	free(P->nx); free(P->nu); free(P->nb); free(P->W); free(P->tmp); free(P);
+	}
+
+/* fill from the stage-wise column-major ("fortran order") arrays of the high-level API:
+ * A[n] nx1 x nx, B[n] nx1 x nu, S[n] nu x nx  (interfaces/c/fortran_order_interface.c:262-311) */
+void orc_prob_set(orc_prob *P, double *const *A, double *const *B, double *const *b,
+		double *const *Q, double *const *S, double *const *R, double *const *q, double *const *r,
+		double *const *lb, double *const *ub)
+	{
+	int n, i, j;
+	for(n=0; n<=P->N; n++)
+		{
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1;
+		if(n<P->N)
+			{
+			int nx1 = P->nx[n+1];
+			double *M = P->BAbt[n];
+			for(j=0; j<nx1; j++)
+				{
+				for(i=0; i<nu; i++) M[i+nz*j] = B[n][j+nx1*i];
+				for(i=0; i<nx; i++) M[nu+i+nz*j] = A[n][j+nx1*i];
+				M[nux+nz*j] = b[n][j];
+				}
+			}
+		double *H = P->RSQrq[n];
+		memset(H, 0, sizeof(double)*nz*(nux+1));
+		for(j=0; j<nu; j++) for(i=0; i<nu; i++) H[i+nz*j] = R[n][i+nu*j];
+		for(j=0; j<nu; j++) for(i=0; i<nx; i++) H[nu+i+nz*j] = S[n][j+nu*i];       /* S' below R */
+		for(j=0; j<nx; j++) for(i=0; i<nx; i++) H[nu+i+nz*(nu+j)] = Q[n][i+nx*j];
+		for(j=0; j<nu; j++) H[nux+nz*j] = r[n][j];
+		for(j=0; j<nx; j++) H[nux+nz*(nu+j)] = q[n][j];
+		for(j=0; j<P->nb[n]; j++) { P->d[n][j] = lb[n][j]; P->d[n][P->nb[n]+j] = ub[n][j]; }
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------- */
+/* m x n "trapezoidal" Cholesky: top n x n factorized, remaining rows solved against it         */
+/* ------------------------------------------------------------------------------------------- */
+static void chol_mn(int m, int n, double *A, int lda, double *dinv)
+	{
+	int i, j, k;
+	for(j=0; j<n; j++)
+		{
+		double c = A[j+lda*j];
+		for(k=0; k<j; k++) c -= A[j+lda*k]*A[j+lda*k];
+		double inv;
+		if(c>1e-15) { c = sqrt(c); inv = 1.0/c; }
+		else { c = 0.0; inv = 0.0; }
+		A[j+lda*j] = c;
+		dinv[j] = inv;
+		for(i=j+1; i<m; i++)
+			{
+			double v = A[i+lda*j];
+			for(k=0; k<j; k++) v -= A[i+lda*k]*A[j+lda*k];
+			A[i+lda*j] = v*inv;
+			}
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------- */
+/* backward recursion.  with_grad = 1: sv (gradient row carried) ; 0: trf                       */
+/*   bvec  : if non-NULL, b_n replaces the last row of BAbt_n      (update_b)                    */
+/*   rqvec : if non-NULL, rq_n replaces the last row of RSQrq_n    (update_q)                    */
+/*   Qx,qx : if non-NULL, diag[idxb] += Qx , lastrow[idxb] += qx   (IPM box terms)               */
+/*   Pb    : if non-NULL, Pb[n] = P_{n+1} b_n  (edge-indexed like lib4)                          */
+/* ------------------------------------------------------------------------------------------- */
+void orc_ric_backward(orc_prob *P, int with_grad, double *const *bvec, double *const *rqvec,
+		double *const *Qx, double *const *qx, double **Pb)
+	{
+	int N = P->N, n, i, j, k;
+	for(n=N; n>=0; n--)
+		{
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1;
+		int m = with_grad ? nz : nux;
+		double *L = P->L[n], *H = P->RSQrq[n];
+		/* L <- lower part of H (+ box terms) */
+		for(j=0; j<nux; j++) for(i=j; i<m; i++) L[i+nz*j] = H[i+nz*j];
+		if(with_grad && rqvec) for(j=0; j<nux; j++) L[nux+nz*j] = rqvec[n][j];
+		if(P->nb[n]>0 && Qx)
+			for(j=0; j<P->nb[n]; j++)
+				{
+				int id = P->idxb[n][j];
+				L[id+nz*id] += Qx[n][j];
+				if(with_grad && qx) L[nux+nz*id] += qx[n][j];
+				}
+		if(n<N)
+			{
+			int nx1 = P->nx[n+1], nu1 = P->nu[n+1], nz1 = nx1+nu1+1;
+			double *Ln = P->L[n+1], *M = P->BAbt[n], *W = P->W;
+			/* W = BAbt * Lxx_{n+1}   (m x nx1) */
+			for(i=0; i<m; i++)
+				for(j=0; j<nx1; j++)
+					{
+					double s = 0.0;
+					for(k=j; k<nx1; k++)
+						{
+						double a = (i==nux && bvec) ? bvec[n][k] : M[i+nz*k];
+						s += a*Ln[nu1+k+nz1*(nu1+j)];
+						}
+					W[i+nz*j] = s;
+					}
+			if(with_grad)
+				{
+				if(Pb) /* Pb = Lxx * (last row of W)' */
+					for(i=0; i<nx1; i++)
+						{
+						double s = 0.0;
+						for(k=0; k<=i; k++) s += Ln[nu1+i+nz1*(nu1+k)]*W[nux+nz*k];
+						Pb[n][i] = s;
+						}
+				for(j=0; j<nx1; j++) W[nux+nz*j] += Ln[nu1+nx1+nz1*(nu1+j)];   /* + l_x */
+				}
+			/* L += W W' (lower, m rows) */
+			for(j=0; j<nux; j++)
+				for(i=j; i<m; i++)
+					{
+					double s = 0.0;
+					for(k=0; k<nx1; k++) s += W[i+nz*k]*W[j+nz*k];
+					L[i+nz*j] += s;
+					}
+			}
+		chol_mn(m, nux, L, nz, P->dinv[n]);
+		}
+	}
+
+/* x-part helpers on stage n: Lxx_n is L[nu:nu+nx, nu:nu+nx], l_x is L[nux, nu:] */
+static void pi_from_x(const orc_prob *P, int n, const double *x, const double *p, double *pi, double *tmp)
+	{
+	/* pi = p + Lxx (Lxx' x) */
+	int nx = P->nx[n], nu = P->nu[n], nz = nx+nu+1, i, k;
+	const double *L = P->L[n];
+	for(i=0; i<nx; i++)
+		{
+		double s = 0.0;
+		for(k=i; k<nx; k++) s += L[nu+k+nz*(nu+i)]*x[k];
+		tmp[i] = s;
+		}
+	for(i=0; i<nx; i++)
+		{
+		double s = p ? p[i] : 0.0;
+		for(k=0; k<=i; k++) s += L[nu+i+nz*(nu+k)]*tmp[k];
+		pi[i] = s;
+		}
+	}
+
+/* forward substitution shared by sv and trs.
+ *   lrow[n] : the "gradient" for stage n (sv: last row of L_n ; trs: eliminated rhs w_n), length nux
+ *   bsrc    : b_n (length nx1) for the state recursion
+ *   p[n]    : x-part of the eliminated rhs of stage n+1 (NULL in sv, where l_x of L_{n+1} is used)   */
+static void ric_forward(orc_prob *P, double *const *lrow, double *const *bsrc, double *const *p,
+		double **ux, int compute_pi, double **pi)
+	{
+	int N = P->N, n, i, j;
+	for(n=0; n<N; n++)
+		{
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1, nx1 = P->nx[n+1], nu1 = P->nu[n+1];
+		int ks = (n==0) ? nux : nu;           /* stage 0 solves for all of ux_0 */
+		const double *L = P->L[n], *dinv = P->dinv[n];
+		double *v = ux[n];
+		for(i=0; i<ks; i++) v[i] = -lrow[n][i];
+		/* v[:ks] = L[:ks,:ks]^{-T} ( v[:ks] - L[ks:nux,:ks]' v[ks:nux] ) */
+		for(i=ks-1; i>=0; i--)
+			{
+			double s = v[i];
+			for(j=i+1; j<nux; j++) s -= L[j+nz*i]*v[j];
+			v[i] = s*dinv[i];
+			}
+		/* x_{n+1} = b + BAbt[:nux]' ux */
+		const double *M = P->BAbt[n];
+		double *xn = ux[n+1]+nu1;
+		for(j=0; j<nx1; j++)
+			{
+			double s = bsrc ? bsrc[n][j] : M[nux+nz*j];
+			for(i=0; i<nux; i++) s += M[i+nz*j]*v[i];
+			xn[j] = s;
+			}
+		if(compute_pi)
+			{
+			if(p) pi_from_x(P, n+1, xn, p[n], pi[n], P->tmp);
+			else
+				{
+				/* sv: p = Lxx l_x  folded as  Lxx (Lxx' x + l_x) */
+				int nz1 = nx1+nu1+1, k;
+				const double *L1 = P->L[n+1];
+				double *tmp = P->tmp;
+				for(i=0; i<nx1; i++)
+					{
+					double s = L1[nu1+nx1+nz1*(nu1+i)];
+					for(k=i; k<nx1; k++) s += L1[nu1+k+nz1*(nu1+i)]*xn[k];
+					tmp[i] = s;
+					}
+				for(i=0; i<nx1; i++)
+					{
+					double s = 0.0;
+					for(k=0; k<=i; k++) s += L1[nu1+i+nz1*(nu1+k)]*tmp[k];
+					pi[n][i] = s;
+					}
+				}
+			}
+		}
+	}
+
+/* factor + solve (d_back_ric_rec_sv_tv_res).  pi[n], Pb[n] edge-indexed n=0..N-1. */
+void orc_ric_sv(orc_prob *P, double *const *bvec, double *const *rqvec, double *const *Qx, double *const *qx,
+		double **ux, int compute_pi, double **pi, double **Pb)
+	{
+	int n;
+	orc_ric_backward(P, 1, bvec, rqvec, Qx, qx, Pb);
+	/* gradient rows as vectors */
+	double **lrow = malloc((P->N+1)*sizeof(double*));
+	for(n=0; n<=P->N; n++)
+		{
+		int nux = nux_(P,n), nz = nux+1, j;
+		lrow[n] = malloc((nux+1)*sizeof(double));
+		for(j=0; j<nux; j++) lrow[n][j] = P->L[n][nux+nz*j];
+		}
+	ric_forward(P, lrow, bvec, NULL, ux, compute_pi, pi);
+	for(n=0; n<=P->N; n++) free(lrow[n]);
+	free(lrow);
+	}
+
+void orc_ric_trf(orc_prob *P, double *const *Qx)
+	{
+	orc_ric_backward(P, 0, NULL, NULL, Qx, NULL, NULL);
+	}
+
+/* solve with stored factorization (d_back_ric_rec_trs_tv_res).  bvec[n] (nx1), rqvec[n] (nux) required. */
+void orc_ric_trs(orc_prob *P, double *const *bvec, double *const *rqvec, double *const *qx,
+		double **ux, int compute_pi, double **pi, int compute_Pb, double **Pb)
+	{
+	int N = P->N, n, i, j, k;
+	double **w = malloc((N+1)*sizeof(double*));
+	double **p = malloc((N+1)*sizeof(double*));
+	for(n=0; n<=N; n++) { w[n] = calloc(nux_(P,n)+1, sizeof(double)); p[n] = calloc(P->nxM+1, sizeof(double)); }
+	/* backward vector sweep */
+	for(n=N; n>=0; n--)
+		{
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1;
+		for(i=0; i<nux; i++) w[n][i] = rqvec[n][i];
+		if(P->nb[n]>0 && qx) for(j=0; j<P->nb[n]; j++) w[n][P->idxb[n][j]] += qx[n][j];
+		if(n<N)
+			{
+			int nx1 = P->nx[n+1], nu1 = P->nu[n+1];
+			double *tmp = P->tmp;
+			if(compute_Pb)
+				{
+				double *t2 = P->tmp+P->nzM;
+				int nz1 = nx1+nu1+1;
+				const double *L1 = P->L[n+1];
+				for(i=0; i<nx1; i++)
+					{
+					double s = 0.0;
+					for(k=i; k<nx1; k++) s += L1[nu1+k+nz1*(nu1+i)]*bvec[n][k];
+					t2[i] = s;
+					}
+				for(i=0; i<nx1; i++)
+					{
+					double s = 0.0;
+					for(k=0; k<=i; k++) s += L1[nu1+i+nz1*(nu1+k)]*t2[k];
+					Pb[n][i] = s;
+					}
+				}
+			for(j=0; j<nx1; j++) tmp[j] = Pb[n][j] + w[n+1][nu1+j];
+			const double *M = P->BAbt[n];
+			for(i=0; i<nux; i++)
+				{
+				double s = w[n][i];
+				for(j=0; j<nx1; j++) s += M[i+nz*j]*tmp[j];
+				w[n][i] = s;
+				}
+			int ks = (n==0) ? nux : nu;
+			const double *L = P->L[n], *dinv = P->dinv[n];
+			for(i=0; i<ks; i++)
+				{
+				double s = w[n][i];
+				for(j=0; j<i; j++) s -= L[i+nz*j]*w[n][j];
+				w[n][i] = s*dinv[i];
+				}
+			for(i=ks; i<nux; i++)
+				{
+				double s = w[n][i];
+				for(j=0; j<ks; j++) s -= L[i+nz*j]*w[n][j];
+				w[n][i] = s;
+				}
+			}
+		}
+	/* p[n] = x-part of w_{n+1} */
+	for(n=0; n<N; n++) for(i=0; i<P->nx[n+1]; i++) p[n][i] = w[n+1][P->nu[n+1]+i];
+	ric_forward(P, w, bvec, p, ux, compute_pi, pi);
+	for(n=0; n<=N; n++) { free(w[n]); free(p[n]); }
+	free(w); free(p);
+	}
+
+/* ------------------------------------------------------------------------------------------- */
+/* IPM                                                                                          */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+	double **ux, **pi, **lam, **t;            /* iterate: lam,t = [lower(nb) ; upper(nb)] */
+	double **dux, **dpi, **dlam, **dt, **tinv, **lamt, **Qx, **qx, **Pb;
+	double **b, **rq;                          /* copies of b_n and [r;q]_n as vectors */
+	double **res_q, **res_b, **res_d, **res_m;
+} orc_ipm_ws;
+
+static double **vecs(int n, const int *len) { double **v = malloc(n*sizeof(double*)); for(int i=0;i<n;i++) v[i]=calloc(len[i]+1,sizeof(double)); return v; }
+static void vecs_free(double **v, int n) { for(int i=0;i<n;i++) free(v[i]); free(v); }
+
+/* res_q,res_b,res_d,res_m, mu   (mpc_solvers/c99/d_res_ip_res_hard.c:39) */
+static void ipm_residuals(const orc_prob *P, const orc_ipm_ws *w, double *mu)
+	{
+	int N = P->N, n, i, j;
+	double mu2 = 0.0; int nb_tot = 0;
+	for(n=0; n<=N; n++)
+		{
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1, nb = P->nb[n];
+		double *rq = w->res_q[n];
+		for(i=0; i<nux; i++) rq[i] = w->rq[n][i];
+		if(n>0) for(i=0; i<nx; i++) rq[nu+i] -= w->pi[n-1][i];
+		nb_tot += nb;
+		for(j=0; j<nb; j++)
+			{
+			int id = P->idxb[n][j];
+			rq[id] += -w->lam[n][j] + w->lam[n][nb+j];
+			w->res_d[n][j]    = P->d[n][j]    - w->ux[n][id] + w->t[n][j];
+			w->res_d[n][nb+j] = P->d[n][nb+j] - w->ux[n][id] - w->t[n][nb+j];
+			w->res_m[n][j]    = w->lam[n][j]*w->t[n][j];
+			w->res_m[n][nb+j] = w->lam[n][nb+j]*w->t[n][nb+j];
+			mu2 += w->res_m[n][j] + w->res_m[n][nb+j];
+			}
+		/* rq += H ux  (H symmetric, lower stored) */
+		const double *H = P->RSQrq[n];
+		for(i=0; i<nux; i++)
+			{
+			double s = 0.0;
+			for(j=0; j<nux; j++) s += (i>=j ? H[i+nz*j] : H[j+nz*i])*w->ux[n][j];
+			rq[i] += s;
+			}
+		if(n<N)
+			{
+			int nx1 = P->nx[n+1], nu1 = P->nu[n+1];
+			const double *M = P->BAbt[n];
+			for(j=0; j<nx1; j++)
+				{
+				double s = w->b[n][j] - w->ux[n+1][nu1+j];
+				for(i=0; i<nux; i++) s += M[i+nz*j]*w->ux[n][i];
+				w->res_b[n][j] = s;
+				}
+			for(i=0; i<nux; i++)
+				{
+				double s = 0.0;
+				for(j=0; j<nx1; j++) s += M[i+nz*j]*w->pi[n][j];
+				rq[i] += s;
+				}
+			}
+		}
+	if(nb_tot!=0) *mu = mu2/(2.0*nb_tot);
+	}
+
+/* the IPM proper (mpc_solvers/d_ip2_res_hard.c:116).  ux/pi/lam/t in w are in/out. */
+int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *stat, double **ux, double **pi, double **lam, double **t)
+	{
+	int N = P->N, n, i, j;
+	int *lnux = malloc((N+1)*sizeof(int)), *lnx1 = malloc((N+1)*sizeof(int)), *l2nb = malloc((N+1)*sizeof(int)), *lnb = malloc((N+1)*sizeof(int));
+	for(n=0; n<=N; n++) { lnux[n] = nux_(P,n)+1; lnx1[n] = n<N ? P->nx[n+1] : 0; l2nb[n] = 2*P->nb[n]; lnb[n] = P->nb[n]; }
+	orc_ipm_ws W, *w = &W;
+	w->ux = ux; w->pi = pi; w->lam = lam; w->t = t;
+	w->dux = vecs(N+1, lnux); w->dpi = vecs(N+1, lnx1); w->dlam = vecs(N+1, l2nb); w->dt = vecs(N+1, l2nb);
+	w->tinv = vecs(N+1, l2nb); w->lamt = vecs(N+1, l2nb); w->Qx = vecs(N+1, lnb); w->qx = vecs(N+1, lnb);
+	w->Pb = vecs(N+1, lnx1); w->b = vecs(N+1, lnx1); w->rq = vecs(N+1, lnux);
+	w->res_q = vecs(N+1, lnux); w->res_b = vecs(N+1, lnx1); w->res_d = vecs(N+1, l2nb); w->res_m = vecs(N+1, l2nb);
+	for(n=0; n<=N; n++)
+		{
+		int nux = nux_(P,n), nz = nux+1;
+		for(j=0; j<nux; j++) w->rq[n][j] = P->RSQrq[n][nux+nz*j];
+		if(n<N) for(j=0; j<P->nx[n+1]; j++) w->b[n][j] = P->BAbt[n][nux+nz*j];
+		}
+
+	int status = -1;
+	double mu_scal = 0.0;
+	for(n=0; n<=N; n++) mu_scal += 2*P->nb[n];
+	if(mu_scal==0.0)
+		{
+		orc_ric_sv(P, NULL, NULL, NULL, NULL, ux, 1, pi, w->Pb);
+		*kk = 0;
+		status = 0;
+		goto done;
+		}
+	mu_scal = 1.0/mu_scal;
+	double sigma = 0.0, alpha, mu, mu_aff = 0.0;
+	const double thr0 = 0.1;
+
+	/* init (c99/d_aux_ip_hard_lib4.c:43-149) */
+	if(warm_start==0) for(n=0; n<=N; n++) for(i=0; i<nux_(P,n); i++) ux[n][i] = 0.0;
+	for(n=0; n<=N; n++)
+		{
+		int nb = P->nb[n];
+		for(j=0; j<nb; j++)
+			{
+			int id = P->idxb[n][j];
+			t[n][j]    = -P->d[n][j]    + ux[n][id];
+			t[n][nb+j] =  P->d[n][nb+j] - ux[n][id];
+			if(t[n][j]<thr0)
+				{
+				if(t[n][nb+j]<thr0)
+					{
+					ux[n][id] = (-P->d[n][nb+j] + P->d[n][j])*0.5;
+					t[n][j] = thr0; t[n][nb+j] = thr0;
+					}
+				else { t[n][j] = thr0; ux[n][id] = P->d[n][j] + thr0; }
+				}
+			else if(t[n][nb+j]<thr0) { t[n][nb+j] = thr0; ux[n][id] = P->d[n][nb+j] - thr0; }
+			lam[n][j] = mu0/t[n][j];
+			lam[n][nb+j] = mu0/t[n][nb+j];
+			}
+		}
+	for(n=0; n<N; n++) for(i=0; i<P->nx[n+1]; i++) pi[n][i] = 0.0;
+
+	mu = mu0; *kk = 0; alpha = 1.0;
+	double mu_tol_low = mu_tol<1e-5 ? 1e-5 : mu_tol;
+
+	/* ---------------- phase 1: no residuals (d_ip2_res_hard.c:503-718) ---------------- */
+	while(*kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
+		{
+		for(n=0; n<=N; n++)
+			{
+			int nb = P->nb[n];
+			for(j=0; j<nb; j++)
+				{
+				w->tinv[n][j] = 1.0/t[n][j]; w->tinv[n][nb+j] = 1.0/t[n][nb+j];
+				w->lamt[n][j] = lam[n][j]*w->tinv[n][j]; w->lamt[n][nb+j] = lam[n][nb+j]*w->tinv[n][nb+j];
+				w->dlam[n][j] = w->tinv[n][j]*0.0; w->dlam[n][nb+j] = w->tinv[n][nb+j]*0.0;
+				w->Qx[n][j] = w->lamt[n][j] + w->lamt[n][nb+j];
+				w->qx[n][j] = lam[n][nb+j] - w->lamt[n][nb+j]*P->d[n][nb+j] + w->dlam[n][nb+j]
+				            - lam[n][j] - w->lamt[n][j]*P->d[n][j] - w->dlam[n][j];
+				}
+			}
+		orc_ric_sv(P, NULL, w->rq, w->Qx, w->qx, w->dux, 1, w->dpi, w->Pb);
+		for(int pass=0; pass<2; pass++)
+			{
+			alpha = 1.0;
+			for(n=0; n<=N; n++)
+				{
+				int nb = P->nb[n];
+				for(j=0; j<nb; j++)
+					{
+					int id = P->idxb[n][j];
+					w->dt[n][j]    =  w->dux[n][id] - P->d[n][j]    - t[n][j];
+					w->dt[n][nb+j] = -w->dux[n][id] + P->d[n][nb+j] - t[n][nb+j];
+					w->dlam[n][j]    -= w->lamt[n][j]*w->dt[n][j] + lam[n][j];
+					w->dlam[n][nb+j] -= w->lamt[n][nb+j]*w->dt[n][nb+j] + lam[n][nb+j];
+					if(-alpha*w->dlam[n][j]>lam[n][j]) alpha = -lam[n][j]/w->dlam[n][j];
+					if(-alpha*w->dlam[n][nb+j]>lam[n][nb+j]) alpha = -lam[n][nb+j]/w->dlam[n][nb+j];
+					if(-alpha*w->dt[n][j]>t[n][j]) alpha = -t[n][j]/w->dt[n][j];
+					if(-alpha*w->dt[n][nb+j]>t[n][nb+j]) alpha = -t[n][nb+j]/w->dt[n][nb+j];
+					}
+				}
+			if(pass==0)
+				{
+				stat[5*(*kk)] = sigma; stat[5*(*kk)+1] = alpha;
+				alpha *= 0.995;
+				mu_aff = 0.0;
+				for(n=0; n<=N; n++)
+					{
+					int nb = P->nb[n];
+					for(j=0; j<nb; j++)
+						mu_aff += (lam[n][j] + alpha*w->dlam[n][j])*(t[n][j] + alpha*w->dt[n][j])
+						        + (lam[n][nb+j] + alpha*w->dlam[n][nb+j])*(t[n][nb+j] + alpha*w->dt[n][nb+j]);
+					}
+				mu_aff *= mu_scal;
+				stat[5*(*kk)+2] = mu_aff;
+				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
+				double sm = sigma*mu;
+				for(n=0; n<=N; n++)
+					{
+					int nb = P->nb[n];
+					for(j=0; j<nb; j++)
+						{
+						w->dlam[n][j]    = w->tinv[n][j]*(sm - w->dlam[n][j]*w->dt[n][j]);
+						w->dlam[n][nb+j] = w->tinv[n][nb+j]*(sm - w->dlam[n][nb+j]*w->dt[n][nb+j]);
+						w->qx[n][j] += w->dlam[n][nb+j] - w->dlam[n][j];
+						}
+					}
+				orc_ric_trs(P, w->b, w->rq, w->qx, w->dux, 1, w->dpi, 0, w->Pb);
+				}
+			}
+		stat[5*(*kk)] = sigma; stat[5*(*kk)+3] = alpha;
+		alpha *= 0.995;
+		mu = 0.0;
+		for(n=0; n<=N; n++)
+			{
+			int nux = nux_(P,n), nb = P->nb[n];
+			for(i=0; i<nux; i++) ux[n][i] += alpha*(w->dux[n][i] - ux[n][i]);
+			if(n<N) for(i=0; i<P->nx[n+1]; i++) pi[n][i] += alpha*(w->dpi[n][i] - pi[n][i]);
+			for(j=0; j<nb; j++)
+				{
+				lam[n][j] += alpha*w->dlam[n][j]; lam[n][nb+j] += alpha*w->dlam[n][nb+j];
+				t[n][j] += alpha*w->dt[n][j]; t[n][nb+j] += alpha*w->dt[n][nb+j];
+				mu += lam[n][j]*t[n][j] + lam[n][nb+j]*t[n][nb+j];
+				}
+			}
+		mu *= mu_scal;
+		stat[5*(*kk)+4] = mu;
+		(*kk)++;
+		}
+
+	/* ---------------- phase 2: with residuals (d_ip2_res_hard.c:756-1273) ---------------- */
+	ipm_residuals(P, w, &mu);
+	while(*kk<k_max && mu>mu_tol && alpha>=alpha_min)
+		{
+		for(n=0; n<=N; n++)
+			{
+			int nb = P->nb[n];
+			for(j=0; j<nb; j++)
+				{
+				w->tinv[n][j] = 1.0/t[n][j]; w->tinv[n][nb+j] = 1.0/t[n][nb+j];
+				w->Qx[n][j] = w->tinv[n][j]*lam[n][j] + w->tinv[n][nb+j]*lam[n][nb+j];
+				w->qx[n][j] = w->tinv[n][j]*(w->res_m[n][j] - lam[n][j]*w->res_d[n][j])
+				            - w->tinv[n][nb+j]*(w->res_m[n][nb+j] + lam[n][nb+j]*w->res_d[n][nb+j]);
+				}
+			}
+		orc_ric_sv(P, w->res_b, w->res_q, w->Qx, w->qx, w->dux, 1, w->dpi, w->Pb);
+		for(int pass=0; pass<2; pass++)
+			{
+			alpha = 1.0;
+			for(n=0; n<=N; n++)
+				{
+				int nb = P->nb[n];
+				for(j=0; j<nb; j++)
+					{
+					int id = P->idxb[n][j];
+					w->dt[n][j]    =  w->dux[n][id] - w->res_d[n][j];
+					w->dt[n][nb+j] = -w->dux[n][id] + w->res_d[n][nb+j];
+					w->dlam[n][j]    = -w->tinv[n][j]*(lam[n][j]*w->dt[n][j] + w->res_m[n][j]);
+					w->dlam[n][nb+j] = -w->tinv[n][nb+j]*(lam[n][nb+j]*w->dt[n][nb+j] + w->res_m[n][nb+j]);
+					if(-alpha*w->dlam[n][j]>lam[n][j]) alpha = -lam[n][j]/w->dlam[n][j];
+					if(-alpha*w->dlam[n][nb+j]>lam[n][nb+j]) alpha = -lam[n][nb+j]/w->dlam[n][nb+j];
+					if(-alpha*w->dt[n][j]>t[n][j]) alpha = -t[n][j]/w->dt[n][j];
+					if(-alpha*w->dt[n][nb+j]>t[n][nb+j]) alpha = -t[n][nb+j]/w->dt[n][nb+j];
+					}
+				}
+			if(pass==0)
+				{
+				stat[5*(*kk)] = sigma; stat[5*(*kk)+1] = alpha;
+				alpha *= 0.995;
+				mu_aff = 0.0;
+				for(n=0; n<=N; n++)
+					{
+					int nb = P->nb[n];
+					for(j=0; j<nb; j++)
+						mu_aff += (lam[n][j] + alpha*w->dlam[n][j])*(t[n][j] + alpha*w->dt[n][j])
+						        + (lam[n][nb+j] + alpha*w->dlam[n][nb+j])*(t[n][nb+j] + alpha*w->dt[n][nb+j]);
+					}
+				mu_aff *= mu_scal;
+				stat[5*(*kk)+2] = mu_aff;
+				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
+				double sm = sigma*mu;
+				for(n=0; n<=N; n++)
+					{
+					int nb = P->nb[n];
+					for(j=0; j<nb; j++)
+						{
+						w->res_m[n][j]    += w->dt[n][j]*w->dlam[n][j] - sm;
+						w->res_m[n][nb+j] += w->dt[n][nb+j]*w->dlam[n][nb+j] - sm;
+						w->qx[n][j] = w->tinv[n][j]*(w->res_m[n][j] - lam[n][j]*w->res_d[n][j])
+						            - w->tinv[n][nb+j]*(w->res_m[n][nb+j] + lam[n][nb+j]*w->res_d[n][nb+j]);
+						}
+					}
+				orc_ric_trs(P, w->res_b, w->res_q, w->qx, w->dux, 1, w->dpi, 0, w->Pb);
+				}
+			}
+		stat[5*(*kk)] = sigma; stat[5*(*kk)+3] = alpha;
+		alpha *= 0.995;
+		for(n=0; n<=N; n++)
+			{
+			int nux = nux_(P,n), nb = P->nb[n];
+			for(i=0; i<nux; i++) ux[n][i] += alpha*w->dux[n][i];
+			if(n<N) for(i=0; i<P->nx[n+1]; i++) pi[n][i] += alpha*w->dpi[n][i];
+			for(j=0; j<2*nb; j++) { lam[n][j] += alpha*w->dlam[n][j]; t[n][j] += alpha*w->dt[n][j]; }
+			}
+		ipm_residuals(P, w, &mu);
+		stat[5*(*kk)+4] = mu;
+		(*kk)++;
+		}
+
+	if(mu<=mu_tol) status = 0;
+	else if(*kk>=k_max) status = 1;
+	else if(alpha<alpha_min) status = 2;
+	else status = -1;
+
+done:
+	vecs_free(w->dux, N+1); vecs_free(w->dpi, N+1); vecs_free(w->dlam, N+1); vecs_free(w->dt, N+1);
+	vecs_free(w->tinv, N+1); vecs_free(w->lamt, N+1); vecs_free(w->Qx, N+1); vecs_free(w->qx, N+1);
+	vecs_free(w->Pb, N+1); vecs_free(w->b, N+1); vecs_free(w->rq, N+1);
+	vecs_free(w->res_q, N+1); vecs_free(w->res_b, N+1); vecs_free(w->res_d, N+1); vecs_free(w->res_m, N+1);
+	free(lnux); free(lnx1); free(l2nb); free(lnb);
+	return status;
+	}
+
+/* exit residual norms (mpc_solvers/d_res_ip_hard.c:38 + interfaces/c/fortran_order_interface.c:612-652) */
+void orc_exit_residuals(const orc_prob *P, double *const *ux, double *const *pi, double *const *lam, double *const *t,
+		double *inf_norm_res)
+	{
+	int N = P->N, n, i, j;
+	double nq = 0.0, nb_ = 0.0, nd = 0.0, mu = 0.0; int nb_tot = 0;
+	for(n=0; n<=N; n++)
+		{
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1, nb = P->nb[n];
+		const double *H = P->RSQrq[n];
+		double *rq = calloc(nux+1, sizeof(double));
+		for(i=0; i<nux; i++) rq[i] = H[nux+nz*i];
+		if(n>0) for(i=0; i<nx; i++) rq[nu+i] -= pi[n-1][i];
+		nb_tot += nb;
+		for(j=0; j<nb; j++)
+			{
+			int id = P->idxb[n][j];
+			rq[id] += -lam[n][j] + lam[n][nb+j];
+			mu += lam[n][j]*t[n][j] + lam[n][nb+j]*t[n][nb+j];
+			nd = fmax(nd, fabs(ux[n][id] - P->d[n][j] - t[n][j]));
+			nd = fmax(nd, fabs(-ux[n][id] + P->d[n][nb+j] - t[n][nb+j]));
+			}
+		for(i=0; i<nux; i++)
+			{
+			double s = 0.0;
+			for(j=0; j<nux; j++) s += (i>=j ? H[i+nz*j] : H[j+nz*i])*ux[n][j];
+			rq[i] += s;
+			}
+		if(n<N)
+			{
+			int nx1 = P->nx[n+1], nu1 = P->nu[n+1];
+			const double *M = P->BAbt[n];
+			for(j=0; j<nx1; j++)
+				{
+				double s = M[nux+nz*j] - ux[n+1][nu1+j];
+				for(i=0; i<nux; i++) s += M[i+nz*j]*ux[n][i];
+				nb_ = fmax(nb_, fabs(s));
+				}
+			for(i=0; i<nux; i++)
+				{
+				double s = 0.0;
+				for(j=0; j<nx1; j++) s += M[i+nz*j]*pi[n][j];
+				rq[i] += s;
+				}
+			}
+		for(i=0; i<nux; i++) nq = fmax(nq, fabs(rq[i]));
+		free(rq);
+		}
+	if(nb_tot) mu /= 2.0*nb_tot;
+	inf_norm_res[0] = nq; inf_norm_res[1] = nb_; inf_norm_res[2] = nd; inf_norm_res[3] = mu;
+	}
+
+/* ------------------------------------------------------------------------------------------- */
+/* drivers with the reference's own high-level signature (column-major stage-wise arrays)       */
+/* ------------------------------------------------------------------------------------------- */
+static double **alloc_ux(const orc_prob *P) { int N=P->N; double **v = malloc((N+1)*sizeof(double*)); for(int n=0;n<=N;n++) v[n]=calloc(nux_(P,n)+1,sizeof(double)); return v; }
+
+/* same argument list as fortran_order_d_ip_ocp_hard_tv (include/c_interface.h:65 of the reference) */
+int orc_fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu_N, int *nb,
+		int **hidxb, int *ng, int N2, int warm_start, double **A, double **B, double **b, double **Q, double **S,
+		double **R, double **q, double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
+		double **x, double **u, double **pi, double **lam, double *inf_norm_res, void *work0, double *stat)
+	{
+	(void)ng; (void)N2; (void)C; (void)D; (void)lg; (void)ug; (void)work0;
+	int n, i, j, l;
+	orc_prob *P = orc_prob_create(N, nx, nu_N, nb, hidxb);
+	orc_prob_set(P, A, B, b, Q, S, R, q, r, lb, ub);
+	/* mu0 estimate: signed max over cost entries (fortran_order_interface.c:318-331) */
+	if(mu0<=0)
+		{
+		for(n=0; n<N; n++)
+			{
+			int nu = P->nu[n];
+			for(j=0; j<nu; j++) for(l=0; l<nu; l++) mu0 = fmax(mu0, R[n][j*nu+l]);
+			for(j=0; j<nx[n]*nu; j++) mu0 = fmax(mu0, S[n][j]);
+			for(j=0; j<nx[n]; j++) for(l=0; l<nx[n]; l++) mu0 = fmax(mu0, Q[n][j*nx[n]+l]);
+			for(j=0; j<nu; j++) mu0 = fmax(mu0, r[n][j]);
+			for(j=0; j<nx[n]; j++) mu0 = fmax(mu0, q[n][j]);
+			}
+		n = N;
+		for(j=0; j<nx[n]; j++) for(l=0; l<nx[n]; l++) mu0 = fmax(mu0, Q[n][j*nx[n]+l]);
+		for(j=0; j<nx[n]; j++) mu0 = fmax(mu0, q[n][j]);
+		}
+	double **hux = alloc_ux(P);
+	double **hpi = malloc((N+1)*sizeof(double*)), **hlam = malloc((N+1)*sizeof(double*)), **ht = malloc((N+1)*sizeof(double*));
+	for(n=0; n<=N; n++) { hpi[n] = calloc(P->nxM+1, sizeof(double)); hlam[n] = calloc(2*P->nb[n]+1, sizeof(double)); ht[n] = calloc(2*P->nb[n]+1, sizeof(double)); }
+	if(warm_start)
+		{
+		for(n=0; n<N; n++) for(i=0; i<P->nu[n]; i++) hux[n][i] = u[n][i];
+		for(n=0; n<=N; n++) for(i=0; i<nx[n]; i++) hux[n][P->nu[n]+i] = x[n][i];
+		}
+	int status = orc_ip2_res_mpc_hard(P, kk, k_max, mu0, mu_tol, 1e-8, warm_start, stat, hux, hpi, hlam, ht);
+	for(n=0; n<N; n++) for(i=0; i<P->nu[n]; i++) u[n][i] = hux[n][i];
+	for(n=0; n<=N; n++) for(i=0; i<nx[n]; i++) x[n][i] = hux[n][P->nu[n]+i];
+	for(n=0; n<N; n++)
+		for(j=0; j<nb[n] && hidxb[n][j]<P->nu[n]; j++)
+			if(lb[n][j]==ub[n][j]) u[n][hidxb[n][j]] = lb[n][j];
+	orc_exit_residuals(P, hux, hpi, hlam, ht, inf_norm_res);
+	for(n=0; n<N; n++) for(i=0; i<nx[n+1]; i++) pi[n][i] = hpi[n][i];
+	for(n=0; n<=N; n++) for(j=0; j<2*nb[n]; j++) lam[n][j] = hlam[n][j];
+	for(n=0; n<=N; n++) { free(hux[n]); free(hpi[n]); free(hlam[n]); free(ht[n]); }
+	free(hux); free(hpi); free(hlam); free(ht);
+	orc_prob_free(P);
+	return status;
+	}
+
+/* unconstrained LQCP, factor+solve, same stage-wise arrays.  mode: 0 = sv ; 1 = trf followed by trs */
+void orc_fortran_order_d_ric(int mode, int N, int *nx, int *nu_N, double **A, double **B, double **b, double **Q, double **S,
+		double **R, double **q, double **r, double **x, double **u, double **pi)
+	{
+	int n, i;
+	int *nb = calloc(N+1, sizeof(int)); int **idxb = calloc(N+1, sizeof(int*));
+	for(n=0; n<=N; n++) idxb[n] = calloc(1, sizeof(int));
+	orc_prob *P = orc_prob_create(N, nx, nu_N, nb, idxb);
+	orc_prob_set(P, A, B, b, Q, S, R, q, r, b /*unused*/, b /*unused*/);
+	double **hux = alloc_ux(P);
+	double **hpi = malloc((N+1)*sizeof(double*)), **hPb = malloc((N+1)*sizeof(double*));
+	for(n=0; n<=N; n++) { hpi[n] = calloc(P->nxM+1, sizeof(double)); hPb[n] = calloc(P->nxM+1, sizeof(double)); }
+	if(mode==0)
+		orc_ric_sv(P, NULL, NULL, NULL, NULL, hux, 1, hpi, hPb);
+	else
+		{
+		double **bv = malloc((N+1)*sizeof(double*)), **rq = malloc((N+1)*sizeof(double*));
+		for(n=0; n<=N; n++)
+			{
+			int nux = nux_(P,n), nz = nux+1, j;
+			rq[n] = calloc(nux+1, sizeof(double)); bv[n] = calloc(P->nxM+1, sizeof(double));
+			for(j=0; j<nux; j++) rq[n][j] = P->RSQrq[n][nux+nz*j];
+			if(n<N) for(j=0; j<nx[n+1]; j++) bv[n][j] = P->BAbt[n][nux+nz*j];
+			}
+		orc_ric_trf(P, NULL);
+		orc_ric_trs(P, bv, rq, NULL, hux, 1, hpi, 1, hPb);
+		for(n=0; n<=N; n++) { free(bv[n]); free(rq[n]); }
+		free(bv); free(rq);
+		}
+	for(n=0; n<N; n++) for(i=0; i<P->nu[n]; i++) u[n][i] = hux[n][i];
+	for(n=0; n<=N; n++) for(i=0; i<nx[n]; i++) x[n][i] = hux[n][P->nu[n]+i];
+	for(n=0; n<N; n++) for(i=0; i<nx[n+1]; i++) pi[n][i] = hpi[n][i];
+	for(n=0; n<=N; n++) { free(hux[n]); free(hpi[n]); free(hPb[n]); free(idxb[n]); }
+	free(hux); free(hpi); free(hPb); free(nb); free(idxb);
+	orc_prob_free(P);
+	}
