@@ -231,7 +231,7 @@ def product() -> C.CDLL:
     if _product is None:
         if not os.path.exists(PRODUCT_LIB):
             raise RuntimeError(f"{PRODUCT_LIB} is missing; run __graft_entry__.build() -- hpmpc_b200 has no CPU fallback")
-        L = C.CDLL(PRODUCT_LIB, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(PRODUCT_LIB, mode=C.RTLD_LOCAL)
         L.hpmpc_b200_ocp_create.restype = C.c_int
         L.hpmpc_b200_ocp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hpmpc_b200_ocp_destroy.argtypes = [C.c_void_p]

@@ -124,6 +124,14 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 	p->lam_stride = 2*(long long)nbtot;
 	if(nzM>64) { fprintf(stderr, "hpmpc_b200: nu+nx+1 = %d > 64 is not supported yet\n", nzM); return -2; }
 
+	if(device<0)
+		{
+		/* host-only handle: layout queries and packing work, every compute entry point refuses to run */
+		p->sms = 148;
+		default_launch(p, 0, 0);
+		*out = p;
+		return 0;
+		}
 	CK(cudaSetDevice(device));
 	hb_stage *d_st; int *d_idxb, *d_cux;
 	CK(cudaMalloc((void**)&d_st, (N+1)*sizeof(hb_stage)));
@@ -145,6 +153,13 @@ void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p)
 	{
 	int n, k;
 	if(!p) return;
+	if(p->device<0)
+		{
+		for(n=0; n<=p->N; n++) free(p->idxb[n]);
+		free(p->idxb); free(p->nx); free(p->nu); free(p->nb); free(p->st); free(p->h_idxb); free(p->h_cux);
+		free(p);
+		return;
+		}
 	cudaSetDevice(p->device);
 	for(k=0; k<2; k++)
 		{
@@ -251,6 +266,7 @@ int hpmpc_b200_d_back_ric_rec_sv_batch(hpmpc_b200_ocp *p, long long n_inst, cons
 		double *d_ux, double *d_pi, double *d_Pb, void *stream)
 	{
 	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*p->dims.L_stride)) return -1;
 	return hb_launch_ric_sv(&p->dims, n_inst, d_in, d_ux, d_pi, d_Pb, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
@@ -259,6 +275,7 @@ int hpmpc_b200_d_back_ric_rec_sv_batch(hpmpc_b200_ocp *p, long long n_inst, cons
 int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_L, void *stream)
 	{
 	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	return hb_launch_ric_trf(&p->dims, n_inst, d_in, d_L, grid_for(p, n_inst), p->warps, stream);
 	}
@@ -267,6 +284,7 @@ int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, con
 		double *d_ux, double *d_pi, void *stream)
 	{
 	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*(p->dims.ux_stride+2*p->dims.pi_stride))) return -1;
 	return hb_launch_ric_trs(&p->dims, n_inst, d_in, d_L, d_ux, d_pi, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
@@ -277,6 +295,7 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
 		double *d_info, void *stream)
 	{
 	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	long long ws = hb_ipm_work_doubles(&p->dims);
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*ws)) return -1;
@@ -322,6 +341,7 @@ static long long chunk_size(const hpmpc_b200_ocp *p, long long n_inst)
 int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in, double *h_ux, double *h_pi)
 	{
 	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	const long long cs = chunk_size(p, n_inst);
 	const size_t in_b = sizeof(double)*(size_t)cs*p->dims.in_stride;
@@ -350,6 +370,7 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 		double mu_tol, double alpha_min, int warm_start, double *h_ux, double *h_pi, double *h_lam, double *h_t, double *h_info)
 	{
 	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	const long long cs = chunk_size(p, n_inst);
 	const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max, lam_len = p->lam_stride>0 ? p->lam_stride : 2;

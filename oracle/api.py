@@ -90,3 +90,110 @@ def ric(p: Ocp, mode: str = "sv"):
     L.orc_fortran_order_d_ric(0 if mode == "sv" else 1, N, int_array(p.nx), int_array(p.nu), *arrs)
     return dict(x=[x[n][:p.nx[n]].copy() for n in range(N + 1)], u=[u[n][:p.nu[n]].copy() for n in range(N)],
                 pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)])
+
+
+# ------------------------------------------------------------------------------------------- CPU timing harness
+def _harness():
+    L = lib()
+    L.ref_harness_ric_sv.restype = C.c_double
+    L.ref_harness_ric_sv.argtypes = [C.c_char_p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long,
+                                     C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+    L.ref_harness_ipm.restype = C.c_double
+    L.ref_harness_ipm.argtypes = [C.c_char_p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+    return L
+
+
+class RefSample:
+    """A bounded sample of the batch workload in the REFERENCE's own input formats, for timing it on the host cores:
+    panel-major hpBAbt/hpRSQrq for d_back_ric_rec_sv_tv_res, column-major stage arrays for fortran_order_d_ip_ocp_hard_tv.
+    Instance i is the same problem as instance i of hpmpc_b200.batchgen.BatchSpec."""
+
+    def __init__(self, spec, n_inst: int, first: int = 0):
+        from hpmpc_b200.capi import to_pmat, _rup
+        self.spec, self.n_inst = spec, n_inst
+        p = spec.base
+        N = p.N
+        x01, x02, qs, rs = spec.scalars(n_inst, first)
+        # ---- panel-major (Riccati)
+        parts, self.off_pm, pos = [], [], 0
+        iq, ir, ib0 = [], [], []
+        href = HpmpcLib.__new__(HpmpcLib)
+        BAbt, RSQ = HpmpcLib._pm_problem(href, p)
+        for n in range(N):
+            a = BAbt[n]; self.off_pm.append(pos)
+            if n == 0 and spec.x0_elim:
+                nux, nx1 = p.nu[0] + p.nx[0], p.nx[1]
+                sda = _rup(nx1, 2)
+                ib0 = [pos + (nux // 4) * 4 * sda + nux % 4 + 4 * j for j in range(nx1)]
+            parts.append(a); pos += _rup(a.size, 8)
+        for n in range(N + 1):
+            a = RSQ[n]; self.off_pm.append(pos)
+            nu, nx = p.nu[n], p.nx[n]; sda = _rup(nu + nx, 2)
+            ir += [pos + (i // 4) * 4 * sda + i % 4 + 4 * i for i in range(nu)]
+            iq += [pos + (i // 4) * 4 * sda + i % 4 + 4 * i for i in range(nu, nu + nx)]
+            parts.append(a); pos += _rup(a.size, 8)
+        self.pm_stride = pos
+        base = np.zeros(pos)
+        for o, a in zip(self.off_pm, parts):
+            base[o:o + a.size] = a
+        from hpmpc_b200.capi import aligned_zeros
+        pm = aligned_zeros(n_inst * pos).reshape(n_inst, pos)
+        pm[:] = base[None, :]
+        pm[:, iq] = qs[:, None]; pm[:, ir] = rs[:, None]
+        if spec.x0_elim:
+            pm[:, ib0] = x01[:, None] * spec.A_cols[None, :, 0] + x02[:, None] * spec.A_cols[None, :, 1] + 0.1
+        self.pm = pm
+        # ---- column-major stage arrays (IPM)
+        parts, offs, pos = [], np.zeros((10, N + 1), dtype=np.int64), 0
+        iq, ir, ib0 = [], [], []
+        lists = (p.A, p.B, p.b, p.Q, p.S, p.R, p.q, p.r, p.lb, p.ub)
+        for k, Lk in enumerate(lists):
+            for n, M in enumerate(Lk):
+                a = np.asfortranarray(M, dtype=np.float64).ravel(order="F")
+                offs[k, n] = pos
+                if k == 3: iq += [pos + i * (p.nx[n] + 1) for i in range(p.nx[n])]
+                if k == 5: ir += [pos + i * (p.nu[n] + 1) for i in range(p.nu[n])]
+                if k == 2 and n == 0 and spec.x0_elim: ib0 = [pos + j for j in range(p.nx[1])]
+                parts.append((pos, a)); pos += _rup(max(a.size, 1), 8)
+        self.cm_stride, self.off_cm = pos, offs
+        base = np.zeros(pos)
+        for o, a in parts:
+            base[o:o + a.size] = a
+        cm = aligned_zeros(n_inst * pos).reshape(n_inst, pos)
+        cm[:] = base[None, :]
+        cm[:, iq] = qs[:, None]; cm[:, ir] = rs[:, None]
+        if spec.x0_elim:
+            cm[:, ib0] = x01[:, None] * spec.A_cols[None, :, 0] + x02[:, None] * spec.A_cols[None, :, 1] + 0.1
+        self.cm = cm
+
+    def time_ric_sv(self, kind="avx2", n_threads=None, n_pass=1, want_out=False):
+        p = self.spec.base
+        L = _harness()
+        n_threads = n_threads or os.cpu_count()
+        off = np.asarray(self.off_pm, dtype=np.int64)
+        n_ux, n_pi = sum(p.nx) + sum(p.nu), sum(p.nx[1:])
+        ux = np.zeros((self.n_inst, n_ux)) if want_out else None
+        pi = np.zeros((self.n_inst, n_pi)) if want_out else None
+        sec = L.ref_harness_ric_sv((REF_AVX2 if kind == "avx2" else REF_C99).encode(), n_threads, self.n_inst, n_pass, p.N,
+                                   int_array(p.nx), int_array(p.nu), self.pm.ctypes.data, self.pm_stride, off.ctypes.data,
+                                   ux.ctypes.data if want_out else None, n_ux, pi.ctypes.data if want_out else None, n_pi)
+        if sec < 0:
+            raise RuntimeError("reference harness failed")
+        return sec, ux, pi
+
+    def time_ipm(self, kind="avx2", n_threads=None, n_pass=1, k_max=40, mu0=2.0, mu_tol=1e-8, want_out=False):
+        p = self.spec.base
+        L = _harness()
+        n_threads = n_threads or os.cpu_count()
+        idxb = np.concatenate([np.asarray(v, dtype=np.int32) for v in p.idxb] + [np.zeros(1, dtype=np.int32)])
+        n_ux = sum(p.nx) + sum(p.nu)
+        kk = np.zeros(self.n_inst, dtype=np.int32); st = np.zeros(self.n_inst, dtype=np.int32)
+        ux = np.zeros((self.n_inst, n_ux)) if want_out else None
+        sec = L.ref_harness_ipm((REF_AVX2 if kind == "avx2" else REF_C99).encode(), n_threads, self.n_inst, n_pass, p.N,
+                                int_array(p.nx), int_array(p.nu), int_array(p.nb), idxb.ctypes.data, k_max, mu0, mu_tol,
+                                self.cm.ctypes.data, self.cm_stride, np.ascontiguousarray(self.off_cm).ctypes.data,
+                                kk.ctypes.data, st.ctypes.data, ux.ctypes.data if want_out else None, n_ux)
+        if sec < 0:
+            raise RuntimeError("reference harness failed")
+        return sec, kk, st, ux
