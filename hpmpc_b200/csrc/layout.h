@@ -69,6 +69,10 @@ int hb_launch_ric_trs(const hb_dims *dims, long long n_inst, const double *in, c
 int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
 		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
 		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, void *stream);
+int hb_fast_variant(int N, const int *nx, const int *nu);
+int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst);
+int hb_launch_ric_sv_fast(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
+		double *stash, int grid, int warps, void *stream);
 long long hb_ipm_work_doubles(const hb_dims *dims);
 int hb_smem_bytes_per_warp(const hb_dims *dims);
 int hb_device_sm_count(int device);

@@ -27,8 +27,11 @@ struct hpmpc_b200_ocp
 	int *h_idxb, *h_cux;     /* flat [nbtot] */
 	hb_dims dims;            /* st / idxb / c_ux are DEVICE pointers */
 	long long lam_stride;
-	/* launch shape */
+	/* launch shape: generic kernels */
 	int sms, grid, warps, n_slots, smem_cta;
+	/* size-specialised sv kernel (ric_fast.cuh), -1 when the pattern has no compiled variant */
+	int fast_id, f_ipw, f_smem_warp, f_grid, f_warps, f_smem_cta;
+	long long f_stash_inst;
 	/* scratch (device), grown on demand */
 	double *scratch; size_t scratch_bytes;
 	int *counter;
@@ -68,6 +71,22 @@ static void default_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps)
 	p->grid = p->sms*ctas_per_sm;
 	p->n_slots = p->grid*p->warps;
 	p->smem_cta = smem_cta;
+	}
+
+static void fast_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps)
+	{
+	if(p->fast_id<0) return;
+	if(warps<=0) warps = 4;
+	while(warps>1 && warps*p->f_smem_warp>220*1024) warps--;
+	int smem_cta = warps*p->f_smem_warp;
+	if(ctas_per_sm<=0)
+		{
+		ctas_per_sm = (225*1024)/(smem_cta+1024);
+		if(ctas_per_sm<1) ctas_per_sm = 1;
+		int cap = 8/warps; if(cap<1) cap = 1;            /* <= 8 resident warps per SM: keeps the factor stash near L2 size */
+		if(ctas_per_sm>cap) ctas_per_sm = cap;
+		}
+	p->f_warps = warps; p->f_grid = p->sms*ctas_per_sm; p->f_smem_cta = smem_cta;
 	}
 
 int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, int device)
@@ -124,11 +143,14 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 	p->lam_stride = 2*(long long)nbtot;
 	if(nzM>64) { fprintf(stderr, "hpmpc_b200: nu+nx+1 = %d > 64 is not supported yet\n", nzM); return -2; }
 
+	p->fast_id = getenv("HPMPC_B200_NO_FAST") ? -1 : hb_fast_variant(N, p->nx, p->nu);
+	if(p->fast_id>=0) hb_fast_info(p->fast_id, N, &p->f_ipw, &p->f_smem_warp, &p->f_stash_inst);
 	if(device<0)
 		{
 		/* host-only handle: layout queries and packing work, every compute entry point refuses to run */
 		p->sms = 148;
 		default_launch(p, 0, 0);
+		fast_launch(p, 0, 0);
 		*out = p;
 		return 0;
 		}
@@ -145,6 +167,7 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 	p->sms = hb_device_sm_count(device);
 	if(p->sms<=0) { fprintf(stderr, "hpmpc_b200: no CUDA device %d\n", device); return -1; }
 	default_launch(p, 0, 0);
+	fast_launch(p, 0, 0);
 	*out = p;
 	return 0;
 	}
@@ -178,6 +201,12 @@ void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p)
 
 int hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_cta)
 	{
+	if(p->fast_id>=0)
+		{
+		/* the launch shape of the size-specialised kernel is what matters for this pattern */
+		fast_launch(p, ctas_per_sm, warps_per_cta);
+		return 0;
+		}
 	default_launch(p, ctas_per_sm, warps_per_cta);
 	if(p->smem_cta>227*1024) { fprintf(stderr, "hpmpc_b200: %d warps need %d bytes of shared memory\n", p->warps, p->smem_cta); default_launch(p, 0, 0); return -2; }
 	return 0;
@@ -189,6 +218,11 @@ void hpmpc_b200_ocp_sizes(const hpmpc_b200_ocp *p, hpmpc_b200_sizes *o)
 	o->lam_stride = p->lam_stride; o->L_stride = p->dims.L_stride; o->ipm_work_stride = hb_ipm_work_doubles(&p->dims);
 	o->N = p->N; o->nzM = p->dims.nzM; o->nxM = p->dims.nxM; o->nbtot = p->dims.nbtot;
 	o->grid = p->grid; o->warps_per_cta = p->warps; o->n_slots = p->n_slots; o->smem_per_cta = p->smem_cta;
+	o->fast_variant = p->fast_id;
+	if(p->fast_id>=0)
+		{
+		o->grid = p->f_grid; o->warps_per_cta = p->f_warps; o->n_slots = p->f_grid*p->f_warps*p->f_ipw; o->smem_per_cta = p->f_smem_cta;
+		}
 	}
 
 void hpmpc_b200_ocp_stage_offsets(const hpmpc_b200_ocp *p, int n, int *off_BAbt, int *off_RSQ, int *off_d,
@@ -268,6 +302,13 @@ int hpmpc_b200_d_back_ric_rec_sv_batch(hpmpc_b200_ocp *p, long long n_inst, cons
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
+	if(p->fast_id>=0 && d_Pb==NULL)
+		{
+		long long groups = (n_inst + p->f_ipw - 1)/p->f_ipw, need = (groups + p->f_warps - 1)/p->f_warps;
+		int grid = (int)(need<p->f_grid ? need : p->f_grid);
+		if(ensure_scratch(p, sizeof(double)*(size_t)p->f_grid*p->f_warps*p->f_ipw*p->f_stash_inst)) return -1;
+		return hb_launch_ric_sv_fast(p->fast_id, &p->dims, n_inst, d_in, d_ux, d_pi, p->scratch, grid, p->f_warps, stream);
+		}
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*p->dims.L_stride)) return -1;
 	return hb_launch_ric_sv(&p->dims, n_inst, d_in, d_ux, d_pi, d_Pb, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
 	}
@@ -348,7 +389,11 @@ int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst,
 	const size_t ux_b = sizeof(double)*(size_t)cs*p->dims.ux_stride, pi_b = sizeof(double)*(size_t)cs*p->dims.pi_stride;
 	if(ensure_staging(p, in_b, ux_b+pi_b)) return -1;
 	/* each stream owns its own slice of the scratch slots: both chunks can be in flight */
-	if(ensure_scratch(p, sizeof(double)*(size_t)2*p->n_slots*p->dims.L_stride)) return -1;
+	{
+	size_t gen = sizeof(double)*(size_t)2*p->n_slots*p->dims.L_stride;
+	size_t fst = p->fast_id>=0 ? sizeof(double)*(size_t)2*p->f_grid*p->f_warps*p->f_ipw*p->f_stash_inst : 0;
+	if(ensure_scratch(p, gen>fst ? gen : fst)) return -1;
+	}
 	long long done; int k = 0;
 	for(done=0; done<n_inst; done+=cs, k^=1)
 		{
@@ -356,7 +401,14 @@ int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst,
 		cudaStream_t st = p->s_copy[k];
 		double *d_in = p->stage_in[k], *d_ux = p->stage_out[k], *d_pi = d_ux + (size_t)cs*p->dims.ux_stride;
 		CK(cudaMemcpyAsync(d_in, h_in + (size_t)done*p->dims.in_stride, sizeof(double)*(size_t)m*p->dims.in_stride, cudaMemcpyHostToDevice, st));
-		if(hb_launch_ric_sv(&p->dims, m, d_in, d_ux, d_pi, NULL, p->scratch + (size_t)k*p->n_slots*p->dims.L_stride,
+		if(p->fast_id>=0)
+			{
+			long long groups = (m + p->f_ipw - 1)/p->f_ipw, need = (groups + p->f_warps - 1)/p->f_warps;
+			int grid = (int)(need<p->f_grid ? need : p->f_grid);
+			if(hb_launch_ric_sv_fast(p->fast_id, &p->dims, m, d_in, d_ux, d_pi,
+					p->scratch + (size_t)k*p->f_grid*p->f_warps*p->f_ipw*p->f_stash_inst, grid, p->f_warps, st)) return -1;
+			}
+		else if(hb_launch_ric_sv(&p->dims, m, d_in, d_ux, d_pi, NULL, p->scratch + (size_t)k*p->n_slots*p->dims.L_stride,
 				p->n_slots, grid_for(p, m), p->warps, st)) return -1;
 		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));

@@ -37,6 +37,7 @@ typedef struct hpmpc_b200_sizes
 	long long in_stride, ux_stride, pi_stride, lam_stride, L_stride, ipm_work_stride;
 	int N, nzM, nxM, nbtot;
 	int grid, warps_per_cta, n_slots, smem_per_cta;
+	int fast_variant;          /* >= 0 when a size-specialised kernel serves this pattern */
 	} hpmpc_b200_sizes;
 
 /* nu has N entries (nu[N] is taken as 0, like the reference high-level API, c_order_interface.c:78-81);
