@@ -76,14 +76,14 @@ static void default_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps)
 static void fast_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps)
 	{
 	if(p->fast_id<0) return;
-	if(warps<=0) warps = 4;
-	while(warps>1 && warps*p->f_smem_warp>220*1024) warps--;
+	if(warps<=0) warps = 8;
+	while(warps>1 && warps*p->f_smem_warp>113*1024) warps--;
 	int smem_cta = warps*p->f_smem_warp;
 	if(ctas_per_sm<=0)
 		{
-		ctas_per_sm = (225*1024)/(smem_cta+1024);
+		ctas_per_sm = (228*1024)/(smem_cta+1024);
 		if(ctas_per_sm<1) ctas_per_sm = 1;
-		int cap = 8/warps; if(cap<1) cap = 1;            /* <= 8 resident warps per SM: keeps the factor stash near L2 size */
+		int cap = 16/warps; if(cap<1) cap = 1;           /* <= 16 resident warps per SM (128 registers per thread) */
 		if(ctas_per_sm>cap) ctas_per_sm = cap;
 		}
 	p->f_warps = warps; p->f_grid = p->sms*ctas_per_sm; p->f_smem_cta = smem_cta;

@@ -689,7 +689,7 @@ extern "C" int hb_fast_variant(int N, const int *nx, const int *nu)
 	{
 	for(int id=0; id<HBF_NVAR; id++)
 		{
-		int ok = (nx[0]==0) && N>=2;
+		int ok = (nx[0]==0) && N>=3;
 		for(int n=0; n<N && ok; n++) ok = (nu[n]==hbf_shapes[id][1]) && (n==0 || nx[n]==hbf_shapes[id][0]);
 		ok = ok && nx[N]==hbf_shapes[id][0];
 		if(ok) return id;
