@@ -25,6 +25,17 @@
 #include "layout.h"
 
 #define HBF_FULL 0xffffffffu
+#ifdef HBF_TIMING
+/* debug build only (make dbg): warp 0 of the grid records clock64() at phase boundaries */
+__device__ long long *hbf_dbg = nullptr;
+__device__ int hbf_dbg_n = 0;
+#define HBF_STAMP(tag) do { if(gw==0 && lane==0 && hbf_dbg!=nullptr && hbf_dbg_n<4000) { hbf_dbg[2*hbf_dbg_n] = (tag); hbf_dbg[2*hbf_dbg_n+1] = clock64(); hbf_dbg_n++; } } while(0)
+#else
+#define HBF_STAMP(tag) do { } while(0)
+#endif
+#ifndef HBF_RSQRT_ITERS
+#define HBF_RSQRT_ITERS 2
+#endif
 
 template<int NX_, int NU_, int G_>
 struct hbf_cfg
@@ -52,6 +63,7 @@ struct hbf_cfg
 	static constexpr int VEC = even(NU) + 3*XS;                              /* u, x (two slots), tmp */
 	static constexpr int PER_INST = IOB + 2*LBUF + VEC;                      /* doubles of smem per instance */
 	static constexpr int PER_WARP = IPW*PER_INST + 8;                        /* + mbarriers (8 doubles) */
+	static constexpr int MINB = (CO+2*NX>48) ? 1 : 2;                        /* 2 CTAs of 8 warps per SM = 128 registers per thread */
 	};
 
 /* ---- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ---- */
@@ -94,8 +106,10 @@ __device__ __forceinline__ double hbf_rsqrt(double p)
 	y = fma(y, e, y);
 	t = h*y; e = fma(-t, y, 0.5);
 	y = fma(y, e, y);
+#if HBF_RSQRT_ITERS>2
 	t = h*y; e = fma(-t, y, 0.5);
 	y = fma(y, e, y);
+#endif
 	return y;
 	}
 
@@ -249,31 +263,18 @@ __device__ __forceinline__ void hbf_back_assemble(int l, int kind, double *__res
 	for(int m=0; m<NX; m++) acc = fma(w[m], w[m], acc);
 	T.hd = acc;
 	}
+	/* m outer, k inner: CO independent accumulator chains keep the FP64 pipe busy */
+	constexpr int KS = (RO>CO) ? CO : CO-1;     /* off-diagonal columns that some row-owned row uses */
 	#pragma unroll
-	for(int k=0; k<CO-1; k++)           /* column CO-1 is nobody's off-diagonal among row-owned rows unless RO > CO */
+	for(int m=0; m<NX; m+=2)
 		{
-		double acc0 = T.Hrow[k], acc1 = 0.0;
 		#pragma unroll
-		for(int m=0; m<NX; m+=2)
+		for(int k=0; k<KS; k++)
 			{
 			const double2 t = *reinterpret_cast<const double2*>(sW + k*LDW + m);
-			acc0 = fma(w[m], t.x, acc0);
-			acc1 = fma(w[m+1], t.y, acc1);
+			T.Hrow[k] = fma(w[m], t.x, T.Hrow[k]);
+			T.Hrow[k] = fma(w[m+1], t.y, T.Hrow[k]);
 			}
-		T.Hrow[k] = acc0 + acc1;
-		}
-	if(RO>CO)
-		{
-		constexpr int k = CO-1;
-		double acc0 = T.Hrow[k], acc1 = 0.0;
-		#pragma unroll
-		for(int m=0; m<NX; m+=2)
-			{
-			const double2 t = *reinterpret_cast<const double2*>(sW + k*LDW + m);
-			acc0 = fma(w[m], t.x, acc0);
-			acc1 = fma(w[m+1], t.y, acc1);
-			}
-		T.Hrow[k] = acc0 + acc1;
 		}
 	if(E>0)
 		{
@@ -493,7 +494,7 @@ __device__ __forceinline__ void hbf_final_pi(int l, const double *__restrict__ L
 /* kernel: persistent warps, IPW instances per warp                                                  */
 /* ------------------------------------------------------------------------------------------------ */
 template<class C>
-__global__ void __launch_bounds__(256) hbf_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+__global__ void __launch_bounds__(256, C::MINB) hbf_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
 		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ stash)
 	{
 	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF, IOB = C::IOB, BAB = C::BAB;
@@ -583,13 +584,18 @@ __global__ void __launch_bounds__(256) hbf_ric_sv_kernel(hb_dims d, long long n_
 			double *Lc = (n&1) ? Lb1 : Lb0;
 			const double *Lp = (n&1) ? Lb0 : Lb1;
 			hbf_tile<C> T;
+			HBF_STAMP(100);
 			wait_bar(0);
+			HBF_STAMP(101);
 			hbf_back_assemble<C>(l, kind, io, rsq_off, Lp, T);
+			HBF_STAMP(102);
 			if(n>0) issue_backward(n-1);                          /* lands while the factorization runs */
 			/* the factor of stage n+2 was stored from this buffer: that bulk store must have finished reading smem */
 			if(lane==0) hbf_bulk_wait_read<1>();
 			__syncwarp();
+			HBF_STAMP(103);
 			hbf_back_factor<C>(l, T, Lc);
+			HBF_STAMP(104);
 			hbf_fence_async();
 			__syncwarp();
 			if(lane==0)
@@ -616,11 +622,14 @@ __global__ void __launch_bounds__(256) hbf_ric_sv_kernel(hb_dims d, long long n_
 			const double *Ln = (n&1) ? Lb1 : Lb0;
 			const double *xs = (n&1) ? xs1 : xs0;
 			double *xo = (n&1) ? xs0 : xs1;
+			HBF_STAMP(200);
 			if(n>=2) wait_bar(2+(n&1));                           /* L_n (n = 0, 1 are still resident from the backward sweep) */
 			wait_bar(n&1);                                        /* [B A b]'_n */
+			HBF_STAMP(201);
 			const int o_ux = (n==0) ? 0 : NU + (n-1)*NUX, o_ux1 = NU + n*NUX + ((n+1<N) ? NU : 0);
 			hbf_stage_forward<C>(l, kind, n>0, io + (n&1)*BAB, Ln, us, xs, xo, tmp, xreg,
 					ux + o_ux, ux + o_ux1, pi + (n-1)*NX, active);
+			HBF_STAMP(202);
 			/* both buffers of parity n are free now: prefetch stage n+2 */
 			if(n+2<=N) issue_L(n+2, n&1);
 			if(n+2<N) issue_BAbt(n+2, n&1);

@@ -737,3 +737,13 @@ extern "C" int hb_launch_ric_sv_fast(int id, const hb_dims *d, long long n_inst,
 		}
 	return -2;
 	}
+
+#ifdef HBF_TIMING
+extern "C" int hb_debug_timing(long long *d_buf)
+	{
+	int zero = 0;
+	HB_CK(cudaMemcpyToSymbol(hbf_dbg, &d_buf, sizeof(d_buf)));
+	HB_CK(cudaMemcpyToSymbol(hbf_dbg_n, &zero, sizeof(int)));
+	return 0;
+	}
+#endif
