@@ -1,0 +1,765 @@
+/*
+ * ric_blk.cuh -- register-blocked, size-specialised Riccati factor+solve for sm_100a.
+ *
+ * G lanes work on one OCP instance (32/G instances per warp) and every lane owns R rows of the stage's
+ * (NU+NX+1) x (NU+NX) trapezoid, so one shared-memory broadcast operand feeds R FP64 FMAs and the per-column
+ * overhead of the Cholesky (reciprocal square root, shuffles, barriers) is shared by 32/G instances.
+ * ncu on the one-row-per-lane kernel (ric_fast.cuh) showed the shared-memory data pipe at 74-86 % and only
+ * 37 % of the issued instructions being FP64 math; this mapping halves the LDS count per FMA (R = 2) and the
+ * overhead per instance (G = 8 instead of 16 for nx = 12, nu = 5).
+ *
+ * Frame = NZ x NUX trapezoid, NZ = NU+NX+1, virtual row v = l + s*G (lane l, slot s < R):
+ *   rows v < RO = min(NZ, G*R)       "row-owned": H[s][k] (k < v) and the diagonal hd[s] live in registers of lane l
+ *   rows RO..NZ-1 (E of them)        "column-owned": entry (row, c) lives on lane c%G, slot c/G  (c < CO = min(NUX, G*R))
+ *   columns CO..NUX-1 (NCC)          the E x NCC corner is replicated on every lane
+ *
+ * What leaves the backward sweep for the forward sweep ("stash", written with one bulk store per stage) is not the
+ * whole factor but the part the forward sweep needs, in the form it needs it:
+ *   K = -Luu^-T Lxu'  (NU x NX),  k = -Luu^-T l_u,  the packed columns of Lxx with l_x appended
+ * so the forward stage is three small matrix-vector products and no triangular solve:
+ *   u_n = k + K x_n ,  x_{n+1} = b + B u + A x ,  pi_n = Lxx (Lxx' x_n + l_x)
+ *
+ * Restates (reference paths relative to /root/reference):
+ *   backward stage   lqcp_solvers/d_back_ric_rec.c:236-333      (dtrmm_nt_u, gradient-row add, dsyrk_dpotrf)
+ *   pivot rule       kernel/c99/kernel_dpotrf_c99_lib4.c:553-573 (pivot <= 1e-15 -> zero column)
+ *   forward stage    lqcp_solvers/d_back_ric_rec.c:341-397      (dtrsv_t + dgemv_t, dtrmv_u_n / dtrmv_u_t for pi)
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "layout.h"
+#include "ric_fast.cuh"          /* PTX helpers (mbarrier, bulk copies), stage kinds */
+
+template<int NX_, int NU_, int G_, int R_>
+struct hbk_cfg
+	{
+	static constexpr int NX = NX_, NU = NU_, G = G_, R = R_;
+	static constexpr int NUX = NX+NU, NZ = NUX+1;
+	static constexpr int GR = G*R;
+	static constexpr int RO = NZ<GR ? NZ : GR;
+	static constexpr int E = NZ-RO;
+	static constexpr int CO = NUX<GR ? NUX : GR;
+	static constexpr int NCC = NUX-CO;
+	static constexpr int IPW = 32/G;
+	__host__ __device__ static constexpr int even(int x) { return (x+1)&~1; }
+	/* u-columns of L (c < NU): column c holds rows c..NZ-1 */
+	__host__ __device__ static constexpr int uOff(int c) { int o = 0; for(int j=0; j<c; j++) o += even(NZ-j); return o; }
+	/* x-columns of L (j < NX, frame column NU+j): rows NU+j..NZ-1, i.e. Lxx[j..NX-1][j] then l_x[j] */
+	__host__ __device__ static constexpr int xOff(int j) { int o = 0; for(int i=0; i<j; i++) o += even(NX+1-i); return o; }
+	static constexpr int UDINV = uOff(NU);                                   /* inverse diagonal of the u-columns */
+	static constexpr int LU = uOff(NU) + even(NU);                           /* scratch: u-columns + their inverse diagonal */
+	/* stash image of one stage */
+	static constexpr int SK = 0;                                             /* K, NU x NX row-major */
+	static constexpr int Sk = even(NU*NX);                                   /* k */
+	static constexpr int SX = Sk + even(NU);                                 /* x-columns */
+	static constexpr int SB = SX + xOff(NX);
+	static constexpr int LDW = ((even(NX)/2)%2==0) ? even(NX)+2 : even(NX);
+	static constexpr int BAB = even(NZ*NX);
+	static constexpr int RSQ = even(HB_TRI(NUX)+NUX);
+	static constexpr int INB = BAB + RSQ;
+	static constexpr int WSZ = even(NZ*LDW);
+	__host__ __device__ static constexpr int max3(int a, int b, int c) { return a>b ? (a>c ? a : c) : (b>c ? b : c); }
+	static constexpr int IOB = max3(INB, WSZ, 2*BAB);
+	static constexpr int XS = even(NX);
+	static constexpr int VEC = even(NU) + 3*XS;
+	static constexpr int PER_INST = IOB + LU + 2*SB + VEC;
+	static constexpr int PER_WARP = IPW*PER_INST + 8;
+	static constexpr int KS = (RO>CO) ? CO : CO-1;                           /* off-diagonal columns some row-owned row uses */
+	static_assert(NX%2==0, "NX must be even (16-byte rows)");
+	static_assert(NU<=GR && NX<GR, "one u-column / x-column (and the gradient) per lane slot");
+	};
+
+/* sqrt and 1/sqrt of p: hardware seed + two coupled (Goldschmidt) steps; dependent depth 5 instead of 7 */
+__device__ __forceinline__ void hbk_sqrt_rsqrt(double p, double &sq, double &rs)
+	{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+	double g = p*y, h = 0.5*y;
+	double r = fma(-g, h, 0.5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	r = fma(-g, h, 0.5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	r = fma(-g, h, 0.5);                 /* third correction on h only: keeps the result within ~1 ulp */
+	h = fma(h, r, h);
+	sq = g; rs = h+h;
+	}
+
+template<class C, int KIND>
+__device__ __forceinline__ constexpr int hbk_arow(int f)
+	{
+	if(KIND==HBF_MID) return f;
+	if(f<C::NU) return KIND==HBF_FIRST ? f : -1;
+	if(f<C::NUX) return KIND==HBF_LAST ? f - C::NU : -1;
+	return KIND==HBF_FIRST ? C::NU : C::NX;
+	}
+
+template<class C>
+struct hbk_tile
+	{
+	double H[C::R][C::CO];                                /* H[s][k]: row l+s*G, column k (meaningful for k < row) */
+	double hd[C::R];                                      /* own diagonals */
+	double X[C::E>0 ? C::E : 1][C::R];                    /* column-owned entries of the extra rows */
+	double Z[C::E>0 ? C::E : 1][C::NCC>0 ? C::NCC : 1];   /* replicated corner */
+	};
+
+/* per-thread constants: offsets of the columns this lane owns */
+template<class C>
+struct hbk_lane
+	{
+	int l;
+	int uo[C::R];        /* uOff(c), c = l+s*G (u-column), 0 when c >= NU */
+	int xo[C::R];        /* xOff(j), j = l+s*G (x-column), 0 when j >= NX */
+	__device__ __forceinline__ void init(int l_)
+		{
+		l = l_;
+		#pragma unroll
+		for(int s=0; s<C::R; s++)
+			{
+			uo[s] = 0; xo[s] = 0;
+			#pragma unroll
+			for(int c=0; c<C::NU; c++) if(c==l+s*C::G) uo[s] = C::uOff(c);
+			#pragma unroll
+			for(int j=0; j<C::NX; j++) if(j==l+s*C::G) xo[s] = C::xOff(j);
+			}
+		}
+	};
+
+/* pointer to column c of the factor being built: u-columns in the scratch, x-columns in the stash image */
+template<class C>
+__device__ __forceinline__ double *hbk_col(int c, double *LUs, double *Sc)
+	{
+	return c<C::NU ? LUs + C::uOff(c) : Sc + C::SX + C::xOff(c-C::NU);
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* backward stage, part 1: H <- RSQrq_n + W W',  W = [B A b]'_n Lxx_{n+1}  (io: inputs in, W scratch) */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C, int KIND>
+__device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double *__restrict__ io, const double *__restrict__ Sp,
+		hbk_tile<C> &T)
+	{
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, G = C::G, R = C::R, RO = C::RO, E = C::E, CO = C::CO, NCC = C::NCC, LDW = C::LDW;
+	constexpr int rsq_off = (KIND==HBF_FIRST) ? C::even((NU+1)*NX) : (KIND==HBF_LAST ? 0 : C::BAB);
+	const int l = ln.l;
+	const double *sB = io, *sQ = io + rsq_off;
+	double w[R][NX];
+	double wx[E>0 ? E : 1][R];
+	if(KIND!=HBF_LAST)
+		{
+		const double *xc = Sp + C::SX;                            /* x-columns of L_{n+1}: col j at xOff(j), [k-j] = Lxx[k][j], [NX-j] = l_x[j] */
+		/* ---- W = [B A b]' Lxx' : own rows ---- */
+		double a[R][NX];
+		#pragma unroll
+		for(int s=0; s<R; s++)
+			{
+			const int v = l + s*G;
+			int ar = -1;
+			if(KIND==HBF_MID) ar = (v<RO) ? v : -1;
+			else ar = (v<NU) ? v : ((v==NUX && v<RO) ? NU : -1);              /* FIRST: B' rows and the b row */
+			#pragma unroll
+			for(int k=0; k<NX; k+=2)
+				{
+				double2 t = make_double2(0.0, 0.0);
+				if(ar>=0) t = *reinterpret_cast<const double2*>(sB + ar*NX + k);
+				a[s][k] = t.x; a[s][k+1] = t.y;
+				}
+			}
+		#pragma unroll
+		for(int j=0; j<NX; j++)
+			{
+			const double *col = xc + C::xOff(j);
+			double acc[R][2];
+			#pragma unroll
+			for(int s=0; s<R; s++) { acc[s][0] = 0.0; acc[s][1] = 0.0; }
+			#pragma unroll
+			for(int k=j; k<NX; k+=2)
+				{
+				const double2 t = *reinterpret_cast<const double2*>(col + (k-j));
+				#pragma unroll
+				for(int s=0; s<R; s++)
+					{
+					acc[s][0] = fma(a[s][k], t.x, acc[s][0]);
+					if(k+1<NX) acc[s][1] = fma(a[s][k+1], t.y, acc[s][1]);
+					}
+				}
+			#pragma unroll
+			for(int s=0; s<R; s++) w[s][j] = acc[s][0] + acc[s][1];
+			if(E==0)                    /* gradient row is row-owned: add l_x' */
+				{
+				const double lx = col[NX-j];
+				#pragma unroll
+				for(int s=0; s<R; s++) if(l+s*G==NUX) w[s][j] += lx;
+				}
+			}
+		/* ---- extra rows: lane owns columns j = l+s*G of them ---- */
+		if(E>0)
+			{
+			#pragma unroll
+			for(int s=0; s<R; s++)
+				{
+				const int j = l + s*G;
+				#pragma unroll
+				for(int e=0; e<E; e++) wx[e][s] = 0.0;
+				if(s*G<NX)
+					{
+					const double *col = xc + ln.xo[s] - (j<NX ? j : 0);      /* col[k] = Lxx[k][j], k >= j */
+					#pragma unroll
+					for(int k=s*G; k<NX; k++)
+						{
+						const double lkj = (j<NX && k>=j) ? col[k] : 0.0;
+						#pragma unroll
+						for(int e=0; e<E; e++)
+							{
+							constexpr int dummy = 0; (void)dummy;
+							const int ae = hbk_arow<C, KIND>(RO+e);
+							const double b = (ae>=0) ? sB[ae*NX + k] : 0.0;
+							wx[e][s] = fma(b, lkj, wx[e][s]);
+							}
+						}
+					if(j<NX) wx[E-1][s] += col[NX];                          /* gradient row: + l_x[j] */
+					}
+				}
+			}
+		}
+	/* ---- H <- RSQrq (before W is stored: with LDW > NX the W rows run over the RSQ part of the buffer) ---- */
+	#pragma unroll
+	for(int s=0; s<R; s++)
+		{
+		const int v = l + s*G;
+		int ar = -1;
+		if(v<RO)
+			{
+			if(KIND==HBF_MID) ar = v;
+			else if(KIND==HBF_FIRST) ar = (v<NU) ? v : (v==NUX ? NU : -1);
+			else ar = (v<NU) ? -1 : v-NU;                                    /* LAST: rows NU.. map to 0.. ; gradient row NUX -> NX */
+			}
+		const double *row = sQ + HB_TRI(ar>=0 ? ar : 0);
+		#pragma unroll
+		for(int k=0; k<CO; k++)
+			{
+			if(k < (s+1)*G-1 && k<C::KS)
+				{
+				constexpr int dummy = 0; (void)dummy;
+				const int ak = hbk_arow<C, KIND>(k);
+				T.H[s][k] = (k<v && ar>=0 && ak>=0) ? row[ak>=0 ? ak : 0] : 0.0;
+				}
+			else T.H[s][k] = 0.0;
+			}
+		T.hd[s] = (v<CO && ar>=0) ? row[ar>=0 ? ar : 0] : 1.0;
+		#pragma unroll
+		for(int e=0; e<E; e++)
+			{
+			const int ae = hbk_arow<C, KIND>(RO+e);
+			int ac = -1;
+			if(v<CO)
+				{
+				if(KIND==HBF_MID) ac = v;
+				else if(KIND==HBF_FIRST) ac = (v<NU) ? v : -1;
+				else ac = (v<NU) ? -1 : v-NU;
+				}
+			T.X[e][s] = (ae>=0 && ac>=0) ? sQ[HB_TRI(ae>=0 ? ae : 0) + (ac>=0 ? ac : 0)] : 0.0;
+			}
+		}
+	#pragma unroll
+	for(int e=0; e<E; e++)
+		#pragma unroll
+		for(int cc=0; cc<NCC; cc++)
+			{
+			const int ae = hbk_arow<C, KIND>(RO+e), acol = hbk_arow<C, KIND>(CO+cc);
+			double hc = (e==cc) ? 1.0 : 0.0;
+			if(e>=cc && ae>=0 && acol>=0) hc = sQ[HB_TRI(ae>=0 ? ae : 0) + (acol>=0 ? acol : 0)];
+			T.Z[e][cc] = hc;
+			}
+	if(KIND==HBF_LAST) { __syncwarp(); return; }
+	{
+	__syncwarp();                       /* every lane has read its inputs: the buffer becomes W */
+		double *sW = io;
+		#pragma unroll
+		for(int s=0; s<R; s++)
+			{
+			const int v = l + s*G;
+			if(v<RO)
+				{
+				#pragma unroll
+				for(int j=0; j<NX; j+=2) *reinterpret_cast<double2*>(sW + v*LDW + j) = make_double2(w[s][j], w[s][j+1]);
+				}
+			if(E>0 && v<NX)
+				{
+				#pragma unroll
+				for(int e=0; e<E; e++) sW[(RO+e)*LDW + v] = wx[e][s];
+				}
+			}
+	}
+	__syncwarp();
+	/* ---- H += W W' ---- */
+	const double *sW = io;
+	#pragma unroll
+	for(int s=0; s<R; s++)
+		{
+		double acc = T.hd[s];
+		#pragma unroll
+		for(int m=0; m<NX; m++) acc = fma(w[s][m], w[s][m], acc);
+		T.hd[s] = acc;
+		}
+	#pragma unroll
+	for(int m=0; m<NX; m+=2)
+		{
+		#pragma unroll
+		for(int k=0; k<C::KS; k++)
+			{
+			const double2 t = *reinterpret_cast<const double2*>(sW + k*LDW + m);
+			#pragma unroll
+			for(int s=0; s<R; s++)
+				if(k < (s+1)*G-1)
+					{
+					T.H[s][k] = fma(w[s][m], t.x, T.H[s][k]);
+					T.H[s][k] = fma(w[s][m+1], t.y, T.H[s][k]);
+					}
+			}
+		}
+	if(E>0)
+		{
+		double wr[E>0 ? E : 1][NX];
+		#pragma unroll
+		for(int e=0; e<E; e++)
+			{
+			double acc[R][2];
+			#pragma unroll
+			for(int s=0; s<R; s++) { acc[s][0] = T.X[e][s]; acc[s][1] = 0.0; }
+			#pragma unroll
+			for(int m=0; m<NX; m+=2)
+				{
+				const double2 t = *reinterpret_cast<const double2*>(sW + (RO+e)*LDW + m);
+				wr[e][m] = t.x; wr[e][m+1] = t.y;
+				#pragma unroll
+				for(int s=0; s<R; s++)
+					{
+					acc[s][0] = fma(w[s][m], t.x, acc[s][0]);
+					acc[s][1] = fma(w[s][m+1], t.y, acc[s][1]);
+					}
+				}
+			#pragma unroll
+			for(int s=0; s<R; s++) T.X[e][s] = acc[s][0] + acc[s][1];
+			}
+		#pragma unroll
+		for(int e=0; e<E; e++)
+			#pragma unroll
+			for(int cc=0; cc<NCC; cc++)
+				if(e>=cc)
+					{
+					double acc = T.Z[e][cc];
+					#pragma unroll
+					for(int m=0; m<NX; m++) acc = fma(wr[e][m], wr[cc][m], acc);
+					T.Z[e][cc] = acc;
+					}
+		}
+	__syncwarp();                       /* W is dead: the caller may refill the buffer */
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* backward stage, part 2: right-looking Cholesky, look-ahead diagonal; column c is finished on lane  */
+/* c%G (slot c/G) and broadcast through shared memory.  Then K, k for the forward sweep.               */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C, int KIND>
+__device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<C> &T, double *__restrict__ LUs, double *__restrict__ Sc)
+	{
+	constexpr int NX = C::NX, NU = C::NU, NZ = C::NZ, G = C::G, R = C::R, RO = C::RO, E = C::E, CO = C::CO, NCC = C::NCC;
+	const int l = ln.l;
+	#pragma unroll
+	for(int c=0; c<CO; c++)
+		{
+		constexpr int dummy = 0; (void)dummy;
+		const int so = c/G, lo = c%G;
+		/* the owner's diagonal is final here; every lane runs the same instruction stream on its own hd[so] */
+		double sq, rs;
+		hbk_sqrt_rsqrt(T.hd[so], sq, rs);
+		if(!(T.hd[so]>1e-15)) { rs = 0.0; sq = 0.0; }
+		const double inv = __shfl_sync(HBF_FULL, rs, lo, G);
+		double lc[R];
+		#pragma unroll
+		for(int s=0; s<R; s++) lc[s] = 0.0;
+		#pragma unroll
+		for(int s=so; s<R; s++)
+			{
+			const int v = l + s*G;
+			lc[s] = (s==so && v==c) ? sq : T.H[s][c<C::KS ? c : 0]*inv;      /* owner: sqrt(p) ; rows > c: L[v][c] */
+			if(s>so || v>c) T.hd[s] = fma(-lc[s], lc[s], T.hd[s]);          /* look-ahead: next pivots do not wait for smem */
+			}
+		double *col = hbk_col<C>(c, LUs, Sc);
+		#pragma unroll
+		for(int s=so; s<R; s++)
+			{
+			const int v = l + s*G;
+			if((s>so || v>=c) && v<RO) col[v-c] = lc[s];
+			}
+		if(l==lo)
+			{
+			#pragma unroll
+			for(int e=0; e<E; e++) col[RO+e-c] = T.X[e][so]*inv;
+			if(c<NU) LUs[C::UDINV+c] = inv;
+			}
+		__syncwarp();
+		#pragma unroll
+		for(int q=0; c+2*q<C::KS; q++)
+			{
+			const double2 t = *reinterpret_cast<const double2*>(col + 2*q);
+			const int k0 = c+2*q, k1 = k0+1;
+			#pragma unroll
+			for(int s=so; s<R; s++)
+				{
+				if(q>0 && k0<C::KS && k0 < (s+1)*G-1) T.H[s][k0] = fma(-lc[s], t.x, T.H[s][k0]);
+				if(k1<C::KS && k1 < (s+1)*G-1) T.H[s][k1] = fma(-lc[s], t.y, T.H[s][k1]);
+				}
+			}
+		if(E>0)
+			{
+			double le[E>0 ? E : 1];
+			#pragma unroll
+			for(int e=0; e<E; e++) le[e] = col[RO+e-c];
+			#pragma unroll
+			for(int e=0; e<E; e++)
+				{
+				#pragma unroll
+				for(int s=so; s<R; s++) T.X[e][s] = fma(-le[e], lc[s], T.X[e][s]);    /* meaningful for columns > c */
+				#pragma unroll
+				for(int cc=0; cc<NCC; cc++) if(e>=cc) T.Z[e][cc] = fma(-le[e], le[cc], T.Z[e][cc]);
+				}
+			}
+		}
+	#pragma unroll
+	for(int cc=0; cc<NCC; cc++)
+		{
+		const double p = T.Z[cc][cc];
+		double sq, rs;
+		hbk_sqrt_rsqrt(p, sq, rs);
+		if(!(p>1e-15)) { rs = 0.0; sq = 0.0; }
+		double *col = hbk_col<C>(CO+cc, LUs, Sc);
+		double lcol[E>0 ? E : 1];
+		lcol[cc] = sq;
+		#pragma unroll
+		for(int e=cc+1; e<E; e++) lcol[e] = T.Z[e][cc]*rs;
+		if(l==0)
+			{
+			#pragma unroll
+			for(int e=cc; e<E; e++) col[e-cc] = lcol[e];
+			if(CO+cc<NU) LUs[C::UDINV+CO+cc] = rs;
+			}
+		#pragma unroll
+		for(int e=cc+1; e<E; e++)
+			#pragma unroll
+			for(int c2=cc+1; c2<NCC; c2++)
+				if(e>=c2) T.Z[e][c2] = fma(-lcol[e], lcol[c2], T.Z[e][c2]);
+		}
+	__syncwarp();
+	if(KIND==HBF_LAST) return;
+	/* ---- K' rows: y Luu = -L[NU+x][0:NU]  (x = NX is the gradient row: y = k') ---- */
+	#pragma unroll
+	for(int s=0; s<R; s++)
+		{
+		const int x = l + s*G;
+		if(s*G<=NX)
+			{
+			double y[NU];
+			#pragma unroll
+			for(int c=0; c<NU; c++) y[c] = (x<=NX) ? -LUs[C::uOff(c) + (NU+x-c)] : 0.0;
+			#pragma unroll
+			for(int c=NU-1; c>=0; c--)
+				{
+				y[c] *= LUs[C::UDINV+c];
+				#pragma unroll
+				for(int c2=0; c2<c; c2++) y[c2] = fma(-y[c], LUs[C::uOff(c2) + (c-c2)], y[c2]);
+				}
+			if(x<NX)
+				{
+				#pragma unroll
+				for(int c=0; c<NU; c++) Sc[C::SK + c*NX + x] = y[c];
+				}
+			else if(x==NX)
+				{
+				#pragma unroll
+				for(int c=0; c<NU; c++) Sc[C::Sk + c] = y[c];
+				}
+			}
+		}
+	__syncwarp();
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* forward stage n: u_n = k + K x_n ; x_{n+1} = b + B u + A x ; pi_{n-1} = Lxx (Lxx' x_n + l_x)       */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C, int KIND>
+__device__ __forceinline__ void hbk_stage_forward(const hbk_lane<C> &ln, const double *__restrict__ sB, const double *__restrict__ Sn,
+		double *__restrict__ us, const double *__restrict__ xs, double *__restrict__ xo, double *__restrict__ tmp,
+		double *__restrict__ g_u, double *__restrict__ g_x1, double *__restrict__ g_pi, bool active)
+	{
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, G = C::G, R = C::R;
+	const int l = ln.l;
+	const double *xc = Sn + C::SX;
+	/* ---- phase A ---- */
+	#pragma unroll
+	for(int s=0; s<R; s++)
+		{
+		const int i = l + s*G;
+		if(s*G<NU && i<NU)
+			{
+			double t0 = Sn[C::Sk + i], t1 = 0.0;
+			if(KIND!=HBF_FIRST)
+				{
+				const double *Kr = Sn + C::SK + i*NX;
+				#pragma unroll
+				for(int k=0; k<NX; k+=2)
+					{
+					const double2 kk = *reinterpret_cast<const double2*>(Kr + k);
+					const double2 xx = *reinterpret_cast<const double2*>(xs + k);
+					t0 = fma(kk.x, xx.x, t0); t1 = fma(kk.y, xx.y, t1);
+					}
+				}
+			const double u = t0 + t1;
+			us[i] = u;
+			if(active) g_u[i] = u;
+			}
+		if(KIND!=HBF_FIRST && s*G<NX && i<NX)
+			{
+			const double *col = xc + ln.xo[s] - i;                          /* col[k] = Lxx[k][i] */
+			double a0 = col[NX], a1 = 0.0;
+			#pragma unroll
+			for(int k=s*G; k<NX; k+=2)
+				{
+				if(k>=i) a0 = fma(col[k], xs[k], a0);
+				if(k+1>=i && k+1<NX) a1 = fma(col[k+1], xs[k+1], a1);
+				}
+			tmp[i] = a0 + a1;
+			}
+		}
+	__syncwarp();
+	/* ---- phase B ---- */
+	#pragma unroll
+	for(int s=0; s<R; s++)
+		{
+		const int j = l + s*G;
+		if(s*G<NX && j<NX)
+			{
+			constexpr int brow = (KIND==HBF_FIRST) ? NU : NUX;
+			double x0 = sB[brow*NX + j], x1 = 0.0, x2 = 0.0;
+			#pragma unroll
+			for(int i=0; i<NU; i++) x0 = fma(sB[i*NX+j], us[i], x0);
+			if(KIND!=HBF_FIRST)
+				{
+				#pragma unroll
+				for(int i=0; i<NX; i+=2) { x1 = fma(sB[(NU+i)*NX+j], xs[i], x1); x2 = fma(sB[(NU+i+1)*NX+j], xs[i+1], x2); }
+				}
+			const double xn = x0 + (x1+x2);
+			xo[j] = xn;
+			if(active) g_x1[j] = xn;
+			if(KIND!=HBF_FIRST)
+				{
+				double p0 = 0.0, p1 = 0.0;
+				#pragma unroll
+				for(int cc=0; cc<NX; cc+=2)
+					{
+					if(cc<(s+1)*G && cc<=j) p0 = fma(xc[C::xOff(cc) + (j-cc)], tmp[cc], p0);
+					if(cc+1<(s+1)*G && cc+1<=j) p1 = fma(xc[C::xOff(cc+1) + (j-cc-1)], tmp[cc+1], p1);
+					}
+				if(active) g_pi[j] = p0+p1;
+				}
+			}
+		}
+	__syncwarp();
+	}
+
+/* pi_{N-1} from x_N and the x-columns of L_N */
+template<class C>
+__device__ __forceinline__ void hbk_final_pi(const hbk_lane<C> &ln, const double *__restrict__ Sn, const double *__restrict__ xs,
+		double *__restrict__ tmp, double *__restrict__ g_pi, bool active)
+	{
+	constexpr int NX = C::NX, G = C::G, R = C::R;
+	const int l = ln.l;
+	const double *xc = Sn + C::SX;
+	#pragma unroll
+	for(int s=0; s<R; s++)
+		{
+		const int i = l + s*G;
+		if(s*G<NX && i<NX)
+			{
+			const double *col = xc + ln.xo[s] - i;
+			double a0 = col[NX];
+			#pragma unroll
+			for(int k=s*G; k<NX; k++) if(k>=i) a0 = fma(col[k], xs[k], a0);
+			tmp[i] = a0;
+			}
+		}
+	__syncwarp();
+	#pragma unroll
+	for(int s=0; s<R; s++)
+		{
+		const int j = l + s*G;
+		if(s*G<NX && j<NX)
+			{
+			double p0 = 0.0;
+			#pragma unroll
+			for(int cc=0; cc<NX; cc++) if(cc<(s+1)*G && cc<=j) p0 = fma(xc[C::xOff(cc) + (j-cc)], tmp[cc], p0);
+			if(active) g_pi[j] = p0;
+			}
+		}
+	__syncwarp();
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernel: persistent warps, IPW instances per warp                                                  */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C>
+__global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ stash)
+	{
+	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
+	extern __shared__ __align__(16) double hbf_smem[];
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const int g = lane/G;
+	hbk_lane<C> ln; ln.init(lane%G);
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	double *wbase = hbf_smem + (size_t)warp*C::PER_WARP;
+	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);      /* [0] stage inputs / [B A b]' slot 0, [1] [B A b]' slot 1, [2..3] stash images */
+	double *ibase = wbase + 8 + (size_t)g*C::PER_INST;
+	double *io = ibase;
+	double *LUs = ibase + IOB;
+	double *S0 = LUs + LU, *S1 = S0 + SB;
+	double *us = S1 + SB, *xs0 = us + C::even(NU), *xs1 = xs0 + C::XS, *tmp = xs1 + C::XS;
+	if(lane==0)
+		{
+		for(int b=0; b<4; b++) hbf_mbar_init(&bars[b], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+	__syncwarp();
+	uint32_t phase = 0;
+	const int N = d.N;
+	const int o_in1 = d.st[1].off_BAbt, s_in = d.st[2].off_BAbt - d.st[1].off_BAbt, o_inN = d.st[N].off_BAbt;
+	constexpr uint32_t bytes_first = 8u*(uint32_t)(C::even((NU+1)*NX) + C::even(HB_TRI(NU)+NU));
+	constexpr uint32_t bytes_mid = 8u*(uint32_t)C::INB;
+	constexpr uint32_t bytes_last = 8u*(uint32_t)C::even(HB_TRI(NX)+NX);
+	const long long stash_stride = (long long)(N+1)*SB;
+	const long long n_groups = (n_inst + IPW - 1)/IPW;
+	double *stash_w = stash + gw*IPW*stash_stride;
+
+	for(long long grp=gw; grp<n_groups; grp+=tw)
+		{
+		long long inst = grp*IPW + g;
+		const bool active = inst<n_inst;
+		if(!active) inst = n_inst-1;
+		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+
+		auto issue_backward = [&](int n)                          /* [B A b]'_n | RSQrq_n -> io */
+			{
+			if(lane==0)
+				{
+				const int off = (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in);
+				const uint32_t bytes = (n==0) ? bytes_first : (n==N ? bytes_last : bytes_mid);
+				hbf_mbar_expect(&bars[0], bytes*IPW);
+				#pragma unroll
+				for(int gg=0; gg<IPW; gg++)
+					{
+					long long ii = grp*IPW + gg; if(ii>=n_inst) ii = n_inst-1;
+					hbf_bulk_g2s(wbase + 8 + (size_t)gg*C::PER_INST, in + ii*d.in_stride + off, bytes, &bars[0]);
+					}
+				}
+			};
+		auto issue_BAbt = [&](int n, int slot)                    /* forward: [B A b]'_n -> io + slot*BAB */
+			{
+			if(lane==0)
+				{
+				const int off = (n==0) ? 0 : o_in1 + (n-1)*s_in;
+				const uint32_t bytes = (n==0) ? 8u*(uint32_t)C::even((NU+1)*NX) : 8u*(uint32_t)BAB;
+				hbf_mbar_expect(&bars[slot], bytes*IPW);
+				#pragma unroll
+				for(int gg=0; gg<IPW; gg++)
+					{
+					long long ii = grp*IPW + gg; if(ii>=n_inst) ii = n_inst-1;
+					hbf_bulk_g2s(wbase + 8 + (size_t)gg*C::PER_INST + slot*BAB, in + ii*d.in_stride + off, bytes, &bars[slot]);
+					}
+				}
+			};
+		auto issue_S = [&](int n, int slot)                       /* forward: stash image of stage n -> S[slot] */
+			{
+			if(lane==0)
+				{
+				hbf_mbar_expect(&bars[2+slot], 8u*SB*IPW);
+				#pragma unroll
+				for(int gg=0; gg<IPW; gg++)
+					hbf_bulk_g2s(wbase + 8 + (size_t)gg*C::PER_INST + IOB + LU + slot*SB, stash_w + gg*stash_stride + (long long)n*SB, 8u*SB, &bars[2+slot]);
+				}
+			};
+		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
+		auto store_S = [&](int n)
+			{
+			hbf_fence_async();
+			__syncwarp();
+			if(lane==0)
+				{
+				#pragma unroll
+				for(int gg=0; gg<IPW; gg++)
+					hbf_bulk_s2g(stash_w + gg*stash_stride + (long long)n*SB, wbase + 8 + (size_t)gg*C::PER_INST + IOB + LU + (n&1)*SB, 8u*SB);
+				hbf_bulk_commit();
+				}
+			};
+
+		/* ---------------- backward sweep: stage n builds S[n&1], reads the x-columns in S[(n+1)&1] ---------------- */
+		issue_backward(N);
+		{
+		hbk_tile<C> T;
+		wait_bar(0);
+		hbk_back_assemble<C, HBF_LAST>(ln, io, nullptr, T);
+		issue_backward(N-1);
+		if(lane==0) hbf_bulk_wait_read<1>();
+		__syncwarp();
+		hbk_back_factor<C, HBF_LAST>(ln, T, LUs, (N&1) ? S1 : S0);
+		store_S(N);
+		}
+		for(int n=N-1; n>0; n--)
+			{
+			double *Sc = (n&1) ? S1 : S0;
+			const double *Sp = (n&1) ? S0 : S1;
+			hbk_tile<C> T;
+			wait_bar(0);
+			hbk_back_assemble<C, HBF_MID>(ln, io, Sp, T);
+			issue_backward(n-1);                                  /* lands while the factorization runs */
+			/* the image of stage n+2 was stored from this buffer: that bulk store must have finished reading smem */
+			if(lane==0) hbf_bulk_wait_read<1>();
+			__syncwarp();
+			hbk_back_factor<C, HBF_MID>(ln, T, LUs, Sc);
+			store_S(n);
+			}
+		{
+		hbk_tile<C> T;
+		wait_bar(0);
+		hbk_back_assemble<C, HBF_FIRST>(ln, io, S1, T);
+		if(lane==0) hbf_bulk_wait_read<1>();
+		__syncwarp();
+		hbk_back_factor<C, HBF_FIRST>(ln, T, LUs, S0);
+		store_S(0);
+		}
+		/* now: S0 = image of stage 0, S1 = image of stage 1 ; io is free */
+		if(lane==0) hbf_bulk_wait_all<0>();        /* every image is in the stash before any is read back */
+		__syncwarp();
+
+		/* ---------------- forward sweep ---------------- */
+		issue_BAbt(0, 0);
+		if(N>1) issue_BAbt(1, 1);
+		wait_bar(0);
+		hbk_stage_forward<C, HBF_FIRST>(ln, io, S0, us, xs0, xs1, tmp, ux, ux + NU + ((1<N) ? NU : 0), pi, active);
+		if(2<=N) issue_S(2, 0);
+		if(2<N) issue_BAbt(2, 0);
+		for(int n=1; n<N; n++)
+			{
+			const double *Sn = (n&1) ? S1 : S0;
+			const double *xs = (n&1) ? xs1 : xs0;
+			double *xo = (n&1) ? xs0 : xs1;
+			if(n>=2) wait_bar(2+(n&1));                           /* image n (0 and 1 are still resident from the backward sweep) */
+			wait_bar(n&1);                                        /* [B A b]'_n */
+			const int o_ux = NU + (n-1)*NUX, o_ux1 = NU + n*NUX + ((n+1<N) ? NU : 0);
+			hbk_stage_forward<C, HBF_MID>(ln, io + (n&1)*BAB, Sn, us, xs, xo, tmp, ux + o_ux, ux + o_ux1, pi + (n-1)*NX, active);
+			if(n+2<=N) issue_S(n+2, n&1);
+			if(n+2<N) issue_BAbt(n+2, n&1);
+			}
+		if(N>=2) wait_bar(2+(N&1));
+		hbk_final_pi<C>(ln, (N&1) ? S1 : S0, (N&1) ? xs1 : xs0, tmp, pi + (N-1)*NX, active);
+		}
+	}

@@ -13,9 +13,11 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "layout.h"
 #include "ric_generic.cuh"
 #include "ric_fast.cuh"
+#include "ric_blk.cuh"
 
 /* ------------------------------------------------------------------------------------------------ */
 /* sweeps                                                                                            */
@@ -675,19 +677,24 @@ extern "C" double hb_fp64_peak_probe(int device, int iters, void *stream)
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
-/* size-specialised variants (ric_fast.cuh)                                                          */
+/* size-specialised variants (ric_blk.cuh: register-blocked; ric_fast.cuh: one row per lane)          */
 /* ------------------------------------------------------------------------------------------------ */
-typedef hbf_cfg<12, 5, 16> hbf_v0;     /* BASELINE config 2: two instances per warp */
-typedef hbf_cfg<8, 3, 16> hbf_v1;      /* the reference's own test size (test_d_ip_hard.c) */
-typedef hbf_cfg<4, 2, 8> hbf_v2;       /* four instances per warp */
+typedef hbk_cfg<12, 5, 8, 2> hbk_v0;   /* BASELINE config 2: four instances per warp, two rows per lane */
+typedef hbk_cfg<8, 3, 4, 3> hbk_v1;    /* the reference's own test size (test_d_ip_hard.c): eight instances per warp */
+typedef hbk_cfg<4, 2, 4, 2> hbk_v2;    /* eight instances per warp */
 typedef hbf_cfg<24, 11, 32> hbf_v3;    /* BASELINE config 3 shape: one instance per warp, 4 column-owned rows */
-#define HBF_NVAR 4
-static const int hbf_shapes[HBF_NVAR][3] = { {12, 5, 16}, {8, 3, 16}, {4, 2, 8}, {24, 11, 32} };
+typedef hbf_cfg<12, 5, 16> hbf_v0;     /* one-row-per-lane predecessors, kept for A/B runs (HPMPC_B200_FAST_GEN=1) */
+typedef hbf_cfg<8, 3, 16> hbf_v1;
+typedef hbf_cfg<4, 2, 8> hbf_v2;
+#define HBF_NVAR 7
+static const int hbf_shapes[HBF_NVAR][2] = { {12, 5}, {8, 3}, {4, 2}, {24, 11}, {12, 5}, {8, 3}, {4, 2} };
 
 /* a pattern qualifies when x0 is eliminated (nx[0] = 0) and every other stage has the variant's (nx, nu) */
 extern "C" int hb_fast_variant(int N, const int *nx, const int *nu)
 	{
-	for(int id=0; id<HBF_NVAR; id++)
+	const char *gen = getenv("HPMPC_B200_FAST_GEN");
+	const int first = (gen!=NULL && gen[0]=='1') ? 3 : 0;
+	for(int id=first; id<HBF_NVAR; id++)
 		{
 		int ok = (nx[0]==0) && N>=3;
 		for(int n=0; n<N && ok; n++) ok = (nu[n]==hbf_shapes[id][1]) && (n==0 || nx[n]==hbf_shapes[id][0]);
@@ -701,15 +708,22 @@ template<class C> static void hbf_info(int N, int *ipw, int *smem_warp, long lon
 	{
 	*ipw = C::IPW; *smem_warp = (int)sizeof(double)*C::PER_WARP; *stash_per_inst = (long long)(N+1)*C::LBUF;
 	}
+template<class C> static void hbk_info(int N, int *ipw, int *smem_warp, long long *stash_per_inst)
+	{
+	*ipw = C::IPW; *smem_warp = (int)sizeof(double)*C::PER_WARP; *stash_per_inst = (long long)(N+1)*C::SB;
+	}
 
 extern "C" int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst)
 	{
 	switch(id)
 		{
-		case 0: hbf_info<hbf_v0>(N, ipw, smem_warp, stash_per_inst); return 0;
-		case 1: hbf_info<hbf_v1>(N, ipw, smem_warp, stash_per_inst); return 0;
-		case 2: hbf_info<hbf_v2>(N, ipw, smem_warp, stash_per_inst); return 0;
+		case 0: hbk_info<hbk_v0>(N, ipw, smem_warp, stash_per_inst); return 0;
+		case 1: hbk_info<hbk_v1>(N, ipw, smem_warp, stash_per_inst); return 0;
+		case 2: hbk_info<hbk_v2>(N, ipw, smem_warp, stash_per_inst); return 0;
 		case 3: hbf_info<hbf_v3>(N, ipw, smem_warp, stash_per_inst); return 0;
+		case 4: hbf_info<hbf_v0>(N, ipw, smem_warp, stash_per_inst); return 0;
+		case 5: hbf_info<hbf_v1>(N, ipw, smem_warp, stash_per_inst); return 0;
+		case 6: hbf_info<hbf_v2>(N, ipw, smem_warp, stash_per_inst); return 0;
 		}
 	return -1;
 	}
@@ -723,6 +737,15 @@ template<class C> static int hbf_launch(const hb_dims *d, long long n_inst, cons
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
+template<class C> static int hbk_launch(const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi,
+		double *stash, int grid, int warps, cudaStream_t st)
+	{
+	int smem = warps*(int)sizeof(double)*C::PER_WARP;
+	if(hb_prep(hbk_ric_sv_kernel<C>, smem)) return -1;
+	hbk_ric_sv_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_inst, in, ux, pi, stash);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
 
 extern "C" int hb_launch_ric_sv_fast(int id, const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, void *stream)
@@ -730,10 +753,13 @@ extern "C" int hb_launch_ric_sv_fast(int id, const hb_dims *d, long long n_inst,
 	cudaStream_t st = (cudaStream_t)stream;
 	switch(id)
 		{
-		case 0: return hbf_launch<hbf_v0>(d, n_inst, in, ux, pi, stash, grid, warps, st);
-		case 1: return hbf_launch<hbf_v1>(d, n_inst, in, ux, pi, stash, grid, warps, st);
-		case 2: return hbf_launch<hbf_v2>(d, n_inst, in, ux, pi, stash, grid, warps, st);
+		case 0: return hbk_launch<hbk_v0>(d, n_inst, in, ux, pi, stash, grid, warps, st);
+		case 1: return hbk_launch<hbk_v1>(d, n_inst, in, ux, pi, stash, grid, warps, st);
+		case 2: return hbk_launch<hbk_v2>(d, n_inst, in, ux, pi, stash, grid, warps, st);
 		case 3: return hbf_launch<hbf_v3>(d, n_inst, in, ux, pi, stash, grid, warps, st);
+		case 4: return hbf_launch<hbf_v0>(d, n_inst, in, ux, pi, stash, grid, warps, st);
+		case 5: return hbf_launch<hbf_v1>(d, n_inst, in, ux, pi, stash, grid, warps, st);
+		case 6: return hbf_launch<hbf_v2>(d, n_inst, in, ux, pi, stash, grid, warps, st);
 		}
 	return -2;
 	}
