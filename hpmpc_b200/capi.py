@@ -17,7 +17,7 @@ import numpy as np
 from .problems import Ocp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(_HERE, "lib", "libhpmpc_b200.so")
+PRODUCT_LIB = os.environ.get("HPMPC_B200_LIB") or os.path.join(_HERE, "lib", "libhpmpc_b200.so")   # override: A/B builds in tools/
 
 c_dpp = C.POINTER(C.c_void_p)
 BS, NCL = 4, 2

@@ -69,19 +69,19 @@ struct hbk_cfg
 	static_assert(NU<=GR && NX<GR, "one u-column / x-column (and the gradient) per lane slot");
 	};
 
-/* sqrt and 1/sqrt of p: hardware seed + two coupled (Goldschmidt) steps; dependent depth 5 instead of 7 */
-__device__ __forceinline__ void hbk_sqrt_rsqrt(double p, double &sq, double &rs)
+/* 1/sqrt(p) with the reference's pivot rule (p <= 1e-15 -> 0): hardware seed (MUFU.RSQ64H, ~22 bits) and two coupled
+ * (Goldschmidt) steps on h ~ 1/sqrt(p), g ~ sqrt(p)/2; dependent depth 5 FP64 operations after the seed */
+__device__ __forceinline__ double hbk_rsqrt(double p)
 	{
 	double y;
 	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-	double g = p*y, h = 0.5*y;
-	double r = fma(-g, h, 0.5);
-	g = fma(g, r, g); h = fma(h, r, h);
-	r = fma(-g, h, 0.5);
-	g = fma(g, r, g); h = fma(h, r, h);
-	r = fma(-g, h, 0.5);                 /* third correction on h only: keeps the result within ~1 ulp */
-	h = fma(h, r, h);
-	sq = g; rs = h+h;
+	const double hp = 0.5*p;
+	double g = hp*y;
+	double r = fma(-g, y, 0.5);
+	g = fma(g, r, g); y = fma(y, r, y);
+	r = fma(-g, y, 0.5);
+	y = fma(y, r, y);
+	return (p>1e-15) ? y : 0.0;
 	}
 
 template<class C, int KIND>
@@ -221,6 +221,7 @@ __device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double 
 				}
 			}
 		}
+	HBF_STAMP(110);
 	/* ---- H <- RSQrq (before W is stored: with LDW > NX the W rows run over the RSQ part of the buffer) ---- */
 	#pragma unroll
 	for(int s=0; s<R; s++)
@@ -291,6 +292,7 @@ __device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double 
 			}
 	}
 	__syncwarp();
+	HBF_STAMP(111);
 	/* ---- H += W W' ---- */
 	const double *sW = io;
 	#pragma unroll
@@ -361,19 +363,19 @@ __device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double 
 /* c%G (slot c/G) and broadcast through shared memory.  Then K, k for the forward sweep.               */
 /* ------------------------------------------------------------------------------------------------ */
 template<class C, int KIND>
-__device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<C> &T, double *__restrict__ LUs, double *__restrict__ Sc)
+__device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<C> &T, double *__restrict__ LUs, double *__restrict__ Sc,
+		double *__restrict__ gS)
 	{
-	constexpr int NX = C::NX, NU = C::NU, NZ = C::NZ, G = C::G, R = C::R, RO = C::RO, E = C::E, CO = C::CO, NCC = C::NCC;
+	constexpr int NX = C::NX, NU = C::NU, G = C::G, R = C::R, RO = C::RO, E = C::E, CO = C::CO, NCC = C::NCC;
 	const int l = ln.l;
+	/* software pipeline: the reciprocal square root of pivot c+1 is started as soon as the look-ahead update has
+	 * finished its diagonal, so its dependent chain overlaps the broadcast and trailing update of column c */
+	double rs = hbk_rsqrt(T.hd[0]);
 	#pragma unroll
 	for(int c=0; c<CO; c++)
 		{
 		constexpr int dummy = 0; (void)dummy;
 		const int so = c/G, lo = c%G;
-		/* the owner's diagonal is final here; every lane runs the same instruction stream on its own hd[so] */
-		double sq, rs;
-		hbk_sqrt_rsqrt(T.hd[so], sq, rs);
-		if(!(T.hd[so]>1e-15)) { rs = 0.0; sq = 0.0; }
 		const double inv = __shfl_sync(HBF_FULL, rs, lo, G);
 		double lc[R];
 		#pragma unroll
@@ -382,20 +384,30 @@ __device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<
 		for(int s=so; s<R; s++)
 			{
 			const int v = l + s*G;
-			lc[s] = (s==so && v==c) ? sq : T.H[s][c<C::KS ? c : 0]*inv;      /* owner: sqrt(p) ; rows > c: L[v][c] */
-			if(s>so || v>c) T.hd[s] = fma(-lc[s], lc[s], T.hd[s]);          /* look-ahead: next pivots do not wait for smem */
+			lc[s] = (s==so && v==c) ? T.hd[s]*inv : T.H[s][c<C::KS ? c : 0]*inv;     /* owner: sqrt(p) ; rows > c: L[v][c] */
+			if(s>so || v>c) T.hd[s] = fma(-lc[s], lc[s], T.hd[s]);                  /* look-ahead */
 			}
+		if(c+1<CO) rs = hbk_rsqrt(T.hd[(c+1)/G]);
 		double *col = hbk_col<C>(c, LUs, Sc);
 		#pragma unroll
 		for(int s=so; s<R; s++)
 			{
 			const int v = l + s*G;
-			if((s>so || v>=c) && v<RO) col[v-c] = lc[s];
+			if((s>so || v>=c) && v<RO)
+				{
+				col[v-c] = lc[s];
+				if(c>=NU) gS[C::SX + C::xOff(c>=NU ? c-NU : 0) + (v-c)] = lc[s];      /* x-columns go to the stash as they are finished */
+				}
 			}
 		if(l==lo)
 			{
 			#pragma unroll
-			for(int e=0; e<E; e++) col[RO+e-c] = T.X[e][so]*inv;
+			for(int e=0; e<E; e++)
+				{
+				const double le = T.X[e][so]*inv;
+				col[RO+e-c] = le;
+				if(c>=NU) gS[C::SX + C::xOff(c>=NU ? c-NU : 0) + (RO+e-c)] = le;
+				}
 			if(c<NU) LUs[C::UDINV+c] = inv;
 			}
 		__syncwarp();
@@ -425,24 +437,59 @@ __device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<
 				for(int cc=0; cc<NCC; cc++) if(e>=cc) T.Z[e][cc] = fma(-le[e], le[cc], T.Z[e][cc]);
 				}
 			}
+		if(c==NU-1 && KIND!=HBF_LAST)
+			{
+			/* the u-columns are complete: K' rows, y Luu = -L[NU+x][0:NU]  (x = NX is the gradient row: y = k').
+			 * Independent of the remaining columns, so it fills their pivot latency. */
+			#pragma unroll
+			for(int s=0; s<R; s++)
+				{
+				const int x = l + s*G;
+				if(s*G<=NX)
+					{
+					double y[NU];
+					#pragma unroll
+					for(int c1=0; c1<NU; c1++) y[c1] = (x<=NX) ? -LUs[C::uOff(c1) + (NU+(x<=NX ? x : 0)-c1)] : 0.0;
+					#pragma unroll
+					for(int c1=NU-1; c1>=0; c1--)
+						{
+						y[c1] *= LUs[C::UDINV+c1];
+						#pragma unroll
+						for(int c2=0; c2<c1; c2++) y[c2] = fma(-y[c1], LUs[C::uOff(c2) + (c1-c2)], y[c2]);
+						}
+					if(x<NX)
+						{
+						#pragma unroll
+						for(int c1=0; c1<NU; c1++) gS[C::SK + c1*NX + x] = y[c1];
+						}
+					else if(x==NX)
+						{
+						#pragma unroll
+						for(int c1=0; c1<NU; c1++) gS[C::Sk + c1] = y[c1];
+						}
+					}
+				}
+			}
 		}
 	#pragma unroll
 	for(int cc=0; cc<NCC; cc++)
 		{
 		const double p = T.Z[cc][cc];
-		double sq, rs;
-		hbk_sqrt_rsqrt(p, sq, rs);
-		if(!(p>1e-15)) { rs = 0.0; sq = 0.0; }
+		const double rsc = hbk_rsqrt(p);
 		double *col = hbk_col<C>(CO+cc, LUs, Sc);
 		double lcol[E>0 ? E : 1];
-		lcol[cc] = sq;
+		lcol[cc] = p*rsc;
 		#pragma unroll
-		for(int e=cc+1; e<E; e++) lcol[e] = T.Z[e][cc]*rs;
+		for(int e=cc+1; e<E; e++) lcol[e] = T.Z[e][cc]*rsc;
 		if(l==0)
 			{
 			#pragma unroll
-			for(int e=cc; e<E; e++) col[e-cc] = lcol[e];
-			if(CO+cc<NU) LUs[C::UDINV+CO+cc] = rs;
+			for(int e=cc; e<E; e++)
+				{
+				col[e-cc] = lcol[e];
+				if(CO+cc>=NU) gS[C::SX + C::xOff(CO+cc>=NU ? CO+cc-NU : 0) + (e-cc)] = lcol[e];
+				}
+			if(CO+cc<NU) LUs[C::UDINV+CO+cc] = rsc;
 			}
 		#pragma unroll
 		for(int e=cc+1; e<E; e++)
@@ -451,37 +498,7 @@ __device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<
 				if(e>=c2) T.Z[e][c2] = fma(-lcol[e], lcol[c2], T.Z[e][c2]);
 		}
 	__syncwarp();
-	if(KIND==HBF_LAST) return;
-	/* ---- K' rows: y Luu = -L[NU+x][0:NU]  (x = NX is the gradient row: y = k') ---- */
-	#pragma unroll
-	for(int s=0; s<R; s++)
-		{
-		const int x = l + s*G;
-		if(s*G<=NX)
-			{
-			double y[NU];
-			#pragma unroll
-			for(int c=0; c<NU; c++) y[c] = (x<=NX) ? -LUs[C::uOff(c) + (NU+x-c)] : 0.0;
-			#pragma unroll
-			for(int c=NU-1; c>=0; c--)
-				{
-				y[c] *= LUs[C::UDINV+c];
-				#pragma unroll
-				for(int c2=0; c2<c; c2++) y[c2] = fma(-y[c], LUs[C::uOff(c2) + (c-c2)], y[c2]);
-				}
-			if(x<NX)
-				{
-				#pragma unroll
-				for(int c=0; c<NU; c++) Sc[C::SK + c*NX + x] = y[c];
-				}
-			else if(x==NX)
-				{
-				#pragma unroll
-				for(int c=0; c<NU; c++) Sc[C::Sk + c] = y[c];
-				}
-			}
-		}
-	__syncwarp();
+	HBF_STAMP(120);
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -647,59 +664,34 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 		if(!active) inst = n_inst-1;
 		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
 
+		/* lanes 0..IPW-1 each move the data of one instance of the warp (one bulk copy per lane and buffer);
+		 * lane 0 posts the byte count, one mbarrier per buffer */
+		const int mg = lane<IPW ? lane : 0;
+		long long my_i = grp*IPW + mg; if(my_i>=n_inst) my_i = n_inst-1;
+		const double *my_in = in + my_i*d.in_stride;
+		double *my_sm = wbase + 8 + (size_t)mg*C::PER_INST;
+		double *my_st = stash_w + mg*stash_stride;
 		auto issue_backward = [&](int n)                          /* [B A b]'_n | RSQrq_n -> io */
 			{
-			if(lane==0)
-				{
-				const int off = (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in);
-				const uint32_t bytes = (n==0) ? bytes_first : (n==N ? bytes_last : bytes_mid);
-				hbf_mbar_expect(&bars[0], bytes*IPW);
-				#pragma unroll
-				for(int gg=0; gg<IPW; gg++)
-					{
-					long long ii = grp*IPW + gg; if(ii>=n_inst) ii = n_inst-1;
-					hbf_bulk_g2s(wbase + 8 + (size_t)gg*C::PER_INST, in + ii*d.in_stride + off, bytes, &bars[0]);
-					}
-				}
+			const int off = (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in);
+			const uint32_t bytes = (n==0) ? bytes_first : (n==N ? bytes_last : bytes_mid);
+			if(lane==0) hbf_mbar_expect(&bars[0], bytes*IPW);
+			if(lane<IPW) hbf_bulk_g2s(my_sm, my_in + off, bytes, &bars[0]);
 			};
 		auto issue_BAbt = [&](int n, int slot)                    /* forward: [B A b]'_n -> io + slot*BAB */
 			{
-			if(lane==0)
-				{
-				const int off = (n==0) ? 0 : o_in1 + (n-1)*s_in;
-				const uint32_t bytes = (n==0) ? 8u*(uint32_t)C::even((NU+1)*NX) : 8u*(uint32_t)BAB;
-				hbf_mbar_expect(&bars[slot], bytes*IPW);
-				#pragma unroll
-				for(int gg=0; gg<IPW; gg++)
-					{
-					long long ii = grp*IPW + gg; if(ii>=n_inst) ii = n_inst-1;
-					hbf_bulk_g2s(wbase + 8 + (size_t)gg*C::PER_INST + slot*BAB, in + ii*d.in_stride + off, bytes, &bars[slot]);
-					}
-				}
+			const int off = (n==0) ? 0 : o_in1 + (n-1)*s_in;
+			const uint32_t bytes = (n==0) ? 8u*(uint32_t)C::even((NU+1)*NX) : 8u*(uint32_t)BAB;
+			if(lane==0) hbf_mbar_expect(&bars[slot], bytes*IPW);
+			if(lane<IPW) hbf_bulk_g2s(my_sm + slot*BAB, my_in + off, bytes, &bars[slot]);
 			};
 		auto issue_S = [&](int n, int slot)                       /* forward: stash image of stage n -> S[slot] */
 			{
-			if(lane==0)
-				{
-				hbf_mbar_expect(&bars[2+slot], 8u*SB*IPW);
-				#pragma unroll
-				for(int gg=0; gg<IPW; gg++)
-					hbf_bulk_g2s(wbase + 8 + (size_t)gg*C::PER_INST + IOB + LU + slot*SB, stash_w + gg*stash_stride + (long long)n*SB, 8u*SB, &bars[2+slot]);
-				}
+			if(lane==0) hbf_mbar_expect(&bars[2+slot], 8u*SB*IPW);
+			if(lane<IPW) hbf_bulk_g2s(my_sm + IOB + LU + slot*SB, my_st + (long long)n*SB, 8u*SB, &bars[2+slot]);
 			};
 		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
-		auto store_S = [&](int n)
-			{
-			hbf_fence_async();
-			__syncwarp();
-			if(lane==0)
-				{
-				#pragma unroll
-				for(int gg=0; gg<IPW; gg++)
-					hbf_bulk_s2g(stash_w + gg*stash_stride + (long long)n*SB, wbase + 8 + (size_t)gg*C::PER_INST + IOB + LU + (n&1)*SB, 8u*SB);
-				hbf_bulk_commit();
-				}
-			};
+		double *gst = stash_w + g*stash_stride;                 /* this instance's stash slot: images written with plain stores */
 
 		/* ---------------- backward sweep: stage n builds S[n&1], reads the x-columns in S[(n+1)&1] ---------------- */
 		issue_backward(N);
@@ -708,41 +700,39 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 		wait_bar(0);
 		hbk_back_assemble<C, HBF_LAST>(ln, io, nullptr, T);
 		issue_backward(N-1);
-		if(lane==0) hbf_bulk_wait_read<1>();
-		__syncwarp();
-		hbk_back_factor<C, HBF_LAST>(ln, T, LUs, (N&1) ? S1 : S0);
-		store_S(N);
+		hbk_back_factor<C, HBF_LAST>(ln, T, LUs, (N&1) ? S1 : S0, gst + (long long)N*SB);
 		}
 		for(int n=N-1; n>0; n--)
 			{
 			double *Sc = (n&1) ? S1 : S0;
 			const double *Sp = (n&1) ? S0 : S1;
 			hbk_tile<C> T;
+			HBF_STAMP(100);
 			wait_bar(0);
+			HBF_STAMP(101);
 			hbk_back_assemble<C, HBF_MID>(ln, io, Sp, T);
+			HBF_STAMP(102);
 			issue_backward(n-1);                                  /* lands while the factorization runs */
-			/* the image of stage n+2 was stored from this buffer: that bulk store must have finished reading smem */
-			if(lane==0) hbf_bulk_wait_read<1>();
-			__syncwarp();
-			hbk_back_factor<C, HBF_MID>(ln, T, LUs, Sc);
-			store_S(n);
+			HBF_STAMP(103);
+			hbk_back_factor<C, HBF_MID>(ln, T, LUs, Sc, gst + (long long)n*SB);
+			HBF_STAMP(104);
 			}
 		{
 		hbk_tile<C> T;
 		wait_bar(0);
 		hbk_back_assemble<C, HBF_FIRST>(ln, io, S1, T);
-		if(lane==0) hbf_bulk_wait_read<1>();
-		__syncwarp();
-		hbk_back_factor<C, HBF_FIRST>(ln, T, LUs, S0);
-		store_S(0);
+		hbk_back_factor<C, HBF_FIRST>(ln, T, LUs, S0, gst);
 		}
-		/* now: S0 = image of stage 0, S1 = image of stage 1 ; io is free */
-		if(lane==0) hbf_bulk_wait_all<0>();        /* every image is in the stash before any is read back */
+		/* the images were written through the generic proxy and are read back by bulk copies (async proxy) */
+		asm volatile("fence.proxy.async;" ::: "memory");
 		__syncwarp();
 
 		/* ---------------- forward sweep ---------------- */
+		issue_S(0, 0);
 		issue_BAbt(0, 0);
+		issue_S(1, 1);
 		if(N>1) issue_BAbt(1, 1);
+		wait_bar(2);
 		wait_bar(0);
 		hbk_stage_forward<C, HBF_FIRST>(ln, io, S0, us, xs0, xs1, tmp, ux, ux + NU + ((1<N) ? NU : 0), pi, active);
 		if(2<=N) issue_S(2, 0);
@@ -752,14 +742,17 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 			const double *Sn = (n&1) ? S1 : S0;
 			const double *xs = (n&1) ? xs1 : xs0;
 			double *xo = (n&1) ? xs0 : xs1;
-			if(n>=2) wait_bar(2+(n&1));                           /* image n (0 and 1 are still resident from the backward sweep) */
+			HBF_STAMP(200);
+			wait_bar(2+(n&1));                                    /* image n */
 			wait_bar(n&1);                                        /* [B A b]'_n */
+			HBF_STAMP(201);
 			const int o_ux = NU + (n-1)*NUX, o_ux1 = NU + n*NUX + ((n+1<N) ? NU : 0);
 			hbk_stage_forward<C, HBF_MID>(ln, io + (n&1)*BAB, Sn, us, xs, xo, tmp, ux + o_ux, ux + o_ux1, pi + (n-1)*NX, active);
+			HBF_STAMP(202);
 			if(n+2<=N) issue_S(n+2, n&1);
 			if(n+2<N) issue_BAbt(n+2, n&1);
 			}
-		if(N>=2) wait_bar(2+(N&1));
+		wait_bar(2+(N&1));
 		hbk_final_pi<C>(ln, (N&1) ? S1 : S0, (N&1) ? xs1 : xs0, tmp, pi + (N-1)*NX, active);
 		}
 	}

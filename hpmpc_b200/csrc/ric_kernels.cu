@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "layout.h"
 #include "ric_generic.cuh"
 #include "ric_fast.cuh"
@@ -679,7 +680,11 @@ extern "C" double hb_fp64_peak_probe(int device, int iters, void *stream)
 /* ------------------------------------------------------------------------------------------------ */
 /* size-specialised variants (ric_blk.cuh: register-blocked; ric_fast.cuh: one row per lane)          */
 /* ------------------------------------------------------------------------------------------------ */
-typedef hbk_cfg<12, 5, 8, 2> hbk_v0;   /* BASELINE config 2: four instances per warp, two rows per lane */
+#ifndef HBK_V0_G
+#define HBK_V0_G 8
+#define HBK_V0_R 2
+#endif
+typedef hbk_cfg<12, 5, HBK_V0_G, HBK_V0_R> hbk_v0;   /* BASELINE config 2: four instances per warp, two rows per lane */
 typedef hbk_cfg<8, 3, 4, 3> hbk_v1;    /* the reference's own test size (test_d_ip_hard.c): eight instances per warp */
 typedef hbk_cfg<4, 2, 4, 2> hbk_v2;    /* eight instances per warp */
 typedef hbf_cfg<24, 11, 32> hbf_v3;    /* BASELINE config 3 shape: one instance per warp, 4 column-owned rows */
@@ -737,12 +742,50 @@ template<class C> static int hbf_launch(const hb_dims *d, long long n_inst, cons
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
+/* The factor stash is scratch that every warp slot rewrites for each instance it solves (written in the backward sweep,
+ * read back in the forward sweep).  A persisting-L2 access window over it keeps a fraction of its lines resident, so that
+ * fraction of the stash traffic never reaches HBM (HPMPC_B200_L2_PERSIST=0 disables; value = hit ratio in percent). */
+static int hb_stash_window(cudaLaunchAttribute *attr, const void *stash, size_t stash_bytes)
+	{
+	static int inited = 0, max_persist = 0, max_window = 0, pct = -1;
+	if(!inited)
+		{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+		const char *e = getenv("HPMPC_B200_L2_PERSIST");
+		pct = e ? atoi(e) : 0;          /* opt-in: measured neutral (16-40 MiB set aside) to harmful (79 MiB) on B200 */
+		{ const char *m = getenv("HPMPC_B200_L2_MB"); if(m && atoi(m)>0 && ((size_t)atoi(m)<<20)<(size_t)max_persist) max_persist = atoi(m)<<20; }
+		if(pct!=0 && max_persist>0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+		if(getenv("HPMPC_B200_VERBOSE")) fprintf(stderr, "hpmpc_b200: persisting L2 max %d MiB, window max %d MiB\n", max_persist>>20, max_window>>20);
+		inited = 1;
+		}
+	if(pct==0 || max_persist<=0 || max_window<=0 || stash_bytes==0) return 0;
+	size_t win = stash_bytes<(size_t)max_window ? stash_bytes : (size_t)max_window;
+	double ratio = pct>0 ? pct/100.0 : 0.9*(double)max_persist/(double)win;
+	if(ratio>1.0) ratio = 1.0;
+	attr->id = cudaLaunchAttributeAccessPolicyWindow;
+	attr->val.accessPolicyWindow.base_ptr = (void*)stash;
+	attr->val.accessPolicyWindow.num_bytes = win;
+	attr->val.accessPolicyWindow.hitRatio = (float)ratio;
+	attr->val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	attr->val.accessPolicyWindow.missProp = getenv("HPMPC_B200_L2_MISS_NORMAL") ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+	return 1;
+	}
+
 template<class C> static int hbk_launch(const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, cudaStream_t st)
 	{
 	int smem = warps*(int)sizeof(double)*C::PER_WARP;
 	if(hb_prep(hbk_ric_sv_kernel<C>, smem)) return -1;
-	hbk_ric_sv_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_inst, in, ux, pi, stash);
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = dim3(grid); cfg.blockDim = dim3(warps*32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	cfg.attrs = attr;
+	cfg.numAttrs = hb_stash_window(&attr[0], stash, sizeof(double)*(size_t)grid*warps*C::IPW*(size_t)(d->N+1)*C::SB);
+	HB_CK(cudaLaunchKernelEx(&cfg, hbk_ric_sv_kernel<C>, *d, n_inst, in, ux, pi, stash));
 	HB_CK(cudaGetLastError());
 	return 0;
 	}

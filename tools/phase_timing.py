@@ -26,7 +26,7 @@ agg = collections.OrderedDict()
 for i in range(len(v) - 1):
     key = (int(v[i, 0]), int(v[i + 1, 0]))
     agg.setdefault(key, []).append(int(v[i + 1, 1] - v[i, 1]))
-names = {100: "bwd:top", 101: "bwd:inputs ready", 102: "bwd:assembled", 103: "bwd:pre-factor", 104: "bwd:factored", 200: "fwd:top", 201: "fwd:ready", 202: "fwd:done"}
+names = {110: "bwd:W computed", 111: "bwd:W stored", 120: "bwd:chol done", 100: "bwd:top", 101: "bwd:inputs ready", 102: "bwd:assembled", 103: "bwd:pre-factor", 104: "bwd:factored", 200: "fwd:top", 201: "fwd:ready", 202: "fwd:done"}
 tot = 0
 for (a, b), ds in agg.items():
     print(f"{names.get(a,a):>18s} -> {names.get(b,b):<18s} n={len(ds):4d} mean={sum(ds)/len(ds):9.0f} min={min(ds):7d} max={max(ds):7d}")
