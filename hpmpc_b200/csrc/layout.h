@@ -53,6 +53,24 @@ typedef struct hb_dims
 	const int *c_ux;            /* [nbtot] flat index into the instance's ux vector */
 	} hb_dims;
 
+/* scenario tree (ric_tree.cuh): one entry per node, BFS order; the edge data [B A b]' belongs to the kid */
+typedef struct hb_tnode
+	{
+	int nx, nu, nkids, first_kid, dad;
+	int off_BAbt, off_RSQ;      /* into the tree's input block (doubles); off_BAbt is the edge INTO this node */
+	int off_ux, off_pi, off_L;  /* node-indexed outputs / factor stash */
+	int pad0, pad1;
+	} hb_tnode;
+
+typedef struct hb_tdims
+	{
+	int Nn, nzM, nxM, n_seg;    /* n_seg segments: segment 0 = top (may be empty), 1.. = tails */
+	long long in_stride, ux_stride, pi_stride, L_stride;
+	const hb_tnode *tn;         /* [Nn]            (device pointer in kernel launches) */
+	const int *seg_start;       /* [n_seg+1]       first entry of each segment in seg_nodes */
+	const int *seg_nodes;       /* node indices, top-down within a segment */
+	} hb_tdims;
+
 /* packed trapezoid helpers */
 #define HB_TRI(i) (((i)*((i)+1))>>1)
 #define HB_EVEN(x) (((x)+1)&~1)
@@ -73,8 +91,11 @@ int hb_fast_variant(int N, const int *nx, const int *nu);
 int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst);
 int hb_launch_ric_sv_fast(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, void *stream);
+int hb_launch_tree(const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
+		int mode /* 0 backward, 1 forward, 2 backward then forward */, int seg_lo, int seg_hi, int grid, int warps, void *stream);
 long long hb_ipm_work_doubles(const hb_dims *dims);
 int hb_smem_bytes_per_warp(const hb_dims *dims);
+int hb_smem_bytes_per_warp_sz(int nzM, int nxM);
 int hb_device_sm_count(int device);
 double hb_fp64_peak_probe(int device, int iters, void *stream);   /* measured DFMA TFLOP/s */
 

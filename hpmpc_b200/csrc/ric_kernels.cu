@@ -19,6 +19,7 @@
 #include "ric_generic.cuh"
 #include "ric_fast.cuh"
 #include "ric_blk.cuh"
+#include "ric_tree.cuh"
 
 /* ------------------------------------------------------------------------------------------------ */
 /* sweeps                                                                                            */
@@ -564,6 +565,45 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
+/* scenario tree                                                                                     */
+/* ------------------------------------------------------------------------------------------------ */
+__global__ void hb_tree_kernel(hb_tdims d, long long n_trees, const double *__restrict__ in, double *__restrict__ ux_all,
+		double *__restrict__ pi_all, double *__restrict__ L_all, int mode, int seg_lo, int seg_hi)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	hb_ctx c;
+	{
+	double *smem_warp = hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM);
+	int lsz = HB_EVEN(HB_TRI(d.nzM) + 2*d.nzM);
+	c.lane = lane; c.ldW = d.nxM | 1;
+	c.bufA = smem_warp; c.bufB = c.bufA + lsz; c.sW = c.bufB + lsz; c.sV = c.sW + HB_EVEN(d.nzM*c.ldW);
+	}
+	const int nseg = seg_hi - seg_lo;
+	const long long n_items = n_trees*nseg;
+	for(long long item=gw; item<n_items; item+=tw)
+		{
+		const long long t = item/nseg;
+		const int seg = seg_lo + (int)(item - t*nseg);
+		const double *in_tree = in + t*d.in_stride;
+		double *Lt = L_all + t*d.L_stride, *ux = ux_all + t*d.ux_stride, *pi = pi_all + t*d.pi_stride;
+		const int s0 = d.seg_start[seg], s1 = d.seg_start[seg+1];
+		if(mode==0 || mode==2)
+			for(int q=s1-1; q>=s0; q--)
+				{
+				hb_tree_node_factor(c, d.tn, d.seg_nodes[q], in_tree, Lt, c.bufA, c.bufB);
+				__syncwarp();
+				}
+		if(mode==1 || mode==2)
+			for(int q=s0; q<s1; q++)
+				{
+				hb_tree_node_forward(c, d.tn, d.seg_nodes[q], in_tree, Lt, ux, pi, c.bufA, c.bufB);
+				__syncwarp();
+				}
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* FP64 peak probe                                                                                   */
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void hb_fp64_probe(double *out, int iters)
@@ -587,6 +627,8 @@ extern "C" int hb_smem_bytes_per_warp(const hb_dims *d)
 	{
 	return (int)sizeof(double)*hb_smem_doubles_per_warp(d->nzM, d->nxM);
 	}
+
+extern "C" int hb_smem_bytes_per_warp_sz(int nzM, int nxM) { return (int)sizeof(double)*hb_smem_doubles_per_warp(nzM, nxM); }
 
 extern "C" long long hb_ipm_work_doubles(const hb_dims *d) { return hb_ipm_work_doubles_(*d); }
 
@@ -650,6 +692,18 @@ extern "C" int hb_launch_ipm(const hb_dims *d, long long n_inst, const double *i
 	HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
 	hb_ipm_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
 			ux, pi, lam, t, info, work, work_stride, counter);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+extern "C" int hb_launch_tree(const hb_tdims *d, long long n_trees, const double *in, double *ux, double *pi, double *L,
+		int mode, int seg_lo, int seg_hi, int grid, int warps, void *stream)
+	{
+	if(d->nzM>64) { fprintf(stderr, "hpmpc_b200: tree: nu+nx+1 > 64 not supported\n"); return -2; }
+	if(seg_hi<=seg_lo || n_trees<=0) return 0;
+	int smem = warps*(int)sizeof(double)*hb_smem_doubles_per_warp(d->nzM, d->nxM);
+	if(hb_prep(hb_tree_kernel, smem)) return -1;
+	hb_tree_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}

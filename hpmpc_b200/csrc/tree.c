@@ -1,0 +1,218 @@
+/*
+ * tree.c -- host side (plain C) of the scenario-tree Riccati path: topology -> node table, segments (top + tails),
+ * device layout, packing, phase launches.  The arithmetic runs in ric_tree.cuh / ric_kernels.cu.
+ * Reference: include/tree.h:34-44 (struct node), lqcp_solvers/d_tree_back_ric_rec_libstr.c:524-583 (node order, edges
+ * indexed by the kid), test_problems/test_d_tree_ip_hard_libstr.c:93-176 (how callers build the tree).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_runtime_api.h>
+#include "layout.h"
+#include "../../include/hpmpc_b200_tree.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if(e_!=cudaSuccess) { fprintf(stderr, "hpmpc_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while(0)
+
+struct hpmpc_b200_tree
+	{
+	int device, Nn, cut_stage, n_tails, n_top;
+	hb_tnode *tn;            /* host copy */
+	int *stage;
+	int *seg_start, *seg_nodes, n_seg;
+	int *tail_root;
+	hb_tdims dims;           /* device pointers inside */
+	int sms;
+	};
+
+int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
+	{
+	int n, j;
+	*out = NULL;
+	if(Nn<1) return -2;
+	hpmpc_b200_tree *t = calloc(1, sizeof(*t));
+	t->device = device; t->Nn = Nn;
+	t->tn = calloc(Nn, sizeof(hb_tnode));
+	t->stage = calloc(Nn, sizeof(int));
+	int nzM = 1, nxM = 1, max_stage = 0;
+	for(n=0; n<Nn; n++)
+		{
+		hb_tnode *s = &t->tn[n];
+		s->nx = nx[n]; s->nu = nu[n]; s->nkids = tree[n].nkids; s->dad = (n==0) ? -1 : tree[n].dad;
+		s->first_kid = s->nkids>0 ? tree[n].kids[0] : -1;
+		for(j=0; j<s->nkids; j++)
+			if(tree[n].kids[j]!=s->first_kid+j || s->first_kid<=n || s->first_kid+j>=Nn)
+				{ fprintf(stderr, "hpmpc_b200: tree: node %d: kids must be contiguous and follow their dad (BFS order)\n", n); return -2; }
+		t->stage[n] = (n==0) ? 0 : t->stage[s->dad]+1;
+		if(t->stage[n]>max_stage) max_stage = t->stage[n];
+		if(s->nu+s->nx+1>nzM) nzM = s->nu+s->nx+1;
+		if(s->nx>nxM) nxM = s->nx;
+		}
+	if(nzM>64) { fprintf(stderr, "hpmpc_b200: tree: nu+nx+1 = %d > 64 is not supported\n", nzM); return -2; }
+	/* cut: smallest stage c such that every node of stage >= c has at most one kid */
+	int cut = 0;
+	for(n=0; n<Nn; n++) if(t->tn[n].nkids>1 && t->stage[n]+1>cut) cut = t->stage[n]+1;
+	t->cut_stage = cut;
+	long long o_in = 0, o_ux = 0, o_pi = 0, o_L = 0;
+	int n_top = 0, n_tails = 0;
+	for(n=0; n<Nn; n++)
+		{
+		hb_tnode *s = &t->tn[n];
+		int nux = s->nu+s->nx;
+		if(n>0)
+			{
+			int nuxd = t->tn[s->dad].nu + t->tn[s->dad].nx;
+			s->off_BAbt = (int)o_in; o_in += HB_EVEN((nuxd+1)*s->nx);
+			}
+		else s->off_BAbt = -1;
+		s->off_RSQ = (int)o_in; o_in += HB_EVEN(HB_TRI(nux)+nux);
+		s->off_ux = (int)o_ux; o_ux += nux;
+		s->off_pi = (int)o_pi; o_pi += s->nx;
+		s->off_L = (int)o_L; o_L += HB_EVEN(HB_TRI(nux)+2*nux);
+		if(t->stage[n]<cut) n_top++;
+		if(t->stage[n]==cut) n_tails++;
+		}
+	t->n_top = n_top; t->n_tails = n_tails; t->n_seg = 1+n_tails;
+	t->seg_start = calloc(t->n_seg+1, sizeof(int)); t->seg_nodes = calloc(Nn, sizeof(int)); t->tail_root = calloc(n_tails+1, sizeof(int));
+	int pos = 0, seg = 0;
+	t->seg_start[0] = 0;
+	for(n=0; n<Nn; n++) if(t->stage[n]<cut) t->seg_nodes[pos++] = n;
+	t->seg_start[++seg] = pos;
+	for(n=0; n<Nn; n++)
+		if(t->stage[n]==cut)
+			{
+			int m = n;
+			t->tail_root[seg-1] = n;
+			for(;;)
+				{
+				t->seg_nodes[pos++] = m;
+				if(t->tn[m].nkids==0) break;
+				m = t->tn[m].first_kid;
+				}
+			t->seg_start[++seg] = pos;
+			}
+	if(pos!=Nn) { fprintf(stderr, "hpmpc_b200: tree: inconsistent topology (%d of %d nodes reached)\n", pos, Nn); return -2; }
+	t->dims.Nn = Nn; t->dims.nzM = nzM; t->dims.nxM = nxM; t->dims.n_seg = t->n_seg;
+	t->dims.in_stride = o_in; t->dims.ux_stride = HB_EVEN(o_ux); t->dims.pi_stride = HB_EVEN(o_pi); t->dims.L_stride = o_L;
+	t->sms = 148;
+	if(device>=0)
+		{
+		CK(cudaSetDevice(device));
+		hb_tnode *d_tn; int *d_ss, *d_sn;
+		CK(cudaMalloc((void**)&d_tn, Nn*sizeof(hb_tnode)));
+		CK(cudaMalloc((void**)&d_ss, (t->n_seg+1)*sizeof(int)));
+		CK(cudaMalloc((void**)&d_sn, Nn*sizeof(int)));
+		CK(cudaMemcpy(d_tn, t->tn, Nn*sizeof(hb_tnode), cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(d_ss, t->seg_start, (t->n_seg+1)*sizeof(int), cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(d_sn, t->seg_nodes, Nn*sizeof(int), cudaMemcpyHostToDevice));
+		t->dims.tn = d_tn; t->dims.seg_start = d_ss; t->dims.seg_nodes = d_sn;
+		t->sms = hb_device_sm_count(device);
+		if(t->sms<=0) return -1;
+		}
+	*out = t;
+	return 0;
+	}
+
+void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
+	{
+	if(!t) return;
+	if(t->device>=0)
+		{
+		cudaSetDevice(t->device);
+		cudaFree((void*)t->dims.tn); cudaFree((void*)t->dims.seg_start); cudaFree((void*)t->dims.seg_nodes);
+		}
+	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->tail_root); free(t);
+	}
+
+void hpmpc_b200_tree_sizes_get(const hpmpc_b200_tree *t, hpmpc_b200_tree_sizes *o)
+	{
+	o->in_stride = t->dims.in_stride; o->ux_stride = t->dims.ux_stride; o->pi_stride = t->dims.pi_stride; o->L_stride = t->dims.L_stride;
+	o->Nn = t->Nn; o->nzM = t->dims.nzM; o->nxM = t->dims.nxM;
+	o->n_tails = t->n_tails; o->n_top_nodes = t->n_top; o->cut_stage = t->cut_stage;
+	}
+
+void hpmpc_b200_tree_node_offsets(const hpmpc_b200_tree *t, int n, int *off_BAbt, int *off_RSQ, int *off_ux, int *off_pi, int *off_L)
+	{
+	const hb_tnode *s = &t->tn[n];
+	if(off_BAbt) *off_BAbt = s->off_BAbt;
+	if(off_RSQ) *off_RSQ = s->off_RSQ;
+	if(off_ux) *off_ux = s->off_ux;
+	if(off_pi) *off_pi = s->off_pi;
+	if(off_L) *off_L = s->off_L;
+	}
+
+void hpmpc_b200_tree_tail_root(const hpmpc_b200_tree *t, int tail, int *node, int *off_L, int *len_L)
+	{
+	int n = t->tail_root[tail];
+	int nux = t->tn[n].nu + t->tn[n].nx;
+	if(node) *node = n;
+	if(off_L) *off_L = t->tn[n].off_L;
+	if(len_L) *len_L = HB_EVEN(HB_TRI(nux)+2*nux);
+	}
+
+int hpmpc_b200_tree_pack_instance(const hpmpc_b200_tree *t, double *const *A, double *const *B, double *const *b,
+		double *const *Q, double *const *S, double *const *R, double *const *q, double *const *r, double *blk)
+	{
+	int n, i, j;
+	memset(blk, 0, sizeof(double)*t->dims.in_stride);
+	for(n=0; n<t->Nn; n++)
+		{
+		const hb_tnode *s = &t->tn[n];
+		int nx = s->nx, nu = s->nu, nux = nx+nu;
+		if(n>0)
+			{
+			const hb_tnode *d = &t->tn[s->dad];
+			int nxd = d->nx, nud = d->nu, nuxd = nxd+nud;
+			double *M = blk + s->off_BAbt;                       /* (nuxd+1) x nx row-major */
+			for(i=0; i<nud; i++) for(j=0; j<nx; j++) M[i*nx+j] = B[n][j+(size_t)nx*i];
+			for(i=0; i<nxd; i++) for(j=0; j<nx; j++) M[(nud+i)*nx+j] = A[n][j+(size_t)nx*i];
+			for(j=0; j<nx; j++) M[nuxd*nx+j] = b[n][j];
+			}
+		double *H = blk + s->off_RSQ;
+		for(i=0; i<nu; i++) for(j=0; j<=i; j++) H[HB_TRI(i)+j] = R[n][i+(size_t)nu*j];
+		for(i=0; i<nx; i++)
+			{
+			for(j=0; j<nu; j++) H[HB_TRI(nu+i)+j] = S[n][j+(size_t)nu*i];
+			for(j=0; j<=i; j++) H[HB_TRI(nu+i)+nu+j] = Q[n][i+(size_t)nx*j];
+			}
+		for(j=0; j<nu; j++) H[HB_TRI(nux)+j] = r[n][j];
+		for(j=0; j<nx; j++) H[HB_TRI(nux)+nu+j] = q[n][j];
+		}
+	return 0;
+	}
+
+static void launch_shape(const hpmpc_b200_tree *t, long long items, int *grid, int *warps)
+	{
+	int w = 4;
+	int smem_warp = hb_smem_bytes_per_warp_sz(t->dims.nzM, t->dims.nxM);
+	while(w>1 && w*smem_warp>100*1024) w--;
+	int per_sm = (220*1024)/(w*smem_warp+1024); if(per_sm<1) per_sm = 1; if(per_sm*w>16) per_sm = 16/w>0 ? 16/w : 1;
+	long long need = (items + w - 1)/w, cap = (long long)t->sms*per_sm;
+	*warps = w; *grid = (int)(need<cap ? (need<1 ? 1 : need) : cap);
+	}
+
+int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_trees, int phase, int tail_lo, int tail_hi,
+		const double *d_in, double *d_ux, double *d_pi, double *d_L, void *stream)
+	{
+	if(n_trees<=0) return 0;
+	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
+	if(tail_lo<0 || tail_hi>t->n_tails || tail_lo>tail_hi) return -2;
+	CK(cudaSetDevice(t->device));
+	int grid, warps;
+	if(phase==1)
+		{
+		if(t->n_top==0) return 0;
+		launch_shape(t, n_trees, &grid, &warps);
+		return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 2, 0, 1, grid, warps, stream);
+		}
+	launch_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
+	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, 1+tail_lo, 1+tail_hi, grid, warps, stream);
+	}
+
+int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in,
+		double *d_ux, double *d_pi, double *d_L, void *stream)
+	{
+	int rc;
+	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 0, 0, t->n_tails, d_in, d_ux, d_pi, d_L, stream))) return rc;
+	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 1, 0, 0, d_in, d_ux, d_pi, d_L, stream))) return rc;
+	return hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 2, 0, t->n_tails, d_in, d_ux, d_pi, d_L, stream);
+	}

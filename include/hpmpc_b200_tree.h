@@ -1,0 +1,72 @@
+/*
+ * hpmpc_b200_tree.h -- batched Riccati factor+solve over scenario trees (BASELINE config 5).
+ *
+ * Replaces, for a batch of trees that share one topology and size pattern,
+ *     d_tree_back_ric_rec_sv_libstr        reference include/lqcp_solvers.h (lqcp_solvers/d_tree_back_ric_rec_libstr.c:524)
+ * whose own signature takes BLASFEO matrix structs (BLASFEO is an external, un-vendored dependency of the reference,
+ * Makefile.rule:47-48), so the batched entry points below take the tree (`struct node`, reference include/tree.h:34-44,
+ * same fields in the same order) plus plain arrays in the packed layout described by hpmpc_b200_tree_node_offsets().
+ *
+ * A tree is cut at the first level from which every node has at most one kid (the robust horizon) into the "top" and
+ * one "tail" chain per node of that level.  Tails are independent: phase 0 (backward over tails) and phase 2 (forward
+ * over tails) can run on different GPUs for different tail ranges; phase 1 (backward + forward over the top) needs the
+ * factor blocks of all tail roots, which is the one exchange of the multi-GPU path (hpmpc_b200_tree_tail_root()).
+ *
+ * Every function returns 0 on success, negative on error; nothing falls back to the CPU.
+ */
+#ifndef HPMPC_B200_TREE_H
+#define HPMPC_B200_TREE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef TREE_MPC
+#define TREE_MPC
+struct node          /* reference include/tree.h:34-44 */
+	{
+	int *kids;
+	int idx;
+	int dad;
+	int nkids;
+	int stage;
+	int real;
+	int idxkid;
+	};
+#endif
+
+typedef struct hpmpc_b200_tree hpmpc_b200_tree;
+
+typedef struct hpmpc_b200_tree_sizes
+	{
+	long long in_stride, ux_stride, pi_stride, L_stride;   /* doubles per tree */
+	int Nn, nzM, nxM;
+	int n_tails, n_top_nodes, cut_stage;
+	} hpmpc_b200_tree_sizes;
+
+/* nodes in BFS order (kids of a node contiguous, as the reference's setup_tree builds them,
+ * test_problems/test_d_tree_ip_hard_libstr.c:93-176); nx, nu are node-indexed, nu of a leaf is taken as given */
+int  hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device);
+void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t);
+void hpmpc_b200_tree_sizes_get(const hpmpc_b200_tree *t, hpmpc_b200_tree_sizes *out);
+/* offsets (doubles) of node n: [B A b]' of the edge into n ((nux_dad+1) x nx_n row-major; -1 for the root), RSQrq_n
+ * (packed lower trapezoid by rows, gradient row last), ux_n, pi_n (multiplier of the edge into n), L_n in the stash */
+void hpmpc_b200_tree_node_offsets(const hpmpc_b200_tree *t, int n, int *off_BAbt, int *off_RSQ, int *off_ux, int *off_pi, int *off_L);
+/* tail j = 0..n_tails-1: its root node and where that node's factor block sits in the per-tree stash */
+void hpmpc_b200_tree_tail_root(const hpmpc_b200_tree *t, int tail, int *node, int *off_L, int *len_L);
+/* host-side packing of one tree from node/edge-indexed column-major arrays: A[k] nx_k x nx_dad, B[k] nx_k x nu_dad,
+ * b[k] nx_k for k >= 1 (entry 0 unused); Q[n] nx x nx, S[n] nu x nx, R[n] nu x nu, q[n], r[n] for every node */
+int  hpmpc_b200_tree_pack_instance(const hpmpc_b200_tree *t, double *const *A, double *const *B, double *const *b,
+                                   double *const *Q, double *const *S, double *const *R, double *const *q, double *const *r, double *block);
+
+/* whole solve on one GPU (phases 0, 1, 2 back to back) */
+int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in,
+                                            double *d_ux, double *d_pi, double *d_L, void *stream);
+/* one phase: 0 = backward over tails [tail_lo, tail_hi), 1 = top (backward + forward), 2 = forward over tails [tail_lo, tail_hi) */
+int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_trees, int phase, int tail_lo, int tail_hi,
+                                            const double *d_in, double *d_ux, double *d_pi, double *d_L, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

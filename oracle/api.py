@@ -92,6 +92,38 @@ def ric(p: Ocp, mode: str = "sv"):
                 pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)])
 
 
+def tree_ric(t):
+    """orc_tree_ric_sv (oracle/ric_oracle.c): Riccati factor+solve over a scenario tree; t is a hpmpc_b200.tree.TreeOcp."""
+    L = lib()
+    topo = t.topo
+    Nn = topo["Nn"]
+    L.orc_tree_ric_sv.restype = None
+    L.orc_tree_ric_sv.argtypes = [C.c_int] + [C.c_void_p] * 9
+    BAbt, RSQ = [], []
+    for n in range(Nn):
+        nx, nu = t.nx[n], t.nu[n]
+        nz = nx + nu + 1
+        H = np.zeros((nz, nx + nu + 1), order="F")
+        H[:nu, :nu] = t.R[n]; H[nu:nu + nx, :nu] = t.S[n].T; H[nu:nu + nx, nu:nu + nx] = t.Q[n]
+        H[nu + nx, :nu] = t.r[n]; H[nu + nx, nu:nu + nx] = t.q[n]
+        RSQ.append(np.asfortranarray(H[:, :max(nx + nu, 1)]))
+        if n == 0:
+            BAbt.append(np.zeros((1, 1), order="F"))
+        else:
+            d = topo["dad"][n]
+            nzd = t.nx[d] + t.nu[d] + 1
+            M = np.zeros((nzd, max(nx, 1)), order="F")
+            M[:t.nu[d], :nx] = t.B[n].T; M[t.nu[d]:t.nu[d] + t.nx[d], :nx] = t.A[n].T; M[nzd - 1, :nx] = t.b[n]
+            BAbt.append(M)
+    ux = [np.zeros(max(t.nx[n] + t.nu[n], 1)) for n in range(Nn)]
+    pi = [np.zeros(max(t.nx[n], 1)) for n in range(Nn)]
+    pa = ptr_array
+    L.orc_tree_ric_sv(Nn, int_array(topo["dad"]), int_array(topo["first_kid"]), int_array(topo["nkids"]), int_array(t.nx), int_array(t.nu),
+                      pa(BAbt), pa(RSQ), pa(ux), pa(pi))
+    return dict(u=[ux[n][:t.nu[n]].copy() for n in range(Nn)], x=[ux[n][t.nu[n]:t.nu[n] + t.nx[n]].copy() for n in range(Nn)],
+                pi=[pi[n][:t.nx[n]].copy() if n > 0 else np.zeros(0) for n in range(Nn)])
+
+
 # ------------------------------------------------------------------------------------------- CPU timing harness
 def _harness():
     L = lib()

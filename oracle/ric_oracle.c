@@ -833,3 +833,109 @@ void orc_fortran_order_d_ric(int mode, int N, int *nx, int *nu_N, double **A, do
 	free(hux); free(hpi); free(hPb); free(nb); free(idxb);
 	orc_prob_free(P);
 	}
+
+/* ------------------------------------------------------------------------------------------- */
+/* scenario tree: Riccati factor + solve over a tree of nodes (TEST INFRASTRUCTURE)             */
+/*                                                                                             */
+/* Follows lqcp_solvers/d_tree_back_ric_rec_libstr.c:                                          */
+/*   :524-583  d_tree_back_ric_rec_sv_libstr: nodes in BFS order, backward nn = Nn-1..0,         */
+/*             forward nn = 0..Nn-1; edge data (BAbt) indexed by kid-1                           */
+/*   :79-156   d_back_ric_sv_back_1_libstr: W = [W_kid0 | W_kid1 | ...], W_k = BAbt_k Lxx_k,     */
+/*             last row += l_x,k ; L = chol_mn(RSQrq + W W')                                     */
+/*   :160-200  d_back_ric_sv_back_N_libstr: leaf, L = chol_mn(RSQrq)                            */
+/*   :204-260  d_back_ric_sv_forw_0 / forw_1: root solves all of ux_0, the others only u;       */
+/*             every kid gets x_k = b_k + BAbt_k' ux_dad and pi_k = Lxx_k (Lxx_k' x_k + l_x,k)   */
+/* BLASFEO (needed by that file) is not in this image, so parity is pinned indirectly: for a   */
+/* path graph this function is checked against orc_ric_sv / the lib4 reference, and for real   */
+/* trees against the reference solving the stacked chain problem of                            */
+/* test_problems/test_d_tree_ric_libstr.c:797-1018 (tests/test_tree.py).                        */
+/*                                                                                             */
+/* nodes 0..Nn-1, dad[0] = -1, the kids of a node are first_kid[n] .. first_kid[n]+nkids[n]-1  */
+/* BAbt[k] (k >= 1): (nux_dad+1) x nx_k column-major, ld = nux_dad+1 (rows B', A', b')          */
+/* RSQrq[n]: (nux_n+1) x nux_n column-major, ld = nux_n+1                                      */
+/* out: ux[n] (nu_n + nx_n), pi[k] (nx_k, k >= 1; pi[0] untouched)                              */
+/* ------------------------------------------------------------------------------------------- */
+void orc_tree_ric_sv(int Nn, const int *dad, const int *first_kid, const int *nkids, const int *nx, const int *nu,
+		double *const *BAbt, double *const *RSQrq, double **ux, double **pi)
+	{
+	int nn, i, j, k, c;
+	double **L = calloc(Nn, sizeof(double*)), **dinv = calloc(Nn, sizeof(double*));
+	int nzM = 1, nxM = 1;
+	for(nn=0; nn<Nn; nn++)
+		{
+		int nz = nu[nn]+nx[nn]+1;
+		L[nn] = calloc((size_t)nz*nz, sizeof(double)); dinv[nn] = calloc(nz, sizeof(double));
+		if(nz>nzM) nzM = nz;
+		if(nx[nn]>nxM) nxM = nx[nn];
+		}
+	double *W = calloc((size_t)nzM*nxM, sizeof(double)), *tmp = calloc(nxM+1, sizeof(double));
+	/* backward */
+	for(nn=Nn-1; nn>=0; nn--)
+		{
+		int nux = nu[nn]+nx[nn], nz = nux+1;
+		double *Ln = L[nn];
+		for(j=0; j<nux; j++) for(i=j; i<nz; i++) Ln[i+nz*j] = RSQrq[nn][i+nz*j];
+		for(c=0; c<nkids[nn]; c++)
+			{
+			int kid = first_kid[nn]+c, nx1 = nx[kid], nu1 = nu[kid], nz1 = nx1+nu1+1;
+			const double *Lk = L[kid], *M = BAbt[kid];
+			for(i=0; i<nz; i++)
+				for(j=0; j<nx1; j++)
+					{
+					double s = 0.0;
+					for(k=j; k<nx1; k++) s += M[i+nz*k]*Lk[nu1+k+nz1*(nu1+j)];
+					W[i+nz*j] = s;
+					}
+			for(j=0; j<nx1; j++) W[nux+nz*j] += Lk[nu1+nx1+nz1*(nu1+j)];
+			for(j=0; j<nux; j++)
+				for(i=j; i<nz; i++)
+					{
+					double s = 0.0;
+					for(k=0; k<nx1; k++) s += W[i+nz*k]*W[j+nz*k];
+					Ln[i+nz*j] += s;
+					}
+			}
+		chol_mn(nz, nux, Ln, nz, dinv[nn]);
+		}
+	/* forward */
+	for(nn=0; nn<Nn; nn++)
+		{
+		int nux = nu[nn]+nx[nn], nz = nux+1;
+		int ks = (dad[nn]<0) ? nux : nu[nn];
+		const double *Ln = L[nn];
+		double *v = ux[nn];
+		for(i=0; i<ks; i++) v[i] = -Ln[nux+nz*i];
+		for(i=ks-1; i>=0; i--)
+			{
+			double s = v[i];
+			for(j=i+1; j<nux; j++) s -= Ln[j+nz*i]*v[j];
+			v[i] = s*dinv[nn][i];
+			}
+		for(c=0; c<nkids[nn]; c++)
+			{
+			int kid = first_kid[nn]+c, nx1 = nx[kid], nu1 = nu[kid], nz1 = nx1+nu1+1;
+			const double *Lk = L[kid], *M = BAbt[kid];
+			double *xk = ux[kid]+nu1;
+			for(j=0; j<nx1; j++)
+				{
+				double s = M[nux+nz*j];
+				for(i=0; i<nux; i++) s += M[i+nz*j]*v[i];
+				xk[j] = s;
+				}
+			for(i=0; i<nx1; i++)
+				{
+				double s = Lk[nu1+nx1+nz1*(nu1+i)];
+				for(k=i; k<nx1; k++) s += Lk[nu1+k+nz1*(nu1+i)]*xk[k];
+				tmp[i] = s;
+				}
+			for(i=0; i<nx1; i++)
+				{
+				double s = 0.0;
+				for(k=0; k<=i; k++) s += Lk[nu1+i+nz1*(nu1+k)]*tmp[k];
+				pi[kid][i] = s;
+				}
+			}
+		}
+	for(nn=0; nn<Nn; nn++) { free(L[nn]); free(dinv[nn]); }
+	free(L); free(dinv); free(W); free(tmp);
+	}
