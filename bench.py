@@ -282,6 +282,75 @@ def run_ours(args):
         spec.h.close()
         return out
 
+    def bench_tree(steps, warmup):
+        """BASELINE config 5: scenario trees md=4, Nr=3, Nh=20, nx=12, nu=5 (1173 nodes).  The 64 tails below the robust horizon
+        are sharded over the ranks (strong scaling); the one exchange per solve is an all-gather of the tail-root factor blocks
+        (NCCL over NVLink); the 21-node top is solved redundantly on every rank."""
+        from hpmpc_b200 import tree as T
+        t0 = T.mass_spring_tree(12, 5, 4, 3, 20)
+        h = T.TreeBatch(t0, device=local)
+        n = args.n_trees or 1024
+        base = torch.from_numpy(h.pack(t0)).to(dev)
+        mask = torch.zeros_like(base)
+        for nd in range(h.sz.Nn):
+            nux = t0.nu[nd] + t0.nx[nd]
+            mask[h.off[nd]["RSQ"]:h.off[nd]["RSQ"] + nux * (nux + 1) // 2 + nux] = 1.0
+        from hpmpc_b200.problems import instance_xi
+        xi = torch.from_numpy(instance_xi(n)[:, 2].copy()).to(dev)
+        d_in = base[None, :] * (1.0 + 0.1 * xi[:, None] * mask[None, :])       # per-instance cost scaling: distinct, well-posed problems
+        ux = torch.zeros((n, h.sz.ux_stride), dtype=torch.float64, device=dev)
+        pi = torch.zeros((n, h.sz.pi_stride), dtype=torch.float64, device=dev)
+        Lst = torch.zeros((n, h.sz.L_stride), dtype=torch.float64, device=dev)
+        lo, hi = shard_range(h.sz.n_tails, rank, world)
+        o0, ln = h.tails[0]["off_L"], h.tails[0]["len_L"]
+        assert all(h.tails[j]["off_L"] == o0 + j * ln for j in range(h.sz.n_tails))      # tail roots are contiguous in the stash
+        even = h.sz.n_tails % world == 0
+        ph = h.L.hpmpc_b200_d_tree_back_ric_rec_sv_phase
+        args_ = (d_in.data_ptr(), ux.data_ptr(), pi.data_ptr(), Lst.data_ptr(), st)
+        gathered = torch.empty((world, n, (hi - lo) * ln), dtype=torch.float64, device=dev) if world > 1 else None
+
+        def launch():
+            assert ph(h.h, n, 0, lo, hi, *args_) == 0
+            if world > 1:
+                assert even, "tails must divide evenly over the ranks"
+                mine = Lst[:, o0 + lo * ln:o0 + hi * ln].contiguous()
+                dist.all_gather_into_tensor(gathered, mine)
+                Lst[:, o0:o0 + h.sz.n_tails * ln] = gathered.permute(1, 0, 2).reshape(n, -1)
+            assert ph(h.h, n, 1, 0, 0, *args_) == 0
+            assert ph(h.h, n, 2, lo, hi, *args_) == 0
+        tot_ms, per = time_steps(launch, steps, warmup, stream, barrier)
+        tot_ms = reduce_max_time(tot_ms, dev)
+        # flops: edge-wise sums of SURVEY.md section 8d; bytes: inputs once + factors written and read + outputs
+        F = 0.0
+        for nd in range(h.sz.Nn):
+            nux = t0.nu[nd] + t0.nx[nd]
+            F += nux ** 3 / 3
+            if nd > 0:
+                dd = t0.topo["dad"][nd]
+                nuxd, nxk = t0.nu[dd] + t0.nx[dd], t0.nx[nd]
+                F += nuxd * nxk ** 2 + nuxd ** 2 * nxk + 4 * nxk ** 2 + 4 * nuxd * nxk
+        Bt = 8.0 * (h.sz.in_stride + h.sz.ux_stride + h.sz.pi_stride)
+        out = {"metric": "tree_riccati_solves_per_s", "value": n * steps / (tot_ms * 1e-3), "unit": "trees/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": f"scenario-tree Riccati factor+solve (d_tree_back_ric_rec_sv), {n} trees, md=4 Nr=3 Nh=20 nx=12 nu=5 (1173 nodes), FP64",
+                          "parallelism": f"64 tails sharded over {world} GPU(s), top replicated, one all-gather of tail-root factor blocks per solve"},
+               "roofline": {"bound": "hbm", "achieved": Bt * n / (float(np.mean(per)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": Bt * n / (float(np.mean(per)) * 1e-3) / 1e9 / hbm_peak, "traffic": None, "kernel": "hb_tree_kernel (3 launches)",
+                            "algorithmic_bytes_per_tree": Bt, "algorithmic_flops_per_tree": F},
+               "gpu_launches": 3 * steps}
+        h.close()
+        return out
+
+    if args.workload == "tree":
+        tr = bench_tree(args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps(tr))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     if args.workload == "ipm":
         ipm = bench_ipm(args.steps, args.warmup)
         if rank == 0:
@@ -308,7 +377,7 @@ def run_ours(args):
            "config": {"workload": workload_name("ric"), "instances_per_gpu": n, "l2": "inputs (6.4 GB per GPU) exceed the 126 MB L2; no flush between steps",
                       "launch": {"grid": sz.grid, "warps_per_cta": sz.warps_per_cta, "smem_per_cta": sz.smem_per_cta}, "parallelism": f"instances sharded, {world} GPU(s), no collective"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                        "peak_source": peak_src, "kernel": "hb_ric_sv_kernel", "launch_ms": res["launch_ms"],
+                        "peak_source": peak_src, "kernel": ("hbk_ric_sv_kernel<12,5,8,2>" if sz.fast_variant == 0 else "hb_ric_sv_kernel"), "launch_ms": res["launch_ms"],
                         "algorithmic_bytes_per_solve": w["B_sv"], "algorithmic_flops_per_solve": w["F_sv"],
                         "fp64": {"achieved_tflops": w["F_sv"] * n / launch_s / 1e12, "peak_tflops": fp64_peak, "frac": w["F_sv"] * n / launch_s / 1e12 / fp64_peak if fp64_peak > 0 else None,
                                  "peak_source": "measured DFMA probe (hb_fp64_probe)"}},
@@ -352,7 +421,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ric", choices=["ric", "ipm"])
+    ap.add_argument("--workload", default="ric", choices=["ric", "ipm", "tree"])
+    ap.add_argument("--n-trees", type=int, default=0)
     ap.add_argument("--n-inst", type=int, default=0)
     ap.add_argument("--n-inst-ipm", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
