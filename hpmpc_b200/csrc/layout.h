@@ -86,7 +86,10 @@ int hb_launch_ric_trs(const hb_dims *dims, long long n_inst, const double *in, c
 		double *work, int n_slots, int grid, int warps, void *stream);
 int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
 		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
-		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, void *stream);
+		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream);
+int hb_ipm_fast_variant(int N, const int *nx, const int *nu, int nbtot);
+int hb_ipm_fast_info(int id, int N, int *smem_warp, long long *L_doubles);
+long long hb_ipm_work_doubles2(const hb_dims *dims, long long L_doubles);
 int hb_fast_variant(int N, const int *nx, const int *nu);
 int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst);
 int hb_launch_ric_sv_fast(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,

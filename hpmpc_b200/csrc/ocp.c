@@ -32,6 +32,9 @@ struct hpmpc_b200_ocp
 	/* size-specialised sv kernel (ric_fast.cuh), -1 when the pattern has no compiled variant */
 	int fast_id, f_ipw, f_smem_warp, f_grid, f_warps, f_smem_cta;
 	long long f_stash_inst;
+	/* size-specialised IPM sweeps (ric_ipm_fast.cuh), -1 when none */
+	int ipm_fast_id, i_smem_warp, i_grid, i_warps;
+	long long i_L_doubles, ipm_ws;
 	/* scratch (device), grown on demand */
 	double *scratch; size_t scratch_bytes;
 	int *counter;
@@ -87,6 +90,19 @@ static void fast_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps)
 		if(ctas_per_sm>cap) ctas_per_sm = cap;
 		}
 	p->f_warps = warps; p->f_grid = p->sms*ctas_per_sm; p->f_smem_cta = smem_cta;
+	}
+
+/* launch shape of the IPM kernel: the generic shape, or for the size-specialised sweeps as many 4-warp CTAs as fit */
+static void ipm_launch(hpmpc_b200_ocp *p)
+	{
+	p->i_warps = p->warps; p->i_grid = p->grid;
+	if(p->ipm_fast_id<0) return;
+	int warps = 4;
+	while(warps>1 && warps*p->i_smem_warp>113*1024) warps--;
+	int per_sm = (228*1024)/(warps*p->i_smem_warp+1024);
+	if(per_sm<1) per_sm = 1;
+	if(per_sm*warps>16) per_sm = 16/warps;
+	p->i_warps = warps; p->i_grid = p->sms*per_sm;
 	}
 
 int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, int device)
@@ -145,12 +161,17 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 
 	p->fast_id = getenv("HPMPC_B200_NO_FAST") ? -1 : hb_fast_variant(N, p->nx, p->nu);
 	if(p->fast_id>=0) hb_fast_info(p->fast_id, N, &p->f_ipw, &p->f_smem_warp, &p->f_stash_inst);
+	p->ipm_fast_id = hb_ipm_fast_variant(N, p->nx, p->nu, nbtot);
+	p->i_L_doubles = p->dims.L_stride;
+	if(p->ipm_fast_id>=0) hb_ipm_fast_info(p->ipm_fast_id, N, &p->i_smem_warp, &p->i_L_doubles);
+	p->ipm_ws = hb_ipm_work_doubles2(&p->dims, p->i_L_doubles);
 	if(device<0)
 		{
 		/* host-only handle: layout queries and packing work, every compute entry point refuses to run */
 		p->sms = 148;
 		default_launch(p, 0, 0);
 		fast_launch(p, 0, 0);
+		ipm_launch(p);
 		*out = p;
 		return 0;
 		}
@@ -168,6 +189,7 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 	if(p->sms<=0) { fprintf(stderr, "hpmpc_b200: no CUDA device %d\n", device); return -1; }
 	default_launch(p, 0, 0);
 	fast_launch(p, 0, 0);
+	ipm_launch(p);
 	*out = p;
 	return 0;
 	}
@@ -208,6 +230,7 @@ int hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_
 		return 0;
 		}
 	default_launch(p, ctas_per_sm, warps_per_cta);
+	ipm_launch(p);
 	if(p->smem_cta>227*1024) { fprintf(stderr, "hpmpc_b200: %d warps need %d bytes of shared memory\n", p->warps, p->smem_cta); default_launch(p, 0, 0); return -2; }
 	return 0;
 	}
@@ -215,7 +238,7 @@ int hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_
 void hpmpc_b200_ocp_sizes(const hpmpc_b200_ocp *p, hpmpc_b200_sizes *o)
 	{
 	o->in_stride = p->dims.in_stride; o->ux_stride = p->dims.ux_stride; o->pi_stride = p->dims.pi_stride;
-	o->lam_stride = p->lam_stride; o->L_stride = p->dims.L_stride; o->ipm_work_stride = hb_ipm_work_doubles(&p->dims);
+	o->lam_stride = p->lam_stride; o->L_stride = p->dims.L_stride; o->ipm_work_stride = p->ipm_ws;
 	o->N = p->N; o->nzM = p->dims.nzM; o->nxM = p->dims.nxM; o->nbtot = p->dims.nbtot;
 	o->grid = p->grid; o->warps_per_cta = p->warps; o->n_slots = p->n_slots; o->smem_per_cta = p->smem_cta;
 	o->fast_variant = p->fast_id;
@@ -338,10 +361,29 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
-	long long ws = hb_ipm_work_doubles(&p->dims);
-	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*ws)) return -1;
-	return hb_launch_ipm(&p->dims, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
-			p->scratch, ws, p->n_slots, grid_for(p, n_inst), p->warps, p->counter, stream);
+	long long ws = p->ipm_ws;
+	int slots = p->i_grid*p->i_warps;
+	if(ensure_scratch(p, sizeof(double)*(size_t)slots*ws)) return -1;
+	/* Waves: one launch per `slots` instances (one instance per resident warp).  Warps of a wave stay in step, so the
+	 * SM's instruction cache serves all of them from the same sweep; a single persistent launch in which warps pull instances
+	 * from a queue drifts apart and was measured 2.3x slower on config 3 (the fused kernel is several hundred KB of SASS).
+	 * HPMPC_B200_IPM_CHUNK=0 restores the single launch, any other value sets the wave size. */
+	long long chunk = slots;
+	{ const char *e = getenv("HPMPC_B200_IPM_CHUNK"); if(e) chunk = atoll(e); }
+	if(chunk<=0 || chunk>n_inst) chunk = n_inst;
+	const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max, lam_len = p->lam_stride;
+	long long done;
+	for(done=0; done<n_inst; done+=chunk)
+		{
+		long long m = n_inst-done<chunk ? n_inst-done : chunk;
+		long long need = (m + p->i_warps - 1)/p->i_warps;
+		int grid = (int)(need<p->i_grid ? (need<1 ? 1 : need) : p->i_grid);
+		int rc = hb_launch_ipm(&p->dims, m, d_in + done*p->dims.in_stride, k_max, mu0, mu_tol, alpha_min, warm_start,
+				d_ux + done*p->dims.ux_stride, d_pi + done*p->dims.pi_stride, d_lam + done*lam_len, d_t + done*lam_len,
+				d_info + done*info_len, p->scratch, ws, slots, grid, p->i_warps, p->counter, p->ipm_fast_id, stream);
+		if(rc) return rc;
+		}
+	return 0;
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -429,8 +471,9 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 	const size_t in_b = sizeof(double)*(size_t)cs*p->dims.in_stride;
 	const size_t out_d = (size_t)cs*(p->dims.ux_stride + p->dims.pi_stride + 2*lam_len + info_len);
 	if(ensure_staging(p, in_b, sizeof(double)*out_d)) return -1;
-	const long long ws = hb_ipm_work_doubles(&p->dims);
-	if(ensure_scratch(p, sizeof(double)*(size_t)2*p->n_slots*ws)) return -1;
+	const long long ws = p->ipm_ws;
+	const int slots = p->i_grid*p->i_warps;
+	if(ensure_scratch(p, sizeof(double)*(size_t)2*slots*ws)) return -1;
 	long long done; int k = 0;
 	for(done=0; done<n_inst; done+=cs, k^=1)
 		{
@@ -442,8 +485,12 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 		CK(cudaMemcpyAsync(d_in, h_in + (size_t)done*p->dims.in_stride, sizeof(double)*(size_t)m*p->dims.in_stride, cudaMemcpyHostToDevice, st));
 		if(warm_start) CK(cudaMemcpyAsync(d_ux, h_ux + (size_t)done*p->dims.ux_stride, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(d_info, 0, sizeof(double)*(size_t)m*info_len, st));
+		{
+		long long need = (m + p->i_warps - 1)/p->i_warps;
+		int grid = (int)(need<p->i_grid ? (need<1 ? 1 : need) : p->i_grid);
 		if(hb_launch_ipm(&p->dims, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
-				p->scratch + (size_t)k*p->n_slots*ws, ws, p->n_slots, grid_for(p, m), p->warps, p->counter + 8*k, st)) return -1;
+				p->scratch + (size_t)k*slots*ws, ws, slots, grid, p->i_warps, p->counter + 8*k, p->ipm_fast_id, st)) return -1;
+		}
 		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));
 		if(p->lam_stride>0)

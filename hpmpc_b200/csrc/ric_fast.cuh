@@ -29,13 +29,15 @@
 /* debug build only (make dbg): warp 0 of the grid records clock64() at phase boundaries */
 __device__ long long *hbf_dbg = nullptr;
 __device__ int hbf_dbg_n = 0;
+__device__ int hbf_dbg_gen = 0;
 /* cheap stamp: the running index lives in shared memory (a global counter costs an L2 round trip per stamp) */
 __device__ __forceinline__ void hbf_stamp_(long long tag)
 	{
 	__shared__ int cnt_init, cnt;
 	if(blockIdx.x==0 && threadIdx.x==0 && hbf_dbg!=nullptr)
 		{
-		if(cnt_init!=0x5a5a) { cnt_init = 0x5a5a; cnt = 0; }
+		const int gen = hbf_dbg_gen;
+		if(cnt_init!=gen) { cnt_init = gen; cnt = 0; }
 		if(cnt<3990) { const long long t = clock64(); hbf_dbg[2*cnt] = tag; hbf_dbg[2*cnt+1] = t; cnt++; }
 		}
 	}

@@ -20,6 +20,7 @@
 #include "ric_fast.cuh"
 #include "ric_blk.cuh"
 #include "ric_tree.cuh"
+#include "ric_ipm_fast.cuh"
 
 /* ------------------------------------------------------------------------------------------------ */
 /* sweeps                                                                                            */
@@ -208,6 +209,25 @@ __device__ __forceinline__ double hb_warp_sum(double v)
 	return v;
 	}
 
+/* bound part of the residuals: res_d, res_m and their sum (mpc_solvers/c99/d_res_ip_res_hard.c:39-319) */
+__device__ __forceinline__ void hb_ipm_residuals_bounds(int lane, const hb_dims &d, const hb_ipm_ws &w, const double *ux, double &mu2, double &nd)
+	{
+	const double *lam_lo = w.v(CV_LAM_LO), *lam_up = w.v(CV_LAM_UP), *t_lo = w.v(CV_T_LO), *t_up = w.v(CV_T_UP);
+	mu2 = 0.0; nd = 0.0;
+	for(int cc=lane; cc<d.nbtot; cc+=32)
+		{
+		double u = ux[d.c_ux[cc]];
+		double rdl = w.v(CV_LB)[cc] - u + t_lo[cc];
+		double rdu = w.v(CV_UB)[cc] - u - t_up[cc];
+		double rml = lam_lo[cc]*t_lo[cc], rmu = lam_up[cc]*t_up[cc];
+		w.v(CV_RD_LO)[cc] = rdl; w.v(CV_RD_UP)[cc] = rdu;
+		w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
+		mu2 += rml + rmu;
+		nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
+		}
+	mu2 = hb_warp_sum(mu2);
+	}
+
 /* res_q, res_b, res_d, res_m and mu (mpc_solvers/c99/d_res_ip_res_hard.c:39-319); also returns the three
  * infinity norms used by the high-level wrapper on exit (interfaces/c/fortran_order_interface.c:616-652) */
 __device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
@@ -283,10 +303,10 @@ __device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const double
 
 /* step length + dt, dlam.  RES = false: phase 1 (c99/d_aux_ip_hard_lib4.c:489-614) ; true: phase 2 (:1180-1313) */
 template<bool RES>
-__device__ __forceinline__ double hb_ipm_alpha(const hb_ctx &c, const hb_dims &d, const hb_ipm_ws &w, const double *dux)
+__device__ __forceinline__ double hb_ipm_alpha(int lane_, const hb_dims &d, const hb_ipm_ws &w, const double *dux)
 	{
 	double alpha = 1.0;
-	for(int cc=c.lane; cc<d.nbtot; cc+=32)
+	for(int cc=lane_; cc<d.nbtot; cc+=32)
 		{
 		double du = dux[d.c_ux[cc]];
 		double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc], tl = w.v(CV_T_LO)[cc], tu = w.v(CV_T_UP)[cc];
@@ -316,27 +336,86 @@ __device__ __forceinline__ double hb_ipm_alpha(const hb_ctx &c, const hb_dims &d
 	}
 
 /* mu_aff = mu_scal * sum (lam + a dlam)(t + a dt)   (c99/d_aux_ip_hard_lib4.c:715-770, :1453-1508) */
-__device__ __forceinline__ double hb_ipm_mu_aff(const hb_ctx &c, const hb_dims &d, const hb_ipm_ws &w, double alpha, double mu_scal)
+__device__ __forceinline__ double hb_ipm_mu_aff(int lane_, const hb_dims &d, const hb_ipm_ws &w, double alpha, double mu_scal)
 	{
 	double mu = 0.0;
-	for(int cc=c.lane; cc<d.nbtot; cc+=32)
+	for(int cc=lane_; cc<d.nbtot; cc+=32)
 		mu += (w.v(CV_LAM_LO)[cc] + alpha*w.v(CV_DLAM_LO)[cc])*(w.v(CV_T_LO)[cc] + alpha*w.v(CV_DT_LO)[cc])
 		    + (w.v(CV_LAM_UP)[cc] + alpha*w.v(CV_DLAM_UP)[cc])*(w.v(CV_T_UP)[cc] + alpha*w.v(CV_DT_UP)[cc]);
 	return hb_warp_sum(mu)*mu_scal;
 	}
 
-__global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, int k_max, double mu0,
+/* The IPM kernel is written once; the five sweeps over the horizon come from a policy: the run-time-size routines of
+ * ric_generic.cuh, or the size-specialised, bulk-copy-pipelined ones of ric_ipm_fast.cuh. */
+struct hb_sweeps_generic
+	{
+	typedef hb_ctx ctx_t;
+	__device__ static __forceinline__ int smem_doubles(const hb_dims &d) { return hb_smem_doubles_per_warp(d.nzM, d.nxM); }
+	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return d.L_stride; }
+	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c = hb_make_ctx(d, smem_warp, lane); }
+	__device__ static __forceinline__ void backward(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *Qx, const double *qx)
+		{ hb_backward<true>(c, d, in_inst, w.L, bv, rqv!=nullptr ? rqv : w.rq0, Qx, qx, w.Pb); }
+	__device__ static __forceinline__ void forward_sv(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, double *ux, double *pi)
+		{ hb_forward(c, d, in_inst, w.L, nullptr, bv, false, ux, pi, true); }
+	__device__ static __forceinline__ void trs(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		hb_trs_backward(c, d, in_inst, w.L, bv, rqv, qx, w.dux, w.Pb, false);
+		hb_forward(c, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
+		}
+	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *ux, const double *pi, double *mu, double *norms)
+		{ hb_ipm_residuals(c, d, in_inst, w, ux, pi, mu, norms); }
+	};
+
+template<class C>
+struct hb_sweeps_fast
+	{
+	typedef hbi_ctx<C> ctx_t;
+	__device__ static __forceinline__ int smem_doubles(const hb_dims &) { return hbi_cfg<C>::PER_WARP; }
+	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return (long long)(d.N+1)*C::LBUF; }
+	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c.init(smem_warp, lane, d); }
+	__device__ static __forceinline__ void backward(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *Qx, const double *qx)
+		{ hbi_backward<C>(c, d, in_inst, w.L, bv, rqv, Qx, qx, w.Pb); }
+	__device__ static __forceinline__ void forward_sv(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, double *ux, double *pi)
+		{ hbi_forward<C, false>(c, in_inst, w.L, bv, nullptr, ux, pi); }
+	__device__ static __forceinline__ void trs(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		hbi_trs_backward<C>(c, d, in_inst, w.L, rqv, qx, w.Pb, w.dux);
+		__syncwarp();
+		hbi_forward<C, true>(c, in_inst, w.L, bv, w.dux, w.dux, w.dpi);
+		}
+	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *ux, const double *pi, double *mu, double *norms)
+		{
+		double mu2, nd, nq = 0.0, nb_ = 0.0;
+		hb_ipm_residuals_bounds(c.lane, d, w, ux, mu2, nd);
+		__syncwarp();
+		hbi_residuals<C>(c, d, in_inst, w.rq0, w.b0, w.v(CV_LAM_LO), w.v(CV_LAM_UP), ux, pi, w.res_q, w.res_b, nq, nb_);
+		if(d.nbtot>0) *mu = mu2/(2.0*d.nbtot);
+		if(norms!=nullptr) { norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd); }
+		}
+	};
+
+template<class S>
+__global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, int k_max, double mu0,
 		double mu_tol, double alpha_min, int warm_start, double *__restrict__ ux_all, double *__restrict__ pi_all,
 		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all,
 		double *__restrict__ work, long long work_stride, int *counter)
 	{
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const long long gw = (long long)blockIdx.x*nw + warp;
-	hb_ctx c = hb_make_ctx(d, hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM), lane);
+	typename S::ctx_t c;
+	S::init(c, d, hb_smem + (size_t)warp*S::smem_doubles(d), lane);
 	hb_ipm_ws w;
 	{
 	double *p = work + gw*work_stride;
-	w.L = p; p += d.L_stride;
+	w.L = p; p += S::L_doubles(d);
 	w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
 	w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
 	w.cv = p; w.nbp = HB_EVEN(d.nbtot);
@@ -379,11 +458,11 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 		if(d.nbtot==0)
 			{
 			/* no constraints: one Riccati solve (d_ip2_res_hard.c:430-450) */
-			hb_backward<true>(c, d, in_inst, w.L, nullptr, nullptr, nullptr, nullptr, w.Pb);
+			S::backward(c, d, in_inst, w, nullptr, nullptr, nullptr, nullptr);
 			__syncwarp();
-			hb_forward(c, d, in_inst, w.L, nullptr, nullptr, false, ux, pi, true);
+			S::forward_sv(c, d, in_inst, w, nullptr, ux, pi);
 			__syncwarp();
-			hb_ipm_residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+			S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
 			status = 0;
 			}
 		else
@@ -429,15 +508,18 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 					w.v(CV_QXG)[cc] = lu - ltu*w.v(CV_UB)[cc] + dlu - ll - ltl*w.v(CV_LB)[cc] - dll;
 					}
 				__syncwarp();
-				hb_backward<true>(c, d, in_inst, w.L, nullptr, w.rq0, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
+				HBF_STAMP(300);
+				S::backward(c, d, in_inst, w, nullptr, nullptr, w.v(CV_QXD), w.v(CV_QXG));
 				__syncwarp();
-				hb_forward(c, d, in_inst, w.L, nullptr, nullptr, false, w.dux, w.dpi, true);
+				HBF_STAMP(301);
+				S::forward_sv(c, d, in_inst, w, nullptr, w.dux, w.dpi);
+				HBF_STAMP(302);
 				__syncwarp();
-				alpha = hb_ipm_alpha<false>(c, d, w, w.dux);
+				alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
 				alpha *= 0.995;
-				mu_aff = hb_ipm_mu_aff(c, d, w, alpha, mu_scal);
+				mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
 				if(lane==0) stat[5*kk+2] = mu_aff;
 				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
 				{
@@ -452,10 +534,11 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 					}
 				}
 				__syncwarp();
-				hb_trs_backward(c, d, in_inst, w.L, w.b0, w.rq0, w.v(CV_QXG), w.dux, w.Pb, false);
-				hb_forward(c, d, in_inst, w.L, w.dux, w.b0, true, w.dux, w.dpi, true);
+				HBF_STAMP(303);
+				S::trs(c, d, in_inst, w, w.b0, w.rq0, w.v(CV_QXG));
+				HBF_STAMP(304);
 				__syncwarp();
-				alpha = hb_ipm_alpha<false>(c, d, w, w.dux);
+				alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
 				alpha *= 0.995;
@@ -479,7 +562,7 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 				}
 
 			/* ---------- phase 2 (d_ip2_res_hard.c:756-1273) ---------- */
-			hb_ipm_residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+			S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
 			__syncwarp();
 			while(kk<k_max && mu>mu_tol && alpha>=alpha_min)
 				{
@@ -493,15 +576,18 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 					w.v(CV_QXG)[cc] = til*(w.v(CV_RM_LO)[cc] - ll*w.v(CV_RD_LO)[cc]) - tiu*(w.v(CV_RM_UP)[cc] + lu*w.v(CV_RD_UP)[cc]);
 					}
 				__syncwarp();
-				hb_backward<true>(c, d, in_inst, w.L, w.res_b, w.res_q, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
+				HBF_STAMP(300);
+				S::backward(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXD), w.v(CV_QXG));
 				__syncwarp();
-				hb_forward(c, d, in_inst, w.L, nullptr, w.res_b, false, w.dux, w.dpi, true);
+				HBF_STAMP(301);
+				S::forward_sv(c, d, in_inst, w, w.res_b, w.dux, w.dpi);
+				HBF_STAMP(302);
 				__syncwarp();
-				alpha = hb_ipm_alpha<true>(c, d, w, w.dux);
+				alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
 				alpha *= 0.995;
-				mu_aff = hb_ipm_mu_aff(c, d, w, alpha, mu_scal);
+				mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
 				if(lane==0) stat[5*kk+2] = mu_aff;
 				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
 				{
@@ -517,10 +603,11 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 					}
 				}
 				__syncwarp();
-				hb_trs_backward(c, d, in_inst, w.L, w.res_b, w.res_q, w.v(CV_QXG), w.dux, w.Pb, false);
-				hb_forward(c, d, in_inst, w.L, w.dux, w.res_b, true, w.dux, w.dpi, true);
+				HBF_STAMP(303);
+				S::trs(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXG));
+				HBF_STAMP(304);
 				__syncwarp();
-				alpha = hb_ipm_alpha<true>(c, d, w, w.dux);
+				alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
 				alpha *= 0.995;
@@ -533,7 +620,9 @@ __global__ void hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restr
 					w.v(CV_T_LO)[cc] += alpha*w.v(CV_DT_LO)[cc]; w.v(CV_T_UP)[cc] += alpha*w.v(CV_DT_UP)[cc];
 					}
 				__syncwarp();
-				hb_ipm_residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+				HBF_STAMP(305);
+				S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+				HBF_STAMP(306);
 				if(lane==0) stat[5*kk+4] = mu;
 				kk++;
 				__syncwarp();
@@ -681,19 +770,82 @@ extern "C" int hb_launch_ric_trs(const hb_dims *d, long long n_inst, const doubl
 	return 0;
 	}
 
-extern "C" int hb_launch_ipm(const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
-		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
-		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, void *stream)
+/* size-specialised IPM sweeps (ric_ipm_fast.cuh): one warp per instance, x0 eliminated, uniform (nx, nu) */
+typedef hbf_cfg<24, 11, 32> hbi_v0;    /* BASELINE config 3 */
+typedef hbf_cfg<12, 5, 32> hbi_v1;     /* config-2 sizes with bounds */
+typedef hbf_cfg<8, 3, 32> hbi_v2;      /* the reference's own IPM test size (test_d_ip_hard.c) */
+#define HBI_NVAR 3
+static const int hbi_shapes[HBI_NVAR][2] = { {24, 11}, {12, 5}, {8, 3} };
+
+extern "C" int hb_ipm_fast_variant(int N, const int *nx, const int *nu, int nbtot)
 	{
-	if(d->nzM>64) return -2;
-	if(grid*warps>n_slots) return -3;
-	int smem = warps*hb_smem_bytes_per_warp(d);
-	if(hb_prep(hb_ipm_kernel, smem)) return -1;
-	HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
-	hb_ipm_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
+	if(getenv("HPMPC_B200_NO_FAST_IPM")!=NULL || nbtot<=0) return -1;
+	for(int id=0; id<HBI_NVAR; id++)
+		{
+		int ok = (nx[0]==0) && N>=3;
+		for(int n=0; n<N && ok; n++) ok = (nu[n]==hbi_shapes[id][1]) && (n==0 || nx[n]==hbi_shapes[id][0]);
+		ok = ok && nx[N]==hbi_shapes[id][0];
+		if(ok) return id;
+		}
+	return -1;
+	}
+
+template<class C> static void hbi_info(int N, int *smem_warp, long long *L_doubles)
+	{ *smem_warp = (int)sizeof(double)*hbi_cfg<C>::PER_WARP; *L_doubles = (long long)(N+1)*C::LBUF; }
+
+extern "C" int hb_ipm_fast_info(int id, int N, int *smem_warp, long long *L_doubles)
+	{
+	switch(id)
+		{
+		case 0: hbi_info<hbi_v0>(N, smem_warp, L_doubles); return 0;
+		case 1: hbi_info<hbi_v1>(N, smem_warp, L_doubles); return 0;
+		case 2: hbi_info<hbi_v2>(N, smem_warp, L_doubles); return 0;
+		}
+	return -1;
+	}
+
+/* doubles of per-slot work area; L_doubles = size of the factor stash of the variant in use */
+extern "C" long long hb_ipm_work_doubles2(const hb_dims *d, long long L_doubles)
+	{
+	return hb_ipm_work_doubles_(*d) - d->L_stride + L_doubles;
+	}
+
+template<class S> static int hb_launch_ipm_t(int smem, const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int grid, int warps, int *counter, cudaStream_t st)
+	{
+	if(hb_prep(hb_ipm_kernel<S>, smem)) return -1;
+	if(getenv("HPMPC_B200_VERBOSE"))
+		{
+		int nb = 0; cudaFuncAttributes fa;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb_ipm_kernel<S>, warps*32, smem);
+		cudaFuncGetAttributes(&fa, hb_ipm_kernel<S>);
+		fprintf(stderr, "hpmpc_b200: ipm kernel: grid %d x %d threads, %d B dynamic + %zu B static smem, %d regs, %zu B local, %d CTAs/SM\n",
+			grid, warps*32, smem, fa.sharedSizeBytes, fa.numRegs, fa.localSizeBytes, nb);
+		}
+	HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+	hb_ipm_kernel<S><<<grid, warps*32, smem, st>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
 			ux, pi, lam, t, info, work, work_stride, counter);
 	HB_CK(cudaGetLastError());
 	return 0;
+	}
+
+extern "C" int hb_launch_ipm(const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
+		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream)
+	{
+	if(d->nzM>64) return -2;
+	if(grid*warps>n_slots || warps>8) return -3;
+	cudaStream_t st = (cudaStream_t)stream;
+#define HB_IPM_ARGS d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start, ux, pi, lam, t, info, work, work_stride, grid, warps, counter, st
+	switch(fast_id)
+		{
+		case 0: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v0> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v0>::PER_WARP, HB_IPM_ARGS);
+		case 1: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v1> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v1>::PER_WARP, HB_IPM_ARGS);
+		case 2: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v2> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v2>::PER_WARP, HB_IPM_ARGS);
+		}
+	return hb_launch_ipm_t<hb_sweeps_generic>(warps*hb_smem_bytes_per_warp(d), HB_IPM_ARGS);
+#undef HB_IPM_ARGS
 	}
 
 extern "C" int hb_launch_tree(const hb_tdims *d, long long n_trees, const double *in, double *ux, double *pi, double *L,
@@ -741,7 +893,7 @@ extern "C" double hb_fp64_peak_probe(int device, int iters, void *stream)
 typedef hbk_cfg<12, 5, HBK_V0_G, HBK_V0_R> hbk_v0;   /* BASELINE config 2: four instances per warp, two rows per lane */
 typedef hbk_cfg<8, 3, 4, 3> hbk_v1;    /* the reference's own test size (test_d_ip_hard.c): eight instances per warp */
 typedef hbk_cfg<4, 2, 4, 2> hbk_v2;    /* eight instances per warp */
-typedef hbf_cfg<24, 11, 32> hbf_v3;    /* BASELINE config 3 shape: one instance per warp, 4 column-owned rows */
+typedef hbf_cfg<24, 11, 32> hbf_v3;    /* BASELINE config 3 shape: one instance per warp, 4 column-owned rows */   /* (hbk_cfg<24,11,16,2> was tried: 1.7 KB of local-memory stack, 9x slower) */
 typedef hbf_cfg<12, 5, 16> hbf_v0;     /* one-row-per-lane predecessors, kept for A/B runs (HPMPC_B200_FAST_GEN=1) */
 typedef hbf_cfg<8, 3, 16> hbf_v1;
 typedef hbf_cfg<4, 2, 8> hbf_v2;
@@ -865,6 +1017,9 @@ extern "C" int hb_launch_ric_sv_fast(int id, const hb_dims *d, long long n_inst,
 extern "C" int hb_debug_timing(long long *d_buf)
 	{
 	int zero = 0;
+	static int gen = 1000;
+	gen++;
+	HB_CK(cudaMemcpyToSymbol(hbf_dbg_gen, &gen, sizeof(int)));
 	HB_CK(cudaMemcpyToSymbol(hbf_dbg, &d_buf, sizeof(d_buf)));
 	HB_CK(cudaMemcpyToSymbol(hbf_dbg_n, &zero, sizeof(int)));
 	return 0;
