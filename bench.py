@@ -255,7 +255,7 @@ def run_ours(args):
             del h_in, h_ux, h_pi
         return res, (d_in, ux, pi)
 
-    def bench_ipm(steps, warmup):
+    def bench_ipm(steps, warmup, e2e=True):
         spec = BatchSpec("cfg3", device=local)
         h = spec.h
         n, k_max = args.n_inst_ipm or 16384, 40
@@ -273,12 +273,37 @@ def run_ours(args):
         w = algorithmic_work(spec.base)
         mean_kk = float(kk.mean())
         launch_ms = float(np.mean(per))
+        wave = max(1, h.sz.ipm_grid * h.sz.ipm_warps_per_cta)
         out = {"metric": "box_ipm_qp_solves_per_s", "value": world * n * steps / (tot_ms * 1e-3), "unit": "solves/s",
                "workload": workload_name("ipm"), "steps": steps, "ms_per_step": tot_ms / steps, "mean_iterations": mean_kk,
                "converged": int((info[:, 1] == 0).sum()), "instances_per_gpu": n,
+               "launch": {"grid": h.sz.ipm_grid, "warps_per_cta": h.sz.ipm_warps_per_cta, "wave": wave, "fast_variant": h.sz.ipm_fast_variant},
+               "gpu_launches": steps * ((n + wave - 1) // wave),
                "roofline": {"bound": "hbm", "achieved": w["B_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": w["B_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                            "bytes_per_iteration_model": w["B_it"], "flops_per_iteration_model": w["F_it"]}}
+                            "kernel": "hb_ipm_kernel<hb_sweeps_fast<24,11>> (one launch per wave)",
+                            "bytes_per_iteration_model": w["B_it"], "flops_per_iteration_model": w["F_it"],
+                            "fp64_tflops": w["F_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e12}}
+        if e2e:
+            pin = lambda m: torch.empty((n, max(int(m), 2)), dtype=torch.float64, pin_memory=True)
+            h_in = pin(h.sz.in_stride); h_in.copy_(d_in)
+            hux, hpi, hlam, ht, hinfo = pin(h.sz.ux_stride), pin(h.sz.pi_stride), pin(h.sz.lam_stride), pin(h.sz.lam_stride), pin(6 + 5 * k_max)
+            torch.cuda.synchronize()
+
+            def e2e_step():
+                rc = L.hpmpc_b200_d_ip2_res_mpc_hard_batch_host(h.h, n, h_in.data_ptr(), k_max, 2.0, 1e-8, 1e-8, 0, hux.data_ptr(), hpi.data_ptr(),
+                                                                hlam.data_ptr(), ht.data_ptr(), hinfo.data_ptr())
+                assert rc == 0
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            e2e_step()
+            t1 = time.perf_counter()
+            barrier()
+            te = reduce_max_time(t1 - t0, dev)
+            assert float((hinfo[:, 0] - info.cpu()[:, 0]).abs().max()) == 0.0
+            out["e2e"] = {"value": world * n / te, "unit": "solves/s", "h2d_bytes_per_step": int(n * h.sz.in_stride * 8),
+                          "d2h_bytes_per_step": int(n * (h.sz.ux_stride + h.sz.pi_stride + 2 * h.sz.lam_stride + 6 + 5 * k_max) * 8), "steps": 1}
         spec.h.close()
         return out
 
@@ -355,7 +380,7 @@ def run_ours(args):
         ipm = bench_ipm(args.steps, args.warmup)
         if rank == 0:
             ipm.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                        "dtype": "f64", "data": "synthetic", "config": {"workload": ipm.pop("workload")}, "gpu_launches": 2 * args.steps})
+                        "dtype": "f64", "data": "synthetic", "config": {"workload": ipm.pop("workload"), "launch": ipm.pop("launch")}})
             print(json.dumps(ipm))
         return
 

@@ -219,7 +219,8 @@ class HpmpcLib:
 # ------------------------------------------------------------------------------------------- batched C ABI
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("in_stride", "ux_stride", "pi_stride", "lam_stride", "L_stride", "ipm_work_stride")] \
-        + [(n, C.c_int) for n in ("N", "nzM", "nxM", "nbtot", "grid", "warps_per_cta", "n_slots", "smem_per_cta", "fast_variant")]
+        + [(n, C.c_int) for n in ("N", "nzM", "nxM", "nbtot", "grid", "warps_per_cta", "n_slots", "smem_per_cta", "fast_variant",
+                                    "ipm_grid", "ipm_warps_per_cta", "ipm_fast_variant")]
 
 
 _product = None

@@ -242,6 +242,7 @@ void hpmpc_b200_ocp_sizes(const hpmpc_b200_ocp *p, hpmpc_b200_sizes *o)
 	o->N = p->N; o->nzM = p->dims.nzM; o->nxM = p->dims.nxM; o->nbtot = p->dims.nbtot;
 	o->grid = p->grid; o->warps_per_cta = p->warps; o->n_slots = p->n_slots; o->smem_per_cta = p->smem_cta;
 	o->fast_variant = p->fast_id;
+	o->ipm_grid = p->i_grid; o->ipm_warps_per_cta = p->i_warps; o->ipm_fast_variant = p->ipm_fast_id;
 	if(p->fast_id>=0)
 		{
 		o->grid = p->f_grid; o->warps_per_cta = p->f_warps; o->n_slots = p->f_grid*p->f_warps*p->f_ipw; o->smem_per_cta = p->f_smem_cta;
@@ -354,24 +355,20 @@ int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, con
 	return hb_launch_ric_trs(&p->dims, n_inst, d_in, d_L, d_ux, d_pi, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
 	}
 
-int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
-		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t,
-		double *d_info, void *stream)
+/* Waves: one launch per `slots` instances (one instance per resident warp).  Warps of a wave stay in step, so the SM's
+ * instruction cache serves all of them from the same sweep; a single persistent launch in which warps pull instances from a
+ * queue drifts apart and was measured 2.3x slower on config 3 (the fused kernel is several hundred KB of SASS).
+ * HPMPC_B200_IPM_CHUNK=0 restores the single launch, any other value sets the wave size. */
+static int ipm_waves(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, double *scratch, int *counter,
+		long long lam_len, void *stream)
 	{
-	if(n_inst<=0) return 0;
-	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
-	CK(cudaSetDevice(p->device));
-	long long ws = p->ipm_ws;
-	int slots = p->i_grid*p->i_warps;
-	if(ensure_scratch(p, sizeof(double)*(size_t)slots*ws)) return -1;
-	/* Waves: one launch per `slots` instances (one instance per resident warp).  Warps of a wave stay in step, so the
-	 * SM's instruction cache serves all of them from the same sweep; a single persistent launch in which warps pull instances
-	 * from a queue drifts apart and was measured 2.3x slower on config 3 (the fused kernel is several hundred KB of SASS).
-	 * HPMPC_B200_IPM_CHUNK=0 restores the single launch, any other value sets the wave size. */
+	const long long ws = p->ipm_ws;
+	const int slots = p->i_grid*p->i_warps;
 	long long chunk = slots;
 	{ const char *e = getenv("HPMPC_B200_IPM_CHUNK"); if(e) chunk = atoll(e); }
 	if(chunk<=0 || chunk>n_inst) chunk = n_inst;
-	const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max, lam_len = p->lam_stride;
+	const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max;
 	long long done;
 	for(done=0; done<n_inst; done+=chunk)
 		{
@@ -380,10 +377,22 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
 		int grid = (int)(need<p->i_grid ? (need<1 ? 1 : need) : p->i_grid);
 		int rc = hb_launch_ipm(&p->dims, m, d_in + done*p->dims.in_stride, k_max, mu0, mu_tol, alpha_min, warm_start,
 				d_ux + done*p->dims.ux_stride, d_pi + done*p->dims.pi_stride, d_lam + done*lam_len, d_t + done*lam_len,
-				d_info + done*info_len, p->scratch, ws, slots, grid, p->i_warps, p->counter, p->ipm_fast_id, stream);
+				d_info + done*info_len, scratch, ws, slots, grid, p->i_warps, counter, p->ipm_fast_id, stream);
 		if(rc) return rc;
 		}
 	return 0;
+	}
+
+int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t,
+		double *d_info, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(p->device));
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->i_grid*p->i_warps*p->ipm_ws)) return -1;
+	return ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
+			p->lam_stride, stream);
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -466,7 +475,14 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
-	const long long cs = chunk_size(p, n_inst);
+	/* one chunk = one wave of the IPM kernel (one instance per resident warp), unless that exceeds ~1.5 GiB of staging */
+	long long cs = (long long)p->i_grid*p->i_warps;
+	{
+	long long cap = (1536LL<<20)/(long long)(sizeof(double)*p->dims.in_stride);
+	if(cap<1) cap = 1;
+	if(cs>cap) cs = cap;
+	if(cs>n_inst) cs = n_inst;
+	}
 	const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max, lam_len = p->lam_stride>0 ? p->lam_stride : 2;
 	const size_t in_b = sizeof(double)*(size_t)cs*p->dims.in_stride;
 	const size_t out_d = (size_t)cs*(p->dims.ux_stride + p->dims.pi_stride + 2*lam_len + info_len);
@@ -485,12 +501,8 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 		CK(cudaMemcpyAsync(d_in, h_in + (size_t)done*p->dims.in_stride, sizeof(double)*(size_t)m*p->dims.in_stride, cudaMemcpyHostToDevice, st));
 		if(warm_start) CK(cudaMemcpyAsync(d_ux, h_ux + (size_t)done*p->dims.ux_stride, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(d_info, 0, sizeof(double)*(size_t)m*info_len, st));
-		{
-		long long need = (m + p->i_warps - 1)/p->i_warps;
-		int grid = (int)(need<p->i_grid ? (need<1 ? 1 : need) : p->i_grid);
-		if(hb_launch_ipm(&p->dims, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
-				p->scratch + (size_t)k*slots*ws, ws, slots, grid, p->i_warps, p->counter + 8*k, p->ipm_fast_id, st)) return -1;
-		}
+		if(ipm_waves(p, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
+				p->scratch + (size_t)k*slots*ws, p->counter + 8*k, lam_len, st)) return -1;
 		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));
 		if(p->lam_stride>0)

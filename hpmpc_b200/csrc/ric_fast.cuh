@@ -99,6 +99,18 @@ __device__ __forceinline__ void hbf_bulk_g2s(void *sdst, const void *gsrc, uint3
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 		:: "r"(hbf_saddr(sdst)), "l"(gsrc), "r"(bytes), "r"(hbf_saddr(bar)) : "memory");
 	}
+/* same with an L2 eviction-priority hint (createpolicy) */
+__device__ __forceinline__ uint64_t hbf_policy_evict_first()
+	{ uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t hbf_policy_evict_last()
+	{ uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void hbf_bulk_g2s_hint(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t policy)
+	{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+		:: "r"(hbf_saddr(sdst)), "l"(gsrc), "r"(bytes), "r"(hbf_saddr(bar)), "l"(policy) : "memory");
+	}
+__device__ __forceinline__ void hbf_st_hint(double *p, double v, uint64_t policy)
+	{ asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(policy) : "memory"); }
 __device__ __forceinline__ void hbf_bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes)
 	{
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(hbf_saddr(ssrc)), "r"(bytes) : "memory");

@@ -38,6 +38,8 @@ typedef struct hpmpc_b200_sizes
 	int N, nzM, nxM, nbtot;
 	int grid, warps_per_cta, n_slots, smem_per_cta;
 	int fast_variant;          /* >= 0 when a size-specialised kernel serves this pattern */
+	int ipm_grid, ipm_warps_per_cta;   /* launch shape of the IPM kernel; one wave = ipm_grid*ipm_warps_per_cta instances */
+	int ipm_fast_variant;      /* >= 0 when the IPM uses the size-specialised sweeps */
 	} hpmpc_b200_sizes;
 
 /* nu has N entries (nu[N] is taken as 0, like the reference high-level API, c_order_interface.c:78-81);
