@@ -131,6 +131,45 @@ def test_batched_sv_vs_oracle(cfg, n_inst):
     spec.h.close()
 
 
+@pytest.mark.parametrize("cfg,n_inst", [("cfg2", 1), ("cfg2", 7), ("cfg2", 301), (dict(nx=4, nu=2, N=3, bounds=False), 13),
+                                        (dict(nx=8, nu=3, N=10, bounds=False), 1027)])
+def test_batched_sv_ragged_batches(cfg, n_inst):
+    """Batch sizes that do not fill the last group of lanes / the last warp: every instance must still be solved, and
+    nothing outside the batch may be written."""
+    import torch
+    spec = BatchSpec(cfg)
+    h = spec.h
+    d_in = spec.torch_batch(n_inst + 3, 17)
+    ux = torch.full((n_inst + 3, h.sz.ux_stride), -7.0, dtype=torch.float64, device="cuda")
+    pi = torch.full((n_inst + 3, h.sz.pi_stride), -7.0, dtype=torch.float64, device="cuda")
+    rc = capi.product().hpmpc_b200_d_back_ric_rec_sv_batch(h.h, n_inst, d_in.data_ptr(), ux.data_ptr(), pi.data_ptr(), None, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert float((ux[n_inst:] + 7.0).abs().max()) == 0.0 and float((pi[n_inst:] + 7.0).abs().max()) == 0.0
+    uxh, pih = ux.cpu().numpy(), pi.cpu().numpy()
+    for i in sorted({0, n_inst // 2, n_inst - 1}):
+        o = oracle.ric(spec.problem(17 + i), "sv")
+        u, x = h.split_ux(uxh[i])
+        assert rel_err(u, o["u"]) < TOL and rel_err(x, o["x"]) < TOL and rel_err(h.split_pi(pih[i]), o["pi"]) < TOL
+    h.close()
+
+
+def test_batched_ipm_waves_and_ragged_batch():
+    """The IPM runs in waves of one instance per resident warp: a batch of one wave + 5 must give the same answers as the same
+    instances solved as single-instance batches, and must not touch rows outside the batch."""
+    import torch
+    spec = BatchSpec(dict(nx=8, nu=3, N=10, bounds=True))
+    h = spec.h
+    wave = h.sz.ipm_grid * h.sz.ipm_warps_per_cta
+    n = wave + 5
+    _, ux, pi, lam, t, info = _run_ipm(spec, n, first=3)
+    assert np.all(info.cpu().numpy()[:, 1] == 0)
+    for i in (0, wave - 1, wave, n - 1):
+        _, ux1, pi1, lam1, t1, info1 = _run_ipm(spec, 1, first=3 + i)
+        assert torch.equal(ux1[0], ux[i]) and torch.equal(lam1[0], lam[i]) and torch.equal(info1[0], info[i])
+    h.close()
+
+
 def test_batched_trf_trs_equals_sv():
     import torch
     spec = BatchSpec("cfg2")
