@@ -327,8 +327,10 @@ def run_ours(args):
         pi = torch.zeros((n, h.sz.pi_stride), dtype=torch.float64, device=dev)
         Lst = torch.zeros((n, h.sz.L_stride), dtype=torch.float64, device=dev)
         lo, hi = shard_range(h.sz.n_tails, rank, world)
-        o0, ln = h.tails[0]["off_L"], h.tails[0]["len_L"]
-        assert all(h.tails[j]["off_L"] == o0 + j * ln for j in range(h.sz.n_tails))      # tail roots are contiguous in the stash
+        # factor slots of the tail roots are equally spaced in the per-tree stash: the exchange moves whole slots
+        o0 = h.tails[0]["off_L"]
+        ln = (h.tails[1]["off_L"] - o0) if h.sz.n_tails > 1 else h.tails[0]["len_L"]
+        assert ln >= h.tails[0]["len_L"] and all(h.tails[j]["off_L"] == o0 + j * ln for j in range(h.sz.n_tails))
         even = h.sz.n_tails % world == 0
         ph = h.L.hpmpc_b200_d_tree_back_ric_rec_sv_phase
         args_ = (d_in.data_ptr(), ux.data_ptr(), pi.data_ptr(), Lst.data_ptr(), st)

@@ -71,6 +71,19 @@ typedef struct hb_tdims
 	const int *seg_nodes;       /* node indices, top-down within a segment */
 	} hb_tdims;
 
+/* tails of a scenario tree solved by the size-specialised chain kernel (ric_blk.cuh: hbk_tail_kernel): all tails have the same
+ * length and node sizes, and the offsets of the node at position m of tail j are affine in j: pos*[m] + j*str*[m] */
+#define HB_TAIL_MAXLEN 64
+typedef struct hb_tail_tab
+	{
+	int len;                           /* nodes per tail; position len-1 is the leaf (nu = 0) */
+	int posB[HB_TAIL_MAXLEN], strB[HB_TAIL_MAXLEN];     /* [B A b]' of the edge INTO the node */
+	int posQ[HB_TAIL_MAXLEN];                           /* RSQrq of the node (same stride as posB) */
+	int posU[HB_TAIL_MAXLEN], strU[HB_TAIL_MAXLEN];     /* ux */
+	int posP[HB_TAIL_MAXLEN], strP[HB_TAIL_MAXLEN];     /* pi (multiplier of the edge into the node) */
+	int posL[HB_TAIL_MAXLEN], posI[HB_TAIL_MAXLEN], strL[HB_TAIL_MAXLEN];   /* factor slot: generic block at posL, stash image at posI */
+	} hb_tail_tab;
+
 /* packed trapezoid helpers */
 #define HB_TRI(i) (((i)*((i)+1))>>1)
 #define HB_EVEN(x) (((x)+1)&~1)
@@ -96,6 +109,10 @@ int hb_launch_ric_sv_fast(int id, const hb_dims *dims, long long n_inst, const d
 		double *stash, int grid, int warps, void *stream);
 int hb_launch_tree(const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
 		int mode /* 0 backward, 1 forward, 2 backward then forward */, int seg_lo, int seg_hi, int grid, int warps, void *stream);
+int hb_tail_variant(int nx, int nu);                     /* -1 when no size-specialised tail kernel exists */
+int hb_tail_info(int id, int *ipw, int *smem_warp, int *image_doubles);
+int hb_launch_tail(int id, const hb_tdims *dims, const hb_tail_tab *tab, long long n_trees, const double *in, double *ux, double *pi,
+		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream);
 long long hb_ipm_work_doubles(const hb_dims *dims);
 int hb_smem_bytes_per_warp(const hb_dims *dims);
 int hb_smem_bytes_per_warp_sz(int nzM, int nxM);

@@ -775,6 +775,143 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 		}
 	}
 
+/* ------------------------------------------------------------------------------------------------ */
+/* tails of a scenario tree (ric_tree.cuh): the same register-blocked stages on chains whose first node */
+/* has a given state (it comes from the top of the tree) and whose data sit in the tree's node-indexed  */
+/* layout.  mode 0: backward over the tail, images -> the nodes' factor slots, and the root's Lxx, l_x   */
+/* also in the generic packed form the top kernel reads; mode 1: forward from the root's x.              */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C>
+__global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long long n_trees, long long in_stride, long long ux_stride,
+		long long pi_stride, long long L_stride, const double *__restrict__ in, double *__restrict__ ux_all, double *__restrict__ pi_all,
+		double *__restrict__ L_all, int mode, int tail_lo, int tail_hi)
+	{
+	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
+	extern __shared__ __align__(16) double hbf_smem[];
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const int g = lane/G;
+	hbk_lane<C> ln; ln.init(lane%G);
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	double *wbase = hbf_smem + (size_t)warp*C::PER_WARP;
+	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);
+	double *ibase = wbase + 8 + (size_t)g*C::PER_INST;
+	double *io = ibase;
+	double *LUs = ibase + IOB;
+	double *S0 = LUs + LU, *S1 = S0 + SB;
+	double *us = S1 + SB, *xs0 = us + C::even(NU), *xs1 = xs0 + C::XS, *tmp = xs1 + C::XS;
+	if(lane==0)
+		{
+		for(int b=0; b<4; b++) hbf_mbar_init(&bars[b], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+	__syncwarp();
+	uint32_t phase = 0;
+	const int len = tab.len, ntl = tail_hi - tail_lo;
+	const long long n_items = n_trees*ntl, n_groups = (n_items + IPW - 1)/IPW;
+	constexpr uint32_t bytes_Q = 8u*(uint32_t)C::RSQ, bytes_Qlast = 8u*(uint32_t)C::even(HB_TRI(NX)+NX), bytes_B = 8u*(uint32_t)BAB;
+
+	for(long long grp=gw; grp<n_groups; grp+=tw)
+		{
+		long long item = grp*IPW + g;
+		const bool active = item<n_items;
+		if(!active) item = n_items-1;
+		const long long t = item/ntl;
+		const int j = tail_lo + (int)(item - t*ntl);
+		double *ux = ux_all + t*ux_stride, *pi = pi_all + t*pi_stride, *Lt = L_all + t*L_stride;
+		const int mg = lane<IPW ? lane : 0;
+		long long my_item = grp*IPW + mg; if(my_item>=n_items) my_item = n_items-1;
+		const long long my_t = my_item/ntl;
+		const int my_j = tail_lo + (int)(my_item - my_t*ntl);
+		const double *my_in = in + my_t*in_stride;
+		const double *my_L = L_all + my_t*L_stride;
+		double *my_sm = wbase + 8 + (size_t)mg*C::PER_INST;
+		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
+
+		if(mode==0)
+			{
+			/* stage m needs RSQrq of node m and [B A b]' of the edge m -> m+1, which the tree layout keeps with node m+1 */
+			auto issue = [&](int m)
+				{
+				const bool last = (m==len-1);
+				if(lane==0) hbf_mbar_expect(&bars[0], (last ? bytes_Qlast : bytes_B + bytes_Q)*IPW);
+				if(lane<IPW)
+					{
+					if(!last) hbf_bulk_g2s(my_sm, my_in + tab.posB[m+1] + my_j*tab.strB[m+1], bytes_B, &bars[0]);
+					hbf_bulk_g2s(my_sm + (last ? 0 : BAB), my_in + tab.posQ[m] + my_j*tab.strB[m], last ? bytes_Qlast : bytes_Q, &bars[0]);
+					}
+				};
+			issue(len-1);
+			{
+			hbk_tile<C> T;
+			wait_bar(0);
+			hbk_back_assemble<C, HBF_LAST, C::LDW>(ln, io, io, nullptr, T, hbk_nop());
+			issue(len-2);
+			hbk_back_factor<C, HBF_LAST>(ln, T, LUs, (((len-1)&1) ? S1 : S0) + C::SX, Lt + tab.posI[len-1] + j*tab.strL[len-1], hbk_nop());
+			}
+			for(int m=len-2; m>=0; m--)
+				{
+				double *Sc = (m&1) ? S1 : S0;
+				const double *Sp = (m&1) ? S0 : S1;
+				hbk_tile<C> T;
+				wait_bar(0);
+				hbk_back_assemble<C, HBF_MID, C::LDW>(ln, io, io + BAB, Sp + C::SX, T, hbk_nop());
+				if(m>0) issue(m-1);
+				hbk_back_factor<C, HBF_MID>(ln, T, LUs, Sc + C::SX, Lt + tab.posI[m] + j*tab.strL[m], hbk_nop());
+				}
+			/* the root's Lxx and l_x in the generic packed form (row r = NU+x: element (r, NU+c) at r(r+1)/2 + NU + c) for the top */
+			if(active)
+				{
+				double *gen = Lt + tab.posL[0] + j*tab.strL[0];
+				const double *xc = S0 + C::SX;
+				#pragma unroll
+				for(int s=0; s<C::R; s++)
+					{
+					const int c = ln.l + s*G;
+					if(s*G<NX && c<NX)
+						{
+						const double *col = xc + ln.xo[s] - c;                   /* col[x] = Lxx[x][c], col[NX] = l_x[c] */
+						for(int x=c; x<=NX; x++) gen[HB_TRI(NU+x) + NU + c] = col[x];
+						}
+					}
+				}
+			__syncwarp();
+			}
+		else
+			{
+			auto issue_B = [&](int m, int slot)                   /* [B A b]' of the edge m -> m+1 */
+				{
+				if(lane==0) hbf_mbar_expect(&bars[slot], bytes_B*IPW);
+				if(lane<IPW) hbf_bulk_g2s(my_sm + slot*BAB, my_in + tab.posB[m+1] + my_j*tab.strB[m+1], bytes_B, &bars[slot]);
+				};
+			auto issue_S = [&](int m, int slot)
+				{
+				if(lane==0) hbf_mbar_expect(&bars[2+slot], 8u*SB*IPW);
+				if(lane<IPW) hbf_bulk_g2s(my_sm + IOB + LU + slot*SB, my_L + tab.posI[m] + my_j*tab.strL[m], 8u*SB, &bars[2+slot]);
+				};
+			asm volatile("fence.proxy.async;" ::: "memory");
+			issue_S(0, 0); issue_B(0, 0);
+			issue_S(1, 1); if(len>2) issue_B(1, 1);
+			if(ln.l<NX) xs0[ln.l] = ux[tab.posU[0] + j*tab.strU[0] + NU + ln.l];
+			if(C::R>1 && ln.l+G<NX) xs0[ln.l+G] = ux[tab.posU[0] + j*tab.strU[0] + NU + ln.l + G];
+			__syncwarp();
+			for(int m=0; m<len-1; m++)
+				{
+				const double *Sn = (m&1) ? S1 : S0;
+				const double *xs = (m&1) ? xs1 : xs0;
+				double *xo = (m&1) ? xs0 : xs1;
+				wait_bar(2+(m&1));
+				wait_bar(m&1);
+				hbk_stage_forward<C, HBF_MID>(ln, io + (m&1)*BAB, Sn, us, xs, xo, tmp, ux + tab.posU[m] + j*tab.strU[m],
+						ux + tab.posU[m+1] + j*tab.strU[m+1] + ((m+1<len-1) ? NU : 0), pi + tab.posP[m] + j*tab.strP[m], active);
+				if(m+2<=len-1) issue_S(m+2, m&1);
+				if(m+2<len-1) issue_B(m+2, m&1);
+				}
+			wait_bar(2+((len-1)&1));
+			hbk_final_pi<C>(ln, ((len-1)&1) ? S1 : S0, ((len-1)&1) ? xs1 : xs0, tmp, pi + tab.posP[len-1] + j*tab.strP[len-1], active);
+			}
+		}
+	}
+
 #ifdef HBK_EXPERIMENTAL_V2   /* measured: 15.3 M solves/s at 12 warps/SM versus 19.8 M for the kernel above at 8 -- kept as a record */
 /* ================================================================================================ */
 /* v2: 12 resident warps per SM.  Shared memory per instance shrinks from 886 to 538 doubles (nx=12,  */

@@ -1022,6 +1022,54 @@ extern "C" int hb_launch_ric_sv_fast(int id, const hb_dims *d, long long n_inst,
 	return -2;
 	}
 
+/* ------------------------------------------------------------------------------------------------ */
+/* size-specialised tails of scenario trees                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+extern "C" int hb_tail_variant(int nx, int nu)
+	{
+	for(int id=0; id<3; id++) if(hbf_shapes[id][0]==nx && hbf_shapes[id][1]==nu) return id;
+	return -1;
+	}
+
+template<class C> static void hbk_tail_info_t(int *ipw, int *smem_warp, int *image_doubles)
+	{ *ipw = C::IPW; *smem_warp = (int)sizeof(double)*C::PER_WARP; *image_doubles = C::SB; }
+
+extern "C" int hb_tail_info(int id, int *ipw, int *smem_warp, int *image_doubles)
+	{
+	switch(id)
+		{
+		case 0: hbk_tail_info_t<hbk_v0>(ipw, smem_warp, image_doubles); return 0;
+		case 1: hbk_tail_info_t<hbk_v1>(ipw, smem_warp, image_doubles); return 0;
+		case 2: hbk_tail_info_t<hbk_v2>(ipw, smem_warp, image_doubles); return 0;
+		}
+	return -1;
+	}
+
+template<class C> static int hbk_tail_launch(const hb_tdims *d, const hb_tail_tab *tab, long long n_trees, const double *in, double *ux,
+		double *pi, double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, cudaStream_t st)
+	{
+	int smem = warps*(int)sizeof(double)*C::PER_WARP;
+	if(hb_prep(hbk_tail_kernel<C>, smem)) return -1;
+	hbk_tail_kernel<C><<<grid, warps*32, smem, st>>>(*tab, n_trees, d->in_stride, d->ux_stride, d->pi_stride, d->L_stride, in, ux, pi, L,
+			mode, tail_lo, tail_hi);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+extern "C" int hb_launch_tail(int id, const hb_tdims *d, const hb_tail_tab *tab, long long n_trees, const double *in, double *ux, double *pi,
+		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream)
+	{
+	if(tail_hi<=tail_lo || n_trees<=0) return 0;
+	cudaStream_t st = (cudaStream_t)stream;
+	switch(id)
+		{
+		case 0: return hbk_tail_launch<hbk_v0>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st);
+		case 1: return hbk_tail_launch<hbk_v1>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st);
+		case 2: return hbk_tail_launch<hbk_v2>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st);
+		}
+	return -2;
+	}
+
 #ifdef HBF_TIMING
 extern "C" int hb_debug_timing(long long *d_buf)
 	{

@@ -22,6 +22,8 @@ struct hpmpc_b200_tree
 	int *tail_root;
 	hb_tdims dims;           /* device pointers inside */
 	int sms;
+	int tail_fast_id, t_ipw, t_smem_warp;   /* size-specialised tail kernel, -1 when the tails do not qualify */
+	hb_tail_tab tab;
 	};
 
 int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
@@ -52,6 +54,23 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 	int cut = 0;
 	for(n=0; n<Nn; n++) if(t->tn[n].nkids>1 && t->stage[n]+1>cut) cut = t->stage[n]+1;
 	t->cut_stage = cut;
+	/* do all tails look alike (same length, uniform (nx, nu), leaf without inputs) and does a size-specialised kernel exist? */
+	int tail_len = 0, tnx = -1, tnu = -1, uniform = 1, img = 0;
+	for(n=0; n<Nn && uniform; n++)
+		if(t->stage[n]>=cut)
+			{
+			const hb_tnode *s = &t->tn[n];
+			if(s->nkids>0) { if(tnx<0) { tnx = s->nx; tnu = s->nu; } if(s->nx!=tnx || s->nu!=tnu) uniform = 0; }
+			else if(s->nu!=0 || (tnx>=0 && s->nx!=tnx)) uniform = 0;
+			}
+	tail_len = max_stage - cut + 1;
+	for(n=0; n<Nn && uniform; n++) if(t->tn[n].nkids==0 && t->stage[n]!=max_stage) uniform = 0;
+	t->tail_fast_id = -1;
+	if(uniform && tnx>0 && tail_len>=3 && tail_len<=HB_TAIL_MAXLEN && getenv("HPMPC_B200_NO_FAST")==NULL)
+		{
+		t->tail_fast_id = hb_tail_variant(tnx, tnu);
+		if(t->tail_fast_id>=0) hb_tail_info(t->tail_fast_id, &t->t_ipw, &t->t_smem_warp, &img);
+		}
 	long long o_in = 0, o_ux = 0, o_pi = 0, o_L = 0;
 	int n_top = 0, n_tails = 0;
 	for(n=0; n<Nn; n++)
@@ -67,7 +86,14 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 		s->off_RSQ = (int)o_in; o_in += HB_EVEN(HB_TRI(nux)+nux);
 		s->off_ux = (int)o_ux; o_ux += nux;
 		s->off_pi = (int)o_pi; o_pi += s->nx;
-		s->off_L = (int)o_L; o_L += HB_EVEN(HB_TRI(nux)+2*nux);
+		s->off_L = (int)o_L;
+		{
+		/* factor slot: the generic packed block; for tail nodes of the size-specialised kernel also room for its stash image
+		 * (behind the generic block at the tail root, which the top reads in the generic form) */
+		int gen = HB_EVEN(HB_TRI(nux)+2*nux), slot = gen;
+		if(t->tail_fast_id>=0 && t->stage[n]>=cut) slot = (t->stage[n]==cut) ? gen + img : (gen>img ? gen : img);
+		o_L += slot;
+		}
 		if(t->stage[n]<cut) n_top++;
 		if(t->stage[n]==cut) n_tails++;
 		}
@@ -91,6 +117,32 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 			t->seg_start[++seg] = pos;
 			}
 	if(pos!=Nn) { fprintf(stderr, "hpmpc_b200: tree: inconsistent topology (%d of %d nodes reached)\n", pos, Nn); return -2; }
+	if(t->tail_fast_id>=0)
+		{
+		/* offsets must be affine in the tail index; otherwise fall back to the generic kernel */
+		int m, j, ok = 1;
+		hb_tail_tab *tb = &t->tab;
+		tb->len = tail_len;
+		for(m=0; m<tail_len && ok; m++)
+			{
+			const hb_tnode *a = &t->tn[t->seg_nodes[t->seg_start[1]+m]];
+			const hb_tnode *b = n_tails>1 ? &t->tn[t->seg_nodes[t->seg_start[2]+m]] : a;
+			int gen = HB_EVEN(HB_TRI(a->nu+a->nx)+2*(a->nu+a->nx));
+			if(t->seg_start[2]-t->seg_start[1]!=tail_len) { ok = 0; break; }
+			tb->posB[m] = a->off_BAbt; tb->strB[m] = b->off_BAbt - a->off_BAbt; tb->posQ[m] = a->off_RSQ;
+			tb->posU[m] = a->off_ux; tb->strU[m] = b->off_ux - a->off_ux;
+			tb->posP[m] = a->off_pi; tb->strP[m] = b->off_pi - a->off_pi;
+			tb->posL[m] = a->off_L; tb->strL[m] = b->off_L - a->off_L; tb->posI[m] = a->off_L + (m==0 ? gen : 0);
+			for(j=0; j<n_tails && ok; j++)
+				{
+				const hb_tnode *c = &t->tn[t->seg_nodes[t->seg_start[1+j]+m]];
+				if(t->seg_start[2+j]-t->seg_start[1+j]!=tail_len) { ok = 0; break; }
+				ok = c->off_BAbt==tb->posB[m]+j*tb->strB[m] && c->off_RSQ==tb->posQ[m]+j*tb->strB[m] && c->off_ux==tb->posU[m]+j*tb->strU[m]
+					&& c->off_pi==tb->posP[m]+j*tb->strP[m] && c->off_L==tb->posL[m]+j*tb->strL[m];
+				}
+			}
+		if(!ok) t->tail_fast_id = -1;          /* not affine: the generic tail kernel serves this tree */
+		}
 	t->dims.Nn = Nn; t->dims.nzM = nzM; t->dims.nxM = nxM; t->dims.n_seg = t->n_seg;
 	t->dims.in_stride = o_in; t->dims.ux_stride = HB_EVEN(o_ux); t->dims.pi_stride = HB_EVEN(o_pi); t->dims.L_stride = o_L;
 	t->sms = 148;
@@ -203,6 +255,16 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 		if(t->n_top==0) return 0;
 		launch_shape(t, n_trees, &grid, &warps);
 		return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 2, 0, 1, grid, warps, stream);
+		}
+	if(t->tail_fast_id>=0)
+		{
+		long long items = n_trees*(tail_hi-tail_lo), groups = (items + t->t_ipw - 1)/t->t_ipw;
+		int w = 8;
+		while(w>1 && w*t->t_smem_warp>113*1024) w--;
+		int per_sm = (228*1024)/(w*t->t_smem_warp+1024); if(per_sm<1) per_sm = 1; if(per_sm*w>16) per_sm = 16/w;
+		long long need = (groups + w - 1)/w, cap = (long long)t->sms*per_sm;
+		grid = (int)(need<cap ? (need<1 ? 1 : need) : cap);
+		return hb_launch_tail(t->tail_fast_id, &t->dims, &t->tab, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, tail_lo, tail_hi, grid, w, stream);
 		}
 	launch_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
 	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, 1+tail_lo, 1+tail_hi, grid, warps, stream);
