@@ -64,7 +64,7 @@ typedef struct hb_tnode
 
 typedef struct hb_tdims
 	{
-	int Nn, nzM, nxM, n_seg;    /* n_seg segments: segment 0 = top (may be empty), 1.. = tails */
+	int Nn, nzM, nxM, n_seg;    /* segments: one per top node (ordered by level), then one per tail */
 	long long in_stride, ux_stride, pi_stride, L_stride;
 	const hb_tnode *tn;         /* [Nn]            (device pointer in kernel launches) */
 	const int *seg_start;       /* [n_seg+1]       first entry of each segment in seg_nodes */

@@ -18,7 +18,8 @@ struct hpmpc_b200_tree
 	int device, Nn, cut_stage, n_tails, n_top;
 	hb_tnode *tn;            /* host copy */
 	int *stage;
-	int *seg_start, *seg_nodes, n_seg;
+	int *seg_start, *seg_nodes, n_seg;   /* segments: every top node on its own (ordered by level), then one segment per tail */
+	int *lvl_seg;            /* [cut+1] first segment of each top level */
 	int *tail_root;
 	hb_tdims dims;           /* device pointers inside */
 	int sms;
@@ -97,17 +98,23 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 		if(t->stage[n]<cut) n_top++;
 		if(t->stage[n]==cut) n_tails++;
 		}
-	t->n_top = n_top; t->n_tails = n_tails; t->n_seg = 1+n_tails;
+	t->n_top = n_top; t->n_tails = n_tails; t->n_seg = n_top+n_tails;
 	t->seg_start = calloc(t->n_seg+1, sizeof(int)); t->seg_nodes = calloc(Nn, sizeof(int)); t->tail_root = calloc(n_tails+1, sizeof(int));
-	int pos = 0, seg = 0;
+	t->lvl_seg = calloc(cut+2, sizeof(int));
+	int pos = 0, seg = 0, lv;
 	t->seg_start[0] = 0;
-	for(n=0; n<Nn; n++) if(t->stage[n]<cut) t->seg_nodes[pos++] = n;
-	t->seg_start[++seg] = pos;
+	/* top: nodes are in BFS order, so the nodes of a level are contiguous; one single-node segment each (level-parallel launches) */
+	for(lv=0; lv<cut; lv++)
+		{
+		t->lvl_seg[lv] = seg;
+		for(n=0; n<Nn; n++) if(t->stage[n]==lv) { t->seg_nodes[pos++] = n; t->seg_start[++seg] = pos; }
+		}
+	t->lvl_seg[cut] = seg;
 	for(n=0; n<Nn; n++)
 		if(t->stage[n]==cut)
 			{
 			int m = n;
-			t->tail_root[seg-1] = n;
+			t->tail_root[seg-n_top] = n;
 			for(;;)
 				{
 				t->seg_nodes[pos++] = m;
@@ -125,18 +132,18 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 		tb->len = tail_len;
 		for(m=0; m<tail_len && ok; m++)
 			{
-			const hb_tnode *a = &t->tn[t->seg_nodes[t->seg_start[1]+m]];
-			const hb_tnode *b = n_tails>1 ? &t->tn[t->seg_nodes[t->seg_start[2]+m]] : a;
+			const hb_tnode *a = &t->tn[t->seg_nodes[t->seg_start[n_top]+m]];
+			const hb_tnode *b = n_tails>1 ? &t->tn[t->seg_nodes[t->seg_start[n_top+1]+m]] : a;
 			int gen = HB_EVEN(HB_TRI(a->nu+a->nx)+2*(a->nu+a->nx));
-			if(t->seg_start[2]-t->seg_start[1]!=tail_len) { ok = 0; break; }
+			if(t->seg_start[n_top+1]-t->seg_start[n_top]!=tail_len) { ok = 0; break; }
 			tb->posB[m] = a->off_BAbt; tb->strB[m] = b->off_BAbt - a->off_BAbt; tb->posQ[m] = a->off_RSQ;
 			tb->posU[m] = a->off_ux; tb->strU[m] = b->off_ux - a->off_ux;
 			tb->posP[m] = a->off_pi; tb->strP[m] = b->off_pi - a->off_pi;
 			tb->posL[m] = a->off_L; tb->strL[m] = b->off_L - a->off_L; tb->posI[m] = a->off_L + (m==0 ? gen : 0);
 			for(j=0; j<n_tails && ok; j++)
 				{
-				const hb_tnode *c = &t->tn[t->seg_nodes[t->seg_start[1+j]+m]];
-				if(t->seg_start[2+j]-t->seg_start[1+j]!=tail_len) { ok = 0; break; }
+				const hb_tnode *c = &t->tn[t->seg_nodes[t->seg_start[n_top+j]+m]];
+				if(t->seg_start[n_top+j+1]-t->seg_start[n_top+j]!=tail_len) { ok = 0; break; }
 				ok = c->off_BAbt==tb->posB[m]+j*tb->strB[m] && c->off_RSQ==tb->posQ[m]+j*tb->strB[m] && c->off_ux==tb->posU[m]+j*tb->strU[m]
 					&& c->off_pi==tb->posP[m]+j*tb->strP[m] && c->off_L==tb->posL[m]+j*tb->strL[m];
 				}
@@ -172,7 +179,7 @@ void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
 		cudaSetDevice(t->device);
 		cudaFree((void*)t->dims.tn); cudaFree((void*)t->dims.seg_start); cudaFree((void*)t->dims.seg_nodes);
 		}
-	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->tail_root); free(t);
+	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->tail_root); free(t);
 	}
 
 void hpmpc_b200_tree_sizes_get(const hpmpc_b200_tree *t, hpmpc_b200_tree_sizes *o)
@@ -252,9 +259,21 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 	int grid, warps;
 	if(phase==1)
 		{
-		if(t->n_top==0) return 0;
-		launch_shape(t, n_trees, &grid, &warps);
-		return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 2, 0, 1, grid, warps, stream);
+		/* the top, level by level: all nodes of a level are independent (one warp per (tree, node)) */
+		int lv, rc;
+		for(lv=t->cut_stage-1; lv>=0; lv--)
+			{
+			int a = t->lvl_seg[lv], b = t->lvl_seg[lv+1];
+			launch_shape(t, n_trees*(b-a), &grid, &warps);
+			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, grid, warps, stream))) return rc;
+			}
+		for(lv=0; lv<t->cut_stage; lv++)
+			{
+			int a = t->lvl_seg[lv], b = t->lvl_seg[lv+1];
+			launch_shape(t, n_trees*(b-a), &grid, &warps);
+			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, grid, warps, stream))) return rc;
+			}
+		return 0;
 		}
 	if(t->tail_fast_id>=0)
 		{
@@ -267,7 +286,7 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 		return hb_launch_tail(t->tail_fast_id, &t->dims, &t->tab, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, tail_lo, tail_hi, grid, w, stream);
 		}
 	launch_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
-	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, 1+tail_lo, 1+tail_hi, grid, warps, stream);
+	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, t->n_top+tail_lo, t->n_top+tail_hi, grid, warps, stream);
 	}
 
 int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in,
