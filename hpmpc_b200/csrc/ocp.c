@@ -39,7 +39,8 @@ struct hpmpc_b200_ocp
 	double *scratch; size_t scratch_bytes;
 	int *counter;
 	/* staging for the host-buffer entry points */
-	cudaStream_t s_copy[2];
+	cudaStream_t s_copy[2], s_comp;
+	cudaEvent_t ev_in[2], ev_done[2];
 	double *stage_in[2], *stage_out[2]; size_t stage_in_bytes, stage_out_bytes;
 	cudaEvent_t ev[2];
 	};
@@ -212,7 +213,10 @@ void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p)
 		if(p->stage_out[k]) cudaFree(p->stage_out[k]);
 		if(p->s_copy[k]) cudaStreamDestroy(p->s_copy[k]);
 		if(p->ev[k]) cudaEventDestroy(p->ev[k]);
+		if(p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
+		if(p->ev_done[k]) cudaEventDestroy(p->ev_done[k]);
 		}
+	if(p->s_comp) cudaStreamDestroy(p->s_comp);
 	if(p->scratch) cudaFree(p->scratch);
 	if(p->counter) cudaFree(p->counter);
 	cudaFree((void*)p->dims.st); cudaFree((void*)p->dims.idxb); cudaFree((void*)p->dims.c_ux);
@@ -405,7 +409,10 @@ static int ensure_staging(hpmpc_b200_ocp *p, size_t in_bytes, size_t out_bytes)
 		{
 		if(!p->s_copy[k]) CK(cudaStreamCreateWithFlags(&p->s_copy[k], cudaStreamNonBlocking));
 		if(!p->ev[k]) CK(cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming));
+		if(!p->ev_in[k]) CK(cudaEventCreateWithFlags(&p->ev_in[k], cudaEventDisableTiming));
+		if(!p->ev_done[k]) CK(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
 		}
+	if(!p->s_comp) CK(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
 	if(in_bytes>p->stage_in_bytes)
 		{
 		for(k=0; k<2; k++) { if(p->stage_in[k]) CK(cudaFree(p->stage_in[k])); p->stage_in[k] = NULL; CK(cudaMalloc((void**)&p->stage_in[k], in_bytes)); }
@@ -489,7 +496,9 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 	if(ensure_staging(p, in_b, sizeof(double)*out_d)) return -1;
 	const long long ws = p->ipm_ws;
 	const int slots = p->i_grid*p->i_warps;
-	if(ensure_scratch(p, sizeof(double)*(size_t)2*slots*ws)) return -1;
+	if(ensure_scratch(p, sizeof(double)*(size_t)slots*ws)) return -1;
+	/* copies alternate between two staging buffers / copy streams; the waves of all chunks run back to back on ONE compute
+	 * stream (two IPM kernels sharing the SMs would drift apart in the instruction cache, see ipm_waves) */
 	long long done; int k = 0;
 	for(done=0; done<n_inst; done+=cs, k^=1)
 		{
@@ -501,8 +510,12 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 		CK(cudaMemcpyAsync(d_in, h_in + (size_t)done*p->dims.in_stride, sizeof(double)*(size_t)m*p->dims.in_stride, cudaMemcpyHostToDevice, st));
 		if(warm_start) CK(cudaMemcpyAsync(d_ux, h_ux + (size_t)done*p->dims.ux_stride, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(d_info, 0, sizeof(double)*(size_t)m*info_len, st));
+		CK(cudaEventRecord(p->ev_in[k], st));
+		CK(cudaStreamWaitEvent(p->s_comp, p->ev_in[k], 0));
 		if(ipm_waves(p, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
-				p->scratch + (size_t)k*slots*ws, p->counter + 8*k, lam_len, st)) return -1;
+				p->scratch, p->counter, lam_len, p->s_comp)) return -1;
+		CK(cudaEventRecord(p->ev_done[k], p->s_comp));
+		CK(cudaStreamWaitEvent(st, p->ev_done[k], 0));
 		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));
 		if(p->lam_stride>0)
