@@ -310,9 +310,7 @@ def run_ours(args):
         return out
 
     def bench_tree(steps, warmup):
-        """BASELINE config 5: scenario trees md=4, Nr=3, Nh=20, nx=12, nu=5 (1173 nodes).  The 64 tails below the robust horizon
-        are sharded over the ranks (strong scaling); the one exchange per solve is an all-gather of the tail-root factor blocks
-        (NCCL over NVLink); the 21-node top is solved redundantly on every rank."""
+        """BASELINE config 5: scenario trees md=4, Nr=3, Nh=20, nx=12, nu=5 (1173 nodes), subtrees sharded over the ranks (strong scaling)."""
         from hpmpc_b200 import tree as T
         t0 = T.mass_spring_tree(12, 5, 4, 3, 20)
         h = T.TreeBatch(t0, device=local)
@@ -328,25 +326,29 @@ def run_ours(args):
         ux = torch.zeros((n, h.sz.ux_stride), dtype=torch.float64, device=dev)
         pi = torch.zeros((n, h.sz.pi_stride), dtype=torch.float64, device=dev)
         Lst = torch.zeros((n, h.sz.L_stride), dtype=torch.float64, device=dev)
-        lo, hi = shard_range(h.sz.n_tails, rank, world)
-        # factor slots of the tail roots are equally spaced in the per-tree stash: the exchange moves whole slots
-        o0 = h.tails[0]["off_L"]
-        ln = (h.tails[1]["off_L"] - o0) if h.sz.n_tails > 1 else h.tails[0]["len_L"]
-        assert ln >= h.tails[0]["len_L"] and all(h.tails[j]["off_L"] == o0 + j * ln for j in range(h.sz.n_tails))
-        even = h.sz.n_tails % world == 0
+        # subtree sharding: the 16 depth-2 subtrees (their roots, their 4 tails each) are split over the ranks; the one exchange per
+        # solve is an all-gather of the subtree roots' factor blocks (NCCL over NVLink); the 5 nodes above are solved redundantly
+        ns = h.sz.n_shard_nodes
+        lo, hi = shard_range(ns, rank, world)
+        tlo, thi = (h.subtrees[lo]["tail_lo"], h.subtrees[hi - 1]["tail_hi"]) if hi > lo else (0, 0)
+        o0, ln = h.subtrees[0]["off_L"], h.subtrees[0]["len_L"]
+        assert all(h.subtrees[k]["off_L"] == o0 + k * ln for k in range(ns))             # subtree roots are contiguous in the stash
+        even = ns % world == 0
         ph = h.L.hpmpc_b200_d_tree_back_ric_rec_sv_phase
         args_ = (d_in.data_ptr(), ux.data_ptr(), pi.data_ptr(), Lst.data_ptr(), st)
         gathered = torch.empty((world, n, (hi - lo) * ln), dtype=torch.float64, device=dev) if world > 1 else None
 
         def launch():
-            assert ph(h.h, n, 0, lo, hi, *args_) == 0
+            assert ph(h.h, n, 0, tlo, thi, *args_) == 0
+            assert ph(h.h, n, 3, lo, hi, *args_) == 0
             if world > 1:
-                assert even, "tails must divide evenly over the ranks"
+                assert even, "subtrees must divide evenly over the ranks"
                 mine = Lst[:, o0 + lo * ln:o0 + hi * ln].contiguous()
                 dist.all_gather_into_tensor(gathered, mine)
-                Lst[:, o0:o0 + h.sz.n_tails * ln] = gathered.permute(1, 0, 2).reshape(n, -1)
-            assert ph(h.h, n, 1, 0, 0, *args_) == 0
-            assert ph(h.h, n, 2, lo, hi, *args_) == 0
+                Lst[:, o0:o0 + ns * ln] = gathered.permute(1, 0, 2).reshape(n, -1)
+            assert ph(h.h, n, 4, 0, 0, *args_) == 0
+            assert ph(h.h, n, 5, lo, hi, *args_) == 0
+            assert ph(h.h, n, 2, tlo, thi, *args_) == 0
         tot_ms, per = time_steps(launch, steps, warmup, stream, barrier)
         tot_ms = reduce_max_time(tot_ms, dev)
         # flops: edge-wise sums of SURVEY.md section 8d; bytes: inputs once + factors written and read + outputs
@@ -363,11 +365,11 @@ def run_ours(args):
                "warmup": warmup, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": {"workload": f"scenario-tree Riccati factor+solve (d_tree_back_ric_rec_sv), {n} trees, md=4 Nr=3 Nh=20 nx=12 nu=5 (1173 nodes), FP64",
-                          "parallelism": f"64 tails sharded over {world} GPU(s), top replicated, one all-gather of tail-root factor blocks per solve"},
+                          "parallelism": f"16 depth-2 subtrees sharded over {world} GPU(s), 5 nodes above replicated, one all-gather of subtree-root factor blocks per solve"},
                "roofline": {"bound": "hbm", "achieved": Bt * n / (float(np.mean(per)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": Bt * n / (float(np.mean(per)) * 1e-3) / 1e9 / hbm_peak, "traffic": None, "kernel": "hb_tree_kernel (3 launches)",
                             "algorithmic_bytes_per_tree": Bt, "algorithmic_flops_per_tree": F},
-               "gpu_launches": 3 * steps}
+               "gpu_launches": 8 * steps}
         h.close()
         return out
 

@@ -187,6 +187,7 @@ void hpmpc_b200_tree_sizes_get(const hpmpc_b200_tree *t, hpmpc_b200_tree_sizes *
 	o->in_stride = t->dims.in_stride; o->ux_stride = t->dims.ux_stride; o->pi_stride = t->dims.pi_stride; o->L_stride = t->dims.L_stride;
 	o->Nn = t->Nn; o->nzM = t->dims.nzM; o->nxM = t->dims.nxM;
 	o->n_tails = t->n_tails; o->n_top_nodes = t->n_top; o->cut_stage = t->cut_stage;
+	o->n_shard_nodes = t->cut_stage>0 ? t->lvl_seg[t->cut_stage] - t->lvl_seg[t->cut_stage-1] : 0;
 	}
 
 void hpmpc_b200_tree_node_offsets(const hpmpc_b200_tree *t, int n, int *off_BAbt, int *off_RSQ, int *off_ux, int *off_pi, int *off_L)
@@ -206,6 +207,18 @@ void hpmpc_b200_tree_tail_root(const hpmpc_b200_tree *t, int tail, int *node, in
 	if(node) *node = n;
 	if(off_L) *off_L = t->tn[n].off_L;
 	if(len_L) *len_L = HB_EVEN(HB_TRI(nux)+2*nux);
+	}
+
+void hpmpc_b200_tree_shard_node(const hpmpc_b200_tree *t, int k, int *node, int *off_L, int *len_L, int *tail_lo, int *tail_hi)
+	{
+	int n = t->seg_nodes[t->seg_start[t->lvl_seg[t->cut_stage-1]+k]];
+	int nux = t->tn[n].nu + t->tn[n].nx;
+	if(node) *node = n;
+	if(off_L) *off_L = t->tn[n].off_L;
+	if(len_L) *len_L = HB_EVEN(HB_TRI(nux)+2*nux);
+	/* kids of a node are contiguous and tail roots are numbered in BFS order */
+	if(tail_lo) *tail_lo = t->tn[n].first_kid - t->tail_root[0];
+	if(tail_hi) *tail_hi = t->tn[n].first_kid + t->tn[n].nkids - t->tail_root[0];
 	}
 
 int hpmpc_b200_tree_pack_instance(const hpmpc_b200_tree *t, double *const *A, double *const *B, double *const *b,
@@ -254,22 +267,32 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 	{
 	if(n_trees<=0) return 0;
 	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
-	if(tail_lo<0 || tail_hi>t->n_tails || tail_lo>tail_hi) return -2;
+	if(phase==0 || phase==2) { if(tail_lo<0 || tail_hi>t->n_tails || tail_lo>tail_hi) return -2; }
+	if(phase==3 || phase==5) { if(t->cut_stage<1 || tail_lo<0 || tail_lo>tail_hi || tail_hi>t->lvl_seg[t->cut_stage]-t->lvl_seg[t->cut_stage-1]) return -2; }
 	CK(cudaSetDevice(t->device));
 	int grid, warps;
-	if(phase==1)
+	if(phase==1 || phase==3 || phase==4 || phase==5)
 		{
-		/* the top, level by level: all nodes of a level are independent (one warp per (tree, node)) */
+		/* the top, level by level: all nodes of a level are independent (one warp per (tree, node)).  Phases 3 / 5 restrict
+		 * the deepest top level to the subtree roots [lo, hi); phase 4 is everything above that level. */
 		int lv, rc;
-		for(lv=t->cut_stage-1; lv>=0; lv--)
+		const int deep = t->cut_stage-1;
+		if(t->n_top==0) return 0;
+		for(lv=deep; lv>=0; lv--)
 			{
 			int a = t->lvl_seg[lv], b = t->lvl_seg[lv+1];
+			if(phase==5 || (phase==4 && lv==deep) || (phase==3 && lv<deep)) continue;
+			if(phase==3) { b = a + tail_hi; a = a + tail_lo; }
+			if(b<=a) continue;
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
 			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, grid, warps, stream))) return rc;
 			}
-		for(lv=0; lv<t->cut_stage; lv++)
+		for(lv=0; lv<=deep; lv++)
 			{
 			int a = t->lvl_seg[lv], b = t->lvl_seg[lv+1];
+			if(phase==3 || (phase==4 && lv==deep) || (phase==5 && lv<deep)) continue;
+			if(phase==5) { b = a + tail_hi; a = a + tail_lo; }
+			if(b<=a) continue;
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
 			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, grid, warps, stream))) return rc;
 			}

@@ -25,7 +25,8 @@ class Node(C.Structure):          # reference include/tree.h:34-44
 
 class TreeSizes(C.Structure):
     _fields_ = [("in_stride", C.c_longlong), ("ux_stride", C.c_longlong), ("pi_stride", C.c_longlong), ("L_stride", C.c_longlong),
-                ("Nn", C.c_int), ("nzM", C.c_int), ("nxM", C.c_int), ("n_tails", C.c_int), ("n_top_nodes", C.c_int), ("cut_stage", C.c_int)]
+                ("Nn", C.c_int), ("nzM", C.c_int), ("nxM", C.c_int), ("n_tails", C.c_int), ("n_top_nodes", C.c_int), ("cut_stage", C.c_int),
+                ("n_shard_nodes", C.c_int)]
 
 
 def number_of_nodes(md: int, Nr: int, Nh: int) -> int:
@@ -181,6 +182,12 @@ class TreeBatch:
             v = [C.c_int() for _ in range(5)]
             L.hpmpc_b200_tree_node_offsets(self.h, n, *[C.byref(x) for x in v])
             self.off.append(dict(zip(("BAbt", "RSQ", "ux", "pi", "L"), [x.value for x in v])))
+        L.hpmpc_b200_tree_shard_node.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 5
+        self.subtrees = []
+        for k in range(self.sz.n_shard_nodes):
+            v = [C.c_int() for _ in range(5)]
+            L.hpmpc_b200_tree_shard_node(self.h, k, *[C.byref(x) for x in v])
+            self.subtrees.append(dict(node=v[0].value, off_L=v[1].value, len_L=v[2].value, tail_lo=v[3].value, tail_hi=v[4].value))
         self.tails = []
         for j in range(self.sz.n_tails):
             v = [C.c_int() for _ in range(3)]

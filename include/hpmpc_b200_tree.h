@@ -42,6 +42,7 @@ typedef struct hpmpc_b200_tree_sizes
 	long long in_stride, ux_stride, pi_stride, L_stride;   /* doubles per tree */
 	int Nn, nzM, nxM;
 	int n_tails, n_top_nodes, cut_stage;
+	int n_shard_nodes;          /* nodes of the deepest top level (cut_stage-1): the roots of the subtrees that shard over GPUs */
 	} hpmpc_b200_tree_sizes;
 
 /* nodes in BFS order (kids of a node contiguous, as the reference's setup_tree builds them,
@@ -54,6 +55,9 @@ void hpmpc_b200_tree_sizes_get(const hpmpc_b200_tree *t, hpmpc_b200_tree_sizes *
 void hpmpc_b200_tree_node_offsets(const hpmpc_b200_tree *t, int n, int *off_BAbt, int *off_RSQ, int *off_ux, int *off_pi, int *off_L);
 /* tail j = 0..n_tails-1: its root node and where that node's factor block sits in the per-tree stash */
 void hpmpc_b200_tree_tail_root(const hpmpc_b200_tree *t, int tail, int *node, int *off_L, int *len_L);
+/* subtree k = 0..n_shard_nodes-1: its root node (level cut_stage-1), that node's factor block in the per-tree stash, and the
+ * range of tails [tail_lo, tail_hi) below it */
+void hpmpc_b200_tree_shard_node(const hpmpc_b200_tree *t, int k, int *node, int *off_L, int *len_L, int *tail_lo, int *tail_hi);
 /* host-side packing of one tree from node/edge-indexed column-major arrays: A[k] nx_k x nx_dad, B[k] nx_k x nu_dad,
  * b[k] nx_k for k >= 1 (entry 0 unused); Q[n] nx x nx, S[n] nu x nx, R[n] nu x nu, q[n], r[n] for every node */
 int  hpmpc_b200_tree_pack_instance(const hpmpc_b200_tree *t, double *const *A, double *const *B, double *const *b,
@@ -62,7 +66,11 @@ int  hpmpc_b200_tree_pack_instance(const hpmpc_b200_tree *t, double *const *A, d
 /* whole solve on one GPU (phases 0, 1, 2 back to back) */
 int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in,
                                             double *d_ux, double *d_pi, double *d_L, void *stream);
-/* one phase: 0 = backward over tails [tail_lo, tail_hi), 1 = top (backward + forward), 2 = forward over tails [tail_lo, tail_hi) */
+/* one phase; lo/hi are tail indices for phases 0 and 2, subtree indices for phases 3 and 5, ignored otherwise:
+ *   0 = backward over tails [lo, hi)          2 = forward over tails [lo, hi)
+ *   1 = the whole top (backward + forward)    -- tail sharding: 0, exchange tail-root blocks, 1, 2
+ *   3 = backward over subtree roots [lo, hi)  4 = levels above the subtree roots (backward + forward)  5 = forward over subtree roots [lo, hi)
+ *                                             -- subtree sharding: 0, 3, exchange subtree-root blocks, 4, 5, 2 */
 int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_trees, int phase, int tail_lo, int tail_hi,
                                             const double *d_in, double *d_ux, double *d_pi, double *d_L, void *stream);
 

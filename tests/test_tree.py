@@ -55,6 +55,8 @@ def test_tree_handle_layout_host_only():
     h = T.TreeBatch(t, device=-1)
     assert (h.sz.Nn, h.sz.n_tails, h.sz.n_top_nodes, h.sz.cut_stage) == (1173, 64, 21, 3)
     assert [tl["node"] for tl in h.tails] == list(range(21, 85))
+    assert h.sz.n_shard_nodes == 16 and [st["node"] for st in h.subtrees] == list(range(5, 21))
+    assert [(st["tail_lo"], st["tail_hi"]) for st in h.subtrees] == [(4 * k, 4 * k + 4) for k in range(16)]
     blk = h.pack(t)
     n = 100
     d = t.topo["dad"][n]
@@ -183,6 +185,57 @@ def test_tree_gpu_golden_and_phase_split_equals_single_pass():
             if topo["nkids"][m] == 0:
                 break
             m = topo["first_kid"][m]
+    for node in range(topo["Nn"]):
+        for r in ([owner[node]] if node in owner else range(world)):
+            a, ln = h.off[node]["ux"], trees[0].nu[node] + trees[0].nx[node]
+            assert torch.equal(st[r]["ux"][:, a:a + ln], ux0[:, a:a + ln]), node
+            a, ln = h.off[node]["pi"], trees[0].nx[node]
+            assert torch.equal(st[r]["pi"][:, a:a + ln], pi0[:, a:a + ln]), node
+    h.close()
+
+
+@pytest.mark.gpu
+def test_tree_gpu_subtree_sharding_equals_single_pass():
+    """Config 5 solved the way four GPUs would with SUBTREE sharding: every 'rank' owns four of the 16 depth-2 subtrees (their
+    tails and their roots), the subtree-root factor blocks are exchanged, the five nodes above are solved redundantly, and the
+    union of the results must equal the single-pass result bit for bit."""
+    import torch
+    xis = problems.instance_xi(5, first=300)
+    trees = [T.mass_spring_tree(12, 5, 4, 3, 20, xi=tuple(x)) for x in xis]
+    h = T.TreeBatch(trees[0], device=0)
+    blocks = np.stack([h.pack(t) for t in trees])
+    d_in, ux0, pi0, _ = _solve(h, blocks)
+    n, world = len(trees), 4
+    st = [dict(ux=torch.zeros_like(ux0), pi=torch.zeros_like(pi0), L=torch.zeros((n, h.sz.L_stride), dtype=torch.float64, device="cuda")) for _ in range(world)]
+    ph = h.L.hpmpc_b200_d_tree_back_ric_rec_sv_phase
+    rng = [tail_range(h.sz.n_shard_nodes, r, world) for r in range(world)]
+    trng = [(h.subtrees[a]["tail_lo"], h.subtrees[b - 1]["tail_hi"]) for a, b in rng]
+    args = lambda r: (d_in.data_ptr(), st[r]["ux"].data_ptr(), st[r]["pi"].data_ptr(), st[r]["L"].data_ptr(), None)
+    for r in range(world):
+        assert ph(h.h, n, 0, trng[r][0], trng[r][1], *args(r)) == 0
+        assert ph(h.h, n, 3, rng[r][0], rng[r][1], *args(r)) == 0
+    torch.cuda.synchronize()
+    for r in range(world):                       # the exchange: factor blocks of the subtree roots owned by the others
+        for s in range(world):
+            if s != r:
+                for k in range(*rng[s]):
+                    o, ln = h.subtrees[k]["off_L"], h.subtrees[k]["len_L"]
+                    st[r]["L"][:, o:o + ln] = st[s]["L"][:, o:o + ln]
+    for r in range(world):
+        assert ph(h.h, n, 4, 0, 0, *args(r)) == 0
+        assert ph(h.h, n, 5, rng[r][0], rng[r][1], *args(r)) == 0
+        assert ph(h.h, n, 2, trng[r][0], trng[r][1], *args(r)) == 0
+    torch.cuda.synchronize()
+    topo = trees[0].topo
+    owner = {}
+    for r in range(world):
+        for k in range(*rng[r]):
+            stack = [h.subtrees[k]["node"]]
+            while stack:
+                m = stack.pop()
+                owner[m] = r
+                stack += [topo["first_kid"][m] + i for i in range(topo["nkids"][m])]
+    assert len(owner) == topo["Nn"] - 5
     for node in range(topo["Nn"]):
         for r in ([owner[node]] if node in owner else range(world)):
             a, ln = h.off[node]["ux"], trees[0].nu[node] + trees[0].nx[node]
