@@ -113,6 +113,8 @@ int hb_tail_variant(int nx, int nu);                     /* -1 when no size-spec
 int hb_tail_info(int id, int *ipw, int *smem_warp, int *image_doubles);
 int hb_launch_tail(int id, const hb_tdims *dims, const hb_tail_tab *tab, long long n_trees, const double *in, double *ux, double *pi,
 		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream);
+int hb_launch_top(int id, const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
+		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream);
 long long hb_ipm_work_doubles(const hb_dims *dims);
 int hb_smem_bytes_per_warp(const hb_dims *dims);
 int hb_smem_bytes_per_warp_sz(int nzM, int nxM);

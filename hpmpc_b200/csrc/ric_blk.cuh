@@ -138,7 +138,8 @@ struct hbk_nop { __device__ __forceinline__ void operator()() const {} };
 
 /* sBW: [B A b]' of the stage on entry, W (leading dimension LDW) afterwards ; sQ: RSQrq of the stage ; xc: x-columns of L_{n+1} ;
  * pre_h() is called after W has been computed and before RSQrq is read (the place to wait for a separately fetched RSQrq) */
-template<class C, int KIND, int LDW, class F>
+/* ACC: add the W W' of a further kid (scenario-tree nodes with several kids) to an H that is already in the tile */
+template<class C, int KIND, int LDW, class F, bool ACC = false>
 __device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double *__restrict__ sBW, const double *__restrict__ sQ,
 		const double *__restrict__ xc, hbk_tile<C> &T, F pre_h)
 	{
@@ -225,6 +226,8 @@ __device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double 
 			}
 		}
 	HBF_STAMP(110);
+	if(!ACC)
+	{
 	pre_h();
 	/* ---- H <- RSQrq (before W is stored: with LDW > NX the W rows run over the RSQ part of the buffer) ---- */
 	#pragma unroll
@@ -275,6 +278,7 @@ __device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double 
 			if(e>=cc && ae>=0 && acol>=0) hc = sQ[HB_TRI(ae>=0 ? ae : 0) + (acol>=0 ? acol : 0)];
 			T.Z[e][cc] = hc;
 			}
+	}
 	if(KIND==HBF_LAST) { __syncwarp(); return; }
 	{
 	__syncwarp();                       /* every lane has read its inputs: the buffer becomes W */
@@ -908,6 +912,116 @@ __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long 
 				}
 			wait_bar(2+((len-1)&1));
 			hbk_final_pi<C>(ln, ((len-1)&1) ? S1 : S0, ((len-1)&1) ? xs1 : xs0, tmp, pi + tab.posP[len-1] + j*tab.strP[len-1], active);
+			}
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* top of a scenario tree: one (tree, node) work item per G lanes, all nodes of one level per launch.     */
+/* mode 0: H = RSQrq + sum over kids W_k W_k' (d_tree_back_ric_rec_libstr.c:79-156), factor, image -> the */
+/* node's slot; mode 1: u from the node's image, x of every kid (:204-260); pi of a node is computed when   */
+/* the node itself is visited, from its own image (as in the chain kernels).                              */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C>
+__global__ void __launch_bounds__(256, 1) hbk_top_kernel(hb_tdims d, long long n_trees, const double *__restrict__ in,
+		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ L_all, int mode, int seg_lo, int seg_hi, int first)
+	{
+	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
+	constexpr int GEN = HB_EVEN(HB_TRI(NUX)+2*NUX), GEN0 = HB_EVEN(HB_TRI(NU)+2*NU), XC = C::xOff(NX);
+	extern __shared__ __align__(16) double hbf_smem[];
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const int g = lane/G;
+	hbk_lane<C> ln; ln.init(lane%G);
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	double *wbase = hbf_smem + (size_t)warp*C::PER_WARP;
+	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);      /* [0] [B A b]' of a kid, [1] RSQrq / own image, [2] x-columns of a kid */
+	double *ibase = wbase + 8 + (size_t)g*C::PER_INST;
+	double *io = ibase, *LUs = ibase + IOB, *S0 = LUs + LU, *S1 = S0 + SB;
+	double *us = S1 + SB, *xs0 = us + C::even(NU), *xs1 = xs0 + C::XS, *tmp = xs1 + C::XS;
+	if(lane==0)
+		{
+		for(int b=0; b<4; b++) hbf_mbar_init(&bars[b], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+	__syncwarp();
+	uint32_t phase = 0;
+	const int nseg = seg_hi - seg_lo;
+	const long long n_items = n_trees*nseg, n_groups = (n_items + IPW - 1)/IPW;
+	const uint32_t bytes_B = 8u*(uint32_t)(first ? C::even((NU+1)*NX) : BAB);
+	const uint32_t bytes_Q = 8u*(uint32_t)(first ? C::even(HB_TRI(NU)+NU) : C::RSQ);
+	const int gen_own = first ? GEN0 : GEN;
+	asm volatile("fence.proxy.async;" ::: "memory");
+
+	for(long long grp=gw; grp<n_groups; grp+=tw)
+		{
+		long long item = grp*IPW + g;
+		const bool active = item<n_items;
+		if(!active) item = n_items-1;
+		const long long t = item/nseg;
+		const hb_tnode nd = d.tn[d.seg_nodes[d.seg_start[seg_lo + (int)(item - t*nseg)]]];
+		double *ux = ux_all + t*d.ux_stride, *pi = pi_all + t*d.pi_stride, *Lt = L_all + t*d.L_stride;
+		const int mg = lane<IPW ? lane : 0;
+		long long my_item = grp*IPW + mg; if(my_item>=n_items) my_item = n_items-1;
+		const long long my_t = my_item/nseg;
+		const hb_tnode my_nd = d.tn[d.seg_nodes[d.seg_start[seg_lo + (int)(my_item - my_t*nseg)]]];
+		const double *my_in = in + my_t*d.in_stride;
+		const double *my_L = L_all + my_t*d.L_stride;
+		double *my_sm = wbase + 8 + (size_t)mg*C::PER_INST;
+		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
+		const int nkids = nd.nkids;                              /* the same for every node of a level */
+
+		if(mode==0)
+			{
+			hbk_tile<C> T;
+			if(lane==0) hbf_mbar_expect(&bars[1], bytes_Q*IPW);
+			if(lane<IPW) hbf_bulk_g2s(my_sm + BAB, my_in + my_nd.off_RSQ, bytes_Q, &bars[1]);
+			for(int kc=0; kc<nkids; kc++)
+				{
+				if(lane==0) { hbf_mbar_expect(&bars[0], bytes_B*IPW); hbf_mbar_expect(&bars[2], 8u*XC*IPW); }
+				if(lane<IPW)
+					{
+					const hb_tnode kd = d.tn[my_nd.first_kid+kc];
+					hbf_bulk_g2s(my_sm, my_in + kd.off_BAbt, bytes_B, &bars[0]);
+					hbf_bulk_g2s(my_sm + IOB + LU + SB + C::SX, my_L + kd.off_L + GEN + C::SX, 8u*XC, &bars[2]);
+					}
+				wait_bar(0); wait_bar(2);
+				if(kc==0)
+					{
+					if(first) hbk_back_assemble<C, HBF_FIRST, C::LDW>(ln, io, io + BAB, S1 + C::SX, T, [&]() { wait_bar(1); });
+					else      hbk_back_assemble<C, HBF_MID, C::LDW>(ln, io, io + BAB, S1 + C::SX, T, [&]() { wait_bar(1); });
+					}
+				else
+					{
+					if(first) hbk_back_assemble<C, HBF_FIRST, C::LDW, hbk_nop, true>(ln, io, io + BAB, S1 + C::SX, T, hbk_nop());
+					else      hbk_back_assemble<C, HBF_MID, C::LDW, hbk_nop, true>(ln, io, io + BAB, S1 + C::SX, T, hbk_nop());
+					}
+				__syncwarp();
+				}
+			if(first) hbk_back_factor<C, HBF_FIRST>(ln, T, LUs, S0 + C::SX, Lt + nd.off_L + gen_own, hbk_nop());
+			else      hbk_back_factor<C, HBF_MID>(ln, T, LUs, S0 + C::SX, Lt + nd.off_L + gen_own, hbk_nop());
+			__syncwarp();
+			}
+		else
+			{
+			if(lane==0) hbf_mbar_expect(&bars[1], 8u*SB*IPW);
+			if(lane<IPW) hbf_bulk_g2s(my_sm + IOB + LU, my_L + my_nd.off_L + gen_own, 8u*SB, &bars[1]);
+			if(!first)
+				{
+				if(ln.l<NX) xs0[ln.l] = ux[nd.off_ux + NU + ln.l];
+				if(C::R>1 && ln.l+G<NX) xs0[ln.l+G] = ux[nd.off_ux + NU + ln.l + G];
+				}
+			__syncwarp();
+			wait_bar(1);
+			for(int kc=0; kc<nkids; kc++)
+				{
+				if(lane==0) hbf_mbar_expect(&bars[0], bytes_B*IPW);
+				if(lane<IPW) hbf_bulk_g2s(my_sm, my_in + d.tn[my_nd.first_kid+kc].off_BAbt, bytes_B, &bars[0]);
+				wait_bar(0);
+				const hb_tnode kd = d.tn[nd.first_kid+kc];
+				/* u and pi of the node are recomputed for every kid (a few dozen FMAs) to reuse the chain routine unchanged */
+				if(first) hbk_stage_forward<C, HBF_FIRST>(ln, io, S0, us, xs0, xs1, tmp, ux + nd.off_ux, ux + kd.off_ux + NU, pi + nd.off_pi, active);
+				else      hbk_stage_forward<C, HBF_MID>(ln, io, S0, us, xs0, xs1, tmp, ux + nd.off_ux, ux + kd.off_ux + NU, pi + nd.off_pi, active);
+				}
 			}
 		}
 	}

@@ -1070,6 +1070,30 @@ extern "C" int hb_launch_tail(int id, const hb_tdims *d, const hb_tail_tab *tab,
 	return -2;
 	}
 
+template<class C> static int hbk_top_launch(const hb_tdims *d, long long n_trees, const double *in, double *ux, double *pi, double *L,
+		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, cudaStream_t st)
+	{
+	int smem = warps*(int)sizeof(double)*C::PER_WARP;
+	if(hb_prep(hbk_top_kernel<C>, smem)) return -1;
+	hbk_top_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+extern "C" int hb_launch_top(int id, const hb_tdims *d, long long n_trees, const double *in, double *ux, double *pi, double *L,
+		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream)
+	{
+	if(seg_hi<=seg_lo || n_trees<=0) return 0;
+	cudaStream_t st = (cudaStream_t)stream;
+	switch(id)
+		{
+		case 0: return hbk_top_launch<hbk_v0>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st);
+		case 1: return hbk_top_launch<hbk_v1>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st);
+		case 2: return hbk_top_launch<hbk_v2>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st);
+		}
+	return -2;
+	}
+
 #ifdef HBF_TIMING
 extern "C" int hb_debug_timing(long long *d_buf)
 	{

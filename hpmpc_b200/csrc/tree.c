@@ -20,10 +20,12 @@ struct hpmpc_b200_tree
 	int *stage;
 	int *seg_start, *seg_nodes, n_seg;   /* segments: every top node on its own (ordered by level), then one segment per tail */
 	int *lvl_seg;            /* [cut+1] first segment of each top level */
+	int *slot;               /* [Nn] size of each node's factor slot in the stash (doubles) */
 	int *tail_root;
 	hb_tdims dims;           /* device pointers inside */
 	int sms;
 	int tail_fast_id, t_ipw, t_smem_warp;   /* size-specialised tail kernel, -1 when the tails do not qualify */
+	int top_fast;                           /* the top runs on the size-specialised stage routines too */
 	hb_tail_tab tab;
 	};
 
@@ -36,6 +38,7 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 	t->device = device; t->Nn = Nn;
 	t->tn = calloc(Nn, sizeof(hb_tnode));
 	t->stage = calloc(Nn, sizeof(int));
+	t->slot = calloc(Nn, sizeof(int));
 	int nzM = 1, nxM = 1, max_stage = 0;
 	for(n=0; n<Nn; n++)
 		{
@@ -72,6 +75,17 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 		t->tail_fast_id = hb_tail_variant(tnx, tnu);
 		if(t->tail_fast_id>=0) hb_tail_info(t->tail_fast_id, &t->t_ipw, &t->t_smem_warp, &img);
 		}
+	/* the top qualifies when the root has no state (x0 eliminated), every other top node has the tails' (nx, nu) and the
+	 * nodes of a level all have the same number of kids */
+	t->top_fast = (t->tail_fast_id>=0 && cut>0 && getenv("HPMPC_B200_NO_FAST_TOP")==NULL);
+	for(n=0; n<Nn && t->top_fast; n++)
+		if(t->stage[n]<cut)
+			{
+			const hb_tnode *s = &t->tn[n];
+			if(n==0) { if(s->nx!=0 || s->nu!=tnu) t->top_fast = 0; }
+			else if(s->nx!=tnx || s->nu!=tnu) t->top_fast = 0;
+			for(j=n+1; j<Nn && t->stage[j]==t->stage[n]; j++) if(t->tn[j].nkids!=s->nkids) t->top_fast = 0;
+			}
 	long long o_in = 0, o_ux = 0, o_pi = 0, o_L = 0;
 	int n_top = 0, n_tails = 0;
 	for(n=0; n<Nn; n++)
@@ -93,7 +107,9 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 		 * (behind the generic block at the tail root, which the top reads in the generic form) */
 		int gen = HB_EVEN(HB_TRI(nux)+2*nux), slot = gen;
 		if(t->tail_fast_id>=0 && t->stage[n]>=cut) slot = (t->stage[n]==cut) ? gen + img : (gen>img ? gen : img);
+		if(t->top_fast && t->stage[n]<cut) slot = gen + img;
 		o_L += slot;
+		t->slot[n] = slot;
 		}
 		if(t->stage[n]<cut) n_top++;
 		if(t->stage[n]==cut) n_tails++;
@@ -179,7 +195,7 @@ void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
 		cudaSetDevice(t->device);
 		cudaFree((void*)t->dims.tn); cudaFree((void*)t->dims.seg_start); cudaFree((void*)t->dims.seg_nodes);
 		}
-	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->tail_root); free(t);
+	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->slot); free(t->tail_root); free(t);
 	}
 
 void hpmpc_b200_tree_sizes_get(const hpmpc_b200_tree *t, hpmpc_b200_tree_sizes *o)
@@ -203,19 +219,17 @@ void hpmpc_b200_tree_node_offsets(const hpmpc_b200_tree *t, int n, int *off_BAbt
 void hpmpc_b200_tree_tail_root(const hpmpc_b200_tree *t, int tail, int *node, int *off_L, int *len_L)
 	{
 	int n = t->tail_root[tail];
-	int nux = t->tn[n].nu + t->tn[n].nx;
 	if(node) *node = n;
 	if(off_L) *off_L = t->tn[n].off_L;
-	if(len_L) *len_L = HB_EVEN(HB_TRI(nux)+2*nux);
+	if(len_L) *len_L = t->slot[n];           /* the whole slot: generic block and, when present, the stash image */
 	}
 
 void hpmpc_b200_tree_shard_node(const hpmpc_b200_tree *t, int k, int *node, int *off_L, int *len_L, int *tail_lo, int *tail_hi)
 	{
 	int n = t->seg_nodes[t->seg_start[t->lvl_seg[t->cut_stage-1]+k]];
-	int nux = t->tn[n].nu + t->tn[n].nx;
 	if(node) *node = n;
 	if(off_L) *off_L = t->tn[n].off_L;
-	if(len_L) *len_L = HB_EVEN(HB_TRI(nux)+2*nux);
+	if(len_L) *len_L = t->slot[n];           /* the whole slot: generic block and, when present, the stash image */
 	/* kids of a node are contiguous and tail roots are numbered in BFS order */
 	if(tail_lo) *tail_lo = t->tn[n].first_kid - t->tail_root[0];
 	if(tail_hi) *tail_hi = t->tn[n].first_kid + t->tn[n].nkids - t->tail_root[0];
@@ -262,6 +276,17 @@ static void launch_shape(const hpmpc_b200_tree *t, long long items, int *grid, i
 	*warps = w; *grid = (int)(need<cap ? (need<1 ? 1 : need) : cap);
 	}
 
+/* launch shape of the size-specialised kernels: `items` work items, t_ipw of them per warp */
+static void fast_shape(const hpmpc_b200_tree *t, long long items, int *grid, int *warps)
+	{
+	long long groups = (items + t->t_ipw - 1)/t->t_ipw;
+	int w = 8;
+	while(w>1 && w*t->t_smem_warp>113*1024) w--;
+	int per_sm = (228*1024)/(w*t->t_smem_warp+1024); if(per_sm<1) per_sm = 1; if(per_sm*w>16) per_sm = 16/w;
+	long long need = (groups + w - 1)/w, cap = (long long)t->sms*per_sm;
+	*warps = w; *grid = (int)(need<cap ? (need<1 ? 1 : need) : cap);
+	}
+
 int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_trees, int phase, int tail_lo, int tail_hi,
 		const double *d_in, double *d_ux, double *d_pi, double *d_L, void *stream)
 	{
@@ -284,6 +309,12 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 			if(phase==5 || (phase==4 && lv==deep) || (phase==3 && lv<deep)) continue;
 			if(phase==3) { b = a + tail_hi; a = a + tail_lo; }
 			if(b<=a) continue;
+			if(t->top_fast)
+				{
+				fast_shape(t, n_trees*(b-a), &grid, &warps);
+				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, lv==0, grid, warps, stream))) return rc;
+				continue;
+				}
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
 			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, grid, warps, stream))) return rc;
 			}
@@ -293,6 +324,12 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 			if(phase==3 || (phase==4 && lv==deep) || (phase==5 && lv<deep)) continue;
 			if(phase==5) { b = a + tail_hi; a = a + tail_lo; }
 			if(b<=a) continue;
+			if(t->top_fast)
+				{
+				fast_shape(t, n_trees*(b-a), &grid, &warps);
+				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, lv==0, grid, warps, stream))) return rc;
+				continue;
+				}
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
 			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, grid, warps, stream))) return rc;
 			}
@@ -300,13 +337,8 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 		}
 	if(t->tail_fast_id>=0)
 		{
-		long long items = n_trees*(tail_hi-tail_lo), groups = (items + t->t_ipw - 1)/t->t_ipw;
-		int w = 8;
-		while(w>1 && w*t->t_smem_warp>113*1024) w--;
-		int per_sm = (228*1024)/(w*t->t_smem_warp+1024); if(per_sm<1) per_sm = 1; if(per_sm*w>16) per_sm = 16/w;
-		long long need = (groups + w - 1)/w, cap = (long long)t->sms*per_sm;
-		grid = (int)(need<cap ? (need<1 ? 1 : need) : cap);
-		return hb_launch_tail(t->tail_fast_id, &t->dims, &t->tab, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, tail_lo, tail_hi, grid, w, stream);
+		fast_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
+		return hb_launch_tail(t->tail_fast_id, &t->dims, &t->tab, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, tail_lo, tail_hi, grid, warps, stream);
 		}
 	launch_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
 	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, t->n_top+tail_lo, t->n_top+tail_hi, grid, warps, stream);
