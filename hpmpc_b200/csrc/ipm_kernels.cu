@@ -1,0 +1,581 @@
+/*
+ * ipm_kernels.cu -- the fused two-phase Mehrotra IPM kernel (policy-templated on the sweeps) and its C launchers.
+ *   hb_ipm_kernel      whole IPM on device, no host round trip per iteration
+ *                                                <- d_ip2_res_mpc_hard_tv      (mpc_solvers/d_ip2_res_hard.c:116)
+ *                      element-wise steps        <- mpc_solvers/c99/d_aux_ip_hard_lib4.c (lines cited inline)
+ *                      residuals                 <- mpc_solvers/c99/d_res_ip_res_hard.c:39
+ * A translation unit of its own so that it compiles in parallel with the Riccati kernels (the size-specialised
+ * instantiation is ~0.5 MB of SASS).
+ */
+#include "launch_util.cuh"
+#include "layout.h"
+#include "ric_sweeps.cuh"
+#include "ric_fast.cuh"
+#include "ric_ipm_fast.cuh"
+
+extern "C" int hb_smem_bytes_per_warp(const hb_dims *d);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* IPM                                                                                               */
+/* ------------------------------------------------------------------------------------------------ */
+enum { CV_LB=0, CV_UB, CV_LAM_LO, CV_LAM_UP, CV_T_LO, CV_T_UP, CV_DLAM_LO, CV_DLAM_UP, CV_DT_LO, CV_DT_UP,
+       CV_TINV_LO, CV_TINV_UP, CV_LAMT_LO, CV_LAMT_UP, CV_QXD /* "Qx": Hessian diagonal term */,
+       CV_QXG /* "qx": gradient term */, CV_RD_LO, CV_RD_UP, CV_RM_LO, CV_RM_UP, CV_COUNT };
+
+struct hb_ipm_ws
+	{
+	double *L;                               /* factor stash */
+	double *dux, *res_q, *rq0;               /* ux layout */
+	double *dpi, *Pb, *res_b, *b0;           /* pi layout */
+	double *cv;                              /* CV_COUNT x nbp */
+	int nbp;
+	__device__ __forceinline__ double *v(int k) const { return cv + (size_t)k*nbp; }
+	};
+
+__host__ __device__ inline long long hb_ipm_work_doubles_(const hb_dims &d)
+	{
+	long long nbp = HB_EVEN(d.nbtot);
+	return d.L_stride + 3*d.ux_stride + 4*d.pi_stride + (long long)CV_COUNT*nbp;
+	}
+
+__device__ __forceinline__ double hb_warp_min(double v)
+	{
+	for(int o=16; o>0; o>>=1) v = fmin(v, __shfl_xor_sync(HB_FULL, v, o));
+	return v;
+	}
+__device__ __forceinline__ double hb_warp_max(double v)
+	{
+	for(int o=16; o>0; o>>=1) v = fmax(v, __shfl_xor_sync(HB_FULL, v, o));
+	return v;
+	}
+/* fixed-order (deterministic) warp sum */
+__device__ __forceinline__ double hb_warp_sum(double v)
+	{
+	for(int o=16; o>0; o>>=1) v += __shfl_xor_sync(HB_FULL, v, o);
+	return v;
+	}
+
+/* bound part of the residuals: res_d, res_m and their sum (mpc_solvers/c99/d_res_ip_res_hard.c:39-319) */
+__device__ __forceinline__ void hb_ipm_residuals_bounds(int lane, const hb_dims &d, const hb_ipm_ws &w, const double *ux, double &mu2, double &nd)
+	{
+	const double *lam_lo = w.v(CV_LAM_LO), *lam_up = w.v(CV_LAM_UP), *t_lo = w.v(CV_T_LO), *t_up = w.v(CV_T_UP);
+	mu2 = 0.0; nd = 0.0;
+	for(int cc=lane; cc<d.nbtot; cc+=32)
+		{
+		double u = ux[d.c_ux[cc]];
+		double rdl = w.v(CV_LB)[cc] - u + t_lo[cc];
+		double rdu = w.v(CV_UB)[cc] - u - t_up[cc];
+		double rml = lam_lo[cc]*t_lo[cc], rmu = lam_up[cc]*t_up[cc];
+		w.v(CV_RD_LO)[cc] = rdl; w.v(CV_RD_UP)[cc] = rdu;
+		w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
+		mu2 += rml + rmu;
+		nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
+		}
+	mu2 = hb_warp_sum(mu2);
+	}
+
+/* res_q, res_b, res_d, res_m and mu (mpc_solvers/c99/d_res_ip_res_hard.c:39-319); also returns the three
+ * infinity norms used by the high-level wrapper on exit (interfaces/c/fortran_order_interface.c:616-652) */
+__device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+		const double *ux, const double *pi, double *mu, double *norms)
+	{
+	const int lane = c.lane;
+	double nq = 0.0, nb_ = 0.0, nd = 0.0, mu2 = 0.0;
+	const double *lam_lo = w.v(CV_LAM_LO), *lam_up = w.v(CV_LAM_UP), *t_lo = w.v(CV_T_LO), *t_up = w.v(CV_T_UP);
+	for(int cc=lane; cc<d.nbtot; cc+=32)
+		{
+		double u = ux[d.c_ux[cc]];
+		double rdl = w.v(CV_LB)[cc] - u + t_lo[cc];
+		double rdu = w.v(CV_UB)[cc] - u - t_up[cc];
+		double rml = lam_lo[cc]*t_lo[cc], rmu = lam_up[cc]*t_up[cc];
+		w.v(CV_RD_LO)[cc] = rdl; w.v(CV_RD_UP)[cc] = rdu;
+		w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
+		mu2 += rml + rmu;
+		nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
+		}
+	mu2 = hb_warp_sum(mu2);
+	double *xs = c.sV;            /* ux_n */
+	double *ps = c.sV + 64;       /* pi_n */
+	for(int n=0; n<=d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		const int nu = s.nu, nx = s.nx, nux = nu+nx, nx1 = s.nx1;
+		double *H = c.bufA;
+		hb_copy(c, H, in_inst + s.off_RSQ, HB_TRI(nux));
+		if(nx1>0) hb_load_BAbt(c, s, in_inst);
+		for(int i=lane; i<nux; i+=32) xs[i] = ux[s.off_ux+i];
+		for(int j=lane; j<nx1; j+=32) ps[j] = pi[s.off_pi+j];
+		/* rq = rq0 - pi_{n-1} (x part) + (lam_up - lam_lo)[idxb] */
+		for(int i=lane; i<nux; i+=32)
+			{
+			double v = w.rq0[s.off_ux+i];
+			if(n>0 && i>=nu) v -= pi[d.st[n-1].off_pi + (i-nu)];
+			w.res_q[s.off_ux+i] = v;
+			}
+		__syncwarp();
+		for(int j=lane; j<s.nb; j+=32)
+			w.res_q[s.off_ux+d.idxb[s.off_c+j]] += -lam_lo[s.off_c+j] + lam_up[s.off_c+j];
+		__syncwarp();
+		for(int i=lane; i<nux; i+=32)
+			{
+			double acc = w.res_q[s.off_ux+i];
+			const double *hi = H + HB_TRI(i);
+			for(int j=0; j<=i; j++) acc += hi[j]*xs[j];
+			for(int j=i+1; j<nux; j++) acc += H[HB_TRI(j)+i]*xs[j];
+			const double *wr = c.sW + i*c.ldW;
+			for(int j=0; j<nx1; j++) acc += wr[j]*ps[j];
+			w.res_q[s.off_ux+i] = acc;
+			nq = fmax(nq, fabs(acc));
+			}
+		if(nx1>0)
+			{
+			const hb_stage s1 = d.st[n+1];
+			for(int j=lane; j<nx1; j+=32)
+				{
+				double acc = w.b0[s.off_pi+j] - ux[s1.off_ux+s1.nu+j];
+				for(int i=0; i<nux; i++) acc += c.sW[i*c.ldW+j]*xs[i];
+				w.res_b[s.off_pi+j] = acc;
+				nb_ = fmax(nb_, fabs(acc));
+				}
+			}
+		__syncwarp();
+		}
+	if(d.nbtot>0) *mu = mu2/(2.0*d.nbtot);
+	if(norms!=nullptr)
+		{
+		norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd);
+		}
+	}
+
+/* step length + dt, dlam.  RES = false: phase 1 (c99/d_aux_ip_hard_lib4.c:489-614) ; true: phase 2 (:1180-1313) */
+template<bool RES>
+__device__ __forceinline__ double hb_ipm_alpha(int lane_, const hb_dims &d, const hb_ipm_ws &w, const double *dux)
+	{
+	double alpha = 1.0;
+	for(int cc=lane_; cc<d.nbtot; cc+=32)
+		{
+		double du = dux[d.c_ux[cc]];
+		double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc], tl = w.v(CV_T_LO)[cc], tu = w.v(CV_T_UP)[cc];
+		double dtl, dtu, dll, dlu;
+		if(!RES)
+			{
+			dtl =  du - w.v(CV_LB)[cc] - tl;
+			dtu = -du + w.v(CV_UB)[cc] - tu;
+			dll = w.v(CV_DLAM_LO)[cc] - (w.v(CV_LAMT_LO)[cc]*dtl + ll);
+			dlu = w.v(CV_DLAM_UP)[cc] - (w.v(CV_LAMT_UP)[cc]*dtu + lu);
+			}
+		else
+			{
+			dtl =  du - w.v(CV_RD_LO)[cc];
+			dtu = -du + w.v(CV_RD_UP)[cc];
+			dll = -w.v(CV_TINV_LO)[cc]*(ll*dtl + w.v(CV_RM_LO)[cc]);
+			dlu = -w.v(CV_TINV_UP)[cc]*(lu*dtu + w.v(CV_RM_UP)[cc]);
+			}
+		w.v(CV_DT_LO)[cc] = dtl; w.v(CV_DT_UP)[cc] = dtu;
+		w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
+		if(-alpha*dll>ll) alpha = -ll/dll;
+		if(-alpha*dlu>lu) alpha = -lu/dlu;
+		if(-alpha*dtl>tl) alpha = -tl/dtl;
+		if(-alpha*dtu>tu) alpha = -tu/dtu;
+		}
+	return hb_warp_min(alpha);
+	}
+
+/* mu_aff = mu_scal * sum (lam + a dlam)(t + a dt)   (c99/d_aux_ip_hard_lib4.c:715-770, :1453-1508) */
+__device__ __forceinline__ double hb_ipm_mu_aff(int lane_, const hb_dims &d, const hb_ipm_ws &w, double alpha, double mu_scal)
+	{
+	double mu = 0.0;
+	for(int cc=lane_; cc<d.nbtot; cc+=32)
+		mu += (w.v(CV_LAM_LO)[cc] + alpha*w.v(CV_DLAM_LO)[cc])*(w.v(CV_T_LO)[cc] + alpha*w.v(CV_DT_LO)[cc])
+		    + (w.v(CV_LAM_UP)[cc] + alpha*w.v(CV_DLAM_UP)[cc])*(w.v(CV_T_UP)[cc] + alpha*w.v(CV_DT_UP)[cc]);
+	return hb_warp_sum(mu)*mu_scal;
+	}
+
+/* The IPM kernel is written once; the five sweeps over the horizon come from a policy: the run-time-size routines of
+ * ric_generic.cuh, or the size-specialised, bulk-copy-pipelined ones of ric_ipm_fast.cuh. */
+struct hb_sweeps_generic
+	{
+	typedef hb_ctx ctx_t;
+	__device__ static __forceinline__ int smem_doubles(const hb_dims &d) { return hb_smem_doubles_per_warp(d.nzM, d.nxM); }
+	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return d.L_stride; }
+	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c = hb_make_ctx(d, smem_warp, lane); }
+	__device__ static __forceinline__ void backward(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *Qx, const double *qx)
+		{ hb_backward<true>(c, d, in_inst, w.L, bv, rqv!=nullptr ? rqv : w.rq0, Qx, qx, w.Pb); }
+	__device__ static __forceinline__ void forward_sv(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, double *ux, double *pi)
+		{ hb_forward(c, d, in_inst, w.L, nullptr, bv, false, ux, pi, true); }
+	__device__ static __forceinline__ void trs(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		hb_trs_backward(c, d, in_inst, w.L, bv, rqv, qx, w.dux, w.Pb, false);
+		hb_forward(c, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
+		}
+	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *ux, const double *pi, double *mu, double *norms)
+		{ hb_ipm_residuals(c, d, in_inst, w, ux, pi, mu, norms); }
+	};
+
+template<class C>
+struct hb_sweeps_fast
+	{
+	typedef hbi_ctx<C> ctx_t;
+	__device__ static __forceinline__ int smem_doubles(const hb_dims &) { return hbi_cfg<C>::PER_WARP; }
+	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return (long long)(d.N+1)*C::LBUF; }
+	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c.init(smem_warp, lane, d); }
+	__device__ static __forceinline__ void backward(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *Qx, const double *qx)
+		{ hbi_backward<C>(c, d, in_inst, w.L, bv, rqv, Qx, qx, w.Pb); }
+	__device__ static __forceinline__ void forward_sv(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, double *ux, double *pi)
+		{ hbi_forward<C, false>(c, in_inst, w.L, bv, nullptr, ux, pi); }
+	__device__ static __forceinline__ void trs(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		hbi_trs_backward<C>(c, d, in_inst, w.L, rqv, qx, w.Pb, w.dux);
+		__syncwarp();
+		hbi_forward<C, true>(c, in_inst, w.L, bv, w.dux, w.dux, w.dpi);
+		}
+	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *ux, const double *pi, double *mu, double *norms)
+		{
+		double mu2, nd, nq = 0.0, nb_ = 0.0;
+		hb_ipm_residuals_bounds(c.lane, d, w, ux, mu2, nd);
+		__syncwarp();
+		hbi_residuals<C>(c, d, in_inst, w.rq0, w.b0, w.v(CV_LAM_LO), w.v(CV_LAM_UP), ux, pi, w.res_q, w.res_b, nq, nb_);
+		if(d.nbtot>0) *mu = mu2/(2.0*d.nbtot);
+		if(norms!=nullptr) { norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd); }
+		}
+	};
+
+template<class S>
+__global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *__restrict__ ux_all, double *__restrict__ pi_all,
+		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all,
+		double *__restrict__ work, long long work_stride, int *counter)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp;
+	typename S::ctx_t c;
+	S::init(c, d, hb_smem + (size_t)warp*S::smem_doubles(d), lane);
+	hb_ipm_ws w;
+	{
+	double *p = work + gw*work_stride;
+	w.L = p; p += S::L_doubles(d);
+	w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
+	w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
+	w.cv = p; w.nbp = HB_EVEN(d.nbtot);
+	}
+	const int info_len = HB_IPM_INFO_HEAD + 5*k_max;
+	const double thr0 = 0.1;
+
+	for(;;)
+		{
+		/* dynamic instance queue: a warp that converges early simply takes the next instance, so the
+		 * active set stays compact without a separate compaction pass */
+		long long inst = 0;
+		if(lane==0) inst = atomicAdd(counter, 1);
+		inst = __shfl_sync(HB_FULL, inst, 0);
+		if(inst>=n_inst) break;
+
+		const double *in_inst = in + inst*d.in_stride;
+		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+		double *info = info_all + inst*info_len;
+		double *stat = info + HB_IPM_INFO_HEAD;
+
+		/* vectors taken from the instance block: rq0 = [r q], b0 = b, bounds */
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_stage s = d.st[n];
+			const int nux = s.nu+s.nx;
+			for(int i=lane; i<nux; i+=32) w.rq0[s.off_ux+i] = in_inst[s.off_RSQ+HB_TRI(nux)+i];
+			for(int j=lane; j<s.nx1; j+=32) w.b0[s.off_pi+j] = in_inst[s.off_BAbt+nux*s.nx1+j];
+			for(int j=lane; j<s.nb; j+=32)
+				{
+				w.v(CV_LB)[s.off_c+j] = in_inst[s.off_d+j];
+				w.v(CV_UB)[s.off_c+j] = in_inst[s.off_d+s.nb+j];
+				}
+			}
+		__syncwarp();
+
+		int kk = 0, status = -1;
+		double mu = 0.0, norms[3] = {0.0, 0.0, 0.0};
+
+		if(d.nbtot==0)
+			{
+			/* no constraints: one Riccati solve (d_ip2_res_hard.c:430-450) */
+			S::backward(c, d, in_inst, w, nullptr, nullptr, nullptr, nullptr);
+			__syncwarp();
+			S::forward_sv(c, d, in_inst, w, nullptr, ux, pi);
+			__syncwarp();
+			S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+			status = 0;
+			}
+		else
+			{
+			const double mu_scal = 1.0/(2.0*d.nbtot);
+			double sigma = 0.0, alpha = 1.0, mu_aff;
+			/* init (c99/d_aux_ip_hard_lib4.c:43-149) */
+			if(!warm_start) for(long long i=lane; i<d.ux_stride; i+=32) ux[i] = 0.0;
+			for(long long i=lane; i<d.pi_stride; i+=32) pi[i] = 0.0;
+			__syncwarp();
+			for(int cc=lane; cc<d.nbtot; cc+=32)
+				{
+				const int iu = d.c_ux[cc];
+				double lb = w.v(CV_LB)[cc], ub = w.v(CV_UB)[cc], u = ux[iu];
+				double tl = -lb + u, tu = ub - u;
+				if(tl<thr0)
+					{
+					if(tu<thr0) { ux[iu] = (-ub + lb)*0.5; tl = thr0; tu = thr0; }
+					else { tl = thr0; ux[iu] = lb + thr0; }
+					}
+				else if(tu<thr0) { tu = thr0; ux[iu] = ub - thr0; }
+				w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
+				w.v(CV_LAM_LO)[cc] = mu0/tl; w.v(CV_LAM_UP)[cc] = mu0/tu;
+				}
+			__syncwarp();
+			mu = mu0;
+			const double mu_tol_low = mu_tol<1e-5 ? 1e-5 : mu_tol;
+
+			/* ---------- phase 1 (d_ip2_res_hard.c:503-718) ---------- */
+			while(kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
+				{
+				/* update_hessian, sigma_mu = 0 (c99/d_aux_ip_hard_lib4.c:217-383) */
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double til = 1.0/w.v(CV_T_LO)[cc], tiu = 1.0/w.v(CV_T_UP)[cc];
+					double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc];
+					double ltl = ll*til, ltu = lu*tiu;
+					double dll = til*0.0, dlu = tiu*0.0;
+					w.v(CV_TINV_LO)[cc] = til; w.v(CV_TINV_UP)[cc] = tiu;
+					w.v(CV_LAMT_LO)[cc] = ltl; w.v(CV_LAMT_UP)[cc] = ltu;
+					w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
+					w.v(CV_QXD)[cc] = ltl + ltu;
+					w.v(CV_QXG)[cc] = lu - ltu*w.v(CV_UB)[cc] + dlu - ll - ltl*w.v(CV_LB)[cc] - dll;
+					}
+				__syncwarp();
+				HBF_STAMP(300);
+				S::backward(c, d, in_inst, w, nullptr, nullptr, w.v(CV_QXD), w.v(CV_QXG));
+				__syncwarp();
+				HBF_STAMP(301);
+				S::forward_sv(c, d, in_inst, w, nullptr, w.dux, w.dpi);
+				HBF_STAMP(302);
+				__syncwarp();
+				alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
+				__syncwarp();
+				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
+				alpha *= 0.995;
+				mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
+				if(lane==0) stat[5*kk+2] = mu_aff;
+				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
+				{
+				/* update_gradient (c99/d_aux_ip_hard_lib4.c:387-485) */
+				const double sm = sigma*mu;
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double dll = w.v(CV_TINV_LO)[cc]*(sm - w.v(CV_DLAM_LO)[cc]*w.v(CV_DT_LO)[cc]);
+					double dlu = w.v(CV_TINV_UP)[cc]*(sm - w.v(CV_DLAM_UP)[cc]*w.v(CV_DT_UP)[cc]);
+					w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
+					w.v(CV_QXG)[cc] += dlu - dll;
+					}
+				}
+				__syncwarp();
+				HBF_STAMP(303);
+				S::trs(c, d, in_inst, w, w.b0, w.rq0, w.v(CV_QXG));
+				HBF_STAMP(304);
+				__syncwarp();
+				alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
+				__syncwarp();
+				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
+				alpha *= 0.995;
+				/* update_var (c99/d_aux_ip_hard_lib4.c:618-711) */
+				for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += alpha*(w.dux[i] - ux[i]);
+				for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += alpha*(w.dpi[i] - pi[i]);
+				double ms = 0.0;
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double ll = w.v(CV_LAM_LO)[cc] + alpha*w.v(CV_DLAM_LO)[cc];
+					double lu = w.v(CV_LAM_UP)[cc] + alpha*w.v(CV_DLAM_UP)[cc];
+					double tl = w.v(CV_T_LO)[cc] + alpha*w.v(CV_DT_LO)[cc];
+					double tu = w.v(CV_T_UP)[cc] + alpha*w.v(CV_DT_UP)[cc];
+					w.v(CV_LAM_LO)[cc] = ll; w.v(CV_LAM_UP)[cc] = lu; w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
+					ms += ll*tl + lu*tu;
+					}
+				mu = hb_warp_sum(ms)*mu_scal;
+				if(lane==0) stat[5*kk+4] = mu;
+				kk++;
+				__syncwarp();
+				}
+
+			/* ---------- phase 2 (d_ip2_res_hard.c:756-1273) ---------- */
+			S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+			__syncwarp();
+			while(kk<k_max && mu>mu_tol && alpha>=alpha_min)
+				{
+				/* update_hessian_gradient_res (c99/d_aux_ip_hard_lib4.c:954-1078) */
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double til = 1.0/w.v(CV_T_LO)[cc], tiu = 1.0/w.v(CV_T_UP)[cc];
+					double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc];
+					w.v(CV_TINV_LO)[cc] = til; w.v(CV_TINV_UP)[cc] = tiu;
+					w.v(CV_QXD)[cc] = til*ll + tiu*lu;
+					w.v(CV_QXG)[cc] = til*(w.v(CV_RM_LO)[cc] - ll*w.v(CV_RD_LO)[cc]) - tiu*(w.v(CV_RM_UP)[cc] + lu*w.v(CV_RD_UP)[cc]);
+					}
+				__syncwarp();
+				HBF_STAMP(300);
+				S::backward(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXD), w.v(CV_QXG));
+				__syncwarp();
+				HBF_STAMP(301);
+				S::forward_sv(c, d, in_inst, w, w.res_b, w.dux, w.dpi);
+				HBF_STAMP(302);
+				__syncwarp();
+				alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
+				__syncwarp();
+				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
+				alpha *= 0.995;
+				mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
+				if(lane==0) stat[5*kk+2] = mu_aff;
+				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
+				{
+				/* centering correction + update_gradient_res (c99/d_aux_ip_hard_lib4.c:1512-1546, :1550-1639) */
+				const double sm = sigma*mu;
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double rml = w.v(CV_RM_LO)[cc] + (w.v(CV_DT_LO)[cc]*w.v(CV_DLAM_LO)[cc] - sm);
+					double rmu = w.v(CV_RM_UP)[cc] + (w.v(CV_DT_UP)[cc]*w.v(CV_DLAM_UP)[cc] - sm);
+					w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
+					w.v(CV_QXG)[cc] = w.v(CV_TINV_LO)[cc]*(rml - w.v(CV_LAM_LO)[cc]*w.v(CV_RD_LO)[cc])
+					                  - w.v(CV_TINV_UP)[cc]*(rmu + w.v(CV_LAM_UP)[cc]*w.v(CV_RD_UP)[cc]);
+					}
+				}
+				__syncwarp();
+				HBF_STAMP(303);
+				S::trs(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXG));
+				HBF_STAMP(304);
+				__syncwarp();
+				alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
+				__syncwarp();
+				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
+				alpha *= 0.995;
+				/* backup_update_var_res (c99/d_aux_ip_hard_lib4.c:1382-1449) */
+				for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += alpha*w.dux[i];
+				for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += alpha*w.dpi[i];
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					w.v(CV_LAM_LO)[cc] += alpha*w.v(CV_DLAM_LO)[cc]; w.v(CV_LAM_UP)[cc] += alpha*w.v(CV_DLAM_UP)[cc];
+					w.v(CV_T_LO)[cc] += alpha*w.v(CV_DT_LO)[cc]; w.v(CV_T_UP)[cc] += alpha*w.v(CV_DT_UP)[cc];
+					}
+				__syncwarp();
+				HBF_STAMP(305);
+				S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+				HBF_STAMP(306);
+				if(lane==0) stat[5*kk+4] = mu;
+				kk++;
+				__syncwarp();
+				}
+			if(mu<=mu_tol) status = 0;
+			else if(kk>=k_max) status = 1;
+			else if(alpha<alpha_min) status = 2;
+			else status = -1;
+			}
+
+		/* results: lam, t as [lower(nb) upper(nb)] per stage (interfaces/c/fortran_order_interface.c:662-671) */
+		double *lam = lam_all + inst*2*(long long)d.nbtot, *tt = t_all + inst*2*(long long)d.nbtot;
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_stage s = d.st[n];
+			for(int j=lane; j<s.nb; j+=32)
+				{
+				lam[2*s.off_c+j] = w.v(CV_LAM_LO)[s.off_c+j]; lam[2*s.off_c+s.nb+j] = w.v(CV_LAM_UP)[s.off_c+j];
+				tt[2*s.off_c+j] = w.v(CV_T_LO)[s.off_c+j]; tt[2*s.off_c+s.nb+j] = w.v(CV_T_UP)[s.off_c+j];
+				}
+			}
+		if(lane==0)
+			{
+			info[0] = (double)kk; info[1] = (double)status;
+			info[2] = norms[0]; info[3] = norms[1]; info[4] = norms[2]; info[5] = mu;
+			}
+		__syncwarp();
+		}
+	}
+
+extern "C" long long hb_ipm_work_doubles(const hb_dims *d) { return hb_ipm_work_doubles_(*d); }
+
+/* size-specialised IPM sweeps (ric_ipm_fast.cuh): one warp per instance, x0 eliminated, uniform (nx, nu) */
+typedef hbf_cfg<24, 11, 32> hbi_v0;    /* BASELINE config 3 */
+typedef hbf_cfg<12, 5, 32> hbi_v1;     /* config-2 sizes with bounds */
+typedef hbf_cfg<8, 3, 32> hbi_v2;      /* the reference's own IPM test size (test_d_ip_hard.c) */
+#define HBI_NVAR 3
+static const int hbi_shapes[HBI_NVAR][2] = { {24, 11}, {12, 5}, {8, 3} };
+
+extern "C" int hb_ipm_fast_variant(int N, const int *nx, const int *nu, int nbtot)
+	{
+	if(getenv("HPMPC_B200_NO_FAST_IPM")!=NULL || nbtot<=0) return -1;
+	for(int id=0; id<HBI_NVAR; id++)
+		{
+		int ok = (nx[0]==0) && N>=3;
+		for(int n=0; n<N && ok; n++) ok = (nu[n]==hbi_shapes[id][1]) && (n==0 || nx[n]==hbi_shapes[id][0]);
+		ok = ok && nx[N]==hbi_shapes[id][0];
+		if(ok) return id;
+		}
+	return -1;
+	}
+
+template<class C> static void hbi_info(int N, int *smem_warp, long long *L_doubles)
+	{ *smem_warp = (int)sizeof(double)*hbi_cfg<C>::PER_WARP; *L_doubles = (long long)(N+1)*C::LBUF; }
+
+extern "C" int hb_ipm_fast_info(int id, int N, int *smem_warp, long long *L_doubles)
+	{
+	switch(id)
+		{
+		case 0: hbi_info<hbi_v0>(N, smem_warp, L_doubles); return 0;
+		case 1: hbi_info<hbi_v1>(N, smem_warp, L_doubles); return 0;
+		case 2: hbi_info<hbi_v2>(N, smem_warp, L_doubles); return 0;
+		}
+	return -1;
+	}
+
+/* doubles of per-slot work area; L_doubles = size of the factor stash of the variant in use */
+extern "C" long long hb_ipm_work_doubles2(const hb_dims *d, long long L_doubles)
+	{
+	return hb_ipm_work_doubles_(*d) - d->L_stride + L_doubles;
+	}
+
+template<class S> static int hb_launch_ipm_t(int smem, const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int grid, int warps, int *counter, cudaStream_t st)
+	{
+	if(hb_prep(hb_ipm_kernel<S>, smem)) return -1;
+	if(getenv("HPMPC_B200_VERBOSE"))
+		{
+		int nb = 0; cudaFuncAttributes fa;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb_ipm_kernel<S>, warps*32, smem);
+		cudaFuncGetAttributes(&fa, hb_ipm_kernel<S>);
+		fprintf(stderr, "hpmpc_b200: ipm kernel: grid %d x %d threads, %d B dynamic + %zu B static smem, %d regs, %zu B local, %d CTAs/SM\n",
+			grid, warps*32, smem, fa.sharedSizeBytes, fa.numRegs, fa.localSizeBytes, nb);
+		}
+	HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+	hb_ipm_kernel<S><<<grid, warps*32, smem, st>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
+			ux, pi, lam, t, info, work, work_stride, counter);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+extern "C" int hb_launch_ipm(const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
+		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream)
+	{
+	if(d->nzM>64) return -2;
+	if(grid*warps>n_slots || warps>8) return -3;
+	cudaStream_t st = (cudaStream_t)stream;
+#define HB_IPM_ARGS d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start, ux, pi, lam, t, info, work, work_stride, grid, warps, counter, st
+	switch(fast_id)
+		{
+		case 0: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v0> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v0>::PER_WARP, HB_IPM_ARGS);
+		case 1: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v1> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v1>::PER_WARP, HB_IPM_ARGS);
+		case 2: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v2> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v2>::PER_WARP, HB_IPM_ARGS);
+		}
+	return hb_launch_ipm_t<hb_sweeps_generic>(warps*hb_smem_bytes_per_warp(d), HB_IPM_ARGS);
+#undef HB_IPM_ARGS
+	}
+

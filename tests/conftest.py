@@ -18,7 +18,7 @@ def built_libraries():
     """Make sure the product library and the oracle are built (no-op when the .so files travelled with the snapshot)."""
     prod = os.path.join(ROOT, "hpmpc_b200", "lib", "libhpmpc_b200.so")
     if not os.path.exists(prod):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "hpmpc_b200", "csrc")], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run(["make", "-C", os.path.join(ROOT, "hpmpc_b200", "csrc"), "-j4"], check=True, stdout=subprocess.DEVNULL)
     orc = os.path.join(ROOT, "oracle", "_ref", "liboracle.so")
     ref = os.path.join(ROOT, "oracle", "_ref", "libhpmpc_ref_c99.so")
     if not os.path.exists(orc) or (os.path.isdir("/root/reference") and not os.path.exists(ref)):
