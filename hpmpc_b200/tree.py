@@ -69,11 +69,17 @@ class TreeOcp:
     R: List[np.ndarray] = field(default_factory=list)
     q: List[np.ndarray] = field(default_factory=list)
     r: List[np.ndarray] = field(default_factory=list)
+    # box bounds per node (empty lists = unconstrained): idxb[n] indexes [u_n ; x_n], lb/ub have nb[n] entries
+    nb: List[int] = field(default_factory=list)
+    idxb: List[np.ndarray] = field(default_factory=list)
+    lb: List[np.ndarray] = field(default_factory=list)
+    ub: List[np.ndarray] = field(default_factory=list)
 
 
-def mass_spring_tree(nx: int, nu: int, md: int, Nr: int, Nh: int, xi=(0.0, 0.0, 0.0, 0.0)) -> TreeOcp:
+def mass_spring_tree(nx: int, nu: int, md: int, Nr: int, Nh: int, xi=(0.0, 0.0, 0.0, 0.0), bounds: bool = False) -> TreeOcp:
     """per-branch dynamics A, B (1 + 0.05 real), cost scaled md^(Nr - stage) on the robust
-    stages, x0 eliminated at the root (nx[0] = 0, b of the root's edges = A x0 + b)."""
+    stages, x0 eliminated at the root (nx[0] = 0, b of the root's edges = A x0 + b); bounds: u in [-0.5, 0.5] on every
+    input of every node (test_d_tree_ip_hard_libstr.c: "u-bounds")."""
     topo = setup_tree(md, Nr, Nh)
     Nn = topo["Nn"]
     A0, B0 = mass_spring_AB(nx, nu)
@@ -96,6 +102,9 @@ def mass_spring_tree(nx: int, nu: int, md: int, Nr: int, Nh: int, xi=(0.0, 0.0, 
         w = float(md ** (Nr - s)) if s < Nr else 1.0
         t.Q.append(w * qs * np.eye(nxs[n])); t.S.append(np.zeros((nus[n], nxs[n]))); t.R.append(w * rs * np.eye(nus[n]))
         t.q.append(w * 0.1 * np.ones(nxs[n])); t.r.append(w * 0.2 * np.ones(nus[n]))
+        if bounds:
+            t.nb.append(nus[n]); t.idxb.append(np.arange(nus[n], dtype=np.int32))
+            t.lb.append(-0.5 * np.ones(nus[n])); t.ub.append(0.5 * np.ones(nus[n]))
     return t
 
 
@@ -109,7 +118,18 @@ def stacked_chain(t: TreeOcp):
     nu2 = [sum(t.nu[n] for n in lv) for lv in levels]
     uo = [{n: sum(t.nu[m] for m in lv[:i]) for i, n in enumerate(lv)} for lv in levels]
     xo = [{n: sum(t.nx[m] for m in lv[:i]) for i, n in enumerate(lv)} for lv in levels]
-    p = Ocp(N=Nh, nx=nx2, nu=nu2, nb=[0] * (Nh + 1), idxb=[np.zeros(0, dtype=np.int32) for _ in range(Nh + 1)])
+    has_b = len(t.nb) > 0
+    idx2, lb2, ub2 = [], [], []
+    for s, lv in enumerate(levels):
+        ii, ll, uu = [], [], []
+        for n in (lv if has_b else []):
+            for j in range(t.nb[n]):
+                i = int(t.idxb[n][j])
+                ii.append(uo[s][n] + i if i < t.nu[n] else nu2[s] + xo[s][n] + i - t.nu[n]); ll.append(t.lb[n][j]); uu.append(t.ub[n][j])
+        o = np.argsort(np.asarray(ii, dtype=np.int64), kind="stable") if ii else np.zeros(0, dtype=np.int64)
+        idx2.append(np.asarray(ii, dtype=np.int32)[o] if ii else np.zeros(0, dtype=np.int32))
+        lb2.append(np.asarray(ll, dtype=np.float64)[o] if ii else np.zeros(0)); ub2.append(np.asarray(uu, dtype=np.float64)[o] if ii else np.zeros(0))
+    p = Ocp(N=Nh, nx=nx2, nu=nu2, nb=[len(v) for v in idx2], idxb=idx2)
     for s in range(Nh + 1):
         lv = levels[s]
         Q = np.zeros((nx2[s], nx2[s])); R = np.zeros((nu2[s], nu2[s])); S = np.zeros((nu2[s], nx2[s]))
@@ -119,7 +139,7 @@ def stacked_chain(t: TreeOcp):
             Q[a:a + t.nx[n], a:a + t.nx[n]] = t.Q[n]; R[e:e + t.nu[n], e:e + t.nu[n]] = t.R[n]
             S[e:e + t.nu[n], a:a + t.nx[n]] = t.S[n]; q[a:a + t.nx[n]] = t.q[n]; r[e:e + t.nu[n]] = t.r[n]
         p.Q.append(Q); p.R.append(R); p.S.append(S); p.q.append(q); p.r.append(r)
-        p.lb.append(np.zeros(0)); p.ub.append(np.zeros(0))
+        p.lb.append(lb2[s]); p.ub.append(ub2[s])
         if s < Nh:
             A = np.zeros((nx2[s + 1], nx2[s])); B = np.zeros((nx2[s + 1], nu2[s])); b = np.zeros(nx2[s + 1])
             for k in levels[s + 1]:

@@ -124,6 +124,53 @@ def tree_ric(t):
                 pi=[pi[n][:t.nx[n]].copy() if n > 0 else np.zeros(0) for n in range(Nn)])
 
 
+def _tree_dense(t):
+    """Node-indexed dense matrices of a TreeOcp in the oracle's formats (BAbt[k]: edge into node k)."""
+    topo = t.topo
+    BAbt, RSQ = [], []
+    for n in range(topo["Nn"]):
+        nx, nu = t.nx[n], t.nu[n]
+        nz = nx + nu + 1
+        H = np.zeros((nz, nx + nu + 1), order="F")
+        H[:nu, :nu] = t.R[n]; H[nu:nu + nx, :nu] = t.S[n].T; H[nu:nu + nx, nu:nu + nx] = t.Q[n]
+        H[nu + nx, :nu] = t.r[n]; H[nu + nx, nu:nu + nx] = t.q[n]
+        RSQ.append(np.asfortranarray(H[:, :max(nx + nu, 1)]))
+        if n == 0:
+            BAbt.append(np.zeros((1, 1), order="F"))
+        else:
+            d = topo["dad"][n]
+            nzd = t.nx[d] + t.nu[d] + 1
+            M = np.zeros((nzd, max(nx, 1)), order="F")
+            M[:t.nu[d], :nx] = t.B[n].T; M[t.nu[d]:t.nu[d] + t.nx[d], :nx] = t.A[n].T; M[nzd - 1, :nx] = t.b[n]
+            BAbt.append(M)
+    return BAbt, RSQ
+
+
+def tree_ipm(t, *, k_max=40, mu0=2.0, mu_tol=1e-8, alpha_min=1e-8, warm_start=0):
+    """orc_tree_ip2_res_mpc_hard (oracle/ric_oracle.c): box-constrained IPM over a scenario tree (TreeOcp with bounds)."""
+    L = lib()
+    topo = t.topo
+    Nn = topo["Nn"]
+    L.orc_tree_ip2_res_mpc_hard.restype = C.c_int
+    L.orc_tree_ip2_res_mpc_hard.argtypes = [C.c_int] + [C.c_void_p] * 8 + [C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 5
+    BAbt, RSQ = _tree_dense(t)
+    nb = list(t.nb) if t.nb else [0] * Nn
+    idxb = [np.ascontiguousarray(t.idxb[n], dtype=np.int32) if nb[n] else np.zeros(1, dtype=np.int32) for n in range(Nn)]
+    d = [np.concatenate([t.lb[n], t.ub[n]]).astype(np.float64) if nb[n] else np.zeros(1) for n in range(Nn)]
+    ux = [np.zeros(max(t.nx[n] + t.nu[n], 1)) for n in range(Nn)]
+    pi = [np.zeros(max(t.nx[n], 1)) for n in range(Nn)]
+    lam = [np.zeros(max(2 * nb[n], 1)) for n in range(Nn)]; tt = [np.zeros(max(2 * nb[n], 1)) for n in range(Nn)]
+    stat = np.zeros(5 * k_max + 5); kk = C.c_int(0)
+    pa = ptr_array
+    status = L.orc_tree_ip2_res_mpc_hard(Nn, int_array(topo["dad"]), int_array(t.nx), int_array(t.nu), int_array(nb), pa(idxb), pa(BAbt), pa(RSQ), pa(d),
+                                         C.byref(kk), k_max, mu0, mu_tol, alpha_min, warm_start, stat.ctypes.data, pa(ux), pa(pi), pa(lam), pa(tt))
+    return dict(status=status, kk=kk.value, u=[ux[n][:t.nu[n]].copy() for n in range(Nn)],
+                x=[ux[n][t.nu[n]:t.nu[n] + t.nx[n]].copy() for n in range(Nn)],
+                pi=[pi[n][:t.nx[n]].copy() if n > 0 else np.zeros(0) for n in range(Nn)],
+                lam=[lam[n][:2 * nb[n]].copy() for n in range(Nn)], t=[tt[n][:2 * nb[n]].copy() for n in range(Nn)],
+                stat=stat[:5 * kk.value].reshape(-1, 5).copy())
+
+
 # ------------------------------------------------------------------------------------------- CPU timing harness
 def _harness():
     L = lib()

@@ -51,17 +51,28 @@ typedef struct {
 	int nzM, nxM;
 	double *W;              /* scratch (nzM x nxM) */
 	double *tmp;            /* scratch 2*nzM */
+	/* scenario tree (NULL for a chain): stages are the nodes in BFS order, dad[0] = -1, and "edge n" (BAbt[n], b, pi[n],
+	 * Pb[n], n = 0..N-1) is the edge INTO node n+1, whose rows are those of dad[n+1] instead of stage n */
+	int *dad;
 } orc_prob;
 
 static int nux_(const orc_prob *P, int n) { return P->nu[n] + P->nx[n]; }
+static int dad_(const orc_prob *P, int k) { return P->dad ? P->dad[k] : k-1; }
 
+orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *dad);
 orc_prob *orc_prob_create(int N, const int *nx, const int *nu, const int *nb, int *const *idxb)
+	{
+	return orc_prob_create_tree(N, nx, nu, nb, idxb, NULL);
+	}
+
+orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *dad)
 	{
 	orc_prob *P = calloc(1, sizeof(orc_prob));
 	int n, j;
 	P->N = N;
+	if(dad) { P->dad = malloc((N+1)*sizeof(int)); for(n=0; n<=N; n++) P->dad[n] = dad[n]; }
 	P->nx = malloc((N+1)*sizeof(int)); P->nu = malloc((N+1)*sizeof(int)); P->nb = malloc((N+1)*sizeof(int));
-	for(n=0; n<=N; n++) { P->nx[n] = nx[n]; P->nu[n] = n<N ? nu[n] : 0; P->nb[n] = nb ? nb[n] : 0; }
+	for(n=0; n<=N; n++) { P->nx[n] = nx[n]; P->nu[n] = (n<N || dad) ? nu[n] : 0; P->nb[n] = nb ? nb[n] : 0; }
 	P->idxb = calloc(N+1, sizeof(int*));
 	for(n=0; n<=N; n++)
 		{
@@ -76,7 +87,7 @@ orc_prob *orc_prob_create(int N, const int *nx, const int *nu, const int *nb, in
 		int nux = nux_(P, n), nz = nux+1;
 		if(nz>P->nzM) P->nzM = nz;
 		if(P->nx[n]>P->nxM) P->nxM = P->nx[n];
-		if(n<N) P->BAbt[n] = calloc((size_t)nz*(P->nx[n+1]+1), sizeof(double));
+		if(n<N) P->BAbt[n] = calloc((size_t)(nux_(P, dad_(P, n+1))+1)*(P->nx[n+1]+1), sizeof(double));
 		P->RSQrq[n] = calloc((size_t)nz*(nux+1), sizeof(double));
 		P->L[n] = calloc((size_t)nz*(nux+1), sizeof(double));
 		P->dinv[n] = calloc(nux+1, sizeof(double));
@@ -93,7 +104,7 @@ void orc_prob_free(orc_prob *P)
 	for(n=0; n<=P->N; n++)
 		{ free(P->idxb[n]); free(P->BAbt[n]); free(P->RSQrq[n]); free(P->L[n]); free(P->dinv[n]); free(P->d[n]); }
 	free(P->idxb); free(P->BAbt); free(P->RSQrq); free(P->L); free(P->dinv); free(P->d);
-	free(P->nx); free(P->nu); free(P->nb); free(P->W); free(P->tmp); free(P);
+	free(P->nx); free(P->nu); free(P->nb); free(P->W); free(P->tmp); free(P->dad); free(P);
 	}
 
 /* fill from the stage-wise column-major ("fortran order") arrays of the high-level API:
@@ -178,18 +189,22 @@ void orc_ric_backward(orc_prob *P, int with_grad, double *const *bvec, double *c
 				L[id+nz*id] += Qx[n][j];
 				if(with_grad && qx) L[nux+nz*id] += qx[n][j];
 				}
-		if(n<N)
+		/* every kid c of this node (a chain has the one kid n+1; lqcp_solvers/d_tree_back_ric_rec_libstr.c:79-156 sums
+		 * W_c W_c' over the kids); e = c-1 is the edge into the kid */
+		for(int c=n+1; c<=N; c++)
 			{
-			int nx1 = P->nx[n+1], nu1 = P->nu[n+1], nz1 = nx1+nu1+1;
-			double *Ln = P->L[n+1], *M = P->BAbt[n], *W = P->W;
-			/* W = BAbt * Lxx_{n+1}   (m x nx1) */
+			if(dad_(P, c)!=n) { if(P->dad) continue; else break; }
+			const int e = c-1;
+			int nx1 = P->nx[c], nu1 = P->nu[c], nz1 = nx1+nu1+1;
+			double *Ln = P->L[c], *M = P->BAbt[e], *W = P->W;
+			/* W = BAbt * Lxx_c   (m x nx1) */
 			for(i=0; i<m; i++)
 				for(j=0; j<nx1; j++)
 					{
 					double s = 0.0;
 					for(k=j; k<nx1; k++)
 						{
-						double a = (i==nux && bvec) ? bvec[n][k] : M[i+nz*k];
+						double a = (i==nux && bvec) ? bvec[e][k] : M[i+nz*k];
 						s += a*Ln[nu1+k+nz1*(nu1+j)];
 						}
 					W[i+nz*j] = s;
@@ -201,7 +216,7 @@ void orc_ric_backward(orc_prob *P, int with_grad, double *const *bvec, double *c
 						{
 						double s = 0.0;
 						for(k=0; k<=i; k++) s += Ln[nu1+i+nz1*(nu1+k)]*W[nux+nz*k];
-						Pb[n][i] = s;
+						Pb[e][i] = s;
 						}
 				for(j=0; j<nx1; j++) W[nux+nz*j] += Ln[nu1+nx1+nz1*(nu1+j)];   /* + l_x */
 				}
@@ -213,6 +228,7 @@ void orc_ric_backward(orc_prob *P, int with_grad, double *const *bvec, double *c
 					for(k=0; k<nx1; k++) s += W[i+nz*k]*W[j+nz*k];
 					L[i+nz*j] += s;
 					}
+			if(!P->dad) break;
 			}
 		chol_mn(m, nux, L, nz, P->dinv[n]);
 		}
@@ -246,9 +262,49 @@ static void ric_forward(orc_prob *P, double *const *lrow, double *const *bsrc, d
 		double **ux, int compute_pi, double **pi)
 	{
 	int N = P->N, n, i, j;
-	for(n=0; n<N; n++)
+	/* node by node (for a chain: stage by stage): first the state and multiplier of the edge into the node, from the
+	 * finished ux of its dad, then the node's own inputs */
+	for(n=0; n<=N; n++)
 		{
-		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1, nx1 = P->nx[n+1], nu1 = P->nu[n+1];
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1;
+		if(n>0)
+			{
+			const int e = n-1, dd = dad_(P, n);
+			const int nuxd = nux_(P, dd), nzd = nuxd+1;
+			/* x_n = b + BAbt[:nuxd]' ux_dad */
+			const double *M = P->BAbt[e], *vd = ux[dd];
+			double *xn = ux[n]+nu;
+			for(j=0; j<nx; j++)
+				{
+				double s = bsrc ? bsrc[e][j] : M[nuxd+nzd*j];
+				for(i=0; i<nuxd; i++) s += M[i+nzd*j]*vd[i];
+				xn[j] = s;
+				}
+			if(compute_pi)
+				{
+				if(p) pi_from_x(P, n, xn, p[e], pi[e], P->tmp);
+				else
+					{
+					/* sv: p = Lxx l_x  folded as  Lxx (Lxx' x + l_x) */
+					int k;
+					const double *L1 = P->L[n];
+					double *tmp = P->tmp;
+					for(i=0; i<nx; i++)
+						{
+						double s = L1[nu+nx+nz*(nu+i)];
+						for(k=i; k<nx; k++) s += L1[nu+k+nz*(nu+i)]*xn[k];
+						tmp[i] = s;
+						}
+					for(i=0; i<nx; i++)
+						{
+						double s = 0.0;
+						for(k=0; k<=i; k++) s += L1[nu+i+nz*(nu+k)]*tmp[k];
+						pi[e][i] = s;
+						}
+					}
+				}
+			}
+		if(!P->dad && n==N) break;            /* the last stage of a chain has no inputs */
 		int ks = (n==0) ? nux : nu;           /* stage 0 solves for all of ux_0 */
 		const double *L = P->L[n], *dinv = P->dinv[n];
 		double *v = ux[n];
@@ -259,38 +315,6 @@ static void ric_forward(orc_prob *P, double *const *lrow, double *const *bsrc, d
 			double s = v[i];
 			for(j=i+1; j<nux; j++) s -= L[j+nz*i]*v[j];
 			v[i] = s*dinv[i];
-			}
-		/* x_{n+1} = b + BAbt[:nux]' ux */
-		const double *M = P->BAbt[n];
-		double *xn = ux[n+1]+nu1;
-		for(j=0; j<nx1; j++)
-			{
-			double s = bsrc ? bsrc[n][j] : M[nux+nz*j];
-			for(i=0; i<nux; i++) s += M[i+nz*j]*v[i];
-			xn[j] = s;
-			}
-		if(compute_pi)
-			{
-			if(p) pi_from_x(P, n+1, xn, p[n], pi[n], P->tmp);
-			else
-				{
-				/* sv: p = Lxx l_x  folded as  Lxx (Lxx' x + l_x) */
-				int nz1 = nx1+nu1+1, k;
-				const double *L1 = P->L[n+1];
-				double *tmp = P->tmp;
-				for(i=0; i<nx1; i++)
-					{
-					double s = L1[nu1+nx1+nz1*(nu1+i)];
-					for(k=i; k<nx1; k++) s += L1[nu1+k+nz1*(nu1+i)]*xn[k];
-					tmp[i] = s;
-					}
-				for(i=0; i<nx1; i++)
-					{
-					double s = 0.0;
-					for(k=0; k<=i; k++) s += L1[nu1+i+nz1*(nu1+k)]*tmp[k];
-					pi[n][i] = s;
-					}
-				}
 			}
 		}
 	}
@@ -333,36 +357,44 @@ void orc_ric_trs(orc_prob *P, double *const *bvec, double *const *rqvec, double 
 		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1;
 		for(i=0; i<nux; i++) w[n][i] = rqvec[n][i];
 		if(P->nb[n]>0 && qx) for(j=0; j<P->nb[n]; j++) w[n][P->idxb[n][j]] += qx[n][j];
-		if(n<N)
+		int has_kid = 0;
+		for(int c=n+1; c<=N; c++)
 			{
-			int nx1 = P->nx[n+1], nu1 = P->nu[n+1];
+			if(dad_(P, c)!=n) { if(P->dad) continue; else break; }
+			const int e = c-1;
+			has_kid = 1;
+			int nx1 = P->nx[c], nu1 = P->nu[c];
 			double *tmp = P->tmp;
 			if(compute_Pb)
 				{
 				double *t2 = P->tmp+P->nzM;
 				int nz1 = nx1+nu1+1;
-				const double *L1 = P->L[n+1];
+				const double *L1 = P->L[c];
 				for(i=0; i<nx1; i++)
 					{
 					double s = 0.0;
-					for(k=i; k<nx1; k++) s += L1[nu1+k+nz1*(nu1+i)]*bvec[n][k];
+					for(k=i; k<nx1; k++) s += L1[nu1+k+nz1*(nu1+i)]*bvec[e][k];
 					t2[i] = s;
 					}
 				for(i=0; i<nx1; i++)
 					{
 					double s = 0.0;
 					for(k=0; k<=i; k++) s += L1[nu1+i+nz1*(nu1+k)]*t2[k];
-					Pb[n][i] = s;
+					Pb[e][i] = s;
 					}
 				}
-			for(j=0; j<nx1; j++) tmp[j] = Pb[n][j] + w[n+1][nu1+j];
-			const double *M = P->BAbt[n];
+			for(j=0; j<nx1; j++) tmp[j] = Pb[e][j] + w[c][nu1+j];
+			const double *M = P->BAbt[e];
 			for(i=0; i<nux; i++)
 				{
 				double s = w[n][i];
 				for(j=0; j<nx1; j++) s += M[i+nz*j]*tmp[j];
 				w[n][i] = s;
 				}
+			if(!P->dad) break;
+			}
+		if(has_kid)
+			{
 			int ks = (n==0) ? nux : nu;
 			const double *L = P->L[n], *dinv = P->dinv[n];
 			for(i=0; i<ks; i++)
@@ -429,22 +461,26 @@ static void ipm_residuals(const orc_prob *P, const orc_ipm_ws *w, double *mu)
 			for(j=0; j<nux; j++) s += (i>=j ? H[i+nz*j] : H[j+nz*i])*w->ux[n][j];
 			rq[i] += s;
 			}
-		if(n<N)
+		/* every edge out of this node (chain: the one into n+1; tree: mpc_solvers/d_tree_res_ip_res_hard_libstr.c:66) */
+		for(int c=n+1; c<=N; c++)
 			{
-			int nx1 = P->nx[n+1], nu1 = P->nu[n+1];
-			const double *M = P->BAbt[n];
+			if(dad_(P, c)!=n) { if(P->dad) continue; else break; }
+			const int e = c-1;
+			int nx1 = P->nx[c], nu1 = P->nu[c];
+			const double *M = P->BAbt[e];
 			for(j=0; j<nx1; j++)
 				{
-				double s = w->b[n][j] - w->ux[n+1][nu1+j];
+				double s = w->b[e][j] - w->ux[c][nu1+j];
 				for(i=0; i<nux; i++) s += M[i+nz*j]*w->ux[n][i];
-				w->res_b[n][j] = s;
+				w->res_b[e][j] = s;
 				}
 			for(i=0; i<nux; i++)
 				{
 				double s = 0.0;
-				for(j=0; j<nx1; j++) s += M[i+nz*j]*w->pi[n][j];
+				for(j=0; j<nx1; j++) s += M[i+nz*j]*w->pi[e][j];
 				rq[i] += s;
 				}
+			if(!P->dad) break;
 			}
 		}
 	if(nb_tot!=0) *mu = mu2/(2.0*nb_tot);
@@ -467,7 +503,7 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 		{
 		int nux = nux_(P,n), nz = nux+1;
 		for(j=0; j<nux; j++) w->rq[n][j] = P->RSQrq[n][nux+nz*j];
-		if(n<N) for(j=0; j<P->nx[n+1]; j++) w->b[n][j] = P->BAbt[n][nux+nz*j];
+		if(n<N) { int nuxd = nux_(P, dad_(P, n+1)); for(j=0; j<P->nx[n+1]; j++) w->b[n][j] = P->BAbt[n][nuxd+(nuxd+1)*j]; }
 		}
 
 	int status = -1;
@@ -938,4 +974,32 @@ void orc_tree_ric_sv(int Nn, const int *dad, const int *first_kid, const int *nk
 		}
 	for(nn=0; nn<Nn; nn++) { free(L[nn]); free(dinv[nn]); }
 	free(L); free(dinv); free(W); free(tmp);
+	}
+
+/* ------------------------------------------------------------------------------------------- */
+/* box-constrained IPM over a scenario tree: the IPM above with the tree Riccati               */
+/* (mpc_solvers/d_tree_ip2_res_hard_libstr.c:80: "IPM identical to the chain one with N = Nn-1",   */
+/* tree residuals mpc_solvers/d_tree_res_ip_res_hard_libstr.c:66).  The reference's tree path    */
+/* needs BLASFEO (absent): this is pinned by tests/test_tree_ipm.py against the chain IPM (itself */
+/* pinned on the compiled reference) solving the level-stacked problem, and on md = 1 trees.      */
+/*                                                                                             */
+/* nodes in BFS order; matrices as in orc_tree_ric_sv; d[n] = [lb(nb_n) ; ub(nb_n)]             */
+/* in/out: ux[n], lam[n], t[n] (2 nb_n each) ; pi[k], k >= 1 ; stat 5*k_max ; returns the status  */
+/* ------------------------------------------------------------------------------------------- */
+int orc_tree_ip2_res_mpc_hard(int Nn, const int *dad, const int *nx, const int *nu, const int *nb, int *const *idxb,
+		double *const *BAbt, double *const *RSQrq, double *const *d, int *kk, int k_max, double mu0, double mu_tol,
+		double alpha_min, int warm_start, double *stat, double **ux, double **pi, double **lam, double **t)
+	{
+	int n, N = Nn-1;
+	orc_prob *P = orc_prob_create_tree(N, nx, nu, nb, idxb, dad);
+	for(n=0; n<=N; n++)
+		{
+		int nux = nx[n]+nu[n], nz = nux+1;
+		memcpy(P->RSQrq[n], RSQrq[n], sizeof(double)*nz*(nux>0 ? nux : 0));
+		memcpy(P->d[n], d[n], sizeof(double)*2*P->nb[n]);
+		if(n>0) { int nzd = nux_(P, dad[n])+1; memcpy(P->BAbt[n-1], BAbt[n], sizeof(double)*nzd*nx[n]); }
+		}
+	int status = orc_ip2_res_mpc_hard(P, kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat, ux, pi+1, lam, t);
+	orc_prob_free(P);
+	return status;
 	}

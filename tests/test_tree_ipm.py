@@ -1,0 +1,56 @@
+"""Scenario-tree box IPM (BASELINE config 5: d_tree_ip2_res_hard).
+
+CPU: the oracle's tree IPM (oracle/ric_oracle.c: orc_tree_ip2_res_mpc_hard) against golden vectors produced by the REAL
+reference solving the level-stacked chain problem (tests/golden/make_golden_tree_ipm.py), and against the oracle's chain
+IPM on the same stacked problem.  GPU: hpmpc_b200_d_tree_ip2_res_mpc_hard_batch through the C ABI against the oracle
+(tolerance 1e-9 relative on u, x, pi, lam; identical iteration counts)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_golden_tree_ipm as G  # noqa: E402
+from hpmpc_b200 import tree as T  # noqa: E402
+from oracle import api  # noqa: E402
+
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "golden_tree_ipm_v1.npz"))
+TOL = 1e-9
+
+
+def cat(v):
+    return np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in v])
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b))))) if a.size else 0.0
+
+
+@pytest.mark.parametrize("case", list(G.CASES))
+def test_tree_ipm_oracle_matches_reference_golden(case):
+    t = G.build(case)
+    r = api.tree_ipm(t, k_max=G.K_MAX, mu0=G.MU0, mu_tol=G.MU_TOL)
+    assert [r["kk"], r["status"]] == list(GOLD[f"{case}/kk"])
+    for f in ("u", "x", "pi", "lam"):
+        assert rel(cat(r[f]), GOLD[f"{case}/{f}"]) < TOL, f
+
+
+def test_tree_ipm_oracle_matches_stacked_chain_oracle():
+    for shape in [(4, 2, 2, 2, 5), (8, 3, 3, 2, 6), (12, 5, 1, 0, 8), (12, 5, 2, 3, 8)]:
+        t = T.mass_spring_tree(*shape, xi=(0.3, -0.2, 0.1, 0.4), bounds=True)
+        r = api.tree_ipm(t)
+        p, maps = T.stacked_chain(t)
+        c = api.ipm(p, mu0=2.0)
+        u, x, pi = T.unstack(t, maps, c)
+        assert (r["kk"], r["status"]) == (c["kk"], c["status"]) and r["kk"] >= 5      # the input bounds are active
+        assert max(rel(cat(r["u"]), cat(u)), rel(cat(r["x"]), cat(x)), rel(cat(r["pi"]), cat(pi))) < TOL
+        assert rel(cat(r["lam"]), cat(G.node_lam(t, maps, p, c["lam"]))) < TOL
+
+
+def test_tree_ipm_without_bounds_is_the_tree_riccati():
+    t = T.mass_spring_tree(6, 2, 3, 2, 5, xi=(0.1, 0.2, -0.3, 0.0), bounds=False)
+    r, s = api.tree_ipm(t), api.tree_ric(t)
+    assert r["kk"] == 0 and r["status"] == 0
+    assert max(rel(cat(r[f]), cat(s[f])) for f in ("u", "x", "pi")) < 1e-12
