@@ -12,6 +12,7 @@
 #include "ric_sweeps.cuh"
 #include "ric_fast.cuh"
 #include "ric_ipm_fast.cuh"
+#include "ric_tree_ipm.cuh"
 
 extern "C" int hb_smem_bytes_per_warp(const hb_dims *d);
 
@@ -191,11 +192,45 @@ __device__ __forceinline__ double hb_ipm_mu_aff(int lane_, const hb_dims &d, con
 	return hb_warp_sum(mu)*mu_scal;
 	}
 
-/* The IPM kernel is written once; the five sweeps over the horizon come from a policy: the run-time-size routines of
- * ric_generic.cuh, or the size-specialised, bulk-copy-pipelined ones of ric_ipm_fast.cuh. */
+/* vectors taken from the instance block of a chain: rq0 = [r q], b0 = b, bounds */
+__device__ __forceinline__ void hb_ipm_extract_chain(int lane, const hb_dims &d, const double *__restrict__ in_inst, const hb_ipm_ws &w)
+	{
+	for(int n=0; n<=d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		const int nux = s.nu+s.nx;
+		for(int i=lane; i<nux; i+=32) w.rq0[s.off_ux+i] = in_inst[s.off_RSQ+HB_TRI(nux)+i];
+		for(int j=lane; j<s.nx1; j+=32) w.b0[s.off_pi+j] = in_inst[s.off_BAbt+nux*s.nx1+j];
+		for(int j=lane; j<s.nb; j+=32)
+			{
+			w.v(CV_LB)[s.off_c+j] = in_inst[s.off_d+j];
+			w.v(CV_UB)[s.off_c+j] = in_inst[s.off_d+s.nb+j];
+			}
+		}
+	}
+
+/* results: lam, t as [lower(nb) upper(nb)] per stage (interfaces/c/fortran_order_interface.c:662-671) */
+__device__ __forceinline__ void hb_ipm_emit_chain(int lane, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt)
+	{
+	for(int n=0; n<=d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		for(int j=lane; j<s.nb; j+=32)
+			{
+			lam[2*s.off_c+j] = w.v(CV_LAM_LO)[s.off_c+j]; lam[2*s.off_c+s.nb+j] = w.v(CV_LAM_UP)[s.off_c+j];
+			tt[2*s.off_c+j] = w.v(CV_T_LO)[s.off_c+j]; tt[2*s.off_c+s.nb+j] = w.v(CV_T_UP)[s.off_c+j];
+			}
+		}
+	}
+
+/* The IPM kernel is written once; the sweeps over the horizon (or the tree) come from a policy: the run-time-size routines
+ * of ric_generic.cuh, the size-specialised, bulk-copy-pipelined ones of ric_ipm_fast.cuh, or the tree ones of
+ * ric_tree_ipm.cuh. */
 struct hb_sweeps_generic
 	{
 	typedef hb_ctx ctx_t;
+	__device__ static __forceinline__ void extract(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w) { hb_ipm_extract_chain(c.lane, d, in_inst, w); }
+	__device__ static __forceinline__ void emit(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt) { hb_ipm_emit_chain(c.lane, d, w, lam, tt); }
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &d) { return hb_smem_doubles_per_warp(d.nzM, d.nxM); }
 	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return d.L_stride; }
 	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c = hb_make_ctx(d, smem_warp, lane); }
@@ -220,6 +255,8 @@ template<class C>
 struct hb_sweeps_fast
 	{
 	typedef hbi_ctx<C> ctx_t;
+	__device__ static __forceinline__ void extract(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w) { hb_ipm_extract_chain(c.lane, d, in_inst, w); }
+	__device__ static __forceinline__ void emit(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt) { hb_ipm_emit_chain(c.lane, d, w, lam, tt); }
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &) { return hbi_cfg<C>::PER_WARP; }
 	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return (long long)(d.N+1)*C::LBUF; }
 	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c.init(smem_warp, lane, d); }
@@ -243,6 +280,76 @@ struct hb_sweeps_fast
 		hb_ipm_residuals_bounds(c.lane, d, w, ux, mu2, nd);
 		__syncwarp();
 		hbi_residuals<C>(c, d, in_inst, w.rq0, w.b0, w.v(CV_LAM_LO), w.v(CV_LAM_UP), ux, pi, w.res_q, w.res_b, nq, nb_);
+		if(d.nbtot>0) *mu = mu2/(2.0*d.nbtot);
+		if(norms!=nullptr) { norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd); }
+		}
+	};
+
+/* scenario tree: d.tn is the node table (BFS order), d.N = Nn-1; nodes play the role of the stages */
+struct hb_sweeps_tree
+	{
+	typedef hb_ctx ctx_t;
+	__device__ static __forceinline__ int smem_doubles(const hb_dims &d) { return hb_smem_doubles_per_warp(d.nzM, d.nxM); }
+	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return d.L_stride; }
+	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c = hb_make_ctx(d, smem_warp, lane); }
+	__device__ static __forceinline__ void extract(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w)
+		{
+		const int lane = c.lane;
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_tnode s = d.tn[n];
+			const int nux = s.nu+s.nx;
+			for(int i=lane; i<nux; i+=32) w.rq0[s.off_ux+i] = in_inst[s.off_RSQ+HB_TRI(nux)+i];
+			if(s.dad>=0)
+				{
+				const hb_tnode dd = d.tn[s.dad];
+				const int nuxd = dd.nu+dd.nx;
+				for(int j=lane; j<s.nx; j+=32) w.b0[s.off_pi+j] = in_inst[s.off_BAbt+nuxd*s.nx+j];
+				}
+			for(int j=lane; j<s.nb; j+=32)
+				{
+				w.v(CV_LB)[s.off_c+j] = in_inst[s.off_d+j];
+				w.v(CV_UB)[s.off_c+j] = in_inst[s.off_d+s.nb+j];
+				}
+			}
+		}
+	__device__ static __forceinline__ void emit(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt)
+		{
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_tnode s = d.tn[n];
+			for(int j=c.lane; j<s.nb; j+=32)
+				{
+				lam[2*s.off_c+j] = w.v(CV_LAM_LO)[s.off_c+j]; lam[2*s.off_c+s.nb+j] = w.v(CV_LAM_UP)[s.off_c+j];
+				tt[2*s.off_c+j] = w.v(CV_T_LO)[s.off_c+j]; tt[2*s.off_c+s.nb+j] = w.v(CV_T_UP)[s.off_c+j];
+				}
+			}
+		}
+	__device__ static __forceinline__ void backward(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *Qx, const double *qx)
+		{
+		for(int n=d.N; n>=0; n--)
+			hb_tipm_node_factor(c, d.tn, n, in_inst, w.L, bv, rqv!=nullptr ? rqv : w.rq0, Qx, qx, d.idxb, w.Pb, c.bufA, c.bufB);
+		}
+	__device__ static __forceinline__ void forward_sv(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, double *ux, double *pi)
+		{
+		for(int n=0; n<=d.N; n++) hb_tipm_node_forward(c, d.tn, n, in_inst, w.L, nullptr, bv, false, ux, pi, c.bufA, c.bufB);
+		}
+	__device__ static __forceinline__ void trs(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		for(int n=d.N; n>=0; n--) hb_tipm_node_trs_back(c, d.tn, n, in_inst, w.L, rqv, qx, d.idxb, w.dux, w.Pb, c.bufA);
+		for(int n=0; n<=d.N; n++) hb_tipm_node_forward(c, d.tn, n, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, c.bufA, c.bufB);
+		}
+	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *ux, const double *pi, double *mu, double *norms)
+		{
+		double mu2, nd, nq = 0.0, nb_ = 0.0;
+		hb_ipm_residuals_bounds(c.lane, d, w, ux, mu2, nd);
+		__syncwarp();
+		for(int n=0; n<=d.N; n++)
+			hb_tipm_node_residuals(c, d.tn, n, in_inst, w.rq0, w.b0, w.v(CV_LAM_LO), w.v(CV_LAM_UP), d.idxb, ux, pi, w.res_q, w.res_b, nq, nb_);
 		if(d.nbtot>0) *mu = mu2/(2.0*d.nbtot);
 		if(norms!=nullptr) { norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd); }
 		}
@@ -284,18 +391,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 		double *stat = info + HB_IPM_INFO_HEAD;
 
 		/* vectors taken from the instance block: rq0 = [r q], b0 = b, bounds */
-		for(int n=0; n<=d.N; n++)
-			{
-			const hb_stage s = d.st[n];
-			const int nux = s.nu+s.nx;
-			for(int i=lane; i<nux; i+=32) w.rq0[s.off_ux+i] = in_inst[s.off_RSQ+HB_TRI(nux)+i];
-			for(int j=lane; j<s.nx1; j+=32) w.b0[s.off_pi+j] = in_inst[s.off_BAbt+nux*s.nx1+j];
-			for(int j=lane; j<s.nb; j+=32)
-				{
-				w.v(CV_LB)[s.off_c+j] = in_inst[s.off_d+j];
-				w.v(CV_UB)[s.off_c+j] = in_inst[s.off_d+s.nb+j];
-				}
-			}
+		S::extract(c, d, in_inst, w);
 		__syncwarp();
 
 		int kk = 0, status = -1;
@@ -481,15 +577,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 
 		/* results: lam, t as [lower(nb) upper(nb)] per stage (interfaces/c/fortran_order_interface.c:662-671) */
 		double *lam = lam_all + inst*2*(long long)d.nbtot, *tt = t_all + inst*2*(long long)d.nbtot;
-		for(int n=0; n<=d.N; n++)
-			{
-			const hb_stage s = d.st[n];
-			for(int j=lane; j<s.nb; j+=32)
-				{
-				lam[2*s.off_c+j] = w.v(CV_LAM_LO)[s.off_c+j]; lam[2*s.off_c+s.nb+j] = w.v(CV_LAM_UP)[s.off_c+j];
-				tt[2*s.off_c+j] = w.v(CV_T_LO)[s.off_c+j]; tt[2*s.off_c+s.nb+j] = w.v(CV_T_UP)[s.off_c+j];
-				}
-			}
+		S::emit(c, d, w, lam, tt);
 		if(lane==0)
 			{
 			info[0] = (double)kk; info[1] = (double)status;
@@ -571,6 +659,7 @@ extern "C" int hb_launch_ipm(const hb_dims *d, long long n_inst, const double *i
 #define HB_IPM_ARGS d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start, ux, pi, lam, t, info, work, work_stride, grid, warps, counter, st
 	switch(fast_id)
 		{
+		case HB_IPM_TREE: return d->tn==NULL ? -4 : hb_launch_ipm_t<hb_sweeps_tree>(warps*hb_smem_bytes_per_warp(d), HB_IPM_ARGS);
 		case 0: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v0> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v0>::PER_WARP, HB_IPM_ARGS);
 		case 1: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v1> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v1>::PER_WARP, HB_IPM_ARGS);
 		case 2: return hb_launch_ipm_t<hb_sweeps_fast<hbi_v2> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v2>::PER_WARP, HB_IPM_ARGS);

@@ -51,6 +51,7 @@ typedef struct hb_dims
 	const hb_stage *st;         /* [N+1]  (device pointer in kernel launches) */
 	const int *idxb;            /* [nbtot] bound index within its stage's ux */
 	const int *c_ux;            /* [nbtot] flat index into the instance's ux vector */
+	const struct hb_tnode *tn;  /* scenario-tree IPM only (ric_tree_ipm.cuh): node table [N+1], st is unused then; else NULL */
 	} hb_dims;
 
 /* scenario tree (ric_tree.cuh): one entry per node, BFS order; the edge data [B A b]' belongs to the kid */
@@ -59,7 +60,8 @@ typedef struct hb_tnode
 	int nx, nu, nkids, first_kid, dad;
 	int off_BAbt, off_RSQ;      /* into the tree's input block (doubles); off_BAbt is the edge INTO this node */
 	int off_ux, off_pi, off_L;  /* node-indexed outputs / factor stash */
-	int pad0, pad1;
+	int nb, off_c, off_d;       /* box bounds of the node: count, first flat constraint, [lb(nb) ub(nb)] in the input block */
+	int pad0, pad1, pad2;
 	} hb_tnode;
 
 typedef struct hb_tdims
@@ -100,6 +102,8 @@ int hb_launch_ric_trs(const hb_dims *dims, long long n_inst, const double *in, c
 int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
 		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
 		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream);
+/* fast_id -2 : dims->tn describes a scenario tree (one warp per tree, generic node sizes) */
+#define HB_IPM_TREE (-2)
 int hb_ipm_fast_variant(int N, const int *nx, const int *nu, int nbtot);
 int hb_ipm_fast_info(int id, int N, int *smem_warp, long long *L_doubles);
 long long hb_ipm_work_doubles2(const hb_dims *dims, long long L_doubles);

@@ -27,9 +27,20 @@ struct hpmpc_b200_tree
 	int tail_fast_id, t_ipw, t_smem_warp;   /* size-specialised tail kernel, -1 when the tails do not qualify */
 	int top_fast;                           /* the top runs on the size-specialised stage routines too */
 	hb_tail_tab tab;
+	/* box-constrained IPM over the tree (hpmpc_b200_tree_create_box): flat constraint tables and the per-warp work slots */
+	int nbtot;
+	int *idxb, *c_ux;        /* host copies [nbtot] */
+	hb_dims ipm_dims;        /* device pointers inside; st unused, tn = the node table */
+	double *ipm_ws; long long ipm_ws_stride; int ipm_slots; int *ipm_counter;
 	};
 
 int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
+	{
+	return hpmpc_b200_tree_create_box(out, Nn, tree, nx, nu, NULL, NULL, device);
+	}
+
+int hpmpc_b200_tree_create_box(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu,
+		const int *nb, int *const *idxb, int device)
 	{
 	int n, j;
 	*out = NULL;
@@ -52,6 +63,9 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 		if(t->stage[n]>max_stage) max_stage = t->stage[n];
 		if(s->nu+s->nx+1>nzM) nzM = s->nu+s->nx+1;
 		if(s->nx>nxM) nxM = s->nx;
+		s->nb = nb ? nb[n] : 0;
+		if(s->nb<0 || s->nb>s->nu+s->nx) { fprintf(stderr, "hpmpc_b200: tree: node %d: nb = %d out of range\n", n, s->nb); return -2; }
+		s->off_c = t->nbtot; t->nbtot += s->nb;
 		}
 	if(nzM>64) { fprintf(stderr, "hpmpc_b200: tree: nu+nx+1 = %d > 64 is not supported\n", nzM); return -2; }
 	/* cut: smallest stage c such that every node of stage >= c has at most one kid */
@@ -99,6 +113,7 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 			}
 		else s->off_BAbt = -1;
 		s->off_RSQ = (int)o_in; o_in += HB_EVEN(HB_TRI(nux)+nux);
+		s->off_d = (int)o_in; o_in += HB_EVEN(2*s->nb);           /* [lb(nb) ub(nb)] */
 		s->off_ux = (int)o_ux; o_ux += nux;
 		s->off_pi = (int)o_pi; o_pi += s->nx;
 		s->off_L = (int)o_L;
@@ -169,6 +184,18 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 	t->dims.Nn = Nn; t->dims.nzM = nzM; t->dims.nxM = nxM; t->dims.n_seg = t->n_seg;
 	t->dims.in_stride = o_in; t->dims.ux_stride = HB_EVEN(o_ux); t->dims.pi_stride = HB_EVEN(o_pi); t->dims.L_stride = o_L;
 	t->sms = 148;
+	t->idxb = calloc(t->nbtot+1, sizeof(int)); t->c_ux = calloc(t->nbtot+1, sizeof(int));
+	for(n=0; n<Nn; n++)
+		for(j=0; j<t->tn[n].nb; j++)
+			{
+			int id = idxb[n][j];
+			if(id<0 || id>=t->tn[n].nu+t->tn[n].nx) { fprintf(stderr, "hpmpc_b200: tree: node %d: idxb[%d] = %d out of range\n", n, j, id); return -2; }
+			t->idxb[t->tn[n].off_c+j] = id; t->c_ux[t->tn[n].off_c+j] = t->tn[n].off_ux + id;
+			}
+	memset(&t->ipm_dims, 0, sizeof(t->ipm_dims));
+	t->ipm_dims.N = Nn-1; t->ipm_dims.nzM = nzM; t->ipm_dims.nxM = nxM; t->ipm_dims.nbtot = t->nbtot;
+	t->ipm_dims.in_stride = t->dims.in_stride; t->ipm_dims.ux_stride = t->dims.ux_stride; t->ipm_dims.pi_stride = t->dims.pi_stride;
+	t->ipm_dims.L_stride = HB_EVEN(t->dims.L_stride);
 	if(device>=0)
 		{
 		CK(cudaSetDevice(device));
@@ -180,6 +207,14 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 		CK(cudaMemcpy(d_ss, t->seg_start, (t->n_seg+1)*sizeof(int), cudaMemcpyHostToDevice));
 		CK(cudaMemcpy(d_sn, t->seg_nodes, Nn*sizeof(int), cudaMemcpyHostToDevice));
 		t->dims.tn = d_tn; t->dims.seg_start = d_ss; t->dims.seg_nodes = d_sn;
+		{
+		int *d_idxb, *d_cux;
+		CK(cudaMalloc((void**)&d_idxb, (t->nbtot+1)*sizeof(int)));
+		CK(cudaMalloc((void**)&d_cux, (t->nbtot+1)*sizeof(int)));
+		CK(cudaMemcpy(d_idxb, t->idxb, (t->nbtot+1)*sizeof(int), cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(d_cux, t->c_ux, (t->nbtot+1)*sizeof(int), cudaMemcpyHostToDevice));
+		t->ipm_dims.idxb = d_idxb; t->ipm_dims.c_ux = d_cux; t->ipm_dims.tn = d_tn;
+		}
 		t->sms = hb_device_sm_count(device);
 		if(t->sms<=0) return -1;
 		}
@@ -194,7 +229,9 @@ void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
 		{
 		cudaSetDevice(t->device);
 		cudaFree((void*)t->dims.tn); cudaFree((void*)t->dims.seg_start); cudaFree((void*)t->dims.seg_nodes);
+		cudaFree((void*)t->ipm_dims.idxb); cudaFree((void*)t->ipm_dims.c_ux); cudaFree(t->ipm_ws); cudaFree(t->ipm_counter);
 		}
+	free(t->idxb); free(t->c_ux);
 	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->slot); free(t->tail_root); free(t);
 	}
 
@@ -264,6 +301,24 @@ int hpmpc_b200_tree_pack_instance(const hpmpc_b200_tree *t, double *const *A, do
 		for(j=0; j<nx; j++) H[HB_TRI(nux)+nu+j] = q[n][j];
 		}
 	return 0;
+	}
+
+int hpmpc_b200_tree_pack_bounds(const hpmpc_b200_tree *t, double *const *lb, double *const *ub, double *blk)
+	{
+	int n, j;
+	for(n=0; n<t->Nn; n++)
+		{
+		const hb_tnode *s = &t->tn[n];
+		for(j=0; j<s->nb; j++) { blk[s->off_d+j] = lb[n][j]; blk[s->off_d+s->nb+j] = ub[n][j]; }
+		}
+	return 0;
+	}
+
+void hpmpc_b200_tree_bound_offsets(const hpmpc_b200_tree *t, int n, int *nb, int *off_c, int *off_d)
+	{
+	if(nb) *nb = t->tn[n].nb;
+	if(off_c) *off_c = t->tn[n].off_c;
+	if(off_d) *off_d = t->tn[n].off_d;
 	}
 
 static void launch_shape(const hpmpc_b200_tree *t, long long items, int *grid, int *warps)
@@ -351,4 +406,29 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_tree
 	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 0, 0, t->n_tails, d_in, d_ux, d_pi, d_L, stream))) return rc;
 	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 1, 0, 0, d_in, d_ux, d_pi, d_L, stream))) return rc;
 	return hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 2, 0, t->n_tails, d_in, d_ux, d_pi, d_L, stream);
+	}
+
+/* box-constrained IPM over a batch of trees: the whole iteration runs in one kernel, one warp per tree taking trees from a
+ * queue (hb_ipm_kernel with the tree sweeps of ric_tree_ipm.cuh); per-warp work slots live in the handle */
+int hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info,
+		void *stream)
+	{
+	if(n_trees<=0) return 0;
+	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
+	if(k_max<1) return -2;
+	CK(cudaSetDevice(t->device));
+	int grid, warps;
+	launch_shape(t, n_trees, &grid, &warps);
+	const long long stride = HB_EVEN(hb_ipm_work_doubles(&t->ipm_dims));
+	if(t->ipm_ws==NULL || t->ipm_slots<grid*warps || t->ipm_ws_stride!=stride)
+		{
+		CK(cudaStreamSynchronize((cudaStream_t)stream));
+		cudaFree(t->ipm_ws); t->ipm_ws = NULL;
+		t->ipm_slots = grid*warps; t->ipm_ws_stride = stride;
+		CK(cudaMalloc((void**)&t->ipm_ws, sizeof(double)*(size_t)stride*t->ipm_slots));
+		if(t->ipm_counter==NULL) CK(cudaMalloc((void**)&t->ipm_counter, sizeof(int)));
+		}
+	return hb_launch_ipm(&t->ipm_dims, n_trees, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
+			t->ipm_ws, stride, t->ipm_slots, grid, warps, t->ipm_counter, HB_IPM_TREE, stream);
 	}

@@ -191,10 +191,25 @@ class TreeBatch:
         L.hpmpc_b200_d_tree_back_ric_rec_sv_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 5
         L.hpmpc_b200_d_tree_back_ric_rec_sv_phase.restype = C.c_int
         L.hpmpc_b200_d_tree_back_ric_rec_sv_phase.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.hpmpc_b200_tree_create_box.restype = C.c_int
+        L.hpmpc_b200_tree_create_box.argtypes = [C.POINTER(C.c_void_p), C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+        L.hpmpc_b200_tree_pack_bounds.restype = C.c_int
+        L.hpmpc_b200_tree_pack_bounds.argtypes = [C.c_void_p] * 4
+        L.hpmpc_b200_tree_bound_offsets.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
+        L.hpmpc_b200_d_tree_ip2_res_mpc_hard_batch.restype = C.c_int
+        L.hpmpc_b200_d_tree_ip2_res_mpc_hard_batch.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                                               C.c_int] + [C.c_void_p] * 6
         self.h = C.c_void_p()
-        rc = L.hpmpc_b200_tree_create(C.byref(self.h), Nn, C.cast(self._nodes, C.c_void_p), capi.int_array(t.nx), capi.int_array(t.nu), device)
+        self.nb = list(t.nb) if t.nb else [0] * Nn
+        if t.nb:
+            self._idxb = [np.ascontiguousarray(t.idxb[n], dtype=np.int32) if self.nb[n] else np.zeros(1, dtype=np.int32) for n in range(Nn)]
+            rc = L.hpmpc_b200_tree_create_box(C.byref(self.h), Nn, C.cast(self._nodes, C.c_void_p), capi.int_array(t.nx), capi.int_array(t.nu),
+                                              capi.int_array(self.nb), capi.ptr_array(self._idxb), device)
+        else:
+            rc = L.hpmpc_b200_tree_create(C.byref(self.h), Nn, C.cast(self._nodes, C.c_void_p), capi.int_array(t.nx), capi.int_array(t.nu), device)
         if rc != 0:
             raise RuntimeError(f"hpmpc_b200_tree_create failed ({rc})")
+        self.nbtot = sum(self.nb)
         self.sz = TreeSizes()
         L.hpmpc_b200_tree_sizes_get(self.h, C.byref(self.sz))
         self.off = []
@@ -228,7 +243,19 @@ class TreeBatch:
         self._keep = arrs
         rc = self.L.hpmpc_b200_tree_pack_instance(self.h, *[ptr_array(a) for a in arrs], blk.ctypes.data)
         assert rc == 0
+        if t.nb:
+            lb = [np.ascontiguousarray(v, dtype=np.float64) if len(v) else np.zeros(1) for v in t.lb]
+            ub = [np.ascontiguousarray(v, dtype=np.float64) if len(v) else np.zeros(1) for v in t.ub]
+            rc = self.L.hpmpc_b200_tree_pack_bounds(self.h, ptr_array(lb), ptr_array(ub), blk.ctypes.data)
+            assert rc == 0
         return blk
+
+    def split_lam(self, lam: np.ndarray):
+        """per tree [node: lower(nb) upper(nb)] -> list per node"""
+        out, o = [], 0
+        for n in range(self.t.topo["Nn"]):
+            out.append(lam[o:o + 2 * self.nb[n]].copy()); o += 2 * self.nb[n]
+        return out
 
     def split(self, ux: np.ndarray, pi: np.ndarray):
         t = self.t

@@ -63,6 +63,22 @@ void hpmpc_b200_tree_shard_node(const hpmpc_b200_tree *t, int k, int *node, int 
 int  hpmpc_b200_tree_pack_instance(const hpmpc_b200_tree *t, double *const *A, double *const *B, double *const *b,
                                    double *const *Q, double *const *S, double *const *R, double *const *q, double *const *r, double *block);
 
+/* ---- box-constrained IPM over the tree:  d_tree_ip2_res_mpc_hard_libstr (reference include/mpc_solvers.h,
+ * mpc_solvers/d_tree_ip2_res_hard_libstr.c:80), ng = 0 ----
+ * nb[n] bounds at node n on the entries idxb[n][0..nb[n]) of [u_n ; x_n]; with nb == NULL this is hpmpc_b200_tree_create.
+ * The bounds [lb(nb) ub(nb)] of a node follow its RSQrq in the packed block (hpmpc_b200_tree_bound_offsets: off_d);
+ * constraints are numbered node by node (off_c), and d_lam / d_t hold per tree, per node, [lower(nb) upper(nb)] at 2*off_c. */
+int  hpmpc_b200_tree_create_box(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu,
+                                const int *nb, int *const *idxb, int device);
+void hpmpc_b200_tree_bound_offsets(const hpmpc_b200_tree *t, int n, int *nb, int *off_c, int *off_d);
+int  hpmpc_b200_tree_pack_bounds(const hpmpc_b200_tree *t, double *const *lb, double *const *ub, double *block);   /* after pack_instance */
+/* same arguments and return record as hpmpc_b200_d_ip2_res_mpc_hard_batch (hpmpc_b200.h): d_info holds 6 + 5*k_max doubles per
+ * tree (kk, status, |res_q|, |res_b|, |res_d|, mu, then sigma/alpha_aff/mu_aff/alpha/mu per iteration); status 0 converged,
+ * 1 kk >= k_max, 2 alpha < alpha_min (mpc_solvers/d_ip2_res_hard.c:1331-1343).  d_ux, d_pi in the node-indexed layouts above. */
+int  hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, int k_max, double mu0,
+                                              double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi,
+                                              double *d_lam, double *d_t, double *d_info, void *stream);
+
 /* whole solve on one GPU (phases 0, 1, 2 back to back) */
 int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in,
                                             double *d_ux, double *d_pi, double *d_L, void *stream);

@@ -54,3 +54,72 @@ def test_tree_ipm_without_bounds_is_the_tree_riccati():
     r, s = api.tree_ipm(t), api.tree_ric(t)
     assert r["kk"] == 0 and r["status"] == 0
     assert max(rel(cat(r[f]), cat(s[f])) for f in ("u", "x", "pi")) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU
+def _gpu_ipm(tb, blocks, k_max=G.K_MAX, mu0=G.MU0, mu_tol=G.MU_TOL):
+    import ctypes as C
+    import torch
+    n = len(blocks)
+    sz = tb.sz
+    d_in = torch.from_numpy(np.stack(blocks)).cuda()
+    z = lambda m: torch.zeros((n, max(int(m), 2)), dtype=torch.float64, device="cuda")
+    ux, pi, lam, tt, info = z(sz.ux_stride), z(sz.pi_stride), z(2 * tb.nbtot), z(2 * tb.nbtot), z(6 + 5 * k_max)
+    rc = tb.L.hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(tb.h, n, d_in.data_ptr(), k_max, C.c_double(mu0), C.c_double(mu_tol), C.c_double(1e-8), 0,
+                                                      ux.data_ptr(), pi.data_ptr(), lam.data_ptr(), tt.data_ptr(), info.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return ux.cpu().numpy(), pi.cpu().numpy(), lam.cpu().numpy(), info.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(G.CASES))
+def test_tree_ipm_gpu_matches_reference_golden(case):
+    t = G.build(case)
+    tb = T.TreeBatch(t)
+    try:
+        ux, pi, lam, info = _gpu_ipm(tb, [tb.pack(t)])
+        assert [int(info[0, 0]), int(info[0, 1])] == list(GOLD[f"{case}/kk"])
+        u, x, p = tb.split(ux[0], pi[0])
+        got = dict(u=u, x=x, pi=p, lam=tb.split_lam(lam[0]))
+        for f in ("u", "x", "pi", "lam"):
+            assert rel(cat(got[f]), GOLD[f"{case}/{f}"]) < TOL, f
+    finally:
+        tb.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 2, 2, 2, 5), (8, 3, 3, 2, 6), (12, 5, 1, 0, 8), (12, 5, 4, 3, 20)])
+def test_tree_ipm_gpu_batch_vs_oracle(shape):
+    """a ragged batch of different instances (more trees than one warp slot sees), every tree against the oracle"""
+    from hpmpc_b200 import problems
+    n = 5 if shape[-1] < 20 else 2
+    xis = problems.instance_xi(n, first=11)
+    ts = [T.mass_spring_tree(*shape, xi=tuple(xis[i]), bounds=True) for i in range(n)]
+    tb = T.TreeBatch(ts[0])
+    try:
+        ux, pi, lam, info = _gpu_ipm(tb, [tb.pack(t) for t in ts])
+        for i, t in enumerate(ts):
+            r = api.tree_ipm(t, k_max=G.K_MAX, mu0=G.MU0, mu_tol=G.MU_TOL)
+            assert (int(info[i, 0]), int(info[i, 1])) == (r["kk"], r["status"])
+            u, x, p = tb.split(ux[i], pi[i])
+            got = dict(u=u, x=x, pi=p, lam=tb.split_lam(lam[i]))
+            for f in ("u", "x", "pi", "lam"):
+                assert rel(cat(got[f]), cat(r[f])) < TOL, (i, f)
+            assert abs(info[i, 5] - r["stat"][-1, 4]) <= 1e-9 * max(1.0, abs(r["stat"][-1, 4]))      # final mu
+    finally:
+        tb.close()
+
+
+@pytest.mark.gpu
+def test_tree_ipm_gpu_unconstrained_tree_is_one_riccati_solve():
+    t = T.mass_spring_tree(6, 2, 3, 2, 5, xi=(0.1, 0.2, -0.3, 0.0), bounds=False)
+    tb = T.TreeBatch(t)
+    try:
+        ux, pi, lam, info = _gpu_ipm(tb, [tb.pack(t)])
+        s = api.tree_ric(t)
+        u, x, p = tb.split(ux[0], pi[0])
+        assert int(info[0, 0]) == 0 and int(info[0, 1]) == 0
+        assert max(rel(cat(u), cat(s["u"])), rel(cat(x), cat(s["x"])), rel(cat(p), cat(s["pi"]))) < TOL
+    finally:
+        tb.close()
