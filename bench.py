@@ -373,6 +373,58 @@ def run_ours(args):
         h.close()
         return out
 
+    def bench_tree_ipm(steps, warmup):
+        """BASELINE config 5 as named (d_tree_ip2_res_hard): box IPM over scenario trees md=4, Nr=3, Nh=20, nx=12, nu=5 (1173 nodes,
+        u in [-0.5, 0.5] at every node); the batch of trees is split over the ranks (independent units, no collective)."""
+        import ctypes as C
+        from hpmpc_b200 import tree as T
+        from hpmpc_b200.problems import instance_xi
+        t0 = T.mass_spring_tree(12, 5, 4, 3, 20, bounds=True)
+        h = T.TreeBatch(t0, device=local)
+        n = args.n_trees or 2048
+        k_max = 40
+        base = torch.from_numpy(h.pack(t0)).to(dev)
+        mask = torch.zeros_like(base)
+        for nd in range(h.sz.Nn):
+            nux = t0.nu[nd] + t0.nx[nd]
+            mask[h.off[nd]["RSQ"]:h.off[nd]["RSQ"] + nux * (nux + 1) // 2 + nux] = 1.0
+        xi = torch.from_numpy(instance_xi(n, first=rank * n)[:, 2].copy()).to(dev)
+        d_in = base[None, :] * (1.0 + 0.1 * xi[:, None] * mask[None, :])       # per-tree cost scaling: distinct problems, same bounds
+        z = lambda m: torch.zeros((n, max(int(m), 2)), dtype=torch.float64, device=dev)
+        ux, pi, lam, tt, info = z(h.sz.ux_stride), z(h.sz.pi_stride), z(2 * h.nbtot), z(2 * h.nbtot), z(6 + 5 * k_max)
+        fn = h.L.hpmpc_b200_d_tree_ip2_res_mpc_hard_batch
+
+        def launch():
+            assert fn(h.h, n, d_in.data_ptr(), k_max, C.c_double(2.0), C.c_double(1e-8), C.c_double(1e-8), 0, ux.data_ptr(), pi.data_ptr(),
+                      lam.data_ptr(), tt.data_ptr(), info.data_ptr(), st) == 0
+        tot_ms, per = time_steps(launch, steps, warmup, stream, barrier)
+        tot_ms = reduce_max_time(tot_ms, dev)
+        kk = info[:, 0]
+        conv = int((info[:, 1] == 0).sum().item())
+        out = {"metric": "tree_box_ipm_solves_per_s", "value": world * n * steps / (tot_ms * 1e-3), "unit": "trees/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": f"scenario-tree box IPM (d_tree_ip2_res_mpc_hard), {n} trees/GPU, md=4 Nr=3 Nh=20 nx=12 nu=5 (1173 nodes, "
+                                      f"{h.nbtot} bounded inputs), tol 1e-8, FP64",
+                          "parallelism": f"trees sharded over {world} GPU(s), no collective (one warp per tree, whole IPM in one kernel)"},
+               "mean_iterations": float(kk.mean().item()), "converged": conv, "trees_per_gpu": n, "gpu_launches": steps}
+        if rank == 0 and not args.no_cpu:
+            from oracle import api
+            t1 = time.perf_counter(); r = api.tree_ipm(t0); dt = time.perf_counter() - t1
+            out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "trees/s", "cores": 1, "kind": "port",
+                                   "sample": f"1 tree, oracle/ric_oracle.c orc_tree_ip2_res_mpc_hard (kk={r['kk']}); the reference's own tree IPM needs BLASFEO (absent)"}
+        h.close()
+        return out
+
+    if args.workload == "tree_ipm":
+        tr = bench_tree_ipm(min(args.steps, 3), min(args.warmup, 1))
+        if rank == 0:
+            print(json.dumps(tr))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     if args.workload == "tree":
         tr = bench_tree(args.steps, args.warmup)
         if rank == 0:
@@ -452,7 +504,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ric", choices=["ric", "ipm", "tree"])
+    ap.add_argument("--workload", default="ric", choices=["ric", "ipm", "tree", "tree_ipm"])
     ap.add_argument("--n-trees", type=int, default=0)
     ap.add_argument("--n-inst", type=int, default=0)
     ap.add_argument("--n-inst-ipm", type=int, default=0)
