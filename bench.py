@@ -276,13 +276,18 @@ def run_ours(args):
         mean_kk = float(kk.mean())
         launch_ms = float(np.mean(per))
         wave = max(1, h.sz.ipm_grid * h.sz.ipm_warps_per_cta)
+        try:
+            ipm_traffic_wave = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("hb_ipm_bytes_per_launch") if h.sz.ipm_fast_variant == 0 else None
+        except Exception:
+            ipm_traffic_wave = None
         out = {"metric": "box_ipm_qp_solves_per_s", "value": world * n * steps / (tot_ms * 1e-3), "unit": "solves/s",
                "workload": workload_name("ipm"), "steps": steps, "ms_per_step": tot_ms / steps, "mean_iterations": mean_kk,
                "converged": int((info[:, 1] == 0).sum()), "instances_per_gpu": n,
                "launch": {"grid": h.sz.ipm_grid, "warps_per_cta": h.sz.ipm_warps_per_cta, "wave": wave, "fast_variant": h.sz.ipm_fast_variant},
                "gpu_launches": steps * ((n + wave - 1) // wave),
                "roofline": {"bound": "hbm", "achieved": w["B_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": w["B_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                            "frac": w["B_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ipm_traffic_wave,
+                            "traffic_note": "DRAM bytes of one wave launch (1184 instances) from the ncu capture in profiles/",
                             "kernel": "hb_ipm_kernel<hb_sweeps_fast<24,11>> (one launch per wave)",
                             "bytes_per_iteration_model": w["B_it"], "flops_per_iteration_model": w["F_it"],
                             "fp64_tflops": w["F_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e12}}
