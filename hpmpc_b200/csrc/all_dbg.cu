@@ -3,3 +3,4 @@
 #include "ric_kernels.cu"
 #include "ipm_kernels.cu"
 #include "blk_kernels.cu"
+#include "tree_ipm_kernels.cu"

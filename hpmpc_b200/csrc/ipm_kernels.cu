@@ -19,61 +19,7 @@ extern "C" int hb_smem_bytes_per_warp(const hb_dims *d);
 /* ------------------------------------------------------------------------------------------------ */
 /* IPM                                                                                               */
 /* ------------------------------------------------------------------------------------------------ */
-enum { CV_LB=0, CV_UB, CV_LAM_LO, CV_LAM_UP, CV_T_LO, CV_T_UP, CV_DLAM_LO, CV_DLAM_UP, CV_DT_LO, CV_DT_UP,
-       CV_TINV_LO, CV_TINV_UP, CV_LAMT_LO, CV_LAMT_UP, CV_QXD /* "Qx": Hessian diagonal term */,
-       CV_QXG /* "qx": gradient term */, CV_RD_LO, CV_RD_UP, CV_RM_LO, CV_RM_UP, CV_COUNT };
-
-struct hb_ipm_ws
-	{
-	double *L;                               /* factor stash */
-	double *dux, *res_q, *rq0;               /* ux layout */
-	double *dpi, *Pb, *res_b, *b0;           /* pi layout */
-	double *cv;                              /* CV_COUNT x nbp */
-	int nbp;
-	__device__ __forceinline__ double *v(int k) const { return cv + (size_t)k*nbp; }
-	};
-
-__host__ __device__ inline long long hb_ipm_work_doubles_(const hb_dims &d)
-	{
-	long long nbp = HB_EVEN(d.nbtot);
-	return d.L_stride + 3*d.ux_stride + 4*d.pi_stride + (long long)CV_COUNT*nbp;
-	}
-
-__device__ __forceinline__ double hb_warp_min(double v)
-	{
-	for(int o=16; o>0; o>>=1) v = fmin(v, __shfl_xor_sync(HB_FULL, v, o));
-	return v;
-	}
-__device__ __forceinline__ double hb_warp_max(double v)
-	{
-	for(int o=16; o>0; o>>=1) v = fmax(v, __shfl_xor_sync(HB_FULL, v, o));
-	return v;
-	}
-/* fixed-order (deterministic) warp sum */
-__device__ __forceinline__ double hb_warp_sum(double v)
-	{
-	for(int o=16; o>0; o>>=1) v += __shfl_xor_sync(HB_FULL, v, o);
-	return v;
-	}
-
-/* bound part of the residuals: res_d, res_m and their sum (mpc_solvers/c99/d_res_ip_res_hard.c:39-319) */
-__device__ __forceinline__ void hb_ipm_residuals_bounds(int lane, const hb_dims &d, const hb_ipm_ws &w, const double *ux, double &mu2, double &nd)
-	{
-	const double *lam_lo = w.v(CV_LAM_LO), *lam_up = w.v(CV_LAM_UP), *t_lo = w.v(CV_T_LO), *t_up = w.v(CV_T_UP);
-	mu2 = 0.0; nd = 0.0;
-	for(int cc=lane; cc<d.nbtot; cc+=32)
-		{
-		double u = ux[d.c_ux[cc]];
-		double rdl = w.v(CV_LB)[cc] - u + t_lo[cc];
-		double rdu = w.v(CV_UB)[cc] - u - t_up[cc];
-		double rml = lam_lo[cc]*t_lo[cc], rmu = lam_up[cc]*t_up[cc];
-		w.v(CV_RD_LO)[cc] = rdl; w.v(CV_RD_UP)[cc] = rdu;
-		w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
-		mu2 += rml + rmu;
-		nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
-		}
-	mu2 = hb_warp_sum(mu2);
-	}
+#include "ipm_elem.cuh"
 
 /* res_q, res_b, res_d, res_m and mu (mpc_solvers/c99/d_res_ip_res_hard.c:39-319); also returns the three
  * infinity norms used by the high-level wrapper on exit (interfaces/c/fortran_order_interface.c:616-652) */
@@ -146,50 +92,6 @@ __device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const double
 		{
 		norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd);
 		}
-	}
-
-/* step length + dt, dlam.  RES = false: phase 1 (c99/d_aux_ip_hard_lib4.c:489-614) ; true: phase 2 (:1180-1313) */
-template<bool RES>
-__device__ __forceinline__ double hb_ipm_alpha(int lane_, const hb_dims &d, const hb_ipm_ws &w, const double *dux)
-	{
-	double alpha = 1.0;
-	for(int cc=lane_; cc<d.nbtot; cc+=32)
-		{
-		double du = dux[d.c_ux[cc]];
-		double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc], tl = w.v(CV_T_LO)[cc], tu = w.v(CV_T_UP)[cc];
-		double dtl, dtu, dll, dlu;
-		if(!RES)
-			{
-			dtl =  du - w.v(CV_LB)[cc] - tl;
-			dtu = -du + w.v(CV_UB)[cc] - tu;
-			dll = w.v(CV_DLAM_LO)[cc] - (w.v(CV_LAMT_LO)[cc]*dtl + ll);
-			dlu = w.v(CV_DLAM_UP)[cc] - (w.v(CV_LAMT_UP)[cc]*dtu + lu);
-			}
-		else
-			{
-			dtl =  du - w.v(CV_RD_LO)[cc];
-			dtu = -du + w.v(CV_RD_UP)[cc];
-			dll = -w.v(CV_TINV_LO)[cc]*(ll*dtl + w.v(CV_RM_LO)[cc]);
-			dlu = -w.v(CV_TINV_UP)[cc]*(lu*dtu + w.v(CV_RM_UP)[cc]);
-			}
-		w.v(CV_DT_LO)[cc] = dtl; w.v(CV_DT_UP)[cc] = dtu;
-		w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
-		if(-alpha*dll>ll) alpha = -ll/dll;
-		if(-alpha*dlu>lu) alpha = -lu/dlu;
-		if(-alpha*dtl>tl) alpha = -tl/dtl;
-		if(-alpha*dtu>tu) alpha = -tu/dtu;
-		}
-	return hb_warp_min(alpha);
-	}
-
-/* mu_aff = mu_scal * sum (lam + a dlam)(t + a dt)   (c99/d_aux_ip_hard_lib4.c:715-770, :1453-1508) */
-__device__ __forceinline__ double hb_ipm_mu_aff(int lane_, const hb_dims &d, const hb_ipm_ws &w, double alpha, double mu_scal)
-	{
-	double mu = 0.0;
-	for(int cc=lane_; cc<d.nbtot; cc+=32)
-		mu += (w.v(CV_LAM_LO)[cc] + alpha*w.v(CV_DLAM_LO)[cc])*(w.v(CV_T_LO)[cc] + alpha*w.v(CV_DT_LO)[cc])
-		    + (w.v(CV_LAM_UP)[cc] + alpha*w.v(CV_DLAM_UP)[cc])*(w.v(CV_T_UP)[cc] + alpha*w.v(CV_DT_UP)[cc]);
-	return hb_warp_sum(mu)*mu_scal;
 	}
 
 /* vectors taken from the instance block of a chain: rq0 = [r q], b0 = b, bounds */

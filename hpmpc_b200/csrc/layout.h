@@ -73,6 +73,16 @@ typedef struct hb_tdims
 	const int *seg_nodes;       /* node indices, top-down within a segment */
 	} hb_tdims;
 
+/* flat maps of the multi-kernel tree IPM (tree_ipm_kernels.cu): where the entries of the right-hand sides and of the bounded
+ * Hessian diagonal sit in a tree's packed block (device pointers in kernel launches) */
+typedef struct hb_tipm_maps
+	{
+	const int *g_ux;            /* [n_ux]  ux index -> gradient-row entry of its node's RSQrq */
+	const int *b_pi;            /* [n_pi]  pi index -> b-row entry of the edge's [B A b]'     */
+	const int *c_diag, *c_grad; /* [nbtot] constraint -> Hessian diagonal / gradient-row entry of the bounded variable */
+	int n_ux, n_pi;
+	} hb_tipm_maps;
+
 /* tails of a scenario tree solved by the size-specialised chain kernel (ric_blk.cuh: hbk_tail_kernel): all tails have the same
  * length and node sizes, and the offsets of the node at position m of tail j are affine in j: pos*[m] + j*str*[m] */
 #define HB_TAIL_MAXLEN 64
@@ -119,6 +129,10 @@ int hb_launch_tail(int id, const hb_tdims *dims, const hb_tail_tab *tab, long lo
 		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream);
 int hb_launch_top(int id, const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
 		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream);
+long long hb_tipm_work_doubles(const hb_dims *dims);
+int hb_launch_tipm_step(const hb_dims *dims, const hb_tipm_maps *maps, long long n_trees, const double *in, double *in_mod, int k_max,
+		double mu0, double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *dux, double *dpi, double *lam,
+		double *t, double *info, double *work, long long work_stride, double *state, int *n_active, void *stream);
 long long hb_ipm_work_doubles(const hb_dims *dims);
 int hb_smem_bytes_per_warp(const hb_dims *dims);
 int hb_smem_bytes_per_warp_sz(int nzM, int nxM);

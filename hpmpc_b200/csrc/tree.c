@@ -32,6 +32,11 @@ struct hpmpc_b200_tree
 	int *idxb, *c_ux;        /* host copies [nbtot] */
 	hb_dims ipm_dims;        /* device pointers inside; st unused, tn = the node table */
 	double *ipm_ws; long long ipm_ws_stride; int ipm_slots; int *ipm_counter;
+	/* multi-kernel IPM around the size-specialised tree Riccati (tree_ipm_kernels.cu): flat maps and per-tree buffers */
+	hb_tipm_maps maps;       /* device pointers inside */
+	long long f_trees;       /* trees the buffers below are sized for */
+	double *f_in_mod, *f_dux, *f_dpi, *f_L, *f_ws, *f_state; long long f_ws_stride;
+	int *f_nact, *h_nact;    /* device / pinned host: trees still iterating */
 	};
 
 int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
@@ -215,6 +220,34 @@ int hpmpc_b200_tree_create_box(hpmpc_b200_tree **out, int Nn, const struct node 
 		CK(cudaMemcpy(d_cux, t->c_ux, (t->nbtot+1)*sizeof(int), cudaMemcpyHostToDevice));
 		t->ipm_dims.idxb = d_idxb; t->ipm_dims.c_ux = d_cux; t->ipm_dims.tn = d_tn;
 		}
+		if(t->nbtot>0)
+			{
+			/* where the right-hand sides and the bounded diagonal entries sit in a packed block */
+			int n_ux = (int)o_ux, n_pi = (int)o_pi, i;
+			int *g_ux = calloc(n_ux+1, sizeof(int)), *b_pi = calloc(n_pi+1, sizeof(int));
+			int *c_diag = calloc(t->nbtot+1, sizeof(int)), *c_grad = calloc(t->nbtot+1, sizeof(int));
+			for(n=0; n<Nn; n++)
+				{
+				const hb_tnode *s = &t->tn[n];
+				int nux = s->nu+s->nx;
+				for(i=0; i<nux; i++) g_ux[s->off_ux+i] = s->off_RSQ + HB_TRI(nux) + i;
+				if(n>0) { int nuxd = t->tn[s->dad].nu + t->tn[s->dad].nx; for(i=0; i<s->nx; i++) b_pi[s->off_pi+i] = s->off_BAbt + nuxd*s->nx + i; }
+				for(j=0; j<s->nb; j++)
+					{
+					int id = t->idxb[s->off_c+j];
+					c_diag[s->off_c+j] = s->off_RSQ + HB_TRI(id) + id; c_grad[s->off_c+j] = s->off_RSQ + HB_TRI(nux) + id;
+					}
+				}
+			int *dv[4]; const int *hv[4] = { g_ux, b_pi, c_diag, c_grad }; const int len[4] = { n_ux+1, n_pi+1, t->nbtot+1, t->nbtot+1 };
+			for(i=0; i<4; i++)
+				{
+				CK(cudaMalloc((void**)&dv[i], len[i]*sizeof(int)));
+				CK(cudaMemcpy(dv[i], hv[i], len[i]*sizeof(int), cudaMemcpyHostToDevice));
+				}
+			t->maps.g_ux = dv[0]; t->maps.b_pi = dv[1]; t->maps.c_diag = dv[2]; t->maps.c_grad = dv[3];
+			t->maps.n_ux = n_ux; t->maps.n_pi = n_pi;
+			free(g_ux); free(b_pi); free(c_diag); free(c_grad);
+			}
 		t->sms = hb_device_sm_count(device);
 		if(t->sms<=0) return -1;
 		}
@@ -230,6 +263,9 @@ void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
 		cudaSetDevice(t->device);
 		cudaFree((void*)t->dims.tn); cudaFree((void*)t->dims.seg_start); cudaFree((void*)t->dims.seg_nodes);
 		cudaFree((void*)t->ipm_dims.idxb); cudaFree((void*)t->ipm_dims.c_ux); cudaFree(t->ipm_ws); cudaFree(t->ipm_counter);
+		cudaFree((void*)t->maps.g_ux); cudaFree((void*)t->maps.b_pi); cudaFree((void*)t->maps.c_diag); cudaFree((void*)t->maps.c_grad);
+		cudaFree(t->f_in_mod); cudaFree(t->f_dux); cudaFree(t->f_dpi); cudaFree(t->f_L); cudaFree(t->f_ws); cudaFree(t->f_state);
+		cudaFree(t->f_nact); if(t->h_nact) cudaFreeHost(t->h_nact);
 		}
 	free(t->idxb); free(t->c_ux);
 	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->slot); free(t->tail_root); free(t);
@@ -408,6 +444,44 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_tree
 	return hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 2, 0, t->n_tails, d_in, d_ux, d_pi, d_L, stream);
 	}
 
+/* multi-kernel IPM: per-tree state machine between the solves (hb_tipm_step_kernel), the solves by the size-specialised tree
+ * Riccati on a private copy of the blocks.  Blocking: the host reads the number of trees still iterating after every step. */
+static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d_in, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, void *stream)
+	{
+	cudaStream_t st = (cudaStream_t)stream;
+	int rc, round;
+	if(t->f_trees<n_trees)
+		{
+		CK(cudaStreamSynchronize(st));
+		cudaFree(t->f_in_mod); cudaFree(t->f_dux); cudaFree(t->f_dpi); cudaFree(t->f_L); cudaFree(t->f_ws); cudaFree(t->f_state);
+		t->f_in_mod = t->f_dux = t->f_dpi = t->f_L = t->f_ws = t->f_state = NULL; t->f_trees = 0;
+		t->f_ws_stride = HB_EVEN(hb_tipm_work_doubles(&t->ipm_dims));
+		CK(cudaMalloc((void**)&t->f_in_mod, sizeof(double)*(size_t)n_trees*t->dims.in_stride));
+		CK(cudaMalloc((void**)&t->f_dux, sizeof(double)*(size_t)n_trees*t->dims.ux_stride));
+		CK(cudaMalloc((void**)&t->f_dpi, sizeof(double)*(size_t)n_trees*t->dims.pi_stride));
+		CK(cudaMalloc((void**)&t->f_L, sizeof(double)*(size_t)n_trees*t->dims.L_stride));
+		CK(cudaMalloc((void**)&t->f_ws, sizeof(double)*(size_t)n_trees*t->f_ws_stride));
+		CK(cudaMalloc((void**)&t->f_state, sizeof(double)*(size_t)n_trees*8));
+		if(t->f_nact==NULL) { CK(cudaMalloc((void**)&t->f_nact, sizeof(int))); CK(cudaMallocHost((void**)&t->h_nact, sizeof(int))); }
+		t->f_trees = n_trees;
+		}
+	CK(cudaMemcpyAsync(t->f_in_mod, d_in, sizeof(double)*(size_t)n_trees*t->dims.in_stride, cudaMemcpyDeviceToDevice, st));
+	CK(cudaMemsetAsync(t->f_state, 0, sizeof(double)*(size_t)n_trees*8, st));
+	for(round=0; round<2*k_max+2; round++)
+		{
+		CK(cudaMemsetAsync(t->f_nact, 0, sizeof(int), st));
+		if((rc = hb_launch_tipm_step(&t->ipm_dims, &t->maps, n_trees, d_in, t->f_in_mod, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi,
+				t->f_dux, t->f_dpi, d_lam, d_t, d_info, t->f_ws, t->f_ws_stride, t->f_state, t->f_nact, stream))) return rc;
+		CK(cudaMemcpyAsync(t->h_nact, t->f_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		if(*t->h_nact==0) return 0;
+		if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_batch(t, n_trees, t->f_in_mod, t->f_dux, t->f_dpi, t->f_L, stream))) return rc;
+		}
+	fprintf(stderr, "hpmpc_b200: tree IPM: state machine did not terminate\n");
+	return -5;
+	}
+
 /* box-constrained IPM over a batch of trees: the whole iteration runs in one kernel, one warp per tree taking trees from a
  * queue (hb_ipm_kernel with the tree sweeps of ric_tree_ipm.cuh); per-warp work slots live in the handle */
 int hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, int k_max, double mu0,
@@ -418,6 +492,10 @@ int hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_tre
 	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
 	if(k_max<1) return -2;
 	CK(cudaSetDevice(t->device));
+	/* uniform tails with a size-specialised Riccati: iterate around the fast tree solver (HPMPC_B200_TREE_IPM_FUSED=1 keeps the
+	 * single-kernel path below, which also serves every other tree) */
+	if(t->tail_fast_id>=0 && t->nbtot>0 && getenv("HPMPC_B200_TREE_IPM_FUSED")==NULL)
+		return tree_ipm_multi(t, n_trees, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, stream);
 	int grid, warps;
 	launch_shape(t, n_trees, &grid, &warps);
 	const long long stride = HB_EVEN(hb_ipm_work_doubles(&t->ipm_dims));
