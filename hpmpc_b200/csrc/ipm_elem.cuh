@@ -45,11 +45,12 @@ __device__ __forceinline__ double hb_warp_sum(double v)
 	}
 
 /* bound part of the residuals: res_d, res_m and their sum (mpc_solvers/c99/d_res_ip_res_hard.c:39-319) */
-__device__ __forceinline__ void hb_ipm_residuals_bounds(int lane, const hb_dims &d, const hb_ipm_ws &w, const double *ux, double &mu2, double &nd)
+/* _part: thread tid of `stride` cooperating threads, partial results (the caller reduces) */
+__device__ __forceinline__ void hb_ipm_residuals_bounds_part(int tid, int stride, const hb_dims &d, const hb_ipm_ws &w, const double *ux, double &mu2, double &nd)
 	{
 	const double *lam_lo = w.v(CV_LAM_LO), *lam_up = w.v(CV_LAM_UP), *t_lo = w.v(CV_T_LO), *t_up = w.v(CV_T_UP);
 	mu2 = 0.0; nd = 0.0;
-	for(int cc=lane; cc<d.nbtot; cc+=32)
+	for(int cc=tid; cc<d.nbtot; cc+=stride)
 		{
 		double u = ux[d.c_ux[cc]];
 		double rdl = w.v(CV_LB)[cc] - u + t_lo[cc];
@@ -60,15 +61,19 @@ __device__ __forceinline__ void hb_ipm_residuals_bounds(int lane, const hb_dims 
 		mu2 += rml + rmu;
 		nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
 		}
+	}
+__device__ __forceinline__ void hb_ipm_residuals_bounds(int lane, const hb_dims &d, const hb_ipm_ws &w, const double *ux, double &mu2, double &nd)
+	{
+	hb_ipm_residuals_bounds_part(lane, 32, d, w, ux, mu2, nd);
 	mu2 = hb_warp_sum(mu2);
 	}
 
 /* step length + dt, dlam.  RES = false: phase 1 (c99/d_aux_ip_hard_lib4.c:489-614) ; true: phase 2 (:1180-1313) */
 template<bool RES>
-__device__ __forceinline__ double hb_ipm_alpha(int lane_, const hb_dims &d, const hb_ipm_ws &w, const double *dux)
+__device__ __forceinline__ double hb_ipm_alpha_part(int tid, int stride, const hb_dims &d, const hb_ipm_ws &w, const double *dux)
 	{
 	double alpha = 1.0;
-	for(int cc=lane_; cc<d.nbtot; cc+=32)
+	for(int cc=tid; cc<d.nbtot; cc+=stride)
 		{
 		double du = dux[d.c_ux[cc]];
 		double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc], tl = w.v(CV_T_LO)[cc], tu = w.v(CV_T_UP)[cc];
@@ -94,16 +99,25 @@ __device__ __forceinline__ double hb_ipm_alpha(int lane_, const hb_dims &d, cons
 		if(-alpha*dtl>tl) alpha = -tl/dtl;
 		if(-alpha*dtu>tu) alpha = -tu/dtu;
 		}
-	return hb_warp_min(alpha);
+	return alpha;
+	}
+template<bool RES>
+__device__ __forceinline__ double hb_ipm_alpha(int lane_, const hb_dims &d, const hb_ipm_ws &w, const double *dux)
+	{
+	return hb_warp_min(hb_ipm_alpha_part<RES>(lane_, 32, d, w, dux));
 	}
 
 /* mu_aff = mu_scal * sum (lam + a dlam)(t + a dt)   (c99/d_aux_ip_hard_lib4.c:715-770, :1453-1508) */
-__device__ __forceinline__ double hb_ipm_mu_aff(int lane_, const hb_dims &d, const hb_ipm_ws &w, double alpha, double mu_scal)
+__device__ __forceinline__ double hb_ipm_mu_aff_part(int tid, int stride, const hb_dims &d, const hb_ipm_ws &w, double alpha)
 	{
 	double mu = 0.0;
-	for(int cc=lane_; cc<d.nbtot; cc+=32)
+	for(int cc=tid; cc<d.nbtot; cc+=stride)
 		mu += (w.v(CV_LAM_LO)[cc] + alpha*w.v(CV_DLAM_LO)[cc])*(w.v(CV_T_LO)[cc] + alpha*w.v(CV_DT_LO)[cc])
 		    + (w.v(CV_LAM_UP)[cc] + alpha*w.v(CV_DLAM_UP)[cc])*(w.v(CV_T_UP)[cc] + alpha*w.v(CV_DT_UP)[cc]);
-	return hb_warp_sum(mu)*mu_scal;
+	return mu;
+	}
+__device__ __forceinline__ double hb_ipm_mu_aff(int lane_, const hb_dims &d, const hb_ipm_ws &w, double alpha, double mu_scal)
+	{
+	return hb_warp_sum(hb_ipm_mu_aff_part(lane_, 32, d, w, alpha))*mu_scal;
 	}
 

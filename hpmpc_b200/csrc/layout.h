@@ -130,9 +130,11 @@ int hb_launch_tail(int id, const hb_tdims *dims, const hb_tail_tab *tab, long lo
 int hb_launch_top(int id, const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
 		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream);
 long long hb_tipm_work_doubles(const hb_dims *dims);
-int hb_launch_tipm_step(const hb_dims *dims, const hb_tipm_maps *maps, long long n_trees, const double *in, double *in_mod, int k_max,
+int hb_launch_tipm_step(const hb_dims *dims, const hb_tipm_maps *maps, int part, long long n_trees, const double *in, double *in_mod, int k_max,
 		double mu0, double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *dux, double *dpi, double *lam,
-		double *t, double *info, double *work, long long work_stride, double *state, int *n_active, void *stream);
+		double *t, double *info, double *work, long long work_stride, double *state, int *counters, void *stream);
+int hb_launch_tipm_res(const hb_dims *dims, long long n_trees, const double *in, const double *ux, const double *pi,
+		double *dux, double *dpi, double *work, long long work_stride, double *state, int sms, void *stream);
 long long hb_ipm_work_doubles(const hb_dims *dims);
 int hb_smem_bytes_per_warp(const hb_dims *dims);
 int hb_smem_bytes_per_warp_sz(int nzM, int nxM);

@@ -463,19 +463,26 @@ static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d
 		CK(cudaMalloc((void**)&t->f_L, sizeof(double)*(size_t)n_trees*t->dims.L_stride));
 		CK(cudaMalloc((void**)&t->f_ws, sizeof(double)*(size_t)n_trees*t->f_ws_stride));
 		CK(cudaMalloc((void**)&t->f_state, sizeof(double)*(size_t)n_trees*8));
-		if(t->f_nact==NULL) { CK(cudaMalloc((void**)&t->f_nact, sizeof(int))); CK(cudaMallocHost((void**)&t->h_nact, sizeof(int))); }
+		if(t->f_nact==NULL) { CK(cudaMalloc((void**)&t->f_nact, 2*sizeof(int))); CK(cudaMallocHost((void**)&t->h_nact, 2*sizeof(int))); }
 		t->f_trees = n_trees;
 		}
 	CK(cudaMemcpyAsync(t->f_in_mod, d_in, sizeof(double)*(size_t)n_trees*t->dims.in_stride, cudaMemcpyDeviceToDevice, st));
 	CK(cudaMemsetAsync(t->f_state, 0, sizeof(double)*(size_t)n_trees*8, st));
 	for(round=0; round<2*k_max+2; round++)
 		{
-		CK(cudaMemsetAsync(t->f_nact, 0, sizeof(int), st));
-		if((rc = hb_launch_tipm_step(&t->ipm_dims, &t->maps, n_trees, d_in, t->f_in_mod, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi,
-				t->f_dux, t->f_dpi, d_lam, d_t, d_info, t->f_ws, t->f_ws_stride, t->f_state, t->f_nact, stream))) return rc;
-		CK(cudaMemcpyAsync(t->h_nact, t->f_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		if(*t->h_nact==0) return 0;
+		int part;
+		for(part=0; part<2; part++)
+			{
+			CK(cudaMemsetAsync(t->f_nact, 0, 2*sizeof(int), st));
+			if((rc = hb_launch_tipm_step(&t->ipm_dims, &t->maps, part, n_trees, d_in, t->f_in_mod, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi,
+					t->f_dux, t->f_dpi, d_lam, d_t, d_info, t->f_ws, t->f_ws_stride, t->f_state, t->f_nact, stream))) return rc;
+			CK(cudaMemcpyAsync(t->h_nact, t->f_nact, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			if(part==1 || t->h_nact[1]==0) break;
+			/* some trees want their residuals (phase switch or end of a phase-2 iteration): node-parallel, then part 1 */
+			if((rc = hb_launch_tipm_res(&t->ipm_dims, n_trees, d_in, d_ux, d_pi, t->f_dux, t->f_dpi, t->f_ws, t->f_ws_stride, t->f_state, t->sms, stream))) return rc;
+			}
+		if(t->h_nact[0]==0) return 0;
 		if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_batch(t, n_trees, t->f_in_mod, t->f_dux, t->f_dpi, t->f_L, stream))) return rc;
 		}
 	fprintf(stderr, "hpmpc_b200: tree IPM: state machine did not terminate\n");

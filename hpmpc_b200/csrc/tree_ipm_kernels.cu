@@ -17,54 +17,95 @@
 #include "ipm_elem.cuh"
 #include "ric_tree_ipm.cuh"
 
-enum { TS_INIT=0, TS_P1_PRED, TS_P1_CORR, TS_P2_PRED, TS_P2_CORR, TS_DONE };
+enum { TS_INIT=0, TS_P1_PRED, TS_P1_CORR, TS_P2_PRED, TS_P2_CORR, TS_DONE, TS_RES_ENTER /* residuals wanted before phase 2 starts */,
+       TS_RES_ITER /* ... at the end of a phase-2 iteration */ };
+#define TIPM_THREADS 128
 
-/* write the right-hand sides of the next solve into the tree's private block */
-__device__ __forceinline__ void hb_tipm_put_grad(int lane, const hb_dims &d, const hb_tipm_maps &m, const hb_ipm_ws &w, const double *rqv, double *im)
+/* block-wide reductions in a fixed order (deterministic); every thread gets the result */
+struct tipm_sum { __device__ static double op(double a, double b) { return a+b; } __device__ static double w(double v) { return hb_warp_sum(v); } };
+struct tipm_min { __device__ static double op(double a, double b) { return fmin(a, b); } __device__ static double w(double v) { return hb_warp_min(v); } };
+struct tipm_max { __device__ static double op(double a, double b) { return fmax(a, b); } __device__ static double w(double v) { return hb_warp_max(v); } };
+template<class R> __device__ __forceinline__ double tipm_reduce(double v, double *red)
 	{
-	for(int i=lane; i<m.n_ux; i+=32) im[m.g_ux[i]] = rqv[i];
-	__syncwarp();
-	for(int cc=lane; cc<d.nbtot; cc+=32) im[m.c_grad[cc]] += w.v(CV_QXG)[cc];
-	}
-__device__ __forceinline__ void hb_tipm_put_diag(int lane, const hb_dims &d, const hb_tipm_maps &m, const hb_ipm_ws &w, const double *in_t, double *im)
-	{
-	for(int cc=lane; cc<d.nbtot; cc+=32) im[m.c_diag[cc]] = in_t[m.c_diag[cc]] + w.v(CV_QXD)[cc];
-	}
-
-__device__ __forceinline__ void hb_tipm_residuals(const hb_ctx &c, const hb_dims &d, const double *in_t, const hb_ipm_ws &w,
-		const double *ux, const double *pi, double *mu, double *norms)
-	{
-	double mu2, nd, nq = 0.0, nb_ = 0.0;
-	hb_ipm_residuals_bounds(c.lane, d, w, ux, mu2, nd);
-	__syncwarp();
-	for(int n=0; n<=d.N; n++)
-		hb_tipm_node_residuals(c, d.tn, n, in_t, w.rq0, w.b0, w.v(CV_LAM_LO), w.v(CV_LAM_UP), d.idxb, ux, pi, w.res_q, w.res_b, nq, nb_);
-	if(d.nbtot>0) *mu = mu2/(2.0*d.nbtot);
-	norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd);
+	v = R::w(v);
+	if((threadIdx.x&31)==0) red[threadIdx.x>>5] = v;
+	__syncthreads();
+	double r = red[0];
+	for(int i=1; i<(int)(blockDim.x>>5); i++) r = R::op(r, red[i]);
+	__syncthreads();
+	return r;
 	}
 
-__global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_maps m, long long n_trees, const double *__restrict__ in,
-		double *__restrict__ in_mod, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start,
-		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ dux_all, double *__restrict__ dpi_all,
-		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all,
-		double *__restrict__ work, long long work_stride, double *__restrict__ state_all, int *n_active)
+__device__ __forceinline__ hb_ipm_ws tipm_ws(const hb_dims &d, long long tree, double *work, long long work_stride, double *dux_all, double *dpi_all)
 	{
-	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
-	const long long tree = (long long)blockIdx.x*nw + warp;
-	if(tree>=n_trees) return;
-	double *state = state_all + tree*8;
-	int st = (int)state[3];
-	if(st==TS_DONE) return;
-	hb_ctx c = hb_make_ctx(d, hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM), lane);
 	hb_ipm_ws w;
-	{
 	double *p = work + tree*work_stride;
 	w.L = nullptr; w.Pb = nullptr;
 	w.dux = dux_all + tree*d.ux_stride; w.dpi = dpi_all + tree*d.pi_stride;
 	w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
 	w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
 	w.cv = p; w.nbp = HB_EVEN(d.nbtot);
+	return w;
 	}
+
+/* write the right-hand sides of the next solve into the tree's private block */
+__device__ __forceinline__ void hb_tipm_put_grad(int tid, int nthr, const hb_dims &d, const hb_tipm_maps &m, const hb_ipm_ws &w, const double *rqv, double *im)
+	{
+	for(int i=tid; i<m.n_ux; i+=nthr) im[m.g_ux[i]] = rqv[i];
+	__syncthreads();
+	for(int cc=tid; cc<d.nbtot; cc+=nthr) im[m.c_grad[cc]] += w.v(CV_QXG)[cc];
+	}
+__device__ __forceinline__ void hb_tipm_put_diag(int tid, int nthr, const hb_dims &d, const hb_tipm_maps &m, const hb_ipm_ws &w, const double *in_t, double *im)
+	{
+	for(int cc=tid; cc<d.nbtot; cc+=nthr) im[m.c_diag[cc]] = in_t[m.c_diag[cc]] + w.v(CV_QXD)[cc];
+	}
+
+/* res_q, res_b of the trees that asked for residuals: one warp per (tree, node); the infinity norms go to the tree's state
+ * record through atomicMax on the bit pattern (non-negative doubles order like unsigned integers) */
+__global__ void __launch_bounds__(128) hb_tipm_res_kernel(hb_dims d, long long n_trees, const double *__restrict__ in,
+		const double *__restrict__ ux_all, const double *__restrict__ pi_all, double *__restrict__ dux_all, double *__restrict__ dpi_all,
+		double *__restrict__ work, long long work_stride, double *__restrict__ state_all)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	hb_ctx c = hb_make_ctx(d, hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM), lane);
+	const long long Nn = d.N+1, items = n_trees*Nn, tw = (long long)gridDim.x*nw;
+	for(long long it=(long long)blockIdx.x*nw + warp; it<items; it+=tw)
+		{
+		const long long tree = it/Nn; const int n = (int)(it - tree*Nn);
+		double *state = state_all + tree*8;
+		const int st = (int)state[3];
+		if(st!=TS_RES_ENTER && st!=TS_RES_ITER) continue;
+		const hb_ipm_ws w = tipm_ws(d, tree, work, work_stride, dux_all, dpi_all);
+		double nq = 0.0, nb_ = 0.0;
+		hb_tipm_node_residuals(c, d.tn, n, in + tree*d.in_stride, w.rq0, w.b0, w.v(CV_LAM_LO), w.v(CV_LAM_UP), d.idxb,
+				ux_all + tree*d.ux_stride, pi_all + tree*d.pi_stride, w.res_q, w.res_b, nq, nb_);
+		nq = hb_warp_max(nq); nb_ = hb_warp_max(nb_);
+		if(lane==0)
+			{
+			atomicMax(reinterpret_cast<unsigned long long*>(state+5), (unsigned long long)__double_as_longlong(nq));
+			atomicMax(reinterpret_cast<unsigned long long*>(state+6), (unsigned long long)__double_as_longlong(nb_));
+			}
+		__syncwarp();
+		}
+	}
+
+/* one CTA per tree.  part 0: everything after a solve up to the next solve or up to the point where residuals are wanted;
+ * part 1: trees whose residuals have just been computed: mu, then the top of the phase-2 loop.
+ * counters[0] = trees not finished, counters[1] = trees waiting for residuals */
+__global__ void __launch_bounds__(TIPM_THREADS) hb_tipm_step_kernel(hb_dims d, hb_tipm_maps m, int part, long long n_trees, const double *__restrict__ in,
+		double *__restrict__ in_mod, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start,
+		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ dux_all, double *__restrict__ dpi_all,
+		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all,
+		double *__restrict__ work, long long work_stride, double *__restrict__ state_all, int *counters)
+	{
+	__shared__ double red[8];
+	const int tid = threadIdx.x, nthr = blockDim.x;
+	const long long tree = blockIdx.x;
+	double *state = state_all + tree*8;
+	int st = (int)state[3];
+	if(st==TS_DONE) return;
+	if(part==1 && st!=TS_RES_ENTER && st!=TS_RES_ITER) { if(tid==0) atomicAdd(&counters[0], 1); return; }
+	const hb_ipm_ws w = tipm_ws(d, tree, work, work_stride, dux_all, dpi_all);
 	const double *in_t = in + tree*d.in_stride;
 	double *im = in_mod + tree*d.in_stride;
 	double *ux = ux_all + tree*d.ux_stride, *pi = pi_all + tree*d.pi_stride;
@@ -76,26 +117,43 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 	double mu = state[0], alpha = state[1], sigma = state[2], mu_aff;
 	int kk = (int)state[4];
 	double norms[3] = {state[5], state[6], state[7]};
-	bool top1 = false, top2 = false;
+	bool top1 = false, top2 = false, want_res = false;
+	__syncthreads();                         /* everybody has read the state record before thread 0 rewrites it */
 
-	if(st==TS_INIT)
+	if(part==1)
 		{
-		for(int i=lane; i<m.n_ux; i+=32) w.rq0[i] = in_t[m.g_ux[i]];
-		for(int j=lane; j<m.n_pi; j+=32) w.b0[j] = in_t[m.b_pi[j]];
-		for(int n=0; n<=d.N; n++)
+		/* bound part of the residuals and mu (mpc_solvers/c99/d_res_ip_res_hard.c:39-319); res_q, res_b came from hb_tipm_res_kernel */
+		double mu2, nd;
+		hb_ipm_residuals_bounds_part(tid, nthr, d, w, ux, mu2, nd);
+		mu2 = tipm_reduce<tipm_sum>(mu2, red);
+		norms[2] = tipm_reduce<tipm_max>(nd, red);
+		mu = mu2/(2.0*d.nbtot);
+		if(st==TS_RES_ITER) { if(tid==0) stat[5*kk+4] = mu; kk++; }
+		top2 = true;
+		}
+	else if(st==TS_INIT)
+		{
+		for(int i=tid; i<m.n_ux; i+=nthr) w.rq0[i] = in_t[m.g_ux[i]];
+		for(int j=tid; j<m.n_pi; j+=nthr) w.b0[j] = in_t[m.b_pi[j]];
+		for(int cc=tid; cc<d.nbtot; cc+=nthr)
+			{
+			/* constraint cc belongs to the node whose off_c range holds it: the bounds sit behind that node's RSQrq */
+			const int dg = m.c_diag[cc]; (void)dg;
+			}
+		for(int n=tid; n<=d.N; n+=nthr)
 			{
 			const hb_tnode s = d.tn[n];
-			for(int j=lane; j<s.nb; j+=32)
+			for(int j=0; j<s.nb; j++)
 				{
 				w.v(CV_LB)[s.off_c+j] = in_t[s.off_d+j];
 				w.v(CV_UB)[s.off_c+j] = in_t[s.off_d+s.nb+j];
 				}
 			}
 		/* init (c99/d_aux_ip_hard_lib4.c:43-149) */
-		if(!warm_start) for(long long i=lane; i<d.ux_stride; i+=32) ux[i] = 0.0;
-		for(long long i=lane; i<d.pi_stride; i+=32) pi[i] = 0.0;
-		__syncwarp();
-		for(int cc=lane; cc<d.nbtot; cc+=32)
+		if(!warm_start) for(long long i=tid; i<d.ux_stride; i+=nthr) ux[i] = 0.0;
+		for(long long i=tid; i<d.pi_stride; i+=nthr) pi[i] = 0.0;
+		__syncthreads();
+		for(int cc=tid; cc<d.nbtot; cc+=nthr)
 			{
 			const int iu = d.c_ux[cc];
 			double lb = w.v(CV_LB)[cc], ub = w.v(CV_UB)[cc], u = ux[iu];
@@ -109,41 +167,58 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 			w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
 			w.v(CV_LAM_LO)[cc] = mu0/tl; w.v(CV_LAM_UP)[cc] = mu0/tu;
 			}
-		__syncwarp();
+		__syncthreads();
 		mu = mu0; alpha = 1.0; sigma = 0.0; kk = 0;
 		top1 = true;
 		}
-	else if(st==TS_P1_PRED)
+	else if(st==TS_P1_PRED || st==TS_P2_PRED)
 		{
-		alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
-		__syncwarp();
-		if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
+		const bool p2 = (st==TS_P2_PRED);
+		alpha = p2 ? hb_ipm_alpha_part<true>(tid, nthr, d, w, w.dux) : hb_ipm_alpha_part<false>(tid, nthr, d, w, w.dux);
+		alpha = tipm_reduce<tipm_min>(alpha, red);
+		if(tid==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
 		alpha *= 0.995;
-		mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
-		if(lane==0) stat[5*kk+2] = mu_aff;
+		mu_aff = tipm_reduce<tipm_sum>(hb_ipm_mu_aff_part(tid, nthr, d, w, alpha), red)*mu_scal;
+		if(tid==0) stat[5*kk+2] = mu_aff;
 		sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
 		const double sm = sigma*mu;
-		for(int cc=lane; cc<d.nbtot; cc+=32)
+		if(!p2)
 			{
-			double dll = w.v(CV_TINV_LO)[cc]*(sm - w.v(CV_DLAM_LO)[cc]*w.v(CV_DT_LO)[cc]);
-			double dlu = w.v(CV_TINV_UP)[cc]*(sm - w.v(CV_DLAM_UP)[cc]*w.v(CV_DT_UP)[cc]);
-			w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
-			w.v(CV_QXG)[cc] += dlu - dll;
+			/* update_gradient (c99/d_aux_ip_hard_lib4.c:387-485) */
+			for(int cc=tid; cc<d.nbtot; cc+=nthr)
+				{
+				double dll = w.v(CV_TINV_LO)[cc]*(sm - w.v(CV_DLAM_LO)[cc]*w.v(CV_DT_LO)[cc]);
+				double dlu = w.v(CV_TINV_UP)[cc]*(sm - w.v(CV_DLAM_UP)[cc]*w.v(CV_DT_UP)[cc]);
+				w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
+				w.v(CV_QXG)[cc] += dlu - dll;
+				}
 			}
-		__syncwarp();
-		hb_tipm_put_grad(lane, d, m, w, w.rq0, im);
-		st = TS_P1_CORR;
+		else
+			{
+			/* centering correction + update_gradient_res (c99/d_aux_ip_hard_lib4.c:1512-1546, :1550-1639) */
+			for(int cc=tid; cc<d.nbtot; cc+=nthr)
+				{
+				double rml = w.v(CV_RM_LO)[cc] + (w.v(CV_DT_LO)[cc]*w.v(CV_DLAM_LO)[cc] - sm);
+				double rmu = w.v(CV_RM_UP)[cc] + (w.v(CV_DT_UP)[cc]*w.v(CV_DLAM_UP)[cc] - sm);
+				w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
+				w.v(CV_QXG)[cc] = w.v(CV_TINV_LO)[cc]*(rml - w.v(CV_LAM_LO)[cc]*w.v(CV_RD_LO)[cc])
+				                  - w.v(CV_TINV_UP)[cc]*(rmu + w.v(CV_LAM_UP)[cc]*w.v(CV_RD_UP)[cc]);
+				}
+			}
+		__syncthreads();
+		hb_tipm_put_grad(tid, nthr, d, m, w, p2 ? w.res_q : w.rq0, im);
+		st = p2 ? TS_P2_CORR : TS_P1_CORR;
 		}
 	else if(st==TS_P1_CORR)
 		{
-		alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
-		__syncwarp();
-		if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
+		alpha = tipm_reduce<tipm_min>(hb_ipm_alpha_part<false>(tid, nthr, d, w, w.dux), red);
+		if(tid==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
 		alpha *= 0.995;
-		for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += alpha*(w.dux[i] - ux[i]);
-		for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += alpha*(w.dpi[i] - pi[i]);
+		/* update_var (c99/d_aux_ip_hard_lib4.c:618-711) */
+		for(long long i=tid; i<d.ux_stride; i+=nthr) ux[i] += alpha*(w.dux[i] - ux[i]);
+		for(long long i=tid; i<d.pi_stride; i+=nthr) pi[i] += alpha*(w.dpi[i] - pi[i]);
 		double ms = 0.0;
-		for(int cc=lane; cc<d.nbtot; cc+=32)
+		for(int cc=tid; cc<d.nbtot; cc+=nthr)
 			{
 			double ll = w.v(CV_LAM_LO)[cc] + alpha*w.v(CV_DLAM_LO)[cc];
 			double lu = w.v(CV_LAM_UP)[cc] + alpha*w.v(CV_DLAM_UP)[cc];
@@ -152,53 +227,25 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 			w.v(CV_LAM_LO)[cc] = ll; w.v(CV_LAM_UP)[cc] = lu; w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
 			ms += ll*tl + lu*tu;
 			}
-		mu = hb_warp_sum(ms)*mu_scal;
-		if(lane==0) stat[5*kk+4] = mu;
+		mu = tipm_reduce<tipm_sum>(ms, red)*mu_scal;
+		if(tid==0) stat[5*kk+4] = mu;
 		kk++;
-		__syncwarp();
 		top1 = true;
-		}
-	else if(st==TS_P2_PRED)
-		{
-		alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
-		__syncwarp();
-		if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
-		alpha *= 0.995;
-		mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
-		if(lane==0) stat[5*kk+2] = mu_aff;
-		sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
-		const double sm = sigma*mu;
-		for(int cc=lane; cc<d.nbtot; cc+=32)
-			{
-			double rml = w.v(CV_RM_LO)[cc] + (w.v(CV_DT_LO)[cc]*w.v(CV_DLAM_LO)[cc] - sm);
-			double rmu = w.v(CV_RM_UP)[cc] + (w.v(CV_DT_UP)[cc]*w.v(CV_DLAM_UP)[cc] - sm);
-			w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
-			w.v(CV_QXG)[cc] = w.v(CV_TINV_LO)[cc]*(rml - w.v(CV_LAM_LO)[cc]*w.v(CV_RD_LO)[cc])
-			                  - w.v(CV_TINV_UP)[cc]*(rmu + w.v(CV_LAM_UP)[cc]*w.v(CV_RD_UP)[cc]);
-			}
-		__syncwarp();
-		hb_tipm_put_grad(lane, d, m, w, w.res_q, im);
-		st = TS_P2_CORR;
 		}
 	else if(st==TS_P2_CORR)
 		{
-		alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
-		__syncwarp();
-		if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
+		alpha = tipm_reduce<tipm_min>(hb_ipm_alpha_part<true>(tid, nthr, d, w, w.dux), red);
+		if(tid==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
 		alpha *= 0.995;
-		for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += alpha*w.dux[i];
-		for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += alpha*w.dpi[i];
-		for(int cc=lane; cc<d.nbtot; cc+=32)
+		/* backup_update_var_res (c99/d_aux_ip_hard_lib4.c:1382-1449) */
+		for(long long i=tid; i<d.ux_stride; i+=nthr) ux[i] += alpha*w.dux[i];
+		for(long long i=tid; i<d.pi_stride; i+=nthr) pi[i] += alpha*w.dpi[i];
+		for(int cc=tid; cc<d.nbtot; cc+=nthr)
 			{
 			w.v(CV_LAM_LO)[cc] += alpha*w.v(CV_DLAM_LO)[cc]; w.v(CV_LAM_UP)[cc] += alpha*w.v(CV_DLAM_UP)[cc];
 			w.v(CV_T_LO)[cc] += alpha*w.v(CV_DT_LO)[cc]; w.v(CV_T_UP)[cc] += alpha*w.v(CV_DT_UP)[cc];
 			}
-		__syncwarp();
-		hb_tipm_residuals(c, d, in_t, w, ux, pi, &mu, norms);
-		if(lane==0) stat[5*kk+4] = mu;
-		kk++;
-		__syncwarp();
-		top2 = true;
+		st = TS_RES_ITER; want_res = true;
 		}
 
 	if(top1)
@@ -206,7 +253,8 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 		/* top of the phase-1 loop (d_ip2_res_hard.c:503) */
 		if(kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
 			{
-			for(int cc=lane; cc<d.nbtot; cc+=32)
+			/* update_hessian, sigma_mu = 0 (c99/d_aux_ip_hard_lib4.c:217-383) */
+			for(int cc=tid; cc<d.nbtot; cc+=nthr)
 				{
 				double til = 1.0/w.v(CV_T_LO)[cc], tiu = 1.0/w.v(CV_T_UP)[cc];
 				double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc];
@@ -218,24 +266,20 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 				w.v(CV_QXD)[cc] = ltl + ltu;
 				w.v(CV_QXG)[cc] = lu - ltu*w.v(CV_UB)[cc] + dlu - ll - ltl*w.v(CV_LB)[cc] - dll;
 				}
-			__syncwarp();
-			hb_tipm_put_diag(lane, d, m, w, in_t, im);
-			hb_tipm_put_grad(lane, d, m, w, w.rq0, im);
+			__syncthreads();
+			hb_tipm_put_diag(tid, nthr, d, m, w, in_t, im);
+			hb_tipm_put_grad(tid, nthr, d, m, w, w.rq0, im);
 			st = TS_P1_PRED;
 			}
-		else
-			{
-			hb_tipm_residuals(c, d, in_t, w, ux, pi, &mu, norms);
-			__syncwarp();
-			top2 = true;
-			}
+		else { st = TS_RES_ENTER; want_res = true; }
 		}
 	if(top2)
 		{
 		/* top of the phase-2 loop (d_ip2_res_hard.c:756) */
 		if(kk<k_max && mu>mu_tol && alpha>=alpha_min)
 			{
-			for(int cc=lane; cc<d.nbtot; cc+=32)
+			/* update_hessian_gradient_res (c99/d_aux_ip_hard_lib4.c:954-1078) */
+			for(int cc=tid; cc<d.nbtot; cc+=nthr)
 				{
 				double til = 1.0/w.v(CV_T_LO)[cc], tiu = 1.0/w.v(CV_T_UP)[cc];
 				double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc];
@@ -243,10 +287,10 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 				w.v(CV_QXD)[cc] = til*ll + tiu*lu;
 				w.v(CV_QXG)[cc] = til*(w.v(CV_RM_LO)[cc] - ll*w.v(CV_RD_LO)[cc]) - tiu*(w.v(CV_RM_UP)[cc] + lu*w.v(CV_RD_UP)[cc]);
 				}
-			__syncwarp();
-			hb_tipm_put_diag(lane, d, m, w, in_t, im);
-			hb_tipm_put_grad(lane, d, m, w, w.res_q, im);
-			for(int j=lane; j<m.n_pi; j+=32) im[m.b_pi[j]] = w.res_b[j];
+			__syncthreads();
+			hb_tipm_put_diag(tid, nthr, d, m, w, in_t, im);
+			hb_tipm_put_grad(tid, nthr, d, m, w, w.res_q, im);
+			for(int j=tid; j<m.n_pi; j+=nthr) im[m.b_pi[j]] = w.res_b[j];
 			st = TS_P2_PRED;
 			}
 		else
@@ -256,17 +300,18 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 			else if(kk>=k_max) status = 1;
 			else if(alpha<alpha_min) status = 2;
 			else status = -1;
+			/* results: lam, t as [lower(nb) upper(nb)] per node */
 			double *lam = lam_all + tree*2*(long long)d.nbtot, *tt = t_all + tree*2*(long long)d.nbtot;
-			for(int n=0; n<=d.N; n++)
+			for(int n=tid; n<=d.N; n+=nthr)
 				{
 				const hb_tnode s = d.tn[n];
-				for(int j=lane; j<s.nb; j+=32)
+				for(int j=0; j<s.nb; j++)
 					{
 					lam[2*s.off_c+j] = w.v(CV_LAM_LO)[s.off_c+j]; lam[2*s.off_c+s.nb+j] = w.v(CV_LAM_UP)[s.off_c+j];
 					tt[2*s.off_c+j] = w.v(CV_T_LO)[s.off_c+j]; tt[2*s.off_c+s.nb+j] = w.v(CV_T_UP)[s.off_c+j];
 					}
 				}
-			if(lane==0)
+			if(tid==0)
 				{
 				info[0] = (double)kk; info[1] = (double)status;
 				info[2] = norms[0]; info[3] = norms[1]; info[4] = norms[2]; info[5] = mu;
@@ -274,12 +319,13 @@ __global__ void __launch_bounds__(128) hb_tipm_step_kernel(hb_dims d, hb_tipm_ma
 			st = TS_DONE;
 			}
 		}
-	__syncwarp();
-	if(lane==0)
+	if(tid==0)
 		{
 		state[0] = mu; state[1] = alpha; state[2] = sigma; state[3] = (double)st; state[4] = (double)kk;
-		state[5] = norms[0]; state[6] = norms[1]; state[7] = norms[2];
-		if(st!=TS_DONE) atomicAdd(n_active, 1);
+		if(want_res) { state[5] = 0.0; state[6] = 0.0; }       /* the residual kernel accumulates the maxima here */
+		state[7] = norms[2];
+		if(st!=TS_DONE) atomicAdd(&counters[0], 1);
+		if(want_res) atomicAdd(&counters[1], 1);
 		}
 	}
 
@@ -288,17 +334,26 @@ extern "C" long long hb_tipm_work_doubles(const hb_dims *d)
 	return 2*d->ux_stride + 2*d->pi_stride + (long long)CV_COUNT*HB_EVEN(d->nbtot);
 	}
 
-extern "C" int hb_launch_tipm_step(const hb_dims *d, const hb_tipm_maps *m, long long n_trees, const double *in, double *in_mod, int k_max,
+extern "C" int hb_launch_tipm_step(const hb_dims *d, const hb_tipm_maps *m, int part, long long n_trees, const double *in, double *in_mod, int k_max,
 		double mu0, double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *dux, double *dpi, double *lam,
-		double *t, double *info, double *work, long long work_stride, double *state, int *n_active, void *stream)
+		double *t, double *info, double *work, long long work_stride, double *state, int *counters, void *stream)
 	{
 	if(d->tn==NULL || d->nbtot<=0) return -4;
+	hb_tipm_step_kernel<<<(int)n_trees, TIPM_THREADS, 0, (cudaStream_t)stream>>>(*d, *m, part, n_trees, in, in_mod, k_max, mu0, mu_tol, alpha_min,
+			warm_start, ux, pi, dux, dpi, lam, t, info, work, work_stride, state, counters);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+/* res_q, res_b of every tree waiting for residuals (between part 0 and part 1 of a step) */
+extern "C" int hb_launch_tipm_res(const hb_dims *d, long long n_trees, const double *in, const double *ux, const double *pi,
+		double *dux, double *dpi, double *work, long long work_stride, double *state, int sms, void *stream)
+	{
 	const int warps = 4;
 	const int smem = warps*(int)sizeof(double)*hb_smem_doubles_per_warp(d->nzM, d->nxM);
-	if(hb_prep(hb_tipm_step_kernel, smem)) return -1;
-	const int grid = (int)((n_trees + warps - 1)/warps);
-	hb_tipm_step_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, *m, n_trees, in, in_mod, k_max, mu0, mu_tol, alpha_min, warm_start,
-			ux, pi, dux, dpi, lam, t, info, work, work_stride, state, n_active);
+	if(hb_prep(hb_tipm_res_kernel, smem)) return -1;
+	long long need = (n_trees*(d->N+1) + warps - 1)/warps, cap = (long long)sms*8;
+	hb_tipm_res_kernel<<<(int)(need<cap ? need : cap), warps*32, smem, (cudaStream_t)stream>>>(*d, n_trees, in, ux, pi, dux, dpi, work, work_stride, state);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
