@@ -19,7 +19,7 @@
 
 enum { TS_INIT=0, TS_P1_PRED, TS_P1_CORR, TS_P2_PRED, TS_P2_CORR, TS_DONE, TS_RES_ENTER /* residuals wanted before phase 2 starts */,
        TS_RES_ITER /* ... at the end of a phase-2 iteration */ };
-#define TIPM_THREADS 128
+#define TIPM_THREADS 256
 
 /* block-wide reductions in a fixed order (deterministic); every thread gets the result */
 struct tipm_sum { __device__ static double op(double a, double b) { return a+b; } __device__ static double w(double v) { return hb_warp_sum(v); } };
@@ -135,11 +135,6 @@ __global__ void __launch_bounds__(TIPM_THREADS) hb_tipm_step_kernel(hb_dims d, h
 		{
 		for(int i=tid; i<m.n_ux; i+=nthr) w.rq0[i] = in_t[m.g_ux[i]];
 		for(int j=tid; j<m.n_pi; j+=nthr) w.b0[j] = in_t[m.b_pi[j]];
-		for(int cc=tid; cc<d.nbtot; cc+=nthr)
-			{
-			/* constraint cc belongs to the node whose off_c range holds it: the bounds sit behind that node's RSQrq */
-			const int dg = m.c_diag[cc]; (void)dg;
-			}
 		for(int n=tid; n<=d.N; n+=nthr)
 			{
 			const hb_tnode s = d.tn[n];
