@@ -123,3 +123,39 @@ def test_tree_ipm_gpu_unconstrained_tree_is_one_riccati_solve():
         assert max(rel(cat(u), cat(s["u"])), rel(cat(x), cat(s["x"])), rel(cat(p), cat(s["pi"]))) < TOL
     finally:
         tb.close()
+
+
+@pytest.mark.gpu
+def test_tree_ipm_gpu_single_kernel_path_agrees(monkeypatch):
+    """HPMPC_B200_TREE_IPM_FUSED=1 forces the one-kernel path (the one trees without size-specialised tails always take);
+    both paths must give the oracle's iteration counts and agree with each other far below the parity tolerance."""
+    t = G.build("ipm_cfg5_small")
+    tb = T.TreeBatch(t)
+    try:
+        blk = [tb.pack(t)]
+        ux0, pi0, lam0, info0 = _gpu_ipm(tb, blk)
+        monkeypatch.setenv("HPMPC_B200_TREE_IPM_FUSED", "1")
+        ux1, pi1, lam1, info1 = _gpu_ipm(tb, blk)
+        assert list(info0[0, :2]) == list(info1[0, :2]) == [float(v) for v in GOLD["ipm_cfg5_small/kk"]]
+        assert rel(ux0, ux1) < 1e-11 and rel(pi0, pi1) < 1e-11 and rel(lam0, lam1) < 1e-10
+    finally:
+        tb.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
+def test_tree_ipm_gpu_iteration_limit(monkeypatch, fused):
+    """k_max reached -> status 1 (mpc_solvers/d_ip2_res_hard.c:1331-1343), same iterate as the oracle after 3 iterations"""
+    if fused:
+        monkeypatch.setenv("HPMPC_B200_TREE_IPM_FUSED", "1")
+    t = G.build("ipm_2x2")
+    tb = T.TreeBatch(t)
+    try:
+        ux, pi, lam, info = _gpu_ipm(tb, [tb.pack(t)], k_max=3)
+        r = api.tree_ipm(t, k_max=3, mu0=G.MU0, mu_tol=G.MU_TOL)
+        assert (int(info[0, 0]), int(info[0, 1])) == (3, 1) == (r["kk"], r["status"])
+        u, x, p = tb.split(ux[0], pi[0])
+        assert max(rel(cat(u), cat(r["u"])), rel(cat(x), cat(r["x"])), rel(cat(p), cat(r["pi"])), rel(cat(tb.split_lam(lam[0])), cat(r["lam"]))) < TOL
+        assert np.allclose(info[0, 6:6 + 15].reshape(3, 5), r["stat"], rtol=1e-9, atol=1e-12)      # sigma, alpha_aff, mu_aff, alpha, mu
+    finally:
+        tb.close()
