@@ -402,6 +402,10 @@ def run_ours(args):
         def launch():
             assert fn(h.h, n, d_in.data_ptr(), k_max, C.c_double(2.0), C.c_double(1e-8), C.c_double(1e-8), 0, ux.data_ptr(), pi.data_ptr(),
                       lam.data_ptr(), tt.data_ptr(), info.data_ptr(), st) == 0
+        h.L.hpmpc_b200_tree_launch_count.restype = C.c_longlong
+        h.L.hpmpc_b200_tree_launch_count.argtypes = [C.c_void_p]
+        launch(); torch.cuda.synchronize()
+        l0 = h.L.hpmpc_b200_tree_launch_count(h.h); launch(); torch.cuda.synchronize(); per_solve = h.L.hpmpc_b200_tree_launch_count(h.h) - l0
         tot_ms, per = time_steps(launch, steps, warmup, stream, barrier)
         tot_ms = reduce_max_time(tot_ms, dev)
         kk = info[:, 0]
@@ -412,7 +416,7 @@ def run_ours(args):
                "config": {"workload": f"scenario-tree box IPM (d_tree_ip2_res_mpc_hard), {n} trees/GPU, md=4 Nr=3 Nh=20 nx=12 nu=5 (1173 nodes, "
                                       f"{h.nbtot} bounded inputs), tol 1e-8, FP64",
                           "parallelism": f"trees sharded over {world} GPU(s), no collective (one warp per tree, whole IPM in one kernel)"},
-               "mean_iterations": float(kk.mean().item()), "converged": conv, "trees_per_gpu": n, "gpu_launches": steps}
+               "mean_iterations": float(kk.mean().item()), "converged": conv, "trees_per_gpu": n, "gpu_launches": int(per_solve) * steps}
         if rank == 0 and not args.no_cpu:
             from oracle import api
             t1 = time.perf_counter(); r = api.tree_ipm(t0); dt = time.perf_counter() - t1
@@ -479,6 +483,20 @@ def run_ours(args):
             out["extra"] = {"ipm": bench_ipm(max(1, min(args.steps, args.ipm_steps)), 1, e2e=(world == 1))}
         except Exception as e:      # the secondary workload must not hide the headline number
             out["extra"] = {"ipm_error": repr(e)}
+        if world == 1:
+            # BASELINE config 5 (scenario trees): Riccati and box IPM, short runs, single GPU only here (--workload tree / tree_ipm
+            # are the full lines, including the multi-GPU paths)
+            torch.cuda.empty_cache()
+            try:
+                saved = args.n_trees, args.no_cpu
+                args.n_trees, args.no_cpu = args.n_trees or 1024, True
+                tr = bench_tree(3, 2)
+                out["extra"]["tree"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "gpu_launches")} | {"workload": tr["config"]["workload"]}
+                ti = bench_tree_ipm(2, 1)
+                out["extra"]["tree_ipm"] = {k: ti[k] for k in ("metric", "value", "unit", "ms_per_step", "mean_iterations", "converged")} | {"workload": ti["config"]["workload"]}
+                args.n_trees, args.no_cpu = saved
+            except Exception as e:
+                out["extra"]["tree_error"] = repr(e)
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             from oracle import api as oracle

@@ -37,6 +37,7 @@ struct hpmpc_b200_tree
 	long long f_trees;       /* trees the buffers below are sized for */
 	double *f_in_mod, *f_dux, *f_dpi, *f_L, *f_ws, *f_state; long long f_ws_stride;
 	int *f_nact, *h_nact;    /* device / pinned host: trees still iterating */
+	long long n_launches;    /* kernels launched through this handle so far (bench.py reports it) */
 	};
 
 int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
@@ -350,6 +351,8 @@ int hpmpc_b200_tree_pack_bounds(const hpmpc_b200_tree *t, double *const *lb, dou
 	return 0;
 	}
 
+long long hpmpc_b200_tree_launch_count(const hpmpc_b200_tree *t) { return t->n_launches; }
+
 void hpmpc_b200_tree_bound_offsets(const hpmpc_b200_tree *t, int n, int *nb, int *off_c, int *off_d)
 	{
 	if(nb) *nb = t->tn[n].nb;
@@ -403,10 +406,12 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 			if(t->top_fast)
 				{
 				fast_shape(t, n_trees*(b-a), &grid, &warps);
+				t->n_launches++;
 				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, lv==0, grid, warps, stream))) return rc;
 				continue;
 				}
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
+			t->n_launches++;
 			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, grid, warps, stream))) return rc;
 			}
 		for(lv=0; lv<=deep; lv++)
@@ -418,10 +423,12 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 			if(t->top_fast)
 				{
 				fast_shape(t, n_trees*(b-a), &grid, &warps);
+				t->n_launches++;
 				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, lv==0, grid, warps, stream))) return rc;
 				continue;
 				}
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
+			t->n_launches++;
 			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, grid, warps, stream))) return rc;
 			}
 		return 0;
@@ -429,9 +436,11 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 	if(t->tail_fast_id>=0)
 		{
 		fast_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
+		t->n_launches++;
 		return hb_launch_tail(t->tail_fast_id, &t->dims, &t->tab, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, tail_lo, tail_hi, grid, warps, stream);
 		}
 	launch_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
+	t->n_launches++;
 	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, t->n_top+tail_lo, t->n_top+tail_hi, grid, warps, stream);
 	}
 
@@ -474,12 +483,14 @@ static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d
 		for(part=0; part<2; part++)
 			{
 			CK(cudaMemsetAsync(t->f_nact, 0, 2*sizeof(int), st));
+			t->n_launches++;
 			if((rc = hb_launch_tipm_step(&t->ipm_dims, &t->maps, part, n_trees, d_in, t->f_in_mod, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi,
 					t->f_dux, t->f_dpi, d_lam, d_t, d_info, t->f_ws, t->f_ws_stride, t->f_state, t->f_nact, stream))) return rc;
 			CK(cudaMemcpyAsync(t->h_nact, t->f_nact, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
 			if(part==1 || t->h_nact[1]==0) break;
 			/* some trees want their residuals (phase switch or end of a phase-2 iteration): node-parallel, then part 1 */
+			t->n_launches++;
 			if((rc = hb_launch_tipm_res(&t->ipm_dims, n_trees, d_in, d_ux, d_pi, t->f_dux, t->f_dpi, t->f_ws, t->f_ws_stride, t->f_state, t->sms, stream))) return rc;
 			}
 		if(t->h_nact[0]==0) return 0;
@@ -514,6 +525,7 @@ int hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_tre
 		CK(cudaMalloc((void**)&t->ipm_ws, sizeof(double)*(size_t)stride*t->ipm_slots));
 		if(t->ipm_counter==NULL) CK(cudaMalloc((void**)&t->ipm_counter, sizeof(int)));
 		}
+	t->n_launches++;
 	return hb_launch_ipm(&t->ipm_dims, n_trees, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
 			t->ipm_ws, stride, t->ipm_slots, grid, warps, t->ipm_counter, HB_IPM_TREE, stream);
 	}

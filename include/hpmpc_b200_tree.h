@@ -79,6 +79,9 @@ int  hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_tr
                                               double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi,
                                               double *d_lam, double *d_t, double *d_info, void *stream);
 
+/* kernels launched through this handle so far (measurement: bench.py's gpu_launches) */
+long long hpmpc_b200_tree_launch_count(const hpmpc_b200_tree *t);
+
 /* whole solve on one GPU (phases 0, 1, 2 back to back) */
 int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in,
                                             double *d_ux, double *d_pi, double *d_L, void *stream);
