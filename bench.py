@@ -133,6 +133,38 @@ def run_reference(args):
     from hpmpc_b200.batchgen import BatchSpec
     from oracle import api as oracle
     cores = os.cpu_count()
+    if args.workload in ("tree", "tree_ipm"):
+        # the reference's tree path needs BLASFEO (absent from /root/reference and from this image): the CPU arm is the oracle's
+        # plain-C port, one tree per thread on all host cores (ctypes releases the GIL during the call)
+        from concurrent.futures import ThreadPoolExecutor
+        from hpmpc_b200 import tree as T
+        from hpmpc_b200.problems import instance_xi
+        ipm = args.workload == "tree_ipm"
+        n_sample = args.ref_sample or 2 * cores
+        xis = instance_xi(n_sample)
+        trees = [T.mass_spring_tree(12, 5, 4, 3, 20, xi=tuple(xis[i]), bounds=ipm) for i in range(n_sample)]
+        fn = oracle.tree_ipm if ipm else oracle.tree_ric
+        oracle.lib()
+
+        def run_once():
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(fn, trees))
+            return time.perf_counter() - t0
+        for _ in range(max(min(args.warmup, 1), 1)):
+            run_once()
+        steps = min(args.steps, 3)
+        tot = sum(run_once() for _ in range(steps))
+        value = n_sample * steps / tot
+        sample = f"{n_sample} distinct trees per step, oracle/ric_oracle.c port ({'orc_tree_ip2_res_mpc_hard' if ipm else 'orc_tree_ric_sv'}), {cores} threads"
+        print(json.dumps({"metric": "tree_box_ipm_solves_per_s" if ipm else "tree_riccati_solves_per_s", "value": value, "unit": "trees/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * tot / steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                          "config": {"workload": "scenario tree md=4 Nr=3 Nh=20 nx=12 nu=5 (1173 nodes)" + (", box IPM, tol 1e-8" if ipm else ", Riccati factor+solve"),
+                                     "note": "CPU port (the reference's tree files need BLASFEO), bounded sample"},
+                          "cpu_baseline": {"value": value, "unit": "trees/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": value, "unit": "trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     cfg = "cfg2" if args.workload == "ric" else "cfg3"
     spec = BatchSpec(cfg, device=-1)
     kind = "avx2" if os.path.exists(oracle.REF_AVX2) else "c99"
@@ -417,6 +449,16 @@ def run_ours(args):
                                       f"{h.nbtot} bounded inputs), tol 1e-8, FP64",
                           "parallelism": f"trees sharded over {world} GPU(s), no collective (one warp per tree, whole IPM in one kernel)"},
                "mean_iterations": float(kk.mean().item()), "converged": conv, "trees_per_gpu": n, "gpu_launches": int(per_solve) * steps}
+        # per-iteration byte model of SURVEY.md section 8d applied edge-wise: factor pass reads the data and writes L, the corrector solve
+        # re-reads L and [B A b]', vectors four times:  B_it = 8 (2 D_BAbt + D_RSQ + 2 D_L + 4 D_vec)
+        D_B = sum((t0.nu[t0.topo["dad"][k]] + t0.nx[t0.topo["dad"][k]] + 1) * t0.nx[k] for k in range(1, h.sz.Nn))
+        D_Q = sum((t0.nu[k] + t0.nx[k]) * (t0.nu[k] + t0.nx[k] + 1) // 2 + t0.nu[k] + t0.nx[k] for k in range(h.sz.Nn))
+        D_v = sum(t0.nu) + 2 * sum(t0.nx) + 6 * h.nbtot
+        B_it = 8.0 * (2 * D_B + D_Q + 2 * D_Q + 4 * D_v)
+        ach = B_it * out["mean_iterations"] * n / (float(np.mean(per)) * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                           "kernel": "whole solve (hb_tipm_step_kernel + hbk_tail_kernel + hbk_top_kernel + hb_tipm_res_kernel)",
+                           "bytes_per_iteration_model": B_it}
         if rank == 0 and not args.no_cpu:
             from oracle import api
             t1 = time.perf_counter(); r = api.tree_ipm(t0); dt = time.perf_counter() - t1

@@ -54,6 +54,7 @@ typedef struct {
 	/* scenario tree (NULL for a chain): stages are the nodes in BFS order, dad[0] = -1, and "edge n" (BAbt[n], b, pi[n],
 	 * Pb[n], n = 0..N-1) is the edge INTO node n+1, whose rows are those of dad[n+1] instead of stage n */
 	int *dad;
+	int *fk, *nk;           /* first kid and number of kids of every stage/node (kids are contiguous in BFS order; chain: n+1, 1) */
 } orc_prob;
 
 static int nux_(const orc_prob *P, int n) { return P->nu[n] + P->nx[n]; }
@@ -71,6 +72,15 @@ orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *n
 	int n, j;
 	P->N = N;
 	if(dad) { P->dad = malloc((N+1)*sizeof(int)); for(n=0; n<=N; n++) P->dad[n] = dad[n]; }
+	P->fk = malloc((N+1)*sizeof(int)); P->nk = calloc(N+1, sizeof(int));
+	for(n=0; n<=N; n++) P->fk[n] = N+1;
+	for(n=1; n<=N; n++)
+		{
+		int dd = dad ? dad[n] : n-1;
+		if(P->nk[dd]==0) P->fk[dd] = n;
+		if(n!=P->fk[dd]+P->nk[dd]) { fprintf(stderr, "oracle: kids of node %d are not contiguous\n", dd); abort(); }
+		P->nk[dd]++;
+		}
 	P->nx = malloc((N+1)*sizeof(int)); P->nu = malloc((N+1)*sizeof(int)); P->nb = malloc((N+1)*sizeof(int));
 	for(n=0; n<=N; n++) { P->nx[n] = nx[n]; P->nu[n] = (n<N || dad) ? nu[n] : 0; P->nb[n] = nb ? nb[n] : 0; }
 	P->idxb = calloc(N+1, sizeof(int*));
@@ -104,7 +114,7 @@ void orc_prob_free(orc_prob *P)
 	for(n=0; n<=P->N; n++)
 		{ free(P->idxb[n]); free(P->BAbt[n]); free(P->RSQrq[n]); free(P->L[n]); free(P->dinv[n]); free(P->d[n]); }
 	free(P->idxb); free(P->BAbt); free(P->RSQrq); free(P->L); free(P->dinv); free(P->d);
-	free(P->nx); free(P->nu); free(P->nb); free(P->W); free(P->tmp); free(P->dad); free(P);
+	free(P->nx); free(P->nu); free(P->nb); free(P->W); free(P->tmp); free(P->dad); free(P->fk); free(P->nk); free(P);
 	}
 
 /* fill from the stage-wise column-major ("fortran order") arrays of the high-level API:
@@ -191,9 +201,8 @@ void orc_ric_backward(orc_prob *P, int with_grad, double *const *bvec, double *c
 				}
 		/* every kid c of this node (a chain has the one kid n+1; lqcp_solvers/d_tree_back_ric_rec_libstr.c:79-156 sums
 		 * W_c W_c' over the kids); e = c-1 is the edge into the kid */
-		for(int c=n+1; c<=N; c++)
+		for(int c=P->fk[n]; c<P->fk[n]+P->nk[n]; c++)
 			{
-			if(dad_(P, c)!=n) { if(P->dad) continue; else break; }
 			const int e = c-1;
 			int nx1 = P->nx[c], nu1 = P->nu[c], nz1 = nx1+nu1+1;
 			double *Ln = P->L[c], *M = P->BAbt[e], *W = P->W;
@@ -228,7 +237,6 @@ void orc_ric_backward(orc_prob *P, int with_grad, double *const *bvec, double *c
 					for(k=0; k<nx1; k++) s += W[i+nz*k]*W[j+nz*k];
 					L[i+nz*j] += s;
 					}
-			if(!P->dad) break;
 			}
 		chol_mn(m, nux, L, nz, P->dinv[n]);
 		}
@@ -358,9 +366,8 @@ void orc_ric_trs(orc_prob *P, double *const *bvec, double *const *rqvec, double 
 		for(i=0; i<nux; i++) w[n][i] = rqvec[n][i];
 		if(P->nb[n]>0 && qx) for(j=0; j<P->nb[n]; j++) w[n][P->idxb[n][j]] += qx[n][j];
 		int has_kid = 0;
-		for(int c=n+1; c<=N; c++)
+		for(int c=P->fk[n]; c<P->fk[n]+P->nk[n]; c++)
 			{
-			if(dad_(P, c)!=n) { if(P->dad) continue; else break; }
 			const int e = c-1;
 			has_kid = 1;
 			int nx1 = P->nx[c], nu1 = P->nu[c];
@@ -391,7 +398,6 @@ void orc_ric_trs(orc_prob *P, double *const *bvec, double *const *rqvec, double 
 				for(j=0; j<nx1; j++) s += M[i+nz*j]*tmp[j];
 				w[n][i] = s;
 				}
-			if(!P->dad) break;
 			}
 		if(has_kid)
 			{
@@ -462,9 +468,8 @@ static void ipm_residuals(const orc_prob *P, const orc_ipm_ws *w, double *mu)
 			rq[i] += s;
 			}
 		/* every edge out of this node (chain: the one into n+1; tree: mpc_solvers/d_tree_res_ip_res_hard_libstr.c:66) */
-		for(int c=n+1; c<=N; c++)
+		for(int c=P->fk[n]; c<P->fk[n]+P->nk[n]; c++)
 			{
-			if(dad_(P, c)!=n) { if(P->dad) continue; else break; }
 			const int e = c-1;
 			int nx1 = P->nx[c], nu1 = P->nu[c];
 			const double *M = P->BAbt[e];
@@ -480,7 +485,6 @@ static void ipm_residuals(const orc_prob *P, const orc_ipm_ws *w, double *mu)
 				for(j=0; j<nx1; j++) s += M[i+nz*j]*w->pi[e][j];
 				rq[i] += s;
 				}
-			if(!P->dad) break;
 			}
 		}
 	if(nb_tot!=0) *mu = mu2/(2.0*nb_tot);
