@@ -135,6 +135,8 @@ int hb_launch_tipm_step(const hb_dims *dims, const hb_tipm_maps *maps, int part,
 		double *t, double *info, double *work, long long work_stride, double *state, int *counters, void *stream);
 int hb_launch_tipm_res(const hb_dims *dims, long long n_trees, const double *in, const double *ux, const double *pi,
 		double *dux, double *dpi, double *work, long long work_stride, double *state, int sms, void *stream);
+int hb_launch_tree_trf_trs(const hb_dims *dims, long long n_trees, const double *in, double *L, double *ux, double *pi,
+		double *work, int n_slots, int mode /* 0 factor, 1 solve with stored factors */, int grid, int warps, void *stream);
 long long hb_ipm_work_doubles(const hb_dims *dims);
 int hb_smem_bytes_per_warp(const hb_dims *dims);
 int hb_smem_bytes_per_warp_sz(int nzM, int nxM);

@@ -38,6 +38,7 @@ struct hpmpc_b200_tree
 	double *f_in_mod, *f_dux, *f_dpi, *f_L, *f_ws, *f_state; long long f_ws_stride;
 	int *f_nact, *h_nact;    /* device / pinned host: trees still iterating */
 	long long n_launches;    /* kernels launched through this handle so far (bench.py reports it) */
+	double *trs_ws; int trs_slots;          /* right-hand sides and Pb of the solve-only path, per warp slot */
 	};
 
 int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
@@ -266,7 +267,7 @@ void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
 		cudaFree((void*)t->ipm_dims.idxb); cudaFree((void*)t->ipm_dims.c_ux); cudaFree(t->ipm_ws); cudaFree(t->ipm_counter);
 		cudaFree((void*)t->maps.g_ux); cudaFree((void*)t->maps.b_pi); cudaFree((void*)t->maps.c_diag); cudaFree((void*)t->maps.c_grad);
 		cudaFree(t->f_in_mod); cudaFree(t->f_dux); cudaFree(t->f_dpi); cudaFree(t->f_L); cudaFree(t->f_ws); cudaFree(t->f_state);
-		cudaFree(t->f_nact); if(t->h_nact) cudaFreeHost(t->h_nact);
+		cudaFree(t->f_nact); if(t->h_nact) cudaFreeHost(t->h_nact); cudaFree(t->trs_ws);
 		}
 	free(t->idxb); free(t->c_ux);
 	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->slot); free(t->tail_root); free(t);
@@ -528,4 +529,36 @@ int hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_tre
 	t->n_launches++;
 	return hb_launch_ipm(&t->ipm_dims, n_trees, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
 			t->ipm_ws, stride, t->ipm_slots, grid, warps, t->ipm_counter, HB_IPM_TREE, stream);
+	}
+
+/* factor only: d_L receives the node factors (generic packed blocks at hpmpc_b200_tree_node_offsets' off_L) */
+int hpmpc_b200_d_tree_back_ric_rec_trf_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, double *d_L, void *stream)
+	{
+	if(n_trees<=0) return 0;
+	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(t->device));
+	int grid, warps;
+	launch_shape(t, n_trees, &grid, &warps);
+	t->n_launches++;
+	return hb_launch_tree_trf_trs(&t->ipm_dims, n_trees, d_in, d_L, NULL, NULL, NULL, grid*warps, 0, grid, warps, stream);
+	}
+
+/* solve with the factors of a previous _trf_batch for the b and [r q] held in d_in (new right-hand sides, same matrices) */
+int hpmpc_b200_d_tree_back_ric_rec_trs_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, const double *d_L,
+		double *d_ux, double *d_pi, void *stream)
+	{
+	if(n_trees<=0) return 0;
+	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(t->device));
+	int grid, warps;
+	launch_shape(t, n_trees, &grid, &warps);
+	if(t->trs_ws==NULL || t->trs_slots<grid*warps)
+		{
+		CK(cudaStreamSynchronize((cudaStream_t)stream));
+		cudaFree(t->trs_ws); t->trs_ws = NULL;
+		t->trs_slots = grid*warps;
+		CK(cudaMalloc((void**)&t->trs_ws, sizeof(double)*(size_t)t->trs_slots*(t->dims.ux_stride + 2*t->dims.pi_stride)));
+		}
+	t->n_launches++;
+	return hb_launch_tree_trf_trs(&t->ipm_dims, n_trees, d_in, (double*)d_L, d_ux, d_pi, t->trs_ws, t->trs_slots, 1, grid, warps, stream);
 	}

@@ -352,3 +352,77 @@ extern "C" int hb_launch_tipm_res(const hb_dims *d, long long n_trees, const dou
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* factor only / solve with stored factors over a tree (d_tree_back_ric_rec_trf_libstr, _trs_libstr:   */
+/* lqcp_solvers/d_tree_back_ric_rec_libstr.c:591, 625): one warp per tree, the node routines of        */
+/* ric_tree_ipm.cuh without the IPM hooks.  mode 0: factors -> L_all.  mode 1: right-hand sides b, [r q] */
+/* taken from the block, Pb_k = Lxx_k (Lxx_k' b_k) per edge, backward vector sweep, forward sweep.      */
+/* work: per warp slot  rq (ux layout) | b (pi layout) | Pb (pi layout)                                */
+/* ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(128) hb_tree_trf_trs_kernel(hb_dims d, long long n_trees, const double *__restrict__ in,
+		double *__restrict__ L_all, double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ work, int mode)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	hb_ctx c = hb_make_ctx(d, hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM), lane);
+	double *rq = work + gw*(d.ux_stride + 2*d.pi_stride), *bv = rq + d.ux_stride, *Pb = bv + d.pi_stride;
+	for(long long tree=gw; tree<n_trees; tree+=tw)
+		{
+		const double *in_t = in + tree*d.in_stride;
+		double *Lt = L_all + tree*d.L_stride;
+		if(mode==0)
+			{
+			for(int n=d.N; n>=0; n--)
+				hb_tipm_node_factor(c, d.tn, n, in_t, Lt, nullptr, nullptr, nullptr, nullptr, d.idxb, nullptr, c.bufA, c.bufB);
+			continue;
+			}
+		double *ux = ux_all + tree*d.ux_stride, *pi = pi_all + tree*d.pi_stride;
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_tnode s = d.tn[n];
+			const int nux = s.nu+s.nx, nu = s.nu;
+			for(int i=lane; i<nux; i+=32) rq[s.off_ux+i] = in_t[s.off_RSQ+HB_TRI(nux)+i];
+			if(s.dad>=0)
+				{
+				const hb_tnode dd = d.tn[s.dad];
+				const int nuxd = dd.nu+dd.nx, nx = s.nx;
+				double *t2 = c.sV, *bs = c.sV + 64;
+				hb_copy(c, c.bufA, Lt + s.off_L, HB_TRI(nux) + 2*nux);
+				for(int j=lane; j<nx; j+=32) { const double v = in_t[s.off_BAbt+nuxd*nx+j]; bv[s.off_pi+j] = v; bs[j] = v; }
+				__syncwarp();
+				/* Pb = Lxx (Lxx' b) */
+				for(int i=lane; i<nx; i+=32)
+					{
+					double acc = 0.0;
+					for(int k=i; k<nx; k++) acc += c.bufA[HB_TRI(nu+k)+nu+i]*bs[k];
+					t2[i] = acc;
+					}
+				__syncwarp();
+				for(int i=lane; i<nx; i+=32)
+					{
+					double acc = 0.0;
+					for(int k=0; k<=i; k++) acc += c.bufA[HB_TRI(nu+i)+nu+k]*t2[k];
+					Pb[s.off_pi+i] = acc;
+					}
+				__syncwarp();
+				}
+			}
+		__syncwarp();
+		for(int n=d.N; n>=0; n--) hb_tipm_node_trs_back(c, d.tn, n, in_t, Lt, rq, nullptr, d.idxb, ux, Pb, c.bufA);
+		for(int n=0; n<=d.N; n++) hb_tipm_node_forward(c, d.tn, n, in_t, Lt, ux, bv, true, ux, pi, c.bufA, c.bufB);
+		__syncwarp();
+		}
+	}
+
+extern "C" int hb_launch_tree_trf_trs(const hb_dims *d, long long n_trees, const double *in, double *L, double *ux, double *pi,
+		double *work, int n_slots, int mode, int grid, int warps, void *stream)
+	{
+	if(d->tn==NULL) return -4;
+	if(grid*warps>n_slots || warps>4) return -3;
+	const int smem = warps*(int)sizeof(double)*hb_smem_doubles_per_warp(d->nzM, d->nxM);
+	if(hb_prep(hb_tree_trf_trs_kernel, smem)) return -1;
+	hb_tree_trf_trs_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_trees, in, L, ux, pi, work, mode);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}

@@ -79,6 +79,13 @@ int  hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_tr
                                               double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi,
                                               double *d_lam, double *d_t, double *d_info, void *stream);
 
+/* factor only / solve with stored factors:  d_tree_back_ric_rec_trf_libstr, d_tree_back_ric_rec_trs_libstr
+ * (lqcp_solvers/d_tree_back_ric_rec_libstr.c:591, 625).  _trf writes the node factors to d_L (L_stride doubles per tree); _trs
+ * solves with them for the b and [r q] held in d_in, so a caller re-solves by re-packing only the right-hand sides. */
+int hpmpc_b200_d_tree_back_ric_rec_trf_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, double *d_L, void *stream);
+int hpmpc_b200_d_tree_back_ric_rec_trs_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, const double *d_L,
+                                             double *d_ux, double *d_pi, void *stream);
+
 /* kernels launched through this handle so far (measurement: bench.py's gpu_launches) */
 long long hpmpc_b200_tree_launch_count(const hpmpc_b200_tree *t);
 

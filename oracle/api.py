@@ -124,6 +124,20 @@ def tree_ric(t):
                 pi=[pi[n][:t.nx[n]].copy() if n > 0 else np.zeros(0) for n in range(Nn)])
 
 
+def tree_ric_trf_trs(t):
+    """orc_tree_ric_trf_trs: factorize the tree, then solve with the stored factors for the b, [r q] of the problem."""
+    L = lib()
+    Nn = t.topo["Nn"]
+    L.orc_tree_ric_trf_trs.restype = None
+    L.orc_tree_ric_trf_trs.argtypes = [C.c_int] + [C.c_void_p] * 7
+    BAbt, RSQ = _tree_dense(t)
+    ux = [np.zeros(max(t.nx[n] + t.nu[n], 1)) for n in range(Nn)]
+    pi = [np.zeros(max(t.nx[n], 1)) for n in range(Nn)]
+    L.orc_tree_ric_trf_trs(Nn, int_array(t.topo["dad"]), int_array(t.nx), int_array(t.nu), ptr_array(BAbt), ptr_array(RSQ), ptr_array(ux), ptr_array(pi))
+    return dict(u=[ux[n][:t.nu[n]].copy() for n in range(Nn)], x=[ux[n][t.nu[n]:t.nu[n] + t.nx[n]].copy() for n in range(Nn)],
+                pi=[pi[n][:t.nx[n]].copy() if n > 0 else np.zeros(0) for n in range(Nn)])
+
+
 def _tree_dense(t):
     """Node-indexed dense matrices of a TreeOcp in the oracle's formats (BAbt[k]: edge into node k)."""
     topo = t.topo

@@ -1007,3 +1007,33 @@ int orc_tree_ip2_res_mpc_hard(int Nn, const int *dad, const int *nx, const int *
 	orc_prob_free(P);
 	return status;
 	}
+
+/* factorize, then solve with the stored factors for the (b, rq) held in the matrices: the tree counterparts of
+ * d_back_ric_rec_trf / _trs (lqcp_solvers/d_tree_back_ric_rec_libstr.c:591,625) through the dad-aware chain routines above.
+ * Same arguments as orc_tree_ric_sv (first_kid / nkids are implied by dad). */
+void orc_tree_ric_trf_trs(int Nn, const int *dad, const int *nx, const int *nu, double *const *BAbt, double *const *RSQrq,
+		double **ux, double **pi)
+	{
+	int n, j, N = Nn-1;
+	orc_prob *P = orc_prob_create_tree(N, nx, nu, NULL, NULL, dad);
+	double **b = malloc((N+1)*sizeof(double*)), **rq = malloc((N+1)*sizeof(double*)), **Pb = malloc((N+1)*sizeof(double*));
+	for(n=0; n<=N; n++)
+		{
+		int nux = nx[n]+nu[n], nz = nux+1;
+		memcpy(P->RSQrq[n], RSQrq[n], sizeof(double)*nz*(nux>0 ? nux : 0));
+		rq[n] = calloc(nux+1, sizeof(double));
+		for(j=0; j<nux; j++) rq[n][j] = RSQrq[n][nux+nz*j];
+		b[n] = calloc(P->nxM+1, sizeof(double)); Pb[n] = calloc(P->nxM+1, sizeof(double));
+		if(n>0)
+			{
+			int nuxd = nux_(P, dad[n]), nzd = nuxd+1;
+			memcpy(P->BAbt[n-1], BAbt[n], sizeof(double)*nzd*nx[n]);
+			for(j=0; j<nx[n]; j++) b[n-1][j] = BAbt[n][nuxd+nzd*j];
+			}
+		}
+	orc_ric_trf(P, NULL);
+	orc_ric_trs(P, b, rq, NULL, ux, 1, pi+1, 1, Pb);
+	for(n=0; n<=N; n++) { free(b[n]); free(rq[n]); free(Pb[n]); }
+	free(b); free(rq); free(Pb);
+	orc_prob_free(P);
+	}

@@ -243,3 +243,48 @@ def test_tree_gpu_subtree_sharding_equals_single_pass():
             a, ln = h.off[node]["pi"], trees[0].nx[node]
             assert torch.equal(st[r]["pi"][:, a:a + ln], pi0[:, a:a + ln]), node
     h.close()
+
+
+def test_tree_oracle_trf_trs_equals_sv():
+    for shape in [(4, 2, 2, 2, 5), (6, 2, 3, 2, 5), (12, 5, 4, 2, 6)]:
+        t = T.mass_spring_tree(*shape, xi=(0.1, -0.3, 0.2, 0.5))
+        a, b = oracle.tree_ric(t), oracle.tree_ric_trf_trs(t)
+        assert max(np.max(np.abs(cat(a[f]) - cat(b[f]))) for f in ("u", "x", "pi")) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 2, 2, 2, 5), (6, 2, 3, 2, 5), (12, 5, 4, 3, 20)])
+def test_tree_gpu_trf_then_trs_with_new_right_hand_sides(shape):
+    """d_tree_back_ric_rec_trf / _trs: factorize once, then solve for the original and for new b, q, r (same matrices)"""
+    import ctypes as C
+    import copy
+    import torch
+    t = T.mass_spring_tree(*shape, xi=(0.2, 0.1, -0.4, 0.3))
+    t2 = copy.deepcopy(t)
+    rng = np.random.default_rng(5)
+    for n in range(t.topo["Nn"]):
+        t2.q[n] = t.q[n] + 0.3 * rng.standard_normal(t.nx[n]); t2.r[n] = t.r[n] - 0.2 * rng.standard_normal(t.nu[n])
+        if n > 0:
+            t2.b[n] = t.b[n] + 0.1 * rng.standard_normal(t.nx[n])
+    tb = T.TreeBatch(t)
+    try:
+        L = tb.L
+        L.hpmpc_b200_d_tree_back_ric_rec_trf_batch.restype = C.c_int
+        L.hpmpc_b200_d_tree_back_ric_rec_trf_batch.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hpmpc_b200_d_tree_back_ric_rec_trs_batch.restype = C.c_int
+        L.hpmpc_b200_d_tree_back_ric_rec_trs_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 5
+        d1 = torch.from_numpy(np.stack([tb.pack(t), tb.pack(t)])).cuda()
+        d2 = torch.from_numpy(np.stack([tb.pack(t2), tb.pack(t)])).cuda()          # tree 0: new right-hand sides, tree 1: unchanged
+        z = lambda m: torch.zeros((2, int(m)), dtype=torch.float64, device="cuda")
+        Lst, ux, pi = z(tb.sz.L_stride), z(tb.sz.ux_stride), z(tb.sz.pi_stride)
+        assert L.hpmpc_b200_d_tree_back_ric_rec_trf_batch(tb.h, 2, d1.data_ptr(), Lst.data_ptr(), None) == 0
+        assert L.hpmpc_b200_d_tree_back_ric_rec_trs_batch(tb.h, 2, d2.data_ptr(), Lst.data_ptr(), ux.data_ptr(), pi.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        for i, prob in enumerate((t2, t)):
+            u, x, p = tb.split(ux[i].cpu().numpy(), pi[i].cpu().numpy())
+            r = oracle.tree_ric(prob)
+            for f, v in (("u", u), ("x", x), ("pi", p)):
+                a, b = cat(v), cat(r[f])
+                assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b))), (i, f)
+    finally:
+        tb.close()
