@@ -43,16 +43,9 @@ template<class C> static void hbf_info(int N, int *ipw, int *smem_warp, long lon
 	{
 	*ipw = C::IPW; *smem_warp = (int)sizeof(double)*C::PER_WARP; *stash_per_inst = (long long)(N+1)*C::LBUF;
 	}
-#ifdef HBK_EXPERIMENTAL_V2
-static int hbk_use_v2() { const char *e = getenv("HPMPC_B200_BLK_V2"); return e!=NULL && e[0]=='1'; }
-#else
-static int hbk_use_v2() { return 0; }
-template<class C> struct hbk2_cfg { static constexpr int PER_WARP = C::PER_WARP; };
-#define hbk2_ric_sv_kernel hbk_ric_sv_kernel
-#endif
 template<class C> static void hbk_info(int N, int *ipw, int *smem_warp, long long *stash_per_inst)
 	{
-	*ipw = C::IPW; *smem_warp = (int)sizeof(double)*(hbk_use_v2() ? hbk2_cfg<C>::PER_WARP : C::PER_WARP); *stash_per_inst = (long long)(N+1)*C::SB;
+	*ipw = C::IPW; *smem_warp = (int)sizeof(double)*C::PER_WARP; *stash_per_inst = (long long)(N+1)*C::SB;
 	}
 
 extern "C" int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst)
@@ -114,17 +107,15 @@ static int hb_stash_window(cudaLaunchAttribute *attr, const void *stash, size_t 
 template<class C> static int hbk_launch(const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, cudaStream_t st)
 	{
-	const int v2 = hbk_use_v2();
-	int smem = warps*(int)sizeof(double)*(v2 ? hbk2_cfg<C>::PER_WARP : C::PER_WARP);
-	if(v2 ? hb_prep(hbk2_ric_sv_kernel<C>, smem) : hb_prep(hbk_ric_sv_kernel<C>, smem)) return -1;
+	int smem = warps*(int)sizeof(double)*C::PER_WARP;
+	if(hb_prep(hbk_ric_sv_kernel<C>, smem)) return -1;
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.gridDim = dim3(grid); cfg.blockDim = dim3(warps*32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
 	cudaLaunchAttribute attr[1];
 	cfg.attrs = attr;
 	cfg.numAttrs = hb_stash_window(&attr[0], stash, sizeof(double)*(size_t)grid*warps*C::IPW*(size_t)(d->N+1)*C::SB);
-	if(v2) { HB_CK(cudaLaunchKernelEx(&cfg, hbk2_ric_sv_kernel<C>, *d, n_inst, in, ux, pi, stash)); }
-	else { HB_CK(cudaLaunchKernelEx(&cfg, hbk_ric_sv_kernel<C>, *d, n_inst, in, ux, pi, stash)); }
+	HB_CK(cudaLaunchKernelEx(&cfg, hbk_ric_sv_kernel<C>, *d, n_inst, in, ux, pi, stash));
 	HB_CK(cudaGetLastError());
 	return 0;
 	}

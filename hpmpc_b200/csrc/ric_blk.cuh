@@ -1025,233 +1025,3 @@ __global__ void __launch_bounds__(256, 1) hbk_top_kernel(hb_tdims d, long long n
 			}
 		}
 	}
-
-#ifdef HBK_EXPERIMENTAL_V2   /* measured: 15.3 M solves/s at 12 warps/SM versus 19.8 M for the kernel above at 8 -- kept as a record */
-/* ================================================================================================ */
-/* v2: 12 resident warps per SM.  Shared memory per instance shrinks from 886 to 538 doubles (nx=12,  */
-/* nu=5): RSQrq_n is fetched separately into the zone [x-columns | u-column scratch] that the factor   */
-/* of stage n overwrites anyway, W replaces [B A b]' in place (LDW = NX), the forward sweep reads       */
-/* [B A b]' straight from global memory (each lane its own columns, coalesced over the lanes of an     */
-/* instance) and double-buffers only the stash image.                                                 */
-/* ================================================================================================ */
-template<class C>
-struct hbk2_cfg
-	{
-	static constexpr int NX = C::NX, NU = C::NU;
-	static constexpr int XC = C::xOff(NX);
-	static constexpr int O_IO = 0, O_X0 = C::BAB, O_LU = O_X0 + XC, O_X1 = O_LU + C::LU, O_VEC = O_X1 + XC;
-	static constexpr int PER_INST = O_VEC + C::VEC;
-	static constexpr int PER_WARP = C::IPW*PER_INST + 8;
-	static_assert(XC + C::LU >= C::RSQ, "RSQrq must fit the zone [x-columns | u-column scratch]");
-	static_assert(C::BAB >= C::SB && XC + C::LU >= C::SB, "a stash image must fit both forward buffers");
-	static_assert(C::BAB >= C::NZ*NX, "W (leading dimension NX) must fit the [B A b]' buffer");
-	};
-
-/* forward stage with [B A b]' columns in registers: bc[s][k] = [B A b]'[k][l+s*G] */
-template<class C, int KIND>
-__device__ __forceinline__ void hbk2_stage_forward(const hbk_lane<C> &ln, const double (&bc)[C::R][C::NZ], const double *__restrict__ Sn,
-		double *__restrict__ us, const double *__restrict__ xs, double *__restrict__ xo, double *__restrict__ tmp,
-		double *__restrict__ g_u, double *__restrict__ g_x1, double *__restrict__ g_pi, bool active)
-	{
-	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, G = C::G, R = C::R;
-	const int l = ln.l;
-	const double *xc = Sn + C::SX;
-	#pragma unroll
-	for(int s=0; s<R; s++)
-		{
-		const int i = l + s*G;
-		if(s*G<NU && i<NU)
-			{
-			double t0 = Sn[C::Sk + i], t1 = 0.0;
-			if(KIND!=HBF_FIRST)
-				{
-				const double *Kr = Sn + C::SK + i*NX;
-				#pragma unroll
-				for(int k=0; k<NX; k+=2)
-					{
-					const double2 kk = *reinterpret_cast<const double2*>(Kr + k);
-					const double2 xx = *reinterpret_cast<const double2*>(xs + k);
-					t0 = fma(kk.x, xx.x, t0); t1 = fma(kk.y, xx.y, t1);
-					}
-				}
-			const double u = t0 + t1;
-			us[i] = u;
-			if(active) g_u[i] = u;
-			}
-		if(KIND!=HBF_FIRST && s*G<NX && i<NX)
-			{
-			const double *col = xc + ln.xo[s] - i;
-			double a0 = col[NX], a1 = 0.0;
-			#pragma unroll
-			for(int k=s*G; k<NX; k+=2)
-				{
-				if(k>=i) a0 = fma(col[k], xs[k], a0);
-				if(k+1>=i && k+1<NX) a1 = fma(col[k+1], xs[k+1], a1);
-				}
-			tmp[i] = a0 + a1;
-			}
-		}
-	__syncwarp();
-	#pragma unroll
-	for(int s=0; s<R; s++)
-		{
-		const int j = l + s*G;
-		if(s*G<NX && j<NX)
-			{
-			constexpr int brow = (KIND==HBF_FIRST) ? NU : NUX;
-			double x0 = bc[s][brow], x1 = 0.0, x2 = 0.0;
-			#pragma unroll
-			for(int i=0; i<NU; i++) x0 = fma(bc[s][i], us[i], x0);
-			if(KIND!=HBF_FIRST)
-				{
-				#pragma unroll
-				for(int i=0; i<NX; i+=2) { x1 = fma(bc[s][NU+i], xs[i], x1); x2 = fma(bc[s][NU+i+1], xs[i+1], x2); }
-				}
-			const double xn = x0 + (x1+x2);
-			xo[j] = xn;
-			if(active) g_x1[j] = xn;
-			if(KIND!=HBF_FIRST)
-				{
-				double p0 = 0.0, p1 = 0.0;
-				#pragma unroll
-				for(int cc=0; cc<NX; cc+=2)
-					{
-					if(cc<(s+1)*G && cc<=j) p0 = fma(xc[C::xOff(cc) + (j-cc)], tmp[cc], p0);
-					if(cc+1<(s+1)*G && cc+1<=j) p1 = fma(xc[C::xOff(cc+1) + (j-cc-1)], tmp[cc+1], p1);
-					}
-				if(active) g_pi[j] = p0+p1;
-				}
-			}
-		}
-	__syncwarp();
-	}
-
-#ifndef HBK2_MINB
-#define HBK2_MINB 3
-#endif
-template<class C>
-__global__ void __launch_bounds__(128, (C::G>=8) ? HBK2_MINB : 1) hbk2_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
-		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ stash)
-	{
-	typedef hbk2_cfg<C> C2;
-	constexpr int G = C::G, R = C::R, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, NZ = C::NZ, SB = C::SB, BAB = C::BAB;
-	extern __shared__ __align__(16) double hbf_smem[];
-	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
-	const int g = lane/G;
-	hbk_lane<C> ln; ln.init(lane%G);
-	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
-	double *wbase = hbf_smem + (size_t)warp*C2::PER_WARP;
-	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);      /* [0] [B A b]' -> io, [1] RSQrq -> zone, [2..3] forward stash images */
-	double *ibase = wbase + 8 + (size_t)g*C2::PER_INST;
-	double *io = ibase + C2::O_IO, *X0 = ibase + C2::O_X0, *LUs = ibase + C2::O_LU, *X1 = ibase + C2::O_X1;
-	double *us = ibase + C2::O_VEC, *xs0 = us + C::even(NU), *xs1 = xs0 + C::XS, *tmp = xs1 + C::XS;
-	if(lane==0)
-		{
-		for(int b=0; b<4; b++) hbf_mbar_init(&bars[b], 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		}
-	__syncwarp();
-	uint32_t phase = 0;
-	const int N = d.N;
-	const int o_in1 = d.st[1].off_BAbt, s_in = d.st[2].off_BAbt - d.st[1].off_BAbt, o_inN = d.st[N].off_BAbt;
-	constexpr int BAB0 = C::even((NU+1)*NX);
-	const long long stash_stride = (long long)(N+1)*SB;
-	const long long n_groups = (n_inst + IPW - 1)/IPW;
-	double *stash_w = stash + gw*IPW*stash_stride;
-
-	for(long long grp=gw; grp<n_groups; grp+=tw)
-		{
-		long long inst = grp*IPW + g;
-		const bool active = inst<n_inst;
-		if(!active) inst = n_inst-1;
-		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
-		const double *inp = in + inst*d.in_stride;               /* this lane's instance (forward sweep reads [B A b]' directly) */
-		const int mg = lane<IPW ? lane : 0;
-		long long my_i = grp*IPW + mg; if(my_i>=n_inst) my_i = n_inst-1;
-		const double *my_in = in + my_i*d.in_stride;
-		double *my_sm = wbase + 8 + (size_t)mg*C2::PER_INST;
-		double *my_st = stash_w + mg*stash_stride;
-		double *gst = stash_w + g*stash_stride;
-		auto off_in = [&](int n) { return (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in); };
-		auto issue_B = [&](int n)                                 /* [B A b]'_n -> io */
-			{
-			const uint32_t bytes = 8u*(uint32_t)((n==0) ? BAB0 : BAB);
-			if(lane==0) hbf_mbar_expect(&bars[0], bytes*IPW);
-			if(lane<IPW) hbf_bulk_g2s(my_sm + C2::O_IO, my_in + off_in(n), bytes, &bars[0]);
-			};
-		auto issue_Q = [&](int n)                                 /* RSQrq_n -> [X(n&1) | LU] (n even) or [LU | X1] (n odd) */
-			{
-			const uint32_t bytes = 8u*(uint32_t)((n==0) ? C::even(HB_TRI(NU)+NU) : (n==N ? C::even(HB_TRI(NX)+NX) : C::RSQ));
-			const int boff = (n==0) ? BAB0 : (n==N ? 0 : BAB);
-			if(lane==0) hbf_mbar_expect(&bars[1], bytes*IPW);
-			if(lane<IPW) hbf_bulk_g2s(my_sm + ((n&1) ? C2::O_LU : C2::O_X0), my_in + off_in(n) + boff, bytes, &bars[1]);
-			};
-		auto issue_S = [&](int n, int slot)                       /* forward: stash image of stage n -> io (slot 0) or [X0 | LU] (slot 1) */
-			{
-			if(lane==0) hbf_mbar_expect(&bars[2+slot], 8u*SB*IPW);
-			if(lane<IPW) hbf_bulk_g2s(my_sm + (slot ? C2::O_X0 : C2::O_IO), my_st + (long long)n*SB, 8u*SB, &bars[2+slot]);
-			};
-		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
-		auto wait_Q = [&]() { wait_bar(1); };
-
-		/* ---------------- backward sweep ---------------- */
-		issue_Q(N);
-		issue_B(N-1);
-		{
-		hbk_tile<C> T;
-		hbk_back_assemble<C, HBF_LAST, NX>(ln, io, (N&1) ? LUs : X0, nullptr, T, wait_Q);
-		hbk_back_factor<C, HBF_LAST>(ln, T, LUs, (N&1) ? X1 : X0, gst + (long long)N*SB, [&]() { issue_Q(N-1); });
-		}
-		for(int n=N-1; n>0; n--)
-			{
-			hbk_tile<C> T;
-			wait_bar(0);
-			hbk_back_assemble<C, HBF_MID, NX>(ln, io, (n&1) ? LUs : X0, (n&1) ? X0 : X1, T, wait_Q);
-			issue_B(n-1);                                         /* lands while the factorization runs */
-			hbk_back_factor<C, HBF_MID>(ln, T, LUs, (n&1) ? X1 : X0, gst + (long long)n*SB, [&]() { issue_Q(n-1); });
-			}
-		{
-		hbk_tile<C> T;
-		wait_bar(0);
-		hbk_back_assemble<C, HBF_FIRST, NX>(ln, io, X0, X1, T, wait_Q);
-		hbk_back_factor<C, HBF_FIRST>(ln, T, LUs, X0, gst, hbk_nop());
-		}
-		/* the images were written through the generic proxy and are read back by bulk copies (async proxy) */
-		asm volatile("fence.proxy.async;" ::: "memory");
-		__syncwarp();
-
-		/* ---------------- forward sweep ---------------- */
-		issue_S(0, 0);
-		issue_S(1, 1);
-		double bc[R][NZ];
-		auto load_B = [&](int n)
-			{
-			const double *gb = inp + off_in(n);
-			#pragma unroll
-			for(int s=0; s<R; s++)
-				{
-				const int j = ln.l + s*G;
-				#pragma unroll
-				for(int k=0; k<NZ; k++) bc[s][k] = (s*G<NX && j<NX && (n>0 || k<=NU)) ? __ldg(gb + k*NX + j) : 0.0;
-				}
-			};
-		load_B(0);
-		wait_bar(2);
-		hbk2_stage_forward<C, HBF_FIRST>(ln, bc, io, us, xs0, xs1, tmp, ux, ux + NU + ((1<N) ? NU : 0), pi, active);
-		if(2<=N) issue_S(2, 0);
-		for(int n=1; n<N; n++)
-			{
-			const double *Sn = (n&1) ? X0 : io;
-			const double *xs = (n&1) ? xs1 : xs0;
-			double *xo = (n&1) ? xs0 : xs1;
-			load_B(n);
-			wait_bar(2+(n&1));
-			const int o_ux = NU + (n-1)*NUX, o_ux1 = NU + n*NUX + ((n+1<N) ? NU : 0);
-			hbk2_stage_forward<C, HBF_MID>(ln, bc, Sn, us, xs, xo, tmp, ux + o_ux, ux + o_ux1, pi + (n-1)*NX, active);
-			if(n+2<=N) issue_S(n+2, n&1);
-			}
-		wait_bar(2+(N&1));
-		hbk_final_pi<C>(ln, (N&1) ? X0 : io, (N&1) ? xs1 : xs0, tmp, pi + (N-1)*NX, active);
-		}
-	}
-#endif
