@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) hb_tipm_res_kernel(hb_dims d, long long n
 /* one CTA per tree.  part 0: everything after a solve up to the next solve or up to the point where residuals are wanted;
  * part 1: trees whose residuals have just been computed: mu, then the top of the phase-2 loop.
  * counters[0] = trees not finished, counters[1] = trees waiting for residuals */
-__global__ void __launch_bounds__(TIPM_THREADS) hb_tipm_step_kernel(hb_dims d, hb_tipm_maps m, int part, long long n_trees, const double *__restrict__ in,
+__global__ void __launch_bounds__(TIPM_THREADS, 4) hb_tipm_step_kernel(hb_dims d, hb_tipm_maps m, int part, long long n_trees, const double *__restrict__ in,
 		double *__restrict__ in_mod, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start,
 		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ dux_all, double *__restrict__ dpi_all,
 		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all,

@@ -29,14 +29,20 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 h2 = rows[1]; ix = {h: i for i, h in enumerate(h2)}
 agg = collections.defaultdict(lambda: [0.0, 0.0, 0])
+need = max(ix["Source"], ix["Instructions Executed"], ix["L1 Wavefronts Shared"])
 for r in rows[2:]:
+    if len(r) <= need or r[ix["Source"]] == "Source":      # a report with several launches repeats the header block per launch
+        continue
     s = r[ix["Source"]].strip()
     if not s:
         continue
     t = s.split()
     op = t[1] if s.startswith("@") and len(t) > 1 else t[0]
     a = agg[op]
-    a[0] += float(r[ix["Instructions Executed"]] or 0); a[1] += float(r[ix["L1 Wavefronts Shared"]] or 0); a[2] += 1
+    try:
+        a[0] += float(r[ix["Instructions Executed"]] or 0); a[1] += float(r[ix["L1 Wavefronts Shared"]] or 0); a[2] += 1
+    except ValueError:
+        pass
 ti = sum(a[0] for a in agg.values()) or 1
 o.append("instruction mix (warp instructions executed; shared-memory wavefronts per instruction):")
 for op, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:16]:
