@@ -58,6 +58,20 @@ static int ensure_scratch(hpmpc_b200_ocp *p, size_t bytes)
 static void default_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps)
 	{
 	int smem_warp = hb_smem_bytes_per_warp(&p->dims);
+	if(warps<=0 && ctas_per_sm<=0)
+		{
+		/* as many resident warps per SM as shared memory allows (<= 16): 4-warp CTAs unless another CTA size fits more warps
+		 * (large stages: e.g. 38.8 KB per warp at BASELINE config 4 -> one 5-warp CTA instead of one 4-warp CTA) */
+		static const int cand[8] = { 4, 5, 6, 7, 8, 3, 2, 1 };
+		int best = 0, k;
+		for(k=0; k<8; k++)
+			{
+			int w = cand[k], c = (227*1024)/(w*smem_warp+1024);
+			if(c>16/w) c = 16/w;
+			if(c>=1 && w*c>best) { best = w*c; warps = w; ctas_per_sm = c; }
+			}
+		if(best==0) { warps = 1; ctas_per_sm = 1; }
+		}
 	if(warps<=0)
 		{
 		warps = 4;
