@@ -185,6 +185,41 @@ def tree_ipm(t, *, k_max=40, mu0=2.0, mu_tol=1e-8, alpha_min=1e-8, warm_start=0)
                 stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
 
+class TreeTimed:
+    """A tree problem packed once into the oracle's formats, so that a timing loop measures only the C solver
+    (bench.py --impl reference --workload tree / tree_ipm; ctypes releases the GIL during the call)."""
+
+    def __init__(self, t, ipm: bool, k_max=40):
+        self.L = lib()
+        topo = t.topo
+        self.Nn = Nn = topo["Nn"]
+        self.ipm, self.k_max = ipm, k_max
+        self.BAbt, self.RSQ = _tree_dense(t)
+        nb = list(t.nb) if (ipm and t.nb) else [0] * Nn
+        self.idxb = [np.ascontiguousarray(t.idxb[n], dtype=np.int32) if nb[n] else np.zeros(1, dtype=np.int32) for n in range(Nn)]
+        self.d = [np.concatenate([t.lb[n], t.ub[n]]).astype(np.float64) if nb[n] else np.zeros(1) for n in range(Nn)]
+        self.ux = [np.zeros(max(t.nx[n] + t.nu[n], 1)) for n in range(Nn)]
+        self.pi = [np.zeros(max(t.nx[n], 1)) for n in range(Nn)]
+        self.lam = [np.zeros(max(2 * nb[n], 1)) for n in range(Nn)]; self.tt = [np.zeros(max(2 * nb[n], 1)) for n in range(Nn)]
+        self.stat = np.zeros(5 * k_max + 5); self.kk = C.c_int(0)
+        pa = ptr_array
+        self.a = dict(dad=int_array(topo["dad"]), fk=int_array(topo["first_kid"]), nk=int_array(topo["nkids"]), nx=int_array(t.nx), nu=int_array(t.nu),
+                      nb=int_array(nb), idxb=pa(self.idxb), B=pa(self.BAbt), Q=pa(self.RSQ), d=pa(self.d), ux=pa(self.ux), pi=pa(self.pi),
+                      lam=pa(self.lam), tt=pa(self.tt))
+        self.L.orc_tree_ric_sv.restype = None
+        self.L.orc_tree_ric_sv.argtypes = [C.c_int] + [C.c_void_p] * 9
+        self.L.orc_tree_ip2_res_mpc_hard.restype = C.c_int
+        self.L.orc_tree_ip2_res_mpc_hard.argtypes = [C.c_int] + [C.c_void_p] * 8 + [C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 5
+
+    def run(self):
+        a = self.a
+        if self.ipm:
+            return self.L.orc_tree_ip2_res_mpc_hard(self.Nn, a["dad"], a["nx"], a["nu"], a["nb"], a["idxb"], a["B"], a["Q"], a["d"], C.byref(self.kk), self.k_max,
+                                                    2.0, 1e-8, 1e-8, 0, self.stat.ctypes.data, a["ux"], a["pi"], a["lam"], a["tt"])
+        self.L.orc_tree_ric_sv(self.Nn, a["dad"], a["fk"], a["nk"], a["nx"], a["nu"], a["B"], a["Q"], a["ux"], a["pi"])
+        return 0
+
+
 # ------------------------------------------------------------------------------------------- CPU timing harness
 def _harness():
     L = lib()
