@@ -85,6 +85,7 @@ static int ctx_get(int N, const int *nx, const int *nu, const int *nb, int *cons
 		const char *e = getenv("HPMPC_B200_DEVICE");
 		if(e) dev = atoi(e); else if(cudaGetDevice(&dev)!=cudaSuccess) { fprintf(stderr, "hpmpc_b200: no CUDA device available\n"); return -1; }
 		if(hpmpc_b200_ocp_create(&G.ocp, N, nx, nu, nb, idxb, dev)) { G.ocp = NULL; return -1; }
+		{ extern void hpmpc_b200_internal_generic_trf(hpmpc_b200_ocp *p); hpmpc_b200_internal_generic_trf(G.ocp); }
 		G.N = N;
 		G.nx = malloc((N+1)*sizeof(int)); G.nu = malloc((N+1)*sizeof(int)); G.nb = malloc((N+1)*sizeof(int)); G.idxb = calloc(N+1, sizeof(int*));
 		for(n=0; n<=N; n++)

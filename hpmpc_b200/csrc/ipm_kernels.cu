@@ -525,6 +525,104 @@ extern "C" int hb_ipm_fast_info(int id, int N, int *smem_warp, long long *L_doub
 	return -1;
 	}
 
+/* ------------------------------------------------------------------------------------------------ */
+/* factor only / solve with stored factors on the size-specialised sweeps (d_back_ric_rec_trf_tv_res,  */
+/* d_back_ric_rec_trs_tv_res: lqcp_solvers/d_back_ric_rec.c:403, 564), one warp per instance.          */
+/* The factor is kept in the sweeps' own column-packed form, (N+1)*LBUF doubles per instance.          */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C>
+__global__ void __launch_bounds__(256) hbi_ric_trf_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+		double *__restrict__ L_all, long long L_stride)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	hbi_ctx<C> c;
+	c.init(hb_smem + (size_t)warp*hbi_cfg<C>::PER_WARP, lane, d);
+	for(long long inst=gw; inst<n_inst; inst+=tw)
+		{
+		hbi_backward<C>(c, d, in + inst*d.in_stride, L_all + inst*L_stride, nullptr, nullptr, nullptr, nullptr, nullptr);
+		__syncwarp();
+		}
+	}
+
+template<class C>
+__global__ void __launch_bounds__(256) hbi_ric_trs_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+		const double *__restrict__ L_all, long long L_stride, double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ work)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	hbi_ctx<C> c;
+	c.init(hb_smem + (size_t)warp*hbi_cfg<C>::PER_WARP, lane, d);
+	double *rq = work + gw*(d.ux_stride + d.pi_stride), *Pb = rq + d.ux_stride;
+	for(long long inst=gw; inst<n_inst; inst+=tw)
+		{
+		const double *in_inst = in + inst*d.in_stride;
+		const double *Lst = L_all + inst*L_stride;
+		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_stage s = d.st[n];
+			const int nux = s.nu+s.nx;
+			for(int i=lane; i<nux; i+=32) rq[s.off_ux+i] = in_inst[s.off_RSQ+HB_TRI(nux)+i];
+			}
+		__syncwarp();
+		hbi_Pb_sweep<C>(c, in_inst, Lst, Pb);
+		__syncwarp();
+		hbi_trs_backward<C>(c, d, in_inst, Lst, rq, nullptr, Pb, ux);
+		__syncwarp();
+		hbi_forward<C, true>(c, in_inst, Lst, nullptr, ux, ux, pi);
+		__syncwarp();
+		}
+	}
+
+/* shape-only test (no bounds needed): which size-specialised sweep set serves this size pattern, -1 for none */
+extern "C" int hb_ric_shape_variant(int N, const int *nx, const int *nu)
+	{
+	if(getenv("HPMPC_B200_NO_FAST_IPM")!=NULL || getenv("HPMPC_B200_NO_FAST_TRF")!=NULL) return -1;
+	for(int id=0; id<HBI_NVAR; id++)
+		{
+		int ok = (nx[0]==0) && N>=3;
+		for(int n=0; n<N && ok; n++) ok = (nu[n]==hbi_shapes[id][1]) && (n==0 || nx[n]==hbi_shapes[id][0]);
+		ok = ok && nx[N]==hbi_shapes[id][0];
+		if(ok) return id;
+		}
+	return -1;
+	}
+
+template<class C> static int hbi_trf_launch(const hb_dims *d, long long n_inst, const double *in, double *L, long long L_stride,
+		int grid, int warps, cudaStream_t st)
+	{
+	const int smem = warps*(int)sizeof(double)*hbi_cfg<C>::PER_WARP;
+	if(hb_prep(hbi_ric_trf_kernel<C>, smem)) return -1;
+	hbi_ric_trf_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_inst, in, L, L_stride);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+template<class C> static int hbi_trs_launch(const hb_dims *d, long long n_inst, const double *in, const double *L, long long L_stride,
+		double *ux, double *pi, double *work, int grid, int warps, cudaStream_t st)
+	{
+	const int smem = warps*(int)sizeof(double)*hbi_cfg<C>::PER_WARP;
+	if(hb_prep(hbi_ric_trs_kernel<C>, smem)) return -1;
+	hbi_ric_trs_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_inst, in, L, L_stride, ux, pi, work);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+/* work (trs only): (ux_stride + pi_stride) doubles per warp of the grid */
+extern "C" int hb_launch_ric_trf_trs_fast(int id, int mode, const hb_dims *d, long long n_inst, const double *in, double *L, long long L_stride,
+		double *ux, double *pi, double *work, int grid, int warps, void *stream)
+	{
+	cudaStream_t st = (cudaStream_t)stream;
+	if(warps>8) return -3;
+	switch(id)
+		{
+		case 0: return mode==0 ? hbi_trf_launch<hbi_v0>(d, n_inst, in, L, L_stride, grid, warps, st) : hbi_trs_launch<hbi_v0>(d, n_inst, in, L, L_stride, ux, pi, work, grid, warps, st);
+		case 1: return mode==0 ? hbi_trf_launch<hbi_v1>(d, n_inst, in, L, L_stride, grid, warps, st) : hbi_trs_launch<hbi_v1>(d, n_inst, in, L, L_stride, ux, pi, work, grid, warps, st);
+		case 2: return mode==0 ? hbi_trf_launch<hbi_v2>(d, n_inst, in, L, L_stride, grid, warps, st) : hbi_trs_launch<hbi_v2>(d, n_inst, in, L, L_stride, ux, pi, work, grid, warps, st);
+		}
+	return -2;
+	}
+
 /* doubles of per-slot work area; L_doubles = size of the factor stash of the variant in use */
 extern "C" long long hb_ipm_work_doubles2(const hb_dims *d, long long L_doubles)
 	{

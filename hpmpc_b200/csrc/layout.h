@@ -115,6 +115,9 @@ int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k
 /* fast_id -2 : dims->tn describes a scenario tree (one warp per tree, generic node sizes) */
 #define HB_IPM_TREE (-2)
 int hb_ipm_fast_variant(int N, const int *nx, const int *nu, int nbtot);
+int hb_ric_shape_variant(int N, const int *nx, const int *nu);      /* same sweep sets for trf / trs, bounds not required */
+int hb_launch_ric_trf_trs_fast(int id, int mode /* 0 factor, 1 solve */, const hb_dims *dims, long long n_inst, const double *in, double *L,
+		long long L_stride, double *ux, double *pi, double *work, int grid, int warps, void *stream);
 int hb_ipm_fast_info(int id, int N, int *smem_warp, long long *L_doubles);
 long long hb_ipm_work_doubles2(const hb_dims *dims, long long L_doubles);
 int hb_fast_variant(int N, const int *nx, const int *nu);

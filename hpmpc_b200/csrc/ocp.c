@@ -34,6 +34,8 @@ struct hpmpc_b200_ocp
 	long long f_stash_inst;
 	/* size-specialised IPM sweeps (ric_ipm_fast.cuh), -1 when none */
 	int ipm_fast_id, i_smem_warp, i_grid, i_warps;
+	int tf_id, tf_smem_warp, tf_grid, tf_warps;   /* size-specialised trf / trs (same sweeps as the fast IPM), -1 when the shape has none */
+	long long tf_L_stride;                        /* their factor: column-packed, (N+1)*LBUF doubles per instance (>= dims.L_stride) */
 	long long i_L_doubles, ipm_ws;
 	/* scratch (device), grown on demand */
 	double *scratch; size_t scratch_bytes;
@@ -120,6 +122,17 @@ static void ipm_launch(hpmpc_b200_ocp *p)
 	p->i_warps = warps; p->i_grid = p->sms*per_sm;
 	}
 
+static void trf_launch(hpmpc_b200_ocp *p)
+	{
+	if(p->tf_id<0) return;
+	int warps = 4;
+	while(warps>1 && warps*p->tf_smem_warp>113*1024) warps--;
+	int per_sm = (228*1024)/(warps*p->tf_smem_warp+1024);
+	if(per_sm<1) per_sm = 1;
+	if(per_sm*warps>8) per_sm = 8/warps>0 ? 8/warps : 1;     /* ~250 registers per thread */
+	p->tf_warps = warps; p->tf_grid = p->sms*per_sm;
+	}
+
 int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, int device)
 	{
 	int n, j;
@@ -179,6 +192,14 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 	p->ipm_fast_id = hb_ipm_fast_variant(N, p->nx, p->nu, nbtot);
 	p->i_L_doubles = p->dims.L_stride;
 	if(p->ipm_fast_id>=0) hb_ipm_fast_info(p->ipm_fast_id, N, &p->i_smem_warp, &p->i_L_doubles);
+	p->tf_id = hb_ric_shape_variant(N, p->nx, p->nu);
+	if(p->tf_id>=0)
+		{
+		/* the factor of trf / trs is kept in the sweeps' column-packed form: the L_stride reported to callers makes room for it */
+		long long Ld = 0;
+		hb_ipm_fast_info(p->tf_id, N, &p->tf_smem_warp, &Ld);
+		p->tf_L_stride = Ld>p->dims.L_stride ? Ld : p->dims.L_stride;
+		}
 	p->ipm_ws = hb_ipm_work_doubles2(&p->dims, p->i_L_doubles);
 	if(device<0)
 		{
@@ -187,6 +208,7 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 		default_launch(p, 0, 0);
 		fast_launch(p, 0, 0);
 		ipm_launch(p);
+		trf_launch(p);
 		*out = p;
 		return 0;
 		}
@@ -205,6 +227,7 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 	default_launch(p, 0, 0);
 	fast_launch(p, 0, 0);
 	ipm_launch(p);
+	trf_launch(p);
 	*out = p;
 	return 0;
 	}
@@ -256,7 +279,7 @@ int hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_
 void hpmpc_b200_ocp_sizes(const hpmpc_b200_ocp *p, hpmpc_b200_sizes *o)
 	{
 	o->in_stride = p->dims.in_stride; o->ux_stride = p->dims.ux_stride; o->pi_stride = p->dims.pi_stride;
-	o->lam_stride = p->lam_stride; o->L_stride = p->dims.L_stride; o->ipm_work_stride = p->ipm_ws;
+	o->lam_stride = p->lam_stride; o->L_stride = p->tf_id>=0 ? p->tf_L_stride : p->dims.L_stride; o->ipm_work_stride = p->ipm_ws;
 	o->N = p->N; o->nzM = p->dims.nzM; o->nxM = p->dims.nxM; o->nbtot = p->dims.nbtot;
 	o->grid = p->grid; o->warps_per_cta = p->warps; o->n_slots = p->n_slots; o->smem_per_cta = p->smem_cta;
 	o->fast_variant = p->fast_id;
@@ -360,6 +383,12 @@ int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, con
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
+	if(p->tf_id>=0)
+		{
+		long long need = (n_inst + p->tf_warps - 1)/p->tf_warps;
+		return hb_launch_ric_trf_trs_fast(p->tf_id, 0, &p->dims, n_inst, d_in, d_L, p->tf_L_stride, NULL, NULL, NULL,
+				(int)(need<p->tf_grid ? need : p->tf_grid), p->tf_warps, stream);
+		}
 	return hb_launch_ric_trf(&p->dims, n_inst, d_in, d_L, grid_for(p, n_inst), p->warps, stream);
 	}
 
@@ -369,6 +398,13 @@ int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, con
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
+	if(p->tf_id>=0)
+		{
+		long long need = (n_inst + p->tf_warps - 1)/p->tf_warps;
+		if(ensure_scratch(p, sizeof(double)*(size_t)p->tf_grid*p->tf_warps*(p->dims.ux_stride+p->dims.pi_stride))) return -1;
+		return hb_launch_ric_trf_trs_fast(p->tf_id, 1, &p->dims, n_inst, d_in, (double*)d_L, p->tf_L_stride, d_ux, d_pi, p->scratch,
+				(int)(need<p->tf_grid ? need : p->tf_grid), p->tf_warps, stream);
+		}
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*(p->dims.ux_stride+2*p->dims.pi_stride))) return -1;
 	return hb_launch_ric_trs(&p->dims, n_inst, d_in, d_L, d_ux, d_pi, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
 	}
@@ -551,6 +587,10 @@ double hpmpc_b200_fp64_peak_tflops(int device)
 	}
 
 const char *hpmpc_b200_version(void) { return "hpmpc_b200 0.1 (sm_100a)"; }
+
+/* used by compat.c only: the legacy symbols pass the factor of sv / trf to trs through the caller's `memory`, whose size and
+ * layout are the generic ones (d_back_ric_rec_sv_tv_memory_space_size_bytes) -- keep trf / trs on the generic kernels there */
+void hpmpc_b200_internal_generic_trf(hpmpc_b200_ocp *p) { p->tf_id = -1; }
 
 /* used by compat.c only: the factor of a batch-of-one sv call sits in scratch slot 0 */
 int hpmpc_b200_internal_copy_stash(hpmpc_b200_ocp *p, double *h_dst)

@@ -358,6 +358,49 @@ __device__ void hbi_trs_backward(hbi_ctx<C> &c, const hb_dims &d, const double *
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Pb_n = Lxx_{n+1} (Lxx_{n+1}' b_n) for every edge, b taken from the instance block: what a solve with stored  */
+/* factors needs first when b is new (d_back_ric_rec_trs_tv_res with compute_Pb = 1, d_back_ric_rec.c:564)       */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C>
+__device__ void hbi_Pb_sweep(hbi_ctx<C> &c, const double *__restrict__ in_inst, const double *__restrict__ Lst, double *Pb)
+	{
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF;
+	const int l = c.lane, N = c.N;
+	auto issue_L = [&](int n) { c.load(2+(n&1), (n&1) ? c.Lb1 : c.Lb0, Lst + (long long)n*LBUF, 8u*LBUF); };
+	issue_L(1); if(N>1) issue_L(2);
+	int coff = 0;
+	#pragma unroll
+	for(int jj=0; jj<NX; jj++) if(jj==l) coff = C::colOff(NU+jj);
+	for(int n=0; n<N; n++)
+		{
+		const int m1 = n+1;
+		const double *Lp = (m1&1) ? c.Lb1 : c.Lb0;
+		const int brow = (n==0) ? NU : NUX;
+		if(l<NX) c.va[l] = in_inst[c.off_in(n) + brow*NX + l];
+		__syncwarp();
+		c.wait(2+(m1&1));
+		if(l<NX)
+			{
+			const double *col = Lp + coff - l;                     /* col[m] = Lxx[m][l] */
+			double a0 = 0.0;
+			#pragma unroll
+			for(int m=0; m<NX; m++) if(m>=l) a0 = fma(col[m], c.va[m], a0);
+			c.tmp[l] = a0;
+			}
+		__syncwarp();
+		if(l<NX)
+			{
+			double p0 = 0.0;
+			#pragma unroll
+			for(int cc=0; cc<NX; cc++) if(cc<=l) p0 = fma(Lp[C::colOff(NU+cc) + (l-cc)], c.tmp[cc], p0);
+			Pb[n*NX+l] = p0;
+			}
+		__syncwarp();
+		if(m1+2<=N) issue_L(m1+2);
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* residuals of the KKT system (res_q, res_b) with the stage data streamed through shared memory.     */
 /*   rq0, b0 : original gradient / b (ux / pi layout) ; lamd = lam_up - lam_lo per bound (nbtot)       */
 /*   returns max |res_q|, max |res_b| over the lanes' entries (caller reduces)                          */
