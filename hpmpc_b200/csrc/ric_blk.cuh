@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long 
 		long long pi_stride, long long L_stride, const double *__restrict__ in, double *__restrict__ ux_all, double *__restrict__ pi_all,
 		double *__restrict__ L_all, int mode, int tail_lo, int tail_hi)
 	{
-	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
+	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
 	extern __shared__ __align__(16) double hbf_smem[];
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const int g = lane/G;
