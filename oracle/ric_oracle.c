@@ -334,7 +334,7 @@ void orc_ric_sv(orc_prob *P, double *const *bvec, double *const *rqvec, double *
 	int n;
 	orc_ric_backward(P, 1, bvec, rqvec, Qx, qx, Pb);
 	/* gradient rows as vectors */
-	double **lrow = malloc((P->N+1)*sizeof(double*));
+	double **lrow = calloc(P->N+1, sizeof(double*));
 	for(n=0; n<=P->N; n++)
 		{
 		int nux = nux_(P,n), nz = nux+1, j;
@@ -356,8 +356,8 @@ void orc_ric_trs(orc_prob *P, double *const *bvec, double *const *rqvec, double 
 		double **ux, int compute_pi, double **pi, int compute_Pb, double **Pb)
 	{
 	int N = P->N, n, i, j, k;
-	double **w = malloc((N+1)*sizeof(double*));
-	double **p = malloc((N+1)*sizeof(double*));
+	double **w = calloc(N+1, sizeof(double*));
+	double **p = calloc(N+1, sizeof(double*));
 	for(n=0; n<=N; n++) { w[n] = calloc(nux_(P,n)+1, sizeof(double)); p[n] = calloc(P->nxM+1, sizeof(double)); }
 	/* backward vector sweep */
 	for(n=N; n>=0; n--)
