@@ -514,7 +514,24 @@ int hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_tre
 	/* uniform tails with a size-specialised Riccati: iterate around the fast tree solver (HPMPC_B200_TREE_IPM_FUSED=1 keeps the
 	 * single-kernel path below, which also serves every other tree) */
 	if(t->tail_fast_id>=0 && t->nbtot>0 && getenv("HPMPC_B200_TREE_IPM_FUSED")==NULL)
-		return tree_ipm_multi(t, n_trees, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, stream);
+		{
+		/* the driver keeps a private copy of the blocks, the factor images and the work vectors of every tree it iterates on
+		 * (about 8 MB per tree at BASELINE config 5): large batches go through in chunks whose buffers stay below ~24 GB */
+		const double per_tree = 8.0*((double)t->dims.in_stride + t->dims.L_stride + t->dims.ux_stride + t->dims.pi_stride
+				+ (double)hb_tipm_work_doubles(&t->ipm_dims) + 8);
+		long long chunk = (long long)(24e9/per_tree), done;
+		{ const char *e = getenv("HPMPC_B200_TREE_IPM_CHUNK"); if(e && atoll(e)>0) chunk = atoll(e); }
+		if(chunk<1) chunk = 1;
+		const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max;
+		for(done=0; done<n_trees; done+=chunk)
+			{
+			long long m = n_trees-done<chunk ? n_trees-done : chunk;
+			int rc = tree_ipm_multi(t, m, d_in + done*t->dims.in_stride, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux + done*t->dims.ux_stride,
+					d_pi + done*t->dims.pi_stride, d_lam + done*2*(long long)t->nbtot, d_t + done*2*(long long)t->nbtot, d_info + done*info_len, stream);
+			if(rc) return rc;
+			}
+		return 0;
+		}
 	int grid, warps;
 	launch_shape(t, n_trees, &grid, &warps);
 	const long long stride = HB_EVEN(hb_ipm_work_doubles(&t->ipm_dims));

@@ -159,3 +159,21 @@ def test_tree_ipm_gpu_iteration_limit(monkeypatch, fused):
         assert np.allclose(info[0, 6:6 + 15].reshape(3, 5), r["stat"], rtol=1e-9, atol=1e-12)      # sigma, alpha_aff, mu_aff, alpha, mu
     finally:
         tb.close()
+
+
+@pytest.mark.gpu
+def test_tree_ipm_gpu_chunked_batch_equals_one_pass(monkeypatch):
+    """large batches go through the multi-kernel driver in chunks (bounded private buffers): same results bit for bit"""
+    from hpmpc_b200 import problems
+    xis = problems.instance_xi(7, first=40)
+    ts = [T.mass_spring_tree(8, 3, 2, 2, 6, xi=tuple(x), bounds=True) for x in xis]
+    tb = T.TreeBatch(ts[0])
+    try:
+        blocks = [tb.pack(t) for t in ts]
+        a = _gpu_ipm(tb, blocks)
+        monkeypatch.setenv("HPMPC_B200_TREE_IPM_CHUNK", "3")
+        b = _gpu_ipm(tb, blocks)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    finally:
+        tb.close()
