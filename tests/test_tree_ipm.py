@@ -173,7 +173,11 @@ def test_tree_ipm_gpu_chunked_batch_equals_one_pass(monkeypatch):
         a = _gpu_ipm(tb, blocks)
         monkeypatch.setenv("HPMPC_B200_TREE_IPM_CHUNK", "3")
         b = _gpu_ipm(tb, blocks)
-        for x, y in zip(a, b):
-            assert np.array_equal(x, y)
+        # strides are padded to an even count: compare what the layout defines (u, x, pi, lam per node) and the info rows
+        for i in range(len(ts)):
+            ua, xa, pa = tb.split(a[0][i], a[1][i]); ub, xb, pb = tb.split(b[0][i], b[1][i])
+            assert np.array_equal(cat(ua), cat(ub)) and np.array_equal(cat(xa), cat(xb)) and np.array_equal(cat(pa), cat(pb))
+            assert np.array_equal(cat(tb.split_lam(a[2][i])), cat(tb.split_lam(b[2][i])))
+        assert np.array_equal(a[3], b[3])
     finally:
         tb.close()
