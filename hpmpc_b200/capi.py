@@ -215,6 +215,52 @@ class HpmpcLib:
                     t=[np.concatenate([t[n][:p.nb[n]], t[n][pnb[n]:pnb[n] + p.nb[n]]]) for n in range(N + 1)],
                     stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
+    def ip2_then_kkt_new_rhs(self, p: Ocp, p2: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, alpha_min=1e-8):
+        """d_ip2_res_mpc_hard_tv on p, then d_kkt_solve_new_rhs_res_mpc_hard_tv (reference mpc_solvers/d_ip2_res_hard.c:1922, called as in
+        test_problems/test_d_ip_hard.c:1040) on the SAME work memory with the vectors b, q, r, lb, ub of p2: the IPM's last KKT system
+        solved again for a new right-hand side.  (The reference's high-level fortran_order_d_solve_kkt_new_rhs_ocp_hard_tv lays its work
+        space out differently from fortran_order_d_ip_ocp_hard_tv -- fortran_order_interface.c:1193 against :459 -- and cannot follow it.)"""
+        N = p.N
+        nx, nu, nb, ng = self._sizes(p)
+        BAbt, RSQ = self._pm_problem(p)
+        pnb = [_rup(v, BS) for v in p.nb]
+        mk = lambda: [aligned_zeros(2 * pnb[n] + 4) for n in range(N + 1)]
+        d, d2, lam, t = mk(), mk(), mk(), mk()
+        for n in range(N + 1):
+            d[n][:p.nb[n]] = p.lb[n]; d[n][pnb[n]:pnb[n] + p.nb[n]] = p.ub[n]
+            d2[n][:p.nb[n]] = p2.lb[n]; d2[n][pnb[n]:pnb[n] + p.nb[n]] = p2.ub[n]
+        ux = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        pi = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        hb = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        hq = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        for n in range(N):
+            hb[n][:p.nx[n + 1]] = p2.b[n]
+        for n in range(N + 1):
+            hq[n][:p.nu[n]] = p2.r[n]; hq[n][p.nu[n]:p.nu[n] + p.nx[n]] = p2.q[n]
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        dummy = [aligned_zeros(8) for _ in range(N + 1)]
+        wsz = self.lib.d_ip2_res_mpc_hard_tv_work_space_size_bytes(N, nx, nu, nb, ng)
+        work = aligned_zeros(wsz // 8 + 16)
+        stat = np.zeros(5 * k_max + 5)
+        kk = C.c_int(0)
+        pa = ptr_array
+        k = dict(BAbt=pa(BAbt), RSQ=pa(RSQ), dm=pa(dummy), d=pa(d), d2=pa(d2), ux=pa(ux), pi=pa(pi), lam=pa(lam), t=pa(t), idxb=pa(idxb),
+                 hb=pa(hb), hq=pa(hq))
+        status = self.lib.d_ip2_res_mpc_hard_tv(C.byref(kk), k_max, mu0, mu_tol, alpha_min, 0, stat.ctypes.data, N,
+                                                nx, nu, nb, k["idxb"], ng, k["BAbt"], k["RSQ"], k["dm"], k["d"], k["ux"], 1,
+                                                k["pi"], k["lam"], k["t"], work.ctypes.data)
+        fn = self.lib.d_kkt_solve_new_rhs_res_mpc_hard_tv
+        fn.restype = None
+        fn.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_int] + [C.c_void_p] * 4
+        fn(N, nx, nu, nb, k["idxb"], ng, k["BAbt"], k["hb"], k["RSQ"], k["hq"], k["dm"], k["d2"], k["ux"], 1, k["pi"], k["lam"], k["t"],
+           work.ctypes.data)
+        return dict(status=status, kk=kk.value, u=[ux[n][:p.nu[n]].copy() for n in range(N)],
+                    x=[ux[n][p.nu[n]:p.nu[n] + p.nx[n]].copy() for n in range(N + 1)],
+                    pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
+                    lam=[np.concatenate([lam[n][:p.nb[n]], lam[n][pnb[n]:pnb[n] + p.nb[n]]]) for n in range(N + 1)],
+                    t=[np.concatenate([t[n][:p.nb[n]], t[n][pnb[n]:pnb[n] + p.nb[n]]]) for n in range(N + 1)])
+
+
 
 # ------------------------------------------------------------------------------------------- batched C ABI
 class Sizes(C.Structure):

@@ -148,6 +148,13 @@ struct hb_sweeps_generic
 		hb_trs_backward(c, d, in_inst, w.L, bv, rqv, qx, w.dux, w.Pb, false);
 		hb_forward(c, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
 		}
+	/* the same with Pb recomputed from bv (d_back_ric_rec_trs_tv_res with compute_Pb = 1): b is new, not the one of the last sv */
+	__device__ static __forceinline__ void trs_newb(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		hb_trs_backward(c, d, in_inst, w.L, bv, rqv, qx, w.dux, w.Pb, true);
+		hb_forward(c, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
+		}
 	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
 			const double *ux, const double *pi, double *mu, double *norms)
 		{ hb_ipm_residuals(c, d, in_inst, w, ux, pi, mu, norms); }
@@ -174,6 +181,13 @@ struct hb_sweeps_fast
 		hbi_trs_backward<C>(c, d, in_inst, w.L, rqv, qx, w.Pb, w.dux);
 		__syncwarp();
 		hbi_forward<C, true>(c, in_inst, w.L, bv, w.dux, w.dux, w.dpi);
+		}
+	__device__ static __forceinline__ void trs_newb(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		hbi_Pb_sweep<C>(c, in_inst, w.L, w.Pb, bv);
+		__syncwarp();
+		trs(c, d, in_inst, w, bv, rqv, qx);
 		}
 	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
 			const double *ux, const double *pi, double *mu, double *norms)
@@ -257,19 +271,25 @@ struct hb_sweeps_tree
 		}
 	};
 
+/* doubles of one work slot of the IPM kernel for the sweeps S: [factor | 3 ux-like | 4 pi-like | constraint vectors] */
+template<class S> __device__ __forceinline__ long long hb_ipm_slot_doubles(const hb_dims &d)
+	{ return S::L_doubles(d) + 3*d.ux_stride + 4*d.pi_stride + (long long)CV_COUNT*HB_EVEN(d.nbtot); }
+
 template<class S>
 __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, int k_max, double mu0,
 		double mu_tol, double alpha_min, int warm_start, double *__restrict__ ux_all, double *__restrict__ pi_all,
 		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all,
-		double *__restrict__ work, long long work_stride, int *counter)
+		double *__restrict__ work, long long work_stride, int *counter, double *__restrict__ kkt, long long kkt_stride)
 	{
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const long long gw = (long long)blockIdx.x*nw + warp;
 	typename S::ctx_t c;
 	S::init(c, d, hb_smem + (size_t)warp*S::smem_doubles(d), lane);
 	hb_ipm_ws w;
+	double *const slot = work + gw*work_stride;
+	const long long slot_doubles = hb_ipm_slot_doubles<S>(d);
 	{
-	double *p = work + gw*work_stride;
+	double *p = slot;
 	w.L = p; p += S::L_doubles(d);
 	w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
 	w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
@@ -296,7 +316,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 		S::extract(c, d, in_inst, w);
 		__syncwarp();
 
-		int kk = 0, status = -1;
+		int kk = 0, status = -1, n_ph2 = 0;
 		double mu = 0.0, norms[3] = {0.0, 0.0, 0.0};
 
 		if(d.nbtot==0)
@@ -455,7 +475,22 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
 				alpha *= 0.995;
-				/* backup_update_var_res (c99/d_aux_ip_hard_lib4.c:1382-1449) */
+				/* backup_update_var_res (c99/d_aux_ip_hard_lib4.c:1382-1449): the backup is what a later solve with a new
+				 * right-hand side starts from (d_ip2_res_hard.c:2138-2173); kept only when the caller asked for the KKT state */
+				if(kkt!=nullptr)
+					{
+					double *kb = kkt + inst*kkt_stride + HB_EVEN(slot_doubles);
+					for(long long i=lane; i<d.ux_stride; i+=32) kb[i] = ux[i];
+					kb += d.ux_stride;
+					for(long long i=lane; i<d.pi_stride; i+=32) kb[i] = pi[i];
+					kb += d.pi_stride;
+					for(int cc=lane; cc<d.nbtot; cc+=32)
+						{
+						kb[cc] = w.v(CV_LAM_LO)[cc]; kb[w.nbp+cc] = w.v(CV_LAM_UP)[cc];
+						kb[2*w.nbp+cc] = w.v(CV_T_LO)[cc]; kb[3*w.nbp+cc] = w.v(CV_T_UP)[cc];
+						}
+					n_ph2++;
+					}
 				for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += alpha*w.dux[i];
 				for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += alpha*w.dpi[i];
 				for(int cc=lane; cc<d.nbtot; cc+=32)
@@ -480,9 +515,99 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 		/* results: lam, t as [lower(nb) upper(nb)] per stage (interfaces/c/fortran_order_interface.c:662-671) */
 		double *lam = lam_all + inst*2*(long long)d.nbtot, *tt = t_all + inst*2*(long long)d.nbtot;
 		S::emit(c, d, w, lam, tt);
+		if(kkt!=nullptr)
+			{
+			/* the slot as it stands (factor of the last iteration, t_inv among the constraint vectors) goes with the backup */
+			__syncwarp();
+			double *ks = kkt + inst*kkt_stride;
+			for(long long i=lane; i<slot_doubles; i+=32) ks[i] = slot[i];
+			if(lane==0) ks[HB_EVEN(slot_doubles) + d.ux_stride + d.pi_stride + 4*w.nbp] = (double)n_ph2;
+			}
 		if(lane==0)
 			{
 			info[0] = (double)kk; info[1] = (double)status;
+			info[2] = norms[0]; info[3] = norms[1]; info[4] = norms[2]; info[5] = mu;
+			}
+		__syncwarp();
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* the IPM's last KKT system solved again for a new right-hand side:             */
+/* d_kkt_solve_new_rhs_res_mpc_hard_tv, mpc_solvers/d_ip2_res_hard.c:1922.  `in` carries the new b, */
+/* [r q] and bounds (its matrices are the ones the factor was made from); `kkt` is the state an IPM */
+/* call left behind.  One warp per instance, working inside the instance's own state block:        */
+/* the factor, t_inv and the backup are read, the other vectors of the block are scratch.           */
+/* ------------------------------------------------------------------------------------------------ */
+template<class S>
+__global__ void __launch_bounds__(256) hb_kkt_new_rhs_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+		double *__restrict__ kkt, long long kkt_stride, double *__restrict__ ux_all, double *__restrict__ pi_all,
+		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all, int *counter)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
+	typename S::ctx_t c;
+	S::init(c, d, hb_smem + (size_t)warp*S::smem_doubles(d), lane);
+	const long long slot_doubles = hb_ipm_slot_doubles<S>(d);
+	for(;;)
+		{
+		long long inst = 0;
+		if(lane==0) inst = atomicAdd(counter, 1);
+		inst = __shfl_sync(HB_FULL, inst, 0);
+		if(inst>=n_inst) break;
+		hb_ipm_ws w;
+		double *p = kkt + inst*kkt_stride;
+		w.L = p; p += S::L_doubles(d);
+		w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
+		w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
+		w.cv = p; w.nbp = HB_EVEN(d.nbtot);
+		const double *kb = kkt + inst*kkt_stride + HB_EVEN(slot_doubles);
+		const double *in_inst = in + inst*d.in_stride;
+		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+		double *info = info_all + inst*HB_IPM_INFO_HEAD;
+		double mu = 0.0, norms[3] = {0.0, 0.0, 0.0};
+		const bool valid = kb[d.ux_stride + d.pi_stride + 4*w.nbp] > 0.0 && d.nbtot>0;
+		if(valid)
+			{
+			/* new b, [r q], bounds ; iterate := backup (d_ip2_res_hard.c:2138-2173) */
+			S::extract(c, d, in_inst, w);
+			for(long long i=lane; i<d.ux_stride; i+=32) ux[i] = kb[i];
+			for(long long i=lane; i<d.pi_stride; i+=32) pi[i] = kb[d.ux_stride+i];
+			{
+			const double *kc = kb + d.ux_stride + d.pi_stride;
+			for(int cc=lane; cc<d.nbtot; cc+=32)
+				{
+				w.v(CV_LAM_LO)[cc] = kc[cc]; w.v(CV_LAM_UP)[cc] = kc[w.nbp+cc];
+				w.v(CV_T_LO)[cc] = kc[2*w.nbp+cc]; w.v(CV_T_UP)[cc] = kc[3*w.nbp+cc];
+				}
+			}
+			__syncwarp();
+			/* residuals at the backup with the new vectors (:2192), gradient from the stored t_inv (:2216) */
+			S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+			__syncwarp();
+			for(int cc=lane; cc<d.nbtot; cc+=32)
+				w.v(CV_QXG)[cc] = w.v(CV_TINV_LO)[cc]*(w.v(CV_RM_LO)[cc] - w.v(CV_LAM_LO)[cc]*w.v(CV_RD_LO)[cc])
+				                  - w.v(CV_TINV_UP)[cc]*(w.v(CV_RM_UP)[cc] + w.v(CV_LAM_UP)[cc]*w.v(CV_RD_UP)[cc]);
+			__syncwarp();
+			/* one solve with the stored factor, Pb from the new b (:2225) */
+			S::trs_newb(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXG));
+			__syncwarp();
+			/* dt, dlam (:2236) and the full step (:2239) */
+			(void)hb_ipm_alpha<true>(lane, d, w, w.dux);
+			__syncwarp();
+			for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += 1.0*w.dux[i];
+			for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += 1.0*w.dpi[i];
+			for(int cc=lane; cc<d.nbtot; cc+=32)
+				{
+				w.v(CV_LAM_LO)[cc] += 1.0*w.v(CV_DLAM_LO)[cc]; w.v(CV_LAM_UP)[cc] += 1.0*w.v(CV_DLAM_UP)[cc];
+				w.v(CV_T_LO)[cc] += 1.0*w.v(CV_DT_LO)[cc]; w.v(CV_T_UP)[cc] += 1.0*w.v(CV_DT_UP)[cc];
+				}
+			__syncwarp();
+			S::emit(c, d, w, lam_all + inst*2*(long long)d.nbtot, t_all + inst*2*(long long)d.nbtot);
+			}
+		if(lane==0)
+			{
+			/* status 0, or -10: the IPM call left no phase-2 factor behind (the reference reads an unset backup then) */
+			info[0] = 0.0; info[1] = valid ? 0.0 : -10.0;
 			info[2] = norms[0]; info[3] = norms[1]; info[4] = norms[2]; info[5] = mu;
 			}
 		__syncwarp();
@@ -631,7 +756,7 @@ extern "C" long long hb_ipm_work_doubles2(const hb_dims *d, long long L_doubles)
 
 template<class S> static int hb_launch_ipm_t(int smem, const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0,
 		double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
-		double *work, long long work_stride, int grid, int warps, int *counter, cudaStream_t st)
+		double *work, long long work_stride, int grid, int warps, int *counter, cudaStream_t st, double *kkt, long long kkt_stride)
 	{
 	if(hb_prep(hb_ipm_kernel<S>, smem)) return -1;
 	if(getenv("HPMPC_B200_VERBOSE"))
@@ -644,19 +769,61 @@ template<class S> static int hb_launch_ipm_t(int smem, const hb_dims *d, long lo
 		}
 	HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
 	hb_ipm_kernel<S><<<grid, warps*32, smem, st>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
-			ux, pi, lam, t, info, work, work_stride, counter);
+			ux, pi, lam, t, info, work, work_stride, counter, kkt, kkt_stride);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
 
+template<class S> static int hb_launch_kkt_t(int smem, const hb_dims *d, long long n_inst, const double *in, double *kkt, long long kkt_stride,
+		double *ux, double *pi, double *lam, double *t, double *info, int grid, int warps, int *counter, cudaStream_t st)
+	{
+	if(hb_prep(hb_kkt_new_rhs_kernel<S>, smem)) return -1;
+	HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+	hb_kkt_new_rhs_kernel<S><<<grid, warps*32, smem, st>>>(*d, n_inst, in, kkt, kkt_stride, ux, pi, lam, t, info, counter);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+/* new right-hand side on the state left by hb_launch_ipm_kkt (chains only) */
+extern "C" int hb_launch_kkt_new_rhs(const hb_dims *d, long long n_inst, const double *in, double *kkt, long long kkt_stride,
+		double *ux, double *pi, double *lam, double *t, double *info, int grid, int warps, int *counter, int fast_id, void *stream)
+	{
+	if(d->nzM>64) return -2;
+	if(warps>8) return -3;
+	cudaStream_t st = (cudaStream_t)stream;
+#define HB_KKT_ARGS d, n_inst, in, kkt, kkt_stride, ux, pi, lam, t, info, grid, warps, counter, st
+	switch(fast_id)
+		{
+		case 0: return hb_launch_kkt_t<hb_sweeps_fast<hbi_v0> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v0>::PER_WARP, HB_KKT_ARGS);
+		case 1: return hb_launch_kkt_t<hb_sweeps_fast<hbi_v1> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v1>::PER_WARP, HB_KKT_ARGS);
+		case 2: return hb_launch_kkt_t<hb_sweeps_fast<hbi_v2> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v2>::PER_WARP, HB_KKT_ARGS);
+		}
+	return hb_launch_kkt_t<hb_sweeps_generic>(warps*hb_smem_bytes_per_warp(d), HB_KKT_ARGS);
+#undef HB_KKT_ARGS
+	}
+
+extern "C" int hb_launch_ipm_kkt(const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
+		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream,
+		double *kkt, long long kkt_stride);
 extern "C" int hb_launch_ipm(const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
 		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
 		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream)
 	{
+	return hb_launch_ipm_kkt(d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start, ux, pi, lam, t, info, work, work_stride, n_slots,
+			grid, warps, counter, fast_id, stream, NULL, 0);
+	}
+
+/* kkt != NULL: every instance also leaves its KKT state (factor, t_inv, backup of the last iterate) in kkt + inst*kkt_stride */
+extern "C" int hb_launch_ipm_kkt(const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
+		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream,
+		double *kkt, long long kkt_stride)
+	{
 	if(d->nzM>64) return -2;
 	if(grid*warps>n_slots || warps>8) return -3;
 	cudaStream_t st = (cudaStream_t)stream;
-#define HB_IPM_ARGS d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start, ux, pi, lam, t, info, work, work_stride, grid, warps, counter, st
+#define HB_IPM_ARGS d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start, ux, pi, lam, t, info, work, work_stride, grid, warps, counter, st, kkt, kkt_stride
 	switch(fast_id)
 		{
 		case HB_IPM_TREE: return d->tn==NULL ? -4 : hb_launch_ipm_t<hb_sweeps_tree>(warps*hb_smem_bytes_per_warp(d), HB_IPM_ARGS);

@@ -112,6 +112,12 @@ int hb_launch_ric_trs(const hb_dims *dims, long long n_inst, const double *in, c
 int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
 		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
 		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream);
+int hb_launch_ipm_kkt(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
+		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
+		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream,
+		double *kkt, long long kkt_stride);
+int hb_launch_kkt_new_rhs(const hb_dims *dims, long long n_inst, const double *in, double *kkt, long long kkt_stride,
+		double *ux, double *pi, double *lam, double *t, double *info, int grid, int warps, int *counter, int fast_id, void *stream);
 /* fast_id -2 : dims->tn describes a scenario tree (one warp per tree, generic node sizes) */
 #define HB_IPM_TREE (-2)
 int hb_ipm_fast_variant(int N, const int *nx, const int *nu, int nbtot);

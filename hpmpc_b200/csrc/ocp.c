@@ -413,11 +413,20 @@ int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, con
  * instruction cache serves all of them from the same sweep; a single persistent launch in which warps pull instances from a
  * queue drifts apart and was measured 2.3x slower on config 3 (the fused kernel is several hundred KB of SASS).
  * HPMPC_B200_IPM_CHUNK=0 restores the single launch, any other value sets the wave size. */
+/* KKT state of one instance: the IPM kernel's work slot (factor, vectors, t_inv) followed by the backup of the iterate the
+ * factor belongs to (ux, pi, lam_lo, lam_up, t_lo, t_up) and a flag */
+static long long kkt_stride(const hpmpc_b200_ocp *p)
+	{
+	return HB_EVEN(p->ipm_ws) + p->dims.ux_stride + p->dims.pi_stride + 4*(long long)HB_EVEN(p->dims.nbtot) + 2;
+	}
+long long hpmpc_b200_kkt_state_stride(const hpmpc_b200_ocp *p) { return kkt_stride(p); }
+
 static int ipm_waves(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0, double mu_tol, double alpha_min,
 		int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, double *scratch, int *counter,
-		long long lam_len, void *stream)
+		long long lam_len, void *stream, double *d_kkt)
 	{
 	const long long ws = p->ipm_ws;
+	const long long ks = kkt_stride(p);
 	const int slots = p->i_grid*p->i_warps;
 	long long chunk = slots;
 	{ const char *e = getenv("HPMPC_B200_IPM_CHUNK"); if(e) chunk = atoll(e); }
@@ -429,9 +438,10 @@ static int ipm_waves(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, in
 		long long m = n_inst-done<chunk ? n_inst-done : chunk;
 		long long need = (m + p->i_warps - 1)/p->i_warps;
 		int grid = (int)(need<p->i_grid ? (need<1 ? 1 : need) : p->i_grid);
-		int rc = hb_launch_ipm(&p->dims, m, d_in + done*p->dims.in_stride, k_max, mu0, mu_tol, alpha_min, warm_start,
+		int rc = hb_launch_ipm_kkt(&p->dims, m, d_in + done*p->dims.in_stride, k_max, mu0, mu_tol, alpha_min, warm_start,
 				d_ux + done*p->dims.ux_stride, d_pi + done*p->dims.pi_stride, d_lam + done*lam_len, d_t + done*lam_len,
-				d_info + done*info_len, scratch, ws, slots, grid, p->i_warps, counter, p->ipm_fast_id, stream);
+				d_info + done*info_len, scratch, ws, slots, grid, p->i_warps, counter, p->ipm_fast_id, stream,
+				d_kkt ? d_kkt + done*ks : NULL, ks);
 		if(rc) return rc;
 		}
 	return 0;
@@ -446,7 +456,37 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
 	CK(cudaSetDevice(p->device));
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->i_grid*p->i_warps*p->ipm_ws)) return -1;
 	return ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
-			p->lam_stride, stream);
+			p->lam_stride, stream, NULL);
+	}
+
+/* the same solve, every instance leaving its KKT state in d_kkt (hpmpc_b200_kkt_state_stride() doubles each) */
+int hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t,
+		double *d_info, double *d_kkt, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	if(d_kkt==NULL) return -2;
+	CK(cudaSetDevice(p->device));
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->i_grid*p->i_warps*p->ipm_ws)) return -1;
+	return ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
+			p->lam_stride, stream, d_kkt);
+	}
+
+/* the last KKT system of that solve again, for the b, [r q] and bounds held in d_in (same matrices): one solve with the stored
+ * factor per instance (reference d_kkt_solve_new_rhs_res_mpc_hard_tv, mpc_solvers/d_ip2_res_hard.c:1922).
+ * d_info: 6 doubles per instance, [1] = 0 or -10 (the IPM left no phase-2 factor), [2..4] residual norms at the backup, [5] mu */
+int hpmpc_b200_d_kkt_solve_new_rhs_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_kkt,
+		double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	if(d_kkt==NULL) return -2;
+	CK(cudaSetDevice(p->device));
+	long long need = (n_inst + p->i_warps - 1)/p->i_warps;
+	int grid = (int)(need<p->i_grid ? (need<1 ? 1 : need) : p->i_grid);
+	return hb_launch_kkt_new_rhs(&p->dims, n_inst, d_in, d_kkt, kkt_stride(p), d_ux, d_pi, d_lam, d_t, d_info, grid, p->i_warps,
+			p->counter, p->ipm_fast_id, stream);
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -563,7 +603,7 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 		CK(cudaEventRecord(p->ev_in[k], st));
 		CK(cudaStreamWaitEvent(p->s_comp, p->ev_in[k], 0));
 		if(ipm_waves(p, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
-				p->scratch, p->counter, lam_len, p->s_comp)) return -1;
+				p->scratch, p->counter, lam_len, p->s_comp, NULL)) return -1;
 		CK(cudaEventRecord(p->ev_done[k], p->s_comp));
 		CK(cudaStreamWaitEvent(st, p->ev_done[k], 0));
 		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));

@@ -362,7 +362,8 @@ __device__ void hbi_trs_backward(hbi_ctx<C> &c, const hb_dims &d, const double *
 /* factors needs first when b is new (d_back_ric_rec_trs_tv_res with compute_Pb = 1, d_back_ric_rec.c:564)       */
 /* ------------------------------------------------------------------------------------------------ */
 template<class C>
-__device__ void hbi_Pb_sweep(hbi_ctx<C> &c, const double *__restrict__ in_inst, const double *__restrict__ Lst, double *Pb)
+__device__ void hbi_Pb_sweep(hbi_ctx<C> &c, const double *__restrict__ in_inst, const double *__restrict__ Lst, double *Pb,
+		const double *bv = nullptr /* b_n as vectors (edge n at n*NX) instead of the block's rows */)
 	{
 	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF;
 	const int l = c.lane, N = c.N;
@@ -376,7 +377,7 @@ __device__ void hbi_Pb_sweep(hbi_ctx<C> &c, const double *__restrict__ in_inst, 
 		const int m1 = n+1;
 		const double *Lp = (m1&1) ? c.Lb1 : c.Lb0;
 		const int brow = (n==0) ? NU : NUX;
-		if(l<NX) c.va[l] = in_inst[c.off_in(n) + brow*NX + l];
+		if(l<NX) c.va[l] = bv!=nullptr ? bv[n*NX+l] : in_inst[c.off_in(n) + brow*NX + l];
 		__syncwarp();
 		c.wait(2+(m1&1));
 		if(l<NX)

@@ -71,6 +71,19 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
                                         double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi,
                                         double *d_lam, double *d_t, double *d_info, void *stream);
 
+/* ---- re-solve with a new right-hand side on the IPM's last factorisation ----
+ * reference: d_kkt_solve_new_rhs_res_mpc_hard_tv, mpc_solvers/d_ip2_res_hard.c:1922 (high level: include/c_interface.h:63,67).
+ * The reference keeps the factor, t_inv and the backed-up iterate in the caller's work memory between the two calls; here the
+ * IPM call writes them to d_kkt (hpmpc_b200_kkt_state_stride() doubles per instance), and the second call reads them there.
+ * d_in of the second call holds the new b, [r q] and bounds in the same packed layout (its matrices must be those of the
+ * first call).  d_info of the second call: 6 doubles per instance, [1] = 0, or -10 when the IPM ran no phase-2 iteration. */
+long long hpmpc_b200_kkt_state_stride(const hpmpc_b200_ocp *p);
+int hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
+                                            double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi,
+                                            double *d_lam, double *d_t, double *d_info, double *d_kkt, void *stream);
+int hpmpc_b200_d_kkt_solve_new_rhs_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_kkt,
+                                         double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, void *stream);
+
 /* ---- data in host memory: copies in, solves, copies out (chunked so copies overlap the kernels) ---- */
 int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in,
                                             double *h_ux, double *h_pi);

@@ -77,6 +77,31 @@ def ipm(p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, warm_start=0):
                 stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
 
+def ipm_then_kkt_new_rhs(p: Ocp, p2: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8):
+    """orc_fortran_order_d_ip_then_kkt_new_rhs: the IPM on p, then its last KKT system solved again for the vectors
+    (b, q, r, lb, ub) of p2 (reference: fortran_order_d_solve_kkt_new_rhs_ocp_hard_tv after fortran_order_d_ip_ocp_hard_tv)."""
+    L, N = lib(), p.N
+    A = [_f(M) for M in p.A]; B = [_f(M) for M in p.B]; Q = [_f(M) for M in p.Q]; S = [_f(M) for M in p.S]; R = [_f(M) for M in p.R]
+    c = np.ascontiguousarray
+    v1 = [[c(v) for v in arr] for arr in (p.b, p.q, p.r, p.lb, p.ub)]
+    v2 = [[c(v) for v in arr] for arr in (p2.b, p2.q, p2.r, p2.lb, p2.ub)]
+    x = [np.zeros(max(n, 1)) for n in p.nx]; u = [np.zeros(max(n, 1)) for n in p.nu[:N]]
+    pi = [np.zeros(max(p.nx[n + 1], 1)) for n in range(N)]
+    lam = [np.zeros(max(2 * nb, 1)) for nb in p.nb]; t = [np.zeros(max(2 * nb, 1)) for nb in p.nb]
+    idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+    kk = C.c_int(0)
+    pa = ptr_array
+    b, q, r, lb, ub = v1
+    arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub)] + [pa(v) for v in v2] + [pa(x), pa(u), pa(pi), pa(lam), pa(t)]
+    fn = L.orc_fortran_order_d_ip_then_kkt_new_rhs
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p] * 20
+    status = fn(C.byref(kk), k_max, mu0, mu_tol, N, int_array(p.nx), int_array(p.nu), int_array(p.nb), pa(idxb), *arrs)
+    return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)],
+                u=[u[n][:p.nu[n]].copy() for n in range(N)], pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
+                lam=[lam[n][:2 * p.nb[n]].copy() for n in range(N + 1)], t=[t[n][:2 * p.nb[n]].copy() for n in range(N + 1)])
+
+
 def ric(p: Ocp, mode: str = "sv"):
     """Unconstrained LQCP by the oracle: mode 'sv' (factor+solve) or 'trf_trs'."""
     L, N = lib(), p.N

@@ -55,6 +55,10 @@ typedef struct {
 	 * Pb[n], n = 0..N-1) is the edge INTO node n+1, whose rows are those of dad[n+1] instead of stage n */
 	int *dad;
 	int *fk, *nk;           /* first kid and number of kids of every stage/node (kids are contiguous in BFS order; chain: n+1, 1) */
+	/* what the IPM leaves behind for a later solve with a new right-hand side (the reference keeps the same in its work
+	 * space: ux_bkp, pi_bkp, t_bkp, lam_bkp, t_inv and the factor, mpc_solvers/d_ip2_res_hard.c:2019-2133) */
+	double **k_ux, **k_pi, **k_lam, **k_t, **k_tinv;
+	int k_valid;            /* 1 once a phase-2 iteration has run */
 } orc_prob;
 
 static int nux_(const orc_prob *P, int n) { return P->nu[n] + P->nx[n]; }
@@ -105,6 +109,14 @@ orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *n
 		}
 	P->W = calloc((size_t)P->nzM*P->nxM, sizeof(double));
 	P->tmp = calloc(4*P->nzM, sizeof(double));
+	P->k_ux = calloc(N+1, sizeof(double*)); P->k_pi = calloc(N+1, sizeof(double*)); P->k_lam = calloc(N+1, sizeof(double*));
+	P->k_t = calloc(N+1, sizeof(double*)); P->k_tinv = calloc(N+1, sizeof(double*));
+	for(n=0; n<=N; n++)
+		{
+		P->k_ux[n] = calloc(nux_(P, n)+1, sizeof(double)); P->k_pi[n] = calloc(P->nxM+1, sizeof(double));
+		P->k_lam[n] = calloc(2*P->nb[n]+1, sizeof(double)); P->k_t[n] = calloc(2*P->nb[n]+1, sizeof(double));
+		P->k_tinv[n] = calloc(2*P->nb[n]+1, sizeof(double));
+		}
 	return P;
 	}
 
@@ -112,7 +124,11 @@ void orc_prob_free(orc_prob *P)
 	{
 	int n;
 	for(n=0; n<=P->N; n++)
-		{ free(P->idxb[n]); free(P->BAbt[n]); free(P->RSQrq[n]); free(P->L[n]); free(P->dinv[n]); free(P->d[n]); }
+		{
+		free(P->idxb[n]); free(P->BAbt[n]); free(P->RSQrq[n]); free(P->L[n]); free(P->dinv[n]); free(P->d[n]);
+		free(P->k_ux[n]); free(P->k_pi[n]); free(P->k_lam[n]); free(P->k_t[n]); free(P->k_tinv[n]);
+		}
+	free(P->k_ux); free(P->k_pi); free(P->k_lam); free(P->k_t); free(P->k_tinv);
 	free(P->idxb); free(P->BAbt); free(P->RSQrq); free(P->L); free(P->dinv); free(P->d);
 	free(P->nx); free(P->nu); free(P->nb); free(P->W); free(P->tmp); free(P->dad); free(P->fk); free(P->nk); free(P);
 	}
@@ -705,6 +721,15 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 			}
 		stat[5*(*kk)] = sigma; stat[5*(*kk)+3] = alpha;
 		alpha *= 0.995;
+		/* backup of the iterate the factor belongs to (d_backup_update_var_res_mpc_hard_tv, c99/d_aux_ip_hard_lib4.c:1382) */
+		for(n=0; n<=N; n++)
+			{
+			int nux = nux_(P,n), nb = P->nb[n];
+			for(i=0; i<nux; i++) P->k_ux[n][i] = ux[n][i];
+			if(n<N) for(i=0; i<P->nx[n+1]; i++) P->k_pi[n][i] = pi[n][i];
+			for(j=0; j<2*nb; j++) { P->k_lam[n][j] = lam[n][j]; P->k_t[n][j] = t[n][j]; P->k_tinv[n][j] = w->tinv[n][j]; }
+			}
+		P->k_valid = 1;
 		for(n=0; n<=N; n++)
 			{
 			int nux = nux_(P,n), nb = P->nb[n];
@@ -729,6 +754,58 @@ done:
 	vecs_free(w->res_q, N+1); vecs_free(w->res_b, N+1); vecs_free(w->res_d, N+1); vecs_free(w->res_m, N+1);
 	free(lnux); free(lnx1); free(l2nb); free(lnb);
 	return status;
+	}
+
+/* solve the KKT system of the IPM's last iteration again for a new right-hand side (new b_n, [r;q]_n, same matrices and
+ * bounds): d_kkt_solve_new_rhs_res_mpc_hard_tv, mpc_solvers/d_ip2_res_hard.c:1922.  Start from the backed-up iterate (:2138-2173),
+ * residuals there with the new vectors (:2192), qx from the stored t_inv (d_update_gradient_res, :2216), one solve with the
+ * stored factor and compute_Pb = 1 (:2225), dt / dlam (d_compute_dt_dlam_res, :2236), full step alpha = 1 (:2239).
+ * bnew[n] (nx_{n+1}), rqnew[n] (nux_n).  Needs P as left by orc_ip2_res_mpc_hard with at least one phase-2 iteration. */
+int orc_kkt_solve_new_rhs(orc_prob *P, double *const *bnew, double *const *rqnew, double **ux, double **pi, double **lam, double **t)
+	{
+	int N = P->N, n, i, j;
+	if(!P->k_valid) return -1;
+	int *lnux = malloc((N+1)*sizeof(int)), *lnx1 = malloc((N+1)*sizeof(int)), *l2nb = malloc((N+1)*sizeof(int)), *lnb = malloc((N+1)*sizeof(int));
+	for(n=0; n<=N; n++) { lnux[n] = nux_(P,n)+1; lnx1[n] = n<N ? P->nx[n+1] : 0; l2nb[n] = 2*P->nb[n]; lnb[n] = P->nb[n]; }
+	orc_ipm_ws W, *w = &W;
+	memset(w, 0, sizeof(W));
+	w->ux = ux; w->pi = pi; w->lam = lam; w->t = t;
+	w->dux = vecs(N+1, lnux); w->dpi = vecs(N+1, lnx1); w->qx = vecs(N+1, lnb); w->Pb = vecs(N+1, lnx1);
+	w->b = vecs(N+1, lnx1); w->rq = vecs(N+1, lnux);
+	w->res_q = vecs(N+1, lnux); w->res_b = vecs(N+1, lnx1); w->res_d = vecs(N+1, l2nb); w->res_m = vecs(N+1, l2nb);
+	for(n=0; n<=N; n++)
+		{
+		int nux = nux_(P,n), nb = P->nb[n];
+		for(i=0; i<nux; i++) { w->rq[n][i] = rqnew[n][i]; ux[n][i] = P->k_ux[n][i]; }
+		if(n<N) for(i=0; i<P->nx[n+1]; i++) { w->b[n][i] = bnew[n][i]; pi[n][i] = P->k_pi[n][i]; }
+		for(j=0; j<2*nb; j++) { lam[n][j] = P->k_lam[n][j]; t[n][j] = P->k_t[n][j]; }
+		}
+	double mu = 0.0;
+	ipm_residuals(P, w, &mu);
+	for(n=0; n<=N; n++)
+		{
+		int nb = P->nb[n]; const double *ti = P->k_tinv[n];
+		for(j=0; j<nb; j++)
+			w->qx[n][j] = ti[j]*(w->res_m[n][j] - lam[n][j]*w->res_d[n][j]) - ti[nb+j]*(w->res_m[n][nb+j] + lam[n][nb+j]*w->res_d[n][nb+j]);
+		}
+	orc_ric_trs(P, w->res_b, w->res_q, w->qx, w->dux, 1, w->dpi, 1, w->Pb);
+	for(n=0; n<=N; n++)
+		{
+		int nux = nux_(P,n), nb = P->nb[n]; const double *ti = P->k_tinv[n];
+		for(j=0; j<nb; j++)
+			{
+			int id = P->idxb[n][j];
+			double dtl =  w->dux[n][id] - w->res_d[n][j], dtu = -w->dux[n][id] + w->res_d[n][nb+j];
+			double dll = -ti[j]*(lam[n][j]*dtl + w->res_m[n][j]), dlu = -ti[nb+j]*(lam[n][nb+j]*dtu + w->res_m[n][nb+j]);
+			lam[n][j] += 1.0*dll; lam[n][nb+j] += 1.0*dlu; t[n][j] += 1.0*dtl; t[n][nb+j] += 1.0*dtu;
+			}
+		for(i=0; i<nux; i++) ux[n][i] += 1.0*w->dux[n][i];
+		if(n<N) for(i=0; i<P->nx[n+1]; i++) pi[n][i] += 1.0*w->dpi[n][i];
+		}
+	vecs_free(w->dux, N+1); vecs_free(w->dpi, N+1); vecs_free(w->qx, N+1); vecs_free(w->Pb, N+1); vecs_free(w->b, N+1); vecs_free(w->rq, N+1);
+	vecs_free(w->res_q, N+1); vecs_free(w->res_b, N+1); vecs_free(w->res_d, N+1); vecs_free(w->res_m, N+1);
+	free(lnux); free(lnx1); free(l2nb); free(lnb);
+	return 0;
 	}
 
 /* exit residual norms (mpc_solvers/d_res_ip_hard.c:38 + interfaces/c/fortran_order_interface.c:612-652) */
@@ -833,6 +910,47 @@ int orc_fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu
 	for(n=0; n<=N; n++) for(j=0; j<2*nb[n]; j++) lam[n][j] = hlam[n][j];
 	for(n=0; n<=N; n++) { free(hux[n]); free(hpi[n]); free(hlam[n]); free(ht[n]); }
 	free(hux); free(hpi); free(hlam); free(ht);
+	orc_prob_free(P);
+	return status;
+	}
+
+/* fortran_order_d_ip_ocp_hard_tv followed by fortran_order_d_solve_kkt_new_rhs_ocp_hard_tv on the same work space
+ * (interfaces/c/fortran_order_interface.c:53 and :1082): the IPM runs on (b, q, r, lb, ub); the last KKT system is then
+ * solved again for (b2, q2, r2, lb2, ub2) with the matrices and the factor left by the IPM (:1333).  x, u, pi, lam, t receive the
+ * result of the SECOND call (lam, t as [lower(nb) upper(nb)] per stage).  Returns the IPM status, or -10 when the IPM left
+ * no phase-2 factor behind (the reference reads an uninitialised backup in that case). */
+int orc_fortran_order_d_ip_then_kkt_new_rhs(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu_N, int *nb, int **hidxb,
+		double **A, double **B, double **b, double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub,
+		double **b2, double **q2, double **r2, double **lb2, double **ub2,
+		double **x, double **u, double **pi, double **lam, double **t)
+	{
+	int n, i, j;
+	orc_prob *P = orc_prob_create(N, nx, nu_N, nb, hidxb);
+	orc_prob_set(P, A, B, b, Q, S, R, q, r, lb, ub);
+	double **hux = alloc_ux(P);
+	double **hpi = malloc((N+1)*sizeof(double*)), **hlam = malloc((N+1)*sizeof(double*)), **ht = malloc((N+1)*sizeof(double*));
+	double **bn = malloc((N+1)*sizeof(double*)), **rqn = malloc((N+1)*sizeof(double*));
+	for(n=0; n<=N; n++)
+		{
+		hpi[n] = calloc(P->nxM+1, sizeof(double)); hlam[n] = calloc(2*P->nb[n]+1, sizeof(double)); ht[n] = calloc(2*P->nb[n]+1, sizeof(double));
+		bn[n] = calloc(P->nxM+1, sizeof(double)); rqn[n] = calloc(nux_(P,n)+1, sizeof(double));
+		}
+	double *stat = calloc(5*k_max+5, sizeof(double));
+	int status = orc_ip2_res_mpc_hard(P, kk, k_max, mu0, mu_tol, 1e-8, 0, stat, hux, hpi, hlam, ht);
+	for(n=0; n<=N; n++)
+		{
+		int nu = P->nu[n];
+		if(n<N) { for(i=0; i<nx[n+1]; i++) bn[n][i] = b2[n][i]; for(i=0; i<nu; i++) rqn[n][i] = r2[n][i]; }
+		for(i=0; i<nx[n]; i++) rqn[n][nu+i] = q2[n][i];
+		for(j=0; j<nb[n]; j++) { P->d[n][j] = lb2[n][j]; P->d[n][nb[n]+j] = ub2[n][j]; }
+		}
+	if(orc_kkt_solve_new_rhs(P, bn, rqn, hux, hpi, hlam, ht)) status = -10;
+	for(n=0; n<N; n++) for(i=0; i<P->nu[n]; i++) u[n][i] = hux[n][i];
+	for(n=0; n<=N; n++) for(i=0; i<nx[n]; i++) x[n][i] = hux[n][P->nu[n]+i];
+	for(n=0; n<N; n++) for(i=0; i<nx[n+1]; i++) pi[n][i] = hpi[n][i];
+	for(n=0; n<=N; n++) for(j=0; j<2*nb[n]; j++) { lam[n][j] = hlam[n][j]; t[n][j] = ht[n][j]; }
+	for(n=0; n<=N; n++) { free(hux[n]); free(hpi[n]); free(hlam[n]); free(ht[n]); free(bn[n]); free(rqn[n]); }
+	free(hux); free(hpi); free(hlam); free(ht); free(bn); free(rqn); free(stat);
 	orc_prob_free(P);
 	return status;
 	}
