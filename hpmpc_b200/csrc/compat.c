@@ -42,6 +42,9 @@ static struct
 	int k_max_alloc;
 	double *h_in, *h_ux, *h_pi, *h_Pb, *h_lam, *h_t, *h_info;
 	double *d_in, *d_ux, *d_pi, *d_Pb, *d_L, *d_lam, *d_t, *d_info;
+	/* KKT state of the last d_ip2_res_mpc_hard_tv call (what the reference keeps in the caller's work memory) and the
+	 * work-memory pointer that call was given: d_kkt_solve_new_rhs_res_mpc_hard_tv must be handed the same one */
+	double *d_kkt; const void *kkt_key;
 	} G;
 
 static void fatal(const char *what)
@@ -71,7 +74,7 @@ static void ctx_free(void)
 	for(n=0; n<=G.N; n++) free(G.idxb[n]);
 	free(G.idxb); free(G.nx); free(G.nu); free(G.nb);
 	free(G.h_in); free(G.h_ux); free(G.h_pi); free(G.h_Pb); free(G.h_lam); free(G.h_t); free(G.h_info);
-	cudaFree(G.d_in); cudaFree(G.d_ux); cudaFree(G.d_pi); cudaFree(G.d_Pb); cudaFree(G.d_L); cudaFree(G.d_lam); cudaFree(G.d_t); cudaFree(G.d_info);
+	cudaFree(G.d_in); cudaFree(G.d_ux); cudaFree(G.d_pi); cudaFree(G.d_Pb); cudaFree(G.d_L); cudaFree(G.d_lam); cudaFree(G.d_t); cudaFree(G.d_info); cudaFree(G.d_kkt);
 	memset(&G, 0, sizeof(G));
 	}
 
@@ -281,13 +284,21 @@ int d_ip2_res_mpc_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb
 	return 64;
 	}
 
-static int run_ipm_single(int *kk, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start, double *stat)
+static int run_ipm_single(int *kk, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start, double *stat, const void *keep_kkt)
 	{
 	int i;
 	if(h2d(G.d_in, G.h_in, G.sz.in_stride)) return -1;
 	if(warm_start && h2d(G.d_ux, G.h_ux, G.sz.ux_stride)) return -1;
 	if(cudaMemset(G.d_info, 0, sizeof(double)*(HB_IPM_INFO_HEAD+5*k_max))!=cudaSuccess) return -1;
-	if(hpmpc_b200_d_ip2_res_mpc_hard_batch(G.ocp, 1, G.d_in, k_max, mu0, mu_tol, alpha_min, warm_start,
+	G.kkt_key = NULL;
+	if(keep_kkt && G.sz.nbtot>0)
+		{
+		if(!G.d_kkt && cudaMalloc((void**)&G.d_kkt, sizeof(double)*(size_t)hpmpc_b200_kkt_state_stride(G.ocp))!=cudaSuccess) return -1;
+		if(hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch(G.ocp, 1, G.d_in, k_max, mu0, mu_tol, alpha_min, warm_start,
+				G.d_ux, G.d_pi, G.d_lam, G.d_t, G.d_info, G.d_kkt, NULL)) return -1;
+		G.kkt_key = keep_kkt;
+		}
+	else if(hpmpc_b200_d_ip2_res_mpc_hard_batch(G.ocp, 1, G.d_in, k_max, mu0, mu_tol, alpha_min, warm_start,
 			G.d_ux, G.d_pi, G.d_lam, G.d_t, G.d_info, NULL)) return -1;
 	if(cudaDeviceSynchronize()!=cudaSuccess) return -1;
 	if(d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_info, G.d_info, HB_IPM_INFO_HEAD+5*k_max)) return -1;
@@ -301,7 +312,7 @@ int d_ip2_res_mpc_hard_tv(int *kk, int k_max, double mu0, double mu_tol, double 
 		int *nx, int *nu_N, int *nb, int **idxb, int *ng, double **pBAbt, double **pQ, double **pDCt, double **d, double **ux,
 		int compute_mult, double **pi, double **lam, double **t, double *double_work_memory)
 	{
-	(void)pDCt; (void)double_work_memory; (void)compute_mult;
+	(void)pDCt; (void)compute_mult;
 	int n, i, status;
 	pthread_mutex_lock(&g_lock);
 	if(ctx_get(N, nx, nu_N, nb, idxb, ng, k_max)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_ip2_res_mpc_hard_tv: GPU context unavailable\n"); return -1; }
@@ -313,7 +324,7 @@ int d_ip2_res_mpc_hard_tv(int *kk, int k_max, double mu0, double mu_tol, double 
 			hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, NULL, NULL, NULL);
 			for(i=0; i<nun+nx[n]; i++) G.h_ux[oU+i] = ux[n][i];
 			}
-	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_ip2_res_mpc_hard_tv: GPU execution failed\n"); return -1; }
+	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat, double_work_memory)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_ip2_res_mpc_hard_tv: GPU execution failed\n"); return -1; }
 	status = (int)G.h_info[1];
 	for(n=0; n<=N; n++)
 		{
@@ -329,6 +340,50 @@ int d_ip2_res_mpc_hard_tv(int *kk, int k_max, double mu0, double mu_tol, double 
 		}
 	pthread_mutex_unlock(&g_lock);
 	return status;
+	}
+
+/* reference include/mpc_solvers.h:46 (mpc_solvers/d_ip2_res_hard.c:1922): the last KKT system of the preceding
+ * d_ip2_res_mpc_hard_tv call solved again for new b, q, d.  The reference finds the factor, t_inv and the backed-up iterate in
+ * double_work_memory; here they stay on the device, keyed by that pointer: the call must follow a d_ip2_res_mpc_hard_tv call
+ * with the same sizes and the same double_work_memory (anything else is reported and aborts, there is nothing to solve with). */
+void d_kkt_solve_new_rhs_res_mpc_hard_tv(int N, int *nx, int *nu_N, int *nb, int **idxb, int *ng, double **pBAbt, double **b,
+		double **pQ, double **q, double **pDCt, double **d, double **ux, int compute_mult, double **pi, double **lam, double **t,
+		double *double_work_memory)
+	{
+	(void)pDCt; (void)compute_mult; (void)ng;
+	int n, i;
+	pthread_mutex_lock(&g_lock);
+	if(!same_pattern(N, nx, nu_N, nb, idxb) || G.kkt_key==NULL || G.kkt_key!=(const void*)double_work_memory)
+		{ pthread_mutex_unlock(&g_lock); fatal("d_kkt_solve_new_rhs_res_mpc_hard_tv: no KKT state for this work memory (call d_ip2_res_mpc_hard_tv first)"); }
+	pack_from_pmat(N, nx, nu_N, nb, pBAbt, pQ, d);
+	for(n=0; n<=N; n++)
+		{
+		int oB, oH, nun = n<N ? nu_N[n] : 0, nux = nun+nx[n];
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, &oB, &oH, NULL, NULL, NULL, NULL, NULL);
+		if(n<N) for(i=0; i<nx[n+1]; i++) G.h_in[oB + (size_t)nux*nx[n+1] + i] = b[n][i];
+		for(i=0; i<nux; i++) G.h_in[oH + HB_TRI(nux) + i] = q[n][i];
+		}
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride)
+	|| hpmpc_b200_d_kkt_solve_new_rhs_batch(G.ocp, 1, G.d_in, G.d_kkt, G.d_ux, G.d_pi, G.d_lam, G.d_t, G.d_info, NULL)
+	|| cudaDeviceSynchronize()!=cudaSuccess
+	|| d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_info, G.d_info, HB_IPM_INFO_HEAD)
+	|| d2h(G.h_lam, G.d_lam, G.sz.lam_stride) || d2h(G.h_t, G.d_t, G.sz.lam_stride))
+		{ pthread_mutex_unlock(&g_lock); fatal("d_kkt_solve_new_rhs_res_mpc_hard_tv: GPU execution failed"); }
+	if(G.h_info[1]!=0.0)
+		{ pthread_mutex_unlock(&g_lock); fatal("d_kkt_solve_new_rhs_res_mpc_hard_tv: the preceding IPM call ran no phase-2 iteration, there is no factor to reuse"); }
+	for(n=0; n<=N; n++)
+		{
+		int oU, oP, oLm, nun = n<N ? nu_N[n] : 0, nbn = nb[n], pnb = RUP(nbn, BS);
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, &oLm, NULL);
+		for(i=0; i<nun+nx[n]; i++) ux[n][i] = G.h_ux[oU+i];
+		if(n<N) for(i=0; i<nx[n+1]; i++) pi[n][i] = G.h_pi[oP+i];
+		for(i=0; i<nbn; i++)
+			{
+			lam[n][i] = G.h_lam[oLm+i]; lam[n][pnb+i] = G.h_lam[oLm+nbn+i];
+			t[n][i] = G.h_t[oLm+i]; t[n][pnb+i] = G.h_t[oLm+nbn+i];
+			}
+		}
+	pthread_mutex_unlock(&g_lock);
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -374,7 +429,7 @@ static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol
 			for(i=0; i<nun; i++) G.h_ux[oU+i] = u[n][i];
 			for(i=0; i<nx[n]; i++) G.h_ux[oU+nun+i] = x[n][i];
 			}
-	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU execution failed\n"); return -1; }
+	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat, NULL)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU execution failed\n"); return -1; }
 	status = (int)G.h_info[1];
 	hpmpc_b200_unpack_solution(G.ocp, G.h_ux, G.h_pi, G.h_lam, x, u, pi, lam);
 	/* inputs fixed by lb == ub are returned exactly on the bound (c_order_interface.c:599-608) */

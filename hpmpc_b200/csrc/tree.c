@@ -473,6 +473,10 @@ static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d
 		CK(cudaMalloc((void**)&t->f_L, sizeof(double)*(size_t)n_trees*t->dims.L_stride));
 		CK(cudaMalloc((void**)&t->f_ws, sizeof(double)*(size_t)n_trees*t->f_ws_stride));
 		CK(cudaMalloc((void**)&t->f_state, sizeof(double)*(size_t)n_trees*8));
+		/* stride padding of the step vectors is never written by the solver kernels; keep it at zero so that the element-wise
+		 * updates over whole strides leave the padding of ux / pi at zero too */
+		CK(cudaMemsetAsync(t->f_dux, 0, sizeof(double)*(size_t)n_trees*t->dims.ux_stride, st));
+		CK(cudaMemsetAsync(t->f_dpi, 0, sizeof(double)*(size_t)n_trees*t->dims.pi_stride, st));
 		if(t->f_nact==NULL) { CK(cudaMalloc((void**)&t->f_nact, 2*sizeof(int))); CK(cudaMallocHost((void**)&t->h_nact, 2*sizeof(int))); }
 		t->f_trees = n_trees;
 		}

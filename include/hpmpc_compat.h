@@ -45,6 +45,12 @@ int d_ip2_res_mpc_hard_tv(int *kk, int k_max, double mu0, double mu_tol, double 
                           double **pBAbt, double **pQ, double **pDCt, double **d, double **ux,
                           int compute_mult, double **pi, double **lam, double **t, double *double_work_memory);
 
+/* include/mpc_solvers.h:46  (mpc_solvers/d_ip2_res_hard.c:1922): the last KKT system of the preceding d_ip2_res_mpc_hard_tv call
+ * (same sizes, same double_work_memory) solved again for new b, q, d; ux, pi, lam, t receive the result */
+void d_kkt_solve_new_rhs_res_mpc_hard_tv(int N, int *nx, int *nu_N, int *nb, int **idxb, int *ng, double **pBAbt, double **b,
+                                         double **pQ, double **q, double **pDCt, double **d, double **ux, int compute_mult,
+                                         double **pi, double **lam, double **t, double *double_work_memory);
+
 /* ---- high-level interface, dense stage-wise arrays : include/c_interface.h:59-67 ---- */
 /* include/c_interface.h:59  (interfaces/c/c_interface_work_space.c:70) */
 int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2);

@@ -149,3 +149,15 @@ def test_gpu_new_rhs_without_phase2_factor_reports_it():
         assert out[4][0, 1] == -10
     finally:
         h.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["ms_8_3_10", "ms_24_11_50", "ms_8_3_10_free_x0"])
+def test_gpu_compat_symbols_chain_like_the_reference(case):
+    """the reference's own pair of calls (d_ip2_res_mpc_hard_tv, then d_kkt_solve_new_rhs_res_mpc_hard_tv on the same work memory,
+    test_problems/test_d_ip_hard.c:1040) against libhpmpc_b200.so: same symbols, same arguments, reference golden vectors"""
+    prod = capi.HpmpcLib(capi.PRODUCT_LIB)
+    p = G.build(case)
+    r = prod.ip2_then_kkt_new_rhs(p, G.perturbed(p), k_max=G.K_MAX, mu0=G.MU0, mu_tol=G.MU_TOL)
+    assert [r["kk"], r["status"]] == list(GOLD[f"{case}/kk"])
+    check(r, {f: GOLD[f"{case}/{f}"] for f in ("u", "x", "pi", "lam", "t")}, case)
