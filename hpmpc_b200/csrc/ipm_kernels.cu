@@ -131,6 +131,7 @@ __device__ __forceinline__ void hb_ipm_emit_chain(int lane, const hb_dims &d, co
 struct hb_sweeps_generic
 	{
 	typedef hb_ctx ctx_t;
+	static constexpr bool has_kkt = true;
 	__device__ static __forceinline__ void extract(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w) { hb_ipm_extract_chain(c.lane, d, in_inst, w); }
 	__device__ static __forceinline__ void emit(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt) { hb_ipm_emit_chain(c.lane, d, w, lam, tt); }
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &d) { return hb_smem_doubles_per_warp(d.nzM, d.nxM); }
@@ -164,6 +165,7 @@ template<class C>
 struct hb_sweeps_fast
 	{
 	typedef hbi_ctx<C> ctx_t;
+	static constexpr bool has_kkt = true;
 	__device__ static __forceinline__ void extract(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w) { hb_ipm_extract_chain(c.lane, d, in_inst, w); }
 	__device__ static __forceinline__ void emit(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt) { hb_ipm_emit_chain(c.lane, d, w, lam, tt); }
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &) { return hbi_cfg<C>::PER_WARP; }
@@ -205,6 +207,7 @@ struct hb_sweeps_fast
 struct hb_sweeps_tree
 	{
 	typedef hb_ctx ctx_t;
+	static constexpr bool has_kkt = false;     /* the re-solve is built for chains */
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &d) { return hb_smem_doubles_per_warp(d.nzM, d.nxM); }
 	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return d.L_stride; }
 	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c = hb_make_ctx(d, smem_warp, lane); }
@@ -275,7 +278,9 @@ struct hb_sweeps_tree
 template<class S> __device__ __forceinline__ long long hb_ipm_slot_doubles(const hb_dims &d)
 	{ return S::L_doubles(d) + 3*d.ux_stride + 4*d.pi_stride + (long long)CV_COUNT*HB_EVEN(d.nbtot); }
 
-template<class S>
+/* KKT = true: every instance also leaves its KKT state in kkt + inst*kkt_stride (section on the re-solve below); the plain IPM is
+ * compiled without any of it */
+template<class S, bool KKT>
 __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, int k_max, double mu0,
 		double mu_tol, double alpha_min, int warm_start, double *__restrict__ ux_all, double *__restrict__ pi_all,
 		double *__restrict__ lam_all, double *__restrict__ t_all, double *__restrict__ info_all,
@@ -477,7 +482,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				alpha *= 0.995;
 				/* backup_update_var_res (c99/d_aux_ip_hard_lib4.c:1382-1449): the backup is what a later solve with a new
 				 * right-hand side starts from (d_ip2_res_hard.c:2138-2173); kept only when the caller asked for the KKT state */
-				if(kkt!=nullptr)
+				if(KKT)
 					{
 					double *kb = kkt + inst*kkt_stride + HB_EVEN(slot_doubles);
 					for(long long i=lane; i<d.ux_stride; i+=32) kb[i] = ux[i];
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 		/* results: lam, t as [lower(nb) upper(nb)] per stage (interfaces/c/fortran_order_interface.c:662-671) */
 		double *lam = lam_all + inst*2*(long long)d.nbtot, *tt = t_all + inst*2*(long long)d.nbtot;
 		S::emit(c, d, w, lam, tt);
-		if(kkt!=nullptr)
+		if(KKT)
 			{
 			/* the slot as it stands (factor of the last iteration, t_inv among the constraint vectors) goes with the backup */
 			__syncwarp();
@@ -758,18 +763,31 @@ template<class S> static int hb_launch_ipm_t(int smem, const hb_dims *d, long lo
 		double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
 		double *work, long long work_stride, int grid, int warps, int *counter, cudaStream_t st, double *kkt, long long kkt_stride)
 	{
-	if(hb_prep(hb_ipm_kernel<S>, smem)) return -1;
+	if(kkt!=NULL)
+		{
+		if constexpr (S::has_kkt)
+			{
+			if(hb_prep(hb_ipm_kernel<S, true>, smem)) return -1;
+			HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+			hb_ipm_kernel<S, true><<<grid, warps*32, smem, st>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
+					ux, pi, lam, t, info, work, work_stride, counter, kkt, kkt_stride);
+			HB_CK(cudaGetLastError());
+			return 0;
+			}
+		else return -4;
+		}
+	if(hb_prep(hb_ipm_kernel<S, false>, smem)) return -1;
 	if(getenv("HPMPC_B200_VERBOSE"))
 		{
 		int nb = 0; cudaFuncAttributes fa;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb_ipm_kernel<S>, warps*32, smem);
-		cudaFuncGetAttributes(&fa, hb_ipm_kernel<S>);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb_ipm_kernel<S, false>, warps*32, smem);
+		cudaFuncGetAttributes(&fa, hb_ipm_kernel<S, false>);
 		fprintf(stderr, "hpmpc_b200: ipm kernel: grid %d x %d threads, %d B dynamic + %zu B static smem, %d regs, %zu B local, %d CTAs/SM\n",
 			grid, warps*32, smem, fa.sharedSizeBytes, fa.numRegs, fa.localSizeBytes, nb);
 		}
 	HB_CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
-	hb_ipm_kernel<S><<<grid, warps*32, smem, st>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
-			ux, pi, lam, t, info, work, work_stride, counter, kkt, kkt_stride);
+	hb_ipm_kernel<S, false><<<grid, warps*32, smem, st>>>(*d, n_inst, in, k_max, mu0, mu_tol, alpha_min, warm_start,
+			ux, pi, lam, t, info, work, work_stride, counter, nullptr, 0);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
