@@ -187,9 +187,9 @@ struct hb_sweeps_fast
 	__device__ static __forceinline__ void trs_newb(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
 			const double *bv, const double *rqv, const double *qx)
 		{
-		hbi_Pb_sweep<C>(c, in_inst, w.L, w.Pb, bv);
+		hbi_trs_backward_newb<C>(c, d, in_inst, w.L, rqv, qx, bv, w.dux);
 		__syncwarp();
-		trs(c, d, in_inst, w, bv, rqv, qx);
+		hbi_forward<C, true>(c, in_inst, w.L, bv, w.dux, w.dux, w.dpi);
 		}
 	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
 			const double *ux, const double *pi, double *mu, double *norms)

@@ -358,6 +358,114 @@ __device__ void hbi_trs_backward(hbi_ctx<C> &c, const hb_dims &d, const double *
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
+/* the same sweep for a NEW b (d_back_ric_rec_trs_tv_res with compute_Pb = 1): Pb_n is formed from the factor of stage n+1   */
+/* while that factor is on chip for its own elimination step, instead of a separate sweep over all the factors              */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C>
+__device__ void hbi_trs_backward_newb(hbi_ctx<C> &c, const hb_dims &d, const double *__restrict__ in_inst, const double *__restrict__ Lst,
+		const double *rqv, const double *qx, const double *bv, double *wv)
+	{
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF, BAB = C::BAB;
+	const int l = c.lane, N = c.N;
+	auto issue_B = [&](int n) { c.load(n&1, c.io + (n&1)*BAB, in_inst + c.off_in(n), hbi_bytes_BAbt<C>(n==0)); };
+	auto issue_L = [&](int n) { c.load(2+(n&1), (n&1) ? c.Lb1 : c.Lb0, Lst + (long long)n*LBUF, 8u*LBUF); };
+	int coff = 0;
+	#pragma unroll
+	for(int jj=0; jj<NX; jj++) if(jj==l) coff = C::colOff(NU+jj);
+	/* Pb_n = Lxx_{n+1} (Lxx_{n+1}' b_n) with the factor of stage n+1 resident in Lp; lane l < NX returns component l */
+	auto Pb_from = [&](const double *Lp, int n) -> double
+		{
+		if(l<NX) c.va[l] = bv[n*NX+l];
+		__syncwarp();
+		if(l<NX)
+			{
+			const double *col = Lp + coff - l;                     /* col[m] = Lxx[m][l] */
+			double a0 = 0.0;
+			#pragma unroll
+			for(int m=0; m<NX; m++) if(m>=l) a0 = fma(col[m], c.va[m], a0);
+			c.tmp[l] = a0;
+			}
+		__syncwarp();
+		double p0 = 0.0;
+		if(l<NX)
+			{
+			#pragma unroll
+			for(int cc=0; cc<NX; cc++) if(cc<=l) p0 = fma(Lp[C::colOff(NU+cc) + (l-cc)], c.tmp[cc], p0);
+			}
+		__syncwarp();
+		return p0;
+		};
+	/* the factor of stage N is needed once, for Pb_{N-1}; its buffer is the one stage N-2 goes to next */
+	issue_L(N); issue_L(N-1); issue_B(N-1);
+	c.wait(2+(N&1));
+	double pbn = Pb_from((N&1) ? c.Lb1 : c.Lb0, N-1);
+	if(N>1) { issue_L(N-2); issue_B(N-2); }
+	{
+	const hb_stage s = d.st[N];
+	const int o = c.off_ux(N);
+	for(int i=l; i<NX; i+=32) wv[o+i] = rqv[o+i];
+	__syncwarp();
+	if(qx!=nullptr) for(int j=l; j<s.nb; j+=32) wv[o+d.idxb[s.off_c+j]] += qx[s.off_c+j];
+	__syncwarp();
+	}
+	for(int n=N-1; n>=0; n--)
+		{
+		const bool first = (n==0);
+		const double *Ln = (n&1) ? c.Lb1 : c.Lb0;
+		const double *sB = c.io + (n&1)*BAB;
+		const int nux = first ? NU : NUX, o = c.off_ux(n), o1 = c.off_ux(n+1) + ((n+1<N) ? NU : 0);
+		const hb_stage s = d.st[n];
+		for(int i=l; i<nux; i+=32) c.va[i] = rqv[o+i];
+		if(l<NX) c.vb[l] = pbn + wv[o1+l];
+		__syncwarp();
+		if(qx!=nullptr) for(int j=l; j<s.nb; j+=32) c.va[d.idxb[s.off_c+j]] += qx[s.off_c+j];
+		__syncwarp();
+		c.wait(2+(n&1)); c.wait(n&1);
+		/* v = va + [B A]' vb : lane l owns rows l and l+32 */
+		double v0 = 0.0, v1 = 0.0;
+		if(l<nux)
+			{
+			double a0 = c.va[l], a1 = 0.0;
+			#pragma unroll
+			for(int j=0; j<NX; j+=2)
+				{
+				const double2 t = *reinterpret_cast<const double2*>(sB + l*NX + j);
+				a0 = fma(t.x, c.vb[j], a0); a1 = fma(t.y, c.vb[j+1], a1);
+				}
+			v0 = a0+a1;
+			}
+		if(NUX>32 && l+32<nux)
+			{
+			double a0 = c.va[l+32], a1 = 0.0;
+			#pragma unroll
+			for(int j=0; j<NX; j+=2)
+				{
+				const double2 t = *reinterpret_cast<const double2*>(sB + (l+32)*NX + j);
+				a0 = fma(t.x, c.vb[j], a0); a1 = fma(t.y, c.vb[j+1], a1);
+				}
+			v1 = a0+a1;
+			}
+		/* forward substitution with the first NU columns of L_n */
+		const double di = (l<NU) ? Ln[C::DINV+l] : 0.0;
+		#pragma unroll
+		for(int j=0; j<NU; j++)
+			{
+			const double vj = __shfl_sync(HBF_FULL, v0*di, j);
+			const double *col = Ln + C::colOff(j) - j;            /* col[r] = L[r][j] in frame rows */
+			if(l==j) v0 = vj;
+			else if(l>j && l<nux) v0 = fma(-col[l], vj, v0);
+			if(NUX>32 && l+32<nux) v1 = fma(-col[l+32], vj, v1);
+			}
+		if(l<nux) wv[o+l] = v0;
+		if(NUX>32 && l+32<nux) wv[o+l+32] = v1;
+		__syncwarp();
+		if(n>0) pbn = Pb_from(Ln, n-1);          /* while the factor of stage n is still on chip */
+		if(n-2>=0) { issue_L(n-2); issue_B(n-2); }
+		}
+	}
+
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Pb_n = Lxx_{n+1} (Lxx_{n+1}' b_n) for every edge, b taken from the instance block: what a solve with stored  */
 /* factors needs first when b is new (d_back_ric_rec_trs_tv_res with compute_Pb = 1, d_back_ric_rec.c:564)       */
 /* ------------------------------------------------------------------------------------------------ */
