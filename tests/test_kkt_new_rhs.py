@@ -68,6 +68,30 @@ def test_oracle_new_rhs_needs_a_phase2_factor():
     assert o["status"] == -10
 
 
+def test_kkt_state_stride_and_no_cpu_fallback():
+    """host-only handle (device < 0): the state layout can be queried, the solve entry points refuse (there is no CPU path)"""
+    import ctypes as C
+    L = capi.product()
+    L.hpmpc_b200_kkt_state_stride.restype = C.c_longlong
+    L.hpmpc_b200_kkt_state_stride.argtypes = [C.c_void_p]
+    L.hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                                         C.c_double, C.c_int] + [C.c_void_p] * 7
+    L.hpmpc_b200_d_kkt_solve_new_rhs_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 8
+    for case in ("ms_8_3_10", "ms_4_2_5"):
+        p = G.build(case)
+        h = capi.BatchOcp(p, device=-1)
+        try:
+            even = lambda v: (v + 1) & ~1
+            ks = L.hpmpc_b200_kkt_state_stride(h.h)
+            assert ks == even(h.sz.ipm_work_stride) + h.sz.ux_stride + h.sz.pi_stride + 4 * even(h.sz.nbtot) + 2
+            buf = np.zeros(8)
+            a = buf.ctypes.data
+            assert L.hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch(h.h, 1, a, 10, 2.0, 1e-8, 1e-8, 0, a, a, a, a, a, a, None) == -4
+            assert L.hpmpc_b200_d_kkt_solve_new_rhs_batch(h.h, 1, a, a, a, a, a, a, a, None) == -4
+        finally:
+            h.close()
+
+
 # ------------------------------------------------------------------------------------------------------------ GPU
 def _gpu_pair(h, ps, p2s, k_max=G.K_MAX, mu_tol=G.MU_TOL):
     import ctypes as C
