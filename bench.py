@@ -539,6 +539,19 @@ def run_ours(args):
                 args.n_trees, args.no_cpu = saved
             except Exception as e:
                 out["extra"]["tree_error"] = repr(e)
+            # the IPM's last KKT system solved again for a new right-hand side (cfg 3 shapes, 4096 instances)
+            torch.cuda.empty_cache()
+            try:
+                import importlib.util
+                import types
+                sp = importlib.util.spec_from_file_location("bench_kkt_new_rhs", os.path.join(ROOT, "tools", "bench_kkt_new_rhs.py"))
+                mod = importlib.util.module_from_spec(sp)
+                sp.loader.exec_module(mod)
+                kr = mod.measure(types.SimpleNamespace(cfg="cfg3", n_inst=4096, steps=3, warmup=3))
+                out["extra"]["kkt_new_rhs"] = {k: kr[k] for k in ("metric", "value", "unit", "ms_per_step", "ipm_ms", "ipm_with_kkt_state_ms",
+                                                                  "speedup_vs_full_ipm_solve", "roofline")} | {"workload": kr["config"]["workload"]}
+            except Exception as e:
+                out["extra"]["kkt_new_rhs_error"] = repr(e)
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             from oracle import api as oracle

@@ -21,7 +21,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cfg", default="cfg3")
-    a = ap.parse_args()
+    print(json.dumps(measure(ap.parse_args())))
+
+
+def measure(a):
+    """a: namespace with cfg, n_inst, steps, warmup; returns the JSON record (bench.py adds it to its `extra`)"""
     import torch
     from hpmpc_b200 import capi
     from hpmpc_b200.batchgen import BatchSpec
@@ -72,7 +76,7 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6454.6)) if isinstance(peaks, dict) else 6454.6
     ach = bytes_re * n / (ms_re * 1e-3) / 1e9
-    print(json.dumps({
+    rec = {
         "metric": "kkt_new_rhs_resolves_per_s", "value": n / (ms_re * 1e-3), "unit": "solves/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_re, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"re-solve with a new right-hand side on the IPM's last factor, {a.cfg}, {n} instances", "kkt_state_bytes_per_instance": 8 * ks,
@@ -80,8 +84,9 @@ def main():
         "ipm_ms": ms_ipm, "ipm_with_kkt_state_ms": ms_ipm_kkt, "ipm_solves_per_s": n / (ms_ipm * 1e-3),
         "speedup_vs_full_ipm_solve": ms_ipm / ms_re,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "kernel": "hb_kkt_new_rhs_kernel", "algorithmic_bytes_per_solve": bytes_re}}))
+                     "kernel": "hb_kkt_new_rhs_kernel", "algorithmic_bytes_per_solve": bytes_re}}
     h.close()
+    return rec
 
 
 if __name__ == "__main__":
