@@ -291,15 +291,17 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 	typename S::ctx_t c;
 	S::init(c, d, hb_smem + (size_t)warp*S::smem_doubles(d), lane);
 	hb_ipm_ws w;
-	double *const slot = work + gw*work_stride;
 	const long long slot_doubles = hb_ipm_slot_doubles<S>(d);
-	{
-	double *p = slot;
-	w.L = p; p += S::L_doubles(d);
-	w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
-	w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
-	w.cv = p; w.nbp = HB_EVEN(d.nbtot);
-	}
+	auto set_ws = [&](double *p)
+		{
+		w.L = p; p += S::L_doubles(d);
+		w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
+		w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
+		w.cv = p; w.nbp = HB_EVEN(d.nbtot);
+		};
+	/* the warp's own slot -- or, when the KKT state is kept, the instance's state block itself (set per instance below):
+	 * factor, t_inv and vectors are then already where the re-solve expects them when the instance is done */
+	if(!KKT) set_ws(work + gw*work_stride);
 	const int info_len = HB_IPM_INFO_HEAD + 5*k_max;
 	const double thr0 = 0.1;
 
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
 		double *info = info_all + inst*info_len;
 		double *stat = info + HB_IPM_INFO_HEAD;
+		if(KKT) set_ws(kkt + inst*kkt_stride);
 
 		/* vectors taken from the instance block: rq0 = [r q], b0 = b, bounds */
 		S::extract(c, d, in_inst, w);
@@ -522,11 +525,8 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 		S::emit(c, d, w, lam, tt);
 		if(KKT)
 			{
-			/* the slot as it stands (factor of the last iteration, t_inv among the constraint vectors) goes with the backup */
-			__syncwarp();
-			double *ks = kkt + inst*kkt_stride;
-			for(long long i=lane; i<slot_doubles; i+=32) ks[i] = slot[i];
-			if(lane==0) ks[HB_EVEN(slot_doubles) + d.ux_stride + d.pi_stride + 4*w.nbp] = (double)n_ph2;
+			/* the work slot IS the state block: the factor of the last iteration and t_inv are in place; only the flag is left */
+			if(lane==0) kkt[inst*kkt_stride + HB_EVEN(slot_doubles) + d.ux_stride + d.pi_stride + 4*w.nbp] = (double)n_ph2;
 			}
 		if(lane==0)
 			{
