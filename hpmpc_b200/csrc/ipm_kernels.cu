@@ -278,6 +278,16 @@ struct hb_sweeps_tree
 template<class S> __device__ __forceinline__ long long hb_ipm_slot_doubles(const hb_dims &d)
 	{ return S::L_doubles(d) + 3*d.ux_stride + 4*d.pi_stride + (long long)CV_COUNT*HB_EVEN(d.nbtot); }
 
+template<class S> __device__ __forceinline__ hb_ipm_ws hb_ipm_make_ws(const hb_dims &d, double *p)
+	{
+	hb_ipm_ws w;
+	w.L = p; p += S::L_doubles(d);
+	w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
+	w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
+	w.cv = p; w.nbp = HB_EVEN(d.nbtot);
+	return w;
+	}
+
 /* KKT = true: every instance also leaves its KKT state in kkt + inst*kkt_stride (section on the re-solve below); the plain IPM is
  * compiled without any of it */
 template<class S, bool KKT>
@@ -290,18 +300,10 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 	const long long gw = (long long)blockIdx.x*nw + warp;
 	typename S::ctx_t c;
 	S::init(c, d, hb_smem + (size_t)warp*S::smem_doubles(d), lane);
-	hb_ipm_ws w;
 	const long long slot_doubles = hb_ipm_slot_doubles<S>(d);
-	auto set_ws = [&](double *p)
-		{
-		w.L = p; p += S::L_doubles(d);
-		w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
-		w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
-		w.cv = p; w.nbp = HB_EVEN(d.nbtot);
-		};
 	/* the warp's own slot -- or, when the KKT state is kept, the instance's state block itself (set per instance below):
 	 * factor, t_inv and vectors are then already where the re-solve expects them when the instance is done */
-	if(!KKT) set_ws(work + gw*work_stride);
+	hb_ipm_ws w = hb_ipm_make_ws<S>(d, work + gw*work_stride);
 	const int info_len = HB_IPM_INFO_HEAD + 5*k_max;
 	const double thr0 = 0.1;
 
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
 		double *info = info_all + inst*info_len;
 		double *stat = info + HB_IPM_INFO_HEAD;
-		if(KKT) set_ws(kkt + inst*kkt_stride);
+		if(KKT) w = hb_ipm_make_ws<S>(d, kkt + inst*kkt_stride);
 
 		/* vectors taken from the instance block: rq0 = [r q], b0 = b, bounds */
 		S::extract(c, d, in_inst, w);
