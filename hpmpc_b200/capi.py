@@ -107,16 +107,21 @@ class HpmpcLib:
         pi = [np.zeros(max(p.nx[n + 1], 1)) for n in range(N)]
         lam = [np.zeros(max(2 * nb, 1)) for nb in p.nb]
         idxb = [np.ascontiguousarray(v, dtype=np.int32) for v in p.idxb]
-        nx, nu, nb, ng = int_array(p.nx), int_array(p.nu), int_array(p.nb), int_array([0] * (N + 1))
-        empty = [np.zeros(1) for _ in range(N + 1)]
+        ngl = p.ng_list()
+        nx, nu, nb, ng = int_array(p.nx), int_array(p.nu), int_array(p.nb), int_array(ngl)
+        pad = lambda M: M if M.size else np.zeros(1)
+        Cg, Dg, lgg, ugg = p.general_arrays()
+        Cg = [pad(conv(M)) for M in Cg]; Dg = [pad(conv(M)) for M in Dg]
+        lgg = [pad(np.ascontiguousarray(v)) for v in lgg]; ugg = [pad(np.ascontiguousarray(v)) for v in ugg]
+        lam = [np.zeros(max(2 * p.nb[n] + 2 * ngl[n], 1)) for n in range(N + 1)]
         wsz = self.lib.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N)
         work = aligned_zeros(wsz // 8 + 16)
         res = np.zeros(8); stat = np.zeros(5 * k_max + 5)
         kk = C.c_int(0)
-        keep = [A, B, b, Q, S, R, q, r, lb, ub, x, u, pi, lam, idxb, empty]
+        keep = [A, B, b, Q, S, R, q, r, lb, ub, x, u, pi, lam, idxb, Cg, Dg, lgg, ugg]
         fn = self.lib.c_order_d_ip_ocp_hard_tv if order == "c" else self.lib.fortran_order_d_ip_ocp_hard_tv
         pa = ptr_array
-        arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(empty), pa(empty), pa(empty), pa(empty),
+        arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(Cg), pa(Dg), pa(lgg), pa(ugg),
                 pa(x), pa(u), pa(pi), pa(lam)]
         pidx = pa(idxb)
         status = fn(C.byref(kk), k_max, mu0, mu_tol, N, nx, nu, nb, pidx, ng, N, warm_start, *arrs,
@@ -124,7 +129,7 @@ class HpmpcLib:
         del keep
         return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)],
                     u=[u[n][:p.nu[n]].copy() for n in range(N)], pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
-                    lam=[lam[n][:2 * p.nb[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(),
+                    lam=[lam[n][:2 * p.nb[n] + 2 * ngl[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(),
                     stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
     # ---------------------------------------------------------------- low level (panel-major)
@@ -184,36 +189,100 @@ class HpmpcLib:
                     pi=[hpi[n][:p.nx[n + 1]].copy() for n in range(N)],
                     Pb=[hPb[n][:p.nx[n + 1]].copy() for n in range(N)])
 
-    def ip2_res_mpc_hard_tv(self, p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, alpha_min=1e-8, warm_start=0):
-        """d_ip2_res_mpc_hard_tv on panel-major data (reference include/mpc_solvers.h:42)."""
+    def _pm_general(self, p: Ocp):
+        """hpDCt[n] = [D C]'_n panel-major (nux x ng), and the bound-like vector layout [lb(pnb) ub(pnb) lg(png) ug(png)]
+        (interfaces/c/fortran_order_interface.c:276-283, :345-378)."""
         N = p.N
-        nx, nu, nb, ng = self._sizes(p)
-        BAbt, RSQ = self._pm_problem(p)
-        pnb = [_rup(v, BS) for v in p.nb]
-        d = [aligned_zeros(2 * pnb[n] + 4) for n in range(N + 1)]
+        ngl = p.ng_list()
+        Cg, Dg, lgg, ugg = p.general_arrays()
+        DCt = []
+        for n in range(N + 1):
+            M = np.vstack([np.asarray(Dg[n]).reshape(ngl[n], p.nu[n]).T, np.asarray(Cg[n]).reshape(ngl[n], p.nx[n]).T]) if ngl[n] else np.zeros((1, 1))
+            DCt.append(to_pmat(M))
+        pnb = [_rup(v, BS) for v in p.nb]; png = [_rup(v, BS) for v in ngl]
+        d = [aligned_zeros(2 * pnb[n] + 2 * png[n] + 4) for n in range(N + 1)]
         for n in range(N + 1):
             d[n][:p.nb[n]] = p.lb[n]; d[n][pnb[n]:pnb[n] + p.nb[n]] = p.ub[n]
+            if ngl[n]:
+                d[n][2 * pnb[n]:2 * pnb[n] + ngl[n]] = lgg[n]; d[n][2 * pnb[n] + png[n]:2 * pnb[n] + png[n] + ngl[n]] = ugg[n]
+        return DCt, d, pnb, png, ngl
+
+    @staticmethod
+    def _split_bound_like(v, nb, pnb, ng, png):
+        """[lb(pnb) ub(pnb) lg(png) ug(png)] -> [lb(nb) ub(nb) lg(ng) ug(ng)] (the high-level ordering, c_order_interface.c:662-681)."""
+        return np.concatenate([v[:nb], v[pnb:pnb + nb], v[2 * pnb:2 * pnb + ng], v[2 * pnb + png:2 * pnb + png + ng]])
+
+    def ip2_res_mpc_hard_tv(self, p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, alpha_min=1e-8, warm_start=0):
+        """d_ip2_res_mpc_hard_tv on panel-major data (reference include/mpc_solvers.h:42), general constraints included."""
+        N = p.N
+        nx, nu, nb, _ = self._sizes(p)
+        BAbt, RSQ = self._pm_problem(p)
+        DCt, d, pnb, png, ngl = self._pm_general(p)
+        ng = int_array(ngl)
         ux = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
         pi = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
-        lam = [aligned_zeros(2 * pnb[n] + 4) for n in range(N + 1)]
-        t = [aligned_zeros(2 * pnb[n] + 4) for n in range(N + 1)]
+        lam = [aligned_zeros(2 * pnb[n] + 2 * png[n] + 4) for n in range(N + 1)]
+        t = [aligned_zeros(2 * pnb[n] + 2 * png[n] + 4) for n in range(N + 1)]
         idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
-        dummy = [aligned_zeros(8) for _ in range(N + 1)]
         wsz = self.lib.d_ip2_res_mpc_hard_tv_work_space_size_bytes(N, nx, nu, nb, ng)
         work = aligned_zeros(wsz // 8 + 16)
         stat = np.zeros(5 * k_max + 5)
         kk = C.c_int(0)
         pa = ptr_array
-        keep = (pa(BAbt), pa(RSQ), pa(dummy), pa(d), pa(ux), pa(pi), pa(lam), pa(t), pa(idxb))
+        keep = (pa(BAbt), pa(RSQ), pa(DCt), pa(d), pa(ux), pa(pi), pa(lam), pa(t), pa(idxb))
         status = self.lib.d_ip2_res_mpc_hard_tv(C.byref(kk), k_max, mu0, mu_tol, alpha_min, warm_start, stat.ctypes.data, N,
                                                 nx, nu, nb, keep[8], ng, keep[0], keep[1], keep[2], keep[3], keep[4], 1,
                                                 keep[5], keep[6], keep[7], work.ctypes.data)
+        sp = self._split_bound_like
         return dict(status=status, kk=kk.value, u=[ux[n][:p.nu[n]].copy() for n in range(N)],
                     x=[ux[n][p.nu[n]:p.nu[n] + p.nx[n]].copy() for n in range(N + 1)],
                     pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
-                    lam=[np.concatenate([lam[n][:p.nb[n]], lam[n][pnb[n]:pnb[n] + p.nb[n]]]) for n in range(N + 1)],
-                    t=[np.concatenate([t[n][:p.nb[n]], t[n][pnb[n]:pnb[n] + p.nb[n]]]) for n in range(N + 1)],
+                    lam=[sp(lam[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)],
+                    t=[sp(t[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)],
                     stat=stat[:5 * kk.value].reshape(-1, 5).copy())
+
+    def ric_upd(self, p: Ocp, Qx, qx, mode: str = "sv"):
+        """d_back_ric_rec_sv_tv_res (or trf + trs) WITH the IPM's per-constraint updates (reference lqcp_solvers/d_back_ric_rec.c:112):
+        Qx[n], qx[n] hold nb[n] + ng[n] entries (bounds first); bounds add Qx to the Hessian diagonal / qx to the gradient at idxb,
+        general constraints add [D C]' diag(Qx) [D C] and [D C]' qx."""
+        N = p.N
+        nx, nu, nb, _ = self._sizes(p)
+        BAbt, RSQ = self._pm_problem(p)
+        DCt, _, pnb, png, ngl = self._pm_general(p)
+        ng = int_array(ngl)
+        wsz = self.lib.d_back_ric_rec_sv_tv_work_space_size_bytes(N, nx, nu, nb, ng)
+        msz = self.lib.d_back_ric_rec_sv_tv_memory_space_size_bytes(N, nx, nu, nb, ng)
+        work, mem = aligned_zeros(wsz // 8 + 64), aligned_zeros(msz // 8 + 64)
+        hux = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        hpi = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        hPb = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        pQx = [aligned_zeros(pnb[n] + png[n] + 4) for n in range(N + 1)]; pqx = [aligned_zeros(pnb[n] + png[n] + 4) for n in range(N + 1)]
+        bd = [aligned_zeros(pnb[n] + 4) for n in range(N + 1)]
+        for n in range(N + 1):
+            nbn = p.nb[n]
+            pQx[n][:nbn] = Qx[n][:nbn]; pQx[n][pnb[n]:pnb[n] + ngl[n]] = Qx[n][nbn:]
+            pqx[n][:nbn] = qx[n][:nbn]; pqx[n][pnb[n]:pnb[n] + ngl[n]] = qx[n][nbn:]
+            H = np.zeros((p.nu[n] + p.nx[n],)); H[:p.nu[n]] = np.diag(p.R[n]); H[p.nu[n]:] = np.diag(p.Q[n])
+            bd[n][:nbn] = H[np.asarray(p.idxb[n], dtype=int)] if nbn else 0.0
+        hb = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        hq = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        for n in range(N):
+            hb[n][:p.nx[n + 1]] = p.b[n]
+        for n in range(N + 1):
+            hq[n][:p.nu[n]] = p.r[n]; hq[n][p.nu[n]:p.nu[n] + p.nx[n]] = p.q[n]
+        pa = ptr_array
+        k = dict(B=pa(BAbt), Q=pa(RSQ), G=pa(DCt), ux=pa(hux), pi=pa(hpi), Pb=pa(hPb), idx=pa(idxb), Qx=pa(pQx), qx=pa(pqx), bd=pa(bd),
+                 hb=pa(hb), hq=pa(hq))
+        if mode == "sv":
+            self.lib.d_back_ric_rec_sv_tv_res(N, nx, nu, nb, k["idx"], ng, 0, k["B"], k["hb"], 0, k["Q"], k["hq"], k["bd"], k["G"], k["Qx"], k["qx"],
+                                              k["ux"], 1, k["pi"], 1, k["Pb"], mem.ctypes.data, work.ctypes.data)
+        else:
+            self.lib.d_back_ric_rec_trf_tv_res(N, nx, nu, nb, k["idx"], ng, k["B"], k["Q"], k["G"], k["Qx"], k["bd"], mem.ctypes.data, work.ctypes.data)
+            self.lib.d_back_ric_rec_trs_tv_res(N, nx, nu, nb, k["idx"], ng, k["B"], k["hb"], k["hq"], k["G"], k["qx"], k["ux"], 1, k["pi"], 1, k["Pb"],
+                                               mem.ctypes.data, work.ctypes.data)
+        return dict(u=[hux[n][:p.nu[n]].copy() for n in range(N)], x=[hux[n][p.nu[n]:p.nu[n] + p.nx[n]].copy() for n in range(N + 1)],
+                    pi=[hpi[n][:p.nx[n + 1]].copy() for n in range(N)])
 
     def ip2_then_kkt_new_rhs(self, p: Ocp, p2: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, alpha_min=1e-8):
         """d_ip2_res_mpc_hard_tv on p, then d_kkt_solve_new_rhs_res_mpc_hard_tv (reference mpc_solvers/d_ip2_res_hard.c:1922, called as in
@@ -281,6 +350,13 @@ def product() -> C.CDLL:
         L = C.CDLL(PRODUCT_LIB, mode=C.RTLD_LOCAL)
         L.hpmpc_b200_ocp_create.restype = C.c_int
         L.hpmpc_b200_ocp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hpmpc_b200_ocp_create_gen.restype = C.c_int
+        L.hpmpc_b200_ocp_create_gen.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hpmpc_b200_pack_general.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.hpmpc_b200_d_back_ric_rec_sv_upd_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 7
+        L.hpmpc_b200_d_back_ric_rec_trf_upd_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
+        L.hpmpc_b200_d_back_ric_rec_trs_upd_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 6
+        L.hpmpc_b200_ocp_generic_factor_layout.argtypes = [C.c_void_p]
         L.hpmpc_b200_ocp_destroy.argtypes = [C.c_void_p]
         L.hpmpc_b200_ocp_set_launch.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hpmpc_b200_ocp_sizes.argtypes = [C.c_void_p, C.POINTER(Sizes)]
@@ -310,7 +386,8 @@ class BatchOcp:
         self.h = C.c_void_p()
         idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
         self._keep = idxb
-        rc = L.hpmpc_b200_ocp_create(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb), device)
+        rc = L.hpmpc_b200_ocp_create_gen(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb),
+                                         int_array(p.ng_list()), device)
         if rc != 0:
             raise RuntimeError(f"hpmpc_b200_ocp_create failed ({rc})")
         self.refresh()
@@ -342,6 +419,10 @@ class BatchOcp:
         ptrs = [ptr_array(a) for a in arrs]
         rc = self.L.hpmpc_b200_pack_instance(self.h, 1, *ptrs, blk.ctypes.data)
         assert rc == 0
+        if p.ng:
+            g = [[c(M) if M.size else np.zeros(1) for M in L] for L in p.general_arrays()]
+            rc = self.L.hpmpc_b200_pack_general(self.h, 1, *[ptr_array(a) for a in g], blk.ctypes.data)
+            assert rc == 0
         return blk
 
     def split_ux(self, ux: np.ndarray):
@@ -356,4 +437,5 @@ class BatchOcp:
 
     def split_lam(self, lam: np.ndarray):
         p = self.p
-        return [lam[self.off[n]["lam"]:self.off[n]["lam"] + 2 * p.nb[n]].copy() for n in range(p.N + 1)]
+        ng = p.ng_list()
+        return [lam[self.off[n]["lam"]:self.off[n]["lam"] + 2 * p.nb[n] + 2 * ng[n]].copy() for n in range(p.N + 1)]

@@ -4,7 +4,8 @@
  * Each function below has the reference's exact signature (cited per function) and runs the problem as a
  * batch of ONE through the CUDA engine: unpack the caller's arrays into the native packed block, copy in,
  * launch, copy out.  This path exists for link compatibility and for the parity tests; throughput comes
- * from the batched entry points of hpmpc_b200.h.  Nothing here computes the solution on the CPU, and a
+ * from the batched entry points of hpmpc_b200.h.  General constraints (ng > 0: hpDCt / C, D, lg, ug) are supported on the any-size
+ * kernels.  Nothing here computes the solution on the CPU, and a
  * missing / failing GPU is reported on stderr and turned into an error return (or abort() for the void
  * reference signatures, mirroring the reference's own printf+exit(1) on bad sizes, c_order_interface.c:103-110).
  *
@@ -15,7 +16,7 @@
  *   high-level symbols: dense row-major (c_order_) or column-major (fortran_order_) stage arrays
  * Deliberate differences (documented in INTEGRATION.md): the caller's matrices are never modified
  * (lib4 writes q / b / diagonal updates into them and restores them later, d_ip2_res_hard.c:721-732);
- * `work` is not used; `memory` holds the factor in the layout of layout.h; ng must be 0; N2 is ignored.
+ * `work` is not used; `memory` holds the factor in the layout of layout.h; N2 is ignored.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,11 +38,11 @@ static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static struct
 	{
 	hpmpc_b200_ocp *ocp;
-	int N, *nx, *nu, *nb, **idxb;
+	int N, *nx, *nu, *nb, *ng, **idxb;
 	hpmpc_b200_sizes sz;
 	int k_max_alloc;
-	double *h_in, *h_ux, *h_pi, *h_Pb, *h_lam, *h_t, *h_info;
-	double *d_in, *d_ux, *d_pi, *d_Pb, *d_L, *d_lam, *d_t, *d_info;
+	double *h_in, *h_ux, *h_pi, *h_Pb, *h_lam, *h_t, *h_info, *h_Qx, *h_qx;
+	double *d_in, *d_ux, *d_pi, *d_Pb, *d_L, *d_lam, *d_t, *d_info, *d_Qx, *d_qx;
 	/* KKT state of the last d_ip2_res_mpc_hard_tv call (what the reference keeps in the caller's work memory) and the
 	 * work-memory pointer that call was given: d_kkt_solve_new_rhs_res_mpc_hard_tv must be handed the same one */
 	double *d_kkt; const void *kkt_key;
@@ -53,14 +54,14 @@ static void fatal(const char *what)
 	abort();
 	}
 
-static int same_pattern(int N, const int *nx, const int *nu, const int *nb, int *const *idxb)
+static int same_pattern(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *ng)
 	{
 	int n, j;
 	if(!G.ocp || G.N!=N) return 0;
 	for(n=0; n<=N; n++)
 		{
-		int nun = n<N ? nu[n] : 0, nbn = nb ? nb[n] : 0;
-		if(G.nx[n]!=nx[n] || G.nu[n]!=nun || G.nb[n]!=nbn) return 0;
+		int nun = n<N ? nu[n] : 0, nbn = nb ? nb[n] : 0, ngn = ng ? ng[n] : 0;
+		if(G.nx[n]!=nx[n] || G.nu[n]!=nun || G.nb[n]!=nbn || G.ng[n]!=ngn) return 0;
 		for(j=0; j<nbn; j++) if(G.idxb[n][j]!=idxb[n][j]) return 0;
 		}
 	return 1;
@@ -72,8 +73,9 @@ static void ctx_free(void)
 	if(!G.ocp) return;
 	hpmpc_b200_ocp_destroy(G.ocp);
 	for(n=0; n<=G.N; n++) free(G.idxb[n]);
-	free(G.idxb); free(G.nx); free(G.nu); free(G.nb);
-	free(G.h_in); free(G.h_ux); free(G.h_pi); free(G.h_Pb); free(G.h_lam); free(G.h_t); free(G.h_info);
+	free(G.idxb); free(G.nx); free(G.nu); free(G.nb); free(G.ng);
+	free(G.h_in); free(G.h_ux); free(G.h_pi); free(G.h_Pb); free(G.h_lam); free(G.h_t); free(G.h_info); free(G.h_Qx); free(G.h_qx);
+	cudaFree(G.d_Qx); cudaFree(G.d_qx);
 	cudaFree(G.d_in); cudaFree(G.d_ux); cudaFree(G.d_pi); cudaFree(G.d_Pb); cudaFree(G.d_L); cudaFree(G.d_lam); cudaFree(G.d_t); cudaFree(G.d_info); cudaFree(G.d_kkt);
 	memset(&G, 0, sizeof(G));
 	}
@@ -81,19 +83,19 @@ static void ctx_free(void)
 static int ctx_get(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *ng, int k_max)
 	{
 	int n, j, dev = 0;
-	if(ng) for(n=0; n<=N; n++) if(ng[n]>0) { fprintf(stderr, "hpmpc_b200: general constraints (ng>0) are not supported\n"); return -1; }
-	if(!same_pattern(N, nx, nu, nb, idxb))
+	if(!same_pattern(N, nx, nu, nb, idxb, ng))
 		{
 		ctx_free();
 		const char *e = getenv("HPMPC_B200_DEVICE");
 		if(e) dev = atoi(e); else if(cudaGetDevice(&dev)!=cudaSuccess) { fprintf(stderr, "hpmpc_b200: no CUDA device available\n"); return -1; }
-		if(hpmpc_b200_ocp_create(&G.ocp, N, nx, nu, nb, idxb, dev)) { G.ocp = NULL; return -1; }
+		if(hpmpc_b200_ocp_create_gen(&G.ocp, N, nx, nu, nb, idxb, ng, dev)) { G.ocp = NULL; return -1; }
 		{ extern void hpmpc_b200_internal_generic_trf(hpmpc_b200_ocp *p); hpmpc_b200_internal_generic_trf(G.ocp); }
 		G.N = N;
-		G.nx = malloc((N+1)*sizeof(int)); G.nu = malloc((N+1)*sizeof(int)); G.nb = malloc((N+1)*sizeof(int)); G.idxb = calloc(N+1, sizeof(int*));
+		G.nx = malloc((N+1)*sizeof(int)); G.nu = malloc((N+1)*sizeof(int)); G.nb = malloc((N+1)*sizeof(int)); G.ng = malloc((N+1)*sizeof(int));
+		G.idxb = calloc(N+1, sizeof(int*));
 		for(n=0; n<=N; n++)
 			{
-			G.nx[n] = nx[n]; G.nu[n] = n<N ? nu[n] : 0; G.nb[n] = nb ? nb[n] : 0;
+			G.nx[n] = nx[n]; G.nu[n] = n<N ? nu[n] : 0; G.nb[n] = nb ? nb[n] : 0; G.ng[n] = ng ? ng[n] : 0;
 			G.idxb[n] = malloc((G.nb[n]+1)*sizeof(int));
 			for(j=0; j<G.nb[n]; j++) G.idxb[n][j] = idxb[n][j];
 			}
@@ -102,11 +104,14 @@ static int ctx_get(int N, const int *nx, const int *nu, const int *nb, int *cons
 		G.h_in = calloc(G.sz.in_stride, sizeof(double)); G.h_ux = calloc(G.sz.ux_stride, sizeof(double));
 		G.h_pi = calloc(G.sz.pi_stride+2, sizeof(double)); G.h_Pb = calloc(G.sz.pi_stride+2, sizeof(double));
 		G.h_lam = calloc(lam, sizeof(double)); G.h_t = calloc(lam, sizeof(double));
+		G.h_Qx = calloc(lam, sizeof(double)); G.h_qx = calloc(lam, sizeof(double));
 		if(cudaMalloc((void**)&G.d_in, sizeof(double)*G.sz.in_stride)!=cudaSuccess
 		|| cudaMalloc((void**)&G.d_ux, sizeof(double)*G.sz.ux_stride)!=cudaSuccess
 		|| cudaMalloc((void**)&G.d_pi, sizeof(double)*(G.sz.pi_stride+2))!=cudaSuccess
 		|| cudaMalloc((void**)&G.d_Pb, sizeof(double)*(G.sz.pi_stride+2))!=cudaSuccess
 		|| cudaMalloc((void**)&G.d_L, sizeof(double)*G.sz.L_stride)!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_Qx, sizeof(double)*lam)!=cudaSuccess
+		|| cudaMalloc((void**)&G.d_qx, sizeof(double)*lam)!=cudaSuccess
 		|| cudaMalloc((void**)&G.d_lam, sizeof(double)*lam)!=cudaSuccess
 		|| cudaMalloc((void**)&G.d_t, sizeof(double)*lam)!=cudaSuccess)
 			{ fprintf(stderr, "hpmpc_b200: device allocation failed\n"); return -1; }
@@ -125,7 +130,9 @@ static int h2d(double *d, const double *h, size_t n) { return cudaMemcpy(d, h, s
 static int d2h(double *h, const double *d, size_t n) { return cudaMemcpy(h, d, sizeof(double)*n, cudaMemcpyDeviceToHost)!=cudaSuccess; }
 
 /* panel-major problem data -> native block (G.h_in) */
-static void pack_from_pmat(int N, const int *nx, const int *nu, const int *nb, double **hpBAbt, double **hpRSQrq, double **hd)
+/* hpDCt[n]: [D C]' of the stage, (nu+nx) x ng panel-major with cng = ng rounded up to ncl padded columns; hd[n] then continues
+ * with lg (png) and ug (png) behind the two padded bound blocks (interfaces/c/c_order_interface.c:276-283, :371-378) */
+static void pack_from_pmat_g(int N, const int *nx, const int *nu, const int *nb, double **hpBAbt, double **hpRSQrq, double **hd, double **hpDCt)
 	{
 	int n, i, j;
 	memset(G.h_in, 0, sizeof(double)*G.sz.in_stride);
@@ -149,7 +156,34 @@ static void pack_from_pmat(int N, const int *nx, const int *nu, const int *nb, d
 			int pnb = RUP(nb[n], BS);
 			for(j=0; j<nb[n]; j++) { G.h_in[oD+j] = hd[n][j]; G.h_in[oD+nb[n]+j] = hd[n][pnb+j]; }
 			}
+		if(G.ng[n]>0 && hpDCt)
+			{
+			int ng = G.ng[n], cng = RUP(ng, NCL), png = RUP(ng, BS), pnb = (nb && nb[n]>0) ? RUP(nb[n], BS) : 0, oG, oDg;
+			hpmpc_b200_ocp_general_offsets(G.ocp, n, NULL, &oG, &oDg, NULL);
+			for(i=0; i<nux; i++) for(j=0; j<ng; j++) G.h_in[oG+i*ng+j] = PM(hpDCt[n], cng, i, j);
+			if(hd) for(j=0; j<ng; j++) { G.h_in[oDg+j] = hd[n][2*pnb+j]; G.h_in[oDg+ng+j] = hd[n][2*pnb+png+j]; }
+			}
 		}
+	}
+
+/* the reference's Qx / qx arrays ([box (pnb) | general (ng)] per stage, lqcp_solvers/d_back_ric_rec.c:196-214) into the flat
+ * per-constraint device vectors the _upd_ entry points take; returns what to pass (NULL when the caller gave none) */
+static int stage_updates(int N, const int *nb, double **Qx, double **qx, const double **dQx, const double **dqx)
+	{
+	int n, j, any = 0;
+	*dQx = NULL; *dqx = NULL;
+	for(n=0; n<=N; n++) if((nb && nb[n]>0) || G.ng[n]>0) any = 1;
+	if(!any || (!Qx && !qx)) return 0;
+	for(n=0; n<=N; n++)
+		{
+		int oc, nbn = nb ? nb[n] : 0, pnb = nbn>0 ? RUP(nbn, BS) : 0;
+		hpmpc_b200_ocp_general_offsets(G.ocp, n, NULL, NULL, NULL, &oc);
+		for(j=0; j<nbn; j++) { if(Qx) G.h_Qx[oc+j] = Qx[n][j]; if(qx) G.h_qx[oc+j] = qx[n][j]; }
+		for(j=0; j<G.ng[n]; j++) { if(Qx) G.h_Qx[oc+nbn+j] = Qx[n][pnb+j]; if(qx) G.h_qx[oc+nbn+j] = qx[n][pnb+j]; }
+		}
+	if(Qx) { if(cudaMemcpy(G.d_Qx, G.h_Qx, sizeof(double)*G.sz.nbtot, cudaMemcpyHostToDevice)!=cudaSuccess) return -1; *dQx = G.d_Qx; }
+	if(qx) { if(cudaMemcpy(G.d_qx, G.h_qx, sizeof(double)*G.sz.nbtot, cudaMemcpyHostToDevice)!=cudaSuccess) return -1; *dqx = G.d_qx; }
+	return 0;
 	}
 
 /* optional vector overrides of the Riccati entry points, folded into the packed block */
@@ -165,13 +199,15 @@ static void fold_updates(int N, const int *nx, const int *nu, const int *nb, int
 		double *H = G.h_in + oH;
 		if(update_b && n<N) for(j=0; j<nx[n+1]; j++) G.h_in[oB+nux*nx[n+1]+j] = b[n][j];
 		if(update_q) for(j=0; j<nux; j++) H[HB_TRI(nux)+j] = q[n][j];
-		if(nb && nb[n]>0)
+		/* ddiaadin_libsp (d_back_ric_rec.c:199): the bounded diagonal entries are bd + Qx, i.e. bd replaces whatever the
+		 * matrix holds; Qx itself (and qx) are applied on the device */
+		if(nb && nb[n]>0 && Qx && bd)
 			for(j=0; j<nb[n]; j++)
 				{
 				int id = idxb[n][j];
-				if(Qx) H[HB_TRI(id)+id] = (bd ? bd[n][j] : H[HB_TRI(id)+id]) + Qx[n][j];   /* ddiaadin_libsp: bd + Qx */
-				if(qx) H[HB_TRI(nux)+id] += qx[n][j];                                        /* drowad_libsp */
+				H[HB_TRI(id)+id] = bd[n][j];
 				}
+		(void)qx;
 		}
 	}
 
@@ -196,15 +232,16 @@ void d_back_ric_rec_sv_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int 
 		int update_q, double **hpRSQrq, double **q, double **bd, double **hpDCt, double **Qx, double **qx, double **hux,
 		int compute_pi, double **hpi, int compute_Pb, double **hPb, double *memory, double *work)
 	{
-	(void)hpDCt; (void)work;
+	(void)work;
 	int n, i;
+	const double *dQx, *dqx;
 	pthread_mutex_lock(&g_lock);
 	if(ctx_get(N, nx, nu, nb, idxb, ng, 0)) fatal("d_back_ric_rec_sv_tv_res: GPU context unavailable");
-	pack_from_pmat(N, nx, nu, nb, hpBAbt, hpRSQrq, NULL);
+	pack_from_pmat_g(N, nx, nu, nb, hpBAbt, hpRSQrq, NULL, hpDCt);
 	fold_updates(N, nx, nu, nb, idxb, update_b, b, update_q, q, bd, Qx, qx);
-	if(h2d(G.d_in, G.h_in, G.sz.in_stride)) fatal("copy to device failed");
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride) || stage_updates(N, nb, Qx, qx, &dQx, &dqx)) fatal("copy to device failed");
 	/* factor kept per instance (d_L) so that a later trs call can reuse it through `memory` */
-	if(hpmpc_b200_d_back_ric_rec_sv_batch(G.ocp, 1, G.d_in, G.d_ux, G.d_pi, G.d_Pb, NULL)) fatal("sv launch failed");
+	if(hpmpc_b200_d_back_ric_rec_sv_upd_batch(G.ocp, 1, G.d_in, dQx, dqx, G.d_ux, G.d_pi, G.d_Pb, NULL)) fatal("sv launch failed");
 	if(cudaDeviceSynchronize()!=cudaSuccess) fatal("sv kernel failed");
 	if(d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_Pb, G.d_Pb, G.sz.pi_stride)) fatal("copy from device failed");
 	if(memory)
@@ -227,13 +264,14 @@ void d_back_ric_rec_sv_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int 
 void d_back_ric_rec_trf_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hpRSQrq,
 		double **hpDCt, double **Qx, double **bd, double *memory, double *work)
 	{
-	(void)hpDCt; (void)work;
+	(void)work;
+	const double *dQx, *dqx;
 	pthread_mutex_lock(&g_lock);
 	if(ctx_get(N, nx, nu, nb, idxb, ng, 0)) fatal("d_back_ric_rec_trf_tv_res: GPU context unavailable");
-	pack_from_pmat(N, nx, nu, nb, hpBAbt, hpRSQrq, NULL);
+	pack_from_pmat_g(N, nx, nu, nb, hpBAbt, hpRSQrq, NULL, hpDCt);
 	fold_updates(N, nx, nu, nb, idxb, 0, NULL, 0, NULL, bd, Qx, NULL);
-	if(h2d(G.d_in, G.h_in, G.sz.in_stride)) fatal("copy to device failed");
-	if(hpmpc_b200_d_back_ric_rec_trf_batch(G.ocp, 1, G.d_in, G.d_L, NULL)) fatal("trf launch failed");
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride) || stage_updates(N, nb, Qx, NULL, &dQx, &dqx)) fatal("copy to device failed");
+	if(hpmpc_b200_d_back_ric_rec_trf_upd_batch(G.ocp, 1, G.d_in, dQx, G.d_L, NULL)) fatal("trf launch failed");
 	if(cudaDeviceSynchronize()!=cudaSuccess) fatal("trf kernel failed");
 	if(d2h(memory, G.d_L, G.sz.L_stride)) fatal("copy from device failed");
 	pthread_mutex_unlock(&g_lock);
@@ -242,8 +280,9 @@ void d_back_ric_rec_trf_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int
 void d_back_ric_rec_trs_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hb, double **hq,
 		double **hpDCt, double **qx, double **hux, int compute_pi, double **hpi, int compute_Pb, double **hPb, double *memory, double *work)
 	{
-	(void)hpDCt; (void)work; (void)compute_Pb; (void)hPb;
+	(void)work; (void)compute_Pb; (void)hPb;
 	int n, i, j;
+	const double *dQx, *dqx;
 	pthread_mutex_lock(&g_lock);
 	if(ctx_get(N, nx, nu, nb, idxb, ng, 0)) fatal("d_back_ric_rec_trs_tv_res: GPU context unavailable");
 	/* only [B A]', b and the gradient are read by the solve; the Hessian part of the block is unused */
@@ -259,10 +298,15 @@ void d_back_ric_rec_trs_tv_res(int N, int *nx, int *nu, int *nb, int **idxb, int
 			for(j=0; j<nx1; j++) G.h_in[oB+nux*nx1+j] = hb[n][j];
 			}
 		for(j=0; j<nux; j++) G.h_in[oH+HB_TRI(nux)+j] = hq[n][j];
-		if(nb && nb[n]>0 && qx) for(j=0; j<nb[n]; j++) G.h_in[oH+HB_TRI(nux)+idxb[n][j]] += qx[n][j];
+		if(G.ng[n]>0 && hpDCt)
+			{
+			int ngn = G.ng[n], cng = RUP(ngn, NCL), oG;
+			hpmpc_b200_ocp_general_offsets(G.ocp, n, NULL, &oG, NULL, NULL);
+			for(i=0; i<nux; i++) for(j=0; j<ngn; j++) G.h_in[oG+i*ngn+j] = PM(hpDCt[n], cng, i, j);
+			}
 		}
-	if(h2d(G.d_in, G.h_in, G.sz.in_stride) || h2d(G.d_L, memory, G.sz.L_stride)) fatal("copy to device failed");
-	if(hpmpc_b200_d_back_ric_rec_trs_batch(G.ocp, 1, G.d_in, G.d_L, G.d_ux, G.d_pi, NULL)) fatal("trs launch failed");
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride) || h2d(G.d_L, memory, G.sz.L_stride) || stage_updates(N, nb, NULL, qx, &dQx, &dqx)) fatal("copy to device failed");
+	if(hpmpc_b200_d_back_ric_rec_trs_upd_batch(G.ocp, 1, G.d_in, G.d_L, dqx, G.d_ux, G.d_pi, NULL)) fatal("trs launch failed");
 	if(cudaDeviceSynchronize()!=cudaSuccess) fatal("trs kernel failed");
 	if(d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride)) fatal("copy from device failed");
 	for(n=0; n<=N; n++)
@@ -312,11 +356,11 @@ int d_ip2_res_mpc_hard_tv(int *kk, int k_max, double mu0, double mu_tol, double 
 		int *nx, int *nu_N, int *nb, int **idxb, int *ng, double **pBAbt, double **pQ, double **pDCt, double **d, double **ux,
 		int compute_mult, double **pi, double **lam, double **t, double *double_work_memory)
 	{
-	(void)pDCt; (void)compute_mult;
+	(void)compute_mult;
 	int n, i, status;
 	pthread_mutex_lock(&g_lock);
 	if(ctx_get(N, nx, nu_N, nb, idxb, ng, k_max)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_ip2_res_mpc_hard_tv: GPU context unavailable\n"); return -1; }
-	pack_from_pmat(N, nx, nu_N, nb, pBAbt, pQ, d);
+	pack_from_pmat_g(N, nx, nu_N, nb, pBAbt, pQ, d, pDCt);
 	if(warm_start)
 		for(n=0; n<=N; n++)
 			{
@@ -337,6 +381,13 @@ int d_ip2_res_mpc_hard_tv(int *kk, int k_max, double mu0, double mu_tol, double 
 			lam[n][i] = G.h_lam[oLm+i]; lam[n][pnb+i] = G.h_lam[oLm+nbn+i];
 			t[n][i] = G.h_t[oLm+i]; t[n][pnb+i] = G.h_t[oLm+nbn+i];
 			}
+		/* general constraints behind the two padded bound blocks: [lg (png) ug (png)] */
+		for(i=0; i<G.ng[n]; i++)
+			{
+			const int ngn = G.ng[n], png = RUP(ngn, BS);
+			lam[n][2*pnb+i] = G.h_lam[oLm+2*nbn+i]; lam[n][2*pnb+png+i] = G.h_lam[oLm+2*nbn+ngn+i];
+			t[n][2*pnb+i] = G.h_t[oLm+2*nbn+i]; t[n][2*pnb+png+i] = G.h_t[oLm+2*nbn+ngn+i];
+			}
 		}
 	pthread_mutex_unlock(&g_lock);
 	return status;
@@ -350,12 +401,48 @@ void d_kkt_solve_new_rhs_res_mpc_hard_tv(int N, int *nx, int *nu_N, int *nb, int
 		double **pQ, double **q, double **pDCt, double **d, double **ux, int compute_mult, double **pi, double **lam, double **t,
 		double *double_work_memory)
 	{
-	(void)pDCt; (void)compute_mult; (void)ng;
+	(void)compute_mult;
 	int n, i;
 	pthread_mutex_lock(&g_lock);
-	if(!same_pattern(N, nx, nu_N, nb, idxb) || G.kkt_key==NULL || G.kkt_key!=(const void*)double_work_memory)
-		{ pthread_mutex_unlock(&g_lock); fatal("d_kkt_solve_new_rhs_res_mpc_hard_tv: no KKT state for this work memory (call d_ip2_res_mpc_hard_tv first)"); }
-	pack_from_pmat(N, nx, nu_N, nb, pBAbt, pQ, d);
+	/* an unconstrained problem has no IPM state: the reference's re-solve degenerates to one Riccati solve with the new b, q
+	 * (d_ip2_res_hard.c:2225 with empty constraint sets) */
+	{
+	int nctot = 0;
+	for(n=0; n<=N; n++) nctot += (nb ? nb[n] : 0) + (ng ? ng[n] : 0);
+	if(nctot==0)
+		{
+		if(ctx_get(N, nx, nu_N, nb, idxb, ng, 1)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_kkt_solve_new_rhs_res_mpc_hard_tv: GPU context unavailable, outputs untouched\n"); return; }
+		pack_from_pmat_g(N, nx, nu_N, nb, pBAbt, pQ, NULL, NULL);
+		for(n=0; n<=N; n++)
+			{
+			int oB, oH, nun = n<N ? nu_N[n] : 0, nux = nun+nx[n];
+			hpmpc_b200_ocp_stage_offsets(G.ocp, n, &oB, &oH, NULL, NULL, NULL, NULL, NULL);
+			if(n<N) for(i=0; i<nx[n+1]; i++) G.h_in[oB + (size_t)nux*nx[n+1] + i] = b[n][i];
+			for(i=0; i<nux; i++) G.h_in[oH + HB_TRI(nux) + i] = q[n][i];
+			}
+		if(h2d(G.d_in, G.h_in, G.sz.in_stride) || hpmpc_b200_d_back_ric_rec_sv_batch(G.ocp, 1, G.d_in, G.d_ux, G.d_pi, NULL, NULL)
+		|| cudaDeviceSynchronize()!=cudaSuccess || d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride))
+			{ pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_kkt_solve_new_rhs_res_mpc_hard_tv: GPU execution failed, outputs untouched\n"); return; }
+		for(n=0; n<=N; n++)
+			{
+			int oU, oP, nun = n<N ? nu_N[n] : 0;
+			hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, NULL, NULL);
+			for(i=0; i<nun+nx[n]; i++) ux[n][i] = G.h_ux[oU+i];
+			if(n<N) for(i=0; i<nx[n+1]; i++) pi[n][i] = G.h_pi[oP+i];
+			}
+		pthread_mutex_unlock(&g_lock);
+		return;
+		}
+	}
+	/* nothing to solve with: say why and leave the caller's arrays untouched (the reference would read whatever its work memory
+	 * holds); a drop-in library does not kill the host process for this */
+	if(!same_pattern(N, nx, nu_N, nb, idxb, ng) || G.kkt_key==NULL || G.kkt_key!=(const void*)double_work_memory)
+		{
+		pthread_mutex_unlock(&g_lock);
+		fprintf(stderr, "hpmpc_b200: d_kkt_solve_new_rhs_res_mpc_hard_tv: no KKT state for this work memory -- call d_ip2_res_mpc_hard_tv with the same sizes and double_work_memory first; outputs untouched\n");
+		return;
+		}
+	pack_from_pmat_g(N, nx, nu_N, nb, pBAbt, pQ, d, pDCt);
 	for(n=0; n<=N; n++)
 		{
 		int oB, oH, nun = n<N ? nu_N[n] : 0, nux = nun+nx[n];
@@ -368,9 +455,13 @@ void d_kkt_solve_new_rhs_res_mpc_hard_tv(int N, int *nx, int *nu_N, int *nb, int
 	|| cudaDeviceSynchronize()!=cudaSuccess
 	|| d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_info, G.d_info, HB_IPM_INFO_HEAD)
 	|| d2h(G.h_lam, G.d_lam, G.sz.lam_stride) || d2h(G.h_t, G.d_t, G.sz.lam_stride))
-		{ pthread_mutex_unlock(&g_lock); fatal("d_kkt_solve_new_rhs_res_mpc_hard_tv: GPU execution failed"); }
+		{ pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: d_kkt_solve_new_rhs_res_mpc_hard_tv: GPU execution failed, outputs untouched\n"); return; }
 	if(G.h_info[1]!=0.0)
-		{ pthread_mutex_unlock(&g_lock); fatal("d_kkt_solve_new_rhs_res_mpc_hard_tv: the preceding IPM call ran no phase-2 iteration, there is no factor to reuse"); }
+		{
+		pthread_mutex_unlock(&g_lock);
+		fprintf(stderr, "hpmpc_b200: d_kkt_solve_new_rhs_res_mpc_hard_tv: the preceding IPM call ran no phase-2 iteration (it converged in phase 1), there is no factor to reuse; outputs untouched\n");
+		return;
+		}
 	for(n=0; n<=N; n++)
 		{
 		int oU, oP, oLm, nun = n<N ? nu_N[n] : 0, nbn = nb[n], pnb = RUP(nbn, BS);
@@ -381,6 +472,13 @@ void d_kkt_solve_new_rhs_res_mpc_hard_tv(int N, int *nx, int *nu_N, int *nb, int
 			{
 			lam[n][i] = G.h_lam[oLm+i]; lam[n][pnb+i] = G.h_lam[oLm+nbn+i];
 			t[n][i] = G.h_t[oLm+i]; t[n][pnb+i] = G.h_t[oLm+nbn+i];
+			}
+		/* general constraints behind the two padded bound blocks: [lg (png) ug (png)] */
+		for(i=0; i<G.ng[n]; i++)
+			{
+			const int ngn = G.ng[n], png = RUP(ngn, BS);
+			lam[n][2*pnb+i] = G.h_lam[oLm+2*nbn+i]; lam[n][2*pnb+png+i] = G.h_lam[oLm+2*nbn+ngn+i];
+			t[n][2*pnb+i] = G.h_t[oLm+2*nbn+i]; t[n][2*pnb+png+i] = G.h_t[oLm+2*nbn+ngn+i];
 			}
 		}
 	pthread_mutex_unlock(&g_lock);
@@ -397,13 +495,18 @@ int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *n
 
 static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb,
 		int *ng, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q,
-		double **r, double **lb, double **ub, double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *stat)
+		double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
+		double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *stat)
 	{
 	int n, i, j, l, status;
 	const double alpha_min = 1e-8;       /* c_order_interface.c:141 */
 	pthread_mutex_lock(&g_lock);
 	if(ctx_get(N, nx, nu, nb, hidxb, ng, k_max)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU context unavailable\n"); return -1; }
 	hpmpc_b200_pack_instance(G.ocp, c_order, A, B, b, Q, S, R, q, r, lb, ub, G.h_in);
+	/* general constraints: [D C]' per stage.  (The reference's c_order wrapper transposes C[N] once more than the other stages,
+	 * interfaces/c/c_order_interface.c:283 against :279-280 and fortran_order_interface.c:283 -- visible only for a non-symmetric
+	 * C[N]; here both orders mean the same matrix, see INTEGRATION.md.) */
+	if(G.sz.lam_stride>0 && C && D && lg && ug) hpmpc_b200_pack_general(G.ocp, c_order, C, D, lg, ug, G.h_in);
 	/* mu0 estimate when the caller passes mu0 <= 0: signed maximum over the cost entries
 	 * (c_order_interface.c:318-331 / fortran_order_interface.c:318-331) */
 	if(mu0<=0)
@@ -446,8 +549,8 @@ int c_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int 
 		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
 		double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)N2; (void)C; (void)D; (void)lg; (void)ug; (void)work0;
-	return high_level(1, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, x, u, pi, lam, inf_norm_res, stat);
+	(void)N2; (void)work0;
+	return high_level(1, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat);
 	}
 
 int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb, int *ng,
@@ -455,6 +558,6 @@ int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol
 		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
 		double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)N2; (void)C; (void)D; (void)lg; (void)ug; (void)work0;
-	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, x, u, pi, lam, inf_norm_res, stat);
+	(void)N2; (void)work0;
+	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat);
 	}

@@ -9,7 +9,8 @@
 
 enum { CV_LB=0, CV_UB, CV_LAM_LO, CV_LAM_UP, CV_T_LO, CV_T_UP, CV_DLAM_LO, CV_DLAM_UP, CV_DT_LO, CV_DT_UP,
        CV_TINV_LO, CV_TINV_UP, CV_LAMT_LO, CV_LAMT_UP, CV_QXD /* "Qx": Hessian diagonal term */,
-       CV_QXG /* "qx": gradient term */, CV_RD_LO, CV_RD_UP, CV_RM_LO, CV_RM_UP, CV_COUNT };
+       CV_QXG /* "qx": gradient term */, CV_RD_LO, CV_RD_UP, CV_RM_LO, CV_RM_UP,
+       CV_VAL /* values [D C] ux of the general constraints (box constraints read ux[c_ux] directly) */, CV_COUNT };
 
 struct hb_ipm_ws
 	{
@@ -44,6 +45,40 @@ __device__ __forceinline__ double hb_warp_sum(double v)
 	return v;
 	}
 
+/* Value of constraint cc for the vector v (ux layout): the bounded variable itself for a box constraint, ([D C] v)_j for a
+ * general one -- the latter precomputed into CV_VAL by hb_gen_values (the reference's dgemv_t on pDCt,
+ * mpc_solvers/c99/d_aux_ip_hard_lib4.c:135,570,...; libstr twin c99/d_aux_ip_hard_libstr.c:125,329) */
+__device__ __forceinline__ double hb_cval(const hb_dims &d, const hb_ipm_ws &w, const double *v, int cc)
+	{
+	const int iu = d.c_ux[cc];
+	return iu>=0 ? v[iu] : w.v(CV_VAL)[cc];
+	}
+/* CV_VAL <- [D C]_n v_n for every general constraint; thread tid of `stride` cooperating threads; nothing to do when ngtot = 0 */
+__device__ __forceinline__ void hb_gen_values_part(int tid, int stride, const hb_dims &d, const double *__restrict__ in_inst, const hb_ipm_ws &w, const double *v)
+	{
+	if(d.ngtot==0 || d.st==nullptr) return;
+	for(int n=0; n<=d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		if(s.ng==0) continue;
+		const int nux = s.nu+s.nx;
+		const double *G = in_inst + s.off_DCt;
+		for(int j=tid; j<s.ng; j+=stride)
+			{
+			double acc = 0.0;
+			for(int i=0; i<nux; i++) acc += G[i*s.ng+j]*v[s.off_ux+i];
+			w.v(CV_VAL)[s.off_c+s.nb+j] = acc;
+			}
+		}
+	}
+__device__ __forceinline__ void hb_gen_values(int lane, const hb_dims &d, const double *__restrict__ in_inst, const hb_ipm_ws &w, const double *v)
+	{
+	if(d.ngtot==0) return;
+	__syncwarp();
+	hb_gen_values_part(lane, 32, d, in_inst, w, v);
+	__syncwarp();
+	}
+
 /* bound part of the residuals: res_d, res_m and their sum (mpc_solvers/c99/d_res_ip_res_hard.c:39-319) */
 /* _part: thread tid of `stride` cooperating threads, partial results (the caller reduces) */
 __device__ __forceinline__ void hb_ipm_residuals_bounds_part(int tid, int stride, const hb_dims &d, const hb_ipm_ws &w, const double *ux, double &mu2, double &nd)
@@ -52,7 +87,7 @@ __device__ __forceinline__ void hb_ipm_residuals_bounds_part(int tid, int stride
 	mu2 = 0.0; nd = 0.0;
 	for(int cc=tid; cc<d.nbtot; cc+=stride)
 		{
-		double u = ux[d.c_ux[cc]];
+		double u = hb_cval(d, w, ux, cc);
 		double rdl = w.v(CV_LB)[cc] - u + t_lo[cc];
 		double rdu = w.v(CV_UB)[cc] - u - t_up[cc];
 		double rml = lam_lo[cc]*t_lo[cc], rmu = lam_up[cc]*t_up[cc];
@@ -75,7 +110,7 @@ __device__ __forceinline__ double hb_ipm_alpha_part(int tid, int stride, const h
 	double alpha = 1.0;
 	for(int cc=tid; cc<d.nbtot; cc+=stride)
 		{
-		double du = dux[d.c_ux[cc]];
+		double du = hb_cval(d, w, dux, cc);
 		double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc], tl = w.v(CV_T_LO)[cc], tu = w.v(CV_T_UP)[cc];
 		double dtl, dtu, dll, dlu;
 		if(!RES)

@@ -29,9 +29,10 @@ __device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const double
 	const int lane = c.lane;
 	double nq = 0.0, nb_ = 0.0, nd = 0.0, mu2 = 0.0;
 	const double *lam_lo = w.v(CV_LAM_LO), *lam_up = w.v(CV_LAM_UP), *t_lo = w.v(CV_T_LO), *t_up = w.v(CV_T_UP);
+	hb_gen_values(lane, d, in_inst, w, ux);
 	for(int cc=lane; cc<d.nbtot; cc+=32)
 		{
-		double u = ux[d.c_ux[cc]];
+		double u = hb_cval(d, w, ux, cc);
 		double rdl = w.v(CV_LB)[cc] - u + t_lo[cc];
 		double rdu = w.v(CV_UB)[cc] - u - t_up[cc];
 		double rml = lam_lo[cc]*t_lo[cc], rmu = lam_up[cc]*t_up[cc];
@@ -63,6 +64,20 @@ __device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const double
 		for(int j=lane; j<s.nb; j+=32)
 			w.res_q[s.off_ux+d.idxb[s.off_c+j]] += -lam_lo[s.off_c+j] + lam_up[s.off_c+j];
 		__syncwarp();
+		if(s.ng>0)
+			{
+			/* general constraints: + [D C]' (lam_ug - lam_lg)  (mpc_solvers/c99/d_res_ip_res_hard.c:120-144 twin of
+			 * d_res_ip_res_hard_libstr.c:120-144) */
+			const double *G = in_inst + s.off_DCt;
+			const int cg = s.off_c + s.nb;
+			for(int i=lane; i<nux; i+=32)
+				{
+				double acc = w.res_q[s.off_ux+i];
+				for(int j=0; j<s.ng; j++) acc += G[i*s.ng+j]*(lam_up[cg+j] - lam_lo[cg+j]);
+				w.res_q[s.off_ux+i] = acc;
+				}
+			__syncwarp();
+			}
 		for(int i=lane; i<nux; i+=32)
 			{
 			double acc = w.res_q[s.off_ux+i];
@@ -108,6 +123,11 @@ __device__ __forceinline__ void hb_ipm_extract_chain(int lane, const hb_dims &d,
 			w.v(CV_LB)[s.off_c+j] = in_inst[s.off_d+j];
 			w.v(CV_UB)[s.off_c+j] = in_inst[s.off_d+s.nb+j];
 			}
+		for(int j=lane; j<s.ng; j+=32)
+			{
+			w.v(CV_LB)[s.off_c+s.nb+j] = in_inst[s.off_dg+j];
+			w.v(CV_UB)[s.off_c+s.nb+j] = in_inst[s.off_dg+s.ng+j];
+			}
 		}
 	}
 
@@ -121,6 +141,13 @@ __device__ __forceinline__ void hb_ipm_emit_chain(int lane, const hb_dims &d, co
 			{
 			lam[2*s.off_c+j] = w.v(CV_LAM_LO)[s.off_c+j]; lam[2*s.off_c+s.nb+j] = w.v(CV_LAM_UP)[s.off_c+j];
 			tt[2*s.off_c+j] = w.v(CV_T_LO)[s.off_c+j]; tt[2*s.off_c+s.nb+j] = w.v(CV_T_UP)[s.off_c+j];
+			}
+		/* general constraints follow the bounds: [lb ub lg ug] per stage, the lib4 order (interfaces/c/c_order_interface.c:662-681) */
+		for(int j=lane; j<s.ng; j+=32)
+			{
+			const int o = 2*s.off_c + 2*s.nb, cg = s.off_c + s.nb + j;
+			lam[o+j] = w.v(CV_LAM_LO)[cg]; lam[o+s.ng+j] = w.v(CV_LAM_UP)[cg];
+			tt[o+j] = w.v(CV_T_LO)[cg]; tt[o+s.ng+j] = w.v(CV_T_UP)[cg];
 			}
 		}
 	}
@@ -350,6 +377,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 			for(int cc=lane; cc<d.nbtot; cc+=32)
 				{
 				const int iu = d.c_ux[cc];
+				if(iu<0) continue;                                    /* general constraint: below */
 				double lb = w.v(CV_LB)[cc], ub = w.v(CV_UB)[cc], u = ux[iu];
 				double tl = -lb + u, tu = ub - u;
 				if(tl<thr0)
@@ -362,6 +390,21 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				w.v(CV_LAM_LO)[cc] = mu0/tl; w.v(CV_LAM_UP)[cc] = mu0/tu;
 				}
 			__syncwarp();
+			if(d.ngtot>0)
+				{
+				/* general constraints, from the ux the bounds have just moved: t = max(thr0, +-([D C] ux - d)), no projection
+				 * (c99/d_aux_ip_hard_lib4.c:121-147) */
+				hb_gen_values(lane, d, in_inst, w, ux);
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					if(d.c_ux[cc]>=0) continue;
+					const double v = w.v(CV_VAL)[cc];
+					const double tl = fmax(thr0, v - w.v(CV_LB)[cc]), tu = fmax(thr0, -v + w.v(CV_UB)[cc]);
+					w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
+					w.v(CV_LAM_LO)[cc] = mu0/tl; w.v(CV_LAM_UP)[cc] = mu0/tu;
+					}
+				__syncwarp();
+				}
 			mu = mu0;
 			const double mu_tol_low = mu_tol<1e-5 ? 1e-5 : mu_tol;
 
@@ -389,6 +432,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				S::forward_sv(c, d, in_inst, w, nullptr, w.dux, w.dpi);
 				HBF_STAMP(302);
 				__syncwarp();
+				hb_gen_values(lane, d, in_inst, w, w.dux);
 				alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
@@ -412,6 +456,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				S::trs(c, d, in_inst, w, w.b0, w.rq0, w.v(CV_QXG));
 				HBF_STAMP(304);
 				__syncwarp();
+				hb_gen_values(lane, d, in_inst, w, w.dux);
 				alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
@@ -457,6 +502,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				S::forward_sv(c, d, in_inst, w, w.res_b, w.dux, w.dpi);
 				HBF_STAMP(302);
 				__syncwarp();
+				hb_gen_values(lane, d, in_inst, w, w.dux);
 				alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
@@ -481,6 +527,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				S::trs(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXG));
 				HBF_STAMP(304);
 				__syncwarp();
+				hb_gen_values(lane, d, in_inst, w, w.dux);
 				alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
 				__syncwarp();
 				if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
@@ -599,6 +646,7 @@ __global__ void __launch_bounds__(256) hb_kkt_new_rhs_kernel(hb_dims d, long lon
 			S::trs_newb(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXG));
 			__syncwarp();
 			/* dt, dlam (:2236) and the full step (:2239) */
+			hb_gen_values(lane, d, in_inst, w, w.dux);
 			(void)hb_ipm_alpha<true>(lane, d, w, w.dux);
 			__syncwarp();
 			for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += 1.0*w.dux[i];

@@ -11,7 +11,9 @@ template<typename K>
 static int hb_prep(K kernel, int smem)
 	{
 	if(smem>227*1024) { fprintf(stderr, "hpmpc_b200: stage too large for shared memory (%d bytes)\n", smem); return -1; }
-	HB_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	/* always the architectural maximum, not this launch's size: the attribute is per kernel and device, and concurrent host
+	 * threads launching the same kernel with different CTA shapes must not lower it under each other */
+	HB_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
 	return 0;
 	}
 

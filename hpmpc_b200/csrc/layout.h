@@ -8,7 +8,10 @@
  *                    [ RSQrq_n ] packed lower triangle by rows of the (nux+1) x nux trapezoid
  *                                [R S';S Q ; r' q'] : row i holds columns 0..min(i,nux-1),
  *                                element (i,k) at i*(i+1)/2 + k ; row nux (gradient) has nux entries
- *                    [ d_n ]     lb (nb) then ub (nb)
+ *   then, behind the matrices of all stages (so that the stride between the stage matrices does not depend on nb / ng):
+ *   for n = 0..N :   [ d_n ]     lb (nb) then ub (nb)
+ *                    [ DCt_n ]   [D C]'_n, (nu_n+nx_n) x ng_n row-major          (general constraints lg <= D u + C x <= ug)
+ *                    [ dg_n ]    lg (ng) then ug (ng)
  *   every sub-block starts on a 16-byte boundary (sizes padded to an even number of doubles) so a
  *   stage can be moved with 16-byte vector loads or a 1-D bulk (TMA) copy.
  *
@@ -35,7 +38,10 @@ typedef struct hb_stage
 	int off_pi;                 /* into pi-like vectors, edge n -> length nx1 */
 	int off_c;                  /* constraint offset: sum of nb over earlier stages */
 	int off_L;                  /* into the factor stash: packed L_n then dinv_n */
-	int pad;
+	int ng;                     /* general constraints lg <= D u + C x <= ug of the stage (0: none) */
+	int off_DCt;                /* [D C]' of the stage: (nu+nx) x ng row-major, in the instance input block */
+	int off_dg;                 /* lg (ng) then ug (ng), in the instance input block */
+	int pad0, pad1;
 	} hb_stage;
 
 typedef struct hb_dims
@@ -43,7 +49,8 @@ typedef struct hb_dims
 	int N;
 	int nzM;                    /* max over stages of nu+nx+1 */
 	int nxM;                    /* max over stages of nx      */
-	int nbtot;                  /* sum of nb                  */
+	int nbtot;                  /* constraints per instance: sum of nb + ng ; stage n owns [off_c, off_c+nb+ng): box first, then general */
+	int ngtot;                  /* sum of ng (0: box constraints only, the fast paths) */
 	long long in_stride;        /* doubles per instance: inputs        */
 	long long ux_stride;        /* doubles per instance: ux            */
 	long long pi_stride;        /* doubles per instance: pi / Pb / b   */
@@ -105,10 +112,10 @@ typedef struct hb_tail_tab
 
 /* launchers implemented in ric_kernels.cu ; all pointers are device pointers, stream is a cudaStream_t */
 int hb_launch_ric_sv(const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi, double *Pb,
-		double *stash, int n_slots, int grid, int warps, void *stream);
-int hb_launch_ric_trf(const hb_dims *dims, long long n_inst, const double *in, double *L, int grid, int warps, void *stream);
+		double *stash, int n_slots, int grid, int warps, void *stream, const double *Qx, const double *qx);
+int hb_launch_ric_trf(const hb_dims *dims, long long n_inst, const double *in, double *L, int grid, int warps, void *stream, const double *Qx);
 int hb_launch_ric_trs(const hb_dims *dims, long long n_inst, const double *in, const double *L, double *ux, double *pi,
-		double *work, int n_slots, int grid, int warps, void *stream);
+		double *work, int n_slots, int grid, int warps, void *stream, const double *qx);
 int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
 		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
 		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream);

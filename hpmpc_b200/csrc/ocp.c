@@ -21,7 +21,7 @@ struct hpmpc_b200_ocp
 	{
 	int device;
 	int N;
-	int *nx, *nu, *nb;       /* [N+1] */
+	int *nx, *nu, *nb, *ng;  /* [N+1] */
 	int **idxb;              /* [N+1] */
 	hb_stage *st;            /* host copy [N+1] */
 	int *h_idxb, *h_cux;     /* flat [nbtot] */
@@ -40,6 +40,9 @@ struct hpmpc_b200_ocp
 	/* scratch (device), grown on demand */
 	double *scratch; size_t scratch_bytes;
 	int *counter;
+	/* one call in flight per handle: every device entry point makes its stream wait for the previous call's work (the calls share
+	 * the scratch slots and the queue counter), so calls on different streams are serialised instead of racing */
+	cudaEvent_t ev_busy; int busy_valid;
 	/* staging for the host-buffer entry points */
 	cudaStream_t s_copy[2], s_comp;
 	cudaEvent_t ev_in[2], ev_done[2];
@@ -133,66 +136,97 @@ static void trf_launch(hpmpc_b200_ocp *p)
 	p->tf_warps = warps; p->tf_grid = p->sms*per_sm;
 	}
 
-int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, int device)
+static void free_host_side(hpmpc_b200_ocp *p)
 	{
-	int n, j;
+	int n;
+	if(p->idxb) for(n=0; n<=p->N; n++) free(p->idxb[n]);
+	free(p->idxb); free(p->nx); free(p->nu); free(p->nb); free(p->ng); free(p->st); free(p->h_idxb); free(p->h_cux);
+	}
+
+/* all stage matrices first, then the constraint data of all stages: the distance between the matrices of consecutive stages
+ * does not depend on nb / ng, which is what the size-specialised kernels' affine stage addressing relies on */
+int hpmpc_b200_ocp_create_gen(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb,
+		const int *ng, int device)
+	{
+	int n, j, rc = -2;
 	*out = NULL;
 	if(N<1) { fprintf(stderr, "hpmpc_b200: N must be >= 1\n"); return -2; }
 	hpmpc_b200_ocp *p = (hpmpc_b200_ocp*)calloc(1, sizeof(*p));
-	p->device = device; p->N = N;
-	p->nx = malloc((N+1)*sizeof(int)); p->nu = malloc((N+1)*sizeof(int)); p->nb = malloc((N+1)*sizeof(int));
+	if(!p) return -1;
+	p->device = -1;                      /* until the device side exists: the error path frees host memory only */
+	p->N = N;
+	p->nx = malloc((N+1)*sizeof(int)); p->nu = malloc((N+1)*sizeof(int)); p->nb = malloc((N+1)*sizeof(int)); p->ng = malloc((N+1)*sizeof(int));
 	p->idxb = calloc(N+1, sizeof(int*));
 	p->st = calloc(N+1, sizeof(hb_stage));
-	int nbtot = 0, nzM = 1, nxM = 1;
+	if(!p->nx || !p->nu || !p->nb || !p->ng || !p->idxb || !p->st) { rc = -1; goto fail; }
+	int nctot = 0, ngtot = 0, nzM = 1, nxM = 1;
 	for(n=0; n<=N; n++)
 		{
-		p->nx[n] = nx[n]; p->nu[n] = n<N ? nu[n] : 0; p->nb[n] = nb ? nb[n] : 0;
+		p->nx[n] = nx[n]; p->nu[n] = n<N ? nu[n] : 0; p->nb[n] = nb ? nb[n] : 0; p->ng[n] = ng ? ng[n] : 0;
+		if(p->nx[n]<0 || p->nu[n]<0 || p->nb[n]<0 || p->ng[n]<0) { fprintf(stderr, "hpmpc_b200: stage %d: negative size\n", n); goto fail; }
 		if(p->nb[n]>p->nu[n]+p->nx[n])
 			{
 			/* the reference prints this and exit(1)s (c_order_interface.c:103-110); we return an error */
 			fprintf(stderr, "hpmpc_b200: stage %d: nb=%d larger than nu+nx=%d\n", n, p->nb[n], p->nu[n]+p->nx[n]);
-			return -2;
+			goto fail;
 			}
-		nbtot += p->nb[n];
+		if(p->nb[n]>0 && (hidxb==NULL || hidxb[n]==NULL)) { fprintf(stderr, "hpmpc_b200: stage %d: nb=%d but no idxb\n", n, p->nb[n]); goto fail; }
+		nctot += p->nb[n]+p->ng[n]; ngtot += p->ng[n];
 		if(p->nu[n]+p->nx[n]+1>nzM) nzM = p->nu[n]+p->nx[n]+1;
 		if(p->nx[n]>nxM) nxM = p->nx[n];
 		}
-	p->h_idxb = malloc((nbtot+1)*sizeof(int)); p->h_cux = malloc((nbtot+1)*sizeof(int));
+	p->h_idxb = malloc((nctot+1)*sizeof(int)); p->h_cux = malloc((nctot+1)*sizeof(int));
+	if(!p->h_idxb || !p->h_cux) { rc = -1; goto fail; }
 	long long o_in = 0, o_ux = 0, o_pi = 0, o_L = 0; int o_c = 0;
 	for(n=0; n<=N; n++)
 		{
 		hb_stage *s = &p->st[n];
 		int nux = p->nu[n]+p->nx[n];
-		s->nx = p->nx[n]; s->nu = p->nu[n]; s->nb = p->nb[n]; s->nx1 = n<N ? p->nx[n+1] : 0;
+		s->nx = p->nx[n]; s->nu = p->nu[n]; s->nb = p->nb[n]; s->ng = p->ng[n]; s->nx1 = n<N ? p->nx[n+1] : 0;
 		s->off_BAbt = (int)o_in; o_in += HB_EVEN((nux+1)*s->nx1);
 		s->off_RSQ = (int)o_in;  o_in += HB_EVEN(HB_TRI(nux)+nux);
-		s->off_d = (int)o_in;    o_in += HB_EVEN(2*s->nb);
 		s->off_ux = (int)o_ux;   o_ux += nux;
 		s->off_pi = (int)o_pi;   o_pi += s->nx1;
 		s->off_c = o_c;
 		s->off_L = (int)o_L;     o_L += HB_EVEN(HB_TRI(nux)+2*nux);
 		p->idxb[n] = malloc((s->nb+1)*sizeof(int));
+		if(!p->idxb[n]) { rc = -1; goto fail; }
 		for(j=0; j<s->nb; j++)
 			{
 			int id = hidxb[n][j];
-			if(id<0 || id>=nux) { fprintf(stderr, "hpmpc_b200: stage %d: idxb[%d]=%d out of range\n", n, j, id); return -2; }
+			if(id<0 || id>=nux) { fprintf(stderr, "hpmpc_b200: stage %d: idxb[%d]=%d out of range\n", n, j, id); goto fail; }
 			p->idxb[n][j] = id;
 			p->h_idxb[o_c+j] = id;
 			p->h_cux[o_c+j] = s->off_ux + id;
 			}
-		o_c += s->nb;
+		for(j=0; j<s->ng; j++) { p->h_idxb[o_c+s->nb+j] = -1; p->h_cux[o_c+s->nb+j] = -1; }     /* general: value = (DCt' ux)_j */
+		o_c += s->nb+s->ng;
 		}
-	p->dims.N = N; p->dims.nzM = nzM; p->dims.nxM = nxM; p->dims.nbtot = nbtot;
+	for(n=0; n<=N; n++)
+		{
+		hb_stage *s = &p->st[n];
+		int nux = p->nu[n]+p->nx[n];
+		s->off_d = (int)o_in;    o_in += HB_EVEN(2*s->nb);
+		s->off_DCt = (int)o_in;  o_in += HB_EVEN(nux*s->ng);
+		s->off_dg = (int)o_in;   o_in += HB_EVEN(2*s->ng);
+		}
+	p->dims.N = N; p->dims.nzM = nzM; p->dims.nxM = nxM; p->dims.nbtot = nctot; p->dims.ngtot = ngtot;
 	p->dims.in_stride = o_in; p->dims.ux_stride = HB_EVEN(o_ux); p->dims.pi_stride = HB_EVEN(o_pi); p->dims.L_stride = o_L;
-	p->lam_stride = 2*(long long)nbtot;
-	if(nzM>64) { fprintf(stderr, "hpmpc_b200: nu+nx+1 = %d > 64 is not supported yet\n", nzM); return -2; }
+	p->lam_stride = 2*(long long)nctot;
+	if(nzM>64) { fprintf(stderr, "hpmpc_b200: nu+nx+1 = %d > 64 is not supported yet\n", nzM); goto fail; }
 
-	p->fast_id = getenv("HPMPC_B200_NO_FAST") ? -1 : hb_fast_variant(N, p->nx, p->nu);
+	/* size-specialised kernels: chosen from (N, nx, nu) and only when the stage matrices sit at an affine stride (true by
+	 * construction of the layout above; checked because the kernels compute off(n) = off(1) + (n-1)*stride) and no general
+	 * constraints are present */
+	int affine = 1;
+	for(n=2; n<N; n++) if(p->st[n].off_BAbt != p->st[1].off_BAbt + (n-1)*(p->st[2].off_BAbt-p->st[1].off_BAbt)) affine = 0;
+	const int fast_ok = affine && ngtot==0;
+	p->fast_id = (getenv("HPMPC_B200_NO_FAST") || !fast_ok) ? -1 : hb_fast_variant(N, p->nx, p->nu);
 	if(p->fast_id>=0) hb_fast_info(p->fast_id, N, &p->f_ipw, &p->f_smem_warp, &p->f_stash_inst);
-	p->ipm_fast_id = hb_ipm_fast_variant(N, p->nx, p->nu, nbtot);
+	p->ipm_fast_id = fast_ok ? hb_ipm_fast_variant(N, p->nx, p->nu, nctot) : -1;
 	p->i_L_doubles = p->dims.L_stride;
 	if(p->ipm_fast_id>=0) hb_ipm_fast_info(p->ipm_fast_id, N, &p->i_smem_warp, &p->i_L_doubles);
-	p->tf_id = hb_ric_shape_variant(N, p->nx, p->nu);
+	p->tf_id = fast_ok ? hb_ric_shape_variant(N, p->nx, p->nu) : -1;
 	if(p->tf_id>=0)
 		{
 		/* the factor of trf / trs is kept in the sweeps' column-packed form: the L_stride reported to callers makes room for it */
@@ -212,34 +246,53 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 		*out = p;
 		return 0;
 		}
-	CK(cudaSetDevice(device));
-	hb_stage *d_st; int *d_idxb, *d_cux;
-	CK(cudaMalloc((void**)&d_st, (N+1)*sizeof(hb_stage)));
-	CK(cudaMalloc((void**)&d_idxb, (nbtot+1)*sizeof(int)));
-	CK(cudaMalloc((void**)&d_cux, (nbtot+1)*sizeof(int)));
-	CK(cudaMemcpy(d_st, p->st, (N+1)*sizeof(hb_stage), cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(d_idxb, p->h_idxb, (nbtot+1)*sizeof(int), cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(d_cux, p->h_cux, (nbtot+1)*sizeof(int), cudaMemcpyHostToDevice));
-	p->dims.st = d_st; p->dims.idxb = d_idxb; p->dims.c_ux = d_cux;
-	CK(cudaMalloc((void**)&p->counter, 64));
+	rc = -1;
+	if(cudaSetDevice(device)!=cudaSuccess) { fprintf(stderr, "hpmpc_b200: no CUDA device %d\n", device); goto fail; }
 	p->sms = hb_device_sm_count(device);
-	if(p->sms<=0) { fprintf(stderr, "hpmpc_b200: no CUDA device %d\n", device); return -1; }
+	if(p->sms<=0) { fprintf(stderr, "hpmpc_b200: no CUDA device %d\n", device); goto fail; }
+	p->device = device;                  /* from here on the error path is hpmpc_b200_ocp_destroy (frees whatever exists) */
+	{
+	hb_stage *d_st = NULL; int *d_idxb = NULL, *d_cux = NULL;
+	if(cudaMalloc((void**)&d_st, (N+1)*sizeof(hb_stage))!=cudaSuccess) goto fail_dev;
+	p->dims.st = d_st;
+	if(cudaMalloc((void**)&d_idxb, (nctot+1)*sizeof(int))!=cudaSuccess) goto fail_dev;
+	p->dims.idxb = d_idxb;
+	if(cudaMalloc((void**)&d_cux, (nctot+1)*sizeof(int))!=cudaSuccess) goto fail_dev;
+	p->dims.c_ux = d_cux;
+	if(cudaMemcpy(d_st, p->st, (N+1)*sizeof(hb_stage), cudaMemcpyHostToDevice)!=cudaSuccess
+	|| cudaMemcpy(d_idxb, p->h_idxb, (nctot+1)*sizeof(int), cudaMemcpyHostToDevice)!=cudaSuccess
+	|| cudaMemcpy(d_cux, p->h_cux, (nctot+1)*sizeof(int), cudaMemcpyHostToDevice)!=cudaSuccess
+	|| cudaMalloc((void**)&p->counter, 64)!=cudaSuccess
+	|| cudaEventCreateWithFlags(&p->ev_busy, cudaEventDisableTiming)!=cudaSuccess) goto fail_dev;
+	}
 	default_launch(p, 0, 0);
 	fast_launch(p, 0, 0);
 	ipm_launch(p);
 	trf_launch(p);
 	*out = p;
 	return 0;
+fail_dev:
+	fprintf(stderr, "hpmpc_b200: device allocation failed (%s)\n", cudaGetErrorString(cudaGetLastError()));
+	hpmpc_b200_ocp_destroy(p);
+	return -1;
+fail:
+	free_host_side(p);
+	free(p);
+	return rc;
+	}
+
+int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, int device)
+	{
+	return hpmpc_b200_ocp_create_gen(out, N, nx, nu, nb, hidxb, NULL, device);
 	}
 
 void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p)
 	{
-	int n, k;
+	int k;
 	if(!p) return;
 	if(p->device<0)
 		{
-		for(n=0; n<=p->N; n++) free(p->idxb[n]);
-		free(p->idxb); free(p->nx); free(p->nu); free(p->nb); free(p->st); free(p->h_idxb); free(p->h_cux);
+		free_host_side(p);
 		free(p);
 		return;
 		}
@@ -256,14 +309,22 @@ void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p)
 	if(p->s_comp) cudaStreamDestroy(p->s_comp);
 	if(p->scratch) cudaFree(p->scratch);
 	if(p->counter) cudaFree(p->counter);
-	cudaFree((void*)p->dims.st); cudaFree((void*)p->dims.idxb); cudaFree((void*)p->dims.c_ux);
-	for(n=0; n<=p->N; n++) free(p->idxb[n]);
-	free(p->idxb); free(p->nx); free(p->nu); free(p->nb); free(p->st); free(p->h_idxb); free(p->h_cux);
+	if(p->ev_busy) cudaEventDestroy(p->ev_busy);
+	if(p->dims.st) cudaFree((void*)p->dims.st);
+	if(p->dims.idxb) cudaFree((void*)p->dims.idxb);
+	if(p->dims.c_ux) cudaFree((void*)p->dims.c_ux);
+	free_host_side(p);
 	free(p);
 	}
 
 int hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_cta)
 	{
+	/* every kernel of this library is compiled with __launch_bounds__(256): at most 8 warps per CTA */
+	if(warps_per_cta>8)
+		{
+		fprintf(stderr, "hpmpc_b200: set_launch: %d warps per CTA requested, the kernels take at most 8 -- rejected\n", warps_per_cta);
+		return -3;
+		}
 	if(p->fast_id>=0)
 		{
 		/* the launch shape of the size-specialised kernel is what matters for this pattern */
@@ -303,6 +364,15 @@ void hpmpc_b200_ocp_stage_offsets(const hpmpc_b200_ocp *p, int n, int *off_BAbt,
 	if(off_L) *off_L = s->off_L;
 	}
 
+void hpmpc_b200_ocp_general_offsets(const hpmpc_b200_ocp *p, int n, int *ng, int *off_DCt, int *off_dg, int *off_c)
+	{
+	const hb_stage *s = &p->st[n];
+	if(ng) *ng = s->ng;
+	if(off_DCt) *off_DCt = s->off_DCt;
+	if(off_dg) *off_dg = s->off_dg;
+	if(off_c) *off_c = s->off_c;
+	}
+
 /* element (i,j) of an m x n matrix with leading dimension ld given in column- or row-major order */
 #define EL(M, i, j, rows, cols, c_order) ((c_order) ? (M)[(size_t)(i)*(cols)+(j)] : (M)[(i)+(size_t)(j)*(rows)])
 
@@ -338,6 +408,25 @@ int hpmpc_b200_pack_instance(const hpmpc_b200_ocp *p, int c_order, double *const
 	return 0;
 	}
 
+/* general constraints lg <= D u + C x <= ug of one instance into its block: C[n] ng x nx, D[n] ng x nu (n < N), row- or
+ * column-major like the other matrices; stored as [D C]'_n (interfaces/c/fortran_order_interface.c:276-283) */
+int hpmpc_b200_pack_general(const hpmpc_b200_ocp *p, int c_order, double *const *C, double *const *D, double *const *lg,
+		double *const *ug, double *blk)
+	{
+	int n, i, j;
+	for(n=0; n<=p->N; n++)
+		{
+		const hb_stage *s = &p->st[n];
+		const int nx = s->nx, nu = s->nu, ng = s->ng;
+		if(ng==0) continue;
+		double *G = blk + s->off_DCt;                          /* (nu+nx) x ng row-major */
+		for(i=0; i<nu; i++) for(j=0; j<ng; j++) G[i*ng+j] = EL(D[n], j, i, ng, nu, c_order);
+		for(i=0; i<nx; i++) for(j=0; j<ng; j++) G[(nu+i)*ng+j] = EL(C[n], j, i, ng, nx, c_order);
+		for(j=0; j<ng; j++) { blk[s->off_dg+j] = lg[n][j]; blk[s->off_dg+ng+j] = ug[n][j]; }
+		}
+	return 0;
+	}
+
 void hpmpc_b200_unpack_solution(const hpmpc_b200_ocp *p, const double *ux, const double *pi, const double *lam,
 		double **x, double **u, double **pi_out, double **lam_out)
 	{
@@ -348,13 +437,27 @@ void hpmpc_b200_unpack_solution(const hpmpc_b200_ocp *p, const double *ux, const
 		if(u && n<p->N) for(i=0; i<s->nu; i++) u[n][i] = ux[s->off_ux+i];
 		if(x) for(i=0; i<s->nx; i++) x[n][i] = ux[s->off_ux+s->nu+i];
 		if(pi_out && pi && n<p->N) for(i=0; i<s->nx1; i++) pi_out[n][i] = pi[s->off_pi+i];
-		if(lam_out && lam) for(i=0; i<2*s->nb; i++) lam_out[n][i] = lam[2*s->off_c+i];
+		if(lam_out && lam) for(i=0; i<2*(s->nb+s->ng); i++) lam_out[n][i] = lam[2*s->off_c+i];
 		}
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
 /* device-pointer entry points                                                                       */
 /* ------------------------------------------------------------------------------------------------ */
+/* one call in flight per handle (see ev_busy): the stream of a new call first waits for the previous call's work */
+static int call_begin(hpmpc_b200_ocp *p, void *stream)
+	{
+	if(p->busy_valid) CK(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_busy, 0));
+	return 0;
+	}
+static int call_end(hpmpc_b200_ocp *p, void *stream, int rc)
+	{
+	if(rc) return rc;
+	CK(cudaEventRecord(p->ev_busy, (cudaStream_t)stream));
+	p->busy_valid = 1;
+	return 0;
+	}
+
 static int grid_for(const hpmpc_b200_ocp *p, long long n_inst)
 	{
 	long long need = (n_inst + p->warps - 1)/p->warps;
@@ -364,49 +467,75 @@ static int grid_for(const hpmpc_b200_ocp *p, long long n_inst)
 int hpmpc_b200_d_back_ric_rec_sv_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in,
 		double *d_ux, double *d_pi, double *d_Pb, void *stream)
 	{
-	if(n_inst<=0) return 0;
-	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
-	CK(cudaSetDevice(p->device));
-	if(p->fast_id>=0 && d_Pb==NULL)
-		{
-		long long groups = (n_inst + p->f_ipw - 1)/p->f_ipw, need = (groups + p->f_warps - 1)/p->f_warps;
-		int grid = (int)(need<p->f_grid ? need : p->f_grid);
-		if(ensure_scratch(p, sizeof(double)*(size_t)p->f_grid*p->f_warps*p->f_ipw*p->f_stash_inst)) return -1;
-		return hb_launch_ric_sv_fast(p->fast_id, &p->dims, n_inst, d_in, d_ux, d_pi, p->scratch, grid, p->f_warps, stream);
-		}
-	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*p->dims.L_stride)) return -1;
-	return hb_launch_ric_sv(&p->dims, n_inst, d_in, d_ux, d_pi, d_Pb, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
+	return hpmpc_b200_d_back_ric_rec_sv_upd_batch(p, n_inst, d_in, NULL, NULL, d_ux, d_pi, d_Pb, stream);
 	}
 
-int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_L, void *stream)
+/* the same with the reference's Qx / qx arguments (d_back_ric_rec.c:112): per-constraint terms added to the Hessian diagonal and
+ * to the gradient row -- for general constraints through [D C]' -- nbtot doubles per instance each, either may be NULL */
+int hpmpc_b200_d_back_ric_rec_sv_upd_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_Qx, const double *d_qx,
+		double *d_ux, double *d_pi, double *d_Pb, void *stream)
 	{
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
+	if(call_begin(p, stream)) return -1;
+	if(p->fast_id>=0 && d_Pb==NULL && d_Qx==NULL && d_qx==NULL)
+		{
+		long long groups = (n_inst + p->f_ipw - 1)/p->f_ipw, need = (groups + p->f_warps - 1)/p->f_warps;
+		int grid = (int)(need<p->f_grid ? need : p->f_grid);
+		if(ensure_scratch(p, sizeof(double)*(size_t)p->f_grid*p->f_warps*p->f_ipw*p->f_stash_inst)) return -1;
+		return call_end(p, stream, hb_launch_ric_sv_fast(p->fast_id, &p->dims, n_inst, d_in, d_ux, d_pi, p->scratch, grid, p->f_warps, stream));
+		}
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*p->dims.L_stride)) return -1;
+	return call_end(p, stream, hb_launch_ric_sv(&p->dims, n_inst, d_in, d_ux, d_pi, d_Pb, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream, d_Qx, d_qx));
+	}
+
+int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_L, void *stream)
+	{
+	return hpmpc_b200_d_back_ric_rec_trf_upd_batch(p, n_inst, d_in, NULL, d_L, stream);
+	}
+
+int hpmpc_b200_d_back_ric_rec_trf_upd_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_Qx, double *d_L, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(p->device));
+	if(p->tf_id>=0 && d_Qx!=NULL)
+		{ fprintf(stderr, "hpmpc_b200: trf with Qx needs the generic factor layout: call hpmpc_b200_ocp_generic_factor_layout() on the handle first\n"); return -5; }
+	if(call_begin(p, stream)) return -1;
 	if(p->tf_id>=0)
 		{
 		long long need = (n_inst + p->tf_warps - 1)/p->tf_warps;
-		return hb_launch_ric_trf_trs_fast(p->tf_id, 0, &p->dims, n_inst, d_in, d_L, p->tf_L_stride, NULL, NULL, NULL,
-				(int)(need<p->tf_grid ? need : p->tf_grid), p->tf_warps, stream);
+		return call_end(p, stream, hb_launch_ric_trf_trs_fast(p->tf_id, 0, &p->dims, n_inst, d_in, d_L, p->tf_L_stride, NULL, NULL, NULL,
+				(int)(need<p->tf_grid ? need : p->tf_grid), p->tf_warps, stream));
 		}
-	return hb_launch_ric_trf(&p->dims, n_inst, d_in, d_L, grid_for(p, n_inst), p->warps, stream);
+	return call_end(p, stream, hb_launch_ric_trf(&p->dims, n_inst, d_in, d_L, grid_for(p, n_inst), p->warps, stream, d_Qx));
 	}
 
 int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_L,
 		double *d_ux, double *d_pi, void *stream)
 	{
+	return hpmpc_b200_d_back_ric_rec_trs_upd_batch(p, n_inst, d_in, d_L, NULL, d_ux, d_pi, stream);
+	}
+
+int hpmpc_b200_d_back_ric_rec_trs_upd_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_L, const double *d_qx,
+		double *d_ux, double *d_pi, void *stream)
+	{
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
+	if(p->tf_id>=0 && d_qx!=NULL)
+		{ fprintf(stderr, "hpmpc_b200: trs with qx needs the generic factor layout: call hpmpc_b200_ocp_generic_factor_layout() on the handle first\n"); return -5; }
+	if(call_begin(p, stream)) return -1;
 	if(p->tf_id>=0)
 		{
 		long long need = (n_inst + p->tf_warps - 1)/p->tf_warps;
 		if(ensure_scratch(p, sizeof(double)*(size_t)p->tf_grid*p->tf_warps*(p->dims.ux_stride+p->dims.pi_stride))) return -1;
-		return hb_launch_ric_trf_trs_fast(p->tf_id, 1, &p->dims, n_inst, d_in, (double*)d_L, p->tf_L_stride, d_ux, d_pi, p->scratch,
-				(int)(need<p->tf_grid ? need : p->tf_grid), p->tf_warps, stream);
+		return call_end(p, stream, hb_launch_ric_trf_trs_fast(p->tf_id, 1, &p->dims, n_inst, d_in, (double*)d_L, p->tf_L_stride, d_ux, d_pi, p->scratch,
+				(int)(need<p->tf_grid ? need : p->tf_grid), p->tf_warps, stream));
 		}
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*(p->dims.ux_stride+2*p->dims.pi_stride))) return -1;
-	return hb_launch_ric_trs(&p->dims, n_inst, d_in, d_L, d_ux, d_pi, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream);
+	return call_end(p, stream, hb_launch_ric_trs(&p->dims, n_inst, d_in, d_L, d_ux, d_pi, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream, d_qx));
 	}
 
 /* Waves: one launch per `slots` instances (one instance per resident warp).  Warps of a wave stay in step, so the SM's
@@ -454,9 +583,10 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
+	if(call_begin(p, stream)) return -1;
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->i_grid*p->i_warps*p->ipm_ws)) return -1;
-	return ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
-			p->lam_stride, stream, NULL);
+	return call_end(p, stream, ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
+			p->lam_stride, stream, NULL));
 	}
 
 /* the same solve, every instance leaving its KKT state in d_kkt (hpmpc_b200_kkt_state_stride() doubles each) */
@@ -468,9 +598,10 @@ int hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch(hpmpc_b200_ocp *p, long long n_inst,
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	if(d_kkt==NULL) return -2;
 	CK(cudaSetDevice(p->device));
+	if(call_begin(p, stream)) return -1;
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->i_grid*p->i_warps*p->ipm_ws)) return -1;
-	return ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
-			p->lam_stride, stream, d_kkt);
+	return call_end(p, stream, ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
+			p->lam_stride, stream, d_kkt));
 	}
 
 /* the last KKT system of that solve again, for the b, [r q] and bounds held in d_in (same matrices): one solve with the stored
@@ -485,8 +616,9 @@ int hpmpc_b200_d_kkt_solve_new_rhs_batch(hpmpc_b200_ocp *p, long long n_inst, co
 	CK(cudaSetDevice(p->device));
 	long long need = (n_inst + p->i_warps - 1)/p->i_warps;
 	int grid = (int)(need<p->i_grid ? (need<1 ? 1 : need) : p->i_grid);
-	return hb_launch_kkt_new_rhs(&p->dims, n_inst, d_in, d_kkt, kkt_stride(p), d_ux, d_pi, d_lam, d_t, d_info, grid, p->i_warps,
-			p->counter, p->ipm_fast_id, stream);
+	if(call_begin(p, stream)) return -1;
+	return call_end(p, stream, hb_launch_kkt_new_rhs(&p->dims, n_inst, d_in, d_kkt, kkt_stride(p), d_ux, d_pi, d_lam, d_t, d_info, grid, p->i_warps,
+			p->counter, p->ipm_fast_id, stream));
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -536,6 +668,7 @@ int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst,
 	const size_t in_b = sizeof(double)*(size_t)cs*p->dims.in_stride;
 	const size_t ux_b = sizeof(double)*(size_t)cs*p->dims.ux_stride, pi_b = sizeof(double)*(size_t)cs*p->dims.pi_stride;
 	if(ensure_staging(p, in_b, ux_b+pi_b)) return -1;
+	if(call_begin(p, p->s_copy[0]) || call_begin(p, p->s_copy[1])) return -1;
 	/* each stream owns its own slice of the scratch slots: both chunks can be in flight */
 	{
 	size_t gen = sizeof(double)*(size_t)2*p->n_slots*p->dims.L_stride;
@@ -557,12 +690,13 @@ int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst,
 					p->scratch + (size_t)k*p->f_grid*p->f_warps*p->f_ipw*p->f_stash_inst, grid, p->f_warps, st)) return -1;
 			}
 		else if(hb_launch_ric_sv(&p->dims, m, d_in, d_ux, d_pi, NULL, p->scratch + (size_t)k*p->n_slots*p->dims.L_stride,
-				p->n_slots, grid_for(p, m), p->warps, st)) return -1;
+				p->n_slots, grid_for(p, m), p->warps, st, NULL, NULL)) return -1;
 		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));
 		}
 	CK(cudaStreamSynchronize(p->s_copy[0]));
 	CK(cudaStreamSynchronize(p->s_copy[1]));
+	p->busy_valid = 0;                   /* everything this handle issued has completed */
 	return 0;
 	}
 
@@ -584,6 +718,7 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 	const size_t in_b = sizeof(double)*(size_t)cs*p->dims.in_stride;
 	const size_t out_d = (size_t)cs*(p->dims.ux_stride + p->dims.pi_stride + 2*lam_len + info_len);
 	if(ensure_staging(p, in_b, sizeof(double)*out_d)) return -1;
+	if(call_begin(p, p->s_comp)) return -1;
 	const long long ws = p->ipm_ws;
 	const int slots = p->i_grid*p->i_warps;
 	if(ensure_scratch(p, sizeof(double)*(size_t)slots*ws)) return -1;
@@ -617,6 +752,7 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 		}
 	CK(cudaStreamSynchronize(p->s_copy[0]));
 	CK(cudaStreamSynchronize(p->s_copy[1]));
+	p->busy_valid = 0;                   /* everything this handle issued has completed */
 	return 0;
 	}
 
@@ -631,6 +767,9 @@ const char *hpmpc_b200_version(void) { return "hpmpc_b200 0.1 (sm_100a)"; }
 /* used by compat.c only: the legacy symbols pass the factor of sv / trf to trs through the caller's `memory`, whose size and
  * layout are the generic ones (d_back_ric_rec_sv_tv_memory_space_size_bytes) -- keep trf / trs on the generic kernels there */
 void hpmpc_b200_internal_generic_trf(hpmpc_b200_ocp *p) { p->tf_id = -1; }
+/* public name of the same switch: trf / trs keep the factor in the generic packed-trapezoid layout (layout.h) even for a shape
+ * that has size-specialised sweeps -- needed for the _upd_ variants (Qx / qx) and by callers that read the factor */
+void hpmpc_b200_ocp_generic_factor_layout(hpmpc_b200_ocp *p) { p->tf_id = -1; }
 
 /* used by compat.c only: the factor of a batch-of-one sv call sits in scratch slot 0 */
 int hpmpc_b200_internal_copy_stash(hpmpc_b200_ocp *p, double *h_dst)

@@ -92,6 +92,42 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 			}
 		__syncwarp();
 		}
+	if(Qx!=nullptr && s.ng>0)
+		{
+		/* general constraints: H += [D C]' diag(Qx_g) [D C], gradient row += [D C]' qx_g  (the reference appends
+		 * DCt*diag(Qx_g) to W and DCt to its transpose before the syrk: lqcp_solvers/d_back_ric_rec.c:293-315,
+		 * readable twin d_back_ric_rec_libstr.c:105-113,164-171) */
+		const int ng = s.ng;
+		const double *G = in_inst + s.off_DCt;
+		const double *Qg = Qx + s.off_c + s.nb;
+		for(int i=lane; i<m; i+=32)
+			{
+			double *hi = cur + HB_TRI(i);
+			if(i<nux)
+				{
+				const double *gi = G + i*ng;
+				for(int k=0; k<=i; k++)
+					{
+					const double *gk = G + k*ng;
+					double acc = 0.0;
+					for(int j=0; j<ng; j++) acc += gi[j]*Qg[j]*gk[j];
+					hi[k] += acc;
+					}
+				}
+			else if(qx!=nullptr)
+				{
+				const double *qg = qx + s.off_c + s.nb;
+				for(int k=0; k<nux; k++)
+					{
+					const double *gk = G + k*ng;
+					double acc = 0.0;
+					for(int j=0; j<ng; j++) acc += qg[j]*gk[j];
+					hi[k] += acc;
+					}
+				}
+			}
+		__syncwarp();
+		}
 	(void)nu;
 	if(nx1>0)
 		{
@@ -236,7 +272,7 @@ __device__ __forceinline__ void hb_stage_forward(const hb_ctx &c, const hb_stage
  *   Ln (smem) = L_n ; Ln1 (smem) = L_{n+1} (only read when compute_Pb) ; sW holds [B A b]'_n ; w lives in ux */
 __device__ __forceinline__ void hb_trs_stage_back(const hb_ctx &c, const hb_stage &s, const hb_stage &s1, int n,
 		const double *Ln, const double *Ln1, const double *bvec, const double *rqvec, const double *qx,
-		const int *__restrict__ idxb, double *ux, double *Pb, bool compute_Pb)
+		const int *__restrict__ idxb, double *ux, double *Pb, bool compute_Pb, const double *__restrict__ in_inst = nullptr)
 	{
 	const int lane = c.lane;
 	const int nu = s.nu, nux = s.nu+s.nx, nx1 = s.nx1, nu1 = s1.nu;
@@ -266,6 +302,18 @@ __device__ __forceinline__ void hb_trs_stage_back(const hb_ctx &c, const hb_stag
 	if(qx!=nullptr && s.nb>0)
 		{
 		for(int j=lane; j<s.nb; j+=32) v[idxb[s.off_c+j]] += qx[s.off_c+j];
+		__syncwarp();
+		}
+	if(qx!=nullptr && s.ng>0 && in_inst!=nullptr)
+		{
+		/* general constraints: + [D C]' qx_g  (lqcp_solvers/d_back_ric_rec.c:668-672) */
+		const double *G = in_inst + s.off_DCt, *qg = qx + s.off_c + s.nb;
+		for(int i=lane; i<nux; i+=32)
+			{
+			double acc = v[i];
+			for(int j=0; j<s.ng; j++) acc += G[i*s.ng+j]*qg[j];
+			v[i] = acc;
+			}
 		__syncwarp();
 		}
 	for(int i=lane; i<nux; i+=32)

@@ -20,8 +20,12 @@
 /* Riccati kernels                                                                                   */
 /* ------------------------------------------------------------------------------------------------ */
 extern __shared__ double hb_smem[];
+/* Qx, qx (may be NULL): the IPM's per-constraint updates of the Hessian diagonal / gradient row, nbtot doubles per instance in
+ * the flat constraint order (stage after stage: box entries, then general ones) -- the reference's Qx / qx arguments
+ * (lqcp_solvers/d_back_ric_rec.c:112); with general constraints they weight [D C]' (:293-315) */
 __global__ void hb_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
-		double *__restrict__ ux, double *__restrict__ pi, double *__restrict__ Pb, double *__restrict__ stash)
+		double *__restrict__ ux, double *__restrict__ pi, double *__restrict__ Pb, double *__restrict__ stash,
+		const double *__restrict__ Qx, const double *__restrict__ qx)
 	{
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
@@ -30,21 +34,23 @@ __global__ void hb_ric_sv_kernel(hb_dims d, long long n_inst, const double *__re
 	for(long long inst=gw; inst<n_inst; inst+=tw)
 		{
 		const double *in_inst = in + inst*d.in_stride;
-		hb_backward<true>(c, d, in_inst, Lst, nullptr, nullptr, nullptr, nullptr, Pb!=nullptr ? Pb + inst*d.pi_stride : nullptr);
+		hb_backward<true>(c, d, in_inst, Lst, nullptr, nullptr, Qx!=nullptr ? Qx + inst*d.nbtot : nullptr,
+				qx!=nullptr ? qx + inst*d.nbtot : nullptr, Pb!=nullptr ? Pb + inst*d.pi_stride : nullptr);
 		__syncwarp();
 		hb_forward(c, d, in_inst, Lst, nullptr, nullptr, false, ux + inst*d.ux_stride, pi + inst*d.pi_stride, true);
 		__syncwarp();
 		}
 	}
 
-__global__ void hb_ric_trf_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, double *__restrict__ L)
+__global__ void hb_ric_trf_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, double *__restrict__ L,
+		const double *__restrict__ Qx)
 	{
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
 	hb_ctx c = hb_make_ctx(d, hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM), lane);
 	for(long long inst=gw; inst<n_inst; inst+=tw)
 		{
-		hb_backward<false>(c, d, in + inst*d.in_stride, L + inst*d.L_stride, nullptr, nullptr, nullptr, nullptr, nullptr);
+		hb_backward<false>(c, d, in + inst*d.in_stride, L + inst*d.L_stride, nullptr, nullptr, Qx!=nullptr ? Qx + inst*d.nbtot : nullptr, nullptr, nullptr);
 		__syncwarp();
 		}
 	}
@@ -52,7 +58,7 @@ __global__ void hb_ric_trf_kernel(hb_dims d, long long n_inst, const double *__r
 /* solve with the stored factor; b and [r q] are taken from the instance block (new right-hand sides are
  * supplied by packing them into a copy of the block) */
 __global__ void hb_ric_trs_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, const double *__restrict__ L,
-		double *__restrict__ ux, double *__restrict__ pi, double *__restrict__ work)
+		double *__restrict__ ux, double *__restrict__ pi, double *__restrict__ work, const double *__restrict__ qx)
 	{
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
@@ -71,7 +77,7 @@ __global__ void hb_ric_trs_kernel(hb_dims d, long long n_inst, const double *__r
 			}
 		__syncwarp();
 		double *uxi = ux + inst*d.ux_stride;
-		hb_trs_backward(c, d, in_inst, L + inst*d.L_stride, bv, rq, nullptr, uxi, Pb, true);
+		hb_trs_backward(c, d, in_inst, L + inst*d.L_stride, bv, rq, qx!=nullptr ? qx + inst*d.nbtot : nullptr, uxi, Pb, true);
 		hb_forward(c, d, in_inst, L + inst*d.L_stride, uxi, bv, true, uxi, pi + inst*d.pi_stride, true);
 		__syncwarp();
 		}
@@ -151,35 +157,36 @@ extern "C" int hb_device_sm_count(int device)
 	}
 
 extern "C" int hb_launch_ric_sv(const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi, double *Pb,
-		double *stash, int n_slots, int grid, int warps, void *stream)
+		double *stash, int n_slots, int grid, int warps, void *stream, const double *Qx, const double *qx)
 	{
 	if(d->nzM>64) { fprintf(stderr, "hpmpc_b200: nu+nx+1 > 64 not supported\n"); return -2; }
 	if(grid*warps>n_slots) return -3;
 	int smem = warps*hb_smem_bytes_per_warp(d);
 	if(hb_prep(hb_ric_sv_kernel, smem)) return -1;
-	hb_ric_sv_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, ux, pi, Pb, stash);
+	hb_ric_sv_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, ux, pi, Pb, stash, Qx, qx);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
 
-extern "C" int hb_launch_ric_trf(const hb_dims *d, long long n_inst, const double *in, double *L, int grid, int warps, void *stream)
+extern "C" int hb_launch_ric_trf(const hb_dims *d, long long n_inst, const double *in, double *L, int grid, int warps, void *stream,
+		const double *Qx)
 	{
 	if(d->nzM>64) return -2;
 	int smem = warps*hb_smem_bytes_per_warp(d);
 	if(hb_prep(hb_ric_trf_kernel, smem)) return -1;
-	hb_ric_trf_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, L);
+	hb_ric_trf_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, L, Qx);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
 
 extern "C" int hb_launch_ric_trs(const hb_dims *d, long long n_inst, const double *in, const double *L, double *ux, double *pi,
-		double *work, int n_slots, int grid, int warps, void *stream)
+		double *work, int n_slots, int grid, int warps, void *stream, const double *qx)
 	{
 	if(d->nzM>64) return -2;
 	if(grid*warps>n_slots) return -3;
 	int smem = warps*hb_smem_bytes_per_warp(d);
 	if(hb_prep(hb_ric_trs_kernel, smem)) return -1;
-	hb_ric_trs_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, L, ux, pi, work);
+	hb_ric_trs_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, L, ux, pi, work, qx);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}

@@ -80,6 +80,17 @@ static __device__ void hb_trs_backward(const hb_ctx &c, const hb_dims &d, const 
 	__syncwarp();
 	if(qx!=nullptr) for(int j=lane; j<s.nb; j+=32) ux[s.off_ux+d.idxb[s.off_c+j]] += qx[s.off_c+j];
 	__syncwarp();
+	if(qx!=nullptr && s.ng>0)
+		{
+		const double *G = in_inst + s.off_DCt, *qg = qx + s.off_c + s.nb;
+		for(int i=lane; i<nux; i+=32)
+			{
+			double acc = ux[s.off_ux+i];
+			for(int j=0; j<s.ng; j++) acc += G[i*s.ng+j]*qg[j];
+			ux[s.off_ux+i] = acc;
+			}
+		__syncwarp();
+		}
 	}
 	for(int n=d.N-1; n>=0; n--)
 		{
@@ -89,7 +100,7 @@ static __device__ void hb_trs_backward(const hb_ctx &c, const hb_dims &d, const 
 		if(compute_Pb) hb_copy(c, c.bufB, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
 		hb_load_BAbt(c, s, in_inst);
 		__syncwarp();
-		hb_trs_stage_back(c, s, s1, n, c.bufA, c.bufB, bvec, rqvec, qx, d.idxb, ux, Pb, compute_Pb);
+		hb_trs_stage_back(c, s, s1, n, c.bufA, c.bufB, bvec, rqvec, qx, d.idxb, ux, Pb, compute_Pb, in_inst);
 		}
 	}
 

@@ -46,22 +46,39 @@ int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tre
 	return hpmpc_b200_tree_create_box(out, Nn, tree, nx, nu, NULL, NULL, device);
 	}
 
+static int tree_create_impl(hpmpc_b200_tree **out, hpmpc_b200_tree **partial, int Nn, const struct node *tree, const int *nx, const int *nu,
+		const int *nb, int *const *idxb, int device);
+
+/* every error return of the construction goes through here: whatever was allocated so far is released */
 int hpmpc_b200_tree_create_box(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu,
+		const int *nb, int *const *idxb, int device)
+	{
+	hpmpc_b200_tree *partial = NULL;
+	int rc = tree_create_impl(out, &partial, Nn, tree, nx, nu, nb, idxb, device);
+	if(rc) { hpmpc_b200_tree_destroy(partial); *out = NULL; }
+	return rc;
+	}
+
+static int tree_create_impl(hpmpc_b200_tree **out, hpmpc_b200_tree **partial, int Nn, const struct node *tree, const int *nx, const int *nu,
 		const int *nb, int *const *idxb, int device)
 	{
 	int n, j;
 	*out = NULL;
 	if(Nn<1) return -2;
 	hpmpc_b200_tree *t = calloc(1, sizeof(*t));
+	if(!t) return -1;
+	*partial = t;
 	t->device = device; t->Nn = Nn;
 	t->tn = calloc(Nn, sizeof(hb_tnode));
 	t->stage = calloc(Nn, sizeof(int));
 	t->slot = calloc(Nn, sizeof(int));
+	if(!t->tn || !t->stage || !t->slot) return -1;
 	int nzM = 1, nxM = 1, max_stage = 0;
 	for(n=0; n<Nn; n++)
 		{
 		hb_tnode *s = &t->tn[n];
 		s->nx = nx[n]; s->nu = nu[n]; s->nkids = tree[n].nkids; s->dad = (n==0) ? -1 : tree[n].dad;
+		if(n>0 && (s->dad<0 || s->dad>=n)) { fprintf(stderr, "hpmpc_b200: tree: node %d: dad = %d must precede the node (BFS order)\n", n, s->dad); return -2; }
 		s->first_kid = s->nkids>0 ? tree[n].kids[0] : -1;
 		for(j=0; j<s->nkids; j++)
 			if(tree[n].kids[j]!=s->first_kid+j || s->first_kid<=n || s->first_kid+j>=Nn)

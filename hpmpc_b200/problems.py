@@ -89,6 +89,24 @@ class Ocp:
     r: List[np.ndarray] = field(default_factory=list)
     lb: List[np.ndarray] = field(default_factory=list)
     ub: List[np.ndarray] = field(default_factory=list)
+    # general (polytopic) constraints lg <= D u + C x <= ug; empty lists = none (reference include/c_interface.h:62: C, D, lg, ug)
+    ng: List[int] = field(default_factory=list)
+    C: List[np.ndarray] = field(default_factory=list)   # [N+1] ng x nx
+    D: List[np.ndarray] = field(default_factory=list)   # [N+1] ng x nu
+    lg: List[np.ndarray] = field(default_factory=list)
+    ug: List[np.ndarray] = field(default_factory=list)
+
+    def ng_list(self):
+        return list(self.ng) if self.ng else [0] * (self.N + 1)
+
+    def general_arrays(self):
+        """C, D, lg, ug with (ng x n) zero-size placeholders where a stage has no general constraints."""
+        ng = self.ng_list()
+        if not self.ng:
+            z = [np.zeros((0, 1))] * (self.N + 1)
+            return [np.zeros((0, self.nx[n])) for n in range(self.N + 1)], [np.zeros((0, self.nu[n])) for n in range(self.N + 1)], \
+                [np.zeros(0)] * (self.N + 1), [np.zeros(0)] * (self.N + 1)
+        return self.C, self.D, self.lg, self.ug
 
 
 def mass_spring_ocp(nx: int, nu: int, N: int, *, bounds: bool = False, xi=(0.0, 0.0, 0.0, 0.0),
@@ -145,6 +163,53 @@ def mass_spring_ocp(nx: int, nu: int, N: int, *, bounds: bool = False, xi=(0.0, 
             p.lb.append(np.zeros(0))
             p.ub.append(np.zeros(0))
     return p
+
+
+def add_general(p: Ocp, stage_rows) -> Ocp:
+    """Attach general constraints: stage_rows maps stage -> (C, D, lg, ug); other stages get ng = 0."""
+    N = p.N
+    p.ng = [0] * (N + 1)
+    p.C = [np.zeros((0, p.nx[n])) for n in range(N + 1)]
+    p.D = [np.zeros((0, p.nu[n])) for n in range(N + 1)]
+    p.lg = [np.zeros(0) for _ in range(N + 1)]
+    p.ug = [np.zeros(0) for _ in range(N + 1)]
+    for n, (C, D, lg, ug) in stage_rows.items():
+        g = len(lg)
+        C = np.ascontiguousarray(C, dtype=np.float64).reshape(g, p.nx[n])
+        D = np.ascontiguousarray(D, dtype=np.float64).reshape(g, p.nu[n])
+        p.ng[n] = g
+        p.C[n], p.D[n] = C, D
+        p.lg[n], p.ug[n] = np.asarray(lg, dtype=np.float64), np.asarray(ug, dtype=np.float64)
+    return p
+
+
+def guide_problem(N: int = 30, nx: int = 8, nu: int = 3, terminal_band: float = 0.0) -> Ocp:
+    """The problem of the reference's user guide (doc/guide.tex:333-346): mass-spring chain, forces in [-0.5, 0.5], positions in
+    [-4, 4], Q = I, R = 2 I, q = r = 0, and a terminal constraint x_N = 0 imposed as ngN = nx general constraints (C_N = I,
+    lg = ug = 0).  x0 = (2.5, 2.5, 0, ...) is eliminated into b_0 as in test_problems/test_d_ip_hard.c:303-314."""
+    p = mass_spring_ocp(nx, nu, N, bounds=True)
+    for n in range(N + 1):
+        p.q[n] = np.zeros(p.nx[n]); p.r[n] = np.zeros(p.nu[n])
+    return add_general(p, {N: (np.eye(nx), np.zeros((nx, 0)), -terminal_band * np.ones(nx), terminal_band * np.ones(nx))})
+
+
+def general_test_problem(nx: int = 8, nu: int = 3, N: int = 10, xi=(0.0, 0.0, 0.0, 0.0)) -> Ocp:
+    """Box bounds plus general constraints at EVERY stage (inputs only at stage 0, mixed C / D rows in the middle, states only
+    at stage N): exercises every ng > 0 code path with a different ng per stage."""
+    p = mass_spring_ocp(nx, nu, N, bounds=True, xi=xi)
+    rows = {}
+    for n in range(N + 1):
+        nxn, nun = p.nx[n], p.nu[n]
+        if n == 0:
+            rows[n] = (np.zeros((1, 0)), np.ones((1, nun)), [-1.2], [1.2])
+        elif n < N:
+            C = np.zeros((2, nxn)); C[0, 0] = 1.0; C[0, 1] = -1.0; C[1, nxn // 2] = 1.0
+            D = np.zeros((2, nun)); D[1, :] = 0.5; D[0, 0] = 0.3
+            rows[n] = (C, D, [-2.0, -1.5], [2.0, 1.5])
+        else:
+            C = np.zeros((3, nxn)); C[0, 0] = 1.0; C[0, 1] = 1.0; C[1, 2] = 1.0; C[2, nxn // 2 + 1] = 1.0
+            rows[n] = (C, np.zeros((3, 0)), [-1.5, -1.0, -1.0], [1.5, 1.0, 1.0])
+    return add_general(p, rows)
 
 
 def config(name: str):

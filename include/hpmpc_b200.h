@@ -18,7 +18,7 @@
  * hpmpc_b200_ocp_stage_offsets().  Outputs per instance:
  *     ux  [ux_stride]   u_n then x_n for n = 0..N        (reference hux[n], d_back_ric_rec.c:341)
  *     pi  [pi_stride]   multiplier of x_{n+1} = ..., n = 0..N-1   (reference hpi[n], edge-indexed)
- *     lam [lam_stride]  per stage [lower(nb) upper(nb)]  (reference lam ordering, c_order_interface.c:662-671)
+ *     lam [lam_stride]  per stage [lb(nb) ub(nb) lg(ng) ug(ng)]  (reference lib4 ordering, c_order_interface.c:662-681)
  *     t   [lam_stride]  slacks, same ordering
  *     info[6+5*k_max]   kk, status(0 converged /1 k_max /2 alpha_min /-1), ||rq||inf, ||rb||inf, ||rd||inf, mu,
  *                       then the reference's stat table (sigma, alpha_aff, mu_aff, alpha, mu) per iteration
@@ -46,6 +46,15 @@ typedef struct hpmpc_b200_sizes
  * nb / hidxb may be NULL for an unconstrained problem; hidxb[n][j] indexes [u_n ; x_n] */
 int  hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb,
                            int *const *hidxb, int device);
+/* the same with general (polytopic) constraints lg <= D_n u + C_n x <= ug, ng[n] of them at stage n (NULL = none): SURVEY 8f row f1,
+ * reference lqcp_solvers/d_back_ric_rec_libstr.c:105-113,164-171, mpc_solvers/c99/d_aux_ip_hard_libstr.c:125,329,
+ * mpc_solvers/d_res_ip_res_hard_libstr.c:120-144.  Patterns with ng > 0 run on the any-size kernels. */
+int  hpmpc_b200_ocp_create_gen(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb,
+                               int *const *hidxb, const int *ng, int device);
+/* CONCURRENCY: a handle owns one set of scratch slots and one work-queue counter, so it runs ONE call at a time.  The library
+ * enforces this on the device: every entry point makes its stream wait for the handle's previous call (an event), so calls issued
+ * to different streams are serialised, never raced.  Use one handle per stream for concurrent solves.  Host threads must not
+ * call into the same handle simultaneously. */
 void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p);
 /* ctas_per_sm <= 0 or warps_per_cta <= 0 selects the default for the problem size */
 int  hpmpc_b200_ocp_set_launch(hpmpc_b200_ocp *p, int ctas_per_sm, int warps_per_cta);
@@ -58,6 +67,10 @@ void hpmpc_b200_ocp_stage_offsets(const hpmpc_b200_ocp *p, int n, int *off_BAbt,
 int  hpmpc_b200_pack_instance(const hpmpc_b200_ocp *p, int c_order, double *const *A, double *const *B, double *const *b,
                               double *const *Q, double *const *S, double *const *R, double *const *q, double *const *r,
                               double *const *lb, double *const *ub, double *block);
+/* general constraints of one instance into its block (after hpmpc_b200_pack_instance): C[n] ng x nx, D[n] ng x nu (n < N) */
+int  hpmpc_b200_pack_general(const hpmpc_b200_ocp *p, int c_order, double *const *C, double *const *D, double *const *lg,
+                             double *const *ug, double *block);
+void hpmpc_b200_ocp_general_offsets(const hpmpc_b200_ocp *p, int n, int *ng, int *off_DCt, int *off_dg, int *off_c);
 void hpmpc_b200_unpack_solution(const hpmpc_b200_ocp *p, const double *ux, const double *pi, const double *lam,
                                 double **x, double **u, double **pi_out, double **lam_out);
 
@@ -65,6 +78,17 @@ void hpmpc_b200_unpack_solution(const hpmpc_b200_ocp *p, const double *ux, const
 int hpmpc_b200_d_back_ric_rec_sv_batch (hpmpc_b200_ocp *p, long long n_inst, const double *d_in,
                                         double *d_ux, double *d_pi, double *d_Pb /* may be NULL */, void *stream);
 int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_L, void *stream);
+/* the reference's Qx / qx arguments (d_back_ric_rec_sv_tv_res, lqcp_solvers/d_back_ric_rec.c:112): per-constraint terms added to
+ * the Hessian diagonal / gradient row (through [D C]' for general constraints); nbtot doubles per instance in the flat
+ * constraint order (stage after stage: box entries, then general ones); either pointer may be NULL.  These run on the any-size
+ * kernels; trf / trs with updates need hpmpc_b200_ocp_generic_factor_layout() on shapes that have size-specialised sweeps. */
+int hpmpc_b200_d_back_ric_rec_sv_upd_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_Qx,
+                                           const double *d_qx, double *d_ux, double *d_pi, double *d_Pb, void *stream);
+int hpmpc_b200_d_back_ric_rec_trf_upd_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_Qx,
+                                            double *d_L, void *stream);
+int hpmpc_b200_d_back_ric_rec_trs_upd_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_L,
+                                            const double *d_qx, double *d_ux, double *d_pi, void *stream);
+void hpmpc_b200_ocp_generic_factor_layout(hpmpc_b200_ocp *p);
 int hpmpc_b200_d_back_ric_rec_trs_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_L,
                                         double *d_ux, double *d_pi, void *stream);
 int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,

@@ -61,19 +61,22 @@ def ipm(p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, warm_start=0):
     b = [c(v) for v in p.b]; q = [c(v) for v in p.q]; r = [c(v) for v in p.r]; lb = [c(v) for v in p.lb]; ub = [c(v) for v in p.ub]
     x = [np.zeros(max(n, 1)) for n in p.nx]; u = [np.zeros(max(n, 1)) for n in p.nu[:N]]
     pi = [np.zeros(max(p.nx[n + 1], 1)) for n in range(N)]
-    lam = [np.zeros(max(2 * nb, 1)) for nb in p.nb]
+    ngl = p.ng_list()
+    lam = [np.zeros(max(2 * p.nb[n] + 2 * ngl[n], 1)) for n in range(N + 1)]
     idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
-    empty = [np.zeros(1) for _ in range(N + 1)]
+    pad = lambda M: M if M.size else np.zeros(1)
+    Cg, Dg, lgg, ugg = p.general_arrays()
+    Cg = [pad(_f(M)) for M in Cg]; Dg = [pad(_f(M)) for M in Dg]; lgg = [pad(c(v)) for v in lgg]; ugg = [pad(c(v)) for v in ugg]
     res = np.zeros(8); stat = np.zeros(5 * k_max + 5); kk = C.c_int(0)
     pa = ptr_array
-    arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(empty), pa(empty), pa(empty), pa(empty),
+    arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(Cg), pa(Dg), pa(lgg), pa(ugg),
             pa(x), pa(u), pa(pi), pa(lam)]
     pidx = pa(idxb)
     status = L.orc_fortran_order_d_ip_ocp_hard_tv(C.byref(kk), k_max, mu0, mu_tol, N, int_array(p.nx), int_array(p.nu), int_array(p.nb),
-                                                   pidx, int_array([0] * (N + 1)), N, warm_start, *arrs, res.ctypes.data, None, stat.ctypes.data)
+                                                   pidx, int_array(ngl), N, warm_start, *arrs, res.ctypes.data, None, stat.ctypes.data)
     return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)],
                 u=[u[n][:p.nu[n]].copy() for n in range(N)], pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
-                lam=[lam[n][:2 * p.nb[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(),
+                lam=[lam[n][:2 * p.nb[n] + 2 * ngl[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(),
                 stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
 
@@ -262,12 +265,19 @@ class RefSample:
     panel-major hpBAbt/hpRSQrq for d_back_ric_rec_sv_tv_res, column-major stage arrays for fortran_order_d_ip_ocp_hard_tv.
     Instance i is the same problem as instance i of hpmpc_b200.batchgen.BatchSpec."""
 
-    def __init__(self, spec, n_inst: int, first: int = 0):
+    def __init__(self, spec, n_inst: int, first: int = 0, want=("pm", "cm")):
         from hpmpc_b200.capi import to_pmat, _rup
         self.spec, self.n_inst = spec, n_inst
         p = spec.base
         N = p.N
         x01, x02, qs, rs = spec.scalars(n_inst, first)
+        if "pm" in want:
+            self._build_pm(p, N, spec, n_inst, x01, x02, qs, rs)
+        if "cm" in want:
+            self._build_cm(p, N, spec, n_inst, x01, x02, qs, rs)
+
+    def _build_pm(self, p, N, spec, n_inst, x01, x02, qs, rs):
+        from hpmpc_b200.capi import to_pmat, _rup
         # ---- panel-major (Riccati)
         parts, self.off_pm, pos = [], [], 0
         iq, ir, ib0 = [], [], []
@@ -297,6 +307,9 @@ class RefSample:
         if spec.x0_elim:
             pm[:, ib0] = x01[:, None] * spec.A_cols[None, :, 0] + x02[:, None] * spec.A_cols[None, :, 1] + 0.1
         self.pm = pm
+
+    def _build_cm(self, p, N, spec, n_inst, x01, x02, qs, rs):
+        from hpmpc_b200.capi import _rup, aligned_zeros
         # ---- column-major stage arrays (IPM)
         parts, offs, pos = [], np.zeros((10, N + 1), dtype=np.int64), 0
         iq, ir, ib0 = [], [], []
@@ -350,3 +363,25 @@ class RefSample:
         if sec < 0:
             raise RuntimeError("reference harness failed")
         return sec, kk, st, ux
+
+    def solve_ipm_full(self, kind="c99", n_threads=None, k_max=40, mu0=2.0, mu_tol=1e-8):
+        """Every instance of the sample through the reference's fortran_order_d_ip_ocp_hard_tv on the host cores; returns
+        kk, status, ux, pi, lam ([lb ub] per stage) and inf_norm_res of every instance (the checker of the full-batch parity tests)."""
+        p = self.spec.base
+        L = lib()
+        fn = L.ref_harness_ipm_full
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_char_p, C.c_int, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                       C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p]
+        n_threads = n_threads or os.cpu_count()
+        idxb = np.concatenate([np.asarray(v, dtype=np.int32) for v in p.idxb] + [np.zeros(1, dtype=np.int32)])
+        n_ux, n_pi, n_lam = sum(p.nx) + sum(p.nu), sum(p.nx[1:]), 2 * sum(p.nb)
+        n = self.n_inst
+        kk = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32)
+        ux, pi, lam, res = np.zeros((n, n_ux)), np.zeros((n, n_pi)), np.zeros((n, max(n_lam, 1))), np.zeros((n, 4))
+        sec = fn((REF_AVX2 if kind == "avx2" else REF_C99).encode(), n_threads, n, p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb),
+                 idxb.ctypes.data, k_max, mu0, mu_tol, self.cm.ctypes.data, self.cm_stride, np.ascontiguousarray(self.off_cm).ctypes.data,
+                 kk.ctypes.data, st.ctypes.data, ux.ctypes.data, n_ux, pi.ctypes.data, n_pi, lam.ctypes.data, max(n_lam, 1), res.ctypes.data)
+        if sec < 0:
+            raise RuntimeError("reference harness failed")
+        return dict(sec=sec, kk=kk, status=st, ux=ux, pi=pi, lam=lam, inf_norm_res=res)

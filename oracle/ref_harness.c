@@ -41,6 +41,8 @@ typedef struct
 	double mu0, mu_tol;
 	void *fn, *fsz1, *fsz2;
 	double *ux_out, *pi_out; long ux_stride, pi_stride;
+	double *lam_out; long lam_stride;          /* IPM: lam as the wrapper returns it, [lb ub] per stage, stage after stage */
+	double *res_out;                           /* IPM: inf_norm_res[4] per instance */
 	int *kk_out, *status_out;
 	pthread_barrier_t *bar;
 	double t0, t1;
@@ -124,6 +126,17 @@ static void *worker(void *arg)
 							o += J->nx[n]+J->nu[n];
 							}
 						}
+					if(J->pi_out)
+						{
+						long o = 0;
+						for(n=0; n<N; n++) { for(i=0; i<J->nx[n+1]; i++) J->pi_out[inst*J->pi_stride+o+i] = p[16][n][i]; o += J->nx[n+1]; }
+						}
+					if(J->lam_out)
+						{
+						long o = 0;
+						for(n=0; n<=N; n++) { for(i=0; i<2*J->nb[n]; i++) J->lam_out[inst*J->lam_stride+o+i] = p[17][n][i]; o += 2*J->nb[n]; }
+						}
+					if(J->res_out) for(i=0; i<4; i++) J->res_out[inst*4+i] = res[i];
 					}
 				}
 		J->t1 = now();
@@ -133,7 +146,8 @@ static void *worker(void *arg)
 
 static double run(const char *libpath, int mode, int n_threads, long n_inst, int n_pass, int N, int *nx, int *nu, int *nb,
 		int *idxb_flat, int k_max, double mu0, double mu_tol, double *data, long inst_stride, const long *off,
-		double *ux_out, long ux_stride, double *pi_out, long pi_stride, int *kk_out, int *status_out)
+		double *ux_out, long ux_stride, double *pi_out, long pi_stride, int *kk_out, int *status_out,
+		double *lam_out, long lam_stride, double *res_out)
 	{
 	void *h = dlopen(libpath, RTLD_NOW|RTLD_LOCAL);
 	if(!h) { fprintf(stderr, "ref_harness: cannot load %s: %s\n", libpath, dlerror()); return -1.0; }
@@ -158,6 +172,7 @@ static double run(const char *libpath, int mode, int n_threads, long n_inst, int
 		J[t].data = data; J[t].mu0 = mu0; J[t].mu_tol = mu_tol; J[t].fn = fn; J[t].fsz1 = f1; J[t].fsz2 = f2;
 		J[t].ux_out = ux_out; J[t].pi_out = pi_out; J[t].ux_stride = ux_stride; J[t].pi_stride = pi_stride;
 		J[t].kk_out = kk_out; J[t].status_out = status_out; J[t].bar = &bar;
+		J[t].lam_out = lam_out; J[t].lam_stride = lam_stride; J[t].res_out = res_out;
 		pthread_create(&th[t], NULL, worker, &J[t]);
 		}
 	double t0 = 1e300, t1 = 0.0;
@@ -177,7 +192,7 @@ double ref_harness_ric_sv(const char *libpath, int n_threads, long n_inst, int n
 		double *pm_data, long inst_stride, const long *off, double *ux_out, long ux_stride, double *pi_out, long pi_stride)
 	{
 	return run(libpath, 0, n_threads, n_inst, n_pass, N, nx, nu, NULL, NULL, 0, 0.0, 0.0, pm_data, inst_stride, off,
-			ux_out, ux_stride, pi_out, pi_stride, NULL, NULL);
+			ux_out, ux_stride, pi_out, pi_stride, NULL, NULL, NULL, 0, NULL);
 	}
 
 /* column-major stage arrays: off = 10 x (N+1) table for A,B,b,Q,S,R,q,r,lb,ub */
@@ -186,5 +201,15 @@ double ref_harness_ipm(const char *libpath, int n_threads, long n_inst, int n_pa
 		int *kk_out, int *status_out, double *ux_out, long ux_stride)
 	{
 	return run(libpath, 1, n_threads, n_inst, n_pass, N, nx, nu, nb, idxb_flat, k_max, mu0, mu_tol, data, inst_stride, off,
-			ux_out, ux_stride, NULL, 0, kk_out, status_out);
+			ux_out, ux_stride, NULL, 0, kk_out, status_out, NULL, 0, NULL);
+	}
+
+/* the same, also returning pi, lam and inf_norm_res of every instance (full-batch parity runs, tests/test_parity_hardening.py) */
+double ref_harness_ipm_full(const char *libpath, int n_threads, long n_inst, int N, int *nx, int *nu, int *nb, int *idxb_flat,
+		int k_max, double mu0, double mu_tol, double *data, long inst_stride, const long *off,
+		int *kk_out, int *status_out, double *ux_out, long ux_stride, double *pi_out, long pi_stride, double *lam_out, long lam_stride,
+		double *res_out)
+	{
+	return run(libpath, 1, n_threads, n_inst, 1, N, nx, nu, nb, idxb_flat, k_max, mu0, mu_tol, data, inst_stride, off,
+			ux_out, ux_stride, pi_out, pi_stride, kk_out, status_out, lam_out, lam_stride, res_out);
 	}

@@ -28,7 +28,10 @@
  *   high-level wrapper interfaces/c/fortran_order_interface.c:53-688 (packing, mu0 estimate, u=lb if lb==ub,
  *                      inf_norm_res, lam ordering [lb ub])
  *
- * Scope: ng == 0 (no general constraints), N2 >= N (no partial condensing) -- SURVEY.md section 8 rows f1, f3.
+ * General constraints lg <= D u + C x <= ug (ng > 0): the reference treats them exactly like bounds
+ * with the bounded variable replaced by the product [D C] ux (mpc_solvers/c99/d_aux_ip_hard_lib4.c:121-147, :302-383, :556-607;
+ * lqcp_solvers/d_back_ric_rec.c:293-315); here a stage owns nt = nb + ng constraints, box entries first.
+ * Scope: N2 >= N (no partial condensing; that is the separate routine orc_part_cond below when present).
  */
 #include <math.h>
 #include <stdlib.h>
@@ -40,11 +43,13 @@
 /* ------------------------------------------------------------------------------------------- */
 typedef struct {
 	int N;
-	int *nx, *nu, *nb;      /* [N+1], nu[N] = 0 */
-	int **idxb;             /* [N+1][nb]        */
+	int *nx, *nu, *nb;      /* [N+1], nu[N] = 0 ; nb[n] = ALL constraints of the stage: nbx[n] bounds, then ng[n] general ones */
+	int *nbx, *ng;          /* [N+1] */
+	double **DCt;           /* [N+1] (nux) x ng, ld = nux : [D C]' (NULL entries when ng = 0) */
+	int **idxb;             /* [N+1][nbx]       */
 	double **BAbt;          /* [N]   (nux+1) x nx1, ld = nux+1 ; rows: B' , A' , b'   */
 	double **RSQrq;         /* [N+1] (nux+1) x nux, ld = nux+1 ; [R S';S Q] lower + last row [r' q'] */
-	double **d;             /* [N+1] [lb(nb) ; ub(nb)] */
+	double **d;             /* [N+1] [lower(nb) ; upper(nb)], lower = [lb ; lg], upper = [ub ; ug] */
 	/* factorization memory */
 	double **L;             /* [N+1] (nux+1) x nux, ld = nux+1 */
 	double **dinv;          /* [N+1] nux : inverse diagonal of L */
@@ -62,15 +67,36 @@ typedef struct {
 } orc_prob;
 
 static int nux_(const orc_prob *P, int n) { return P->nu[n] + P->nx[n]; }
+/* value of constraint j of stage n for the vector v (ux layout): the bounded variable, or row j-nbx of [D C] times v */
+static double cval(const orc_prob *P, int n, const double *v, int j)
+	{
+	if(j<P->nbx[n]) return v[P->idxb[n][j]];
+	int nux = nux_(P, n), i; const double *g = P->DCt[n] + (size_t)nux*(j-P->nbx[n]);
+	double s = 0.0;
+	for(i=0; i<nux; i++) s += g[i]*v[i];
+	return s;
+	}
+/* v += a * (gradient of constraint j of stage n) */
+static void cscatter(const orc_prob *P, int n, double *v, int j, double a)
+	{
+	if(j<P->nbx[n]) { v[P->idxb[n][j]] += a; return; }
+	int nux = nux_(P, n), i; const double *g = P->DCt[n] + (size_t)nux*(j-P->nbx[n]);
+	for(i=0; i<nux; i++) v[i] += a*g[i];
+	}
 static int dad_(const orc_prob *P, int k) { return P->dad ? P->dad[k] : k-1; }
 
-orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *dad);
+orc_prob *orc_prob_create_gen(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *dad, const int *ng);
+orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *dad)
+	{
+	return orc_prob_create_gen(N, nx, nu, nb, idxb, dad, NULL);
+	}
 orc_prob *orc_prob_create(int N, const int *nx, const int *nu, const int *nb, int *const *idxb)
 	{
-	return orc_prob_create_tree(N, nx, nu, nb, idxb, NULL);
+	return orc_prob_create_gen(N, nx, nu, nb, idxb, NULL, NULL);
 	}
 
-orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *dad)
+/* nb[n] = number of bounds of stage n, ng[n] (may be NULL) = number of general constraints */
+orc_prob *orc_prob_create_gen(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *dad, const int *ng)
 	{
 	orc_prob *P = calloc(1, sizeof(orc_prob));
 	int n, j;
@@ -86,12 +112,18 @@ orc_prob *orc_prob_create_tree(int N, const int *nx, const int *nu, const int *n
 		P->nk[dd]++;
 		}
 	P->nx = malloc((N+1)*sizeof(int)); P->nu = malloc((N+1)*sizeof(int)); P->nb = malloc((N+1)*sizeof(int));
-	for(n=0; n<=N; n++) { P->nx[n] = nx[n]; P->nu[n] = (n<N || dad) ? nu[n] : 0; P->nb[n] = nb ? nb[n] : 0; }
+	P->nbx = malloc((N+1)*sizeof(int)); P->ng = malloc((N+1)*sizeof(int)); P->DCt = calloc(N+1, sizeof(double*));
+	for(n=0; n<=N; n++)
+		{
+		P->nx[n] = nx[n]; P->nu[n] = (n<N || dad) ? nu[n] : 0;
+		P->nbx[n] = nb ? nb[n] : 0; P->ng[n] = ng ? ng[n] : 0; P->nb[n] = P->nbx[n] + P->ng[n];
+		}
 	P->idxb = calloc(N+1, sizeof(int*));
 	for(n=0; n<=N; n++)
 		{
-		P->idxb[n] = malloc((P->nb[n]+1)*sizeof(int));
-		for(j=0; j<P->nb[n]; j++) P->idxb[n][j] = idxb[n][j];
+		P->idxb[n] = malloc((P->nbx[n]+1)*sizeof(int));
+		for(j=0; j<P->nbx[n]; j++) P->idxb[n][j] = idxb[n][j];
+		P->DCt[n] = calloc((size_t)(P->nu[n]+P->nx[n]+1)*(P->ng[n]+1), sizeof(double));
 		}
 	P->BAbt = calloc(N+1, sizeof(double*)); P->RSQrq = calloc(N+1, sizeof(double*)); P->d = calloc(N+1, sizeof(double*));
 	P->L = calloc(N+1, sizeof(double*)); P->dinv = calloc(N+1, sizeof(double*));
@@ -125,12 +157,12 @@ void orc_prob_free(orc_prob *P)
 	int n;
 	for(n=0; n<=P->N; n++)
 		{
-		free(P->idxb[n]); free(P->BAbt[n]); free(P->RSQrq[n]); free(P->L[n]); free(P->dinv[n]); free(P->d[n]);
+		free(P->idxb[n]); free(P->BAbt[n]); free(P->RSQrq[n]); free(P->L[n]); free(P->dinv[n]); free(P->d[n]); free(P->DCt[n]);
 		free(P->k_ux[n]); free(P->k_pi[n]); free(P->k_lam[n]); free(P->k_t[n]); free(P->k_tinv[n]);
 		}
 	free(P->k_ux); free(P->k_pi); free(P->k_lam); free(P->k_t); free(P->k_tinv);
 	free(P->idxb); free(P->BAbt); free(P->RSQrq); free(P->L); free(P->dinv); free(P->d);
-	free(P->nx); free(P->nu); free(P->nb); free(P->W); free(P->tmp); free(P->dad); free(P->fk); free(P->nk); free(P);
+	free(P->nx); free(P->nu); free(P->nb); free(P->nbx); free(P->ng); free(P->DCt); free(P->W); free(P->tmp); free(P->dad); free(P->fk); free(P->nk); free(P);
 	}
 
 /* fill from the stage-wise column-major ("fortran order") arrays of the high-level API:
@@ -161,7 +193,24 @@ void orc_prob_set(orc_prob *P, double *const *A, double *const *B, double *const
 		for(j=0; j<nx; j++) for(i=0; i<nx; i++) H[nu+i+nz*(nu+j)] = Q[n][i+nx*j];
 		for(j=0; j<nu; j++) H[nux+nz*j] = r[n][j];
 		for(j=0; j<nx; j++) H[nux+nz*(nu+j)] = q[n][j];
-		for(j=0; j<P->nb[n]; j++) { P->d[n][j] = lb[n][j]; P->d[n][P->nb[n]+j] = ub[n][j]; }
+		for(j=0; j<P->nbx[n]; j++) { P->d[n][j] = lb[n][j]; P->d[n][P->nb[n]+j] = ub[n][j]; }
+		}
+	}
+
+/* general constraints from the column-major arrays of the high-level API: C[n] ng x nx, D[n] ng x nu (n < N)
+ * (interfaces/c/fortran_order_interface.c:276-283, :371-378) */
+void orc_prob_set_general(orc_prob *P, double *const *C, double *const *D, double *const *lg, double *const *ug)
+	{
+	int n, i, j;
+	for(n=0; n<=P->N; n++)
+		{
+		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, ng = P->ng[n], nbx = P->nbx[n], nt = P->nb[n];
+		for(j=0; j<ng; j++)
+			{
+			for(i=0; i<nu; i++) P->DCt[n][i+nux*j] = D[n][j+ng*i];
+			for(i=0; i<nx; i++) P->DCt[n][nu+i+nux*j] = C[n][j+ng*i];
+			P->d[n][nbx+j] = lg[n][j]; P->d[n][nt+nbx+j] = ug[n][j];
+			}
 		}
 	}
 
@@ -211,9 +260,23 @@ void orc_ric_backward(orc_prob *P, int with_grad, double *const *bvec, double *c
 		if(P->nb[n]>0 && Qx)
 			for(j=0; j<P->nb[n]; j++)
 				{
-				int id = P->idxb[n][j];
-				L[id+nz*id] += Qx[n][j];
-				if(with_grad && qx) L[nux+nz*id] += qx[n][j];
+				if(j<P->nbx[n])
+					{
+					int id = P->idxb[n][j];
+					L[id+nz*id] += Qx[n][j];
+					if(with_grad && qx) L[nux+nz*id] += qx[n][j];
+					}
+				else
+					{
+					/* general constraint: + Qx g g' on the Hessian, + qx g' on the gradient row (d_back_ric_rec.c:293-315) */
+					const double *g = P->DCt[n] + (size_t)nux*(j-P->nbx[n]);
+					int c2;
+					for(c2=0; c2<nux; c2++)
+						{
+						for(i=c2; i<nux; i++) L[i+nz*c2] += Qx[n][j]*g[i]*g[c2];
+						if(with_grad && qx) L[nux+nz*c2] += qx[n][j]*g[c2];
+						}
+					}
 				}
 		/* every kid c of this node (a chain has the one kid n+1; lqcp_solvers/d_tree_back_ric_rec_libstr.c:79-156 sums
 		 * W_c W_c' over the kids); e = c-1 is the edge into the kid */
@@ -380,7 +443,7 @@ void orc_ric_trs(orc_prob *P, double *const *bvec, double *const *rqvec, double 
 		{
 		int nx = P->nx[n], nu = P->nu[n], nux = nx+nu, nz = nux+1;
 		for(i=0; i<nux; i++) w[n][i] = rqvec[n][i];
-		if(P->nb[n]>0 && qx) for(j=0; j<P->nb[n]; j++) w[n][P->idxb[n][j]] += qx[n][j];
+		if(P->nb[n]>0 && qx) for(j=0; j<P->nb[n]; j++) cscatter(P, n, w[n], j, qx[n][j]);
 		int has_kid = 0;
 		for(int c=P->fk[n]; c<P->fk[n]+P->nk[n]; c++)
 			{
@@ -467,10 +530,10 @@ static void ipm_residuals(const orc_prob *P, const orc_ipm_ws *w, double *mu)
 		nb_tot += nb;
 		for(j=0; j<nb; j++)
 			{
-			int id = P->idxb[n][j];
-			rq[id] += -w->lam[n][j] + w->lam[n][nb+j];
-			w->res_d[n][j]    = P->d[n][j]    - w->ux[n][id] + w->t[n][j];
-			w->res_d[n][nb+j] = P->d[n][nb+j] - w->ux[n][id] - w->t[n][nb+j];
+			const double v = cval(P, n, w->ux[n], j);
+			cscatter(P, n, rq, j, -w->lam[n][j] + w->lam[n][nb+j]);
+			w->res_d[n][j]    = P->d[n][j]    - v + w->t[n][j];
+			w->res_d[n][nb+j] = P->d[n][nb+j] - v - w->t[n][nb+j];
 			w->res_m[n][j]    = w->lam[n][j]*w->t[n][j];
 			w->res_m[n][nb+j] = w->lam[n][nb+j]*w->t[n][nb+j];
 			mu2 += w->res_m[n][j] + w->res_m[n][nb+j];
@@ -545,7 +608,7 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 	for(n=0; n<=N; n++)
 		{
 		int nb = P->nb[n];
-		for(j=0; j<nb; j++)
+		for(j=0; j<P->nbx[n]; j++)
 			{
 			int id = P->idxb[n][j];
 			t[n][j]    = -P->d[n][j]    + ux[n][id];
@@ -565,6 +628,18 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 			}
 		}
 	for(n=0; n<N; n++) for(i=0; i<P->nx[n+1]; i++) pi[n][i] = 0.0;
+	/* general constraints, from the ux the bounds have just moved; no projection (c99/d_aux_ip_hard_lib4.c:121-147) */
+	for(n=0; n<=N; n++)
+		{
+		int nb = P->nb[n];
+		for(j=P->nbx[n]; j<nb; j++)
+			{
+			const double v = cval(P, n, ux[n], j);
+			t[n][j] = fmax(thr0, v - P->d[n][j]);
+			t[n][nb+j] = fmax(thr0, -v + P->d[n][nb+j]);
+			lam[n][j] = mu0/t[n][j]; lam[n][nb+j] = mu0/t[n][nb+j];
+			}
+		}
 
 	mu = mu0; *kk = 0; alpha = 1.0;
 	double mu_tol_low = mu_tol<1e-5 ? 1e-5 : mu_tol;
@@ -594,9 +669,9 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 				int nb = P->nb[n];
 				for(j=0; j<nb; j++)
 					{
-					int id = P->idxb[n][j];
-					w->dt[n][j]    =  w->dux[n][id] - P->d[n][j]    - t[n][j];
-					w->dt[n][nb+j] = -w->dux[n][id] + P->d[n][nb+j] - t[n][nb+j];
+					const double dv = cval(P, n, w->dux[n], j);
+					w->dt[n][j]    =  dv - P->d[n][j]    - t[n][j];
+					w->dt[n][nb+j] = -dv + P->d[n][nb+j] - t[n][nb+j];
 					w->dlam[n][j]    -= w->lamt[n][j]*w->dt[n][j] + lam[n][j];
 					w->dlam[n][nb+j] -= w->lamt[n][nb+j]*w->dt[n][nb+j] + lam[n][nb+j];
 					if(-alpha*w->dlam[n][j]>lam[n][j]) alpha = -lam[n][j]/w->dlam[n][j];
@@ -678,9 +753,9 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 				int nb = P->nb[n];
 				for(j=0; j<nb; j++)
 					{
-					int id = P->idxb[n][j];
-					w->dt[n][j]    =  w->dux[n][id] - w->res_d[n][j];
-					w->dt[n][nb+j] = -w->dux[n][id] + w->res_d[n][nb+j];
+					const double dv = cval(P, n, w->dux[n], j);
+					w->dt[n][j]    =  dv - w->res_d[n][j];
+					w->dt[n][nb+j] = -dv + w->res_d[n][nb+j];
 					w->dlam[n][j]    = -w->tinv[n][j]*(lam[n][j]*w->dt[n][j] + w->res_m[n][j]);
 					w->dlam[n][nb+j] = -w->tinv[n][nb+j]*(lam[n][nb+j]*w->dt[n][nb+j] + w->res_m[n][nb+j]);
 					if(-alpha*w->dlam[n][j]>lam[n][j]) alpha = -lam[n][j]/w->dlam[n][j];
@@ -794,8 +869,8 @@ int orc_kkt_solve_new_rhs(orc_prob *P, double *const *bnew, double *const *rqnew
 		int nux = nux_(P,n), nb = P->nb[n]; const double *ti = P->k_tinv[n];
 		for(j=0; j<nb; j++)
 			{
-			int id = P->idxb[n][j];
-			double dtl =  w->dux[n][id] - w->res_d[n][j], dtu = -w->dux[n][id] + w->res_d[n][nb+j];
+			const double dv = cval(P, n, w->dux[n], j);
+			double dtl =  dv - w->res_d[n][j], dtu = -dv + w->res_d[n][nb+j];
 			double dll = -ti[j]*(lam[n][j]*dtl + w->res_m[n][j]), dlu = -ti[nb+j]*(lam[n][nb+j]*dtu + w->res_m[n][nb+j]);
 			lam[n][j] += 1.0*dll; lam[n][nb+j] += 1.0*dlu; t[n][j] += 1.0*dtl; t[n][nb+j] += 1.0*dtu;
 			}
@@ -824,11 +899,11 @@ void orc_exit_residuals(const orc_prob *P, double *const *ux, double *const *pi,
 		nb_tot += nb;
 		for(j=0; j<nb; j++)
 			{
-			int id = P->idxb[n][j];
-			rq[id] += -lam[n][j] + lam[n][nb+j];
+			const double v = cval(P, n, ux[n], j);
+			cscatter(P, n, rq, j, -lam[n][j] + lam[n][nb+j]);
 			mu += lam[n][j]*t[n][j] + lam[n][nb+j]*t[n][nb+j];
-			nd = fmax(nd, fabs(ux[n][id] - P->d[n][j] - t[n][j]));
-			nd = fmax(nd, fabs(-ux[n][id] + P->d[n][nb+j] - t[n][nb+j]));
+			nd = fmax(nd, fabs(v - P->d[n][j] - t[n][j]));
+			nd = fmax(nd, fabs(-v + P->d[n][nb+j] - t[n][nb+j]));
 			}
 		for(i=0; i<nux; i++)
 			{
@@ -871,10 +946,12 @@ int orc_fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu
 		double **R, double **q, double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
 		double **x, double **u, double **pi, double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)ng; (void)N2; (void)C; (void)D; (void)lg; (void)ug; (void)work0;
-	int n, i, j, l;
-	orc_prob *P = orc_prob_create(N, nx, nu_N, nb, hidxb);
+	(void)N2; (void)work0;
+	int n, i, j, l, any_g = 0;
+	if(ng) for(n=0; n<=N; n++) if(ng[n]>0) any_g = 1;
+	orc_prob *P = orc_prob_create_gen(N, nx, nu_N, nb, hidxb, NULL, any_g ? ng : NULL);
 	orc_prob_set(P, A, B, b, Q, S, R, q, r, lb, ub);
+	if(any_g) orc_prob_set_general(P, C, D, lg, ug);
 	/* mu0 estimate: signed max over cost entries (fortran_order_interface.c:318-331) */
 	if(mu0<=0)
 		{
@@ -907,7 +984,13 @@ int orc_fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu
 			if(lb[n][j]==ub[n][j]) u[n][hidxb[n][j]] = lb[n][j];
 	orc_exit_residuals(P, hux, hpi, hlam, ht, inf_norm_res);
 	for(n=0; n<N; n++) for(i=0; i<nx[n+1]; i++) pi[n][i] = hpi[n][i];
-	for(n=0; n<=N; n++) for(j=0; j<2*nb[n]; j++) lam[n][j] = hlam[n][j];
+	/* lam as [lb ub lg ug] per stage, the lib4 order (interfaces/c/fortran_order_interface.c:662-681) */
+	for(n=0; n<=N; n++)
+		{
+		const int nbx = P->nbx[n], g = P->ng[n], nt = P->nb[n];
+		for(j=0; j<nbx; j++) { lam[n][j] = hlam[n][j]; lam[n][nbx+j] = hlam[n][nt+j]; }
+		for(j=0; j<g; j++) { lam[n][2*nbx+j] = hlam[n][nbx+j]; lam[n][2*nbx+g+j] = hlam[n][nt+nbx+j]; }
+		}
 	for(n=0; n<=N; n++) { free(hux[n]); free(hpi[n]); free(hlam[n]); free(ht[n]); }
 	free(hux); free(hpi); free(hlam); free(ht);
 	orc_prob_free(P);

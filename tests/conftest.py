@@ -38,3 +38,18 @@ def rel_err(a, b):
         if y.size:
             worst = max(worst, float(np.max(np.abs(x - y) / np.maximum(1.0, np.abs(y)))))
     return worst
+
+
+def rel_err_true(a, b, floor=1e-6):
+    """TRUE relative error, max over the entries of |a-b| / max(|b|, floor*||b||_inf) per vector: small entries (inactive
+    multipliers ~1e-8) are measured against their own size down to `floor` times the largest entry of their vector, below which
+    a value is rounding noise of the sums it came from.  VERDICT r1: the max(1,|b|) metric hides 10 % errors on inactive lam."""
+    import numpy as np
+    worst = 0.0
+    for x, y in zip(a, b):
+        x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        assert x.shape == y.shape, (x.shape, y.shape)
+        if y.size:
+            den = np.maximum(np.abs(y), floor * float(np.max(np.abs(y))) + 1e-300)
+            worst = max(worst, float(np.max(np.abs(x - y) / den)))
+    return worst
