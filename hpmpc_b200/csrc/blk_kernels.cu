@@ -6,6 +6,17 @@
 #include "layout.h"
 #include "ric_fast.cuh"
 #include "ric_blk.cuh"
+#ifndef HBK_DEFAULT_FLAGS
+/* measured on B200 (profiles/r02_sv_traffic.txt): evict-first on the single-use streams, evict-last + discard on the stash cuts
+ * the DRAM traffic of the sv kernel from 231 to 199 KB per solve (time unchanged: the kernel is shared-memory-pipe bound) */
+#ifdef HBK_BULK_STASH
+#define HBK_DEFAULT_FLAGS (HBK_F_IN_FIRST|HBK_F_RE_FIRST|HBK_F_KEEP|HBK_F_DISCARD)
+#define HBK_DEFAULT_KEEP 1000
+#else
+#define HBK_DEFAULT_FLAGS (HBK_F_IN_FIRST|HBK_F_RE_FIRST)
+#define HBK_DEFAULT_KEEP 0
+#endif
+#endif
 
 /* ------------------------------------------------------------------------------------------------ */
 /* size-specialised variants (ric_blk.cuh: register-blocked; ric_fast.cuh: one row per lane)          */
@@ -45,7 +56,7 @@ template<class C> static void hbf_info(int N, int *ipw, int *smem_warp, long lon
 	}
 template<class C> static void hbk_info(int N, int *ipw, int *smem_warp, long long *stash_per_inst)
 	{
-	*ipw = C::IPW; *smem_warp = (int)sizeof(double)*C::PER_WARP; *stash_per_inst = (long long)(N+1)*C::SB;
+	*ipw = C::IPW; *smem_warp = (int)sizeof(double)*C::PER_WARP; *stash_per_inst = (long long)(N+1)*C::SBG;
 	}
 
 extern "C" int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst)
@@ -114,10 +125,40 @@ template<class C> static int hbk_launch(const hb_dims *d, long long n_inst, cons
 	cfg.gridDim = dim3(grid); cfg.blockDim = dim3(warps*32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
 	cudaLaunchAttribute attr[1];
 	cfg.attrs = attr;
-	cfg.numAttrs = hb_stash_window(&attr[0], stash, sizeof(double)*(size_t)grid*warps*C::IPW*(size_t)(d->N+1)*C::SB);
-	HB_CK(cudaLaunchKernelEx(&cfg, hbk_ric_sv_kernel<C>, *d, n_inst, in, ux, pi, stash));
+	cfg.numAttrs = hb_stash_window(&attr[0], stash, sizeof(double)*(size_t)grid*warps*C::IPW*(size_t)(d->N+1)*C::SBG);
+	/* L2 management of the stash (ric_blk.cuh: HBK_F_*); HPMPC_B200_SV_FLAGS / HPMPC_B200_SV_KEEP override the defaults for A/B runs */
+	static int flags = -1, keep = -1;
+	if(flags<0)
+		{
+		const char *e = getenv("HPMPC_B200_SV_FLAGS"), *k = getenv("HPMPC_B200_SV_KEEP");
+		keep = k ? atoi(k) : HBK_DEFAULT_KEEP;
+		flags = e ? atoi(e) : HBK_DEFAULT_FLAGS;
+		}
+	HB_CK(cudaLaunchKernelEx(&cfg, hbk_ric_sv_kernel<C>, *d, n_inst, in, ux, pi, stash, flags, keep));
 	HB_CK(cudaGetLastError());
 	return 0;
+	}
+
+/* traffic-equivalent probe of the sv kernel (ric_blk.cuh: hbk_traffic_kernel); same launch shape, same flags */
+template<class C> static int hbk_traffic_launch(const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi,
+		double *stash, int grid, int warps, cudaStream_t st)
+	{
+#ifdef HBK_BULK_STASH
+	int smem = warps*(int)sizeof(double)*C::PER_WARP;
+	if(hb_prep(hbk_traffic_kernel<C>, smem)) return -1;
+	const char *e = getenv("HPMPC_B200_SV_FLAGS"), *k = getenv("HPMPC_B200_SV_KEEP");
+	hbk_traffic_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_inst, in, ux, pi, stash, e ? atoi(e) : HBK_DEFAULT_FLAGS, k ? atoi(k) : HBK_DEFAULT_KEEP);
+	HB_CK(cudaGetLastError());
+	return 0;
+#else
+	return -2;
+#endif
+	}
+extern "C" int hb_launch_sv_traffic(int id, const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi,
+		double *stash, int grid, int warps, void *stream)
+	{
+	if(id==0) return hbk_traffic_launch<hbk_v0>(d, n_inst, in, ux, pi, stash, grid, warps, (cudaStream_t)stream);
+	return -2;
 	}
 
 extern "C" int hb_launch_ric_sv_fast(int id, const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi,

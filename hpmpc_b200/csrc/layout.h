@@ -137,6 +137,8 @@ int hb_fast_variant(int N, const int *nx, const int *nu);
 int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst);
 int hb_launch_ric_sv_fast(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, void *stream);
+int hb_launch_sv_traffic(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
+		double *stash, int grid, int warps, void *stream);
 int hb_launch_tree(const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
 		int mode /* 0 backward, 1 forward, 2 backward then forward */, int seg_lo, int seg_hi, int grid, int warps, void *stream);
 int hb_tail_variant(int nx, int nu);                     /* -1 when no size-specialised tail kernel exists */

@@ -490,6 +490,21 @@ int hpmpc_b200_d_back_ric_rec_sv_upd_batch(hpmpc_b200_ocp *p, long long n_inst, 
 	return call_end(p, stream, hb_launch_ric_sv(&p->dims, n_inst, d_in, d_ux, d_pi, d_Pb, p->scratch, p->n_slots, grid_for(p, n_inst), p->warps, stream, d_Qx, d_qx));
 	}
 
+/* MEASUREMENT TOOL: the memory traffic of hpmpc_b200_d_back_ric_rec_sv_batch (same bulk copies, same L2 hints, same output stores)
+ * without the arithmetic -- the ceiling the memory system sets for the two-sweep access pattern.  d_ux / d_pi receive
+ * meaningless values.  Only for the config-2 shape (nx = 12, nu = 5, x0 eliminated); -2 otherwise. */
+int hpmpc_b200_sv_traffic_probe(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_ux, double *d_pi, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0 || p->fast_id!=0) return -2;
+	CK(cudaSetDevice(p->device));
+	if(call_begin(p, stream)) return -1;
+	long long groups = (n_inst + p->f_ipw - 1)/p->f_ipw, need = (groups + p->f_warps - 1)/p->f_warps;
+	int grid = (int)(need<p->f_grid ? need : p->f_grid);
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->f_grid*p->f_warps*p->f_ipw*p->f_stash_inst)) return -1;
+	return call_end(p, stream, hb_launch_sv_traffic(p->fast_id, &p->dims, n_inst, d_in, d_ux, d_pi, p->scratch, grid, p->f_warps, stream));
+	}
+
 int hpmpc_b200_d_back_ric_rec_trf_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_L, void *stream)
 	{
 	return hpmpc_b200_d_back_ric_rec_trf_upd_batch(p, n_inst, d_in, NULL, d_L, stream);

@@ -53,6 +53,11 @@ struct hbk_cfg
 	static constexpr int Sk = even(NU*NX);                                   /* k */
 	static constexpr int SX = Sk + even(NU);                                 /* x-columns */
 	static constexpr int SB = SX + xOff(NX);
+#ifdef HBK_BULK_STASH
+	static constexpr int SBG = (SB+15)&~15;                                  /* image stride in the sv kernel's stash: whole 128-byte lines */
+#else
+	static constexpr int SBG = SB;
+#endif
 	static constexpr int LDW = ((even(NX)/2)%2==0) ? even(NX)+2 : even(NX);
 	static constexpr int BAB = even(NZ*NX);
 	static constexpr int RSQ = even(HB_TRI(NUX)+NUX);
@@ -63,7 +68,19 @@ struct hbk_cfg
 	static constexpr int XS = even(NX);
 	static constexpr int VEC = even(NU) + 3*XS;
 	static constexpr int PER_INST = IOB + LU + 2*SB + VEC;
+#ifndef HBK_NO_SKEW
+	/* Bank skew between the instances of a warp.  The instances' buffers start at (0, 8, 4, 12, 2, 10, 6, 14) doubles mod 16:
+	 * a broadcast LDS.128 (one 16-byte chunk per instance) then touches disjoint banks for all instances of the warp, and the
+	 * one-row-per-lane LDS.64 of the packed triangles (row offsets i(i+1)/2, a complete residue system mod 16 that uses half of
+	 * the 16 double-slots) of the two instances that share a half-warp interleave exactly (offset 8) instead of colliding
+	 * (ncu r01: 23 % of the shared-memory wavefronts were bank conflicts with the uniform stride PER_INST = 6 mod 16). */
+	__host__ __device__ static constexpr int skew_target(int g) { return ((g&1)<<3) | ((g&2)<<1) | ((g&4)>>1); }
+	__host__ __device__ static constexpr int inst_off(int g) { return g*PER_INST + ((skew_target(g) - g*PER_INST) & 15); }
+	static constexpr int PER_WARP = IPW*PER_INST + 8 + 16;
+#else
+	__host__ __device__ static constexpr int inst_off(int g) { return g*PER_INST; }
 	static constexpr int PER_WARP = IPW*PER_INST + 8;
+#endif
 	static constexpr int KS = (RO>CO) ? CO : CO-1;                           /* off-diagonal columns some row-owned row uses */
 	static_assert(NX%2==0, "NX must be even (16-byte rows)");
 	static_assert(NU<=GR && NX<GR, "one u-column / x-column (and the gradient) per lane slot");
@@ -372,7 +389,9 @@ __device__ __forceinline__ void hbk_back_assemble(const hbk_lane<C> &ln, double 
 /* ------------------------------------------------------------------------------------------------ */
 /* Xc: where the x-columns go in shared memory ; gS: stash image of the stage in global memory ; after_u() is called once the
  * u-columns (and K, k) are done and the scratch LUs is dead */
-template<class C, int KIND, class F>
+/* GIMG = false: gS is the image buffer in shared memory that Xc points into (Xc = gS + SX): the x-columns are already there,
+ * only K and k are added, and the caller moves the finished image to global memory with one bulk store */
+template<class C, int KIND, class F, bool GIMG = true>
 __device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<C> &T, double *__restrict__ LUs, double *__restrict__ Xc,
 		double *__restrict__ gS, F after_u)
 	{
@@ -406,7 +425,7 @@ __device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<
 			if((s>so || v>=c) && v<RO)
 				{
 				col[v-c] = lc[s];
-				if(c>=NU) gS[C::SX + C::xOff(c>=NU ? c-NU : 0) + (v-c)] = lc[s];      /* x-columns go to the stash as they are finished */
+				if(GIMG && c>=NU) gS[C::SX + C::xOff(c>=NU ? c-NU : 0) + (v-c)] = lc[s];      /* x-columns go to the stash as they are finished */
 				}
 			}
 		if(l==lo)
@@ -416,7 +435,7 @@ __device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<
 				{
 				const double le = T.X[e][so]*inv;
 				col[RO+e-c] = le;
-				if(c>=NU) gS[C::SX + C::xOff(c>=NU ? c-NU : 0) + (RO+e-c)] = le;
+				if(GIMG && c>=NU) gS[C::SX + C::xOff(c>=NU ? c-NU : 0) + (RO+e-c)] = le;
 				}
 			if(c<NU) LUs[C::UDINV+c] = inv;
 			}
@@ -498,7 +517,7 @@ __device__ __forceinline__ void hbk_back_factor(const hbk_lane<C> &ln, hbk_tile<
 			for(int e=cc; e<E; e++)
 				{
 				col[e-cc] = lcol[e];
-				if(CO+cc>=NU) gS[C::SX + C::xOff(CO+cc>=NU ? CO+cc-NU : 0) + (e-cc)] = lcol[e];
+				if(GIMG && CO+cc>=NU) gS[C::SX + C::xOff(CO+cc>=NU ? CO+cc-NU : 0) + (e-cc)] = lcol[e];
 				}
 			if(CO+cc<NU) LUs[C::UDINV+CO+cc] = rsc;
 			}
@@ -635,11 +654,25 @@ __device__ __forceinline__ void hbk_final_pi(const hbk_lane<C> &ln, const double
 /* ------------------------------------------------------------------------------------------------ */
 /* kernel: persistent warps, IPW instances per warp                                                  */
 /* ------------------------------------------------------------------------------------------------ */
+/* L2 management of the factor stash (flags, set by the launcher):
+ *   HBK_F_IN_FIRST    stage inputs of the backward sweep are fetched evict-first (single use: RSQrq; [B A b]' is re-read a whole
+ *                     sweep later, by which time it has left L2 anyway)
+ *   HBK_F_RE_FIRST    the forward sweep's re-read of [B A b]' is fetched evict-first (dead afterwards)
+ *   HBK_F_KEEP        (bulk-store build) images of stages n < keep_n0 are written evict-last, the others evict-first: the images
+ *                     with the shortest write-to-read distance are the ones worth keeping on chip
+ *   HBK_F_DISCARD     an image is dropped from L2 (discard.global.L2, no write-back) as soon as the forward sweep has fetched it:
+ *                     the slot is rewritten by the warp's next instance, its old content is dead
+ * HBK_BULK_STASH (compile time): the image of a stage is completed in shared memory (K, k next to the x-columns) and moved to
+ * the stash with ONE bulk store per instance and stage instead of 162 STG.64; images 0 and 1 never leave shared memory. */
+#define HBK_F_IN_FIRST 1
+#define HBK_F_RE_FIRST 2
+#define HBK_F_KEEP 4
+#define HBK_F_DISCARD 8
 template<class C>
 __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
-		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ stash)
+		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ stash, int flags, int keep_n0)
 	{
-	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
+	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, SBG = C::SBG, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
 	extern __shared__ __align__(16) double hbf_smem[];
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const int g = lane/G;
@@ -647,7 +680,7 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
 	double *wbase = hbf_smem + (size_t)warp*C::PER_WARP;
 	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);      /* [0] stage inputs / [B A b]' slot 0, [1] [B A b]' slot 1, [2..3] stash images */
-	double *ibase = wbase + 8 + (size_t)g*C::PER_INST;
+	double *ibase = wbase + 8 + C::inst_off(g);
 	double *io = ibase;
 	double *LUs = ibase + IOB;
 	double *S0 = LUs + LU, *S1 = S0 + SB;
@@ -664,9 +697,14 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 	constexpr uint32_t bytes_first = 8u*(uint32_t)(C::even((NU+1)*NX) + C::even(HB_TRI(NU)+NU));
 	constexpr uint32_t bytes_mid = 8u*(uint32_t)C::INB;
 	constexpr uint32_t bytes_last = 8u*(uint32_t)C::even(HB_TRI(NX)+NX);
-	const long long stash_stride = (long long)(N+1)*SB;
+	const long long stash_stride = (long long)(N+1)*SBG;
 	const long long n_groups = (n_inst + IPW - 1)/IPW;
 	double *stash_w = stash + gw*IPW*stash_stride;
+	const uint64_t pol_first = hbf_policy_evict_first();
+#ifdef HBK_BULK_STASH
+	const uint64_t pol_last = hbf_policy_evict_last(), pol_norm = hbf_policy_evict_normal();
+#endif
+	const bool in_first = (flags&HBK_F_IN_FIRST)!=0, re_first = (flags&HBK_F_RE_FIRST)!=0, discard = (flags&HBK_F_DISCARD)!=0;
 
 	for(long long grp=gw; grp<n_groups; grp+=tw)
 		{
@@ -677,43 +715,56 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 
 		/* lanes 0..IPW-1 each move the data of one instance of the warp (one bulk copy per lane and buffer);
 		 * lane 0 posts the byte count, one mbarrier per buffer */
-#ifdef HBK_L2_HINTS
-		const uint64_t pol_first = hbf_policy_evict_first();
-#endif
 		const int mg = lane<IPW ? lane : 0;
 		long long my_i = grp*IPW + mg; if(my_i>=n_inst) my_i = n_inst-1;
 		const double *my_in = in + my_i*d.in_stride;
-		double *my_sm = wbase + 8 + (size_t)mg*C::PER_INST;
+		double *my_sm = wbase + 8 + C::inst_off(mg);
 		double *my_st = stash_w + mg*stash_stride;
 		auto issue_backward = [&](int n)                          /* [B A b]'_n | RSQrq_n -> io */
 			{
 			const int off = (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in);
 			const uint32_t bytes = (n==0) ? bytes_first : (n==N ? bytes_last : bytes_mid);
 			if(lane==0) hbf_mbar_expect(&bars[0], bytes*IPW);
-			if(lane<IPW) hbf_bulk_g2s(my_sm, my_in + off, bytes, &bars[0]);
+			if(lane<IPW)
+				{
+				if(in_first) hbf_bulk_g2s_hint(my_sm, my_in + off, bytes, &bars[0], pol_first);
+				else hbf_bulk_g2s(my_sm, my_in + off, bytes, &bars[0]);
+				}
 			};
 		auto issue_BAbt = [&](int n, int slot)                    /* forward: [B A b]'_n -> io + slot*BAB */
 			{
 			const int off = (n==0) ? 0 : o_in1 + (n-1)*s_in;
 			const uint32_t bytes = (n==0) ? 8u*(uint32_t)C::even((NU+1)*NX) : 8u*(uint32_t)BAB;
 			if(lane==0) hbf_mbar_expect(&bars[slot], bytes*IPW);
-#ifdef HBK_L2_HINTS
-			if(lane<IPW) hbf_bulk_g2s_hint(my_sm + slot*BAB, my_in + off, bytes, &bars[slot], pol_first);
-#else
-			if(lane<IPW) hbf_bulk_g2s(my_sm + slot*BAB, my_in + off, bytes, &bars[slot]);
-#endif
+			if(lane<IPW)
+				{
+				if(re_first) hbf_bulk_g2s_hint(my_sm + slot*BAB, my_in + off, bytes, &bars[slot], pol_first);
+				else hbf_bulk_g2s(my_sm + slot*BAB, my_in + off, bytes, &bars[slot]);
+				}
 			};
 		auto issue_S = [&](int n, int slot)                       /* forward: stash image of stage n -> S[slot] */
 			{
 			if(lane==0) hbf_mbar_expect(&bars[2+slot], 8u*SB*IPW);
-#ifdef HBK_L2_HINTS
-			if(lane<IPW) hbf_bulk_g2s_hint(my_sm + IOB + LU + slot*SB, my_st + (long long)n*SB, 8u*SB, &bars[2+slot], pol_first);
-#else
-			if(lane<IPW) hbf_bulk_g2s(my_sm + IOB + LU + slot*SB, my_st + (long long)n*SB, 8u*SB, &bars[2+slot]);
-#endif
+			if(lane<IPW) hbf_bulk_g2s(my_sm + IOB + LU + slot*SB, my_st + (long long)n*SBG, 8u*SB, &bars[2+slot]);
 			};
 		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
-		double *gst = stash_w + g*stash_stride;                 /* this instance's stash slot: images written with plain stores */
+		double *gst = stash_w + g*stash_stride;                 /* this instance's stash slot */
+#ifdef HBK_BULK_STASH
+		/* the finished image of stage n (in S[n&1]) -> stash, one bulk store per instance; the buffer may be rewritten once the
+		 * store has read it (wait_img_read before the factorisation of stage n-2) */
+		auto store_img = [&](int n)
+			{
+			hbf_fence_async();                                    /* generic-proxy writes of the image -> visible to the bulk copy */
+			__syncwarp();
+			if(lane<IPW)
+				{
+				const uint64_t pol = (flags&HBK_F_KEEP) ? (n<keep_n0 ? pol_last : pol_first) : pol_norm;
+				hbf_bulk_s2g_hint(my_st + (long long)n*SBG, my_sm + IOB + LU + (n&1)*SB, 8u*SB, pol);
+				hbf_bulk_commit();
+				}
+			};
+		auto wait_img_read = [&]() { if(lane<IPW) hbf_bulk_wait_read<1>(); __syncwarp(); };
+#endif
 
 		/* ---------------- backward sweep: stage n builds S[n&1], reads the x-columns in S[(n+1)&1] ---------------- */
 		issue_backward(N);
@@ -722,7 +773,12 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 		wait_bar(0);
 		hbk_back_assemble<C, HBF_LAST, C::LDW>(ln, io, io, nullptr, T, hbk_nop());
 		issue_backward(N-1);
-		hbk_back_factor<C, HBF_LAST>(ln, T, LUs, ((N&1) ? S1 : S0) + C::SX, gst + (long long)N*SB, hbk_nop());
+#ifdef HBK_BULK_STASH
+		hbk_back_factor<C, HBF_LAST, hbk_nop, false>(ln, T, LUs, ((N&1) ? S1 : S0) + C::SX, (N&1) ? S1 : S0, hbk_nop());
+		store_img(N);
+#else
+		hbk_back_factor<C, HBF_LAST>(ln, T, LUs, ((N&1) ? S1 : S0) + C::SX, gst + (long long)N*SBG, hbk_nop());
+#endif
 		}
 		for(int n=N-1; n>0; n--)
 			{
@@ -736,26 +792,60 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 			HBF_STAMP(102);
 			issue_backward(n-1);                                  /* lands while the factorization runs */
 			HBF_STAMP(103);
-			hbk_back_factor<C, HBF_MID>(ln, T, LUs, Sc + C::SX, gst + (long long)n*SB, hbk_nop());
+#ifdef HBK_BULK_STASH
+			wait_img_read();                                      /* the store of image n+2 has left this buffer */
+			hbk_back_factor<C, HBF_MID, hbk_nop, false>(ln, T, LUs, Sc + C::SX, Sc, hbk_nop());
+			if(n>=2) store_img(n);                                /* images 0 and 1 stay in shared memory for the forward sweep */
+#else
+			hbk_back_factor<C, HBF_MID>(ln, T, LUs, Sc + C::SX, gst + (long long)n*SBG, hbk_nop());
+#endif
 			HBF_STAMP(104);
 			}
 		{
 		hbk_tile<C> T;
 		wait_bar(0);
 		hbk_back_assemble<C, HBF_FIRST, C::LDW>(ln, io, io + C::even((NU+1)*NX), S1 + C::SX, T, hbk_nop());
+#ifdef HBK_BULK_STASH
+		wait_img_read();
+		hbk_back_factor<C, HBF_FIRST, hbk_nop, false>(ln, T, LUs, S0 + C::SX, S0, hbk_nop());
+		if(lane<IPW) hbf_bulk_wait_all<0>();                      /* every image is in the stash before any is fetched back */
+		__syncwarp();
+#else
 		hbk_back_factor<C, HBF_FIRST>(ln, T, LUs, S0 + C::SX, gst, hbk_nop());
+#endif
 		}
+#ifndef HBK_BULK_STASH
 		/* the images were written through the generic proxy and are read back by bulk copies (async proxy) */
 		asm volatile("fence.proxy.async;" ::: "memory");
 		__syncwarp();
+#endif
+
+		/* an image that has been fetched is dead: drop its lines from L2 before they are written back (the slot is rewritten by
+		 * the next instance of this warp).  Needs whole 128-byte lines per image (SBG). */
+		auto drop_img = [&](int n)
+			{
+			if(discard && (SBG%16)==0)
+				{
+				const double *img = gst + (long long)n*SBG;
+				#pragma unroll
+				for(int q=ln.l; q<SBG/16; q+=G) hbf_discard_line(img + 16*q);
+				}
+			};
 
 		/* ---------------- forward sweep ---------------- */
+#ifdef HBK_BULK_STASH
+		issue_BAbt(0, 0);
+		if(N>1) issue_BAbt(1, 1);
+		wait_bar(0);
+#else
 		issue_S(0, 0);
 		issue_BAbt(0, 0);
 		issue_S(1, 1);
 		if(N>1) issue_BAbt(1, 1);
 		wait_bar(2);
 		wait_bar(0);
+		drop_img(0);
+#endif
 		hbk_stage_forward<C, HBF_FIRST>(ln, io, S0, us, xs0, xs1, tmp, ux, ux + NU + ((1<N) ? NU : 0), pi, active);
 		if(2<=N) issue_S(2, 0);
 		if(2<N) issue_BAbt(2, 0);
@@ -765,7 +855,12 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 			const double *xs = (n&1) ? xs1 : xs0;
 			double *xo = (n&1) ? xs0 : xs1;
 			HBF_STAMP(200);
+#ifdef HBK_BULK_STASH
+			if(n>=2) { wait_bar(2+(n&1)); drop_img(n); }          /* image 1 is still in shared memory */
+#else
 			wait_bar(2+(n&1));                                    /* image n */
+			drop_img(n);
+#endif
 			wait_bar(n&1);                                        /* [B A b]'_n */
 			HBF_STAMP(201);
 			const int o_ux = NU + (n-1)*NUX, o_ux1 = NU + n*NUX + ((n+1<N) ? NU : 0);
@@ -774,10 +869,145 @@ __global__ void __launch_bounds__(256, 1) hbk_ric_sv_kernel(hb_dims d, long long
 			if(n+2<=N) issue_S(n+2, n&1);
 			if(n+2<N) issue_BAbt(n+2, n&1);
 			}
+#ifdef HBK_BULK_STASH
+		if(N>=2) { wait_bar(2+(N&1)); drop_img(N); }
+#else
 		wait_bar(2+(N&1));
+		drop_img(N);
+#endif
 		hbk_final_pi<C>(ln, (N&1) ? S1 : S0, (N&1) ? xs1 : xs0, tmp, pi + (N-1)*NX, active);
 		}
 	}
+
+#ifdef HBK_BULK_STASH
+/* ------------------------------------------------------------------------------------------------ */
+/* Traffic-equivalent probe of hbk_ric_sv_kernel: the same persistent loop, the same bulk copies in the  */
+/* same order with the same L2 hints (stage inputs, stash images out and back, [B A b]' re-read), the   */
+/* same output stores -- and NO arithmetic.  Its rate is the ceiling the memory system sets for this     */
+/* two-sweep access pattern at this occupancy; the sv kernel's distance from it is what the stage         */
+/* arithmetic (shared-memory pipe, pivot chains) costs.  Measurement tool, not part of the solver.        */
+/* ------------------------------------------------------------------------------------------------ */
+template<class C>
+__global__ void __launch_bounds__(256, 1) hbk_traffic_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ stash, int flags, int keep_n0)
+	{
+	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, SBG = C::SBG, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
+	extern __shared__ __align__(16) double hbf_smem[];
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const int g = lane/G, l = lane%G;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	double *wbase = hbf_smem + (size_t)warp*C::PER_WARP;
+	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);
+	double *ibase = wbase + 8 + C::inst_off(g);
+	double *S0 = ibase + IOB + LU;
+	if(lane==0)
+		{
+		for(int b=0; b<4; b++) hbf_mbar_init(&bars[b], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+	__syncwarp();
+	uint32_t phase = 0;
+	const int N = d.N;
+	const int o_in1 = d.st[1].off_BAbt, s_in = d.st[2].off_BAbt - d.st[1].off_BAbt, o_inN = d.st[N].off_BAbt;
+	constexpr uint32_t bytes_first = 8u*(uint32_t)(C::even((NU+1)*NX) + C::even(HB_TRI(NU)+NU));
+	constexpr uint32_t bytes_mid = 8u*(uint32_t)C::INB;
+	constexpr uint32_t bytes_last = 8u*(uint32_t)C::even(HB_TRI(NX)+NX);
+	const long long stash_stride = (long long)(N+1)*SBG;
+	const long long n_groups = (n_inst + IPW - 1)/IPW;
+	double *stash_w = stash + gw*IPW*stash_stride;
+	const uint64_t pol_first = hbf_policy_evict_first(), pol_last = hbf_policy_evict_last(), pol_norm = hbf_policy_evict_normal();
+	const bool in_first = (flags&HBK_F_IN_FIRST)!=0, re_first = (flags&HBK_F_RE_FIRST)!=0, discard = (flags&HBK_F_DISCARD)!=0;
+	for(long long grp=gw; grp<n_groups; grp+=tw)
+		{
+		long long inst = grp*IPW + g;
+		const bool active = inst<n_inst;
+		if(!active) inst = n_inst-1;
+		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+		const int mg = lane<IPW ? lane : 0;
+		long long my_i = grp*IPW + mg; if(my_i>=n_inst) my_i = n_inst-1;
+		const double *my_in = in + my_i*d.in_stride;
+		double *my_sm = wbase + 8 + C::inst_off(mg);
+		double *my_st = stash_w + mg*stash_stride;
+		double *gst = stash_w + g*stash_stride;
+		auto issue_backward = [&](int n)
+			{
+			const int off = (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in);
+			const uint32_t bytes = (n==0) ? bytes_first : (n==N ? bytes_last : bytes_mid);
+			if(lane==0) hbf_mbar_expect(&bars[0], bytes*IPW);
+			if(lane<IPW) { if(in_first) hbf_bulk_g2s_hint(my_sm, my_in + off, bytes, &bars[0], pol_first); else hbf_bulk_g2s(my_sm, my_in + off, bytes, &bars[0]); }
+			};
+		auto issue_BAbt = [&](int n, int slot)
+			{
+			const int off = (n==0) ? 0 : o_in1 + (n-1)*s_in;
+			const uint32_t bytes = (n==0) ? 8u*(uint32_t)C::even((NU+1)*NX) : 8u*(uint32_t)BAB;
+			if(lane==0) hbf_mbar_expect(&bars[slot], bytes*IPW);
+			if(lane<IPW) { if(re_first) hbf_bulk_g2s_hint(my_sm + slot*BAB, my_in + off, bytes, &bars[slot], pol_first); else hbf_bulk_g2s(my_sm + slot*BAB, my_in + off, bytes, &bars[slot]); }
+			};
+		auto issue_S = [&](int n, int slot)
+			{
+			if(lane==0) hbf_mbar_expect(&bars[2+slot], 8u*SB*IPW);
+			if(lane<IPW) hbf_bulk_g2s(my_sm + IOB + LU + slot*SB, my_st + (long long)n*SBG, 8u*SB, &bars[2+slot]);
+			};
+		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
+		auto store_img = [&](int n)
+			{
+			hbf_fence_async();
+			__syncwarp();
+			if(lane<IPW)
+				{
+				const uint64_t pol = (flags&HBK_F_KEEP) ? (n<keep_n0 ? pol_last : pol_first) : pol_norm;
+				hbf_bulk_s2g_hint(my_st + (long long)n*SBG, my_sm + IOB + LU + (n&1)*SB, 8u*SB, pol);
+				hbf_bulk_commit();
+				}
+			};
+		auto drop_img = [&](int n)
+			{
+			if(discard && (SBG%16)==0)
+				for(int q=l; q<SBG/16; q+=G) hbf_discard_line(gst + (long long)n*SBG + 16*q);
+			};
+		/* the outputs of one stage: u (NU), x (NX), pi (NX), written by the lanes of the instance like the solver does */
+		auto write_out = [&](int n)
+			{
+			if(!active) return;
+			const double v = S0[l];                               /* something that depends on the fetched data */
+			const int o_ux = (n==0) ? 0 : NU + (n-1)*NUX;
+			for(int i=l; i<NUX; i+=G) ux[o_ux + i] = v;
+			if(n>0) for(int i=l; i<NX; i+=G) pi[(n-1)*NX + i] = v;
+			};
+		issue_backward(N);
+		for(int n=N; n>=0; n--)
+			{
+			wait_bar(0);
+			__syncwarp();
+			if(n>0) issue_backward(n-1);
+			if(lane<IPW) hbf_bulk_wait_read<1>();
+			__syncwarp();
+			if(n>=2) store_img(n);
+			}
+		if(lane<IPW) hbf_bulk_wait_all<0>();
+		__syncwarp();
+		issue_BAbt(0, 0);
+		if(N>1) issue_BAbt(1, 1);
+		wait_bar(0);
+		write_out(0);
+		__syncwarp();
+		if(2<=N) issue_S(2, 0);
+		if(2<N) issue_BAbt(2, 0);
+		for(int n=1; n<N; n++)
+			{
+			if(n>=2) { wait_bar(2+(n&1)); drop_img(n); }
+			wait_bar(n&1);
+			write_out(n);
+			__syncwarp();
+			if(n+2<=N) issue_S(n+2, n&1);
+			if(n+2<N) issue_BAbt(n+2, n&1);
+			}
+		if(N>=2) { wait_bar(2+(N&1)); drop_img(N); }
+		write_out(N);
+		__syncwarp();
+		}
+	}
+#endif
 
 /* ------------------------------------------------------------------------------------------------ */
 /* tails of a scenario tree (ric_tree.cuh): the same register-blocked stages on chains whose first node */
@@ -798,7 +1028,7 @@ __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long 
 	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
 	double *wbase = hbf_smem + (size_t)warp*C::PER_WARP;
 	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);
-	double *ibase = wbase + 8 + (size_t)g*C::PER_INST;
+	double *ibase = wbase + 8 + C::inst_off(g);
 	double *io = ibase;
 	double *LUs = ibase + IOB;
 	double *S0 = LUs + LU, *S1 = S0 + SB;
@@ -828,7 +1058,7 @@ __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long 
 		const int my_j = tail_lo + (int)(my_item - my_t*ntl);
 		const double *my_in = in + my_t*in_stride;
 		const double *my_L = L_all + my_t*L_stride;
-		double *my_sm = wbase + 8 + (size_t)mg*C::PER_INST;
+		double *my_sm = wbase + 8 + C::inst_off(mg);
 		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
 
 		if(mode==0)
@@ -935,7 +1165,7 @@ __global__ void __launch_bounds__(256, 1) hbk_top_kernel(hb_tdims d, long long n
 	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
 	double *wbase = hbf_smem + (size_t)warp*C::PER_WARP;
 	uint64_t *bars = reinterpret_cast<uint64_t*>(wbase);      /* [0] [B A b]' of a kid, [1] RSQrq / own image, [2] x-columns of a kid */
-	double *ibase = wbase + 8 + (size_t)g*C::PER_INST;
+	double *ibase = wbase + 8 + C::inst_off(g);
 	double *io = ibase, *LUs = ibase + IOB, *S0 = LUs + LU, *S1 = S0 + SB;
 	double *us = S1 + SB, *xs0 = us + C::even(NU), *xs1 = xs0 + C::XS, *tmp = xs1 + C::XS;
 	if(lane==0)
@@ -966,7 +1196,7 @@ __global__ void __launch_bounds__(256, 1) hbk_top_kernel(hb_tdims d, long long n
 		const hb_tnode my_nd = d.tn[d.seg_nodes[d.seg_start[seg_lo + (int)(my_item - my_t*nseg)]]];
 		const double *my_in = in + my_t*d.in_stride;
 		const double *my_L = L_all + my_t*d.L_stride;
-		double *my_sm = wbase + 8 + (size_t)mg*C::PER_INST;
+		double *my_sm = wbase + 8 + C::inst_off(mg);
 		auto wait_bar = [&](int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); };
 		const int nkids = nd.nkids;                              /* the same for every node of a level */
 

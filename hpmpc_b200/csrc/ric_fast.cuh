@@ -115,6 +115,16 @@ __device__ __forceinline__ void hbf_bulk_s2g(void *gdst, const void *ssrc, uint3
 	{
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(hbf_saddr(ssrc)), "r"(bytes) : "memory");
 	}
+__device__ __forceinline__ void hbf_bulk_s2g_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t policy)
+	{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+		:: "l"(gdst), "r"(hbf_saddr(ssrc)), "r"(bytes), "l"(policy) : "memory");
+	}
+__device__ __forceinline__ uint64_t hbf_policy_evict_normal()
+	{ uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p; }
+/* drop one 128-byte line from L2 without writing it back (scratch that has just been consumed and will be rewritten) */
+__device__ __forceinline__ void hbf_discard_line(const void *g)
+	{ asm volatile("discard.global.L2 [%0], 128;" :: "l"(g) : "memory"); }
 __device__ __forceinline__ void hbf_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template<int N> __device__ __forceinline__ void hbf_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 template<int N> __device__ __forceinline__ void hbf_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }

@@ -115,6 +115,9 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
                                              double mu_tol, double alpha_min, int warm_start, double *h_ux, double *h_pi,
                                              double *h_lam, double *h_t, double *h_info);
 
+/* MEASUREMENT TOOL (bench.py, tools/): the memory traffic of the sv kernel without its arithmetic -- same bulk copies, L2 hints and
+ * output stores; d_ux / d_pi receive meaningless values.  Config-2 shape only (-2 otherwise). */
+int hpmpc_b200_sv_traffic_probe(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_ux, double *d_pi, void *stream);
 /* measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator) */
 double hpmpc_b200_fp64_peak_tflops(int device);
 const char *hpmpc_b200_version(void);

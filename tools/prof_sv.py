@@ -20,6 +20,11 @@ d_in = spec.torch_batch(n)
 ux = torch.zeros((n, h.sz.ux_stride), dtype=torch.float64, device="cuda")
 pi = torch.zeros((n, h.sz.pi_stride), dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
+if os.environ.get("SV_PROBE"):          # the traffic-equivalent probe instead of the solver (same arguments)
+    import ctypes as C
+    L.hpmpc_b200_sv_traffic_probe.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
+    _probe = L.hpmpc_b200_sv_traffic_probe
+    L = type("P", (), {"hpmpc_b200_d_back_ric_rec_sv_batch": staticmethod(lambda h_, n_, a, b, c, _none, s_: _probe(h_, n_, a, b, c, s_))})
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
 for i in range(2):
     L.hpmpc_b200_d_back_ric_rec_sv_batch(h.h, n, d_in.data_ptr(), ux.data_ptr(), pi.data_ptr(), None, st)
