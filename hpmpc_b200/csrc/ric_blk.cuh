@@ -75,8 +75,20 @@ struct hbk_cfg
 	 * the 16 double-slots) of the two instances that share a half-warp interleave exactly (offset 8) instead of colliding
 	 * (ncu r01: 23 % of the shared-memory wavefronts were bank conflicts with the uniform stride PER_INST = 6 mod 16). */
 	__host__ __device__ static constexpr int skew_target(int g) { return ((g&1)<<3) | ((g&2)<<1) | ((g&4)>>1); }
-	__host__ __device__ static constexpr int inst_off(int g) { return g*PER_INST + ((skew_target(g) - g*PER_INST) & 15); }
-	static constexpr int PER_WARP = IPW*PER_INST + 8 + 16;
+	/* start of instance g's buffers: the first offset behind instance g-1 that has the wanted residue (regions never overlap) */
+	__host__ __device__ static constexpr int inst_off_c(int g)
+		{
+		int off = 0;
+		for(int k=1; k<=g; k++) { off += PER_INST; off += (skew_target(k) - off) & 15; }
+		return off;
+		}
+	__host__ __device__ static constexpr int inst_off(int g)
+		{
+		int off = 0;
+		for(int k=1; k<IPW; k++) if(g==k) off = inst_off_c(k);
+		return off;
+		}
+	static constexpr int PER_WARP = inst_off_c(IPW-1) + PER_INST + 8;
 #else
 	__host__ __device__ static constexpr int inst_off(int g) { return g*PER_INST; }
 	static constexpr int PER_WARP = IPW*PER_INST + 8;
