@@ -241,6 +241,82 @@ class HpmpcLib:
                     t=[sp(t[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)],
                     stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
+    def single_newton_step(self, p: Ocp, ux0, pi0, lam0, t0, *, k_max=1, mu0=1e-3):
+        """fortran_order_d_ip_ocp_hard_tv_single_newton_step (reference include/c_interface.h:66): k_max Newton steps from the
+        iterate ux0[n] = [u_n ; x_n], pi0[n], lam0[n] / t0[n] = [lb(nb) ub(nb)]."""
+        N = p.N
+        f = np.asfortranarray
+        A = [f(M) for M in p.A]; B = [f(M) for M in p.B]; Q = [f(M) for M in p.Q]; S = [f(M) for M in p.S]; R = [f(M) for M in p.R]
+        c = np.ascontiguousarray
+        b = [c(v) for v in p.b]; q = [c(v) for v in p.q]; r = [c(v) for v in p.r]; lb = [c(v) for v in p.lb]; ub = [c(v) for v in p.ub]
+        x = [np.zeros(max(n, 1)) for n in p.nx]; u = [np.zeros(max(n, 1)) for n in p.nu[:N]]
+        pi = [np.zeros(max(p.nx[n + 1], 1)) for n in range(N)]
+        lam = [np.zeros(max(2 * nb, 1)) for nb in p.nb]; t = [np.zeros(max(2 * nb, 1)) for nb in p.nb]
+        pad = lambda v: c(np.asarray(v, dtype=np.float64)) if len(v) else np.zeros(1)
+        a_ux0 = [pad(v) for v in ux0]; a_pi0 = [pad(v) for v in pi0] + [np.zeros(1)]; a_lam0 = [pad(v) for v in lam0]; a_t0 = [pad(v) for v in t0]
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        nx, nu, nb, ng = int_array(p.nx), int_array(p.nu), int_array(p.nb), int_array([0] * (N + 1))
+        empty = [np.zeros(1) for _ in range(N + 1)]
+        wsz = self.lib.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N)
+        work = aligned_zeros(wsz // 8 + 16)
+        res = np.zeros(8); stat = np.zeros(5 * k_max + 5); kk = C.c_int(0)
+        fn = self.lib.fortran_order_d_ip_ocp_hard_tv_single_newton_step
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int] + [C.c_void_p] * 26
+        pa = ptr_array
+        arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(empty), pa(empty), pa(empty), pa(empty),
+                pa(x), pa(u), pa(pi), pa(lam), pa(t)]
+        tail = [pa(a_ux0), pa(a_pi0), pa(a_lam0), pa(a_t0)]
+        pidx = pa(idxb)
+        status = fn(C.byref(kk), k_max, mu0, 1e-8, N, nx, nu, nb, pidx, ng, N, 0, *arrs, res.ctypes.data, work.ctypes.data, stat.ctypes.data, *tail)
+        return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)], u=[u[n][:p.nu[n]].copy() for n in range(N)],
+                    pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)], lam=[lam[n][:2 * p.nb[n]].copy() for n in range(N + 1)],
+                    t=[t[n][:2 * p.nb[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(), stat=stat[:5 * kk.value].reshape(-1, 5).copy())
+
+    def residuals(self, p: Ocp, u, x, pi, lam, t, which: str = "res_res"):
+        """d_res_res_mpc_hard_tv (reference include/mpc_solvers.h:47) or d_res_mpc_hard_tv (:36) on panel-major data; lam / t are
+        [lb ub lg ug] per stage.  Returns rq, rb, rd (and rm) in the same orderings, and mu."""
+        N = p.N
+        nx, nu, nb, _ = self._sizes(p)
+        BAbt, RSQ = self._pm_problem(p)
+        DCt, d, pnb, png, ngl = self._pm_general(p)
+        ng = int_array(ngl)
+        az = aligned_zeros
+        hb = [az(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        hq = [az(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        hux = [az(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+        hpi = [az(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        mk = lambda: [az(2 * pnb[n] + 2 * png[n] + 4) for n in range(N + 1)]
+        hlam, ht, hrd, hrm = mk(), mk(), mk(), mk()
+        hrq = [az(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]; hrb = [az(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+        for n in range(N):
+            hb[n][:p.nx[n + 1]] = p.b[n]; hpi[n][:p.nx[n + 1]] = pi[n]
+        for n in range(N + 1):
+            nun, nxn, nbn, ngn = p.nu[n], p.nx[n], p.nb[n], ngl[n]
+            hq[n][:nun] = p.r[n]; hq[n][nun:nun + nxn] = p.q[n]
+            if n < N: hux[n][:nun] = u[n]
+            hux[n][nun:nun + nxn] = x[n]
+            for src, dst in ((lam[n], hlam[n]), (t[n], ht[n])):
+                dst[:nbn] = src[:nbn]; dst[pnb[n]:pnb[n] + nbn] = src[nbn:2 * nbn]
+                dst[2 * pnb[n]:2 * pnb[n] + ngn] = src[2 * nbn:2 * nbn + ngn]; dst[2 * pnb[n] + png[n]:2 * pnb[n] + png[n] + ngn] = src[2 * nbn + ngn:]
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        mu = C.c_double(0.0)
+        work = az(4096)
+        pa = ptr_array
+        k = [pa(BAbt), pa(hb), pa(RSQ), pa(hq), pa(hux), pa(DCt), pa(d), pa(hpi), pa(hlam), pa(ht), pa(hrq), pa(hrb), pa(hrd), pa(hrm), pa(idxb)]
+        if which == "res_res":
+            fn = self.lib.d_res_res_mpc_hard_tv
+            fn.restype = None; fn.argtypes = [C.c_int] + [C.c_void_p] * 21
+            fn(N, nx, nu, nb, k[14], ng, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8], k[9], work.ctypes.data, k[10], k[11], k[12], k[13], C.byref(mu))
+        else:
+            fn = self.lib.d_res_mpc_hard_tv
+            fn.restype = None; fn.argtypes = [C.c_int] + [C.c_void_p] * 19
+            fn(N, nx, nu, nb, k[14], ng, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8], k[9], k[10], k[11], k[12], C.byref(mu))
+        sp = self._split_bound_like
+        return dict(rq=[hrq[n][:p.nu[n] + p.nx[n]].copy() for n in range(N + 1)], rb=[hrb[n][:p.nx[n + 1]].copy() for n in range(N)],
+                    rd=[sp(hrd[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)],
+                    rm=[sp(hrm[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)], mu=mu.value)
+
     def ric_upd(self, p: Ocp, Qx, qx, mode: str = "sv"):
         """d_back_ric_rec_sv_tv_res (or trf + trs) WITH the IPM's per-constraint updates (reference lqcp_solvers/d_back_ric_rec.c:112):
         Qx[n], qx[n] hold nb[n] + ng[n] entries (bounds first); bounds add Qx to the Hessian diagonal / qx to the gradient at idxb,

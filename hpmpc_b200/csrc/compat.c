@@ -484,6 +484,142 @@ void d_kkt_solve_new_rhs_res_mpc_hard_tv(int N, int *nx, int *nu_N, int *nb, int
 	pthread_mutex_unlock(&g_lock);
 	}
 
+/* reference include/mpc_solvers.h:45 (mpc_solvers/d_ip2_res_hard.c:1348): k_max residual-based Newton steps from the iterate
+ * (ux0, pi0, lam0, t0) -- ux0[n] = [u_n ; x_n], lam0[n] / t0[n] = [lb(nb) ub(nb)] UNPADDED (c99/d_aux_ip_hard_lib4.c:178-186) --
+ * with the centering term fixed at mu0.  Returns 1 after k_max steps like the reference (:1911). */
+int d_ip2_res_mpc_hard_tv_single_newton_step(int *kk, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start, double *stat,
+		int N, int *nx, int *nu_N, int *nb, int **idxb, int *ng, double **pBAbt, double **pQ, double **pDCt, double **d, double **ux,
+		int compute_mult, double **pi, double **lam, double **t, double *double_work_memory, double **ux0, double **pi0, double **lam0,
+		double **t0)
+	{
+	(void)mu_tol; (void)warm_start; (void)compute_mult; (void)double_work_memory;
+	int n, i, status;
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu_N, nb, idxb, ng, k_max)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: single_newton_step: GPU context unavailable\n"); return -1; }
+	pack_from_pmat_g(N, nx, nu_N, nb, pBAbt, pQ, d, pDCt);
+	if(G.sz.nbtot==0)
+		{
+		/* no constraints: one Riccati solve, kk = 0, return 0 (:1586-1604) */
+		int rc = run_ipm_single(kk, k_max, mu0, 0.0, alpha_min, 0, stat, NULL);
+		if(rc) { pthread_mutex_unlock(&g_lock); return -1; }
+		}
+	else
+		{
+		for(n=0; n<=N; n++)
+			{
+			int oU, oP, oLm, nun = n<N ? nu_N[n] : 0, nbn = nb[n];
+			hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, &oLm, NULL);
+			for(i=0; i<nun+nx[n]; i++) G.h_ux[oU+i] = ux0[n][i];
+			if(n<N) for(i=0; i<nx[n+1]; i++) G.h_pi[oP+i] = pi0[n][i];
+			for(i=0; i<2*nbn; i++) { G.h_lam[oLm+i] = lam0[n][i]; G.h_t[oLm+i] = t0[n][i]; }
+			}
+		if(h2d(G.d_in, G.h_in, G.sz.in_stride) || h2d(G.d_ux, G.h_ux, G.sz.ux_stride) || h2d(G.d_pi, G.h_pi, G.sz.pi_stride)
+		|| h2d(G.d_lam, G.h_lam, G.sz.lam_stride) || h2d(G.d_t, G.h_t, G.sz.lam_stride)
+		|| cudaMemset(G.d_info, 0, sizeof(double)*(HB_IPM_INFO_HEAD+5*k_max))!=cudaSuccess
+		|| hpmpc_b200_d_ip2_res_mpc_hard_single_newton_step_batch(G.ocp, 1, G.d_in, k_max, mu0, alpha_min, G.d_ux, G.d_pi, G.d_lam, G.d_t, G.d_info, NULL)
+		|| cudaDeviceSynchronize()!=cudaSuccess
+		|| d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_info, G.d_info, HB_IPM_INFO_HEAD+5*k_max)
+		|| d2h(G.h_lam, G.d_lam, G.sz.lam_stride) || d2h(G.h_t, G.d_t, G.sz.lam_stride))
+			{ pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: single_newton_step: GPU execution failed\n"); return -1; }
+		*kk = (int)G.h_info[0];
+		if(stat) for(i=0; i<5*(*kk); i++) stat[i] = G.h_info[HB_IPM_INFO_HEAD+i];
+		}
+	status = (int)G.h_info[1];
+	for(n=0; n<=N; n++)
+		{
+		int oU, oP, oLm, nun = n<N ? nu_N[n] : 0, nbn = nb[n], pnb = RUP(nbn, BS);
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, &oLm, NULL);
+		for(i=0; i<nun+nx[n]; i++) ux[n][i] = G.h_ux[oU+i];
+		if(n<N) for(i=0; i<nx[n+1]; i++) pi[n][i] = G.h_pi[oP+i];
+		for(i=0; i<nbn; i++)
+			{
+			lam[n][i] = G.h_lam[oLm+i]; lam[n][pnb+i] = G.h_lam[oLm+nbn+i];
+			t[n][i] = G.h_t[oLm+i]; t[n][pnb+i] = G.h_t[oLm+nbn+i];
+			}
+		}
+	pthread_mutex_unlock(&g_lock);
+	return status;
+	}
+
+/* reference include/mpc_solvers.h:47 (mpc_solvers/c99/d_res_ip_res_hard.c:39) and :36 (mpc_solvers/d_res_ip_hard.c:38): the KKT
+ * residuals of a given point.  hb / hq are the vectors b_n, [r;q]_n (the reference reads them instead of the last rows of the
+ * matrices); hd, hlam, ht, hrd, hrm in the lib4 padded layout [lb(pnb) ub(pnb) lg(png) ug(png)].  `flip_upper`: d_res_mpc_hard_tv
+ * returns the upper-bound residual with the opposite sign (d_res_ip_hard.c:80,289-295) and no res_m. */
+static void residuals_single(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hb, double **hpQ, double **hq,
+		double **hux, double **hpDCt, double **hd, double **hpi, double **hlam, double **ht, double **hrq, double **hrb, double **hrd,
+		double **hrm, double *mu, int flip_upper, const char *who)
+	{
+	int n, i;
+	double *d_rq = NULL, *d_rb = NULL, *d_rd = NULL, *d_rm = NULL, *d_mu = NULL;
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu, nb, idxb, ng, 1)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: %s: GPU context unavailable, outputs untouched\n", who); return; }
+	pack_from_pmat_g(N, nx, nu, nb, hpBAbt, hpQ, hd, hpDCt);
+	const size_t lam = (size_t)(G.sz.lam_stride>0 ? G.sz.lam_stride : 2);
+	double *h_rd = calloc(lam, sizeof(double)), *h_rm = calloc(lam, sizeof(double)), h_mu = 0.0;
+	for(n=0; n<=N; n++)
+		{
+		int oB, oH, oU, oP, oLm, nun = n<N ? nu[n] : 0, nux = nun+nx[n], nbn = nb ? nb[n] : 0, pnb = nbn>0 ? RUP(nbn, BS) : 0, ngn = G.ng[n], png = RUP(ngn, BS);
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, &oB, &oH, NULL, &oU, &oP, &oLm, NULL);
+		if(n<N && hb) for(i=0; i<nx[n+1]; i++) G.h_in[oB + (size_t)nux*nx[n+1] + i] = hb[n][i];
+		if(hq) for(i=0; i<nux; i++) G.h_in[oH + HB_TRI(nux) + i] = hq[n][i];
+		for(i=0; i<nux; i++) G.h_ux[oU+i] = hux[n][i];
+		if(n<N) for(i=0; i<nx[n+1]; i++) G.h_pi[oP+i] = hpi[n][i];
+		for(i=0; i<nbn; i++) { G.h_lam[oLm+i] = hlam[n][i]; G.h_lam[oLm+nbn+i] = hlam[n][pnb+i]; G.h_t[oLm+i] = ht[n][i]; G.h_t[oLm+nbn+i] = ht[n][pnb+i]; }
+		for(i=0; i<ngn; i++)
+			{
+			G.h_lam[oLm+2*nbn+i] = hlam[n][2*pnb+i]; G.h_lam[oLm+2*nbn+ngn+i] = hlam[n][2*pnb+png+i];
+			G.h_t[oLm+2*nbn+i] = ht[n][2*pnb+i]; G.h_t[oLm+2*nbn+ngn+i] = ht[n][2*pnb+png+i];
+			}
+		}
+	int bad = cudaMalloc((void**)&d_rq, sizeof(double)*G.sz.ux_stride)!=cudaSuccess || cudaMalloc((void**)&d_rb, sizeof(double)*(G.sz.pi_stride+2))!=cudaSuccess
+		|| cudaMalloc((void**)&d_rd, sizeof(double)*lam)!=cudaSuccess || cudaMalloc((void**)&d_rm, sizeof(double)*lam)!=cudaSuccess
+		|| cudaMalloc((void**)&d_mu, sizeof(double))!=cudaSuccess
+		|| h2d(G.d_in, G.h_in, G.sz.in_stride) || h2d(G.d_ux, G.h_ux, G.sz.ux_stride) || h2d(G.d_pi, G.h_pi, G.sz.pi_stride)
+		|| (G.sz.lam_stride>0 && (h2d(G.d_lam, G.h_lam, G.sz.lam_stride) || h2d(G.d_t, G.h_t, G.sz.lam_stride)))
+		|| hpmpc_b200_d_res_res_mpc_hard_batch(G.ocp, 1, G.d_in, G.d_ux, G.d_pi, G.d_lam, G.d_t, d_rq, d_rb, d_rd, d_rm, d_mu, NULL)
+		|| cudaDeviceSynchronize()!=cudaSuccess
+		|| d2h(G.h_ux, d_rq, G.sz.ux_stride) || d2h(G.h_pi, d_rb, G.sz.pi_stride)
+		|| (G.sz.lam_stride>0 && (d2h(h_rd, d_rd, G.sz.lam_stride) || d2h(h_rm, d_rm, G.sz.lam_stride))) || d2h(&h_mu, d_mu, 1);
+	cudaFree(d_rq); cudaFree(d_rb); cudaFree(d_rd); cudaFree(d_rm); cudaFree(d_mu);
+	if(bad) { free(h_rd); free(h_rm); pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: %s: GPU execution failed, outputs untouched\n", who); return; }
+	for(n=0; n<=N; n++)
+		{
+		int oU, oP, oLm, nun = n<N ? nu[n] : 0, nbn = nb ? nb[n] : 0, pnb = nbn>0 ? RUP(nbn, BS) : 0, ngn = G.ng[n], png = RUP(ngn, BS);
+		const double su = flip_upper ? -1.0 : 1.0;
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, &oLm, NULL);
+		for(i=0; i<nun+nx[n]; i++) hrq[n][i] = G.h_ux[oU+i];
+		if(n<N) for(i=0; i<nx[n+1]; i++) hrb[n][i] = G.h_pi[oP+i];
+		for(i=0; i<nbn; i++)
+			{
+			hrd[n][i] = h_rd[oLm+i]; hrd[n][pnb+i] = su*h_rd[oLm+nbn+i];
+			if(hrm) { hrm[n][i] = h_rm[oLm+i]; hrm[n][pnb+i] = h_rm[oLm+nbn+i]; }
+			}
+		for(i=0; i<ngn; i++)
+			{
+			hrd[n][2*pnb+i] = h_rd[oLm+2*nbn+i]; hrd[n][2*pnb+png+i] = su*h_rd[oLm+2*nbn+ngn+i];
+			if(hrm) { hrm[n][2*pnb+i] = h_rm[oLm+2*nbn+i]; hrm[n][2*pnb+png+i] = h_rm[oLm+2*nbn+ngn+i]; }
+			}
+		}
+	*mu = h_mu;
+	free(h_rd); free(h_rm);
+	pthread_mutex_unlock(&g_lock);
+	}
+
+void d_res_res_mpc_hard_tv(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hb, double **hpQ, double **hq,
+		double **hux, double **hpDCt, double **hd, double **hpi, double **hlam, double **ht, double *work, double **hrq, double **hrb,
+		double **hrd, double **hrm, double *mu)
+	{
+	(void)work;
+	residuals_single(N, nx, nu, nb, idxb, ng, hpBAbt, hb, hpQ, hq, hux, hpDCt, hd, hpi, hlam, ht, hrq, hrb, hrd, hrm, mu, 0, "d_res_res_mpc_hard_tv");
+	}
+
+void d_res_mpc_hard_tv(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hb, double **hpQ, double **hq,
+		double **hux, double **hpDCt, double **hd, double **hpi, double **hlam, double **ht, double **hrq, double **hrb, double **hrd,
+		double *mu)
+	{
+	residuals_single(N, nx, nu, nb, idxb, ng, hpBAbt, hb, hpQ, hq, hux, hpDCt, hd, hpi, hlam, ht, hrq, hrb, hrd, NULL, mu, 1, "d_res_mpc_hard_tv");
+	}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* reference include/c_interface.h:59-67                                                              */
 /* ------------------------------------------------------------------------------------------------ */
@@ -560,4 +696,47 @@ int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol
 	{
 	(void)N2; (void)work0;
 	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat);
+	}
+
+/* reference include/c_interface.h:66 (interfaces/c/fortran_order_interface.c:695): k_max Newton steps from (ux0, pi0, lam0, t0) on
+ * column-major stage arrays; x, u, pi, lam, t receive the new iterate, inf_norm_res its residual norms. */
+int fortran_order_d_ip_ocp_hard_tv_single_newton_step(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu_N, int *nb,
+		int **hidxb, int *ng, int N2, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q,
+		double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
+		double **lam, double **t, double *inf_norm_res, void *work0, double *stat, double **ux0, double **pi0, double **lam0, double **t0)
+	{
+	(void)mu_tol; (void)N2; (void)warm_start; (void)work0; (void)C; (void)D; (void)lg; (void)ug;
+	int n, i, j, status;
+	const double alpha_min = 1e-8;
+	pthread_mutex_lock(&g_lock);
+	if(ctx_get(N, nx, nu_N, nb, hidxb, ng, k_max)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU context unavailable\n"); return -1; }
+	if(G.sz.nbtot==0 || k_max<1) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: single_newton_step needs bounds and k_max >= 1\n"); return -1; }
+	hpmpc_b200_pack_instance(G.ocp, 0, A, B, b, Q, S, R, q, r, lb, ub, G.h_in);
+	for(n=0; n<=N; n++)
+		{
+		int oU, oP, oLm, nun = n<N ? nu_N[n] : 0, nbn = nb[n];
+		hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, &oU, &oP, &oLm, NULL);
+		for(i=0; i<nun+nx[n]; i++) G.h_ux[oU+i] = ux0[n][i];
+		if(n<N) for(i=0; i<nx[n+1]; i++) G.h_pi[oP+i] = pi0[n][i];
+		for(i=0; i<2*nbn; i++) { G.h_lam[oLm+i] = lam0[n][i]; G.h_t[oLm+i] = t0[n][i]; }
+		}
+	if(h2d(G.d_in, G.h_in, G.sz.in_stride) || h2d(G.d_ux, G.h_ux, G.sz.ux_stride) || h2d(G.d_pi, G.h_pi, G.sz.pi_stride)
+	|| h2d(G.d_lam, G.h_lam, G.sz.lam_stride) || h2d(G.d_t, G.h_t, G.sz.lam_stride)
+	|| cudaMemset(G.d_info, 0, sizeof(double)*(HB_IPM_INFO_HEAD+5*k_max))!=cudaSuccess
+	|| hpmpc_b200_d_ip2_res_mpc_hard_single_newton_step_batch(G.ocp, 1, G.d_in, k_max, mu0, alpha_min, G.d_ux, G.d_pi, G.d_lam, G.d_t, G.d_info, NULL)
+	|| cudaDeviceSynchronize()!=cudaSuccess
+	|| d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_info, G.d_info, HB_IPM_INFO_HEAD+5*k_max)
+	|| d2h(G.h_lam, G.d_lam, G.sz.lam_stride) || d2h(G.h_t, G.d_t, G.sz.lam_stride))
+		{ pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: single_newton_step: GPU execution failed\n"); return -1; }
+	*kk = (int)G.h_info[0];
+	if(stat) for(i=0; i<5*(*kk); i++) stat[i] = G.h_info[HB_IPM_INFO_HEAD+i];
+	status = (int)G.h_info[1];
+	hpmpc_b200_unpack_solution(G.ocp, G.h_ux, G.h_pi, G.h_lam, x, u, pi, lam);
+	for(n=0; n<=N; n++) { int oLm; hpmpc_b200_ocp_stage_offsets(G.ocp, n, NULL, NULL, NULL, NULL, NULL, &oLm, NULL); for(i=0; i<2*nb[n]; i++) t[n][i] = G.h_t[oLm+i]; }
+	for(n=0; n<N; n++)
+		for(j=0; j<nb[n] && hidxb[n][j]<nu_N[n]; j++)
+			if(lb[n][j]==ub[n][j]) u[n][hidxb[n][j]] = lb[n][j];
+	for(i=0; i<4; i++) inf_norm_res[i] = G.h_info[2+i];
+	pthread_mutex_unlock(&g_lock);
+	return status;
 	}

@@ -152,6 +152,94 @@ __device__ __forceinline__ void hb_ipm_emit_chain(int lane, const hb_dims &d, co
 		}
 	}
 
+/* the inverse of hb_ipm_emit_chain: lam, t of a caller-supplied iterate into the work vectors (single Newton step,
+ * d_init_var_mpc_hard_tv_single_newton, mpc_solvers/c99/d_aux_ip_hard_lib4.c:153-213; bounds only, as in the reference) */
+__device__ __forceinline__ void hb_ipm_load_chain(int lane, const hb_dims &d, const hb_ipm_ws &w, const double *lam, const double *tt)
+	{
+	for(int n=0; n<=d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		for(int j=lane; j<s.nb; j+=32)
+			{
+			w.v(CV_LAM_LO)[s.off_c+j] = lam[2*s.off_c+j]; w.v(CV_LAM_UP)[s.off_c+j] = lam[2*s.off_c+s.nb+j];
+			w.v(CV_T_LO)[s.off_c+j] = tt[2*s.off_c+j]; w.v(CV_T_UP)[s.off_c+j] = tt[2*s.off_c+s.nb+j];
+			}
+		for(int j=lane; j<s.ng; j+=32)
+			{
+			const int o = 2*s.off_c + 2*s.nb, cg = s.off_c + s.nb + j;
+			w.v(CV_LAM_LO)[cg] = lam[o+j]; w.v(CV_LAM_UP)[cg] = lam[o+s.ng+j];
+			w.v(CV_T_LO)[cg] = tt[o+j]; w.v(CV_T_UP)[cg] = tt[o+s.ng+j];
+			}
+		}
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* stand-alone residuals of a given point (ux, pi, lam, t): d_res_res_mpc_hard_tv                      */
+/* (mpc_solvers/c99/d_res_ip_res_hard.c:39) -- res_q, res_b, res_d, res_m and mu; one warp per instance. */
+/* res_d / res_m come out in the layout of lam ([lb ub lg ug] per stage).                               */
+/* ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) hb_res_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+		const double *__restrict__ ux_all, const double *__restrict__ pi_all, const double *__restrict__ lam_all,
+		const double *__restrict__ t_all, double *__restrict__ rq_all, double *__restrict__ rb_all, double *__restrict__ rd_all,
+		double *__restrict__ rm_all, double *__restrict__ mu_all, double *__restrict__ work, long long work_stride)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	hb_ctx c = hb_make_ctx(d, hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM), lane);
+	hb_ipm_ws w;
+	{
+	double *p = work + gw*work_stride;
+	w.L = p;                         /* no factor here: the vectors start at the slot */
+	w.dux = p; p += d.ux_stride; w.res_q = p; p += d.ux_stride; w.rq0 = p; p += d.ux_stride;
+	w.dpi = p; p += d.pi_stride; w.Pb = p; p += d.pi_stride; w.res_b = p; p += d.pi_stride; w.b0 = p; p += d.pi_stride;
+	w.cv = p; w.nbp = HB_EVEN(d.nbtot);
+	}
+	for(long long inst=gw; inst<n_inst; inst+=tw)
+		{
+		const double *in_inst = in + inst*d.in_stride;
+		const double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+		hb_ipm_extract_chain(lane, d, in_inst, w);
+		hb_ipm_load_chain(lane, d, w, lam_all + inst*2*(long long)d.nbtot, t_all + inst*2*(long long)d.nbtot);
+		__syncwarp();
+		double mu = 0.0, norms[3];
+		hb_ipm_residuals(c, d, in_inst, w, ux, pi, &mu, norms);
+		__syncwarp();
+		for(long long i=lane; i<d.ux_stride; i+=32) rq_all[inst*d.ux_stride+i] = w.res_q[i];
+		for(long long i=lane; i<d.pi_stride; i+=32) rb_all[inst*d.pi_stride+i] = w.res_b[i];
+		double *rd = rd_all + inst*2*(long long)d.nbtot, *rm = rm_all ? rm_all + inst*2*(long long)d.nbtot : nullptr;
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_stage s = d.st[n];
+			for(int j=lane; j<s.nb; j+=32)
+				{
+				rd[2*s.off_c+j] = w.v(CV_RD_LO)[s.off_c+j]; rd[2*s.off_c+s.nb+j] = w.v(CV_RD_UP)[s.off_c+j];
+				if(rm) { rm[2*s.off_c+j] = w.v(CV_RM_LO)[s.off_c+j]; rm[2*s.off_c+s.nb+j] = w.v(CV_RM_UP)[s.off_c+j]; }
+				}
+			for(int j=lane; j<s.ng; j+=32)
+				{
+				const int o = 2*s.off_c + 2*s.nb, cg = s.off_c + s.nb + j;
+				rd[o+j] = w.v(CV_RD_LO)[cg]; rd[o+s.ng+j] = w.v(CV_RD_UP)[cg];
+				if(rm) { rm[o+j] = w.v(CV_RM_LO)[cg]; rm[o+s.ng+j] = w.v(CV_RM_UP)[cg]; }
+				}
+			}
+		if(lane==0) mu_all[inst] = mu;
+		__syncwarp();
+		}
+	}
+
+extern "C" long long hb_res_work_doubles(const hb_dims *d) { return 3*d->ux_stride + 4*d->pi_stride + (long long)CV_COUNT*HB_EVEN(d->nbtot); }
+extern "C" int hb_launch_res(const hb_dims *d, long long n_inst, const double *in, const double *ux, const double *pi, const double *lam,
+		const double *t, double *rq, double *rb, double *rd, double *rm, double *mu, double *work, int grid, int warps, void *stream)
+	{
+	if(d->nzM>64) return -2;
+	if(warps>8) return -3;
+	const int smem = warps*hb_smem_bytes_per_warp(d);
+	if(hb_prep(hb_res_kernel, smem)) return -1;
+	hb_res_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, ux, pi, lam, t, rq, rb, rd, rm, mu, work, hb_res_work_doubles(d));
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
 /* The IPM kernel is written once; the sweeps over the horizon (or the tree) come from a policy: the run-time-size routines
  * of ric_generic.cuh, the size-specialised, bulk-copy-pipelined ones of ric_ipm_fast.cuh, or the tree ones of
  * ric_tree_ipm.cuh. */
@@ -161,6 +249,7 @@ struct hb_sweeps_generic
 	static constexpr bool has_kkt = true;
 	__device__ static __forceinline__ void extract(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w) { hb_ipm_extract_chain(c.lane, d, in_inst, w); }
 	__device__ static __forceinline__ void emit(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt) { hb_ipm_emit_chain(c.lane, d, w, lam, tt); }
+	__device__ static __forceinline__ void load(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, const double *lam, const double *tt) { hb_ipm_load_chain(c.lane, d, w, lam, tt); }
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &d) { return hb_smem_doubles_per_warp(d.nzM, d.nxM); }
 	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return d.L_stride; }
 	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c = hb_make_ctx(d, smem_warp, lane); }
@@ -195,6 +284,7 @@ struct hb_sweeps_fast
 	static constexpr bool has_kkt = true;
 	__device__ static __forceinline__ void extract(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w) { hb_ipm_extract_chain(c.lane, d, in_inst, w); }
 	__device__ static __forceinline__ void emit(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, double *lam, double *tt) { hb_ipm_emit_chain(c.lane, d, w, lam, tt); }
+	__device__ static __forceinline__ void load(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, const double *lam, const double *tt) { hb_ipm_load_chain(c.lane, d, w, lam, tt); }
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &) { return hbi_cfg<C>::PER_WARP; }
 	__device__ static __forceinline__ long long L_doubles(const hb_dims &d) { return (long long)(d.N+1)*C::LBUF; }
 	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c.init(smem_warp, lane, d); }
@@ -256,6 +346,18 @@ struct hb_sweeps_tree
 				{
 				w.v(CV_LB)[s.off_c+j] = in_inst[s.off_d+j];
 				w.v(CV_UB)[s.off_c+j] = in_inst[s.off_d+s.nb+j];
+				}
+			}
+		}
+	__device__ static __forceinline__ void load(ctx_t &c, const hb_dims &d, const hb_ipm_ws &w, const double *lam, const double *tt)
+		{
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_tnode s = d.tn[n];
+			for(int j=c.lane; j<s.nb; j+=32)
+				{
+				w.v(CV_LAM_LO)[s.off_c+j] = lam[2*s.off_c+j]; w.v(CV_LAM_UP)[s.off_c+j] = lam[2*s.off_c+s.nb+j];
+				w.v(CV_T_LO)[s.off_c+j] = tt[2*s.off_c+j]; w.v(CV_T_UP)[s.off_c+j] = tt[2*s.off_c+s.nb+j];
 				}
 			}
 		}
@@ -333,6 +435,10 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 	hb_ipm_ws w = hb_ipm_make_ws<S>(d, work + gw*work_stride);
 	const int info_len = HB_IPM_INFO_HEAD + 5*k_max;
 	const double thr0 = 0.1;
+	/* warm_start = 2: single-Newton-step mode (d_ip2_res_mpc_hard_tv_single_newton_step, mpc_solvers/d_ip2_res_hard.c:1348): the
+	 * iterate (ux, pi, lam, t) the caller left in the output arrays is taken as is, phase 1 is skipped, every iteration is a
+	 * residual-based step with the centering term fixed at mu0 (:1749), and the loop runs k_max iterations (:1652) */
+	const bool newton = (warm_start==2);
 
 	for(;;)
 		{
@@ -371,10 +477,11 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 			const double mu_scal = 1.0/(2.0*d.nbtot);
 			double sigma = 0.0, alpha = 1.0, mu_aff;
 			/* init (c99/d_aux_ip_hard_lib4.c:43-149) */
+			if(newton) S::load(c, d, w, lam_all + inst*2*(long long)d.nbtot, t_all + inst*2*(long long)d.nbtot);
 			if(!warm_start) for(long long i=lane; i<d.ux_stride; i+=32) ux[i] = 0.0;
-			for(long long i=lane; i<d.pi_stride; i+=32) pi[i] = 0.0;
+			if(!newton) for(long long i=lane; i<d.pi_stride; i+=32) pi[i] = 0.0;
 			__syncwarp();
-			for(int cc=lane; cc<d.nbtot; cc+=32)
+			for(int cc=lane; cc<(newton ? 0 : d.nbtot); cc+=32)
 				{
 				const int iu = d.c_ux[cc];
 				if(iu<0) continue;                                    /* general constraint: below */
@@ -390,7 +497,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				w.v(CV_LAM_LO)[cc] = mu0/tl; w.v(CV_LAM_UP)[cc] = mu0/tu;
 				}
 			__syncwarp();
-			if(d.ngtot>0)
+			if(d.ngtot>0 && !newton)
 				{
 				/* general constraints, from the ux the bounds have just moved: t = max(thr0, +-([D C] ux - d)), no projection
 				 * (c99/d_aux_ip_hard_lib4.c:121-147) */
@@ -409,7 +516,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 			const double mu_tol_low = mu_tol<1e-5 ? 1e-5 : mu_tol;
 
 			/* ---------- phase 1 (d_ip2_res_hard.c:503-718) ---------- */
-			while(kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
+			while(!newton && kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
 				{
 				/* update_hessian, sigma_mu = 0 (c99/d_aux_ip_hard_lib4.c:217-383) */
 				for(int cc=lane; cc<d.nbtot; cc+=32)
@@ -483,7 +590,7 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 			/* ---------- phase 2 (d_ip2_res_hard.c:756-1273) ---------- */
 			S::residuals(c, d, in_inst, w, ux, pi, &mu, norms);
 			__syncwarp();
-			while(kk<k_max && mu>mu_tol && alpha>=alpha_min)
+			while(kk<k_max && (newton || (mu>mu_tol && alpha>=alpha_min)))
 				{
 				/* update_hessian_gradient_res (c99/d_aux_ip_hard_lib4.c:954-1078) */
 				for(int cc=lane; cc<d.nbtot; cc+=32)
@@ -496,10 +603,12 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 					}
 				__syncwarp();
 				HBF_STAMP(300);
-				S::backward(c, d, in_inst, w, w.res_b, w.res_q, w.v(CV_QXD), w.v(CV_QXG));
+				/* single-Newton-step mode: the reference solves the predictor with the ORIGINAL b and q (update_b = 0, update_q = 1
+				 * with q, d_ip2_res_hard.c:1736) and only the corrector with the residuals (:1788); restated as it is */
+				S::backward(c, d, in_inst, w, newton ? nullptr : w.res_b, newton ? nullptr : w.res_q, w.v(CV_QXD), w.v(CV_QXG));
 				__syncwarp();
 				HBF_STAMP(301);
-				S::forward_sv(c, d, in_inst, w, w.res_b, w.dux, w.dpi);
+				S::forward_sv(c, d, in_inst, w, newton ? nullptr : w.res_b, w.dux, w.dpi);
 				HBF_STAMP(302);
 				__syncwarp();
 				hb_gen_values(lane, d, in_inst, w, w.dux);
@@ -509,10 +618,10 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				alpha *= 0.995;
 				mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
 				if(lane==0) stat[5*kk+2] = mu_aff;
-				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
+				if(!newton) { sigma = mu_aff/mu; sigma = sigma*sigma*sigma; }
 				{
 				/* centering correction + update_gradient_res (c99/d_aux_ip_hard_lib4.c:1512-1546, :1550-1639) */
-				const double sm = sigma*mu;
+				const double sm = newton ? mu0 : sigma*mu;
 				for(int cc=lane; cc<d.nbtot; cc+=32)
 					{
 					double rml = w.v(CV_RM_LO)[cc] + (w.v(CV_DT_LO)[cc]*w.v(CV_DLAM_LO)[cc] - sm);
@@ -563,7 +672,8 @@ __global__ void __launch_bounds__(256) hb_ipm_kernel(hb_dims d, long long n_inst
 				kk++;
 				__syncwarp();
 				}
-			if(mu<=mu_tol) status = 0;
+			if(newton) status = (kk>=k_max) ? 1 : (alpha<alpha_min ? 2 : -1);       /* d_ip2_res_hard.c:1911-1918 */
+			else if(mu<=mu_tol) status = 0;
 			else if(kk>=k_max) status = 1;
 			else if(alpha<alpha_min) status = 2;
 			else status = -1;

@@ -137,6 +137,9 @@ int hb_fast_variant(int N, const int *nx, const int *nu);
 int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst);
 int hb_launch_ric_sv_fast(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, void *stream);
+long long hb_res_work_doubles(const hb_dims *dims);
+int hb_launch_res(const hb_dims *dims, long long n_inst, const double *in, const double *ux, const double *pi, const double *lam,
+		const double *t, double *rq, double *rb, double *rd, double *rm, double *mu, double *work, int grid, int warps, void *stream);
 int hb_launch_sv_traffic(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, void *stream);
 int hb_launch_tree(const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,

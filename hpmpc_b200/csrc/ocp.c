@@ -604,6 +604,37 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
 			p->lam_stride, stream, NULL));
 	}
 
+/* residuals of a given point: d_res_res_mpc_hard_tv (mpc_solvers/c99/d_res_ip_res_hard.c:39; row a6).  d_rq [ux_stride],
+ * d_rb [pi_stride], d_rd / d_rm [lam_stride] in the layout of lam, d_mu [1] per instance; d_rm may be NULL */
+int hpmpc_b200_d_res_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_ux, const double *d_pi,
+		const double *d_lam, const double *d_t, double *d_rq, double *d_rb, double *d_rd, double *d_rm, double *d_mu, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(p->device));
+	if(call_begin(p, stream)) return -1;
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->n_slots*hb_res_work_doubles(&p->dims))) return -1;
+	return call_end(p, stream, hb_launch_res(&p->dims, n_inst, d_in, d_ux, d_pi, d_lam, d_t, d_rq, d_rb, d_rd, d_rm, d_mu, p->scratch,
+			grid_for(p, n_inst), p->warps, stream));
+	}
+
+/* a fixed number of residual-based Newton steps from a caller-supplied iterate: d_ip2_res_mpc_hard_tv_single_newton_step
+ * (mpc_solvers/d_ip2_res_hard.c:1348).  On entry d_ux, d_pi, d_lam, d_t hold (ux0, pi0, lam0, t0) in the output
+ * layouts; they are updated in place.  The centering term is mu0 in every step, as in the reference.  Bounds only (the reference
+ * rejects ng > 0 here, c99/d_aux_ip_hard_lib4.c:205-210). */
+int hpmpc_b200_d_ip2_res_mpc_hard_single_newton_step_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
+		double alpha_min, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	if(p->dims.ngtot>0) { fprintf(stderr, "hpmpc_b200: single Newton step: general constraints are not supported (neither does the reference)\n"); return -5; }
+	CK(cudaSetDevice(p->device));
+	if(call_begin(p, stream)) return -1;
+	if(ensure_scratch(p, sizeof(double)*(size_t)p->i_grid*p->i_warps*p->ipm_ws)) return -1;
+	return call_end(p, stream, ipm_waves(p, n_inst, d_in, k_max, mu0, 0.0, alpha_min, 2, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
+			p->lam_stride, stream, NULL));
+	}
+
 /* the same solve, every instance leaving its KKT state in d_kkt (hpmpc_b200_kkt_state_stride() doubles each) */
 int hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
 		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t,

@@ -95,6 +95,20 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
                                         double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi,
                                         double *d_lam, double *d_t, double *d_info, void *stream);
 
+/* ---- residuals of a given point (row a6): d_res_res_mpc_hard_tv, mpc_solvers/c99/d_res_ip_res_hard.c:39 ----
+ * res_q [ux_stride], res_b [pi_stride], res_d and res_m [lam_stride, in the layout of lam], mu [1] per instance; d_rm may be NULL */
+int hpmpc_b200_d_res_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, const double *d_ux,
+                                        const double *d_pi, const double *d_lam, const double *d_t, double *d_rq, double *d_rb,
+                                        double *d_rd, double *d_rm, double *d_mu, void *stream);
+
+/* ---- a fixed number of Newton steps from a given iterate ----
+ * reference: d_ip2_res_mpc_hard_tv_single_newton_step, mpc_solvers/d_ip2_res_hard.c:1348 (high level include/c_interface.h:66).
+ * d_ux, d_pi, d_lam, d_t: in = (ux0, pi0, lam0, t0), out = the updated iterate; k_max residual-based steps, centering term mu0.
+ * d_info as for the IPM (status is 1 after k_max steps, like the reference's return value). */
+int hpmpc_b200_d_ip2_res_mpc_hard_single_newton_step_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max,
+                                                           double mu0, double alpha_min, double *d_ux, double *d_pi,
+                                                           double *d_lam, double *d_t, double *d_info, void *stream);
+
 /* ---- re-solve with a new right-hand side on the IPM's last factorisation ----
  * reference: d_kkt_solve_new_rhs_res_mpc_hard_tv, mpc_solvers/d_ip2_res_hard.c:1922 (high level: include/c_interface.h:63,67).
  * The reference keeps the factor, t_inv and the backed-up iterate in the caller's work memory between the two calls; here the

@@ -51,6 +51,20 @@ void d_kkt_solve_new_rhs_res_mpc_hard_tv(int N, int *nx, int *nu_N, int *nb, int
                                          double **pQ, double **q, double **pDCt, double **d, double **ux, int compute_mult,
                                          double **pi, double **lam, double **t, double *double_work_memory);
 
+/* include/mpc_solvers.h:45  (mpc_solvers/d_ip2_res_hard.c:1348): k_max Newton steps from the iterate (ux0, pi0, lam0, t0) */
+int d_ip2_res_mpc_hard_tv_single_newton_step(int *kk, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start, double *stat,
+                                             int N, int *nx, int *nu_N, int *nb, int **idxb, int *ng, double **pBAbt, double **pQ, double **pDCt,
+                                             double **d, double **ux, int compute_mult, double **pi, double **lam, double **t,
+                                             double *double_work_memory, double **ux0, double **pi0, double **lam0, double **t0);
+/* include/mpc_solvers.h:47  (mpc_solvers/c99/d_res_ip_res_hard.c:39): residuals res_q, res_b, res_d, res_m and mu of a given point */
+void d_res_res_mpc_hard_tv(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hb, double **hpQ, double **hq,
+                           double **hux, double **hpDCt, double **hd, double **hpi, double **hlam, double **ht, double *work,
+                           double **hrq, double **hrb, double **hrd, double **hrm, double *mu);
+/* include/mpc_solvers.h:36  (mpc_solvers/d_res_ip_hard.c:38): the exit residuals of the high-level wrappers */
+void d_res_mpc_hard_tv(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, double **hpBAbt, double **hb, double **hpQ, double **hq,
+                       double **hux, double **hpDCt, double **hd, double **hpi, double **hlam, double **ht, double **hrq, double **hrb,
+                       double **hrd, double *mu);
+
 /* ---- high-level interface, dense stage-wise arrays : include/c_interface.h:59-67 ---- */
 /* include/c_interface.h:59  (interfaces/c/c_interface_work_space.c:70) */
 int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2);
@@ -68,6 +82,14 @@ int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol
                                    double **lb, double **ub, double **C, double **D, double **lg, double **ug,
                                    double **x, double **u, double **pi, double **lam,
                                    double *inf_norm_res, void *work0, double *stat);
+
+/* include/c_interface.h:66  (interfaces/c/fortran_order_interface.c:695) */
+int fortran_order_d_ip_ocp_hard_tv_single_newton_step(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu_N, int *nb,
+                                                      int **hidxb, int *ng, int N2, int warm_start, double **A, double **B, double **b,
+                                                      double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub,
+                                                      double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
+                                                      double **lam, double **t, double *inf_norm_res, void *work0, double *stat,
+                                                      double **ux0, double **pi0, double **lam0, double **t0);
 
 #ifdef __cplusplus
 }

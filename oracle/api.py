@@ -385,3 +385,28 @@ class RefSample:
         if sec < 0:
             raise RuntimeError("reference harness failed")
         return dict(sec=sec, kk=kk, status=st, ux=ux, pi=pi, lam=lam, inf_norm_res=res)
+
+
+def single_newton_step(p: Ocp, ux0, pi0, lam0, t0, *, k_max=1, mu0=1e-3):
+    """orc_fortran_order_single_newton_step (oracle/ric_oracle.c): k_max Newton steps from the given iterate."""
+    L, N = lib(), p.N
+    A = [_f(M) for M in p.A]; B = [_f(M) for M in p.B]; Q = [_f(M) for M in p.Q]; S = [_f(M) for M in p.S]; R = [_f(M) for M in p.R]
+    c = np.ascontiguousarray
+    b = [c(v) for v in p.b]; q = [c(v) for v in p.q]; r = [c(v) for v in p.r]; lb = [c(v) for v in p.lb]; ub = [c(v) for v in p.ub]
+    x = [np.zeros(max(n, 1)) for n in p.nx]; u = [np.zeros(max(n, 1)) for n in p.nu[:N]]
+    pi = [np.zeros(max(p.nx[n + 1], 1)) for n in range(N)]
+    lam = [np.zeros(max(2 * nb, 1)) for nb in p.nb]; t = [np.zeros(max(2 * nb, 1)) for nb in p.nb]
+    pad = lambda v: c(np.asarray(v, dtype=np.float64)) if len(v) else np.zeros(1)
+    a0 = [[pad(v) for v in ux0], [pad(v) for v in pi0] + [np.zeros(1)], [pad(v) for v in lam0], [pad(v) for v in t0]]
+    idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+    res = np.zeros(8); stat = np.zeros(5 * k_max + 5); kk = C.c_int(0)
+    fn = L.orc_fortran_order_single_newton_step
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 25
+    pa = ptr_array
+    arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(x), pa(u), pa(pi), pa(lam), pa(t)]
+    status = fn(C.byref(kk), k_max, mu0, N, int_array(p.nx), int_array(p.nu), int_array(p.nb), pa(idxb), *arrs, res.ctypes.data, stat.ctypes.data,
+                *[pa(a) for a in a0])
+    return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)], u=[u[n][:p.nu[n]].copy() for n in range(N)],
+                pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)], lam=[lam[n][:2 * p.nb[n]].copy() for n in range(N + 1)],
+                t=[t[n][:2 * p.nb[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(), stat=stat[:5 * kk.value].reshape(-1, 5).copy())

@@ -569,9 +569,23 @@ static void ipm_residuals(const orc_prob *P, const orc_ipm_ws *w, double *mu)
 	if(nb_tot!=0) *mu = mu2/(2.0*nb_tot);
 	}
 
-/* the IPM proper (mpc_solvers/d_ip2_res_hard.c:116).  ux/pi/lam/t in w are in/out. */
+/* the IPM proper (mpc_solvers/d_ip2_res_hard.c:116).  ux/pi/lam/t in w are in/out.
+ * newton = 1: d_ip2_res_mpc_hard_tv_single_newton_step (:1348): the iterate is taken as given (no initialisation, no phase 1),
+ * k_max residual-based steps with the centering term fixed at mu0 (:1749), sigma stays 0, return value :1911-1918. */
+static int ipm_impl(orc_prob *P, int *kk, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *stat, double **ux, double **pi, double **lam, double **t, int newton);
 int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_tol, double alpha_min,
 		int warm_start, double *stat, double **ux, double **pi, double **lam, double **t)
+	{
+	return ipm_impl(P, kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat, ux, pi, lam, t, 0);
+	}
+int orc_ip2_res_mpc_hard_single_newton_step(orc_prob *P, int *kk, int k_max, double mu0, double alpha_min, double *stat,
+		double **ux, double **pi, double **lam, double **t)
+	{
+	return ipm_impl(P, kk, k_max, mu0, 0.0, alpha_min, 1, stat, ux, pi, lam, t, 1);
+	}
+static int ipm_impl(orc_prob *P, int *kk, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *stat, double **ux, double **pi, double **lam, double **t, int newton)
 	{
 	int N = P->N, n, i, j;
 	int *lnux = malloc((N+1)*sizeof(int)), *lnx1 = malloc((N+1)*sizeof(int)), *l2nb = malloc((N+1)*sizeof(int)), *lnb = malloc((N+1)*sizeof(int));
@@ -605,7 +619,7 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 
 	/* init (c99/d_aux_ip_hard_lib4.c:43-149) */
 	if(warm_start==0) for(n=0; n<=N; n++) for(i=0; i<nux_(P,n); i++) ux[n][i] = 0.0;
-	for(n=0; n<=N; n++)
+	for(n=0; n<=N && !newton; n++)
 		{
 		int nb = P->nb[n];
 		for(j=0; j<P->nbx[n]; j++)
@@ -627,9 +641,9 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 			lam[n][nb+j] = mu0/t[n][nb+j];
 			}
 		}
-	for(n=0; n<N; n++) for(i=0; i<P->nx[n+1]; i++) pi[n][i] = 0.0;
+	for(n=0; n<N && !newton; n++) for(i=0; i<P->nx[n+1]; i++) pi[n][i] = 0.0;
 	/* general constraints, from the ux the bounds have just moved; no projection (c99/d_aux_ip_hard_lib4.c:121-147) */
-	for(n=0; n<=N; n++)
+	for(n=0; n<=N && !newton; n++)
 		{
 		int nb = P->nb[n];
 		for(j=P->nbx[n]; j<nb; j++)
@@ -645,7 +659,7 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 	double mu_tol_low = mu_tol<1e-5 ? 1e-5 : mu_tol;
 
 	/* ---------------- phase 1: no residuals (d_ip2_res_hard.c:503-718) ---------------- */
-	while(*kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
+	while(!newton && *kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
 		{
 		for(n=0; n<=N; n++)
 			{
@@ -731,7 +745,7 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 
 	/* ---------------- phase 2: with residuals (d_ip2_res_hard.c:756-1273) ---------------- */
 	ipm_residuals(P, w, &mu);
-	while(*kk<k_max && mu>mu_tol && alpha>=alpha_min)
+	while(*kk<k_max && (newton || (mu>mu_tol && alpha>=alpha_min)))
 		{
 		for(n=0; n<=N; n++)
 			{
@@ -744,7 +758,11 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 				            - w->tinv[n][nb+j]*(w->res_m[n][nb+j] + lam[n][nb+j]*w->res_d[n][nb+j]);
 				}
 			}
-		orc_ric_sv(P, w->res_b, w->res_q, w->Qx, w->qx, w->dux, 1, w->dpi, w->Pb);
+		/* the single-Newton-step routine of the reference solves its predictor system with the ORIGINAL b and q (update_b = 0,
+		 * update_q = 1 with q, mpc_solvers/d_ip2_res_hard.c:1736) and only the corrector with the residuals (:1788, reusing the
+		 * predictor's Pb); restated as it is */
+		if(newton) orc_ric_sv(P, NULL, w->rq, w->Qx, w->qx, w->dux, 1, w->dpi, w->Pb);
+		else orc_ric_sv(P, w->res_b, w->res_q, w->Qx, w->qx, w->dux, 1, w->dpi, w->Pb);
 		for(int pass=0; pass<2; pass++)
 			{
 			alpha = 1.0;
@@ -778,8 +796,8 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 					}
 				mu_aff *= mu_scal;
 				stat[5*(*kk)+2] = mu_aff;
-				sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
-				double sm = sigma*mu;
+				if(!newton) { sigma = mu_aff/mu; sigma = sigma*sigma*sigma; }
+				double sm = newton ? mu0 : sigma*mu;
 				for(n=0; n<=N; n++)
 					{
 					int nb = P->nb[n];
@@ -817,7 +835,8 @@ int orc_ip2_res_mpc_hard(orc_prob *P, int *kk, int k_max, double mu0, double mu_
 		(*kk)++;
 		}
 
-	if(mu<=mu_tol) status = 0;
+	if(newton) status = (*kk>=k_max) ? 1 : (alpha<alpha_min ? 2 : -1);
+	else if(mu<=mu_tol) status = 0;
 	else if(*kk>=k_max) status = 1;
 	else if(alpha<alpha_min) status = 2;
 	else status = -1;
@@ -1237,4 +1256,35 @@ void orc_tree_ric_trf_trs(int Nn, const int *dad, const int *nx, const int *nu, 
 	for(n=0; n<=N; n++) { free(b[n]); free(rq[n]); free(Pb[n]); }
 	free(b); free(rq); free(Pb);
 	orc_prob_free(P);
+	}
+
+/* fortran_order_d_ip_ocp_hard_tv_single_newton_step (interfaces/c/fortran_order_interface.c:695): k_max Newton steps from the iterate
+ * (ux0, pi0, lam0, t0); ux0[n] = [u_n ; x_n], lam0 / t0 = [lb(nb) ub(nb)] per stage.  x, u, pi, lam, t receive the new iterate. */
+int orc_fortran_order_single_newton_step(int *kk, int k_max, double mu0, int N, int *nx, int *nu_N, int *nb, int **hidxb,
+		double **A, double **B, double **b, double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub,
+		double **x, double **u, double **pi, double **lam, double **t, double *inf_norm_res, double *stat,
+		double **ux0, double **pi0, double **lam0, double **t0)
+	{
+	int n, i, j;
+	orc_prob *P = orc_prob_create(N, nx, nu_N, nb, hidxb);
+	orc_prob_set(P, A, B, b, Q, S, R, q, r, lb, ub);
+	double **hux = alloc_ux(P);
+	double **hpi = malloc((N+1)*sizeof(double*)), **hlam = malloc((N+1)*sizeof(double*)), **ht = malloc((N+1)*sizeof(double*));
+	for(n=0; n<=N; n++)
+		{
+		hpi[n] = calloc(P->nxM+1, sizeof(double)); hlam[n] = calloc(2*P->nb[n]+1, sizeof(double)); ht[n] = calloc(2*P->nb[n]+1, sizeof(double));
+		for(i=0; i<nux_(P,n); i++) hux[n][i] = ux0[n][i];
+		if(n<N) for(i=0; i<nx[n+1]; i++) hpi[n][i] = pi0[n][i];
+		for(j=0; j<2*P->nb[n]; j++) { hlam[n][j] = lam0[n][j]; ht[n][j] = t0[n][j]; }
+		}
+	int status = orc_ip2_res_mpc_hard_single_newton_step(P, kk, k_max, mu0, 1e-8, stat, hux, hpi, hlam, ht);
+	for(n=0; n<N; n++) for(i=0; i<P->nu[n]; i++) u[n][i] = hux[n][i];
+	for(n=0; n<=N; n++) for(i=0; i<nx[n]; i++) x[n][i] = hux[n][P->nu[n]+i];
+	orc_exit_residuals(P, hux, hpi, hlam, ht, inf_norm_res);
+	for(n=0; n<N; n++) for(i=0; i<nx[n+1]; i++) pi[n][i] = hpi[n][i];
+	for(n=0; n<=N; n++) for(j=0; j<2*nb[n]; j++) { lam[n][j] = hlam[n][j]; t[n][j] = ht[n][j]; }
+	for(n=0; n<=N; n++) { free(hux[n]); free(hpi[n]); free(hlam[n]); free(ht[n]); }
+	free(hux); free(hpi); free(hlam); free(ht);
+	orc_prob_free(P);
+	return status;
 	}
