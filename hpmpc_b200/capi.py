@@ -241,6 +241,42 @@ class HpmpcLib:
                     t=[sp(t[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)],
                     stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
+    def ip_then_solve_kkt_new_rhs_high_level(self, p: Ocp, p2: Ocp, *, order="fortran", k_max=40, mu0=2.0, mu_tol=1e-8):
+        """{c,fortran}_order_d_ip_ocp_hard_tv on p, then {c,fortran}_order_d_solve_kkt_new_rhs_ocp_hard_tv (reference
+        include/c_interface.h:63,67) on the SAME work0 with the vectors b, q, r, lb, ub of p2."""
+        N = p.N
+        conv = (lambda M: np.ascontiguousarray(M)) if order == "c" else (lambda M: np.asfortranarray(M))
+        A = [conv(M) for M in p.A]; B = [conv(M) for M in p.B]; Q = [conv(M) for M in p.Q]; S = [conv(M) for M in p.S]; R = [conv(M) for M in p.R]
+        c = np.ascontiguousarray
+        v1 = [[c(v) for v in arr] for arr in (p.b, p.q, p.r, p.lb, p.ub)]
+        v2 = [[c(v) for v in arr] for arr in (p2.b, p2.q, p2.r, p2.lb, p2.ub)]
+        x = [np.zeros(max(n, 1)) for n in p.nx]; u = [np.zeros(max(n, 1)) for n in p.nu[:N]]
+        pi = [np.zeros(max(p.nx[n + 1], 1)) for n in range(N)]; lam = [np.zeros(max(2 * nb, 1)) for nb in p.nb]
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        nx, nu, nb, ng = int_array(p.nx), int_array(p.nu), int_array(p.nb), int_array([0] * (N + 1))
+        empty = [np.zeros(1) for _ in range(N + 1)]
+        wsz = self.lib.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N)
+        work = aligned_zeros(wsz // 8 + 16)
+        res = np.zeros(8); stat = np.zeros(5 * k_max + 5); kk = C.c_int(0)
+        pa = ptr_array
+        pidx = pa(idxb)
+        mats = [pa(A), pa(B)]
+        outs = [pa(x), pa(u), pa(pi), pa(lam)]
+        e4 = [pa(empty), pa(empty), pa(empty), pa(empty)]
+        b, q, r, lb, ub = (pa(v) for v in v1)
+        fn = self.lib.c_order_d_ip_ocp_hard_tv if order == "c" else self.lib.fortran_order_d_ip_ocp_hard_tv
+        status = fn(C.byref(kk), k_max, mu0, mu_tol, N, nx, nu, nb, pidx, ng, N, 0, mats[0], mats[1], b, pa(Q), pa(S), pa(R), q, r, lb, ub, *e4,
+                    *outs, res.ctypes.data, work.ctypes.data, stat.ctypes.data)
+        f2 = self.lib.c_order_d_solve_kkt_new_rhs_ocp_hard_tv if order == "c" else self.lib.fortran_order_d_solve_kkt_new_rhs_ocp_hard_tv
+        f2.restype = None
+        f2.argtypes = [C.c_int] + [C.c_void_p] * 25
+        b2, q2, r2, lb2, ub2 = (pa(v) for v in v2)
+        res2 = np.zeros(8)
+        f2(N, nx, nu, nb, pidx, ng, mats[0], mats[1], b2, pa(Q), pa(S), pa(R), q2, r2, lb2, ub2, *e4, *outs, res2.ctypes.data, work.ctypes.data)
+        return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)], u=[u[n][:p.nu[n]].copy() for n in range(N)],
+                    pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)], lam=[lam[n][:2 * p.nb[n]].copy() for n in range(N + 1)],
+                    inf_norm_res=res2[:4].copy())
+
     def single_newton_step(self, p: Ocp, ux0, pi0, lam0, t0, *, k_max=1, mu0=1e-3):
         """fortran_order_d_ip_ocp_hard_tv_single_newton_step (reference include/c_interface.h:66): k_max Newton steps from the
         iterate ux0[n] = [u_n ; x_n], pi0[n], lam0[n] / t0[n] = [lb(nb) ub(nb)]."""

@@ -27,6 +27,7 @@
 #include "layout.h"
 #include "../../include/hpmpc_b200.h"
 #include "../../include/hpmpc_compat.h"
+#include "../../include/hpmpc_blasfeo_compat.h"
 
 #define BS 4
 #define NCL 2
@@ -632,7 +633,7 @@ int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *n
 static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb,
 		int *ng, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q,
 		double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
-		double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *stat)
+		double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *stat, const void *work0)
 	{
 	int n, i, j, l, status;
 	const double alpha_min = 1e-8;       /* c_order_interface.c:141 */
@@ -668,7 +669,9 @@ static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol
 			for(i=0; i<nun; i++) G.h_ux[oU+i] = u[n][i];
 			for(i=0; i<nx[n]; i++) G.h_ux[oU+nun+i] = x[n][i];
 			}
-	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat, NULL)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU execution failed\n"); return -1; }
+	/* the KKT state stays on the device, keyed by the caller's work0 (the reference keeps it IN work0): a later
+	 * {c,fortran}_order_d_solve_kkt_new_rhs_ocp_hard_tv with the same work0 re-solves with it */
+	if(run_ipm_single(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat, work0)) { pthread_mutex_unlock(&g_lock); fprintf(stderr, "hpmpc_b200: GPU execution failed\n"); return -1; }
 	status = (int)G.h_info[1];
 	hpmpc_b200_unpack_solution(G.ocp, G.h_ux, G.h_pi, G.h_lam, x, u, pi, lam);
 	/* inputs fixed by lb == ub are returned exactly on the bound (c_order_interface.c:599-608) */
@@ -685,8 +688,8 @@ int c_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int 
 		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
 		double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)N2; (void)work0;
-	return high_level(1, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat);
+	(void)N2;
+	return high_level(1, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat, work0);
 	}
 
 int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb, int *ng,
@@ -694,8 +697,8 @@ int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol
 		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
 		double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)N2; (void)work0;
-	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat);
+	(void)N2;
+	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat, work0);
 	}
 
 /* reference include/c_interface.h:66 (interfaces/c/fortran_order_interface.c:695): k_max Newton steps from (ux0, pi0, lam0, t0) on
@@ -739,4 +742,257 @@ int fortran_order_d_ip_ocp_hard_tv_single_newton_step(int *kk, int k_max, double
 	for(i=0; i<4; i++) inf_norm_res[i] = G.h_info[2+i];
 	pthread_mutex_unlock(&g_lock);
 	return status;
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* "libstr" twins (row a8): the same entry points on BLASFEO containers (include/hpmpc_blasfeo_compat.h).       */
+/* Each call re-expresses its arguments in the lib4 conventions (host-side format conversion only) and      */
+/* goes through the lib4 symbol above -- one code path to the kernels.                                     */
+/* ------------------------------------------------------------------------------------------------ */
+#define PMS(A, i, j) ((A)->pA[((i)/BS)*BS*(A)->cn + (i)%BS + BS*(j)])
+
+/* blasfeo_dmat (m x n used) -> lib4 panel-major buffer with sda = n rounded up to ncl */
+static double *ls_to_lib4(const struct blasfeo_dmat *A, int m, int n)
+	{
+	int i, j, sda = RUP(n>0 ? n : 1, NCL), pm = RUP(m>0 ? m : 1, BS);
+	double *p = calloc((size_t)pm*sda + 8, sizeof(double));
+	for(i=0; i<m; i++) for(j=0; j<n; j++) PM(p, sda, i, j) = PMS(A, i, j);
+	return p;
+	}
+
+typedef struct { double **BAbt, **RSQ, **DCt, **Qx, **qx, **bd, **b, **q, **ux, **pi, **Pb; int N; } ls_args;
+
+static void ls_free(ls_args *a)
+	{
+	int n;
+	for(n=0; n<=a->N; n++)
+		{
+		if(a->BAbt) free(a->BAbt[n]);
+		if(a->RSQ) free(a->RSQ[n]);
+		if(a->DCt) free(a->DCt[n]);
+		if(a->Qx) free(a->Qx[n]);
+		if(a->qx) free(a->qx[n]);
+		if(a->bd) free(a->bd[n]);
+		}
+	free(a->BAbt); free(a->RSQ); free(a->DCt); free(a->Qx); free(a->qx); free(a->bd); free(a->b); free(a->q); free(a->ux); free(a->pi); free(a->Pb);
+	}
+
+/* matrices, per-constraint vectors ([bounds | general] -> [bounds (pnb) | general]) and the node-indexed pi / Pb as edge arrays */
+static void ls_convert(ls_args *a, int N, int *nx, int *nu, int *nb, int **idxb, int *ng, struct blasfeo_dmat *hsBAbt, struct blasfeo_dmat *hsRSQrq,
+		struct blasfeo_dmat *hsDCt, struct blasfeo_dvec *hsQx, struct blasfeo_dvec *hsqx, struct blasfeo_dvec *hsb, struct blasfeo_dvec *hsrq,
+		struct blasfeo_dvec *hsux, struct blasfeo_dvec *hspi, struct blasfeo_dvec *hsPb)
+	{
+	int n, j;
+	memset(a, 0, sizeof(*a));
+	a->N = N;
+	a->BAbt = calloc(N+1, sizeof(double*)); a->RSQ = calloc(N+1, sizeof(double*)); a->DCt = calloc(N+1, sizeof(double*));
+	a->Qx = calloc(N+1, sizeof(double*)); a->qx = calloc(N+1, sizeof(double*)); a->bd = calloc(N+1, sizeof(double*));
+	a->b = calloc(N+1, sizeof(double*)); a->q = calloc(N+1, sizeof(double*)); a->ux = calloc(N+1, sizeof(double*));
+	a->pi = calloc(N+1, sizeof(double*)); a->Pb = calloc(N+1, sizeof(double*));
+	for(n=0; n<=N; n++)
+		{
+		int nun = n<N ? nu[n] : 0, nux = nun+nx[n], nbn = nb ? nb[n] : 0, ngn = ng ? ng[n] : 0, pnb = nbn>0 ? RUP(nbn, BS) : 0;
+		if(n<N && hsBAbt) a->BAbt[n] = ls_to_lib4(&hsBAbt[n], nux+1, nx[n+1]);
+		if(hsRSQrq) a->RSQ[n] = ls_to_lib4(&hsRSQrq[n], nux+1, nux);
+		if(ngn>0 && hsDCt) a->DCt[n] = ls_to_lib4(&hsDCt[n], nux, ngn);
+		a->Qx[n] = calloc(pnb+ngn+4, sizeof(double)); a->qx[n] = calloc(pnb+ngn+4, sizeof(double)); a->bd[n] = calloc(pnb+4, sizeof(double));
+		for(j=0; j<nbn; j++)
+			{
+			if(hsQx) a->Qx[n][j] = hsQx[n].pa[j];
+			if(hsqx) a->qx[n][j] = hsqx[n].pa[j];
+			if(hsRSQrq) a->bd[n][j] = PMS(&hsRSQrq[n], idxb[n][j], idxb[n][j]);     /* libstr ADDS Qx to the diagonal (:102): bd = the diagonal itself */
+			}
+		for(j=0; j<ngn; j++) { if(hsQx) a->Qx[n][pnb+j] = hsQx[n].pa[nbn+j]; if(hsqx) a->qx[n][pnb+j] = hsqx[n].pa[nbn+j]; }
+		if(n<N && hsb) a->b[n] = hsb[n].pa;
+		if(hsrq) a->q[n] = hsrq[n].pa;
+		if(hsux) a->ux[n] = hsux[n].pa;
+		if(n<N && hspi) a->pi[n] = hspi[n+1].pa;
+		if(n<N && hsPb) a->Pb[n] = hsPb[n+1].pa;
+		}
+	}
+
+int d_back_ric_rec_work_space_size_bytes_libstr(int N, int *nx, int *nu, int *nb, int *ng)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)ng;
+	return 64;
+	}
+
+/* the factor lives in hsL[n].pA in this library's layout: packed trapezoid + inverse diagonal, HB_EVEN(tri(nux)+2 nux) doubles,
+ * which fits the (nux+1) x nux panel-major matrix the caller allocated for every nux >= 1 */
+static double *ls_gather_L(int N, int *nx, int *nu, struct blasfeo_dmat *hsL, int to_struct, double *mem)
+	{
+	int n; size_t off = 0;
+	for(n=0; n<=N; n++)
+		{
+		int nux = (n<N ? nu[n] : 0) + nx[n]; size_t len = HB_EVEN(HB_TRI(nux)+2*nux);
+		if(to_struct) memcpy(hsL[n].pA, mem+off, sizeof(double)*len); else memcpy(mem+off, hsL[n].pA, sizeof(double)*len);
+		off += len;
+		}
+	return mem;
+	}
+
+void d_back_ric_rec_sv_libstr(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int update_b, struct blasfeo_dmat *hsBAbt,
+		struct blasfeo_dvec *hsb, int update_q, struct blasfeo_dmat *hsRSQrq, struct blasfeo_dvec *hsrq, struct blasfeo_dmat *hsDCt,
+		struct blasfeo_dvec *hsQx, struct blasfeo_dvec *hsqx, struct blasfeo_dvec *hsux, int compute_pi, struct blasfeo_dvec *hspi,
+		int compute_Pb, struct blasfeo_dvec *hsPb, struct blasfeo_dmat *hsL, void *work_space)
+	{
+	(void)work_space;
+	ls_args a;
+	int any = 0, n;
+	for(n=0; n<=N; n++) if((nb && nb[n]>0) || (ng && ng[n]>0)) any = 1;
+	ls_convert(&a, N, nx, nu, nb, hidxb, ng, hsBAbt, hsRSQrq, hsDCt, any ? hsQx : NULL, any ? hsqx : NULL, hsb, hsrq, hsux, hspi, hsPb);
+	double *mem = calloc((size_t)d_back_ric_rec_sv_tv_memory_space_size_bytes(N, nx, nu, nb, ng)/sizeof(double) + 8, sizeof(double));
+	d_back_ric_rec_sv_tv_res(N, nx, nu, nb, hidxb, ng, update_b, a.BAbt, a.b, update_q, a.RSQ, a.q, a.bd, a.DCt, any ? a.Qx : NULL, any ? a.qx : NULL,
+			a.ux, compute_pi, a.pi, compute_Pb, a.Pb, mem, NULL);
+	if(hsL) ls_gather_L(N, nx, nu, hsL, 1, mem);
+	free(mem);
+	ls_free(&a);
+	}
+
+void d_back_ric_rec_trf_libstr(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, struct blasfeo_dmat *hsBAbt,
+		struct blasfeo_dmat *hsRSQrq, struct blasfeo_dmat *hsDCt, struct blasfeo_dvec *hsQx, struct blasfeo_dmat *hsL, void *work)
+	{
+	(void)work;
+	ls_args a;
+	int any = 0, n;
+	for(n=0; n<=N; n++) if((nb && nb[n]>0) || (ng && ng[n]>0)) any = 1;
+	ls_convert(&a, N, nx, nu, nb, hidxb, ng, hsBAbt, hsRSQrq, hsDCt, any ? hsQx : NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+	double *mem = calloc((size_t)d_back_ric_rec_sv_tv_memory_space_size_bytes(N, nx, nu, nb, ng)/sizeof(double) + 8, sizeof(double));
+	d_back_ric_rec_trf_tv_res(N, nx, nu, nb, hidxb, ng, a.BAbt, a.RSQ, a.DCt, any ? a.Qx : NULL, a.bd, mem, NULL);
+	ls_gather_L(N, nx, nu, hsL, 1, mem);
+	free(mem);
+	ls_free(&a);
+	}
+
+void d_back_ric_rec_trs_libstr(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, struct blasfeo_dmat *hsBAbt, struct blasfeo_dvec *hsb,
+		struct blasfeo_dvec *hsrq, struct blasfeo_dmat *hsDCt, struct blasfeo_dvec *hsqx, struct blasfeo_dvec *hsux, int compute_pi,
+		struct blasfeo_dvec *hspi, int compute_Pb, struct blasfeo_dvec *hsPb, struct blasfeo_dmat *hsL, void *work)
+	{
+	(void)work;
+	ls_args a;
+	int any = 0, n;
+	for(n=0; n<=N; n++) if((nb && nb[n]>0) || (ng && ng[n]>0)) any = 1;
+	ls_convert(&a, N, nx, nu, nb, idxb, ng, hsBAbt, NULL, hsDCt, NULL, any ? hsqx : NULL, hsb, hsrq, hsux, hspi, hsPb);
+	double *mem = calloc((size_t)d_back_ric_rec_sv_tv_memory_space_size_bytes(N, nx, nu, nb, ng)/sizeof(double) + 8, sizeof(double));
+	ls_gather_L(N, nx, nu, hsL, 0, mem);
+	d_back_ric_rec_trs_tv_res(N, nx, nu, nb, idxb, ng, a.BAbt, a.b, a.q, a.DCt, any ? a.qx : NULL, a.ux, compute_pi, a.pi, compute_Pb, a.Pb, mem, NULL);
+	free(mem);
+	ls_free(&a);
+	}
+
+int d_ip2_res_mpc_hard_work_space_size_bytes_libstr(int N, int *nx, int *nu, int *nb, int *ng)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)ng;
+	return 64;
+	}
+
+int d_ip2_res_mpc_hard_libstr(int *kk, int k_max, double mu0, double mu_tol, double alpha_min, int warm_start, double *stat, int N,
+		int *nx, int *nu, int *nb, int **idxb, int *ng, struct blasfeo_dmat *hsBAbt, struct blasfeo_dmat *hsRSQrq, struct blasfeo_dmat *hsDCt,
+		struct blasfeo_dvec *hsd, struct blasfeo_dvec *hsux, int compute_mult, struct blasfeo_dvec *hspi, struct blasfeo_dvec *hslam,
+		struct blasfeo_dvec *hst, void *work_memory)
+	{
+	ls_args a;
+	int n, j, status;
+	ls_convert(&a, N, nx, nu, nb, idxb, ng, hsBAbt, hsRSQrq, hsDCt, NULL, NULL, NULL, NULL, hsux, hspi, NULL);
+	/* [lb(nb) lg(ng) ub(nb) ug(ng)] unpadded <-> lib4 [lb(pnb) ub(pnb) lg(png) ug(png)] */
+	double **d = calloc(N+1, sizeof(double*)), **lam = calloc(N+1, sizeof(double*)), **t = calloc(N+1, sizeof(double*));
+	for(n=0; n<=N; n++)
+		{
+		int nbn = nb ? nb[n] : 0, ngn = ng ? ng[n] : 0, pnb = nbn>0 ? RUP(nbn, BS) : 0, png = ngn>0 ? RUP(ngn, BS) : 0;
+		d[n] = calloc(2*pnb+2*png+4, sizeof(double)); lam[n] = calloc(2*pnb+2*png+4, sizeof(double)); t[n] = calloc(2*pnb+2*png+4, sizeof(double));
+		for(j=0; j<nbn; j++) { d[n][j] = hsd[n].pa[j]; d[n][pnb+j] = hsd[n].pa[nbn+ngn+j]; }
+		for(j=0; j<ngn; j++) { d[n][2*pnb+j] = hsd[n].pa[nbn+j]; d[n][2*pnb+png+j] = hsd[n].pa[2*nbn+ngn+j]; }
+		}
+	status = d_ip2_res_mpc_hard_tv(kk, k_max, mu0, mu_tol, alpha_min, warm_start, stat, N, nx, nu, nb, idxb, ng, a.BAbt, a.RSQ, a.DCt, d, a.ux,
+			compute_mult, a.pi, lam, t, (double*)work_memory);
+	for(n=0; n<=N; n++)
+		{
+		int nbn = nb ? nb[n] : 0, ngn = ng ? ng[n] : 0, pnb = nbn>0 ? RUP(nbn, BS) : 0, png = ngn>0 ? RUP(ngn, BS) : 0;
+		for(j=0; j<nbn; j++)
+			{
+			hslam[n].pa[j] = lam[n][j]; hslam[n].pa[nbn+ngn+j] = lam[n][pnb+j];
+			hst[n].pa[j] = t[n][j]; hst[n].pa[nbn+ngn+j] = t[n][pnb+j];
+			}
+		for(j=0; j<ngn; j++)
+			{
+			hslam[n].pa[nbn+j] = lam[n][2*pnb+j]; hslam[n].pa[2*nbn+ngn+j] = lam[n][2*pnb+png+j];
+			hst[n].pa[nbn+j] = t[n][2*pnb+j]; hst[n].pa[2*nbn+ngn+j] = t[n][2*pnb+png+j];
+			}
+		free(d[n]); free(lam[n]); free(t[n]);
+		}
+	free(d); free(lam); free(t);
+	ls_free(&a);
+	return status;
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* reference include/c_interface.h:63,67 (interfaces/c/{c,fortran}_order_interface.c:1082): the last KKT system of the         */
+/* preceding {c,fortran}_order_d_ip_ocp_hard_tv call on the same work0, solved again for new b, q, r and bounds.             */
+/* In the reference this pair is unusable as shipped: the second routine lays work0 out differently from the first           */
+/* (fortran_order_interface.c:1193 puts the IPM work space right behind the matrices, :459 puts it last), so it reads         */
+/* factors and backups from the wrong place (tools/repro_highlevel_kkt_new_rhs.py shows it on the compiled reference).        */
+/* Here the pair does what its interface promises: the result equals the low-level pair d_ip2_res_mpc_hard_tv +               */
+/* d_kkt_solve_new_rhs_res_mpc_hard_tv, which IS pinned on the reference (tests/test_kkt_new_rhs.py).                          */
+/* ------------------------------------------------------------------------------------------------ */
+static void high_level_new_rhs(int c_order, int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **A, double **B, double **b,
+		double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
+		double **x, double **u, double **pi, double **lam, double *inf_norm_res, const void *work0, const char *who)
+	{
+	int n, i, j;
+	pthread_mutex_lock(&g_lock);
+	if(!same_pattern(N, nx, nu, nb, hidxb, ng) || G.kkt_key==NULL || G.kkt_key!=work0 || G.sz.nbtot==0)
+		{
+		pthread_mutex_unlock(&g_lock);
+		fprintf(stderr, "hpmpc_b200: %s: no KKT state for this work0 -- call the IPM with the same sizes and work0 first; outputs untouched\n", who);
+		return;
+		}
+	hpmpc_b200_pack_instance(G.ocp, c_order, A, B, b, Q, S, R, q, r, lb, ub, G.h_in);
+	if(C && D && lg && ug) hpmpc_b200_pack_general(G.ocp, c_order, C, D, lg, ug, G.h_in);
+	double *d_rq = NULL, *d_rb = NULL, *d_rd = NULL, *d_mu = NULL;
+	const size_t lamn = (size_t)G.sz.lam_stride;
+	double *h_rq = calloc(G.sz.ux_stride, sizeof(double)), *h_rb = calloc(G.sz.pi_stride+2, sizeof(double)), *h_rd = calloc(lamn, sizeof(double)), h_mu = 0.0;
+	int bad = h2d(G.d_in, G.h_in, G.sz.in_stride)
+		|| hpmpc_b200_d_kkt_solve_new_rhs_batch(G.ocp, 1, G.d_in, G.d_kkt, G.d_ux, G.d_pi, G.d_lam, G.d_t, G.d_info, NULL)
+		|| cudaMalloc((void**)&d_rq, sizeof(double)*G.sz.ux_stride)!=cudaSuccess || cudaMalloc((void**)&d_rb, sizeof(double)*(G.sz.pi_stride+2))!=cudaSuccess
+		|| cudaMalloc((void**)&d_rd, sizeof(double)*lamn)!=cudaSuccess || cudaMalloc((void**)&d_mu, sizeof(double))!=cudaSuccess
+		|| hpmpc_b200_d_res_res_mpc_hard_batch(G.ocp, 1, G.d_in, G.d_ux, G.d_pi, G.d_lam, G.d_t, d_rq, d_rb, d_rd, NULL, d_mu, NULL)
+		|| cudaDeviceSynchronize()!=cudaSuccess
+		|| d2h(G.h_ux, G.d_ux, G.sz.ux_stride) || d2h(G.h_pi, G.d_pi, G.sz.pi_stride) || d2h(G.h_info, G.d_info, HB_IPM_INFO_HEAD)
+		|| d2h(G.h_lam, G.d_lam, G.sz.lam_stride) || d2h(h_rq, d_rq, G.sz.ux_stride) || d2h(h_rb, d_rb, G.sz.pi_stride) || d2h(h_rd, d_rd, lamn) || d2h(&h_mu, d_mu, 1);
+	cudaFree(d_rq); cudaFree(d_rb); cudaFree(d_rd); cudaFree(d_mu);
+	if(bad || G.h_info[1]!=0.0)
+		{
+		free(h_rq); free(h_rb); free(h_rd);
+		pthread_mutex_unlock(&g_lock);
+		fprintf(stderr, "hpmpc_b200: %s: %s; outputs untouched\n", who, bad ? "GPU execution failed" : "the preceding IPM call ran no phase-2 iteration, there is no factor to reuse");
+		return;
+		}
+	hpmpc_b200_unpack_solution(G.ocp, G.h_ux, G.h_pi, G.h_lam, x, u, pi, lam);
+	for(n=0; n<N; n++)
+		for(j=0; j<nb[n] && hidxb[n][j]<nu[n]; j++)
+			if(lb[n][j]==ub[n][j]) u[n][hidxb[n][j]] = lb[n][j];
+	if(inf_norm_res)
+		{
+		double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+		for(i=0; i<G.sz.ux_stride; i++) m0 = fmax(m0, fabs(h_rq[i]));
+		for(i=0; i<G.sz.pi_stride; i++) m1 = fmax(m1, fabs(h_rb[i]));
+		for(i=0; i<(int)lamn; i++) m2 = fmax(m2, fabs(h_rd[i]));
+		inf_norm_res[0] = m0; inf_norm_res[1] = m1; inf_norm_res[2] = m2; inf_norm_res[3] = h_mu;
+		}
+	free(h_rq); free(h_rb); free(h_rd);
+	pthread_mutex_unlock(&g_lock);
+	}
+
+void c_order_d_solve_kkt_new_rhs_ocp_hard_tv(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **A, double **B, double **b,
+		double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
+		double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *work0)
+	{
+	high_level_new_rhs(1, N, nx, nu, nb, hidxb, ng, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, work0, "c_order_d_solve_kkt_new_rhs_ocp_hard_tv");
+	}
+
+void fortran_order_d_solve_kkt_new_rhs_ocp_hard_tv(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **A, double **B, double **b,
+		double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
+		double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *work0)
+	{
+	high_level_new_rhs(0, N, nx, nu, nb, hidxb, ng, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, work0, "fortran_order_d_solve_kkt_new_rhs_ocp_hard_tv");
 	}

@@ -83,6 +83,16 @@ int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol
                                    double **x, double **u, double **pi, double **lam,
                                    double *inf_norm_res, void *work0, double *stat);
 
+/* include/c_interface.h:63,67  (interfaces/c/c_order_interface.c:1082, fortran_order_interface.c:1082): the last KKT system of the
+ * preceding {c,fortran}_order_d_ip_ocp_hard_tv call ON THE SAME work0 solved again for new b, q, r and bounds */
+void c_order_d_solve_kkt_new_rhs_ocp_hard_tv(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **A, double **B, double **b,
+                                             double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub,
+                                             double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
+                                             double **lam, double *inf_norm_res, double *work0);
+void fortran_order_d_solve_kkt_new_rhs_ocp_hard_tv(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **A, double **B, double **b,
+                                                   double **Q, double **S, double **R, double **q, double **r, double **lb, double **ub,
+                                                   double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
+                                                   double **lam, double *inf_norm_res, double *work0);
 /* include/c_interface.h:66  (interfaces/c/fortran_order_interface.c:695) */
 int fortran_order_d_ip_ocp_hard_tv_single_newton_step(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu_N, int *nb,
                                                       int **hidxb, int *ng, int N2, int warm_start, double **A, double **B, double **b,

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = []
-    for h in ("hpmpc_b200.h", "hpmpc_compat.h"):
+    for h in ("hpmpc_b200.h", "hpmpc_compat.h", "hpmpc_blasfeo_compat.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names += re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", " ".join(l for l in src.splitlines() if not l.strip().startswith("#")))
