@@ -198,6 +198,32 @@ def workload_name(w):
 
 
 # ------------------------------------------------------------------------------------------- our arm (GPU)
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this process (and so first-touch its pinned staging buffers) on the host cores of the NUMA node the GPU hangs off:
+    with 8 ranks feeding 8 PCIe links, staging memory on one socket was the e2e limiter of round 1 (SCALE_r01: 0.37 efficiency).
+    Returns a short description for the JSON line; does nothing when sysfs has no answer."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa: rank bound to node {node} ({len(allowed)} cores)"
+        return f"numa: node {node} has no allowed cores"
+    except Exception as e:                                  # noqa: BLE001
+        return f"numa: not bound ({type(e).__name__})"
+
+
 def time_steps(launch, steps, warmup, stream, barrier):
     import torch
     for _ in range(warmup):
@@ -227,6 +253,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- hpmpc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
@@ -260,8 +287,7 @@ def run_ours(args):
                    value=world * n * args.steps / (tot_ms * 1e-3))
         # ---- end to end: pinned host buffers through the host-buffer entry point
         if not args.no_e2e:
-            # with several ranks on one host keep the pinned staging memory bounded (8 x 6 GB would not be polite)
-            ne = n if world == 1 else min(n, 32768)
+            ne = n                          # the same e2e batch at every N: 65 536 instances = 6 GB pinned per rank
             h_in = torch.empty((ne, h.sz.in_stride), dtype=torch.float64, pin_memory=True)
             h_in.copy_(d_in[:ne])
             h_ux = torch.empty((ne, h.sz.ux_stride), dtype=torch.float64, pin_memory=True)
@@ -283,7 +309,7 @@ def run_ours(args):
             te = reduce_max_time(t1 - t0, dev)
             res["e2e"] = {"value": world * ne * ke / te, "unit": "solves/s", "h2d_bytes_per_step": int(ne * h.sz.in_stride * 8),
                           "d2h_bytes_per_step": int(ne * (h.sz.ux_stride + h.sz.pi_stride) * 8), "steps": ke, "instances_per_gpu": ne,
-                          "note": "pinned host buffers -> hpmpc_b200_d_back_ric_rec_sv_batch_host (chunked H2D / kernel / D2H), PCIe-bound"}
+                          "note": "pinned host buffers -> hpmpc_b200_d_back_ric_rec_sv_batch_host (chunked H2D / kernel / D2H), PCIe-bound; " + numa_note}
             assert float((h_ux[:, :8] - ux[:ne].cpu()[:, :8]).abs().max()) == 0.0
             del h_in, h_ux, h_pi
         return res, (d_in, ux, pi)
@@ -498,11 +524,13 @@ def run_ours(args):
     launch_s = res["launch_ms"] * 1e-3
     achieved = w["B_sv"] * n / launch_s / 1e9
     fp64_peak = L.hpmpc_b200_fp64_peak_tflops(local)
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and sz.fast_variant == 0 and n == 65536:
         try:
-            traffic = json.load(open(tpath)).get("hb_ric_sv_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("hb_ric_sv_bytes_per_launch")
+            traffic_src = "static: " + tj.get("hb_ric_sv_source", "profiles/ncu_traffic.json") + " (ncu cannot run inside the timed bench)"
         except Exception:
             traffic = None
     out = {"metric": "lqcp_riccati_solves_per_s", "value": res["value"], "unit": "solves/s", "n_gpus": world, "steps": args.steps,
@@ -510,7 +538,7 @@ def run_ours(args):
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name("ric"), "instances_per_gpu": n, "l2": "inputs (6.4 GB per GPU) exceed the 126 MB L2; no flush between steps",
                       "launch": {"grid": sz.grid, "warps_per_cta": sz.warps_per_cta, "smem_per_cta": sz.smem_per_cta}, "parallelism": f"instances sharded, {world} GPU(s), no collective"},
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": peak_src, "kernel": ("hbk_ric_sv_kernel<12,5,8,2>" if sz.fast_variant == 0 else "hb_ric_sv_kernel"), "launch_ms": res["launch_ms"],
                         "algorithmic_bytes_per_solve": w["B_sv"], "algorithmic_flops_per_solve": w["F_sv"],
                         "fp64": {"achieved_tflops": w["F_sv"] * n / launch_s / 1e12, "peak_tflops": fp64_peak, "frac": w["F_sv"] * n / launch_s / 1e12 / fp64_peak if fp64_peak > 0 else None,
@@ -525,20 +553,26 @@ def run_ours(args):
             out["extra"] = {"ipm": bench_ipm(max(1, min(args.steps, args.ipm_steps)), 1, e2e=(world == 1))}
         except Exception as e:      # the secondary workload must not hide the headline number
             out["extra"] = {"ipm_error": repr(e)}
+        # BASELINE config 5 (scenario trees) at EVERY N, so that the driver's scaling run records it: the Riccati solve of a fixed
+        # batch of trees with the subtrees sharded over the ranks (STRONG scaling, one exchange of subtree-root factor blocks per
+        # solve) and the box IPM over the trees (whole trees per rank, weak).  Short runs; --workload tree / tree_ipm are the full lines.
+        torch.cuda.empty_cache()
+        try:
+            saved = args.n_trees, args.no_cpu
+            args.n_trees, args.no_cpu = args.n_trees or (1024 if world == 1 else 4096), True
+            tr = bench_tree(3, 2)
+            if rank == 0:
+                out["extra"]["tree"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "gpu_launches", "scaling", "n_gpus")} | \
+                    {"workload": tr["config"]["workload"], "parallelism": tr["config"]["parallelism"]}
+            args.n_trees = saved[0] or (1024 if world == 1 else 2048)
+            ti = bench_tree_ipm(2, 1)
+            if rank == 0:
+                out["extra"]["tree_ipm"] = {k: ti[k] for k in ("metric", "value", "unit", "ms_per_step", "mean_iterations", "converged", "scaling", "n_gpus")} | \
+                    {"workload": ti["config"]["workload"]}
+            args.n_trees, args.no_cpu = saved
+        except Exception as e:
+            out["extra"]["tree_error"] = repr(e)
         if world == 1:
-            # BASELINE config 5 (scenario trees): Riccati and box IPM, short runs, single GPU only here (--workload tree / tree_ipm
-            # are the full lines, including the multi-GPU paths)
-            torch.cuda.empty_cache()
-            try:
-                saved = args.n_trees, args.no_cpu
-                args.n_trees, args.no_cpu = args.n_trees or 1024, True
-                tr = bench_tree(3, 2)
-                out["extra"]["tree"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "gpu_launches")} | {"workload": tr["config"]["workload"]}
-                ti = bench_tree_ipm(2, 1)
-                out["extra"]["tree_ipm"] = {k: ti[k] for k in ("metric", "value", "unit", "ms_per_step", "mean_iterations", "converged")} | {"workload": ti["config"]["workload"]}
-                args.n_trees, args.no_cpu = saved
-            except Exception as e:
-                out["extra"]["tree_error"] = repr(e)
             # the IPM's last KKT system solved again for a new right-hand side (cfg 3 shapes, 4096 instances)
             torch.cuda.empty_cache()
             try:
@@ -552,6 +586,25 @@ def run_ours(args):
                                                                   "speedup_vs_full_ipm_solve", "roofline")} | {"workload": kr["config"]["workload"]}
             except Exception as e:
                 out["extra"]["kkt_new_rhs_error"] = repr(e)
+    if rank == 0 and world == 1 and not args.no_cpu and isinstance(out.get("extra", {}).get("ipm"), dict):
+        # the reference's own box IPM (fortran_order_d_ip_ocp_hard_tv, AVX2 lib4 build) on the host cores, bounded sample of config 3
+        try:
+            from oracle import api as oracle
+            cores = os.cpu_count()
+            spec3 = BatchSpec("cfg3", device=-1)
+            n_s = max(128, 4 * cores)
+            rs3 = oracle.RefSample(spec3, n_s, want=("cm",))
+            t1 = rs3.time_ipm("avx2", cores, 1)[0]
+            n_pass = max(1, int(round(3.0 / max(t1, 1e-6))))
+            sec = rs3.time_ipm("avx2", cores, n_pass)[0]
+            v = n_s * n_pass / sec
+            out["extra"]["ipm"]["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "reference",
+                                                   "sample": f"{n_s} distinct config-3 instances x {n_pass} passes, reference X64_AVX2 lib4 build, fortran_order_d_ip_ocp_hard_tv"}
+            if "e2e" in out["extra"]["ipm"]:
+                out["extra"]["ipm"]["e2e_vs_cpu_baseline"] = out["extra"]["ipm"]["e2e"]["value"] / v
+            spec3.h.close()
+        except Exception as e:      # noqa: BLE001
+            out["extra"]["ipm"]["cpu_baseline"] = {"value": None, "sample": f"failed: {e!r}"}
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             from oracle import api as oracle
