@@ -1,0 +1,385 @@
+/*
+ * cipm_kernels.cu -- the box / general-constraint IPM for chains as a MULTI-KERNEL driver with active-set compaction.
+ *
+ * The fused kernel of ipm_kernels.cu runs a whole IPM in one warp: one launch per wave, 254 registers for every phase, several
+ * hundred KB of SASS that the warps of an SM walk through out of step, and a wave that ends with its slowest instance.  Here the
+ * same iteration (mpc_solvers/d_ip2_res_hard.c:116-1345) is cut at its sweeps over the horizon:
+ *
+ *   hb_cipm_step_kernel   everything element-wise between two sweeps, as a per-instance state machine (init, the two step-length /
+ *                         centering computations, the variable update, the loop tests, the barrier terms of the next system);
+ *                         no shared memory, 8 warps per CTA; at the end of a round it COMPACTS: instances that are not finished
+ *                         are appended to the next round's active list, so every warp of the following kernels has work
+ *   hb_cipm_sv_kernel     factor + solve with the IPM hooks      (S::backward + S::forward_sv)   the only 254-register phase
+ *   hb_cipm_trs_kernel    solve with the stored factor             (S::trs)
+ *   hb_cipm_res_kernel    residuals, mu, exit norms                (S::residuals)
+ *
+ * A round is sv, step, trs, step, res, step: every active instance advances by one IPM iteration, whatever its phase.  The host
+ * enqueues k_max rounds without ever reading anything back; a kernel that finds the active list empty returns at once.
+ * Every instance works in its own state block in HBM (the fused kernel's work slot: factor, iterate vectors, constraint vectors).
+ * The device functions are the fused kernel's own (ipm_sweeps.cuh, ipm_elem.cuh), executed in the same order per instance, so the
+ * results -- iteration counts included -- are bit-identical to the fused path (tests/test_cipm.py).
+ */
+#include "launch_util.cuh"
+#include "ipm_sweeps.cuh"
+
+enum { CS_INIT=0, CS_P1_SV, CS_P1_A, CS_P1_TRS, CS_P1_B, CS_P2_SV, CS_P2_A, CS_P2_TRS, CS_P2_B,
+       CS_RES_ENTER /* residuals wanted before phase 2 starts */, CS_RES_ITER /* ... at the end of a phase-2 iteration */,
+       CS_RES_ENTER_DONE, CS_RES_ITER_DONE, CS_DONE };
+
+/* per-instance record: doubles [0] mu [1] alpha [2] sigma [3..5] exit norms ; ints [0] state [1] kk */
+#define CIPM_D 6
+#define CIPM_I 2
+
+struct hb_cipm_args
+	{
+	hb_dims d;
+	long long n_inst;
+	const double *in;
+	int k_max; double mu0, mu_tol, alpha_min; int warm_start;
+	double *ux, *pi, *lam, *t, *info;
+	double *work; long long work_stride;
+	double *sd; int *si;                    /* state records */
+	const int *act; const int *n_act;       /* active list of this launch (act == nullptr: all instances 0..n_inst-1) */
+	int *act_next; int *n_act_next;         /* step kernel, end of a round: the list it builds (nullptr: none) */
+	};
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+template<class S>
+__global__ void __launch_bounds__(256) hb_cipm_step_kernel(hb_cipm_args a)
+	{
+	const hb_dims &d = a.d;
+	const int lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + (threadIdx.x>>5), tw = (long long)gridDim.x*nw;
+	const long long n_items = a.act ? (long long)*a.n_act : a.n_inst;
+	typename S::ctx_t c;
+	c.lane = lane;                                /* extract / emit only look at the lane */
+	const int info_len = HB_IPM_INFO_HEAD + 5*a.k_max;
+	const double thr0 = 0.1, mu0 = a.mu0, mu_tol = a.mu_tol, alpha_min = a.alpha_min;
+	const double mu_tol_low = mu_tol<1e-5 ? 1e-5 : mu_tol;
+	const double mu_scal = d.nbtot>0 ? 1.0/(2.0*d.nbtot) : 0.0;
+	const int k_max = a.k_max;
+	for(long long it=gw; it<n_items; it+=tw)
+		{
+		const long long inst = a.act ? a.act[it] : it;
+		int *si = a.si + inst*CIPM_I; double *sd = a.sd + inst*CIPM_D;
+		int st = si[0], kk = si[1];
+		double mu = sd[0], alpha = sd[1], sigma = sd[2], mu_aff;
+		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst*a.work_stride);
+		const double *in_inst = a.in + inst*d.in_stride;
+		double *ux = a.ux + inst*d.ux_stride, *pi = a.pi + inst*d.pi_stride;
+		double *info = a.info + inst*info_len, *stat = info + HB_IPM_INFO_HEAD;
+		bool top1 = false, top2 = false;
+		__syncwarp();
+		if(st==CS_INIT)
+			{
+			S::extract(c, d, in_inst, w);
+			__syncwarp();
+			/* init (c99/d_aux_ip_hard_lib4.c:43-149) */
+			if(!a.warm_start) for(long long i=lane; i<d.ux_stride; i+=32) ux[i] = 0.0;
+			for(long long i=lane; i<d.pi_stride; i+=32) pi[i] = 0.0;
+			__syncwarp();
+			for(int cc=lane; cc<d.nbtot; cc+=32)
+				{
+				const int iu = d.c_ux[cc];
+				if(iu<0) continue;
+				double lb = w.v(CV_LB)[cc], ub = w.v(CV_UB)[cc], u = ux[iu];
+				double tl = -lb + u, tu = ub - u;
+				if(tl<thr0)
+					{
+					if(tu<thr0) { ux[iu] = (-ub + lb)*0.5; tl = thr0; tu = thr0; }
+					else { tl = thr0; ux[iu] = lb + thr0; }
+					}
+				else if(tu<thr0) { tu = thr0; ux[iu] = ub - thr0; }
+				w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
+				w.v(CV_LAM_LO)[cc] = mu0/tl; w.v(CV_LAM_UP)[cc] = mu0/tu;
+				}
+			__syncwarp();
+			if(d.ngtot>0)
+				{
+				hb_gen_values(lane, d, in_inst, w, ux);
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					if(d.c_ux[cc]>=0) continue;
+					const double v = w.v(CV_VAL)[cc];
+					const double tl = fmax(thr0, v - w.v(CV_LB)[cc]), tu = fmax(thr0, -v + w.v(CV_UB)[cc]);
+					w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
+					w.v(CV_LAM_LO)[cc] = mu0/tl; w.v(CV_LAM_UP)[cc] = mu0/tu;
+					}
+				__syncwarp();
+				}
+			mu = mu0; alpha = 1.0; sigma = 0.0; kk = 0;
+			top1 = true;
+			}
+		else if(st==CS_P1_A || st==CS_P2_A)
+			{
+			/* after the predictor solve: affine step length, mu_aff, sigma, the corrector's gradient (d_ip2_res_hard.c:560-640, :1010-1100) */
+			const bool p2 = (st==CS_P2_A);
+			hb_gen_values(lane, d, in_inst, w, w.dux);
+			alpha = p2 ? hb_ipm_alpha<true>(lane, d, w, w.dux) : hb_ipm_alpha<false>(lane, d, w, w.dux);
+			__syncwarp();
+			if(lane==0) { stat[5*kk] = sigma; stat[5*kk+1] = alpha; }
+			alpha *= 0.995;
+			mu_aff = hb_ipm_mu_aff(lane, d, w, alpha, mu_scal);
+			if(lane==0) stat[5*kk+2] = mu_aff;
+			sigma = mu_aff/mu; sigma = sigma*sigma*sigma;
+			const double sm = sigma*mu;
+			if(!p2)
+				{
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double dll = w.v(CV_TINV_LO)[cc]*(sm - w.v(CV_DLAM_LO)[cc]*w.v(CV_DT_LO)[cc]);
+					double dlu = w.v(CV_TINV_UP)[cc]*(sm - w.v(CV_DLAM_UP)[cc]*w.v(CV_DT_UP)[cc]);
+					w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
+					w.v(CV_QXG)[cc] += dlu - dll;
+					}
+				}
+			else
+				{
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double rml = w.v(CV_RM_LO)[cc] + (w.v(CV_DT_LO)[cc]*w.v(CV_DLAM_LO)[cc] - sm);
+					double rmu = w.v(CV_RM_UP)[cc] + (w.v(CV_DT_UP)[cc]*w.v(CV_DLAM_UP)[cc] - sm);
+					w.v(CV_RM_LO)[cc] = rml; w.v(CV_RM_UP)[cc] = rmu;
+					w.v(CV_QXG)[cc] = w.v(CV_TINV_LO)[cc]*(rml - w.v(CV_LAM_LO)[cc]*w.v(CV_RD_LO)[cc])
+					                  - w.v(CV_TINV_UP)[cc]*(rmu + w.v(CV_LAM_UP)[cc]*w.v(CV_RD_UP)[cc]);
+					}
+				}
+			st = p2 ? CS_P2_TRS : CS_P1_TRS;
+			}
+		else if(st==CS_P1_B)
+			{
+			/* after the corrector solve: step length, update_var, mu (c99/d_aux_ip_hard_lib4.c:489-711) */
+			hb_gen_values(lane, d, in_inst, w, w.dux);
+			alpha = hb_ipm_alpha<false>(lane, d, w, w.dux);
+			__syncwarp();
+			if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
+			alpha *= 0.995;
+			for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += alpha*(w.dux[i] - ux[i]);
+			for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += alpha*(w.dpi[i] - pi[i]);
+			double ms = 0.0;
+			for(int cc=lane; cc<d.nbtot; cc+=32)
+				{
+				double ll = w.v(CV_LAM_LO)[cc] + alpha*w.v(CV_DLAM_LO)[cc];
+				double lu = w.v(CV_LAM_UP)[cc] + alpha*w.v(CV_DLAM_UP)[cc];
+				double tl = w.v(CV_T_LO)[cc] + alpha*w.v(CV_DT_LO)[cc];
+				double tu = w.v(CV_T_UP)[cc] + alpha*w.v(CV_DT_UP)[cc];
+				w.v(CV_LAM_LO)[cc] = ll; w.v(CV_LAM_UP)[cc] = lu; w.v(CV_T_LO)[cc] = tl; w.v(CV_T_UP)[cc] = tu;
+				ms += ll*tl + lu*tu;
+				}
+			mu = hb_warp_sum(ms)*mu_scal;
+			if(lane==0) stat[5*kk+4] = mu;
+			kk++;
+			top1 = true;
+			}
+		else if(st==CS_P2_B)
+			{
+			/* phase 2: step length and update (c99/d_aux_ip_hard_lib4.c:1180-1449); the residuals decide what comes next */
+			hb_gen_values(lane, d, in_inst, w, w.dux);
+			alpha = hb_ipm_alpha<true>(lane, d, w, w.dux);
+			__syncwarp();
+			if(lane==0) { stat[5*kk] = sigma; stat[5*kk+3] = alpha; }
+			alpha *= 0.995;
+			for(long long i=lane; i<d.ux_stride; i+=32) ux[i] += alpha*w.dux[i];
+			for(long long i=lane; i<d.pi_stride; i+=32) pi[i] += alpha*w.dpi[i];
+			for(int cc=lane; cc<d.nbtot; cc+=32)
+				{
+				w.v(CV_LAM_LO)[cc] += alpha*w.v(CV_DLAM_LO)[cc]; w.v(CV_LAM_UP)[cc] += alpha*w.v(CV_DLAM_UP)[cc];
+				w.v(CV_T_LO)[cc] += alpha*w.v(CV_DT_LO)[cc]; w.v(CV_T_UP)[cc] += alpha*w.v(CV_DT_UP)[cc];
+				}
+			st = CS_RES_ITER;
+			}
+		else if(st==CS_RES_ENTER_DONE) top2 = true;
+		else if(st==CS_RES_ITER_DONE)
+			{
+			if(lane==0) stat[5*kk+4] = mu;
+			kk++;
+			top2 = true;
+			}
+		__syncwarp();
+		if(top1)
+			{
+			/* top of the phase-1 loop (d_ip2_res_hard.c:503) */
+			if(kk<k_max && mu>mu_tol_low && alpha>=alpha_min)
+				{
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double til = 1.0/w.v(CV_T_LO)[cc], tiu = 1.0/w.v(CV_T_UP)[cc];
+					double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc];
+					double ltl = ll*til, ltu = lu*tiu;
+					double dll = til*0.0, dlu = tiu*0.0;
+					w.v(CV_TINV_LO)[cc] = til; w.v(CV_TINV_UP)[cc] = tiu;
+					w.v(CV_LAMT_LO)[cc] = ltl; w.v(CV_LAMT_UP)[cc] = ltu;
+					w.v(CV_DLAM_LO)[cc] = dll; w.v(CV_DLAM_UP)[cc] = dlu;
+					w.v(CV_QXD)[cc] = ltl + ltu;
+					w.v(CV_QXG)[cc] = lu - ltu*w.v(CV_UB)[cc] + dlu - ll - ltl*w.v(CV_LB)[cc] - dll;
+					}
+				st = CS_P1_SV;
+				}
+			else st = CS_RES_ENTER;
+			}
+		if(top2)
+			{
+			/* top of the phase-2 loop (d_ip2_res_hard.c:783) */
+			if(kk<k_max && mu>mu_tol && alpha>=alpha_min)
+				{
+				for(int cc=lane; cc<d.nbtot; cc+=32)
+					{
+					double til = 1.0/w.v(CV_T_LO)[cc], tiu = 1.0/w.v(CV_T_UP)[cc];
+					double ll = w.v(CV_LAM_LO)[cc], lu = w.v(CV_LAM_UP)[cc];
+					w.v(CV_TINV_LO)[cc] = til; w.v(CV_TINV_UP)[cc] = tiu;
+					w.v(CV_QXD)[cc] = til*ll + tiu*lu;
+					w.v(CV_QXG)[cc] = til*(w.v(CV_RM_LO)[cc] - ll*w.v(CV_RD_LO)[cc]) - tiu*(w.v(CV_RM_UP)[cc] + lu*w.v(CV_RD_UP)[cc]);
+					}
+				st = CS_P2_SV;
+				}
+			else
+				{
+				int status;
+				if(mu<=mu_tol) status = 0;
+				else if(kk>=k_max) status = 1;
+				else if(alpha<alpha_min) status = 2;
+				else status = -1;
+				S::emit(c, d, w, a.lam + inst*2*(long long)d.nbtot, a.t + inst*2*(long long)d.nbtot);
+				if(lane==0)
+					{
+					info[0] = (double)kk; info[1] = (double)status;
+					info[2] = sd[3]; info[3] = sd[4]; info[4] = sd[5]; info[5] = mu;
+					}
+				st = CS_DONE;
+				}
+			}
+		__syncwarp();
+		if(lane==0)
+			{
+			si[0] = st; si[1] = kk;
+			sd[0] = mu; sd[1] = alpha; sd[2] = sigma;
+			if(a.act_next!=nullptr && st!=CS_DONE) a.act_next[atomicAdd(a.n_act_next, 1)] = (int)inst;      /* compaction */
+			}
+		__syncwarp();
+		}
+	}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* which: 0 = factor + solve (predictor), 1 = solve with the stored factor (corrector), 2 = residuals                 */
+template<class S, int WHICH>
+__global__ void __launch_bounds__(256) hb_cipm_sweep_kernel(hb_cipm_args a)
+	{
+	const hb_dims &d = a.d;
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	const long long n_items = a.act ? (long long)*a.n_act : a.n_inst;
+	if(n_items==0) return;
+	typename S::ctx_t c;
+	S::init(c, d, hb_smem + (size_t)warp*S::smem_doubles(d), lane);
+	for(long long it=gw; it<n_items; it+=tw)
+		{
+		const long long inst = a.act ? a.act[it] : it;
+		int *si = a.si + inst*CIPM_I; double *sd = a.sd + inst*CIPM_D;
+		const int st = si[0];
+		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst*a.work_stride);
+		const double *in_inst = a.in + inst*d.in_stride;
+		__syncwarp();
+		if(WHICH==0)
+			{
+			if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
+			const bool p2 = (st==CS_P2_SV);
+			S::backward(c, d, in_inst, w, p2 ? w.res_b : nullptr, p2 ? w.res_q : nullptr, w.v(CV_QXD), w.v(CV_QXG));
+			__syncwarp();
+			S::forward_sv(c, d, in_inst, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+			__syncwarp();
+			if(lane==0) si[0] = p2 ? CS_P2_A : CS_P1_A;
+			}
+		else if(WHICH==1)
+			{
+			if(st!=CS_P1_TRS && st!=CS_P2_TRS) continue;
+			const bool p2 = (st==CS_P2_TRS);
+			S::trs(c, d, in_inst, w, p2 ? w.res_b : w.b0, p2 ? w.res_q : w.rq0, w.v(CV_QXG));
+			__syncwarp();
+			if(lane==0) si[0] = p2 ? CS_P2_B : CS_P1_B;
+			}
+		else
+			{
+			if(st!=CS_RES_ENTER && st!=CS_RES_ITER) continue;
+			double mu = sd[0], norms[3] = {0.0, 0.0, 0.0};
+			S::residuals(c, d, in_inst, w, a.ux + inst*d.ux_stride, a.pi + inst*d.pi_stride, &mu, norms);
+			__syncwarp();
+			if(lane==0)
+				{
+				sd[0] = mu; sd[3] = norms[0]; sd[4] = norms[1]; sd[5] = norms[2];
+				si[0] = (st==CS_RES_ENTER) ? CS_RES_ENTER_DONE : CS_RES_ITER_DONE;
+				}
+			}
+		__syncwarp();
+		}
+	}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &base, int *lists, int *counters, int grid_sweep, int warps_sweep,
+		int sms, cudaStream_t st)
+	{
+	/* lists: 2 x n_inst ints ; counters: 2 ints */
+	hb_cipm_args a = base;
+	const long long n = a.n_inst;
+	const int step_warps = 8;
+	long long need = (n + step_warps - 1)/step_warps;
+	const int grid_step = (int)(need < (long long)sms*8 ? (need<1 ? 1 : need) : (long long)sms*8);
+	if(hb_prep(hb_cipm_sweep_kernel<S, 0>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 1>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 2>, smem_sweep)) return -1;
+	int *act[2] = { lists, lists + n }, *cnt[2] = { counters, counters + 1 };
+	HB_CK(cudaMemsetAsync(a.si, 0, sizeof(int)*CIPM_I*(size_t)n, st));          /* every instance starts in CS_INIT */
+	HB_CK(cudaMemsetAsync(counters, 0, 2*sizeof(int), st));
+	/* init: all instances, builds list 0 */
+	a.act = nullptr; a.n_act = nullptr; a.act_next = act[0]; a.n_act_next = cnt[0];
+	hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
+	/* instances whose first loop test already fails (mu0 below the phase-1 threshold) want residuals before anything else */
+	a.act = act[0]; a.n_act = cnt[0]; a.act_next = nullptr; a.n_act_next = nullptr;
+	hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+	hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
+	for(int r=0; r<a.k_max; r++)
+		{
+		const int cur = r&1, nxt = cur^1;
+		a.act = act[cur]; a.n_act = cnt[cur]; a.act_next = nullptr; a.n_act_next = nullptr;
+		hb_cipm_sweep_kernel<S, 0><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
+		hb_cipm_sweep_kernel<S, 1><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
+		hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+		HB_CK(cudaMemsetAsync(cnt[nxt], 0, sizeof(int), st));
+		a.act_next = act[nxt]; a.n_act_next = cnt[nxt];
+		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
+		}
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+/* work: n_inst state blocks of work_stride doubles ; aux: n_inst*(CIPM_D doubles) + ints (2 lists, records, 2 counters) */
+extern "C" long long hb_cipm_aux_bytes(long long n_inst)
+	{
+	return (long long)sizeof(double)*CIPM_D*n_inst + (long long)sizeof(int)*(2*n_inst + CIPM_I*n_inst + 8) + 64;
+	}
+
+extern "C" int hb_launch_cipm(const hb_dims *d, long long n_inst, const double *in, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *ux, double *pi, double *lam, double *t, double *info, double *work, long long work_stride, void *aux,
+		int grid, int warps, int sms, int fast_id, void *stream)
+	{
+	if(d->nzM>64) return -2;
+	if(warps>8 || d->nbtot<=0 || n_inst>2000000000LL) return -3;
+	cudaStream_t st = (cudaStream_t)stream;
+	hb_cipm_args a;
+	a.d = *d; a.n_inst = n_inst; a.in = in; a.k_max = k_max; a.mu0 = mu0; a.mu_tol = mu_tol; a.alpha_min = alpha_min; a.warm_start = warm_start;
+	a.ux = ux; a.pi = pi; a.lam = lam; a.t = t; a.info = info; a.work = work; a.work_stride = work_stride;
+	a.sd = (double*)aux;
+	int *ip = (int*)((char*)aux + sizeof(double)*CIPM_D*(size_t)n_inst);
+	a.si = ip; ip += CIPM_I*n_inst;
+	int *lists = ip; ip += 2*n_inst;
+	int *counters = ip;
+	a.act = nullptr; a.n_act = nullptr; a.act_next = nullptr; a.n_act_next = nullptr;
+	long long need = (n_inst + warps - 1)/warps;
+	if(need<grid) grid = (int)(need<1 ? 1 : need);
+	switch(fast_id)
+		{
+		case 0: return hb_cipm_run<hb_sweeps_fast<hbi_v0> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v0>::PER_WARP, a, lists, counters, grid, warps, sms, st);
+		case 1: return hb_cipm_run<hb_sweeps_fast<hbi_v1> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v1>::PER_WARP, a, lists, counters, grid, warps, sms, st);
+		case 2: return hb_cipm_run<hb_sweeps_fast<hbi_v2> >(warps*(int)sizeof(double)*hbi_cfg<hbi_v2>::PER_WARP, a, lists, counters, grid, warps, sms, st);
+		}
+	return hb_cipm_run<hb_sweeps_generic>(warps*hb_smem_bytes_per_warp(d), a, lists, counters, grid, warps, sms, st);
+	}

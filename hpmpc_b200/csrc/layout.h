@@ -137,6 +137,10 @@ int hb_fast_variant(int N, const int *nx, const int *nu);
 int hb_fast_info(int id, int N, int *ipw, int *smem_warp, long long *stash_per_inst);
 int hb_launch_ric_sv_fast(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, void *stream);
+long long hb_cipm_aux_bytes(long long n_inst);
+int hb_launch_cipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *ux, double *pi, double *lam, double *t, double *info, double *work, long long work_stride, void *aux,
+		int grid, int warps, int sms, int fast_id, void *stream);
 long long hb_res_work_doubles(const hb_dims *dims);
 int hb_launch_res(const hb_dims *dims, long long n_inst, const double *in, const double *ux, const double *pi, const double *lam,
 		const double *t, double *rq, double *rb, double *rd, double *rm, double *mu, double *work, int grid, int warps, void *stream);

@@ -591,6 +591,45 @@ static int ipm_waves(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, in
 	return 0;
 	}
 
+/* Large batches: the multi-kernel driver with active-set compaction (cipm_kernels.cu).  Every instance gets its own state block,
+ * so the batch is cut into chunks whose state fits `cap` bytes (HPMPC_B200_IPM_STATE_GB, default 16 GiB); small batches (less than
+ * two waves of the fused kernel), k_max < 1 and unconstrained patterns stay on the fused one-kernel path.  HPMPC_B200_IPM_FUSED=1
+ * forces the fused path, =0 forces the multi-kernel one.  Both give the same bits (tests/test_cipm.py). */
+static int ipm_multi_wanted(const hpmpc_b200_ocp *p, long long n_inst, int k_max, int warm_start)
+	{
+	const char *e = getenv("HPMPC_B200_IPM_FUSED");
+	if(p->dims.nbtot<=0 || k_max<1 || warm_start==2) return 0;
+	if(e) return atoi(e)==0;
+	/* measured on B200 (profiles/r02_ipm_multi_kernel.txt): config 3 (size-specialised sweeps) 67.4 -> 82.9 K solves/s; config 4
+	 * (run-time-size sweeps, whose kernels are latency-bound whatever drives them) 71.2 -> 64.4 K, so those stay fused */
+	return p->ipm_fast_id>=0 && n_inst >= 2LL*p->i_grid*p->i_warps;
+	}
+
+static int ipm_multi(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0, double mu_tol, double alpha_min,
+		int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, void *stream)
+	{
+	const long long ws = HB_EVEN(p->ipm_ws);
+	double cap_gb = 16.0;
+	{ const char *e = getenv("HPMPC_B200_IPM_STATE_GB"); if(e && atof(e)>0) cap_gb = atof(e); }
+	long long chunk = (long long)(cap_gb*1073741824.0/(8.0*(double)ws));
+	if(chunk<1) chunk = 1;
+	if(chunk>n_inst) chunk = n_inst;
+	const size_t work_b = sizeof(double)*(size_t)chunk*ws;
+	const size_t aux_b = (size_t)hb_cipm_aux_bytes(chunk);
+	if(ensure_scratch(p, work_b + aux_b + 256)) return -1;
+	const long long info_len = HB_IPM_INFO_HEAD + 5*(long long)k_max;
+	long long done;
+	for(done=0; done<n_inst; done+=chunk)
+		{
+		long long m = n_inst-done<chunk ? n_inst-done : chunk;
+		int rc = hb_launch_cipm(&p->dims, m, d_in + done*p->dims.in_stride, k_max, mu0, mu_tol, alpha_min, warm_start,
+				d_ux + done*p->dims.ux_stride, d_pi + done*p->dims.pi_stride, d_lam + done*p->lam_stride, d_t + done*p->lam_stride,
+				d_info + done*info_len, p->scratch, ws, (char*)p->scratch + work_b, p->i_grid, p->i_warps, p->sms, p->ipm_fast_id, stream);
+		if(rc) return rc;
+		}
+	return 0;
+	}
+
 int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0,
 		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t,
 		double *d_info, void *stream)
@@ -599,6 +638,8 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch(hpmpc_b200_ocp *p, long long n_inst, con
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	if(call_begin(p, stream)) return -1;
+	if(ipm_multi_wanted(p, n_inst, k_max, warm_start))
+		return call_end(p, stream, ipm_multi(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, stream));
 	if(ensure_scratch(p, sizeof(double)*(size_t)p->i_grid*p->i_warps*p->ipm_ws)) return -1;
 	return call_end(p, stream, ipm_waves(p, n_inst, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->scratch, p->counter,
 			p->lam_stride, stream, NULL));
