@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <cuda_runtime_api.h>
+#include <dlfcn.h>
 #include "layout.h"
 #include "../../include/hpmpc_b200_tree.h"
 
@@ -39,6 +40,7 @@ struct hpmpc_b200_tree
 	int *f_nact, *h_nact;    /* device / pinned host: trees still iterating */
 	long long n_launches;    /* kernels launched through this handle so far (bench.py reports it) */
 	double *trs_ws; int trs_slots;          /* right-hand sides and Pb of the solve-only path, per warp slot */
+	double *mg_send, *mg_recv; size_t mg_send_bytes, mg_recv_bytes;   /* staging of the multi-GPU exchange (tree_mg below) */
 	};
 
 int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
@@ -285,6 +287,7 @@ void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
 		cudaFree((void*)t->maps.g_ux); cudaFree((void*)t->maps.b_pi); cudaFree((void*)t->maps.c_diag); cudaFree((void*)t->maps.c_grad);
 		cudaFree(t->f_in_mod); cudaFree(t->f_dux); cudaFree(t->f_dpi); cudaFree(t->f_L); cudaFree(t->f_ws); cudaFree(t->f_state);
 		cudaFree(t->f_nact); if(t->h_nact) cudaFreeHost(t->h_nact); cudaFree(t->trs_ws);
+		cudaFree(t->mg_send); cudaFree(t->mg_recv);
 		}
 	free(t->idxb); free(t->c_ux);
 	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->slot); free(t->tail_root); free(t);
@@ -599,4 +602,131 @@ int hpmpc_b200_d_tree_back_ric_rec_trs_batch(hpmpc_b200_tree *t, long long n_tre
 		}
 	t->n_launches++;
 	return hb_launch_tree_trf_trs(&t->ipm_dims, n_trees, d_in, (double*)d_L, d_ux, d_pi, t->trs_ws, t->trs_slots, 1, grid, warps, stream);
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Scenario tree on several GPUs: subtrees shard over the ranks, ONE exchange per solve -- an all-gather    */
+/* of the subtree roots' factor blocks over NVLink with NCCL -- issued by this library on the caller's stream.                    */
+/* Reference recursion: lqcp_solvers/d_tree_back_ric_rec_libstr.c:524-583 (the node loop the phases below cut at the level of    */
+/* the subtree roots).  NCCL is reached through dlopen("libnccl.so.2"): the library has no link-time dependency on it, and in a   */
+/* process that already loaded NCCL (torch) the same copy is used.                                                               */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct { char internal[128]; } hb_nccl_uid;
+typedef void *hb_nccl_comm;
+static struct
+	{
+	void *lib;
+	int (*GetUniqueId)(hb_nccl_uid *);
+	int (*CommInitRank)(hb_nccl_comm *, int, hb_nccl_uid, int);
+	int (*CommDestroy)(hb_nccl_comm);
+	int (*AllGather)(const void *, void *, size_t, int, hb_nccl_comm, cudaStream_t);
+	const char *(*GetErrorString)(int);
+	} NC;
+
+static int nccl_load(void)
+	{
+	if(NC.lib) return 0;
+	const char *names[3] = { getenv("HPMPC_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+	int k;
+	for(k=0; k<3 && !NC.lib; k++) if(names[k]) NC.lib = dlopen(names[k], RTLD_NOW|RTLD_GLOBAL);
+	if(!NC.lib) { fprintf(stderr, "hpmpc_b200: NCCL not found (%s)\n", dlerror()); return -1; }
+	NC.GetUniqueId = (int (*)(hb_nccl_uid*))dlsym(NC.lib, "ncclGetUniqueId");
+	NC.CommInitRank = (int (*)(hb_nccl_comm*, int, hb_nccl_uid, int))dlsym(NC.lib, "ncclCommInitRank");
+	NC.CommDestroy = (int (*)(hb_nccl_comm))dlsym(NC.lib, "ncclCommDestroy");
+	NC.AllGather = (int (*)(const void*, void*, size_t, int, hb_nccl_comm, cudaStream_t))dlsym(NC.lib, "ncclAllGather");
+	NC.GetErrorString = (const char *(*)(int))dlsym(NC.lib, "ncclGetErrorString");
+	if(!NC.GetUniqueId || !NC.CommInitRank || !NC.CommDestroy || !NC.AllGather) { fprintf(stderr, "hpmpc_b200: NCCL symbols missing\n"); NC.lib = NULL; return -1; }
+	return 0;
+	}
+#define NCK(x) do { int r_ = (x); if(r_!=0) { fprintf(stderr, "hpmpc_b200: NCCL error %s at %s:%d\n", NC.GetErrorString ? NC.GetErrorString(r_) : "?", __FILE__, __LINE__); return -1; } } while(0)
+
+struct hpmpc_b200_comm { hb_nccl_comm comm; int world, rank, owned; };
+
+int hpmpc_b200_comm_unique_id(void *id, int id_bytes)
+	{
+	if(id_bytes<(int)sizeof(hb_nccl_uid) || nccl_load()) return -1;
+	NCK(NC.GetUniqueId((hb_nccl_uid*)id));
+	return 0;
+	}
+
+int hpmpc_b200_comm_create(hpmpc_b200_comm **out, int world, int rank, const void *id, int device)
+	{
+	*out = NULL;
+	if(nccl_load()) return -1;
+	CK(cudaSetDevice(device));
+	hpmpc_b200_comm *c = calloc(1, sizeof(*c));
+	if(!c) return -1;
+	hb_nccl_uid uid; memcpy(&uid, id, sizeof(uid));
+	int r = NC.CommInitRank(&c->comm, world, uid, rank);
+	if(r!=0) { fprintf(stderr, "hpmpc_b200: ncclCommInitRank failed: %s\n", NC.GetErrorString ? NC.GetErrorString(r) : "?"); free(c); return -1; }
+	c->world = world; c->rank = rank; c->owned = 1;
+	*out = c;
+	return 0;
+	}
+
+/* an ncclComm_t the caller already has (it must come from the NCCL copy this process has loaded) */
+int hpmpc_b200_comm_wrap(hpmpc_b200_comm **out, void *nccl_comm, int world, int rank)
+	{
+	*out = NULL;
+	if(nccl_load()) return -1;
+	hpmpc_b200_comm *c = calloc(1, sizeof(*c));
+	if(!c) return -1;
+	c->comm = nccl_comm; c->world = world; c->rank = rank; c->owned = 0;
+	*out = c;
+	return 0;
+	}
+
+void hpmpc_b200_comm_destroy(hpmpc_b200_comm *c)
+	{
+	if(!c) return;
+	if(c->owned && NC.CommDestroy) NC.CommDestroy(c->comm);
+	free(c);
+	}
+
+/* Every rank holds the data of all n_trees trees and calls this with the same arguments; on return every rank has ux / pi of ITS
+ * subtrees' nodes and of the nodes above them (the latter computed redundantly on every rank).  Subtrees k*world/.. are split
+ * evenly: n_shard_nodes must be a multiple of the communicator size.  Nothing blocks the host. */
+int hpmpc_b200_d_tree_back_ric_rec_sv_batch_mg(hpmpc_b200_tree *t, hpmpc_b200_comm *c, long long n_trees, const double *d_in,
+		double *d_ux, double *d_pi, double *d_L, void *stream)
+	{
+	if(n_trees<=0) return 0;
+	if(!c || c->world<=1) return hpmpc_b200_d_tree_back_ric_rec_sv_batch(t, n_trees, d_in, d_ux, d_pi, d_L, stream);
+	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
+	if(t->cut_stage<1) { fprintf(stderr, "hpmpc_b200: tree_mg: the tree has no level to shard below\n"); return -6; }
+	const int ns = t->lvl_seg[t->cut_stage] - t->lvl_seg[t->cut_stage-1];
+	if(ns%c->world!=0) { fprintf(stderr, "hpmpc_b200: tree_mg: %d subtrees do not split evenly over %d ranks\n", ns, c->world); return -6; }
+	const int per = ns/c->world, lo = c->rank*per, hi = lo+per;
+	int node, o0, ln, tlo, thi, k, rc;
+	hpmpc_b200_tree_shard_node(t, 0, &node, &o0, &ln, NULL, NULL);
+	for(k=0; k<ns; k++)
+		{
+		int ok, lk;
+		hpmpc_b200_tree_shard_node(t, k, &node, &ok, &lk, NULL, NULL);
+		if(ok!=o0+k*ln || lk!=ln) { fprintf(stderr, "hpmpc_b200: tree_mg: subtree-root factor blocks are not contiguous\n"); return -6; }
+		}
+	hpmpc_b200_tree_shard_node(t, lo, NULL, NULL, NULL, &tlo, NULL);
+	hpmpc_b200_tree_shard_node(t, hi-1, NULL, NULL, NULL, NULL, &thi);
+	CK(cudaSetDevice(t->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t seg = (size_t)per*ln;                         /* doubles per tree this rank contributes */
+	const size_t send_b = sizeof(double)*seg*(size_t)n_trees, recv_b = send_b*(size_t)c->world;
+	if(send_b>t->mg_send_bytes) { CK(cudaStreamSynchronize(st)); cudaFree(t->mg_send); t->mg_send = NULL; CK(cudaMalloc((void**)&t->mg_send, send_b)); t->mg_send_bytes = send_b; }
+	if(recv_b>t->mg_recv_bytes) { CK(cudaStreamSynchronize(st)); cudaFree(t->mg_recv); t->mg_recv = NULL; CK(cudaMalloc((void**)&t->mg_recv, recv_b)); t->mg_recv_bytes = recv_b; }
+	/* backward: own tails, own subtree roots */
+	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 0, tlo, thi, d_in, d_ux, d_pi, d_L, stream))) return rc;
+	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 3, lo, hi, d_in, d_ux, d_pi, d_L, stream))) return rc;
+	/* the one exchange: this rank's root blocks of every tree -> contiguous, all-gather over NVLink, scatter back into the stashes */
+	CK(cudaMemcpy2DAsync(t->mg_send, sizeof(double)*seg, d_L + o0 + (size_t)lo*ln, sizeof(double)*t->dims.L_stride, sizeof(double)*seg, (size_t)n_trees,
+			cudaMemcpyDeviceToDevice, st));
+	NCK(NC.AllGather(t->mg_send, t->mg_recv, seg*(size_t)n_trees, 8 /* ncclFloat64 */, c->comm, st));
+	for(k=0; k<c->world; k++)
+		{
+		if(k==c->rank) continue;
+		CK(cudaMemcpy2DAsync(d_L + o0 + (size_t)k*per*ln, sizeof(double)*t->dims.L_stride, t->mg_recv + (size_t)k*seg*(size_t)n_trees, sizeof(double)*seg,
+				sizeof(double)*seg, (size_t)n_trees, cudaMemcpyDeviceToDevice, st));
+		}
+	/* the levels above the subtree roots (redundantly), then down the own subtrees */
+	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 4, 0, 0, d_in, d_ux, d_pi, d_L, stream))) return rc;
+	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 5, lo, hi, d_in, d_ux, d_pi, d_L, stream))) return rc;
+	return hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 2, tlo, thi, d_in, d_ux, d_pi, d_L, stream);
 	}

@@ -100,6 +100,21 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_tree
 int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_trees, int phase, int tail_lo, int tail_hi,
                                             const double *d_in, double *d_ux, double *d_pi, double *d_L, void *stream);
 
+/* ---- several GPUs: subtrees shard over the ranks, one all-gather of subtree-root factor blocks per solve,
+ * issued by the library with NCCL on the caller's stream (reference recursion: lqcp_solvers/d_tree_back_ric_rec_libstr.c:524-583).
+ * One process per GPU.  Rank 0 calls hpmpc_b200_comm_unique_id (128 bytes) and hands the id to the other ranks by whatever means the
+ * application has (MPI, a file, torch.distributed, ...); every rank then creates its communicator.  hpmpc_b200_comm_wrap adopts an
+ * ncclComm_t the application already owns.  The tree must have n_shard_nodes divisible by the number of ranks. */
+typedef struct hpmpc_b200_comm hpmpc_b200_comm;
+int  hpmpc_b200_comm_unique_id(void *id, int id_bytes);
+int  hpmpc_b200_comm_create(hpmpc_b200_comm **out, int world, int rank, const void *id, int device);
+int  hpmpc_b200_comm_wrap(hpmpc_b200_comm **out, void *nccl_comm, int world, int rank);
+void hpmpc_b200_comm_destroy(hpmpc_b200_comm *c);
+/* every rank holds all trees' data and calls this with the same arguments; on return it has ux / pi of the nodes of its subtrees
+ * and of the levels above them.  Non-blocking: everything is enqueued on `stream`. */
+int  hpmpc_b200_d_tree_back_ric_rec_sv_batch_mg(hpmpc_b200_tree *t, hpmpc_b200_comm *c, long long n_trees, const double *d_in,
+                                                double *d_ux, double *d_pi, double *d_L, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,3 +288,19 @@ def test_tree_gpu_trf_then_trs_with_new_right_hand_sides(shape):
                 assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b))), (i, f)
     finally:
         tb.close()
+
+
+@pytest.mark.gpu
+def test_tree_multi_gpu_exchange_inside_the_library():
+    """hpmpc_b200_d_tree_back_ric_rec_sv_batch_mg: subtrees sharded over 2 ranks, the NCCL all-gather issued by the C library;
+    every rank's nodes bit-identical to the single-GPU solve (tools/tree_mg_check.py under torchrun).  Needs 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "tree_mg_check.py"), "256"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatching node vectors (max over ranks): 0" in r.stdout
