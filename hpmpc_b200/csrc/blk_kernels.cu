@@ -202,50 +202,50 @@ extern "C" int hb_tail_info(int id, int *ipw, int *smem_warp, int *image_doubles
 	}
 
 template<class C> static int hbk_tail_launch(const hb_tdims *d, const hb_tail_tab *tab, long long n_trees, const double *in, double *ux,
-		double *pi, double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, cudaStream_t st)
+		double *pi, double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, cudaStream_t st, const double *skip)
 	{
 	int smem = warps*(int)sizeof(double)*C::PER_WARP;
 	if(hb_prep(hbk_tail_kernel<C>, smem)) return -1;
 	hbk_tail_kernel<C><<<grid, warps*32, smem, st>>>(*tab, n_trees, d->in_stride, d->ux_stride, d->pi_stride, d->L_stride, in, ux, pi, L,
-			mode, tail_lo, tail_hi);
+			mode, tail_lo, tail_hi, skip);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
 
 extern "C" int hb_launch_tail(int id, const hb_tdims *d, const hb_tail_tab *tab, long long n_trees, const double *in, double *ux, double *pi,
-		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream)
+		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream, const double *skip)
 	{
 	if(tail_hi<=tail_lo || n_trees<=0) return 0;
 	cudaStream_t st = (cudaStream_t)stream;
 	switch(id)
 		{
-		case 0: return hbk_tail_launch<hbk_v0>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st);
-		case 1: return hbk_tail_launch<hbk_v1>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st);
-		case 2: return hbk_tail_launch<hbk_v2>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st);
+		case 0: return hbk_tail_launch<hbk_v0>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st, skip);
+		case 1: return hbk_tail_launch<hbk_v1>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st, skip);
+		case 2: return hbk_tail_launch<hbk_v2>(d, tab, n_trees, in, ux, pi, L, mode, tail_lo, tail_hi, grid, warps, st, skip);
 		}
 	return -2;
 	}
 
 template<class C> static int hbk_top_launch(const hb_tdims *d, long long n_trees, const double *in, double *ux, double *pi, double *L,
-		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, cudaStream_t st)
+		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, cudaStream_t st, const double *skip)
 	{
 	int smem = warps*(int)sizeof(double)*C::PER_WARP;
 	if(hb_prep(hbk_top_kernel<C>, smem)) return -1;
-	hbk_top_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first);
+	hbk_top_kernel<C><<<grid, warps*32, smem, st>>>(*d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, skip);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}
 
 extern "C" int hb_launch_top(int id, const hb_tdims *d, long long n_trees, const double *in, double *ux, double *pi, double *L,
-		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream)
+		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream, const double *skip)
 	{
 	if(seg_hi<=seg_lo || n_trees<=0) return 0;
 	cudaStream_t st = (cudaStream_t)stream;
 	switch(id)
 		{
-		case 0: return hbk_top_launch<hbk_v0>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st);
-		case 1: return hbk_top_launch<hbk_v1>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st);
-		case 2: return hbk_top_launch<hbk_v2>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st);
+		case 0: return hbk_top_launch<hbk_v0>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st, skip);
+		case 1: return hbk_top_launch<hbk_v1>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st, skip);
+		case 2: return hbk_top_launch<hbk_v2>(d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, first, grid, warps, st, skip);
 		}
 	return -2;
 	}

@@ -147,17 +147,18 @@ int hb_launch_res(const hb_dims *dims, long long n_inst, const double *in, const
 int hb_launch_sv_traffic(int id, const hb_dims *dims, long long n_inst, const double *in, double *ux, double *pi,
 		double *stash, int grid, int warps, void *stream);
 int hb_launch_tree(const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
-		int mode /* 0 backward, 1 forward, 2 backward then forward */, int seg_lo, int seg_hi, int grid, int warps, void *stream);
+		int mode /* 0 backward, 1 forward, 2 backward then forward */, int seg_lo, int seg_hi, int grid, int warps, void *stream, const double *skip);
 int hb_tail_variant(int nx, int nu);                     /* -1 when no size-specialised tail kernel exists */
 int hb_tail_info(int id, int *ipw, int *smem_warp, int *image_doubles);
 int hb_launch_tail(int id, const hb_tdims *dims, const hb_tail_tab *tab, long long n_trees, const double *in, double *ux, double *pi,
-		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream);
+		double *L, int mode, int tail_lo, int tail_hi, int grid, int warps, void *stream, const double *skip);
 int hb_launch_top(int id, const hb_tdims *dims, long long n_trees, const double *in, double *ux, double *pi, double *L,
-		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream);
+		int mode, int seg_lo, int seg_hi, int first, int grid, int warps, void *stream, const double *skip);
 long long hb_tipm_work_doubles(const hb_dims *dims);
 int hb_launch_tipm_step(const hb_dims *dims, const hb_tipm_maps *maps, int part, long long n_trees, const double *in, double *in_mod, int k_max,
 		double mu0, double mu_tol, double alpha_min, int warm_start, double *ux, double *pi, double *dux, double *dpi, double *lam,
 		double *t, double *info, double *work, long long work_stride, double *state, int *counters, void *stream);
+int hb_launch_tipm_gate(const int *counters, double *gate, int init, void *stream);
 int hb_launch_tipm_res(const hb_dims *dims, long long n_trees, const double *in, const double *ux, const double *pi,
 		double *dux, double *dpi, double *work, long long work_stride, double *state, int sms, void *stream);
 int hb_launch_tree_trf_trs(const hb_dims *dims, long long n_trees, const double *in, double *L, double *ux, double *pi,

@@ -30,6 +30,9 @@
 #include "layout.h"
 #include "ric_fast.cuh"          /* PTX helpers (mbarrier, bulk copies), stage kinds */
 
+/* state value of a finished tree in the tree IPM driver's per-tree record (tree_ipm_kernels.cu: TS_DONE, record[3]) */
+#define HBK_TS_DONE 5
+
 template<int NX_, int NU_, int G_, int R_>
 struct hbk_cfg
 	{
@@ -1030,7 +1033,7 @@ __global__ void __launch_bounds__(256, 1) hbk_traffic_kernel(hb_dims d, long lon
 template<class C>
 __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long long n_trees, long long in_stride, long long ux_stride,
 		long long pi_stride, long long L_stride, const double *__restrict__ in, double *__restrict__ ux_all, double *__restrict__ pi_all,
-		double *__restrict__ L_all, int mode, int tail_lo, int tail_hi)
+		double *__restrict__ L_all, int mode, int tail_lo, int tail_hi, const double *__restrict__ skip)
 	{
 	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
 	extern __shared__ __align__(16) double hbf_smem[];
@@ -1052,6 +1055,7 @@ __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long 
 		}
 	__syncwarp();
 	uint32_t phase = 0;
+	if(skip!=nullptr && skip[n_trees*8]==0.0) return;          /* tree IPM driver: every tree has finished */
 	const int len = tab.len, ntl = tail_hi - tail_lo;
 	const long long n_items = n_trees*ntl, n_groups = (n_items + IPW - 1)/IPW;
 	constexpr uint32_t bytes_Q = 8u*(uint32_t)C::RSQ, bytes_Qlast = 8u*(uint32_t)C::even(HB_TRI(NX)+NX), bytes_B = 8u*(uint32_t)BAB;
@@ -1062,6 +1066,8 @@ __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long 
 		const bool active = item<n_items;
 		if(!active) item = n_items-1;
 		const long long t = item/ntl;
+		/* tree IPM driver: trees that have finished are skipped (their state record says so); a group is skipped as a whole */
+		if(skip!=nullptr && __all_sync(HBF_FULL, (int)skip[t*8+3]==HBK_TS_DONE)) continue;
 		const int j = tail_lo + (int)(item - t*ntl);
 		double *ux = ux_all + t*ux_stride, *pi = pi_all + t*pi_stride, *Lt = L_all + t*L_stride;
 		const int mg = lane<IPW ? lane : 0;
@@ -1166,7 +1172,8 @@ __global__ void __launch_bounds__(256, 1) hbk_tail_kernel(hb_tail_tab tab, long 
 /* ------------------------------------------------------------------------------------------------ */
 template<class C>
 __global__ void __launch_bounds__(256, 1) hbk_top_kernel(hb_tdims d, long long n_trees, const double *__restrict__ in,
-		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ L_all, int mode, int seg_lo, int seg_hi, int first)
+		double *__restrict__ ux_all, double *__restrict__ pi_all, double *__restrict__ L_all, int mode, int seg_lo, int seg_hi, int first,
+		const double *__restrict__ skip)
 	{
 	constexpr int G = C::G, IPW = C::IPW, NX = C::NX, NU = C::NU, NUX = C::NUX, SB = C::SB, IOB = C::IOB, BAB = C::BAB, LU = C::LU;
 	constexpr int GEN = HB_EVEN(HB_TRI(NUX)+2*NUX), GEN0 = HB_EVEN(HB_TRI(NU)+2*NU), XC = C::xOff(NX);
@@ -1187,6 +1194,7 @@ __global__ void __launch_bounds__(256, 1) hbk_top_kernel(hb_tdims d, long long n
 		}
 	__syncwarp();
 	uint32_t phase = 0;
+	if(skip!=nullptr && skip[n_trees*8]==0.0) return;
 	const int nseg = seg_hi - seg_lo;
 	const long long n_items = n_trees*nseg, n_groups = (n_items + IPW - 1)/IPW;
 	const uint32_t bytes_B = 8u*(uint32_t)(first ? C::even((NU+1)*NX) : BAB);
@@ -1200,6 +1208,7 @@ __global__ void __launch_bounds__(256, 1) hbk_top_kernel(hb_tdims d, long long n
 		const bool active = item<n_items;
 		if(!active) item = n_items-1;
 		const long long t = item/nseg;
+		if(skip!=nullptr && __all_sync(HBF_FULL, (int)skip[t*8+3]==HBK_TS_DONE)) continue;
 		const hb_tnode nd = d.tn[d.seg_nodes[d.seg_start[seg_lo + (int)(item - t*nseg)]]];
 		double *ux = ux_all + t*d.ux_stride, *pi = pi_all + t*d.pi_stride, *Lt = L_all + t*d.L_stride;
 		const int mg = lane<IPW ? lane : 0;

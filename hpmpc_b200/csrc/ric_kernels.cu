@@ -87,7 +87,7 @@ __global__ void hb_ric_trs_kernel(hb_dims d, long long n_inst, const double *__r
 /* scenario tree                                                                                     */
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void hb_tree_kernel(hb_tdims d, long long n_trees, const double *__restrict__ in, double *__restrict__ ux_all,
-		double *__restrict__ pi_all, double *__restrict__ L_all, int mode, int seg_lo, int seg_hi)
+		double *__restrict__ pi_all, double *__restrict__ L_all, int mode, int seg_lo, int seg_hi, const double *__restrict__ skip)
 	{
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
@@ -98,11 +98,13 @@ __global__ void hb_tree_kernel(hb_tdims d, long long n_trees, const double *__re
 	c.lane = lane; c.ldW = d.nxM | 1;
 	c.bufA = smem_warp; c.bufB = c.bufA + lsz; c.sW = c.bufB + lsz; c.sV = c.sW + HB_EVEN(d.nzM*c.ldW);
 	}
+	if(skip!=nullptr && skip[n_trees*8]==0.0) return;          /* tree IPM driver: every tree has finished */
 	const int nseg = seg_hi - seg_lo;
 	const long long n_items = n_trees*nseg;
 	for(long long item=gw; item<n_items; item+=tw)
 		{
 		const long long t = item/nseg;
+		if(skip!=nullptr && (int)skip[t*8+3]==5 /* TS_DONE: a finished tree of the IPM driver */) continue;
 		const int seg = seg_lo + (int)(item - t*nseg);
 		const double *in_tree = in + t*d.in_stride;
 		double *Lt = L_all + t*d.L_stride, *ux = ux_all + t*d.ux_stride, *pi = pi_all + t*d.pi_stride;
@@ -192,13 +194,13 @@ extern "C" int hb_launch_ric_trs(const hb_dims *d, long long n_inst, const doubl
 	}
 
 extern "C" int hb_launch_tree(const hb_tdims *d, long long n_trees, const double *in, double *ux, double *pi, double *L,
-		int mode, int seg_lo, int seg_hi, int grid, int warps, void *stream)
+		int mode, int seg_lo, int seg_hi, int grid, int warps, void *stream, const double *skip)
 	{
 	if(d->nzM>64) { fprintf(stderr, "hpmpc_b200: tree: nu+nx+1 > 64 not supported\n"); return -2; }
 	if(seg_hi<=seg_lo || n_trees<=0) return 0;
 	int smem = warps*(int)sizeof(double)*hb_smem_doubles_per_warp(d->nzM, d->nxM);
 	if(hb_prep(hb_tree_kernel, smem)) return -1;
-	hb_tree_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi);
+	hb_tree_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_trees, in, ux, pi, L, mode, seg_lo, seg_hi, skip);
 	HB_CK(cudaGetLastError());
 	return 0;
 	}

@@ -40,6 +40,7 @@ struct hpmpc_b200_tree
 	int *f_nact, *h_nact;    /* device / pinned host: trees still iterating */
 	long long n_launches;    /* kernels launched through this handle so far (bench.py reports it) */
 	double *trs_ws; int trs_slots;          /* right-hand sides and Pb of the solve-only path, per warp slot */
+	const double *skip_state;               /* tree IPM driver: per-tree state records; the Riccati kernels skip finished trees */
 	double *mg_send, *mg_recv; size_t mg_send_bytes, mg_recv_bytes;   /* staging of the multi-GPU exchange (tree_mg below) */
 	};
 
@@ -428,12 +429,12 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 				{
 				fast_shape(t, n_trees*(b-a), &grid, &warps);
 				t->n_launches++;
-				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, lv==0, grid, warps, stream))) return rc;
+				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, lv==0, grid, warps, stream, t->skip_state))) return rc;
 				continue;
 				}
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
 			t->n_launches++;
-			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, grid, warps, stream))) return rc;
+			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 0, a, b, grid, warps, stream, t->skip_state))) return rc;
 			}
 		for(lv=0; lv<=deep; lv++)
 			{
@@ -445,12 +446,12 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 				{
 				fast_shape(t, n_trees*(b-a), &grid, &warps);
 				t->n_launches++;
-				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, lv==0, grid, warps, stream))) return rc;
+				if((rc = hb_launch_top(t->tail_fast_id, &t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, lv==0, grid, warps, stream, t->skip_state))) return rc;
 				continue;
 				}
 			launch_shape(t, n_trees*(b-a), &grid, &warps);
 			t->n_launches++;
-			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, grid, warps, stream))) return rc;
+			if((rc = hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, 1, a, b, grid, warps, stream, t->skip_state))) return rc;
 			}
 		return 0;
 		}
@@ -458,11 +459,11 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_phase(hpmpc_b200_tree *t, long long n_tree
 		{
 		fast_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
 		t->n_launches++;
-		return hb_launch_tail(t->tail_fast_id, &t->dims, &t->tab, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, tail_lo, tail_hi, grid, warps, stream);
+		return hb_launch_tail(t->tail_fast_id, &t->dims, &t->tab, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, tail_lo, tail_hi, grid, warps, stream, t->skip_state);
 		}
 	launch_shape(t, n_trees*(tail_hi-tail_lo), &grid, &warps);
 	t->n_launches++;
-	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, t->n_top+tail_lo, t->n_top+tail_hi, grid, warps, stream);
+	return hb_launch_tree(&t->dims, n_trees, d_in, d_ux, d_pi, d_L, phase==0 ? 0 : 1, t->n_top+tail_lo, t->n_top+tail_hi, grid, warps, stream, t->skip_state);
 	}
 
 int hpmpc_b200_d_tree_back_ric_rec_sv_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in,
@@ -492,7 +493,7 @@ static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d
 		CK(cudaMalloc((void**)&t->f_dpi, sizeof(double)*(size_t)n_trees*t->dims.pi_stride));
 		CK(cudaMalloc((void**)&t->f_L, sizeof(double)*(size_t)n_trees*t->dims.L_stride));
 		CK(cudaMalloc((void**)&t->f_ws, sizeof(double)*(size_t)n_trees*t->f_ws_stride));
-		CK(cudaMalloc((void**)&t->f_state, sizeof(double)*(size_t)n_trees*8));
+		CK(cudaMalloc((void**)&t->f_state, sizeof(double)*(size_t)(n_trees+1)*8));       /* + the gate record */
 		/* stride padding of the step vectors is never written by the solver kernels; keep it at zero so that the element-wise
 		 * updates over whole strides leave the padding of ux / pi at zero too */
 		CK(cudaMemsetAsync(t->f_dux, 0, sizeof(double)*(size_t)n_trees*t->dims.ux_stride, st));
@@ -502,6 +503,12 @@ static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d
 		}
 	CK(cudaMemcpyAsync(t->f_in_mod, d_in, sizeof(double)*(size_t)n_trees*t->dims.in_stride, cudaMemcpyDeviceToDevice, st));
 	CK(cudaMemsetAsync(t->f_state, 0, sizeof(double)*(size_t)n_trees*8, st));
+	if((rc = hb_launch_tipm_gate(t->f_nact, t->f_state + (size_t)n_trees*8, (int)(n_trees>2000000000LL ? 2000000000LL : n_trees), stream))) return rc;
+	/* A fixed launch schedule, nothing read back: 2 k_max + 2 rounds of [step, residuals, step, tree Riccati]; every kernel looks at
+	 * the per-tree state record and passes over trees that are not in a state it serves -- finished trees included, which the
+	 * Riccati kernels skip group-wise -- so rounds behind the last active tree cost a few microseconds each.  HPMPC_B200_TREE_IPM_SYNC=1
+	 * restores the adaptive loop that reads the number of unfinished trees after every step (blocking, stops at the last round). */
+	const int adaptive = getenv("HPMPC_B200_TREE_IPM_SYNC")!=NULL;
 	for(round=0; round<2*k_max+2; round++)
 		{
 		int part;
@@ -511,16 +518,26 @@ static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d
 			t->n_launches++;
 			if((rc = hb_launch_tipm_step(&t->ipm_dims, &t->maps, part, n_trees, d_in, t->f_in_mod, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi,
 					t->f_dux, t->f_dpi, d_lam, d_t, d_info, t->f_ws, t->f_ws_stride, t->f_state, t->f_nact, stream))) return rc;
-			CK(cudaMemcpyAsync(t->h_nact, t->f_nact, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-			if(part==1 || t->h_nact[1]==0) break;
-			/* some trees want their residuals (phase switch or end of a phase-2 iteration): node-parallel, then part 1 */
+			if(adaptive)
+				{
+				CK(cudaMemcpyAsync(t->h_nact, t->f_nact, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				if(part==1 || t->h_nact[1]==0) break;
+				}
+			else if(part==1) break;
+			/* trees that want their residuals (phase switch or end of a phase-2 iteration): node-parallel, then part 1 */
 			t->n_launches++;
 			if((rc = hb_launch_tipm_res(&t->ipm_dims, n_trees, d_in, d_ux, d_pi, t->f_dux, t->f_dpi, t->f_ws, t->f_ws_stride, t->f_state, t->sms, stream))) return rc;
 			}
-		if(t->h_nact[0]==0) return 0;
-		if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_batch(t, n_trees, t->f_in_mod, t->f_dux, t->f_dpi, t->f_L, stream))) return rc;
+		if(adaptive && t->h_nact[0]==0) return 0;
+		/* the gate for everything that follows: the number of trees the last step left unfinished */
+		if((rc = hb_launch_tipm_gate(t->f_nact, t->f_state + (size_t)n_trees*8, 0, stream))) return rc;
+		t->skip_state = t->f_state;
+		rc = hpmpc_b200_d_tree_back_ric_rec_sv_batch(t, n_trees, t->f_in_mod, t->f_dux, t->f_dpi, t->f_L, stream);
+		t->skip_state = NULL;
+		if(rc) return rc;
 		}
+	if(!adaptive) return 0;
 	fprintf(stderr, "hpmpc_b200: tree IPM: state machine did not terminate\n");
 	return -5;
 	}

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(128) hb_tipm_res_kernel(hb_dims d, long long n
 	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
 	hb_ctx c = hb_make_ctx(d, hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM), lane);
 	const long long Nn = d.N+1, items = n_trees*Nn, tw = (long long)gridDim.x*nw;
+	if(state_all[n_trees*8]==0.0) return;            /* gate: no tree of the batch is unfinished (written by hb_tipm_gate_kernel) */
 	for(long long it=(long long)blockIdx.x*nw + warp; it<items; it+=tw)
 		{
 		const long long tree = it/Nn; const int n = (int)(it - tree*Nn);
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(TIPM_THREADS, 4) hb_tipm_step_kernel(hb_dims d
 	__shared__ double red[8];
 	const int tid = threadIdx.x, nthr = blockDim.x;
 	const long long tree = blockIdx.x;
+	if(state_all[n_trees*8]==0.0) return;            /* gate: every tree has finished */
 	double *state = state_all + tree*8;
 	int st = (int)state[3];
 	if(st==TS_DONE) return;
@@ -327,6 +329,18 @@ __global__ void __launch_bounds__(TIPM_THREADS, 4) hb_tipm_step_kernel(hb_dims d
 extern "C" long long hb_tipm_work_doubles(const hb_dims *d)
 	{
 	return 2*d->ux_stride + 2*d->pi_stride + (long long)CV_COUNT*HB_EVEN(d->nbtot);
+	}
+
+/* the gate record behind the last tree's state record: the number of unfinished trees (init > 0: that value; else counters[0]) */
+__global__ void hb_tipm_gate_kernel(const int *counters, double *gate, int init)
+	{
+	*gate = init>0 ? (double)init : (double)counters[0];
+	}
+extern "C" int hb_launch_tipm_gate(const int *counters, double *gate, int init, void *stream)
+	{
+	hb_tipm_gate_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counters, gate, init);
+	HB_CK(cudaGetLastError());
+	return 0;
 	}
 
 extern "C" int hb_launch_tipm_step(const hb_dims *d, const hb_tipm_maps *m, int part, long long n_trees, const double *in, double *in_mod, int k_max,
