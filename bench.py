@@ -371,6 +371,85 @@ def run_ours(args):
         spec.h.close()
         return out
 
+    def bench_shared(steps, warmup):
+        """SEPARATELY LABELLED MODE, not the headline: shared dynamics -- one set of config-2 matrices for the whole batch, per-instance
+        vectors b, q, r (fleets of identical systems / sweeps over initial states; how the reference's own test programs call the
+        solver).  Factor once + batched solve with the stored factor whose matrices sit in shared memory."""
+        import ctypes as C
+        spec = BatchSpec("cfg2", device=local)
+        h, base = spec.h, spec.problem(0)
+        n = args.n_inst_shared or 262144
+        L.hpmpc_b200_shared_factor_doubles.restype = C.c_longlong; L.hpmpc_b200_shared_factor_doubles.argtypes = [C.c_void_p]
+        L.hpmpc_b200_d_back_ric_rec_trf_shared.argtypes = [C.c_void_p] * 4
+        L.hpmpc_b200_d_back_ric_rec_trs_shared_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 6
+        L.hpmpc_b200_d_back_ric_rec_sv_shared_batch_host.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
+        n_ux, n_pi = sum(base.nx) + sum(base.nu), sum(base.nx[1:])
+        vs = h.sz.ux_stride + h.sz.pi_stride
+        blk = h.pack(base)
+        v0 = np.zeros(vs)
+        v0[:n_ux] = np.concatenate([np.concatenate([base.r[k], base.q[k]]) for k in range(base.N + 1)])
+        v0[h.sz.ux_stride:h.sz.ux_stride + n_pi] = np.concatenate(base.b)
+        g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+        d_vec = torch.from_numpy(v0).to(dev)[None, :] * (1.0 + 0.2 * (torch.rand((n, vs), generator=g, device=dev, dtype=torch.float64) - 0.5))
+        d_blk = torch.from_numpy(blk).to(dev)
+        d_L = torch.zeros(L.hpmpc_b200_shared_factor_doubles(h.h) + 8, dtype=torch.float64, device=dev)
+        ux = torch.zeros((n, h.sz.ux_stride), dtype=torch.float64, device=dev); pi = torch.zeros((n, h.sz.pi_stride), dtype=torch.float64, device=dev)
+
+        def launch():
+            assert L.hpmpc_b200_d_back_ric_rec_trf_shared(h.h, d_blk.data_ptr(), d_L.data_ptr(), st) == 0
+            assert L.hpmpc_b200_d_back_ric_rec_trs_shared_batch(h.h, n, d_blk.data_ptr(), d_L.data_ptr(), d_vec.data_ptr(), ux.data_ptr(), pi.data_ptr(), st) == 0
+        tot_ms, per = time_steps(launch, steps, warmup, stream, barrier)
+        tot_ms = reduce_max_time(tot_ms, dev)
+        bytes_inst = 8.0 * (n_ux + n_pi) * 2                     # vectors in, solution out
+        out = {"metric": "lqcp_riccati_solves_per_s_shared_dynamics", "value": world * n * steps / (tot_ms * 1e-3), "unit": "solves/s",
+               "ms_per_step": tot_ms / steps, "instances_per_gpu": n, "gpu_launches": 2 * steps,
+               "workload": "SHARED DYNAMICS (not the headline workload): config-2 matrices stored once per batch, per-instance b, q, r; factor once + batched solve with the stored factor",
+               "roofline": {"bound": "hbm", "achieved": bytes_inst * n / (float(np.mean(per)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": bytes_inst * n / (float(np.mean(per)) * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                            "kernel": "hb_ric_trs_shared_kernel (+ hb_ric_trf_kernel once)", "algorithmic_bytes_per_solve": bytes_inst}}
+        pin = lambda m: torch.empty((n, m), dtype=torch.float64, pin_memory=True)
+        h_vec, h_ux, h_pi = pin(vs), pin(h.sz.ux_stride), pin(h.sz.pi_stride)
+        h_vec.copy_(d_vec)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            assert L.hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(h.h, n, blk.ctypes.data, h_vec.data_ptr(), h_ux.data_ptr(), h_pi.data_ptr()) == 0
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step()
+        t1 = time.perf_counter()
+        barrier()
+        te = reduce_max_time(t1 - t0, dev)
+        assert float((h_ux[:64, :n_ux] - ux[:64, :n_ux].cpu()).abs().max()) == 0.0
+        out["e2e"] = {"value": world * n * 3 / te, "unit": "solves/s", "h2d_bytes_per_step": int(n * vs * 8 + blk.nbytes),
+                      "d2h_bytes_per_step": int(n * (h.sz.ux_stride + h.sz.pi_stride) * 8), "steps": 3}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            try:
+                from oracle import api as oracle
+                cores = os.cpu_count()
+                ns = 4096
+                rs = oracle.RefSample(spec, 1, want=("pm",))
+                vec_s = np.ascontiguousarray(np.concatenate([h_vec[:ns, :n_ux].numpy(), h_vec[:ns, h.sz.ux_stride:h.sz.ux_stride + n_pi].numpy()], axis=1))
+                fn = oracle.lib().ref_harness_ric_trs_shared
+                fn.restype = C.c_double
+                fn.argtypes = [C.c_char_p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long]
+                off = np.asarray(rs.off_pm, dtype=np.int64)
+                from hpmpc_b200.capi import int_array
+                run = lambda n_pass: fn(oracle.REF_AVX2.encode(), cores, ns, n_pass, base.N, int_array(base.nx), int_array(base.nu), rs.pm.ctypes.data,
+                                        off.ctypes.data, vec_s.ctypes.data, n_ux + n_pi, n_ux, None, n_ux)
+                t1_ = run(1)
+                n_pass = max(1, int(round(2.0 / max(t1_, 1e-6))))
+                sec = run(n_pass)
+                out["cpu_baseline"] = {"value": ns * n_pass / sec, "unit": "solves/s", "cores": cores, "kind": "reference",
+                                       "sample": f"{ns} instances x {n_pass} passes, reference X64_AVX2 build: d_back_ric_rec_trf_tv_res once per thread and pass, d_back_ric_rec_trs_tv_res per instance"}
+                out["e2e_vs_cpu_baseline"] = out["e2e"]["value"] / out["cpu_baseline"]["value"]
+            except Exception as e:      # noqa: BLE001
+                out["cpu_baseline"] = {"value": None, "sample": f"failed: {e!r}"}
+        h.close()
+        return out
+
     def bench_tree(steps, warmup):
         """BASELINE config 5: scenario trees md=4, Nr=3, Nh=20, nx=12, nu=5 (1173 nodes), subtrees sharded over the ranks (strong scaling)."""
         from hpmpc_b200 import tree as T
@@ -580,6 +659,13 @@ def run_ours(args):
             args.n_trees, args.no_cpu = saved
         except Exception as e:
             out["extra"]["tree_error"] = repr(e)
+        torch.cuda.empty_cache()
+        try:
+            sh = bench_shared(3, 2)
+            if rank == 0:
+                out["extra"]["shared_dynamics"] = sh
+        except Exception as e:      # noqa: BLE001
+            out["extra"]["shared_dynamics_error"] = repr(e)
         if world == 1:
             # the IPM's last KKT system solved again for a new right-hand side (cfg 3 shapes, 4096 instances)
             torch.cuda.empty_cache()
@@ -647,6 +733,7 @@ def main():
     ap.add_argument("--n-trees", type=int, default=0)
     ap.add_argument("--n-inst", type=int, default=0)
     ap.add_argument("--n-inst-ipm", type=int, default=0)
+    ap.add_argument("--n-inst-shared", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")

@@ -116,6 +116,9 @@ int hb_launch_ric_sv(const hb_dims *dims, long long n_inst, const double *in, do
 int hb_launch_ric_trf(const hb_dims *dims, long long n_inst, const double *in, double *L, int grid, int warps, void *stream, const double *Qx);
 int hb_launch_ric_trs(const hb_dims *dims, long long n_inst, const double *in, const double *L, double *ux, double *pi,
 		double *work, int n_slots, int grid, int warps, void *stream, const double *qx);
+long long hb_trs_shared_smem_bytes(const hb_dims *dims, const hb_stage *st_host, int warps, int *resident);
+int hb_launch_ric_trs_shared(const hb_dims *dims, long long n_inst, const double *in_shared, const double *L_shared, const double *vec,
+		double *ux, double *pi, double *work, int grid, int warps, int smem, int resident, void *stream);
 int hb_launch_ipm(const hb_dims *dims, long long n_inst, const double *in, int k_max, double mu0, double mu_tol,
 		double alpha_min, int warm_start, double *ux, double *pi, double *lam, double *t, double *info,
 		double *work, long long work_stride, int n_slots, int grid, int warps, int *counter, int fast_id, void *stream);

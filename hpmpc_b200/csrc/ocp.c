@@ -843,6 +843,91 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 	return 0;
 	}
 
+/* ------------------------------------------------------------------------------------------------ */
+/* shared dynamics: one set of matrices for the whole batch, per-instance vectors (ric_kernels.cu: hb_ric_trs_shared_kernel)     */
+/* ------------------------------------------------------------------------------------------------ */
+long long hpmpc_b200_shared_vec_stride(const hpmpc_b200_ocp *p) { return p->dims.ux_stride + p->dims.pi_stride; }
+long long hpmpc_b200_shared_factor_doubles(const hpmpc_b200_ocp *p) { return p->dims.L_stride; }
+
+/* factorise the ONE shared block (d_in_shared: a packed instance block whose vectors are ignored) into d_L_shared */
+int hpmpc_b200_d_back_ric_rec_trf_shared(hpmpc_b200_ocp *p, const double *d_in_shared, double *d_L_shared, void *stream)
+	{
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(p->device));
+	if(call_begin(p, stream)) return -1;
+	return call_end(p, stream, hb_launch_ric_trf(&p->dims, 1, d_in_shared, d_L_shared, 1, 1, stream, NULL));
+	}
+
+static int trs_shared_shape(hpmpc_b200_ocp *p, long long n_inst, int *grid, int *warps, int *smem, int *resident)
+	{
+	*warps = 8;
+	*smem = (int)hb_trs_shared_smem_bytes(&p->dims, p->st, *warps, resident);
+	if(*smem>227*1024) { *warps = 4; *smem = (int)hb_trs_shared_smem_bytes(&p->dims, p->st, *warps, resident); }
+	if(*smem>227*1024) { fprintf(stderr, "hpmpc_b200: shared-dynamics solve: stage too large for shared memory\n"); return -2; }
+	int per_sm = (227*1024)/(*smem+1024); if(per_sm<1) per_sm = 1; if(per_sm>2) per_sm = 2;
+	long long need = (n_inst + *warps - 1)/(*warps);
+	*grid = (int)(need<(long long)p->sms*per_sm ? (need<1 ? 1 : need) : (long long)p->sms*per_sm);
+	return 0;
+	}
+
+/* every instance: solve with the shared factor for its own vectors.  d_vec: n_inst x hpmpc_b200_shared_vec_stride() doubles,
+ * per instance [r q] of every stage in the ux layout (ux_stride), then b of every stage in the pi layout (pi_stride). */
+int hpmpc_b200_d_back_ric_rec_trs_shared_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in_shared, const double *d_L_shared,
+		const double *d_vec, double *d_ux, double *d_pi, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(p->device));
+	int grid, warps, smem, resident;
+	if(trs_shared_shape(p, n_inst, &grid, &warps, &smem, &resident)) return -2;
+	if(call_begin(p, stream)) return -1;
+	if(ensure_scratch(p, sizeof(double)*(size_t)grid*warps*p->dims.pi_stride)) return -1;
+	return call_end(p, stream, hb_launch_ric_trs_shared(&p->dims, n_inst, d_in_shared, d_L_shared, d_vec, d_ux, d_pi, p->scratch, grid, warps, smem, resident, stream));
+	}
+
+/* the same from host buffers: the shared block goes over once and is factorised once, then the vectors stream through in chunks
+ * (H2D of chunk k+1 overlaps the solve / D2H of chunk k) */
+int hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in_shared, const double *h_vec,
+		double *h_ux, double *h_pi)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(p->device));
+	const long long vs = p->dims.ux_stride + p->dims.pi_stride;
+	long long cs = (256LL<<20)/(long long)(sizeof(double)*vs);
+	if(cs<1) cs = 1;
+	if(cs>n_inst) cs = n_inst;
+	int grid, warps, smem, resident, k = 0;
+	if(trs_shared_shape(p, cs, &grid, &warps, &smem, &resident)) return -2;
+	const size_t in_b = sizeof(double)*(size_t)cs*vs, out_b = sizeof(double)*(size_t)cs*(p->dims.ux_stride + p->dims.pi_stride);
+	if(ensure_staging(p, in_b, out_b)) return -1;
+	if(call_begin(p, p->s_copy[0]) || call_begin(p, p->s_copy[1])) return -1;
+	/* scratch: [shared block | shared factor | Pb of stream 0 | Pb of stream 1] */
+	const size_t pb = (size_t)grid*warps*p->dims.pi_stride;
+	if(ensure_scratch(p, sizeof(double)*((size_t)p->dims.in_stride + p->dims.L_stride + 2*pb + 64))) return -1;
+	double *d_sh = p->scratch, *d_L = d_sh + p->dims.in_stride, *d_pb = d_L + HB_EVEN(p->dims.L_stride);
+	CK(cudaMemcpyAsync(d_sh, h_in_shared, sizeof(double)*p->dims.in_stride, cudaMemcpyHostToDevice, p->s_copy[0]));
+	if(hb_launch_ric_trf(&p->dims, 1, d_sh, d_L, 1, 1, p->s_copy[0], NULL)) return -1;
+	CK(cudaEventRecord(p->ev[0], p->s_copy[0]));
+	CK(cudaStreamWaitEvent(p->s_copy[1], p->ev[0], 0));
+	long long done;
+	for(done=0; done<n_inst; done+=cs, k^=1)
+		{
+		long long m = n_inst-done<cs ? n_inst-done : cs;
+		cudaStream_t st = p->s_copy[k];
+		double *d_vec = p->stage_in[k], *d_ux = p->stage_out[k], *d_pi = d_ux + (size_t)cs*p->dims.ux_stride;
+		int g2 = grid; { long long need = (m + warps - 1)/warps; if(need<g2) g2 = (int)(need<1 ? 1 : need); }
+		CK(cudaMemcpyAsync(d_vec, h_vec + (size_t)done*vs, sizeof(double)*(size_t)m*vs, cudaMemcpyHostToDevice, st));
+		if(hb_launch_ric_trs_shared(&p->dims, m, d_sh, d_L, d_vec, d_ux, d_pi, d_pb + (size_t)k*pb, g2, warps, smem, resident, st)) return -1;
+		CK(cudaMemcpyAsync(h_ux + (size_t)done*p->dims.ux_stride, d_ux, sizeof(double)*(size_t)m*p->dims.ux_stride, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_pi + (size_t)done*p->dims.pi_stride, d_pi, sizeof(double)*(size_t)m*p->dims.pi_stride, cudaMemcpyDeviceToHost, st));
+		}
+	CK(cudaStreamSynchronize(p->s_copy[0]));
+	CK(cudaStreamSynchronize(p->s_copy[1]));
+	p->busy_valid = 0;
+	return 0;
+	}
+
 double hpmpc_b200_fp64_peak_tflops(int device)
 	{
 	if(cudaSetDevice(device)!=cudaSuccess) return -1.0;

@@ -84,6 +84,118 @@ __global__ void hb_ric_trs_kernel(hb_dims d, long long n_inst, const double *__r
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
+/* SHARED DYNAMICS: every instance of the batch has the same matrices (A, B, Q, S, R at every stage) and its own vectors (b, q, r) --
+ * a fleet of identical systems, a parameter sweep over initial states / references; also how the reference's own test programs
+ * call the solver (one pBAbt pointer aliased over all stages, test_problems/test_d_ip_hard.c).  The factorisation is then the
+ * same for all of them: it is done once (hb_ric_trf_kernel on the one shared block), and this kernel is the batched
+ * d_back_ric_rec_trs_tv_res (lqcp_solvers/d_back_ric_rec.c:564) on that one factor.  The factor and [B A]' of the WHOLE horizon
+ * are loaded into the CTA's shared memory once; after that an instance costs its vectors in and its solution out, nothing else
+ * crosses HBM.  vec: per instance [r q] of every stage (ux layout, ux_stride doubles) followed by b of every stage (pi layout).
+ * ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) hb_ric_trs_shared_kernel(hb_dims d, long long n_inst, const double *__restrict__ in_shared,
+		const double *__restrict__ L_shared, const double *__restrict__ vec, double *__restrict__ ux_all, double *__restrict__ pi_all,
+		double *__restrict__ work, int resident)
+	{
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	const int ldW = d.nxM | 1, N = d.N;
+	/* shared memory: [per-warp scratch sV 192 | per-warp stage buffers when not resident] ... then the resident horizon */
+	hb_ctx c;
+	c.lane = lane; c.ldW = ldW;
+	double *base = hb_smem;
+	c.sV = base + (size_t)warp*192;
+	double *Lsm = base + (size_t)nw*192;
+	double *Bsm = Lsm + d.L_stride;
+	int *offB = reinterpret_cast<int*>(Bsm + 0);            /* set below: table of the stages' offsets inside Bsm */
+	if(resident)
+		{
+		/* table first (N+1 ints, padded to doubles), then the matrices */
+		double *tab_end = Bsm + HB_EVEN((N+2+1)/2);
+		offB = reinterpret_cast<int*>(Bsm);
+		Bsm = tab_end;
+		if(threadIdx.x==0)
+			{
+			int o = 0;
+			for(int n=0; n<N; n++) { offB[n] = o; o += HB_EVEN((d.st[n].nu + d.st[n].nx + 1)*ldW); }
+			offB[N] = o;
+			}
+		for(long long e=threadIdx.x; e<d.L_stride; e+=blockDim.x) Lsm[e] = L_shared[e];
+		__syncthreads();
+		for(int n=0; n<N; n++)
+			{
+			const hb_stage s = d.st[n];
+			const int nux = s.nu+s.nx, nx1 = s.nx1;
+			const double *gb = in_shared + s.off_BAbt;
+			double *dst = Bsm + offB[n];
+			for(int e=threadIdx.x; e<(nux+1)*nx1; e+=blockDim.x) { int i = e/nx1, j = e - i*nx1; dst[i*ldW+j] = gb[e]; }
+			}
+		__syncthreads();
+		}
+	else
+		{
+		/* the horizon does not fit: stage matrices are fetched per stage into per-warp buffers (they still come from L2) */
+		const int lsz = HB_EVEN(HB_TRI(d.nzM) + 2*d.nzM);
+		double *wb = base + (size_t)nw*192 + (size_t)warp*(2*lsz + HB_EVEN(d.nzM*ldW));
+		c.bufA = wb; c.bufB = wb + lsz; c.sW = wb + 2*lsz;
+		}
+	double *Pb = work + gw*d.pi_stride;
+	const long long vs = d.ux_stride + d.pi_stride;
+	for(long long inst=gw; inst<n_inst; inst+=tw)
+		{
+		const double *rq = vec + inst*vs, *bv = rq + d.ux_stride;
+		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+		if(!resident)
+			{
+			hb_trs_backward(c, d, in_shared, L_shared, bv, rq, nullptr, ux, Pb, true);
+			hb_forward(c, d, in_shared, L_shared, ux, bv, true, ux, pi, true);
+			__syncwarp();
+			continue;
+			}
+		{
+		const hb_stage s = d.st[N];
+		for(int i=lane; i<s.nu+s.nx; i+=32) ux[s.off_ux+i] = rq[s.off_ux+i];
+		__syncwarp();
+		}
+		for(int n=N-1; n>=0; n--)
+			{
+			const hb_stage s = d.st[n], s1 = d.st[n+1];
+			c.sW = Bsm + offB[n];
+			hb_trs_stage_back(c, s, s1, n, Lsm + s.off_L, Lsm + s1.off_L, bv, rq, nullptr, d.idxb, ux, Pb, true);
+			}
+		for(int n=0; n<N; n++)
+			{
+			const hb_stage s = d.st[n], s1 = d.st[n+1];
+			c.sW = Bsm + offB[n];
+			hb_stage_forward(c, s, s1, n, Lsm + s.off_L, Lsm + s1.off_L, ux, bv, true, ux, pi, true);
+			}
+		__syncwarp();
+		}
+	}
+
+extern "C" long long hb_trs_shared_smem_bytes(const hb_dims *d, const hb_stage *st_host, int warps, int *resident)
+	{
+	const int ldW = d->nxM | 1;
+	long long B = HB_EVEN((d->N+2+1)/2);
+	for(int n=0; n<d->N; n++) B += HB_EVEN((st_host[n].nu + st_host[n].nx + 1)*ldW);
+	long long res = 8LL*((long long)warps*192 + d->L_stride + B);
+	if(res<=220*1024) { *resident = 1; return res; }
+	const int lsz = HB_EVEN(HB_TRI(d->nzM) + 2*d->nzM);
+	*resident = 0;
+	return 8LL*((long long)warps*192 + (long long)warps*(2*lsz + HB_EVEN(d->nzM*ldW)));
+	}
+
+extern "C" int hb_launch_ric_trs_shared(const hb_dims *d, long long n_inst, const double *in_shared, const double *L_shared, const double *vec,
+		double *ux, double *pi, double *work, int grid, int warps, int smem, int resident, void *stream)
+	{
+	if(d->nzM>64) return -2;
+	if(warps>8) return -3;
+	if(hb_prep(hb_ric_trs_shared_kernel, smem)) return -1;
+	hb_ric_trs_shared_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in_shared, L_shared, vec, ux, pi, work, resident);
+	HB_CK(cudaGetLastError());
+	return 0;
+	}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* scenario tree                                                                                     */
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void hb_tree_kernel(hb_tdims d, long long n_trees, const double *__restrict__ in, double *__restrict__ ux_all,

@@ -122,6 +122,20 @@ int hpmpc_b200_d_ip2_res_mpc_hard_kkt_batch(hpmpc_b200_ocp *p, long long n_inst,
 int hpmpc_b200_d_kkt_solve_new_rhs_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, double *d_kkt,
                                          double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info, void *stream);
 
+/* ---- SHARED DYNAMICS (a separately labelled mode, not the headline workload): all instances have the same matrices and their own
+ * vectors b, q, r -- fleets of identical systems, sweeps over initial states / references, and the way the reference's own test
+ * programs call the solver (test_problems/test_d_ip_hard.c: one pBAbt aliased over all stages).  Factor once, then a batched
+ * d_back_ric_rec_trs_tv_res (lqcp_solvers/d_back_ric_rec.c:564) whose matrices sit in shared memory: an instance costs
+ * hpmpc_b200_shared_vec_stride() doubles in ([r q] of every stage in the ux layout, then b of every stage in the pi layout) and its
+ * ux, pi out.  d_in_shared is ONE packed instance block (its vectors are ignored). ---- */
+long long hpmpc_b200_shared_vec_stride(const hpmpc_b200_ocp *p);
+long long hpmpc_b200_shared_factor_doubles(const hpmpc_b200_ocp *p);
+int hpmpc_b200_d_back_ric_rec_trf_shared(hpmpc_b200_ocp *p, const double *d_in_shared, double *d_L_shared, void *stream);
+int hpmpc_b200_d_back_ric_rec_trs_shared_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in_shared, const double *d_L_shared,
+                                               const double *d_vec, double *d_ux, double *d_pi, void *stream);
+int hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in_shared, const double *h_vec,
+                                                   double *h_ux, double *h_pi);
+
 /* ---- data in host memory: copies in, solves, copies out (chunked so copies overlap the kernels) ---- */
 int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in,
                                             double *h_ux, double *h_pi);

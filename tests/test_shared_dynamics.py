@@ -1,0 +1,82 @@
+"""Shared-dynamics batch mode (include/hpmpc_b200.h: one set of matrices for the whole batch, per-instance b, q, r): factor once +
+batched solve with the stored factor (reference d_back_ric_rec_trf_tv_res + d_back_ric_rec_trs_tv_res, lqcp_solvers/d_back_ric_rec.c:403,564),
+against the oracle's factor+solve of every instance's full problem."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from hpmpc_b200 import capi, problems
+from oracle import api as oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def shared_batch(base, n, seed=3):
+    """Instances that share the matrices of `base` and differ in b, q, r (x0 through b_0, references through q, r)."""
+    rng = np.random.default_rng(seed)
+    probs = []
+    for _ in range(n):
+        p = copy.deepcopy(base)
+        for s in range(p.N + 1):
+            if s < p.N:
+                p.b[s] = base.b[s] + 0.3 * rng.standard_normal(base.b[s].shape)
+                p.r[s] = base.r[s] * (1.0 + 0.5 * rng.standard_normal())
+            p.q[s] = base.q[s] + 0.2 * rng.standard_normal(base.q[s].shape)
+        probs.append(p)
+    return probs
+
+
+def vec_of(h, p):
+    """[r q] of every stage in the ux layout, then b of every stage in the pi layout."""
+    v = np.zeros(h.sz.ux_stride + h.sz.pi_stride)
+    for s in range(p.N + 1):
+        o = h.off[s]["ux"]
+        v[o:o + p.nu[s]] = p.r[s]; v[o + p.nu[s]:o + p.nu[s] + p.nx[s]] = p.q[s]
+        if s < p.N:
+            v[h.sz.ux_stride + h.off[s]["pi"]:h.sz.ux_stride + h.off[s]["pi"] + p.nx[s + 1]] = p.b[s]
+    return v
+
+
+def _api():
+    L = capi.product()
+    C = capi.C
+    L.hpmpc_b200_shared_vec_stride.restype = C.c_longlong; L.hpmpc_b200_shared_vec_stride.argtypes = [C.c_void_p]
+    L.hpmpc_b200_shared_factor_doubles.restype = C.c_longlong; L.hpmpc_b200_shared_factor_doubles.argtypes = [C.c_void_p]
+    L.hpmpc_b200_d_back_ric_rec_trf_shared.argtypes = [C.c_void_p] * 4
+    L.hpmpc_b200_d_back_ric_rec_trs_shared_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 6
+    L.hpmpc_b200_d_back_ric_rec_sv_shared_batch_host.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
+    return L
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", dict(nx=8, nu=3, N=10), dict(nx=40, nu=8, N=20, nx_profile=[40 - (9 * n) // 5 for n in range(21)]),
+                                 dict(nx=30, nu=15, N=60)])
+def test_shared_dynamics_device_and_host_paths(cfg):
+    import torch
+    L = _api()
+    base = problems.make(cfg) if isinstance(cfg, str) else problems.mass_spring_ocp(cfg["nx"], cfg["nu"], cfg["N"], nx_profile=cfg.get("nx_profile"))
+    h = capi.BatchOcp(base, device=0)
+    n = 777
+    probs = shared_batch(base, n)
+    assert L.hpmpc_b200_shared_vec_stride(h.h) == h.sz.ux_stride + h.sz.pi_stride
+    blk = h.pack(base)
+    vec = np.stack([vec_of(h, p) for p in probs])
+    d_blk, d_vec = torch.from_numpy(blk).cuda(), torch.from_numpy(vec).cuda()
+    d_L = torch.zeros(L.hpmpc_b200_shared_factor_doubles(h.h) + 8, dtype=torch.float64, device="cuda")
+    ux = torch.zeros((n, h.sz.ux_stride), dtype=torch.float64, device="cuda"); pi = torch.zeros((n, h.sz.pi_stride), dtype=torch.float64, device="cuda")
+    assert L.hpmpc_b200_d_back_ric_rec_trf_shared(h.h, d_blk.data_ptr(), d_L.data_ptr(), None) == 0
+    assert L.hpmpc_b200_d_back_ric_rec_trs_shared_batch(h.h, n, d_blk.data_ptr(), d_L.data_ptr(), d_vec.data_ptr(), ux.data_ptr(), pi.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    uxh, pih = ux.cpu().numpy(), pi.cpu().numpy()
+    for i in (0, 1, 2, n // 2, n - 1):
+        o = oracle.ric(probs[i], "sv")
+        u, x = h.split_ux(uxh[i])
+        assert rel_err(u, o["u"]) < TOL and rel_err(x, o["x"]) < TOL and rel_err(h.split_pi(pih[i]), o["pi"]) < TOL, i
+    hux, hpi = np.zeros_like(uxh), np.zeros_like(pih)
+    assert L.hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(h.h, n, blk.ctypes.data, vec.ctypes.data, hux.ctypes.data, hpi.ctypes.data) == 0
+    n_ux = sum(base.nx) + sum(base.nu)
+    np.testing.assert_array_equal(hux[:, :n_ux], uxh[:, :n_ux])
+    np.testing.assert_array_equal(hpi, pih)
+    h.close()
