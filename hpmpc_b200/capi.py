@@ -91,9 +91,10 @@ class HpmpcLib:
 
     # ---------------------------------------------------------------- high level
     def ip_ocp_hard_tv(self, p: Ocp, *, order: str = "fortran", k_max: int = 40, mu0: float = 2.0, mu_tol: float = 1e-8,
-                       warm_start: int = 0, x_init=None, u_init=None):
-        """{c,fortran}_order_d_ip_ocp_hard_tv (reference include/c_interface.h:62,65)."""
+                       warm_start: int = 0, x_init=None, u_init=None, N2: int = None):
+        """{c,fortran}_order_d_ip_ocp_hard_tv (reference include/c_interface.h:62,65); N2 < N: partial condensing into N2 blocks."""
         N = p.N
+        N2 = N if N2 is None else N2
         conv = (lambda M: np.ascontiguousarray(M)) if order == "c" else (lambda M: np.asfortranarray(M))
         A = [conv(M) for M in p.A]; B = [conv(M) for M in p.B]
         Q = [conv(M) for M in p.Q]; S = [conv(M) for M in p.S]; R = [conv(M) for M in p.R]
@@ -114,7 +115,7 @@ class HpmpcLib:
         Cg = [pad(conv(M)) for M in Cg]; Dg = [pad(conv(M)) for M in Dg]
         lgg = [pad(np.ascontiguousarray(v)) for v in lgg]; ugg = [pad(np.ascontiguousarray(v)) for v in ugg]
         lam = [np.zeros(max(2 * p.nb[n] + 2 * ngl[n], 1)) for n in range(N + 1)]
-        wsz = self.lib.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N)
+        wsz = self.lib.hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N2)
         work = aligned_zeros(wsz // 8 + 16)
         res = np.zeros(8); stat = np.zeros(5 * k_max + 5)
         kk = C.c_int(0)
@@ -124,7 +125,7 @@ class HpmpcLib:
         arrs = [pa(A), pa(B), pa(b), pa(Q), pa(S), pa(R), pa(q), pa(r), pa(lb), pa(ub), pa(Cg), pa(Dg), pa(lgg), pa(ugg),
                 pa(x), pa(u), pa(pi), pa(lam)]
         pidx = pa(idxb)
-        status = fn(C.byref(kk), k_max, mu0, mu_tol, N, nx, nu, nb, pidx, ng, N, warm_start, *arrs,
+        status = fn(C.byref(kk), k_max, mu0, mu_tol, N, nx, nu, nb, pidx, ng, N2, warm_start, *arrs,
                     res.ctypes.data, work.ctypes.data, stat.ctypes.data)
         del keep
         return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)],
@@ -482,6 +483,17 @@ def product() -> C.CDLL:
         L.hpmpc_b200_d_back_ric_rec_sv_batch_host.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
         L.hpmpc_b200_d_ip2_res_mpc_hard_batch_host.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                                               C.c_double, C.c_int] + [C.c_void_p] * 5
+        L.hpmpc_b200_part_cond_compute_problem_size.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5
+        L.hpmpc_b200_pcond_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.hpmpc_b200_pcond_destroy.argtypes = [C.c_void_p]
+        L.hpmpc_b200_pcond_full.restype = C.c_void_p
+        L.hpmpc_b200_pcond_full.argtypes = [C.c_void_p]
+        L.hpmpc_b200_pcond_cond.restype = C.c_void_p
+        L.hpmpc_b200_pcond_cond.argtypes = [C.c_void_p]
+        L.hpmpc_b200_d_part_cond_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
+        L.hpmpc_b200_d_part_expand_solution_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 10
+        L.hpmpc_b200_d_ip2_res_mpc_hard_part_cond_batch.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                                                   C.c_double] + [C.c_void_p] * 6
         L.hpmpc_b200_fp64_peak_tflops.restype = C.c_double
         L.hpmpc_b200_fp64_peak_tflops.argtypes = [C.c_int]
         L.hpmpc_b200_version.restype = C.c_char_p
@@ -492,16 +504,21 @@ def product() -> C.CDLL:
 class BatchOcp:
     """Handle on a size pattern (hpmpc_b200_ocp_create) plus numpy-side packing helpers."""
 
-    def __init__(self, p: Ocp, device: int = 0):
+    def __init__(self, p: Ocp, device: int = 0, handle=None):
+        """handle: wrap an existing hpmpc_b200_ocp* owned by someone else (a partial-condensing handle) instead of creating one."""
         L = product()
         self.L, self.p, self.device = L, p, device
         self.h = C.c_void_p()
-        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
-        self._keep = idxb
-        rc = L.hpmpc_b200_ocp_create_gen(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb),
-                                         int_array(p.ng_list()), device)
-        if rc != 0:
-            raise RuntimeError(f"hpmpc_b200_ocp_create failed ({rc})")
+        self.owned = handle is None
+        if handle is not None:
+            self.h = C.c_void_p(handle)
+        else:
+            idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+            self._keep = idxb
+            rc = L.hpmpc_b200_ocp_create_gen(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb),
+                                             int_array(p.ng_list()), device)
+            if rc != 0:
+                raise RuntimeError(f"hpmpc_b200_ocp_create failed ({rc})")
         self.refresh()
         self.off = []
         for n in range(p.N + 1):
@@ -519,9 +536,9 @@ class BatchOcp:
         return rc
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             self.L.hpmpc_b200_ocp_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def pack(self, p: Ocp) -> np.ndarray:
         """One instance -> native packed block (hpmpc_b200_pack_instance, row-major inputs)."""
@@ -551,3 +568,43 @@ class BatchOcp:
         p = self.p
         ng = p.ng_list()
         return [lam[self.off[n]["lam"]:self.off[n]["lam"] + 2 * p.nb[n] + 2 * ng[n]].copy() for n in range(p.N + 1)]
+
+
+def part_cond_sizes(p: Ocp, N2: int):
+    """hpmpc_b200_part_cond_compute_problem_size: (nx2, nu2, nb2, ng2, idxb2) of the condensed problem (host only)."""
+    L = product()
+    N = p.N
+    idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+    out = [(C.c_int * (N2 + 1))() for _ in range(4)]
+    nbt = sum(p.nb) + 1
+    idxb2 = [np.zeros(nbt, dtype=np.int32) for _ in range(N2 + 1)]
+    rc = L.hpmpc_b200_part_cond_compute_problem_size(N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb),
+                                                     int_array(p.ng_list()) if p.ng else None, N2,
+                                                     *out, ptr_array(idxb2))
+    if rc != 0:
+        raise RuntimeError(f"hpmpc_b200_part_cond_compute_problem_size failed ({rc})")
+    nx2, nu2, nb2, ng2 = (list(v) for v in out)
+    return nx2, nu2, nb2, ng2, [idxb2[k][:nb2[k]].copy() for k in range(N2 + 1)]
+
+
+class PartCond:
+    """hpmpc_b200_pcond: the full and the condensed size pattern of a partially condensed problem (N2 blocks)."""
+
+    def __init__(self, p: Ocp, N2: int, device: int = 0):
+        L = product()
+        self.L, self.p, self.N2 = L, p, N2
+        self.h = C.c_void_p()
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        rc = L.hpmpc_b200_pcond_create(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu[:p.N]), int_array(p.nb), ptr_array(idxb),
+                                       int_array(p.ng_list()) if p.ng else None, N2, device)
+        if rc != 0:
+            raise RuntimeError(f"hpmpc_b200_pcond_create failed ({rc})")
+        nx2, nu2, nb2, ng2, idxb2 = part_cond_sizes(p, N2)
+        self.p2 = Ocp(N=N2, nx=nx2, nu=nu2, nb=nb2, idxb=idxb2, ng=ng2)
+        self.full = BatchOcp(p, device, handle=L.hpmpc_b200_pcond_full(self.h))
+        self.cond = BatchOcp(self.p2, device, handle=L.hpmpc_b200_pcond_cond(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.hpmpc_b200_pcond_destroy(self.h)
+            self.h = C.c_void_p()

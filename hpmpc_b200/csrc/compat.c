@@ -16,7 +16,7 @@
  *   high-level symbols: dense row-major (c_order_) or column-major (fortran_order_) stage arrays
  * Deliberate differences (documented in INTEGRATION.md): the caller's matrices are never modified
  * (lib4 writes q / b / diagonal updates into them and restores them later, d_ip2_res_hard.c:721-732);
- * `work` is not used; `memory` holds the factor in the layout of layout.h; N2 is ignored.
+ * `work` is not used; `memory` holds the factor in the layout of layout.h; N2 < N selects partial condensing (pcond.c).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -630,8 +630,107 @@ int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *n
 	return 64;     /* callers may keep passing their (larger) buffer; it is not touched */
 	}
 
+/* ---- partial condensing (N2 < N): a second cached context, a pcond handle (pcond.c) keyed by the size pattern and N2 ---- */
+static struct
+	{
+	hpmpc_b200_pcond *h;
+	int N, N2, *nx, *nu, *nb, *ng, **idxb;
+	hpmpc_b200_sizes sz;
+	int k_max_alloc;
+	double *h_in, *h_ux, *h_pi, *h_lam, *h_info;
+	double *d_in, *d_ux, *d_pi, *d_lam, *d_t, *d_info;
+	} GP;
+
+static void pc_ctx_free(void)
+	{
+	int n;
+	if(!GP.h) return;
+	hpmpc_b200_pcond_destroy(GP.h);
+	for(n=0; n<=GP.N; n++) free(GP.idxb[n]);
+	free(GP.idxb); free(GP.nx); free(GP.nu); free(GP.nb); free(GP.ng);
+	free(GP.h_in); free(GP.h_ux); free(GP.h_pi); free(GP.h_lam); free(GP.h_info);
+	cudaFree(GP.d_in); cudaFree(GP.d_ux); cudaFree(GP.d_pi); cudaFree(GP.d_lam); cudaFree(GP.d_t); cudaFree(GP.d_info);
+	memset(&GP, 0, sizeof(GP));
+	}
+
+static int pc_ctx_get(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *ng, int N2, int k_max)
+	{
+	int n, j, same = GP.h!=NULL && GP.N==N && GP.N2==N2, dev = 0;
+	for(n=0; same && n<=N; n++)
+		{
+		const int nun = n<N ? nu[n] : 0, nbn = nb ? nb[n] : 0, ngn = ng ? ng[n] : 0;
+		if(GP.nx[n]!=nx[n] || GP.nu[n]!=nun || GP.nb[n]!=nbn || GP.ng[n]!=ngn) same = 0;
+		for(j=0; same && j<nbn; j++) if(GP.idxb[n][j]!=idxb[n][j]) same = 0;
+		}
+	if(!same)
+		{
+		pc_ctx_free();
+		const char *e = getenv("HPMPC_B200_DEVICE");
+		if(e) dev = atoi(e); else if(cudaGetDevice(&dev)!=cudaSuccess) { fprintf(stderr, "hpmpc_b200: no CUDA device available\n"); return -1; }
+		if(hpmpc_b200_pcond_create(&GP.h, N, nx, nu, nb, idxb, ng, N2, dev)) { GP.h = NULL; return -1; }
+		GP.N = N; GP.N2 = N2;
+		GP.nx = malloc((N+1)*sizeof(int)); GP.nu = malloc((N+1)*sizeof(int)); GP.nb = malloc((N+1)*sizeof(int)); GP.ng = malloc((N+1)*sizeof(int));
+		GP.idxb = calloc(N+1, sizeof(int*));
+		for(n=0; n<=N; n++)
+			{
+			GP.nx[n] = nx[n]; GP.nu[n] = n<N ? nu[n] : 0; GP.nb[n] = nb ? nb[n] : 0; GP.ng[n] = ng ? ng[n] : 0;
+			GP.idxb[n] = malloc((GP.nb[n]+1)*sizeof(int));
+			for(j=0; j<GP.nb[n]; j++) GP.idxb[n][j] = idxb[n][j];
+			}
+		hpmpc_b200_ocp_sizes(hpmpc_b200_pcond_full(GP.h), &GP.sz);
+		const size_t lam = (size_t)(GP.sz.lam_stride>0 ? GP.sz.lam_stride : 2);
+		GP.h_in = calloc(GP.sz.in_stride, sizeof(double)); GP.h_ux = calloc(GP.sz.ux_stride, sizeof(double));
+		GP.h_pi = calloc(GP.sz.pi_stride+2, sizeof(double)); GP.h_lam = calloc(lam, sizeof(double));
+		if(cudaMalloc((void**)&GP.d_in, sizeof(double)*GP.sz.in_stride)!=cudaSuccess
+		|| cudaMalloc((void**)&GP.d_ux, sizeof(double)*GP.sz.ux_stride)!=cudaSuccess
+		|| cudaMalloc((void**)&GP.d_pi, sizeof(double)*(GP.sz.pi_stride+2))!=cudaSuccess
+		|| cudaMalloc((void**)&GP.d_lam, sizeof(double)*lam)!=cudaSuccess
+		|| cudaMalloc((void**)&GP.d_t, sizeof(double)*lam)!=cudaSuccess)
+			{ fprintf(stderr, "hpmpc_b200: device allocation failed\n"); return -1; }
+		}
+	if(k_max>GP.k_max_alloc)
+		{
+		free(GP.h_info); if(GP.d_info) cudaFree(GP.d_info);
+		GP.h_info = calloc(HB_IPM_INFO_HEAD+5*k_max, sizeof(double));
+		if(cudaMalloc((void**)&GP.d_info, sizeof(double)*(HB_IPM_INFO_HEAD+5*k_max))!=cudaSuccess) return -1;
+		GP.k_max_alloc = k_max;
+		}
+	return 0;
+	}
+
+/* the N2 < N branch of the reference's wrappers (interfaces/c/fortran_order_interface.c:389-528): condense, IPM on the condensed
+ * problem from a cold start (the reference never fills the condensed initial guess, :493-507), expand */
+static int high_level_part_cond(int c_order, int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb,
+		int *ng, int N2, double **A, double **B, double **b, double **Q, double **S, double **R, double **q,
+		double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
+		double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *stat)
+	{
+	int n, i, j, status;
+	const double alpha_min = 1e-8;
+	if(pc_ctx_get(N, nx, nu, nb, hidxb, ng, N2, k_max)) { fprintf(stderr, "hpmpc_b200: partial condensing: GPU context unavailable\n"); return -1; }
+	hpmpc_b200_ocp *full = hpmpc_b200_pcond_full(GP.h);
+	hpmpc_b200_pack_instance(full, c_order, A, B, b, Q, S, R, q, r, lb, ub, GP.h_in);
+	if(ng && ng[N]>0 && C && D && lg && ug) hpmpc_b200_pack_general(full, c_order, C, D, lg, ug, GP.h_in);
+	if(h2d(GP.d_in, GP.h_in, GP.sz.in_stride)
+	|| cudaMemset(GP.d_info, 0, sizeof(double)*(HB_IPM_INFO_HEAD+5*k_max))!=cudaSuccess
+	|| hpmpc_b200_d_ip2_res_mpc_hard_part_cond_batch(GP.h, 1, GP.d_in, k_max, mu0, mu_tol, alpha_min, GP.d_ux, GP.d_pi, GP.d_lam, GP.d_t, GP.d_info, NULL)
+	|| cudaDeviceSynchronize()!=cudaSuccess
+	|| d2h(GP.h_ux, GP.d_ux, GP.sz.ux_stride) || d2h(GP.h_pi, GP.d_pi, GP.sz.pi_stride) || d2h(GP.h_info, GP.d_info, HB_IPM_INFO_HEAD+5*k_max)
+	|| (GP.sz.lam_stride>0 && d2h(GP.h_lam, GP.d_lam, GP.sz.lam_stride)))
+		{ fprintf(stderr, "hpmpc_b200: partial condensing: GPU execution failed\n"); return -1; }
+	*kk = (int)GP.h_info[0];
+	status = (int)GP.h_info[1];
+	if(stat) for(i=0; i<5*(*kk); i++) stat[i] = GP.h_info[HB_IPM_INFO_HEAD+i];
+	hpmpc_b200_unpack_solution(full, GP.h_ux, GP.h_pi, GP.h_lam, x, u, pi, lam);
+	for(n=0; n<N; n++)
+		for(j=0; j<nb[n] && hidxb[n][j]<nu[n]; j++)
+			if(lb[n][j]==ub[n][j]) u[n][hidxb[n][j]] = lb[n][j];
+	for(i=0; i<4; i++) inf_norm_res[i] = GP.h_info[2+i];
+	return status;
+	}
+
 static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb,
-		int *ng, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q,
+		int *ng, int N2, int warm_start, double **A, double **B, double **b, double **Q, double **S, double **R, double **q,
 		double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
 		double **x, double **u, double **pi, double **lam, double *inf_norm_res, double *stat, const void *work0)
 	{
@@ -661,6 +760,19 @@ static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol
 			for(j=0; j<nx[n]; j++) mu0 = fmax(mu0, q[n][j]);
 			}
 		}
+	/* partial condensing: 1 <= N2 < N and no general constraints before stage N (the reference falls back to N2 = N otherwise,
+	 * interfaces/c/fortran_order_interface.c:85-97) */
+	{
+	int cond = N2>=1 && N2<N && nb!=NULL;
+	if(ng) for(n=0; n<N; n++) if(ng[n]>0) cond = 0;
+	if(cond)
+		{
+		status = high_level_part_cond(c_order, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, N2, A, B, b, Q, S, R, q, r, lb, ub,
+				C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat);
+		pthread_mutex_unlock(&g_lock);
+		return status;
+		}
+	}
 	if(warm_start)
 		for(n=0; n<=N; n++)
 			{
@@ -688,8 +800,7 @@ int c_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int 
 		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
 		double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)N2;
-	return high_level(1, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat, work0);
+	return high_level(1, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, N2, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat, work0);
 	}
 
 int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb, int *ng,
@@ -697,8 +808,7 @@ int fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol
 		double **lb, double **ub, double **C, double **D, double **lg, double **ug, double **x, double **u, double **pi,
 		double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)N2;
-	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat, work0);
+	return high_level(0, kk, k_max, mu0, mu_tol, N, nx, nu, nb, hidxb, ng, N2, warm_start, A, B, b, Q, S, R, q, r, lb, ub, C, D, lg, ug, x, u, pi, lam, inf_norm_res, stat, work0);
 	}
 
 /* reference include/c_interface.h:66 (interfaces/c/fortran_order_interface.c:695): k_max Newton steps from (ux0, pi0, lam0, t0) on

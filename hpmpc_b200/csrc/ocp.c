@@ -943,6 +943,11 @@ void hpmpc_b200_internal_generic_trf(hpmpc_b200_ocp *p) { p->tf_id = -1; }
  * that has size-specialised sweeps -- needed for the _upd_ variants (Qx / qx) and by callers that read the factor */
 void hpmpc_b200_ocp_generic_factor_layout(hpmpc_b200_ocp *p) { p->tf_id = -1; }
 
+/* used by pcond.c only: the device-side descriptor and the host copy of the stage table of a handle */
+const hb_dims *hpmpc_b200_internal_dims(const hpmpc_b200_ocp *p) { return &p->dims; }
+const hb_stage *hpmpc_b200_internal_stages(const hpmpc_b200_ocp *p) { return p->st; }
+int hpmpc_b200_internal_device(const hpmpc_b200_ocp *p, int *sms) { if(sms) *sms = p->sms; return p->device; }
+
 /* used by compat.c only: the factor of a batch-of-one sv call sits in scratch slot 0 */
 int hpmpc_b200_internal_copy_stash(hpmpc_b200_ocp *p, double *h_dst)
 	{

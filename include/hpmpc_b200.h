@@ -136,6 +136,33 @@ int hpmpc_b200_d_back_ric_rec_trs_shared_batch(hpmpc_b200_ocp *p, long long n_in
 int hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in_shared, const double *h_vec,
                                                    double *h_ux, double *h_pi);
 
+/* ---- partial condensing (reference lqcp_solvers/d_part_cond.c, used by {c,fortran}_order_d_ip_ocp_hard_tv when N2 < N,
+ * interfaces/c/fortran_order_interface.c:389-528).  The horizon is cut into N2 blocks (the first N - N2*(N/N2) blocks hold N/N2+1 stages);
+ * inside a block the states are eliminated, so the batch is solved as an N2-stage problem with stage inputs [u_{T-1} .. u_0] (newest
+ * first) and the bounds on eliminated states as general constraints.  A pcond handle owns two size patterns: the full one (pack
+ * inputs / read outputs with it) and the condensed one.  Bounds only before stage N (like the reference); a condensed stage must keep
+ * nu+nx+1 <= 64.  Everything runs on the device: condense -> IPM -> expand on one stream. ---- */
+typedef struct hpmpc_b200_pcond hpmpc_b200_pcond;
+/* d_part_cond_compute_problem_size (d_part_cond.c:694) plus the bound positions of the condensed stages; nu has N+1 entries here */
+int hpmpc_b200_part_cond_compute_problem_size(int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, const int *ng, int N2,
+                                              int *nx2, int *nu2, int *nb2, int *ng2, int **hidxb2 /* may be NULL */);
+int  hpmpc_b200_pcond_create(hpmpc_b200_pcond **out, int N, const int *nx, const int *nu /* N entries */, const int *nb,
+                             int *const *hidxb, const int *ng /* NULL, or zero before stage N */, int N2, int device);
+void hpmpc_b200_pcond_destroy(hpmpc_b200_pcond *h);
+hpmpc_b200_ocp *hpmpc_b200_pcond_full(hpmpc_b200_pcond *h);     /* owned by h */
+hpmpc_b200_ocp *hpmpc_b200_pcond_cond(hpmpc_b200_pcond *h);     /* owned by h */
+/* d_part_cond (d_part_cond.c:926): packed full batch -> packed condensed batch (the condensed handle's in_stride per instance) */
+int hpmpc_b200_d_part_cond_batch(hpmpc_b200_pcond *h, long long n_inst, const double *d_in_full, double *d_in_cond, void *stream);
+/* d_part_expand_solution (d_part_cond.c:1103): solution of the condensed batch -> solution of the full batch */
+int hpmpc_b200_d_part_expand_solution_batch(hpmpc_b200_pcond *h, long long n_inst, const double *d_in_full, const double *d_ux2,
+                                            const double *d_pi2, const double *d_lam2, const double *d_t2, double *d_ux, double *d_pi,
+                                            double *d_lam, double *d_t, void *stream);
+/* condense, IPM (cold start) on the condensed batch, expand; info[0..1] and the stat table are those of the condensed solve,
+ * info[2..5] the exit norms of the FULL problem at the expanded solution (as the reference's wrapper computes them) */
+int hpmpc_b200_d_ip2_res_mpc_hard_part_cond_batch(hpmpc_b200_pcond *h, long long n_inst, const double *d_in_full, int k_max, double mu0,
+                                                  double mu_tol, double alpha_min, double *d_ux, double *d_pi, double *d_lam,
+                                                  double *d_t, double *d_info, void *stream);
+
 /* ---- data in host memory: copies in, solves, copies out (chunked so copies overlap the kernels) ---- */
 int hpmpc_b200_d_back_ric_rec_sv_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in,
                                             double *h_ux, double *h_pi);

@@ -53,7 +53,7 @@ def _f(M):
     return np.asfortranarray(M, dtype=np.float64)
 
 
-def ipm(p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, warm_start=0):
+def ipm(p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, warm_start=0, N2=None):
     """orc_fortran_order_d_ip_ocp_hard_tv: same arguments as the reference's fortran_order_d_ip_ocp_hard_tv."""
     L, N = lib(), p.N
     A = [_f(M) for M in p.A]; B = [_f(M) for M in p.B]; Q = [_f(M) for M in p.Q]; S = [_f(M) for M in p.S]; R = [_f(M) for M in p.R]
@@ -73,7 +73,7 @@ def ipm(p: Ocp, *, k_max=40, mu0=2.0, mu_tol=1e-8, warm_start=0):
             pa(x), pa(u), pa(pi), pa(lam)]
     pidx = pa(idxb)
     status = L.orc_fortran_order_d_ip_ocp_hard_tv(C.byref(kk), k_max, mu0, mu_tol, N, int_array(p.nx), int_array(p.nu), int_array(p.nb),
-                                                   pidx, int_array(ngl), N, warm_start, *arrs, res.ctypes.data, None, stat.ctypes.data)
+                                                   pidx, int_array(ngl), N if N2 is None else N2, warm_start, *arrs, res.ctypes.data, None, stat.ctypes.data)
     return dict(status=status, kk=kk.value, x=[x[n][:p.nx[n]].copy() for n in range(N + 1)],
                 u=[u[n][:p.nu[n]].copy() for n in range(N)], pi=[pi[n][:p.nx[n + 1]].copy() for n in range(N)],
                 lam=[lam[n][:2 * p.nb[n] + 2 * ngl[n]].copy() for n in range(N + 1)], inf_norm_res=res[:4].copy(),

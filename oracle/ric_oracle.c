@@ -31,7 +31,7 @@
  * General constraints lg <= D u + C x <= ug (ng > 0): the reference treats them exactly like bounds
  * with the bounded variable replaced by the product [D C] ux (mpc_solvers/c99/d_aux_ip_hard_lib4.c:121-147, :302-383, :556-607;
  * lqcp_solvers/d_back_ric_rec.c:293-315); here a stage owns nt = nb + ng constraints, box entries first.
- * Scope: N2 >= N (no partial condensing; that is the separate routine orc_part_cond below when present).
+ * Scope: N2 >= N runs the IPM on the problem as given; N2 < N condenses it first (orc_part_cond / orc_part_expand below).
  */
 #include <math.h>
 #include <stdlib.h>
@@ -955,6 +955,279 @@ void orc_exit_residuals(const orc_prob *P, double *const *ux, double *const *pi,
 	}
 
 /* ------------------------------------------------------------------------------------------- */
+/* partial condensing (lqcp_solvers/d_part_cond.c): the horizon is cut into N2 blocks, the states inside a block are    */
+/* eliminated, and every block becomes one stage of a shorter problem with inputs [u_{T-1} .. u_1 u_0] (newest first)     */
+/* and the state of the block's first stage.  State bounds inside a block become general constraints.                    */
+/* ------------------------------------------------------------------------------------------- */
+/* block sizes: the first R1 = N - N2*(N/N2) blocks hold N/N2+1 stages, the others N/N2 (d_part_cond.c:694-735) */
+static int pc_block_len(int N, int N2, int k) { int N1 = N/N2, R1 = N - N2*N1; return k<R1 ? N1+1 : N1; }
+
+/* sizes of the condensed problem and the positions of its bounds (d_part_cond.c:694-735 for the counts, :637-679 for idxb2).
+ * nx2, nu2, nb2, ng2: [N2+1]; idxb2[k] must hold nb2[k] ints.  Returns 0, or -1 when a stage before N has general constraints
+ * (the reference stops there, :962-968). */
+int orc_part_cond_sizes(int N, const int *nx, const int *nu, const int *nb, int *const *idxb, const int *ng, int N2,
+		int *nx2, int *nu2, int *nb2, int *ng2, int **idxb2)
+	{
+	int k, j, l, n0 = 0;
+	if(ng) for(k=0; k<N; k++) if(ng[k]>0) return -1;
+	for(k=0; k<N2; k++)
+		{
+		const int T = pc_block_len(N, N2, k);
+		nx2[k] = nx[n0]; nu2[k] = 0; nb2[k] = 0; ng2[k] = 0;
+		for(j=0; j<T; j++) nu2[k] += nu[n0+j];
+		/* constraints in the order the reference emits them: stages T-1 .. 1 (inputs stay bounds, states become rows of
+		 * [D C]), then every bound of the block's first stage */
+		int nu_tmp = 0, ib = 0;
+		for(j=T-1; j>=1; j--)
+			{
+			nu_tmp += nu[n0+j];
+			for(l=0; l<nb[n0+j]; l++)
+				{
+				if(idxb[n0+j][l]<nu[n0+j]) { if(idxb2) idxb2[k][ib] = nu_tmp - nu[n0+j] + idxb[n0+j][l]; ib++; }
+				else ng2[k]++;
+				}
+			}
+		nu_tmp += nu[n0];
+		for(l=0; l<nb[n0]; l++) { if(idxb2) idxb2[k][ib] = nu_tmp - nu[n0] + idxb[n0][l]; ib++; }
+		nb2[k] = ib;
+		n0 += T;
+		}
+	nx2[N2] = nx[N]; nu2[N2] = 0; nb2[N2] = nb[N]; ng2[N2] = ng ? ng[N] : 0;
+	if(idxb2) for(l=0; l<nb[N]; l++) idxb2[N2][l] = idxb[N][l];
+	return 0;
+	}
+
+/* one block: stages n0 .. n0+T-1 of P -> stage k of P2 */
+static void pc_cond_block(const orc_prob *P, int n0, int T, orc_prob *P2, int k)
+	{
+	const int nx0 = P->nx[n0];
+	int j, i, c, m, l;
+	/* ---- Gamma_j = [ B_j' ; Gamma_{j-1} A_j' ] (+ b_j on the last row): the states x_{j+1} as an affine function of
+	 *      [u_j .. u_0, x_0, 1]   (d_cond_BAbt, d_part_cond.c:214-309) ---- */
+	double **G = malloc(T*sizeof(double*));
+	int *gr = malloc(T*sizeof(int));                          /* rows of Gamma_j = inputs so far + nx0 + 1 */
+	int nuc = 0;
+	for(j=0; j<T; j++)
+		{
+		const int s = n0+j, nu = P->nu[s], nx = P->nx[s], nx1 = P->nx[s+1], nz = nu+nx+1;
+		nuc += nu; gr[j] = nuc + nx0 + 1;
+		G[j] = calloc((size_t)gr[j]*(nx1+1), sizeof(double));
+		const double *M = P->BAbt[s];
+		if(j==0) { for(c=0; c<nx1; c++) for(i=0; i<nz; i++) G[0][i+gr[0]*c] = M[i+nz*c]; continue; }
+		for(c=0; c<nx1; c++)
+			{
+			for(i=0; i<nu; i++) G[j][i+gr[j]*c] = M[i+nz*c];
+			for(i=0; i<gr[j-1]; i++)
+				{
+				double a = 0.0;
+				for(m=0; m<nx; m++) a += G[j-1][i+gr[j-1]*m]*M[nu+m+nz*c];
+				G[j][nu+i+gr[j]*c] = a;
+				}
+			G[j][gr[j]-1+gr[j]*c] += M[nu+nx+nz*c];
+			}
+		}
+	{
+	const int nz2 = gr[T-1], nx1 = P->nx[n0+T];
+	for(c=0; c<nx1; c++) for(i=0; i<nz2; i++) P2->BAbt[k][i+nz2*c] = G[T-1][i+nz2*c];
+	}
+	/* ---- Hessian and gradient of the block (d_cond_RSQrq, d_part_cond.c:312-574): backward recursion
+	 *      pL_s = RSQrq_s + ([B A b]'_s Lx)([B A b]'_s Lx)' with Lx the Cholesky factor of the state block of pL_{s+1} (gradient
+	 *      row carried), no elimination of u; the u-columns of pL_s go to the block's Hessian, the coupling with everything
+	 *      earlier through Gamma_{s-1} ---- */
+	{
+	const int nu2 = P2->nu[k], nux2 = nu2+nx0, nz2 = nux2+1;
+	double *H2 = P2->RSQrq[k];
+	const int nzM = P->nzM;
+	double *pL = calloc((size_t)nzM*nzM, sizeof(double)), *Lx = calloc((size_t)nzM*nzM, sizeof(double));
+	double *W = calloc((size_t)nzM*nzM, sizeof(double)), *dl = calloc(nzM, sizeof(double));
+	int off = 0;                                              /* nu3: inputs of the stages behind s */
+	for(int s=T-1; s>=0; s--)
+		{
+		const int st = n0+s, nu = P->nu[st], nx = P->nx[st], nux = nu+nx, nz = nux+1;
+		const double *H = P->RSQrq[st];
+		if(s==T-1)
+			{ for(c=0; c<nux; c++) for(i=c; i<nz; i++) pL[i+nz*c] = H[i+nz*c]; }
+		else
+			{
+			const int nus = P->nu[st+1], nxs = P->nx[st+1], nzs = nus+nxs+1;    /* pL still holds stage st+1, ld nzs */
+			for(c=0; c<nxs; c++) for(i=c; i<=nxs; i++) Lx[i+(nxs+1)*c] = pL[nus+i+nzs*(nus+c)];
+			chol_mn(nxs+1, nxs, Lx, nxs+1, dl);
+			const double *M = P->BAbt[st];
+			for(i=0; i<nz; i++)
+				for(c=0; c<nxs; c++)
+					{
+					double a = 0.0;
+					for(m=c; m<nxs; m++) a += M[i+nz*m]*Lx[m+(nxs+1)*c];
+					W[i+nz*c] = a;
+					}
+			for(c=0; c<nxs; c++) W[nux+nz*c] += Lx[nxs+(nxs+1)*c];
+			for(c=0; c<nux; c++)
+				for(i=c; i<nz; i++)
+					{
+					double a = 0.0;
+					for(m=0; m<nxs; m++) a += W[i+nz*m]*W[c+nz*m];
+					pL[i+nz*c] = H[i+nz*c] + a;
+					}
+			}
+		if(s==0)
+			{ for(c=0; c<nux; c++) for(i=c; i<nz; i++) H2[off+i+nz2*(off+c)] = pL[i+nz*c]; break; }
+		/* D */
+		for(c=0; c<nu; c++) for(i=c; i<nu; i++) H2[off+i+nz2*(off+c)] = pL[i+nz*c];
+		/* M : Gamma_{s-1} times the state rows of the u-columns; its last row is the b-part of the gradient */
+		for(c=0; c<nu; c++)
+			for(i=0; i<gr[s-1]; i++)
+				{
+				double a = 0.0;
+				for(m=0; m<nx; m++) a += G[s-1][i+gr[s-1]*m]*pL[nu+m+nz*c];
+				H2[off+nu+i+nz2*(off+c)] = a;
+				}
+		/* m */
+		for(c=0; c<nu; c++) H2[nux2+nz2*(off+c)] += pL[nux+nz*c];
+		off += nu;
+		}
+	free(pL); free(Lx); free(W); free(dl);
+	}
+	/* ---- constraints (d_cond_DCtd, d_part_cond.c:579-689) ---- */
+	{
+	const int nux2 = P2->nu[k]+nx0, nbx2 = P2->nbx[k], nt2 = P2->nb[k];
+	int nu_tmp = 0, ib = 0, ig = 0;
+	for(int s=T-1; s>=1; s--)
+		{
+		const int st = n0+s, nu = P->nu[st];
+		const int brow = gr[s-1]-1;                             /* the b-row of Gamma_{s-1} */
+		nu_tmp += nu;
+		for(l=0; l<P->nbx[st]; l++)
+			{
+			const int id = P->idxb[st][l];
+			if(id<nu)
+				{ P2->d[k][ib] = P->d[st][l]; P2->d[k][nt2+ib] = P->d[st][P->nb[st]+l]; ib++; }
+			else
+				{
+				const double *g = G[s-1] + (size_t)gr[s-1]*(id-nu);
+				P2->d[k][nbx2+ig] = P->d[st][l] - g[brow]; P2->d[k][nt2+nbx2+ig] = P->d[st][P->nb[st]+l] - g[brow];
+				for(i=0; i<brow; i++) P2->DCt[k][nu_tmp+i+(size_t)nux2*ig] = g[i];
+				ig++;
+				}
+			}
+		}
+	for(l=0; l<P->nbx[n0]; l++) { P2->d[k][ib] = P->d[n0][l]; P2->d[k][nt2+ib] = P->d[n0][P->nb[n0]+l]; ib++; }
+	}
+	for(j=0; j<T; j++) free(G[j]);
+	free(G); free(gr);
+	}
+
+/* the condensed problem of P with N2 blocks (d_part_cond, d_part_cond.c:926-1066); NULL when P is not condensable */
+orc_prob *orc_part_cond(const orc_prob *P, int N2)
+	{
+	const int N = P->N;
+	int k, n0 = 0;
+	if(N2<1 || N2>=N || P->dad) return NULL;
+	int *nx2 = calloc(N2+1, sizeof(int)), *nu2 = calloc(N2+1, sizeof(int)), *nb2 = calloc(N2+1, sizeof(int)), *ng2 = calloc(N2+1, sizeof(int));
+	int **idxb2 = calloc(N2+1, sizeof(int*));
+	int nbt = 1;
+	for(k=0; k<=N; k++) nbt += P->nbx[k];
+	for(k=0; k<=N2; k++) idxb2[k] = calloc(nbt, sizeof(int));
+	orc_prob *P2 = NULL;
+	if(orc_part_cond_sizes(N, P->nx, P->nu, P->nbx, P->idxb, P->ng, N2, nx2, nu2, nb2, ng2, idxb2)==0)
+		{
+		P2 = orc_prob_create_gen(N2, nx2, nu2, nb2, idxb2, NULL, ng2);
+		for(k=0; k<N2; k++) { const int T = pc_block_len(N, N2, k); pc_cond_block(P, n0, T, P2, k); n0 += T; }
+		/* last stage: the same data (d_part_cond.c:1058-1062) */
+		const int nx = P->nx[N], nz = nx+1, nt = P->nb[N];
+		memcpy(P2->RSQrq[N2], P->RSQrq[N], sizeof(double)*nz*(nx+1));
+		memcpy(P2->d[N2], P->d[N], sizeof(double)*2*nt);
+		memcpy(P2->DCt[N2], P->DCt[N], sizeof(double)*(size_t)nx*P->ng[N]);
+		}
+	for(k=0; k<=N2; k++) free(idxb2[k]);
+	free(idxb2); free(nx2); free(nu2); free(nb2); free(ng2);
+	return P2;
+	}
+
+/* solution of the full problem from the condensed one (d_part_expand_solution, d_part_cond.c:1103-1306): inputs are copied,
+ * the states inside a block are simulated, lam / t are copied back by position (a block's bounds on inputs first, then the
+ * state bounds that became general constraints), pi inside a block by the backward recursion of the stationarity condition */
+void orc_part_expand(const orc_prob *P, const orc_prob *P2, double *const *ux2, double *const *pi2, double *const *lam2, double *const *t2,
+		double **ux, double **pi, double **lam, double **t)
+	{
+	const int N = P->N, N2 = P2->N;
+	int k, j, l, i, n0 = 0;
+	double *w = calloc(P->nzM+1, sizeof(double));
+	for(k=0; k<N2; k++)
+		{
+		const int T = pc_block_len(N, N2, k);
+		const int nt2 = P2->nb[k], nbx2 = P2->nbx[k];
+		int nu_tmp = 0, ib = 0, ig = 0;
+		for(j=T-1; j>=1; j--)
+			{
+			const int st = n0+j, nu = P->nu[st], nt = P->nb[st];
+			for(l=0; l<nu; l++) ux[st][l] = ux2[k][nu_tmp+l];
+			nu_tmp += nu;
+			int nbb = 0;
+			for(l=0; l<P->nbx[st]; l++) if(P->idxb[st][l]<nu) nbb++;
+			for(l=0; l<nbb; l++, ib++)
+				{ lam[st][l] = lam2[k][ib]; lam[st][nt+l] = lam2[k][nt2+ib]; t[st][l] = t2[k][ib]; t[st][nt+l] = t2[k][nt2+ib]; }
+			for(l=nbb; l<P->nbx[st]; l++, ig++)
+				{ lam[st][l] = lam2[k][nbx2+ig]; lam[st][nt+l] = lam2[k][nt2+nbx2+ig]; t[st][l] = t2[k][nbx2+ig]; t[st][nt+l] = t2[k][nt2+nbx2+ig]; }
+			}
+		{
+		const int nt = P->nb[n0];
+		for(l=0; l<P->nu[n0]+P->nx[n0]; l++) ux[n0][l] = ux2[k][nu_tmp+l];
+		for(l=0; l<P->nbx[n0]; l++, ib++)
+			{ lam[n0][l] = lam2[k][ib]; lam[n0][nt+l] = lam2[k][nt2+ib]; t[n0][l] = t2[k][ib]; t[n0][nt+l] = t2[k][nt2+ib]; }
+		}
+		n0 += T;
+		}
+	for(l=0; l<P->nx[N]; l++) ux[N][l] = ux2[N2][l];
+	for(l=0; l<2*P->nb[N]; l++) { lam[N][l] = lam2[N2][l]; t[N][l] = t2[N2][l]; }
+	/* states inside the blocks */
+	n0 = 0;
+	for(k=0; k<N2; k++)
+		{
+		const int T = pc_block_len(N, N2, k);
+		for(j=0; j<T-1; j++)
+			{
+			const int st = n0+j, nux = nux_(P, st), nz = nux+1, nx1 = P->nx[st+1], nu1 = P->nu[st+1];
+			for(l=0; l<nx1; l++)
+				{
+				double a = P->BAbt[st][nux+nz*l];
+				for(i=0; i<nux; i++) a += P->BAbt[st][i+nz*l]*ux[st][i];
+				ux[st+1][nu1+l] = a;
+				}
+			}
+		n0 += T;
+		}
+	/* multipliers of the dynamics */
+	n0 = 0;
+	for(k=0; k<N2; k++)
+		{
+		const int T = pc_block_len(N, N2, k);
+		for(l=0; l<P->nx[n0+T]; l++) pi[n0+T-1][l] = pi2[k][l];
+		for(j=T-1; j>=1; j--)
+			{
+			const int st = n0+j, nu = P->nu[st], nux = nux_(P, st), nz = nux+1, nx1 = P->nx[st+1], nt = P->nb[st];
+			const double *H = P->RSQrq[st];
+			for(l=0; l<nux; l++) w[l] = H[nux+nz*l];
+			for(l=0; l<nt; l++) cscatter(P, st, w, l, -lam[st][l] + lam[st][nt+l]);
+			for(l=0; l<nux; l++)
+				{
+				double a = 0.0;
+				for(i=0; i<nux; i++) a += (i>=l ? H[i+nz*l] : H[l+nz*i])*ux[st][i];
+				w[l] += a;
+				}
+			for(l=0; l<nux; l++)
+				{
+				double a = 0.0;
+				for(i=0; i<nx1; i++) a += P->BAbt[st][l+nz*i]*pi[st][i];
+				w[l] += a;
+				}
+			for(l=0; l<P->nx[st]; l++) pi[st-1][l] = w[nu+l];
+			}
+		n0 += T;
+		}
+	free(w);
+	}
+
+/* ------------------------------------------------------------------------------------------- */
 /* drivers with the reference's own high-level signature (column-major stage-wise arrays)       */
 /* ------------------------------------------------------------------------------------------- */
 static double **alloc_ux(const orc_prob *P) { int N=P->N; double **v = malloc((N+1)*sizeof(double*)); for(int n=0;n<=N;n++) v[n]=calloc(nux_(P,n)+1,sizeof(double)); return v; }
@@ -965,7 +1238,7 @@ int orc_fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu
 		double **R, double **q, double **r, double **lb, double **ub, double **C, double **D, double **lg, double **ug,
 		double **x, double **u, double **pi, double **lam, double *inf_norm_res, void *work0, double *stat)
 	{
-	(void)N2; (void)work0;
+	(void)work0;
 	int n, i, j, l, any_g = 0;
 	if(ng) for(n=0; n<=N; n++) if(ng[n]>0) any_g = 1;
 	orc_prob *P = orc_prob_create_gen(N, nx, nu_N, nb, hidxb, NULL, any_g ? ng : NULL);
@@ -995,7 +1268,23 @@ int orc_fortran_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu
 		for(n=0; n<N; n++) for(i=0; i<P->nu[n]; i++) hux[n][i] = u[n][i];
 		for(n=0; n<=N; n++) for(i=0; i<nx[n]; i++) hux[n][P->nu[n]+i] = x[n][i];
 		}
-	int status = orc_ip2_res_mpc_hard(P, kk, k_max, mu0, mu_tol, 1e-8, warm_start, stat, hux, hpi, hlam, ht);
+	int status;
+	orc_prob *P2 = (N2>=1 && N2<N) ? orc_part_cond(P, N2) : NULL;
+	if(P2!=NULL)
+		{
+		/* the IPM runs on the condensed problem, cold start (the reference leaves the condensed initial guess unset,
+		 * interfaces/c/fortran_order_interface.c:493-507); the full solution is expanded from it (:511-528) */
+		double **ux2 = alloc_ux(P2);
+		double **pi2 = malloc((N2+1)*sizeof(double*)), **lam2 = malloc((N2+1)*sizeof(double*)), **t2 = malloc((N2+1)*sizeof(double*));
+		for(n=0; n<=N2; n++) { pi2[n] = calloc(P2->nxM+1, sizeof(double)); lam2[n] = calloc(2*P2->nb[n]+1, sizeof(double)); t2[n] = calloc(2*P2->nb[n]+1, sizeof(double)); }
+		status = orc_ip2_res_mpc_hard(P2, kk, k_max, mu0, mu_tol, 1e-8, 0, stat, ux2, pi2, lam2, t2);
+		orc_part_expand(P, P2, ux2, pi2, lam2, t2, hux, hpi, hlam, ht);
+		for(n=0; n<=N2; n++) { free(ux2[n]); free(pi2[n]); free(lam2[n]); free(t2[n]); }
+		free(ux2); free(pi2); free(lam2); free(t2);
+		orc_prob_free(P2);
+		}
+	else
+		status = orc_ip2_res_mpc_hard(P, kk, k_max, mu0, mu_tol, 1e-8, warm_start, stat, hux, hpi, hlam, ht);
 	for(n=0; n<N; n++) for(i=0; i<P->nu[n]; i++) u[n][i] = hux[n][i];
 	for(n=0; n<=N; n++) for(i=0; i<nx[n]; i++) x[n][i] = hux[n][P->nu[n]+i];
 	for(n=0; n<N; n++)
