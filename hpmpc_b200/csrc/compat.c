@@ -630,6 +630,13 @@ int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *n
 	return 64;     /* callers may keep passing their (larger) buffer; it is not touched */
 	}
 
+/* reference include/lqcp_solvers.h:86 (lqcp_solvers/d_part_cond.c:694): sizes of the partially condensed problem; host arithmetic only */
+void d_part_cond_compute_problem_size(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int *nx2, int *nu2, int *nb2, int *ng2)
+	{
+	if(hpmpc_b200_part_cond_compute_problem_size(N, nx, nu, nb, hidxb, ng, N2, nx2, nu2, nb2, ng2, NULL))
+		fatal("d_part_cond_compute_problem_size: general constraints before stage N or N2 outside 1..N (the reference exits here too, d_part_cond.c:962-968)");
+	}
+
 /* ---- partial condensing (N2 < N): a second cached context, a pcond handle (pcond.c) keyed by the size pattern and N2 ---- */
 static struct
 	{

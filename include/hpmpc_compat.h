@@ -68,6 +68,10 @@ void d_res_mpc_hard_tv(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, do
 /* ---- high-level interface, dense stage-wise arrays : include/c_interface.h:59-67 ---- */
 /* include/c_interface.h:59  (interfaces/c/c_interface_work_space.c:70) */
 int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2);
+/* reference include/lqcp_solvers.h:86: sizes of the partially condensed problem (N2 blocks).  The high-level symbols below condense
+ * on the device when they are called with N2 < N; the panel-major d_part_cond / d_part_expand_solution pair itself is offered in
+ * batched form only (hpmpc_b200.h: hpmpc_b200_d_part_cond_batch, hpmpc_b200_d_part_expand_solution_batch). */
+void d_part_cond_compute_problem_size(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int *nx2, int *nu2, int *nb2, int *ng2);
 /* include/c_interface.h:62  (interfaces/c/c_order_interface.c:53) row-major matrices */
 int c_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol,
                              int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int warm_start,
