@@ -42,7 +42,24 @@ struct hpmpc_b200_tree
 	double *trs_ws; int trs_slots;          /* right-hand sides and Pb of the solve-only path, per warp slot */
 	const double *skip_state;               /* tree IPM driver: per-tree state records; the Riccati kernels skip finished trees */
 	double *mg_send, *mg_recv; size_t mg_send_bytes, mg_recv_bytes;   /* staging of the multi-GPU exchange (tree_mg below) */
+	/* one call in flight per handle for the entry points that use handle-owned scratch (IPM, trs, multi-GPU exchange): the stream
+	 * of a new call first waits for the previous call's work, so calls on different streams are serialised instead of racing */
+	cudaEvent_t ev_busy; int busy_valid, busy_made;
 	};
+
+static int tcall_begin(hpmpc_b200_tree *t, void *stream)
+	{
+	if(!t->busy_made) { CK(cudaEventCreateWithFlags(&t->ev_busy, cudaEventDisableTiming)); t->busy_made = 1; }
+	if(t->busy_valid) CK(cudaStreamWaitEvent((cudaStream_t)stream, t->ev_busy, 0));
+	return 0;
+	}
+static int tcall_end(hpmpc_b200_tree *t, void *stream, int rc)
+	{
+	if(rc) return rc;
+	CK(cudaEventRecord(t->ev_busy, (cudaStream_t)stream));
+	t->busy_valid = 1;
+	return 0;
+	}
 
 int hpmpc_b200_tree_create(hpmpc_b200_tree **out, int Nn, const struct node *tree, const int *nx, const int *nu, int device)
 	{
@@ -289,6 +306,7 @@ void hpmpc_b200_tree_destroy(hpmpc_b200_tree *t)
 		cudaFree(t->f_in_mod); cudaFree(t->f_dux); cudaFree(t->f_dpi); cudaFree(t->f_L); cudaFree(t->f_ws); cudaFree(t->f_state);
 		cudaFree(t->f_nact); if(t->h_nact) cudaFreeHost(t->h_nact); cudaFree(t->trs_ws);
 		cudaFree(t->mg_send); cudaFree(t->mg_recv);
+		if(t->busy_made) cudaEventDestroy(t->ev_busy);
 		}
 	free(t->idxb); free(t->c_ux);
 	free(t->tn); free(t->stage); free(t->seg_start); free(t->seg_nodes); free(t->lvl_seg); free(t->slot); free(t->tail_root); free(t);
@@ -544,7 +562,20 @@ static int tree_ipm_multi(hpmpc_b200_tree *t, long long n_trees, const double *d
 
 /* box-constrained IPM over a batch of trees: the whole iteration runs in one kernel, one warp per tree taking trees from a
  * queue (hb_ipm_kernel with the tree sweeps of ric_tree_ipm.cuh); per-warp work slots live in the handle */
+static int tree_ipm_impl(hpmpc_b200_tree *t, long long n_trees, const double *d_in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info,
+		void *stream);
 int hpmpc_b200_d_tree_ip2_res_mpc_hard_batch(hpmpc_b200_tree *t, long long n_trees, const double *d_in, int k_max, double mu0,
+		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info,
+		void *stream)
+	{
+	if(n_trees<=0) return 0;
+	if(t->device<0) { fprintf(stderr, "hpmpc_b200: host-only tree handle cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(t->device));
+	if(tcall_begin(t, stream)) return -1;
+	return tcall_end(t, stream, tree_ipm_impl(t, n_trees, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, stream));
+	}
+static int tree_ipm_impl(hpmpc_b200_tree *t, long long n_trees, const double *d_in, int k_max, double mu0,
 		double mu_tol, double alpha_min, int warm_start, double *d_ux, double *d_pi, double *d_lam, double *d_t, double *d_info,
 		void *stream)
 	{
@@ -610,6 +641,7 @@ int hpmpc_b200_d_tree_back_ric_rec_trs_batch(hpmpc_b200_tree *t, long long n_tre
 	CK(cudaSetDevice(t->device));
 	int grid, warps;
 	launch_shape(t, n_trees, &grid, &warps);
+	if(tcall_begin(t, stream)) return -1;
 	if(t->trs_ws==NULL || t->trs_slots<grid*warps)
 		{
 		CK(cudaStreamSynchronize((cudaStream_t)stream));
@@ -618,7 +650,7 @@ int hpmpc_b200_d_tree_back_ric_rec_trs_batch(hpmpc_b200_tree *t, long long n_tre
 		CK(cudaMalloc((void**)&t->trs_ws, sizeof(double)*(size_t)t->trs_slots*(t->dims.ux_stride + 2*t->dims.pi_stride)));
 		}
 	t->n_launches++;
-	return hb_launch_tree_trf_trs(&t->ipm_dims, n_trees, d_in, (double*)d_L, d_ux, d_pi, t->trs_ws, t->trs_slots, 1, grid, warps, stream);
+	return tcall_end(t, stream, hb_launch_tree_trf_trs(&t->ipm_dims, n_trees, d_in, (double*)d_L, d_ux, d_pi, t->trs_ws, t->trs_slots, 1, grid, warps, stream));
 	}
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -725,6 +757,7 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_batch_mg(hpmpc_b200_tree *t, hpmpc_b200_co
 	hpmpc_b200_tree_shard_node(t, hi-1, NULL, NULL, NULL, NULL, &thi);
 	CK(cudaSetDevice(t->device));
 	cudaStream_t st = (cudaStream_t)stream;
+	if(tcall_begin(t, stream)) return -1;
 	const size_t seg = (size_t)per*ln;                         /* doubles per tree this rank contributes */
 	const size_t send_b = sizeof(double)*seg*(size_t)n_trees, recv_b = send_b*(size_t)c->world;
 	if(send_b>t->mg_send_bytes) { CK(cudaStreamSynchronize(st)); cudaFree(t->mg_send); t->mg_send = NULL; CK(cudaMalloc((void**)&t->mg_send, send_b)); t->mg_send_bytes = send_b; }
@@ -745,5 +778,5 @@ int hpmpc_b200_d_tree_back_ric_rec_sv_batch_mg(hpmpc_b200_tree *t, hpmpc_b200_co
 	/* the levels above the subtree roots (redundantly), then down the own subtrees */
 	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 4, 0, 0, d_in, d_ux, d_pi, d_L, stream))) return rc;
 	if((rc = hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 5, lo, hi, d_in, d_ux, d_pi, d_L, stream))) return rc;
-	return hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 2, tlo, thi, d_in, d_ux, d_pi, d_L, stream);
+	return tcall_end(t, stream, hpmpc_b200_d_tree_back_ric_rec_sv_phase(t, n_trees, 2, tlo, thi, d_in, d_ux, d_pi, d_L, stream));
 	}

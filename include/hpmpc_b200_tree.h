@@ -111,7 +111,9 @@ int  hpmpc_b200_comm_create(hpmpc_b200_comm **out, int world, int rank, const vo
 int  hpmpc_b200_comm_wrap(hpmpc_b200_comm **out, void *nccl_comm, int world, int rank);
 void hpmpc_b200_comm_destroy(hpmpc_b200_comm *c);
 /* every rank holds all trees' data and calls this with the same arguments; on return it has ux / pi of the nodes of its subtrees
- * and of the levels above them.  Non-blocking: everything is enqueued on `stream`. */
+ * and of the levels above them.  Non-blocking: everything is enqueued on `stream`. 
+ * CONCURRENCY: the IPM, _trs_batch and _sv_batch_mg use scratch owned by the handle; the library makes the stream of such a call wait for
+ * the handle's previous one (an event), so calls issued to different streams are serialised, never raced. */
 int  hpmpc_b200_d_tree_back_ric_rec_sv_batch_mg(hpmpc_b200_tree *t, hpmpc_b200_comm *c, long long n_trees, const double *d_in,
                                                 double *d_ux, double *d_pi, double *d_L, void *stream);
 
