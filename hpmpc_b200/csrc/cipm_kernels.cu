@@ -9,7 +9,8 @@
  *                         centering computations, the variable update, the loop tests, the barrier terms of the next system);
  *                         no shared memory, 8 warps per CTA; at the end of a round it COMPACTS: instances that are not finished
  *                         are appended to the next round's active list, so every warp of the following kernels has work
- *   hb_cipm_sv_kernel     factor + solve with the IPM hooks      (S::backward + S::forward_sv)   the only 254-register phase
+ *   hb_cipm_sv_kernel     factor + solve with the IPM hooks      (S::backward + S::forward_sv)   the only 254-register phase;
+ *                         BASELINE config 3: hb_cipm_sv2_kernel, two instances per warp on the register-blocked tile (ric_ipm_blk.cuh)
  *   hb_cipm_trs_kernel    solve with the stored factor             (S::trs)
  *   hb_cipm_res_kernel    residuals, mu, exit norms                (S::residuals)
  *
@@ -21,6 +22,7 @@
  */
 #include "launch_util.cuh"
 #include "ipm_sweeps.cuh"
+#include "ric_ipm_blk.cuh"
 
 enum { CS_INIT=0, CS_P1_SV, CS_P1_A, CS_P1_TRS, CS_P1_B, CS_P2_SV, CS_P2_A, CS_P2_TRS, CS_P2_B,
        CS_RES_ENTER /* residuals wanted before phase 2 starts */, CS_RES_ITER /* ... at the end of a phase-2 iteration */,
@@ -314,6 +316,86 @@ __global__ void __launch_bounds__(256) hb_cipm_sweep_kernel(hb_cipm_args a)
 	}
 
 /* ---------------------------------------------------------------------------------------------------------------- */
+/* factor + solve (predictor) with the register-blocked factorisation sweep of ric_ipm_blk.cuh: two instances per warp.  The    */
+/* forward sweep that follows is the one-instance-per-warp routine, run for the two instances in turn on their own regions.     */
+template<class C>
+__global__ void __launch_bounds__(128, 1) hb_cipm_sv2_kernel(hb_cipm_args a)
+	{
+	typedef hb_sweeps_fast<C> S;
+	const hb_dims &d = a.d;
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31, nw = blockDim.x>>5, g = lane>>4;
+	const long long gw = (long long)blockIdx.x*nw + warp, tw = (long long)gridDim.x*nw;
+	const long long n_items = a.act ? (long long)*a.n_act : a.n_inst;
+	if(n_items==0) return;
+	double *wbase = hb_smem + (size_t)warp*hbi2_cfg<C>::PER_WARP;
+	hbi_ctx<C> c0, c1;
+	c0.init(wbase, lane, d); c1.init(wbase + hbi2_cfg<C>::PW, lane, d);
+	hbi2_ctx<C> c2;
+	c2.init(wbase, lane, d);
+	for(long long it=2*gw; it<n_items; it+=2*tw)
+		{
+		const long long i1 = it+1<n_items ? it+1 : it;
+		long long inst0 = a.act ? a.act[it] : it, inst1 = a.act ? a.act[i1] : i1;
+		int st0 = a.si[inst0*CIPM_I], st1 = a.si[inst1*CIPM_I];
+		const bool v0 = (st0==CS_P1_SV || st0==CS_P2_SV), v1 = (st1==CS_P1_SV || st1==CS_P2_SV) && inst1!=inst0;
+		if(!v0 && !v1) continue;
+		/* a pair with one idle member works twice on the other one (same data, same results, same addresses) */
+		if(!v0) { inst0 = inst1; st0 = st1; }
+		if(!v1) { inst1 = inst0; st1 = st0; }
+		__syncwarp();
+		{
+		const long long inst = g ? inst1 : inst0;
+		const bool p2 = ((g ? st1 : st0)==CS_P2_SV);
+		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst*a.work_stride);
+		hbi2_backward<C>(c2, d, a.in + inst*d.in_stride, w.L, p2 ? w.res_b : nullptr, p2 ? w.res_q : nullptr, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
+		}
+		__syncwarp();
+		{
+		const bool p2 = (st0==CS_P2_SV);
+		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst0*a.work_stride);
+		S::forward_sv(c0, d, a.in + inst0*d.in_stride, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+		}
+		if(inst1!=inst0)
+			{
+			const bool p2 = (st1==CS_P2_SV);
+			const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst1*a.work_stride);
+			__syncwarp();
+			S::forward_sv(c1, d, a.in + inst1*d.in_stride, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+			}
+		__syncwarp();
+		if(lane==0)
+			{
+			a.si[inst0*CIPM_I] = (st0==CS_P2_SV) ? CS_P2_A : CS_P1_A;
+			if(inst1!=inst0) a.si[inst1*CIPM_I] = (st1==CS_P2_SV) ? CS_P2_A : CS_P1_A;
+			}
+		__syncwarp();
+		}
+	}
+
+/* which kernel runs the factor + solve sweep of a round */
+template<class S> struct hb_cipm_sv
+	{
+	static int prep(int) { return 0; }
+	static bool use() { return false; }
+	static void launch(const hb_cipm_args &, int, cudaStream_t) {}
+	};
+template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
+	{
+	typedef hbi_v0 C;
+	static constexpr int WARPS = 4;
+	static int smem() { return WARPS*(int)sizeof(double)*hbi2_cfg<C>::PER_WARP; }
+	static int prep(int) { return hb_prep(hb_cipm_sv2_kernel<C>, smem()); }
+	/* HPMPC_B200_IPM_SV2=0 keeps the one-instance-per-warp sweep (A/B runs) */
+	static bool use() { const char *e = getenv("HPMPC_B200_IPM_SV2"); return !(e && e[0]=='0'); }
+	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st)
+		{
+		long long need = (a.n_inst + 2*WARPS - 1)/(2*WARPS);
+		const int grid = (int)(need<sms ? (need<1 ? 1 : need) : sms);
+		hb_cipm_sv2_kernel<C><<<grid, WARPS*32, smem(), st>>>(a);
+		}
+	};
+
+/* ---------------------------------------------------------------------------------------------------------------- */
 template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &base, int *lists, int *counters, int grid_sweep, int warps_sweep,
 		int sms, cudaStream_t st)
 	{
@@ -324,6 +406,8 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 	long long need = (n + step_warps - 1)/step_warps;
 	const int grid_step = (int)(need < (long long)sms*8 ? (need<1 ? 1 : need) : (long long)sms*8);
 	if(hb_prep(hb_cipm_sweep_kernel<S, 0>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 1>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 2>, smem_sweep)) return -1;
+	const bool sv2 = hb_cipm_sv<S>::use();
+	if(sv2 && hb_cipm_sv<S>::prep(0)) return -1;
 	int *act[2] = { lists, lists + n }, *cnt[2] = { counters, counters + 1 };
 	HB_CK(cudaMemsetAsync(a.si, 0, sizeof(int)*CIPM_I*(size_t)n, st));          /* every instance starts in CS_INIT */
 	HB_CK(cudaMemsetAsync(counters, 0, 2*sizeof(int), st));
@@ -338,7 +422,8 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 		{
 		const int cur = r&1, nxt = cur^1;
 		a.act = act[cur]; a.n_act = cnt[cur]; a.act_next = nullptr; a.n_act_next = nullptr;
-		hb_cipm_sweep_kernel<S, 0><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+		if(sv2) hb_cipm_sv<S>::launch(a, sms, st);
+		else hb_cipm_sweep_kernel<S, 0><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
 		hb_cipm_sweep_kernel<S, 1><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
