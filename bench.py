@@ -337,15 +337,27 @@ def run_ours(args):
             ipm_traffic_wave = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("hb_ipm_bytes_per_launch") if h.sz.ipm_fast_variant == 0 else None
         except Exception:
             ipm_traffic_wave = None
+        multi = h.sz.ipm_fast_variant >= 0 and n >= 2 * wave and os.environ.get("HPMPC_B200_IPM_FUSED", "0") != "1"
+        if multi:
+            # multi-kernel driver (cipm_kernels.cu): 3 launches up front, then k_max rounds of sv, step, trs, step, res, step
+            n_launch, kern = 3 + 6 * k_max, ("multi-kernel driver, k_max rounds enqueued: hb_cipm_sv2_kernel<24,11> (factor+solve, two instances per warp; ~50 % "
+                                             "of an iteration) + hb_cipm_sweep_kernel<trs> + <res> + 3 x hb_cipm_step_kernel")
+            try:
+                ipm_traffic_wave = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("hb_cipm_sv2_bytes_per_launch") if h.sz.ipm_fast_variant == 0 else None
+            except Exception:
+                ipm_traffic_wave = None
+            tnote = "DRAM bytes of ONE launch of the dominant kernel (hb_cipm_sv2_kernel, all 16384 instances active) from the ncu capture in profiles/"
+        else:
+            n_launch, kern = (n + wave - 1) // wave, "hb_ipm_kernel<S> (whole IPM in one kernel, one launch per wave)"
+            tnote = "DRAM bytes of one wave launch (1184 instances) from the ncu capture in profiles/"
         out = {"metric": "box_ipm_qp_solves_per_s", "value": world * n * steps / (tot_ms * 1e-3), "unit": "solves/s",
                "workload": workload_name("ipm"), "steps": steps, "ms_per_step": tot_ms / steps, "mean_iterations": mean_kk,
                "converged": int((info[:, 1] == 0).sum()), "instances_per_gpu": n,
                "launch": {"grid": h.sz.ipm_grid, "warps_per_cta": h.sz.ipm_warps_per_cta, "wave": wave, "fast_variant": h.sz.ipm_fast_variant},
-               "gpu_launches": steps * ((n + wave - 1) // wave),
+               "gpu_launches": steps * n_launch,
                "roofline": {"bound": "hbm", "achieved": w["B_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": w["B_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ipm_traffic_wave,
-                            "traffic_note": "DRAM bytes of one wave launch (1184 instances) from the ncu capture in profiles/",
-                            "kernel": "hb_ipm_kernel<hb_sweeps_fast<24,11>> (one launch per wave)",
+                            "traffic_note": tnote, "kernel": kern,
                             "bytes_per_iteration_model": w["B_it"], "flops_per_iteration_model": w["F_it"],
                             "fp64_tflops": w["F_it"] * mean_kk * n / (launch_ms * 1e-3) / 1e12}}
         if e2e:
