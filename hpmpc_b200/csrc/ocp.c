@@ -793,11 +793,14 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 	if(n_inst<=0) return 0;
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
-	/* one chunk = one wave of the IPM kernel (one instance per resident warp), unless that exceeds ~1.5 GiB of staging */
-	long long cs = (long long)p->i_grid*p->i_warps;
+	/* one chunk = one wave of the IPM kernel (one instance per resident warp), or two waves where the multi-kernel driver
+	 * (cipm_kernels.cu, the faster path from two waves on) serves the pattern; never more than ~1.5 GiB of staging per buffer */
+	const long long wave = (long long)p->i_grid*p->i_warps;
+	long long cs = wave;
 	{
 	long long cap = (1536LL<<20)/(long long)(sizeof(double)*p->dims.in_stride);
 	if(cap<1) cap = 1;
+	if(ipm_multi_wanted(p, 2*wave, k_max, warm_start) && n_inst>=2*wave && cap>=2*wave) cs = 2*wave;
 	if(cs>cap) cs = cap;
 	if(cs>n_inst) cs = n_inst;
 	}
@@ -808,7 +811,16 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 	if(call_begin(p, p->s_comp)) return -1;
 	const long long ws = p->ipm_ws;
 	const int slots = p->i_grid*p->i_warps;
-	if(ensure_scratch(p, sizeof(double)*(size_t)slots*ws)) return -1;
+	{
+	/* scratch for both drivers up front: growing it between chunks would synchronise the device */
+	size_t need = sizeof(double)*(size_t)slots*ws;
+	if(cs>=2*wave)
+		{
+		const size_t multi_b = sizeof(double)*(size_t)cs*HB_EVEN(ws) + (size_t)hb_cipm_aux_bytes(cs) + 256;
+		if(multi_b>need) need = multi_b;
+		}
+	if(ensure_scratch(p, need)) return -1;
+	}
 	/* copies alternate between two staging buffers / copy streams; the waves of all chunks run back to back on ONE compute
 	 * stream (two IPM kernels sharing the SMs would drift apart in the instruction cache, see ipm_waves) */
 	long long done; int k = 0;
@@ -824,7 +836,11 @@ int hpmpc_b200_d_ip2_res_mpc_hard_batch_host(hpmpc_b200_ocp *p, long long n_inst
 		CK(cudaMemsetAsync(d_info, 0, sizeof(double)*(size_t)m*info_len, st));
 		CK(cudaEventRecord(p->ev_in[k], st));
 		CK(cudaStreamWaitEvent(p->s_comp, p->ev_in[k], 0));
-		if(ipm_waves(p, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
+		if(m>=2*wave && ipm_multi_wanted(p, m, k_max, warm_start))
+			{
+			if(ipm_multi(p, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info, p->s_comp)) return -1;
+			}
+		else if(ipm_waves(p, m, d_in, k_max, mu0, mu_tol, alpha_min, warm_start, d_ux, d_pi, d_lam, d_t, d_info,
 				p->scratch, p->counter, lam_len, p->s_comp, NULL)) return -1;
 		CK(cudaEventRecord(p->ev_done[k], p->s_comp));
 		CK(cudaStreamWaitEvent(st, p->ev_done[k], 0));
