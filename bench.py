@@ -679,6 +679,28 @@ def run_ours(args):
         except Exception as e:      # noqa: BLE001
             out["extra"]["shared_dynamics_error"] = repr(e)
         if world == 1:
+            # a shape WITHOUT kernels of its own, nx=10 nu=4 N=25: embedded in the (12,5) frame (hpmpc_b200_ocp_create_padded) against
+            # the any-size kernels on the same batch and against the compiled (12,5) shape at the same N
+            torch.cuda.empty_cache()
+            try:
+                from hpmpc_b200 import problems as _pr
+                n_u = 32768
+                res_u = {}
+                for tag, shp, padded in (("padded_into_12_5", (10, 4, 25), True), ("any_size_kernels", (10, 4, 25), False), ("compiled_12_5", (12, 5, 25), False)):
+                    ps = [_pr.mass_spring_ocp(*shp, xi=tuple(xi)) for xi in _pr.instance_xi(64, first=0)]
+                    hu = capi.BatchOcp(ps[0], device=local, padded=padded)
+                    d_u = torch.from_numpy(np.tile(np.stack([hu.pack(q) for q in ps]), (n_u // 64, 1))).to(dev)
+                    uxu = torch.zeros((n_u, hu.sz.ux_stride), dtype=torch.float64, device=dev); piu = torch.zeros((n_u, hu.sz.pi_stride), dtype=torch.float64, device=dev)
+                    run_u = lambda: L.hpmpc_b200_d_back_ric_rec_sv_batch(hu.h, n_u, d_u.data_ptr(), uxu.data_ptr(), piu.data_ptr(), None, st)
+                    tot_u, _ = time_steps(run_u, 3, 2, stream, barrier)
+                    res_u[tag] = {"solves_per_s": n_u * 3 / (tot_u * 1e-3), "fast_variant": hu.sz.fast_variant, "in_bytes_per_solve": int(hu.sz.in_stride * 8)}
+                    hu.close()
+                    del d_u, uxu, piu
+                out["extra"]["unlisted_shape"] = {"workload": "batched Riccati factor+solve, nx=10 nu=4 N=25 (no size-specialised kernel), 32768 instances", **res_u,
+                                                  "padded_vs_compiled": res_u["padded_into_12_5"]["solves_per_s"] / res_u["compiled_12_5"]["solves_per_s"],
+                                                  "padded_vs_any_size": res_u["padded_into_12_5"]["solves_per_s"] / res_u["any_size_kernels"]["solves_per_s"]}
+            except Exception as e:      # noqa: BLE001
+                out["extra"]["unlisted_shape_error"] = repr(e)
             # the IPM's last KKT system solved again for a new right-hand side (cfg 3 shapes, 4096 instances)
             torch.cuda.empty_cache()
             try:

@@ -465,6 +465,9 @@ def product() -> C.CDLL:
         L.hpmpc_b200_ocp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hpmpc_b200_ocp_create_gen.restype = C.c_int
         L.hpmpc_b200_ocp_create_gen.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hpmpc_b200_ocp_create_padded.restype = C.c_int
+        L.hpmpc_b200_ocp_create_padded.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hpmpc_b200_ocp_padded_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.hpmpc_b200_pack_general.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.hpmpc_b200_d_back_ric_rec_sv_upd_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 7
         L.hpmpc_b200_d_back_ric_rec_trf_upd_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
@@ -504,8 +507,9 @@ def product() -> C.CDLL:
 class BatchOcp:
     """Handle on a size pattern (hpmpc_b200_ocp_create) plus numpy-side packing helpers."""
 
-    def __init__(self, p: Ocp, device: int = 0, handle=None):
-        """handle: wrap an existing hpmpc_b200_ocp* owned by someone else (a partial-condensing handle) instead of creating one."""
+    def __init__(self, p: Ocp, device: int = 0, handle=None, padded: bool = False):
+        """handle: wrap an existing hpmpc_b200_ocp* owned by someone else (a partial-condensing handle) instead of creating one.
+        padded: hpmpc_b200_ocp_create_padded -- a uniform shape without kernels of its own is embedded in the next compiled shape."""
         L = product()
         self.L, self.p, self.device = L, p, device
         self.h = C.c_void_p()
@@ -515,11 +519,19 @@ class BatchOcp:
         else:
             idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
             self._keep = idxb
-            rc = L.hpmpc_b200_ocp_create_gen(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb),
-                                             int_array(p.ng_list()), device)
+            if padded:
+                assert not p.ng
+                rc = L.hpmpc_b200_ocp_create_padded(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb), device)
+            else:
+                rc = L.hpmpc_b200_ocp_create_gen(C.byref(self.h), p.N, int_array(p.nx), int_array(p.nu), int_array(p.nb), ptr_array(idxb),
+                                                 int_array(p.ng_list()), device)
             if rc != 0:
                 raise RuntimeError(f"hpmpc_b200_ocp_create failed ({rc})")
         self.refresh()
+        NX, NU = C.c_int(0), C.c_int(0)
+        self.padded = bool(L.hpmpc_b200_ocp_padded_shape(self.h, C.byref(NX), C.byref(NU)))
+        # slots of the u-part of a stage in the handle's frame (the x-part starts behind them)
+        self.nu_frame = [(NU.value if n < p.N else 0) if self.padded else p.nu[n] for n in range(p.N + 1)]
         self.off = []
         for n in range(p.N + 1):
             v = [C.c_int() for _ in range(7)]
@@ -557,12 +569,16 @@ class BatchOcp:
     def split_ux(self, ux: np.ndarray):
         p = self.p
         u = [ux[self.off[n]["ux"]:self.off[n]["ux"] + p.nu[n]].copy() for n in range(p.N)]
-        x = [ux[self.off[n]["ux"] + p.nu[n]:self.off[n]["ux"] + p.nu[n] + p.nx[n]].copy() for n in range(p.N + 1)]
+        x = [ux[self.off[n]["ux"] + self.nu_frame[n]:self.off[n]["ux"] + self.nu_frame[n] + p.nx[n]].copy() for n in range(p.N + 1)]
         return u, x
 
     def split_pi(self, pi: np.ndarray):
         p = self.p
         return [pi[self.off[n]["pi"]:self.off[n]["pi"] + p.nx[n + 1]].copy() for n in range(p.N)]
+
+    def split_pi_real(self, pi: np.ndarray):
+        """pi of every edge, the caller's real entries (they come first in a padded frame's slots)."""
+        return self.split_pi(pi)
 
     def split_lam(self, lam: np.ndarray):
         p = self.p

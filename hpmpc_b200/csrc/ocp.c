@@ -22,6 +22,7 @@ struct hpmpc_b200_ocp
 	int device;
 	int N;
 	int *nx, *nu, *nb, *ng;  /* [N+1] */
+	int *r_nx, *r_nu;        /* [N+1] the caller's sizes when the pattern is embedded in a larger compiled shape (hpmpc_b200_ocp_create_padded), else NULL */
 	int **idxb;              /* [N+1] */
 	hb_stage *st;            /* host copy [N+1] */
 	int *h_idxb, *h_cux;     /* flat [nbtot] */
@@ -140,7 +141,7 @@ static void free_host_side(hpmpc_b200_ocp *p)
 	{
 	int n;
 	if(p->idxb) for(n=0; n<=p->N; n++) free(p->idxb[n]);
-	free(p->idxb); free(p->nx); free(p->nu); free(p->nb); free(p->ng); free(p->st); free(p->h_idxb); free(p->h_cux);
+	free(p->idxb); free(p->nx); free(p->nu); free(p->nb); free(p->ng); free(p->st); free(p->h_idxb); free(p->h_cux); free(p->r_nx); free(p->r_nu);
 	}
 
 /* all stage matrices first, then the constraint data of all stages: the distance between the matrices of consecutive stages
@@ -286,6 +287,71 @@ int hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int 
 	return hpmpc_b200_ocp_create_gen(out, N, nx, nu, nb, hidxb, NULL, device);
 	}
 
+/* A uniform pattern (nx[0] = 0, nx[1..N] = nx, nu[0..N-1] = nu, bounds only) that has no size-specialised kernels of its own is
+ * EMBEDDED in the smallest compiled shape (NX, NU) >= (nx, nu): the missing inputs and states become decoupled dummies (unit
+ * cost, zero dynamics, no bounds), which leaves every real quantity of the recursion unchanged -- the same device the kernels use
+ * for stage 0 (no x) and stage N (no u).  The handle then describes the PADDED frame: strides, stage offsets, ux = [u (NU) x (NX)]
+ * per stage with the real entries first in each part, idxb shifted accordingly; hpmpc_b200_pack_instance / _unpack_solution take
+ * and return the caller's real sizes.  A pattern that is not uniform, already compiled, or larger than every compiled shape gets a
+ * plain handle (any-size kernels), as from hpmpc_b200_ocp_create.  Addresses the fast path's shape list. */
+static const int pad_shapes[][2] = { {4, 2}, {8, 3}, {12, 5}, {24, 11} };
+int hpmpc_b200_ocp_create_padded(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb, int *const *hidxb, int device)
+	{
+	int n, j, k, uniform = (N>=3 && nx[0]==0), nbt = 0;
+	for(n=1; uniform && n<=N; n++) if(nx[n]!=nx[1]) uniform = 0;
+	for(n=0; uniform && n<N; n++) if(nu[n]!=nu[0]) uniform = 0;
+	for(n=0; nb && n<=N; n++) nbt += nb[n];
+	int NX = -1, NU = -1;
+	if(uniform)
+		for(k=0; k<4; k++)
+			{
+			if(nbt>0 && k==0) continue;                      /* the smallest shape has no size-specialised IPM sweeps */
+			if(nx[1]<=pad_shapes[k][0] && nu[0]<=pad_shapes[k][1]) { NX = pad_shapes[k][0]; NU = pad_shapes[k][1]; break; }
+			}
+	if(NX<0 || (NX==nx[1] && NU==nu[0])) return hpmpc_b200_ocp_create_gen(out, N, nx, nu, nb, hidxb, NULL, device);
+	int *nxp = malloc((N+1)*sizeof(int)), *nup = malloc((N+1)*sizeof(int));
+	int **idp = calloc(N+1, sizeof(int*));
+	int rc = -1;
+	if(nxp && nup && idp)
+		{
+		rc = 0;
+		for(n=0; n<=N; n++)
+			{
+			nxp[n] = n==0 ? 0 : NX; nup[n] = n<N ? NU : 0;
+			const int nbn = nb ? nb[n] : 0, nun = n<N ? nu[n] : 0;
+			idp[n] = malloc((nbn+1)*sizeof(int));
+			if(!idp[n]) { rc = -1; break; }
+			for(j=0; j<nbn; j++)
+				{
+				const int id = hidxb[n][j];
+				if(id<0 || id>=nun+nx[n]) { fprintf(stderr, "hpmpc_b200: stage %d: idxb[%d]=%d out of range\n", n, j, id); rc = -2; break; }
+				idp[n][j] = id<nun ? id : nup[n] + (id-nun);
+				}
+			if(rc) break;
+			}
+		if(rc==0) rc = hpmpc_b200_ocp_create_gen(out, N, nxp, nup, nb, idp, NULL, device);
+		if(rc==0)
+			{
+			hpmpc_b200_ocp *p = *out;
+			p->r_nx = malloc((N+1)*sizeof(int)); p->r_nu = malloc((N+1)*sizeof(int));
+			if(!p->r_nx || !p->r_nu) { hpmpc_b200_ocp_destroy(p); *out = NULL; rc = -1; }
+			else for(n=0; n<=N; n++) { p->r_nx[n] = nx[n]; p->r_nu[n] = n<N ? nu[n] : 0; }
+			}
+		}
+	if(idp) for(n=0; n<=N; n++) free(idp[n]);
+	free(idp); free(nxp); free(nup);
+	return rc;
+	}
+
+/* 1 and the compiled shape the pattern is embedded in when the handle came from hpmpc_b200_ocp_create_padded and was padded */
+int hpmpc_b200_ocp_padded_shape(const hpmpc_b200_ocp *p, int *NX, int *NU)
+	{
+	if(!p->r_nx) return 0;
+	if(NX) *NX = p->nx[p->N];
+	if(NU) *NU = p->nu[0];
+	return 1;
+	}
+
 void hpmpc_b200_ocp_destroy(hpmpc_b200_ocp *p)
 	{
 	int k;
@@ -382,6 +448,37 @@ int hpmpc_b200_pack_instance(const hpmpc_b200_ocp *p, int c_order, double *const
 	{
 	int n, i, j;
 	memset(blk, 0, sizeof(double)*p->dims.in_stride);
+	if(p->r_nx)
+		{
+		/* embedded pattern: real entries into the padded frame, unit cost on the dummy inputs and states */
+		for(n=0; n<=p->N; n++)
+			{
+			const hb_stage *s = &p->st[n];
+			const int NXp = s->nx, NUp = s->nu, nuxp = NXp+NUp, nx1p = s->nx1;
+			const int nx = p->r_nx[n], nu = p->r_nu[n], nx1 = n<p->N ? p->r_nx[n+1] : 0;
+			if(n<p->N)
+				{
+				double *M = blk + s->off_BAbt;
+				for(i=0; i<nu; i++) for(j=0; j<nx1; j++) M[i*nx1p+j] = EL(B[n], j, i, nx1, nu, c_order);
+				for(i=0; i<nx; i++) for(j=0; j<nx1; j++) M[(NUp+i)*nx1p+j] = EL(A[n], j, i, nx1, nx, c_order);
+				for(j=0; j<nx1; j++) M[nuxp*nx1p+j] = b[n][j];
+				}
+			double *H = blk + s->off_RSQ;
+			for(i=0; i<nu; i++) for(j=0; j<=i; j++) H[HB_TRI(i)+j] = EL(R[n], i, j, nu, nu, c_order);
+			for(i=nu; i<NUp; i++) H[HB_TRI(i)+i] = 1.0;
+			for(i=0; i<nx; i++)
+				{
+				for(j=0; j<nu; j++) H[HB_TRI(NUp+i)+j] = EL(S[n], j, i, nu, nx, c_order);
+				for(j=0; j<=i; j++) H[HB_TRI(NUp+i)+NUp+j] = EL(Q[n], i, j, nx, nx, c_order);
+				}
+			for(i=nx; i<NXp; i++) H[HB_TRI(NUp+i)+NUp+i] = 1.0;
+			for(j=0; j<nu; j++) H[HB_TRI(nuxp)+j] = r[n][j];
+			for(j=0; j<nx; j++) H[HB_TRI(nuxp)+NUp+j] = q[n][j];
+			double *d = blk + s->off_d;
+			for(j=0; j<s->nb; j++) { d[j] = lb[n][j]; d[s->nb+j] = ub[n][j]; }
+			}
+		return 0;
+		}
 	for(n=0; n<=p->N; n++)
 		{
 		const hb_stage *s = &p->st[n];
@@ -434,9 +531,11 @@ void hpmpc_b200_unpack_solution(const hpmpc_b200_ocp *p, const double *ux, const
 	for(n=0; n<=p->N; n++)
 		{
 		const hb_stage *s = &p->st[n];
-		if(u && n<p->N) for(i=0; i<s->nu; i++) u[n][i] = ux[s->off_ux+i];
-		if(x) for(i=0; i<s->nx; i++) x[n][i] = ux[s->off_ux+s->nu+i];
-		if(pi_out && pi && n<p->N) for(i=0; i<s->nx1; i++) pi_out[n][i] = pi[s->off_pi+i];
+		/* an embedded pattern returns the caller's real entries: they come first in the u- and in the x-part of the padded frame */
+		const int nu = p->r_nu ? p->r_nu[n] : s->nu, nx = p->r_nx ? p->r_nx[n] : s->nx, nx1 = p->r_nx ? (n<p->N ? p->r_nx[n+1] : 0) : s->nx1;
+		if(u && n<p->N) for(i=0; i<nu; i++) u[n][i] = ux[s->off_ux+i];
+		if(x) for(i=0; i<nx; i++) x[n][i] = ux[s->off_ux+s->nu+i];
+		if(pi_out && pi && n<p->N) for(i=0; i<nx1; i++) pi_out[n][i] = pi[s->off_pi+i];
 		if(lam_out && lam) for(i=0; i<2*(s->nb+s->ng); i++) lam_out[n][i] = lam[2*s->off_c+i];
 		}
 	}

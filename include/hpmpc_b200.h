@@ -51,6 +51,14 @@ int  hpmpc_b200_ocp_create(hpmpc_b200_ocp **out, int N, const int *nx, const int
  * mpc_solvers/d_res_ip_res_hard_libstr.c:120-144.  Patterns with ng > 0 run on the any-size kernels. */
 int  hpmpc_b200_ocp_create_gen(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb,
                                int *const *hidxb, const int *ng, int device);
+/* the same for a UNIFORM pattern (nx[0] = 0, nx[1..N] = nx, nu[0..N-1] = nu, bounds only) whose (nx, nu) is not one of the compiled
+ * shapes (8,3), (12,5), (24,11) (and (4,2) without bounds): the pattern is embedded in the smallest compiled shape (NX, NU) >= (nx, nu)
+ * with decoupled dummy inputs and states, so the size-specialised kernels serve it.  The handle describes the PADDED frame (sizes,
+ * stage offsets; per stage ux = [u (NU slots) x (NX slots)], pi NX slots, real entries first); hpmpc_b200_pack_instance and
+ * hpmpc_b200_unpack_solution take / return the caller's real sizes.  Any other pattern gets a plain handle. */
+int  hpmpc_b200_ocp_create_padded(hpmpc_b200_ocp **out, int N, const int *nx, const int *nu, const int *nb,
+                                  int *const *hidxb, int device);
+int  hpmpc_b200_ocp_padded_shape(const hpmpc_b200_ocp *p, int *NX, int *NU);      /* 1 when padded, else 0 */
 /* CONCURRENCY: a handle owns one set of scratch slots and one work-queue counter, so it runs ONE call at a time.  The library
  * enforces this on the device: every entry point makes its stream wait for the handle's previous call (an event), so calls issued
  * to different streams are serialised, never raced.  Use one handle per stream for concurrent solves.  Host threads must not
