@@ -242,6 +242,80 @@ class HpmpcLib:
                     t=[sp(t[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)],
                     stat=stat[:5 * kk.value].reshape(-1, 5).copy())
 
+    def part_cond(self, p: Ocp, N2: int, expand_from=None):
+        """d_part_cond_compute_problem_size + d_part_cond on panel-major data (reference include/lqcp_solvers.h:86-92): the condensed
+        problem as dense arrays per block.  expand_from = (ux2, pi2, lam2, t2) lists in the condensed problem's sizes additionally runs
+        d_part_expand_solution (:95) and returns the full-space (u, x, pi, lam, t)."""
+        N = p.N
+        nx, nu, nb, ng = self._sizes(p)
+        BAbt, RSQ = self._pm_problem(p)
+        DCt, d, pnb, png, ngl = self._pm_general(p)
+        idxb = [np.ascontiguousarray(v, dtype=np.int32) if len(v) else np.zeros(1, dtype=np.int32) for v in p.idxb]
+        o = [(C.c_int * (N2 + 1))() for _ in range(4)]
+        L = self.lib
+        L.d_part_cond_compute_problem_size.restype = None
+        L.d_part_cond_compute_problem_size(N, nx, nu, nb, ptr_array(idxb), ng, N2, *o)
+        nx2, nu2, nb2, ng2 = (list(v) for v in o)
+        for f in (L.d_part_cond_memory_space_size_bytes, L.d_part_cond_work_space_size_bytes, L.d_part_expand_work_space_size_bytes):
+            f.restype = C.c_int
+        msz = L.d_part_cond_memory_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N2, *o)
+        wsz = L.d_part_cond_work_space_size_bytes(N, nx, nu, nb, ptr_array(idxb), ng, N2, *o)
+        mem, work = aligned_zeros(msz // 8 + 64), aligned_zeros(wsz // 8 + 64)
+        P = lambda n: (C.c_void_p * n)()
+        pB2, pQ2, pD2, pd2, pi2_ = P(N2 + 1), P(N2 + 1), P(N2 + 1), P(N2 + 1), P(N2 + 1)
+        pa = ptr_array
+        keep = (pa(BAbt), pa(RSQ), pa(DCt), pa(d), pa(idxb))
+        L.d_part_cond.restype = None
+        L.d_part_cond(N, nx, nu, nb, keep[4], ng, keep[0], keep[1], keep[2], keep[3], N2, o[0], o[1], o[2], pi2_, o[3], pB2, pQ2, pD2, pd2,
+                      C.c_void_p(mem.ctypes.data), C.c_void_p(work.ctypes.data))
+
+        def from_pmat(ptr, rows, cols):
+            pr, sda = _rup(max(rows, 1), BS), _rup(max(cols, 1), NCL)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(pr * sda,))
+            I, J = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+            return a[(I // BS) * BS * sda + I % BS + BS * J].copy() if rows and cols else np.zeros((rows, cols))
+        out = dict(nx2=nx2, nu2=nu2, nb2=nb2, ng2=ng2, BAbt=[], RSQrq=[], DCt=[], lb=[], ub=[], lg=[], ug=[], idxb=[])
+        for k in range(N2):
+            nux2 = nu2[k] + nx2[k]
+            out["BAbt"].append(from_pmat(pB2[k], nux2 + 1, nx2[k + 1]))
+            out["RSQrq"].append(np.tril(from_pmat(pQ2[k], nux2 + 1, nux2)))
+            out["DCt"].append(from_pmat(pD2[k], nux2, ng2[k]))
+            pnb2, png2 = _rup(nb2[k], BS), _rup(ng2[k], BS)
+            dd = np.ctypeslib.as_array(C.cast(pd2[k], C.POINTER(C.c_double)), shape=(2 * pnb2 + 2 * png2 + 1,))
+            out["lb"].append(dd[:nb2[k]].copy()); out["ub"].append(dd[pnb2:pnb2 + nb2[k]].copy())
+            out["lg"].append(dd[2 * pnb2:2 * pnb2 + ng2[k]].copy()); out["ug"].append(dd[2 * pnb2 + png2:2 * pnb2 + png2 + ng2[k]].copy())
+            out["idxb"].append(np.ctypeslib.as_array(C.cast(pi2_[k], C.POINTER(C.c_int)), shape=(max(nb2[k], 1),))[:nb2[k]].copy())
+        if expand_from is not None:
+            ux2l, pi2l, lam2l, t2l = expand_from
+            pnb2 = [_rup(v, BS) for v in nb2]; png2 = [_rup(v, BS) for v in ng2]
+
+            def bound_like(v, k):     # [lb ub lg ug] of a condensed stage -> the padded lib4 arrangement
+                a = aligned_zeros(2 * pnb2[k] + 2 * png2[k] + 4)
+                a[:nb2[k]] = v[:nb2[k]]; a[pnb2[k]:pnb2[k] + nb2[k]] = v[nb2[k]:2 * nb2[k]]
+                a[2 * pnb2[k]:2 * pnb2[k] + ng2[k]] = v[2 * nb2[k]:2 * nb2[k] + ng2[k]]
+                a[2 * pnb2[k] + png2[k]:2 * pnb2[k] + png2[k] + ng2[k]] = v[2 * nb2[k] + ng2[k]:]
+                return a
+            hux2 = [np.concatenate([np.asarray(ux2l[k], dtype=np.float64), np.zeros(4)]) for k in range(N2 + 1)]
+            hpi2 = [np.concatenate([np.asarray(pi2l[k], dtype=np.float64), np.zeros(4)]) for k in range(N2)]
+            hlam2 = [bound_like(np.asarray(lam2l[k]), k) for k in range(N2 + 1)]; ht2 = [bound_like(np.asarray(t2l[k]), k) for k in range(N2 + 1)]
+            hux = [aligned_zeros(_rup(p.nx[n] + p.nu[n] + 1, BS) + 4) for n in range(N + 1)]
+            hpi = [aligned_zeros(_rup(p.nx[n + 1], BS) + 4) for n in range(N)]
+            hlam = [aligned_zeros(2 * pnb[n] + 2 * png[n] + 4) for n in range(N + 1)]; ht = [aligned_zeros(2 * pnb[n] + 2 * png[n] + 4) for n in range(N + 1)]
+            hb = [np.ascontiguousarray(v) for v in p.b]
+            hrq = [np.concatenate([p.r[n], p.q[n]]) if n < N else np.ascontiguousarray(p.q[n]) for n in range(N + 1)]
+            ew = aligned_zeros(L.d_part_expand_work_space_size_bytes(N, nx, nu, nb, ng) // 8 + 64)
+            k2 = (pa(hux2), pa(hpi2), pa(hlam2), pa(ht2), pa(hux), pa(hpi), pa(hlam), pa(ht), pa(hb), pa(hrq))
+            L.d_part_expand_solution.restype = None
+            L.d_part_expand_solution(N, nx, nu, nb, keep[4], ng, keep[0], k2[8], keep[1], k2[9], keep[2], k2[4], k2[5], k2[6], k2[7], N2,
+                                     o[0], o[1], o[2], pi2_, o[3], k2[0], k2[1], k2[2], k2[3], C.c_void_p(ew.ctypes.data))
+            sp = self._split_bound_like
+            out["expanded"] = dict(u=[hux[n][:p.nu[n]].copy() for n in range(N)], x=[hux[n][p.nu[n]:p.nu[n] + p.nx[n]].copy() for n in range(N + 1)],
+                                   pi=[hpi[n][:p.nx[n + 1]].copy() for n in range(N)],
+                                   lam=[sp(hlam[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)],
+                                   t=[sp(ht[n], p.nb[n], pnb[n], ngl[n], png[n]) for n in range(N + 1)])
+        del keep
+        return out
+
     def ip_then_solve_kkt_new_rhs_high_level(self, p: Ocp, p2: Ocp, *, order="fortran", k_max=40, mu0=2.0, mu_tol=1e-8):
         """{c,fortran}_order_d_ip_ocp_hard_tv on p, then {c,fortran}_order_d_solve_kkt_new_rhs_ocp_hard_tv (reference
         include/c_interface.h:63,67) on the SAME work0 with the vectors b, q, r, lb, ub of p2."""

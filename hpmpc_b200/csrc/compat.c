@@ -133,42 +133,46 @@ static int d2h(double *h, const double *d, size_t n) { return cudaMemcpy(h, d, s
 /* panel-major problem data -> native block (G.h_in) */
 /* hpDCt[n]: [D C]' of the stage, (nu+nx) x ng panel-major with cng = ng rounded up to ncl padded columns; hd[n] then continues
  * with lg (png) and ug (png) behind the two padded bound blocks (interfaces/c/c_order_interface.c:276-283, :371-378) */
-static void pack_from_pmat_g(int N, const int *nx, const int *nu, const int *nb, double **hpBAbt, double **hpRSQrq, double **hd, double **hpDCt)
+/* panel-major stage matrices -> one packed instance block of handle `ocp` (ngv: the handle's ng[], may be NULL) */
+static void pack_from_pmat_to(hpmpc_b200_ocp *ocp, const hpmpc_b200_sizes *sz, double *h_in, const int *ngv, int N, const int *nx, const int *nu,
+		const int *nb, double **hpBAbt, double **hpRSQrq, double **hd, double **hpDCt)
 	{
 	int n, i, j;
-	memset(G.h_in, 0, sizeof(double)*G.sz.in_stride);
+	memset(h_in, 0, sizeof(double)*sz->in_stride);
 	for(n=0; n<=N; n++)
 		{
 		int oB, oH, oD;
-		hpmpc_b200_ocp_stage_offsets(G.ocp, n, &oB, &oH, &oD, NULL, NULL, NULL, NULL);
+		hpmpc_b200_ocp_stage_offsets(ocp, n, &oB, &oH, &oD, NULL, NULL, NULL, NULL);
 		int nun = n<N ? nu[n] : 0, nux = nun+nx[n];
 		if(n<N)
 			{
 			int nx1 = nx[n+1], cnx1 = RUP(nx1, NCL);
-			double *M = G.h_in + oB;
+			double *M = h_in + oB;
 			for(i=0; i<=nux; i++) for(j=0; j<nx1; j++) M[i*nx1+j] = PM(hpBAbt[n], cnx1, i, j);
 			}
 		int cnux = RUP(nux, NCL);
-		double *H = G.h_in + oH;
+		double *H = h_in + oH;
 		for(i=0; i<nux; i++) for(j=0; j<=i; j++) H[HB_TRI(i)+j] = PM(hpRSQrq[n], cnux, i, j);
 		for(j=0; j<nux; j++) H[HB_TRI(nux)+j] = PM(hpRSQrq[n], cnux, nux, j);
 		if(hd && nb && nb[n]>0)
 			{
 			int pnb = RUP(nb[n], BS);
-			for(j=0; j<nb[n]; j++) { G.h_in[oD+j] = hd[n][j]; G.h_in[oD+nb[n]+j] = hd[n][pnb+j]; }
+			for(j=0; j<nb[n]; j++) { h_in[oD+j] = hd[n][j]; h_in[oD+nb[n]+j] = hd[n][pnb+j]; }
 			}
-		if(G.ng[n]>0 && hpDCt)
+		if(ngv && ngv[n]>0 && hpDCt)
 			{
-			int ng = G.ng[n], cng = RUP(ng, NCL), png = RUP(ng, BS), pnb = (nb && nb[n]>0) ? RUP(nb[n], BS) : 0, oG, oDg;
-			hpmpc_b200_ocp_general_offsets(G.ocp, n, NULL, &oG, &oDg, NULL);
-			for(i=0; i<nux; i++) for(j=0; j<ng; j++) G.h_in[oG+i*ng+j] = PM(hpDCt[n], cng, i, j);
-			if(hd) for(j=0; j<ng; j++) { G.h_in[oDg+j] = hd[n][2*pnb+j]; G.h_in[oDg+ng+j] = hd[n][2*pnb+png+j]; }
+			int ng = ngv[n], cng = RUP(ng, NCL), png = RUP(ng, BS), pnb = (nb && nb[n]>0) ? RUP(nb[n], BS) : 0, oG, oDg;
+			hpmpc_b200_ocp_general_offsets(ocp, n, NULL, &oG, &oDg, NULL);
+			for(i=0; i<nux; i++) for(j=0; j<ng; j++) h_in[oG+i*ng+j] = PM(hpDCt[n], cng, i, j);
+			if(hd) for(j=0; j<ng; j++) { h_in[oDg+j] = hd[n][2*pnb+j]; h_in[oDg+ng+j] = hd[n][2*pnb+png+j]; }
 			}
 		}
 	}
+static void pack_from_pmat_g(int N, const int *nx, const int *nu, const int *nb, double **hpBAbt, double **hpRSQrq, double **hd, double **hpDCt)
+	{
+	pack_from_pmat_to(G.ocp, &G.sz, G.h_in, G.ng, N, nx, nu, nb, hpBAbt, hpRSQrq, hd, hpDCt);
+	}
 
-/* the reference's Qx / qx arrays ([box (pnb) | general (ng)] per stage, lqcp_solvers/d_back_ric_rec.c:196-214) into the flat
- * per-constraint device vectors the _upd_ entry points take; returns what to pass (NULL when the caller gave none) */
 static int stage_updates(int N, const int *nb, double **Qx, double **qx, const double **dQx, const double **dqx)
 	{
 	int n, j, any = 0;
@@ -734,6 +738,191 @@ static int high_level_part_cond(int c_order, int *kk, int k_max, double mu0, dou
 			if(lb[n][j]==ub[n][j]) u[n][hidxb[n][j]] = lb[n][j];
 	for(i=0; i<4; i++) inf_norm_res[i] = GP.h_info[2+i];
 	return status;
+	}
+
+/* ---- the lib4 routines themselves (reference include/lqcp_solvers.h:88-95, lqcp_solvers/d_part_cond.c:739, :860, :926, :1072, :1103):
+ *      panel-major in and out, a batch of one through the device kernels.  `memory` receives the condensed matrices in the
+ *      reference's own arrangement (all [B A b]', then all RSQrq, all [D C]', all d, then the idxb arrays); `work` is not used ---- */
+static void pc_cond_dims(int N2, const int *nx2, const int *nu2, const int *nb2, const int *ng2, int k, int *pnz, int *pnux, int *pnb, int *png,
+		int *cnx1, int *cnux, int *cng)
+	{
+	(void)N2;
+	*pnz = RUP(nu2[k]+nx2[k]+1, BS); *pnux = RUP(nu2[k]+nx2[k], BS); *pnb = RUP(nb2[k], BS); *png = RUP(ng2[k], BS);
+	*cnx1 = RUP(nx2[k+1], NCL); *cnux = RUP(nu2[k]+nx2[k], NCL); *cng = RUP(ng2[k], NCL);
+	}
+
+int d_part_cond_memory_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int *nx2, int *nu2, int *nb2, int *ng2)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)hidxb; (void)ng;
+	int k, pnz, pnux, pnb, png, cnx1, cnux, cng;
+	size_t d = 0, it = 0;
+	for(k=0; k<N2; k++)
+		{
+		pc_cond_dims(N2, nx2, nu2, nb2, ng2, k, &pnz, &pnux, &pnb, &png, &cnx1, &cnux, &cng);
+		d += (size_t)pnz*cnx1 + (size_t)pnz*cnux + (size_t)pnux*cng + 2*pnb + 2*png;
+		it += nb2[k];
+		}
+	return (int)(d*sizeof(double) + it*sizeof(int) + 64);
+	}
+int d_part_cond_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int *nx2, int *nu2, int *nb2, int *ng2)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)hidxb; (void)ng; (void)N2; (void)nx2; (void)nu2; (void)nb2; (void)ng2;
+	return 64;
+	}
+int d_part_expand_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int *ng)
+	{
+	(void)N; (void)nx; (void)nu; (void)nb; (void)ng;
+	return 64;
+	}
+
+void d_part_cond(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **hpBAbt, double **hpRSQrq, double **hpDCt, double **hd,
+		int N2, int *nx2, int *nu2, int *nb2, int **hidxb2, int *ng2, double **hpBAbt2, double **hpRSQrq2, double **hpDCt2, double **hd2,
+		void *memory, void *work)
+	{
+	(void)work;
+	int k, i, j;
+	if(N2>=N)
+		{
+		/* nothing to condense: the condensed problem IS the problem (d_part_cond.c:937-962) */
+		for(k=0; k<=N; k++)
+			{
+			nx2[k] = nx[k]; nu2[k] = nu[k]; nb2[k] = nb[k]; hidxb2[k] = hidxb[k]; ng2[k] = ng[k];
+			if(k<N) hpBAbt2[k] = hpBAbt[k];
+			hpRSQrq2[k] = hpRSQrq[k]; hpDCt2[k] = hpDCt[k]; hd2[k] = hd[k];
+			}
+		return;
+		}
+	pthread_mutex_lock(&g_lock);
+	if(pc_ctx_get(N, nx, nu, nb, hidxb, ng, N2, 1)) { pthread_mutex_unlock(&g_lock); fatal("d_part_cond: GPU context unavailable"); }
+	hpmpc_b200_ocp *full = hpmpc_b200_pcond_full(GP.h), *cond = hpmpc_b200_pcond_cond(GP.h);
+	hpmpc_b200_sizes szc;
+	hpmpc_b200_ocp_sizes(cond, &szc);
+	pack_from_pmat_to(full, &GP.sz, GP.h_in, GP.ng, N, nx, nu, nb, hpBAbt, hpRSQrq, hd, hpDCt);
+	double *d_in2 = NULL, *h2 = calloc(szc.in_stride, sizeof(double));
+	int bad = h2==NULL || cudaMalloc((void**)&d_in2, sizeof(double)*szc.in_stride)!=cudaSuccess
+		|| h2d(GP.d_in, GP.h_in, GP.sz.in_stride)
+		|| hpmpc_b200_d_part_cond_batch(GP.h, 1, GP.d_in, d_in2, NULL)
+		|| cudaDeviceSynchronize()!=cudaSuccess
+		|| d2h(h2, d_in2, szc.in_stride);
+	cudaFree(d_in2);
+	if(bad) { free(h2); pthread_mutex_unlock(&g_lock); fatal("d_part_cond: GPU execution failed"); }
+	/* the bound positions (d_cond_DCtd assigns them while it condenses) */
+	{
+	int *t0 = malloc((N2+1)*sizeof(int)), *t1 = malloc((N2+1)*sizeof(int)), *t2 = malloc((N2+1)*sizeof(int)), *t3 = malloc((N2+1)*sizeof(int));
+	int **idx = calloc(N2+1, sizeof(int*)), nbt = 1;
+	for(k=0; k<=N; k++) nbt += nb[k];
+	for(k=0; k<=N2; k++) idx[k] = calloc(nbt, sizeof(int));
+	hpmpc_b200_part_cond_compute_problem_size(N, nx, nu, nb, hidxb, ng, N2, t0, t1, t2, t3, idx);
+	/* memory: matrices per kind, then the int arrays */
+	double *ptr = (double*)memory;
+	int pnz, pnux, pnb, png, cnx1, cnux, cng;
+	for(k=0; k<N2; k++) { pc_cond_dims(N2, nx2, nu2, nb2, ng2, k, &pnz, &pnux, &pnb, &png, &cnx1, &cnux, &cng); hpBAbt2[k] = ptr; ptr += (size_t)pnz*cnx1; }
+	for(k=0; k<N2; k++) { pc_cond_dims(N2, nx2, nu2, nb2, ng2, k, &pnz, &pnux, &pnb, &png, &cnx1, &cnux, &cng); hpRSQrq2[k] = ptr; ptr += (size_t)pnz*cnux; }
+	for(k=0; k<N2; k++) { pc_cond_dims(N2, nx2, nu2, nb2, ng2, k, &pnz, &pnux, &pnb, &png, &cnx1, &cnux, &cng); hpDCt2[k] = ptr; ptr += (size_t)pnux*cng; }
+	for(k=0; k<N2; k++) { pc_cond_dims(N2, nx2, nu2, nb2, ng2, k, &pnz, &pnux, &pnb, &png, &cnx1, &cnux, &cng); hd2[k] = ptr; ptr += 2*pnb + 2*png; }
+	int *ip = (int*)ptr;
+	for(k=0; k<N2; k++) { hidxb2[k] = ip; ip += nb2[k]; for(j=0; j<nb2[k]; j++) hidxb2[k][j] = idx[k][j]; }
+	for(k=0; k<=N2; k++) free(idx[k]);
+	free(idx); free(t0); free(t1); free(t2); free(t3);
+	}
+	for(k=0; k<N2; k++)
+		{
+		int oB, oH, oD, oG, oDg, ngk, pnz, pnux, pnb, png, cnx1, cnux, cng;
+		const int nux2 = nu2[k]+nx2[k], nx1 = nx2[k+1];
+		pc_cond_dims(N2, nx2, nu2, nb2, ng2, k, &pnz, &pnux, &pnb, &png, &cnx1, &cnux, &cng);
+		hpmpc_b200_ocp_stage_offsets(cond, k, &oB, &oH, &oD, NULL, NULL, NULL, NULL);
+		hpmpc_b200_ocp_general_offsets(cond, k, &ngk, &oG, &oDg, NULL);
+		memset(hpBAbt2[k], 0, sizeof(double)*(size_t)pnz*cnx1); memset(hpRSQrq2[k], 0, sizeof(double)*(size_t)pnz*cnux);
+		memset(hpDCt2[k], 0, sizeof(double)*(size_t)pnux*cng); memset(hd2[k], 0, sizeof(double)*(2*pnb+2*png));
+		for(i=0; i<=nux2; i++) for(j=0; j<nx1; j++) PM(hpBAbt2[k], cnx1, i, j) = h2[oB+i*nx1+j];
+		for(i=0; i<nux2; i++) for(j=0; j<=i; j++) PM(hpRSQrq2[k], cnux, i, j) = h2[oH+HB_TRI(i)+j];
+		for(j=0; j<nux2; j++) PM(hpRSQrq2[k], cnux, nux2, j) = h2[oH+HB_TRI(nux2)+j];
+		for(i=0; i<nux2; i++) for(j=0; j<ng2[k]; j++) PM(hpDCt2[k], cng, i, j) = h2[oG+i*ng2[k]+j];
+		for(j=0; j<nb2[k]; j++) { hd2[k][j] = h2[oD+j]; hd2[k][pnb+j] = h2[oD+nb2[k]+j]; }
+		for(j=0; j<ng2[k]; j++) { hd2[k][2*pnb+j] = h2[oDg+j]; hd2[k][2*pnb+png+j] = h2[oDg+ng2[k]+j]; }
+		}
+	/* the last stage is shared with the full problem (d_part_cond.c:1058-1062) */
+	hpRSQrq2[N2] = hpRSQrq[N]; hpDCt2[N2] = hpDCt[N]; hd2[N2] = hd[N]; hidxb2[N2] = hidxb[N];
+	free(h2);
+	pthread_mutex_unlock(&g_lock);
+	}
+
+void d_part_expand_solution(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **hpBAbt, double **hb, double **hpRSQrq, double **hrq,
+		double **hpDCt, double **hux, double **hpi, double **hlam, double **ht, int N2, int *nx2, int *nu2, int *nb2, int **hidxb2, int *ng2,
+		double **hux2, double **hpi2, double **hlam2, double **ht2, void *work)
+	{
+	(void)work; (void)hidxb2;
+	int n, k, i;
+	if(N2>=N)
+		{
+		for(n=0; n<=N; n++)
+			{
+			const int nbn = nb[n], pnb = RUP(nbn, BS), ngn = ng[n], png = RUP(ngn, BS);
+			if(hux[n]!=hux2[n]) for(i=0; i<nu[n]+nx[n]; i++) hux[n][i] = hux2[n][i];
+			if(n<N && hpi[n]!=hpi2[n]) for(i=0; i<nx[n+1]; i++) hpi[n][i] = hpi2[n][i];
+			if(hlam[n]!=hlam2[n]) for(i=0; i<2*pnb+2*png; i++) { hlam[n][i] = hlam2[n][i]; ht[n][i] = ht2[n][i]; }
+			}
+		return;
+		}
+	pthread_mutex_lock(&g_lock);
+	if(pc_ctx_get(N, nx, nu, nb, hidxb, ng, N2, 1)) { pthread_mutex_unlock(&g_lock); fatal("d_part_expand_solution: GPU context unavailable"); }
+	hpmpc_b200_ocp *full = hpmpc_b200_pcond_full(GP.h), *cond = hpmpc_b200_pcond_cond(GP.h);
+	hpmpc_b200_sizes szc;
+	hpmpc_b200_ocp_sizes(cond, &szc);
+	pack_from_pmat_to(full, &GP.sz, GP.h_in, GP.ng, N, nx, nu, nb, hpBAbt, hpRSQrq, NULL, hpDCt);
+	for(n=0; n<=N; n++)
+		{
+		int oB, oH, nux = nu[n]+nx[n];
+		hpmpc_b200_ocp_stage_offsets(full, n, &oB, &oH, NULL, NULL, NULL, NULL, NULL);
+		if(n<N && hb) for(i=0; i<nx[n+1]; i++) GP.h_in[oB + (size_t)nux*nx[n+1] + i] = hb[n][i];
+		if(hrq) for(i=0; i<nux; i++) GP.h_in[oH + HB_TRI(nux) + i] = hrq[n][i];
+		}
+	const size_t lamc = (size_t)(szc.lam_stride>0 ? szc.lam_stride : 2), lamf = (size_t)(GP.sz.lam_stride>0 ? GP.sz.lam_stride : 2);
+	double *h_ux2 = calloc(szc.ux_stride, sizeof(double)), *h_pi2 = calloc(szc.pi_stride+2, sizeof(double));
+	double *h_lam2 = calloc(lamc, sizeof(double)), *h_t2 = calloc(lamc, sizeof(double)), *h_t = calloc(lamf, sizeof(double));
+	for(k=0; k<=N2; k++)
+		{
+		int oU, oP, oL;
+		const int nbk = nb2[k], pnb = RUP(nbk, BS), ngk = ng2[k], png = RUP(ngk, BS);
+		hpmpc_b200_ocp_stage_offsets(cond, k, NULL, NULL, NULL, &oU, &oP, &oL, NULL);
+		for(i=0; i<nu2[k]+nx2[k]; i++) h_ux2[oU+i] = hux2[k][i];
+		if(k<N2) for(i=0; i<nx2[k+1]; i++) h_pi2[oP+i] = hpi2[k][i];
+		for(i=0; i<nbk; i++) { h_lam2[oL+i] = hlam2[k][i]; h_lam2[oL+nbk+i] = hlam2[k][pnb+i]; h_t2[oL+i] = ht2[k][i]; h_t2[oL+nbk+i] = ht2[k][pnb+i]; }
+		for(i=0; i<ngk; i++)
+			{
+			h_lam2[oL+2*nbk+i] = hlam2[k][2*pnb+i]; h_lam2[oL+2*nbk+ngk+i] = hlam2[k][2*pnb+png+i];
+			h_t2[oL+2*nbk+i] = ht2[k][2*pnb+i]; h_t2[oL+2*nbk+ngk+i] = ht2[k][2*pnb+png+i];
+			}
+		}
+	double *d2 = NULL;
+	const size_t n2 = (size_t)szc.ux_stride + szc.pi_stride + 2 + 2*lamc;
+	int bad = !h_ux2 || !h_pi2 || !h_lam2 || !h_t2 || !h_t || cudaMalloc((void**)&d2, sizeof(double)*n2)!=cudaSuccess;
+	double *d_ux2 = d2, *d_pi2 = d2 ? d_ux2 + szc.ux_stride : NULL, *d_lam2 = d2 ? d_pi2 + szc.pi_stride + 2 : NULL, *d_t2 = d2 ? d_lam2 + lamc : NULL;
+	bad = bad || h2d(GP.d_in, GP.h_in, GP.sz.in_stride) || h2d(d_ux2, h_ux2, szc.ux_stride) || h2d(d_pi2, h_pi2, szc.pi_stride)
+		|| h2d(d_lam2, h_lam2, lamc) || h2d(d_t2, h_t2, lamc)
+		|| hpmpc_b200_d_part_expand_solution_batch(GP.h, 1, GP.d_in, d_ux2, d_pi2, d_lam2, d_t2, GP.d_ux, GP.d_pi, GP.d_lam, GP.d_t, NULL)
+		|| cudaDeviceSynchronize()!=cudaSuccess
+		|| d2h(GP.h_ux, GP.d_ux, GP.sz.ux_stride) || d2h(GP.h_pi, GP.d_pi, GP.sz.pi_stride)
+		|| (GP.sz.lam_stride>0 && (d2h(GP.h_lam, GP.d_lam, GP.sz.lam_stride) || d2h(h_t, GP.d_t, GP.sz.lam_stride)));
+	cudaFree(d2);
+	if(!bad)
+		for(n=0; n<=N; n++)
+			{
+			int oU, oP, oL;
+			const int nbn = nb[n], pnb = RUP(nbn, BS), ngn = ng[n], png = RUP(ngn, BS);
+			hpmpc_b200_ocp_stage_offsets(full, n, NULL, NULL, NULL, &oU, &oP, &oL, NULL);
+			for(i=0; i<nu[n]+nx[n]; i++) hux[n][i] = GP.h_ux[oU+i];
+			if(n<N) for(i=0; i<nx[n+1]; i++) hpi[n][i] = GP.h_pi[oP+i];
+			for(i=0; i<nbn; i++) { hlam[n][i] = GP.h_lam[oL+i]; hlam[n][pnb+i] = GP.h_lam[oL+nbn+i]; ht[n][i] = h_t[oL+i]; ht[n][pnb+i] = h_t[oL+nbn+i]; }
+			for(i=0; i<ngn; i++)
+				{
+				hlam[n][2*pnb+i] = GP.h_lam[oL+2*nbn+i]; hlam[n][2*pnb+png+i] = GP.h_lam[oL+2*nbn+ngn+i];
+				ht[n][2*pnb+i] = h_t[oL+2*nbn+i]; ht[n][2*pnb+png+i] = h_t[oL+2*nbn+ngn+i];
+				}
+			}
+	free(h_ux2); free(h_pi2); free(h_lam2); free(h_t2); free(h_t);
+	pthread_mutex_unlock(&g_lock);
+	if(bad) fatal("d_part_expand_solution: GPU execution failed");
 	}
 
 static int high_level(int c_order, int *kk, int k_max, double mu0, double mu_tol, int N, int *nx, int *nu, int *nb, int **hidxb,

@@ -68,10 +68,15 @@ void d_res_mpc_hard_tv(int N, int *nx, int *nu, int *nb, int **idxb, int *ng, do
 /* ---- high-level interface, dense stage-wise arrays : include/c_interface.h:59-67 ---- */
 /* include/c_interface.h:59  (interfaces/c/c_interface_work_space.c:70) */
 int hpmpc_d_ip_ocp_hard_tv_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2);
-/* reference include/lqcp_solvers.h:86: sizes of the partially condensed problem (N2 blocks).  The high-level symbols below condense
- * on the device when they are called with N2 < N; the panel-major d_part_cond / d_part_expand_solution pair itself is offered in
- * batched form only (hpmpc_b200.h: hpmpc_b200_d_part_cond_batch, hpmpc_b200_d_part_expand_solution_batch). */
+/* partial condensing, reference include/lqcp_solvers.h:86-95 (lqcp_solvers/d_part_cond.c:694, :739, :860, :926, :1072, :1103): panel-major
+ * (lib4) arguments as in the reference; the condensing and the expansion run on the device as a batch of one (batched forms:
+ * hpmpc_b200.h).  `memory` receives the condensed matrices, `work` is not used.  General constraints only at stage N. */
 void d_part_cond_compute_problem_size(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int *nx2, int *nu2, int *nb2, int *ng2);
+int d_part_cond_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int *nx2, int *nu2, int *nb2, int *ng2);
+int d_part_cond_memory_space_size_bytes(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int *nx2, int *nu2, int *nb2, int *ng2);
+void d_part_cond(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **hpBAbt, double **hpRSQrq, double **hpDCt, double **hd, int N2, int *nx2, int *nu2, int *nb2, int **hidxb2, int *ng2, double **hpBAbt2, double **hpRSQrq2, double **hpDCt2, double **hd2, void *memory, void *work);
+int d_part_expand_work_space_size_bytes(int N, int *nx, int *nu, int *nb, int *ng);
+void d_part_expand_solution(int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, double **hpBAbt, double **hb, double **hpRSQrq, double **hrq, double **hpDCt, double **hux, double **hpi, double **hlam, double **ht, int N2, int *nx2, int *nu2, int *nb2, int **hidxb2, int *ng2, double **hux2, double **hpi2, double **hlam2, double **ht2, void *work);
 /* include/c_interface.h:62  (interfaces/c/c_order_interface.c:53) row-major matrices */
 int c_order_d_ip_ocp_hard_tv(int *kk, int k_max, double mu0, double mu_tol,
                              int N, int *nx, int *nu, int *nb, int **hidxb, int *ng, int N2, int warm_start,

@@ -192,3 +192,61 @@ def test_gpu_condense_then_expand_of_the_uncondensed_solution_is_consistent():
     for i in range(64):
         for c in range(1, 64):
             assert np.array_equal(mg.cat(got[i]["u"]), mg.cat(got[i + 64 * c]["u"]))
+
+
+# ------------------------------------------------------------------------------------------- the lib4 routines themselves
+def _cmp_cond(a, b, tol=1e-11):
+    for k in ("nx2", "nu2", "nb2", "ng2"):
+        assert a[k] == b[k], k
+    for k in ("BAbt", "RSQrq", "DCt", "lb", "ub", "lg", "ug"):
+        for x, y in zip(a[k], b[k]):
+            assert x.shape == y.shape and (x.size == 0 or np.max(np.abs(x - y) / np.maximum(1.0, np.abs(y))) < tol), k
+    for x, y in zip(a["idxb"], b["idxb"]):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not oracle.have_reference(), reason="reference build not present")
+@pytest.mark.parametrize("shape,N2", [((8, 3, 10), 3), ((8, 3, 10), 1), ((12, 4, 10), 4), ((4, 2, 9), 2), ((6, 1, 8), 3), ((12, 5, 10), 5)])
+def test_gpu_lib4_d_part_cond_matches_reference_routine(shape, N2):
+    """d_part_cond through the drop-in library (device kernel behind panel-major arguments) against the reference's own routine:
+    every condensed matrix and vector, entry by entry.  (12,5) with two-stage blocks is the largest nu the reference gets right.)"""
+    nx, nu, N = shape
+    p = problems.mass_spring_ocp(nx, nu, N, bounds=True, xi=(0.3, -0.2, 0.5, 0.1))
+    ref = oracle.reference("c99").part_cond(p, N2)
+    got = capi.HpmpcLib(capi.PRODUCT_LIB).part_cond(p, N2)
+    _cmp_cond(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not oracle.have_reference(), reason="reference build not present")
+def test_gpu_lib4_d_part_cond_where_the_reference_is_wrong():
+    """nu = 5, blocks of four stages: the reference's condensed Hessian differs from the product's -- and it is the reference's that
+    does not reproduce the un-condensed optimum (tools/repro_part_cond_nu5.py); the dynamics and the constraints agree."""
+    p = problems.mass_spring_ocp(12, 5, 10, bounds=True, xi=(0.3, -0.2, 0.5, 0.1))
+    ref = oracle.reference("c99").part_cond(p, 3)
+    got = capi.HpmpcLib(capi.PRODUCT_LIB).part_cond(p, 3)
+    for k in ("BAbt", "DCt", "lb", "ub", "lg", "ug"):
+        for x, y in zip(got[k], ref[k]):
+            assert np.max(np.abs(x - y)) < 1e-11, k
+    assert max(np.max(np.abs(x - y)) for x, y in zip(got["RSQrq"], ref["RSQrq"])) > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not oracle.have_reference(), reason="reference build not present")
+@pytest.mark.parametrize("shape,N2", [((8, 3, 10), 3), ((12, 4, 10), 4), ((4, 2, 9), 2)])
+def test_gpu_lib4_d_part_expand_solution_matches_reference_routine(shape, N2):
+    """d_part_expand_solution on an arbitrary condensed point (not a solution: the map itself is compared), both libraries."""
+    nx, nu, N = shape
+    p = problems.mass_spring_ocp(nx, nu, N, bounds=True, xi=(0.1, 0.4, -0.5, 0.2))
+    R, G = oracle.reference("c99"), capi.HpmpcLib(capi.PRODUCT_LIB)
+    nx2, nu2, nb2, ng2, _ = capi.part_cond_sizes(p, N2)
+    rng = np.random.default_rng(5)
+    ux2 = [rng.standard_normal(nu2[k] + nx2[k]) for k in range(N2 + 1)]
+    pi2 = [rng.standard_normal(nx2[k + 1]) for k in range(N2)]
+    lam2 = [rng.random(2 * nb2[k] + 2 * ng2[k]) for k in range(N2 + 1)]
+    t2 = [rng.random(2 * nb2[k] + 2 * ng2[k]) + 0.5 for k in range(N2 + 1)]
+    a = G.part_cond(p, N2, expand_from=(ux2, pi2, lam2, t2))["expanded"]
+    b = R.part_cond(p, N2, expand_from=(ux2, pi2, lam2, t2))["expanded"]
+    for f in ("u", "x", "pi", "lam", "t"):
+        assert rel_err([mg.cat(a[f])], [mg.cat(b[f])]) < 1e-11, f
