@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) hb_cipm_sweep_kernel(hb_cipm_args a)
 		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst*a.work_stride);
 		const double *in_inst = a.in + inst*d.in_stride;
 		__syncwarp();
-		if(WHICH==0)
+		if constexpr(WHICH==0)
 			{
 			if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
 			const bool p2 = (st==CS_P2_SV);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) hb_cipm_sweep_kernel(hb_cipm_args a)
 			__syncwarp();
 			if(lane==0) si[0] = p2 ? CS_P2_A : CS_P1_A;
 			}
-		else if(WHICH==1)
+		else if constexpr(WHICH==1)
 			{
 			if(st!=CS_P1_TRS && st!=CS_P2_TRS) continue;
 			const bool p2 = (st==CS_P2_TRS);
@@ -395,6 +395,23 @@ template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 		}
 	};
 
+/* which sweep set runs the solve-only and residual kernels, and at what launch shape: the size-specialised sweeps have a
+ * single-slot twin (half the shared memory) that runs 16 warps per SM */
+template<class S> struct hb_cipm_light
+	{
+	typedef S type;
+	static bool use() { return false; }
+	static int smem(int) { return 0; }
+	};
+template<class C> struct hb_cipm_light<hb_sweeps_fast<C> >
+	{
+	typedef hb_sweeps_fast1<C> type;
+	static constexpr int WARPS = 8;
+	/* HPMPC_B200_IPM_LIGHT=0 keeps the double-buffered sweeps at 8 warps per SM (A/B runs) */
+	static bool use() { const char *e = getenv("HPMPC_B200_IPM_LIGHT"); return !(e && e[0]=='0') && 2*(smem(WARPS)+1024)<=233472; }
+	static int smem(int warps) { return warps*(int)sizeof(double)*hbi_cfg1<C>::PER_WARP; }
+	};
+
 /* ---------------------------------------------------------------------------------------------------------------- */
 template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &base, int *lists, int *counters, int grid_sweep, int warps_sweep,
 		int sms, cudaStream_t st)
@@ -408,6 +425,16 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 	if(hb_prep(hb_cipm_sweep_kernel<S, 0>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 1>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 2>, smem_sweep)) return -1;
 	const bool sv2 = hb_cipm_sv<S>::use();
 	if(sv2 && hb_cipm_sv<S>::prep(0)) return -1;
+	typedef typename hb_cipm_light<S>::type S1;
+	const bool light = hb_cipm_light<S>::use();
+	int smem_l = smem_sweep, warps_l = warps_sweep, grid_l = grid_sweep;
+	if(light)
+		{
+		warps_l = 8; smem_l = hb_cipm_light<S>::smem(warps_l);
+		long long need_l = (n + warps_l - 1)/warps_l;
+		grid_l = (int)(need_l < 2LL*sms ? (need_l<1 ? 1 : need_l) : 2LL*sms);
+		if(hb_prep(hb_cipm_sweep_kernel<S1, 1>, smem_l) || hb_prep(hb_cipm_sweep_kernel<S1, 2>, smem_l)) return -1;
+		}
 	int *act[2] = { lists, lists + n }, *cnt[2] = { counters, counters + 1 };
 	HB_CK(cudaMemsetAsync(a.si, 0, sizeof(int)*CIPM_I*(size_t)n, st));          /* every instance starts in CS_INIT */
 	HB_CK(cudaMemsetAsync(counters, 0, 2*sizeof(int), st));
@@ -416,7 +443,8 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 	hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
 	/* instances whose first loop test already fails (mu0 below the phase-1 threshold) want residuals before anything else */
 	a.act = act[0]; a.n_act = cnt[0]; a.act_next = nullptr; a.n_act_next = nullptr;
-	hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+	if(light) hb_cipm_sweep_kernel<S1, 2><<<grid_l, warps_l*32, smem_l, st>>>(a);
+	else hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 	hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
 	for(int r=0; r<a.k_max; r++)
 		{
@@ -425,9 +453,11 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 		if(sv2) hb_cipm_sv<S>::launch(a, sms, st);
 		else hb_cipm_sweep_kernel<S, 0><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
-		hb_cipm_sweep_kernel<S, 1><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+		if(light) hb_cipm_sweep_kernel<S1, 1><<<grid_l, warps_l*32, smem_l, st>>>(a);
+		else hb_cipm_sweep_kernel<S, 1><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
-		hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+		if(light) hb_cipm_sweep_kernel<S1, 2><<<grid_l, warps_l*32, smem_l, st>>>(a);
+		else hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		HB_CK(cudaMemsetAsync(cnt[nxt], 0, sizeof(int), st));
 		a.act_next = act[nxt]; a.n_act_next = cnt[nxt];
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);

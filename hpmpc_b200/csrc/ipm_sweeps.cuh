@@ -261,6 +261,32 @@ template<class S> __device__ __forceinline__ hb_ipm_ws hb_ipm_make_ws(const hb_d
 	return w;
 	}
 
+/* the same sweeps on the single-slot context (ric_ipm_fast.cuh: hbi_ctx1): solve-only and residual sweeps only, half the shared
+ * memory per warp -- what the multi-kernel driver launches at 16 warps per SM (cipm_kernels.cu) */
+template<class C>
+struct hb_sweeps_fast1 : hb_sweeps_fast<C>
+	{
+	typedef hbi_ctx1<C> ctx_t;
+	__device__ static __forceinline__ int smem_doubles(const hb_dims &) { return hbi_cfg1<C>::PER_WARP; }
+	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c.init(smem_warp, lane, d); }
+	__device__ static __forceinline__ void trs(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, const double *rqv, const double *qx)
+		{
+		hbi_trs_backward<C>(c, d, in_inst, w.L, rqv, qx, w.Pb, w.dux);
+		__syncwarp();
+		hbi_forward<C, true>(c, in_inst, w.L, bv, w.dux, w.dux, w.dpi);
+		}
+	__device__ static __forceinline__ void residuals(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *ux, const double *pi, double *mu, double *norms)
+		{
+		double mu2, nd, nq = 0.0, nb_ = 0.0;
+		hb_ipm_residuals_bounds(c.lane, d, w, ux, mu2, nd);
+		__syncwarp();
+		hbi_residuals<C>(c, d, in_inst, w.rq0, w.b0, w.v(CV_LAM_LO), w.v(CV_LAM_UP), ux, pi, w.res_q, w.res_b, nq, nb_);
+		if(d.nbtot>0) *mu = mu2/(2.0*d.nbtot);
+		if(norms!=nullptr) { norms[0] = hb_warp_max(nq); norms[1] = hb_warp_max(nb_); norms[2] = hb_warp_max(nd); }
+		}
+	};
 
 /* size-specialised IPM sweeps (ric_ipm_fast.cuh): one warp per instance, x0 eliminated, uniform (nx, nu) */
 typedef hbf_cfg<24, 11, 32> hbi_v0;    /* BASELINE config 3 */

@@ -31,6 +31,7 @@ struct hbi_cfg
 template<class C>
 struct hbi_ctx
 	{
+	static constexpr int SB = C::BAB;                   /* distance between the two [B A b]' slots of io */
 	int lane, N;
 	uint64_t *bars;
 	double *io, *Lb0, *Lb1, *us, *xs0, *xs1, *tmp, *va, *vb, *vc;
@@ -60,6 +61,63 @@ struct hbi_ctx
 	__device__ __forceinline__ int off_in(int n) const { return (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in); }
 	__device__ __forceinline__ int off_ux(int n) const { return (n==0) ? 0 : C::NU + (n-1)*C::NUX; }
 	/* generic -> async proxy ordering before a buffer this warp has written or read is refilled by a bulk copy */
+	__device__ __forceinline__ void sync() { __syncwarp(); }
+	};
+
+/* The same interface with ONE slot per kind of stage data: half the shared memory (14 instead of 27 KB per warp at config 3), so
+ * the solve-only and residual sweeps of the multi-kernel driver run 16 warps per SM.  load() only records the request; the bulk
+ * copy is issued by wait(), i.e. when the previous stage's data is dead -- nothing is prefetched inside a warp, the other warps of
+ * the SM cover the latency (the sweeps keep their two-stage-ahead issue order, which is what makes two records per kind enough). */
+template<class C>
+struct hbi_cfg1
+	{
+	static constexpr int VZ = C::even(C::NZ);
+	static constexpr int PER_WARP = 8 + C::BAB + C::LBUF + C::even(C::NU) + 3*C::XS + 3*VZ;
+	static_assert(C::even(HB_TRI(C::NUX)+C::NUX)<=C::LBUF, "a Hessian block must fit the factor buffer (residual sweep)");
+	};
+template<class C>
+struct hbi_ctx1
+	{
+	static constexpr int SB = 0;
+	int lane, N;
+	uint64_t *bars;
+	double *io, *Lb0, *Lb1, *us, *xs0, *xs1, *tmp, *va, *vb, *vc;
+	uint32_t phase;
+	int o_in1, s_in, o_inN;
+	const double *p_src0, *p_src1, *p_src2, *p_src3;    /* recorded requests, one per barrier */
+	uint32_t p_b0, p_b1, p_b2, p_b3;
+	__device__ __forceinline__ void init(double *wbase, int lane_, const hb_dims &d)
+		{
+		lane = lane_; N = d.N;
+		bars = reinterpret_cast<uint64_t*>(wbase);
+		io = wbase + 8; Lb0 = io + C::BAB; Lb1 = Lb0;
+		us = Lb0 + C::LBUF; xs0 = us + C::even(C::NU); xs1 = xs0 + C::XS; tmp = xs1 + C::XS;
+		va = tmp + C::XS; vb = va + hbi_cfg1<C>::VZ; vc = vb + hbi_cfg1<C>::VZ;
+		phase = 0;
+		o_in1 = d.st[1].off_BAbt; s_in = d.st[2].off_BAbt - d.st[1].off_BAbt; o_inN = d.st[N].off_BAbt;
+		p_src0 = p_src1 = p_src2 = p_src3 = nullptr; p_b0 = p_b1 = p_b2 = p_b3 = 0;
+		if(lane==0)
+			{
+			for(int b=0; b<4; b++) hbf_mbar_init(&bars[b], 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			}
+		__syncwarp();
+		}
+	__device__ __forceinline__ void load(int b, double *, const double *src, uint32_t bytes)
+		{
+		if(b==0) { p_src0 = src; p_b0 = bytes; } else if(b==1) { p_src1 = src; p_b1 = bytes; }
+		else if(b==2) { p_src2 = src; p_b2 = bytes; } else { p_src3 = src; p_b3 = bytes; }
+		}
+	__device__ __forceinline__ void wait(int b)
+		{
+		const double *src = (b==0) ? p_src0 : (b==1 ? p_src1 : (b==2 ? p_src2 : p_src3));
+		const uint32_t bytes = (b==0) ? p_b0 : (b==1 ? p_b1 : (b==2 ? p_b2 : p_b3));
+		__syncwarp();                                   /* every lane is done with the data this copy replaces */
+		if(lane==0) { hbf_mbar_expect(&bars[b], bytes); hbf_bulk_g2s(b<2 ? io : Lb0, src, bytes, &bars[b]); }
+		hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b);
+		}
+	__device__ __forceinline__ int off_in(int n) const { return (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in); }
+	__device__ __forceinline__ int off_ux(int n) const { return (n==0) ? 0 : C::NU + (n-1)*C::NUX; }
 	__device__ __forceinline__ void sync() { __syncwarp(); }
 	};
 
@@ -161,13 +219,13 @@ __device__ void hbi_backward(hbi_ctx<C> &c, const hb_dims &d, const double *__re
 /* forward sweep n = 0..N-1 (+ pi of the last edge).  TRS: w (ux layout, may alias ux) holds the       */
 /* eliminated right-hand side of hbi_trs_backward: l_u := w_n[:nu], p := x-part of w_n                 */
 /* ------------------------------------------------------------------------------------------------ */
-template<class C, bool TRS>
-__device__ void hbi_forward(hbi_ctx<C> &c, const double *__restrict__ in_inst, const double *__restrict__ Lst,
+template<class C, bool TRS, class X>
+__device__ void hbi_forward(X &c, const double *__restrict__ in_inst, const double *__restrict__ Lst,
 		const double *bv, const double *w, double *ux, double *pi)
 	{
-	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, NZ = C::NZ, LBUF = C::LBUF, BAB = C::BAB;
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, NZ = C::NZ, LBUF = C::LBUF;
 	const int l = c.lane, N = c.N;
-	auto issue_B = [&](int n) { c.load(n&1, c.io + (n&1)*BAB, in_inst + c.off_in(n), hbi_bytes_BAbt<C>(n==0)); };
+	auto issue_B = [&](int n) { c.load(n&1, c.io + (n&1)*X::SB, in_inst + c.off_in(n), hbi_bytes_BAbt<C>(n==0)); };
 	auto issue_L = [&](int n) { c.load(2+(n&1), (n&1) ? c.Lb1 : c.Lb0, Lst + (long long)n*LBUF, 8u*LBUF); };
 	issue_L(0); issue_B(0);
 	issue_L(1); if(N>1) issue_B(1);
@@ -183,7 +241,7 @@ __device__ void hbi_forward(hbi_ctx<C> &c, const double *__restrict__ in_inst, c
 		{
 		const bool first = (n==0);
 		const double *Ln = (n&1) ? c.Lb1 : c.Lb0;
-		double *sB = c.io + (n&1)*BAB;
+		double *sB = c.io + (n&1)*X::SB;
 		const double *xs = (n&1) ? c.xs1 : c.xs0;
 		double *xo = (n&1) ? c.xs0 : c.xs1;
 		const int brow = first ? NU : NUX;
@@ -284,13 +342,13 @@ __device__ void hbi_forward(hbi_ctx<C> &c, const double *__restrict__ in_inst, c
 /* ------------------------------------------------------------------------------------------------ */
 /* solve-only backward vector sweep: w_n = L-eliminated( rq_n (+qx) + [B A]'(Pb_n + w_{n+1,x}) ) -> wv  */
 /* ------------------------------------------------------------------------------------------------ */
-template<class C>
-__device__ void hbi_trs_backward(hbi_ctx<C> &c, const hb_dims &d, const double *__restrict__ in_inst, const double *__restrict__ Lst,
+template<class C, class X>
+__device__ void hbi_trs_backward(X &c, const hb_dims &d, const double *__restrict__ in_inst, const double *__restrict__ Lst,
 		const double *rqv, const double *qx, const double *Pb, double *wv)
 	{
-	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF, BAB = C::BAB;
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF;
 	const int l = c.lane, N = c.N;
-	auto issue_B = [&](int n) { c.load(n&1, c.io + (n&1)*BAB, in_inst + c.off_in(n), hbi_bytes_BAbt<C>(n==0)); };
+	auto issue_B = [&](int n) { c.load(n&1, c.io + (n&1)*X::SB, in_inst + c.off_in(n), hbi_bytes_BAbt<C>(n==0)); };
 	auto issue_L = [&](int n) { c.load(2+(n&1), (n&1) ? c.Lb1 : c.Lb0, Lst + (long long)n*LBUF, 8u*LBUF); };
 	issue_L(N-1); issue_B(N-1);
 	if(N>1) { issue_L(N-2); issue_B(N-2); }
@@ -306,7 +364,7 @@ __device__ void hbi_trs_backward(hbi_ctx<C> &c, const hb_dims &d, const double *
 		{
 		const bool first = (n==0);
 		const double *Ln = (n&1) ? c.Lb1 : c.Lb0;
-		const double *sB = c.io + (n&1)*BAB;
+		const double *sB = c.io + (n&1)*X::SB;
 		const int nux = first ? NU : NUX, o = c.off_ux(n), o1 = c.off_ux(n+1) + ((n+1<N) ? NU : 0);
 		const hb_stage s = d.st[n];
 		for(int i=l; i<nux; i+=32) c.va[i] = rqv[o+i];
@@ -514,18 +572,18 @@ __device__ void hbi_Pb_sweep(hbi_ctx<C> &c, const double *__restrict__ in_inst, 
 /*   rq0, b0 : original gradient / b (ux / pi layout) ; lamd = lam_up - lam_lo per bound (nbtot)       */
 /*   returns max |res_q|, max |res_b| over the lanes' entries (caller reduces)                          */
 /* ------------------------------------------------------------------------------------------------ */
-template<class C>
-__device__ void hbi_residuals(hbi_ctx<C> &c, const hb_dims &d, const double *__restrict__ in_inst, const double *rq0, const double *b0,
+template<class C, class X>
+__device__ void hbi_residuals(X &c, const hb_dims &d, const double *__restrict__ in_inst, const double *rq0, const double *b0,
 		const double *lam_lo, const double *lam_up, const double *ux, const double *pi, double *res_q, double *res_b,
 		double &nq, double &nb_)
 	{
-	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, BAB = C::BAB;
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX;
 	const int l = c.lane, N = c.N;
 	auto issue = [&](int n)
 		{
 		const int kind = (n==0) ? HBF_FIRST : (n==N ? HBF_LAST : HBF_MID);
 		const uint32_t bB = (n<N) ? hbi_bytes_BAbt<C>(n==0) : 0u;
-		if(n<N) c.load(n&1, c.io + (n&1)*BAB, in_inst + c.off_in(n), bB);
+		if(n<N) c.load(n&1, c.io + (n&1)*X::SB, in_inst + c.off_in(n), bB);
 		c.load(2+(n&1), (n&1) ? c.Lb1 : c.Lb0, in_inst + c.off_in(n) + bB/8, hbi_bytes_RSQ<C>(kind));
 		};
 	issue(0); issue(1);
@@ -533,7 +591,7 @@ __device__ void hbi_residuals(hbi_ctx<C> &c, const hb_dims &d, const double *__r
 		{
 		const int nu = (n==N) ? 0 : NU, nux = (n==0) ? NU : (n==N ? NX : NUX);
 		const int o = c.off_ux(n), o1 = c.off_ux(n+1) + ((n+1<N) ? NU : 0);
-		const double *sB = c.io + (n&1)*BAB;
+		const double *sB = c.io + (n&1)*X::SB;
 		const double *H = (n&1) ? c.Lb1 : c.Lb0;
 		const hb_stage s = d.st[n];
 		for(int i=l; i<nux; i+=32)
