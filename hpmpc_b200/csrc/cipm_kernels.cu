@@ -291,6 +291,15 @@ __global__ void __launch_bounds__(256) hb_cipm_sweep_kernel(hb_cipm_args a)
 			__syncwarp();
 			if(lane==0) si[0] = p2 ? CS_P2_A : CS_P1_A;
 			}
+		else if constexpr(WHICH==3)
+			{
+			/* forward sweep of the predictor, after a factorisation-only hb_cipm_sv2_kernel */
+			if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
+			const bool p2 = (st==CS_P2_SV);
+			S::forward_sv(c, d, in_inst, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+			__syncwarp();
+			if(lane==0) si[0] = p2 ? CS_P2_A : CS_P1_A;
+			}
 		else if constexpr(WHICH==1)
 			{
 			if(st!=CS_P1_TRS && st!=CS_P2_TRS) continue;
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(256) hb_cipm_sweep_kernel(hb_cipm_args a)
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* factor + solve (predictor) with the register-blocked factorisation sweep of ric_ipm_blk.cuh: two instances per warp.  The    */
 /* forward sweep that follows is the one-instance-per-warp routine, run for the two instances in turn on their own regions.     */
-template<class C>
+template<class C, bool FWD>
 __global__ void __launch_bounds__(128, 1) hb_cipm_sv2_kernel(hb_cipm_args a)
 	{
 	typedef hb_sweeps_fast<C> S;
@@ -350,24 +359,28 @@ __global__ void __launch_bounds__(128, 1) hb_cipm_sv2_kernel(hb_cipm_args a)
 		hbi2_backward<C>(c2, d, a.in + inst*d.in_stride, w.L, p2 ? w.res_b : nullptr, p2 ? w.res_q : nullptr, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
 		}
 		__syncwarp();
-		{
-		const bool p2 = (st0==CS_P2_SV);
-		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst0*a.work_stride);
-		S::forward_sv(c0, d, a.in + inst0*d.in_stride, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
-		}
-		if(inst1!=inst0)
+		if constexpr(FWD)
 			{
-			const bool p2 = (st1==CS_P2_SV);
-			const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst1*a.work_stride);
+			{
+			const bool p2 = (st0==CS_P2_SV);
+			const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst0*a.work_stride);
+			S::forward_sv(c0, d, a.in + inst0*d.in_stride, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+			}
+			if(inst1!=inst0)
+				{
+				const bool p2 = (st1==CS_P2_SV);
+				const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst1*a.work_stride);
+				__syncwarp();
+				S::forward_sv(c1, d, a.in + inst1*d.in_stride, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+				}
 			__syncwarp();
-			S::forward_sv(c1, d, a.in + inst1*d.in_stride, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+			if(lane==0)
+				{
+				a.si[inst0*CIPM_I] = (st0==CS_P2_SV) ? CS_P2_A : CS_P1_A;
+				if(inst1!=inst0) a.si[inst1*CIPM_I] = (st1==CS_P2_SV) ? CS_P2_A : CS_P1_A;
+				}
 			}
-		__syncwarp();
-		if(lane==0)
-			{
-			a.si[inst0*CIPM_I] = (st0==CS_P2_SV) ? CS_P2_A : CS_P1_A;
-			if(inst1!=inst0) a.si[inst1*CIPM_I] = (st1==CS_P2_SV) ? CS_P2_A : CS_P1_A;
-			}
+		/* !FWD: the state stays *_SV; the forward kernel (hb_cipm_sweep_kernel<S1, 3>, 16 warps per SM) picks the instance up */
 		__syncwarp();
 		}
 	}
@@ -377,21 +390,22 @@ template<class S> struct hb_cipm_sv
 	{
 	static int prep(int) { return 0; }
 	static bool use() { return false; }
-	static void launch(const hb_cipm_args &, int, cudaStream_t) {}
+	static void launch(const hb_cipm_args &, int, cudaStream_t, bool) {}
 	};
 template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 	{
 	typedef hbi_v0 C;
 	static constexpr int WARPS = 4;
 	static int smem() { return WARPS*(int)sizeof(double)*hbi2_cfg<C>::PER_WARP; }
-	static int prep(int) { return hb_prep(hb_cipm_sv2_kernel<C>, smem()); }
+	static int prep(int) { return hb_prep(hb_cipm_sv2_kernel<C, true>, smem()) || hb_prep(hb_cipm_sv2_kernel<C, false>, smem()); }
 	/* HPMPC_B200_IPM_SV2=0 keeps the one-instance-per-warp sweep (A/B runs) */
 	static bool use() { const char *e = getenv("HPMPC_B200_IPM_SV2"); return !(e && e[0]=='0'); }
-	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st)
+	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st, bool fwd)
 		{
 		long long need = (a.n_inst + 2*WARPS - 1)/(2*WARPS);
 		const int grid = (int)(need<sms ? (need<1 ? 1 : need) : sms);
-		hb_cipm_sv2_kernel<C><<<grid, WARPS*32, smem(), st>>>(a);
+		if(fwd) hb_cipm_sv2_kernel<C, true><<<grid, WARPS*32, smem(), st>>>(a);
+		else hb_cipm_sv2_kernel<C, false><<<grid, WARPS*32, smem(), st>>>(a);
 		}
 	};
 
@@ -433,8 +447,10 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 		warps_l = 8; smem_l = hb_cipm_light<S>::smem(warps_l);
 		long long need_l = (n + warps_l - 1)/warps_l;
 		grid_l = (int)(need_l < 2LL*sms ? (need_l<1 ? 1 : need_l) : 2LL*sms);
-		if(hb_prep(hb_cipm_sweep_kernel<S1, 1>, smem_l) || hb_prep(hb_cipm_sweep_kernel<S1, 2>, smem_l)) return -1;
+		if(hb_prep(hb_cipm_sweep_kernel<S1, 1>, smem_l) || hb_prep(hb_cipm_sweep_kernel<S1, 2>, smem_l) || hb_prep(hb_cipm_sweep_kernel<S1, 3>, smem_l)) return -1;
 		}
+	/* the predictor's forward sweep leaves the two-instances-per-warp kernel (4 warps per SM) for the 16-warp launch shape */
+	const bool split_fw = sv2 && light;
 	int *act[2] = { lists, lists + n }, *cnt[2] = { counters, counters + 1 };
 	HB_CK(cudaMemsetAsync(a.si, 0, sizeof(int)*CIPM_I*(size_t)n, st));          /* every instance starts in CS_INIT */
 	HB_CK(cudaMemsetAsync(counters, 0, 2*sizeof(int), st));
@@ -450,8 +466,9 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 		{
 		const int cur = r&1, nxt = cur^1;
 		a.act = act[cur]; a.n_act = cnt[cur]; a.act_next = nullptr; a.n_act_next = nullptr;
-		if(sv2) hb_cipm_sv<S>::launch(a, sms, st);
+		if(sv2) hb_cipm_sv<S>::launch(a, sms, st, !split_fw);
 		else hb_cipm_sweep_kernel<S, 0><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
+		if(split_fw) hb_cipm_sweep_kernel<S1, 3><<<grid_l, warps_l*32, smem_l, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
 		if(light) hb_cipm_sweep_kernel<S1, 1><<<grid_l, warps_l*32, smem_l, st>>>(a);
 		else hb_cipm_sweep_kernel<S, 1><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);

@@ -269,6 +269,9 @@ struct hb_sweeps_fast1 : hb_sweeps_fast<C>
 	typedef hbi_ctx1<C> ctx_t;
 	__device__ static __forceinline__ int smem_doubles(const hb_dims &) { return hbi_cfg1<C>::PER_WARP; }
 	__device__ static __forceinline__ void init(ctx_t &c, const hb_dims &d, double *smem_warp, int lane) { c.init(smem_warp, lane, d); }
+	__device__ static __forceinline__ void forward_sv(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+			const double *bv, double *ux, double *pi)
+		{ hbi_forward<C, false>(c, in_inst, w.L, bv, nullptr, ux, pi); }
 	__device__ static __forceinline__ void trs(ctx_t &c, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
 			const double *bv, const double *rqv, const double *qx)
 		{
