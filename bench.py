@@ -339,9 +339,10 @@ def run_ours(args):
             ipm_traffic_wave = None
         multi = h.sz.ipm_fast_variant >= 0 and n >= 2 * wave and os.environ.get("HPMPC_B200_IPM_FUSED", "0") != "1"
         if multi:
-            # multi-kernel driver (cipm_kernels.cu): 3 launches up front, then k_max rounds of sv, step, trs, step, res, step
-            n_launch, kern = 3 + 6 * k_max, ("multi-kernel driver, k_max rounds enqueued: hb_cipm_sv2_kernel<24,11> (factor+solve, two instances per warp; ~50 % "
-                                             "of an iteration) + hb_cipm_sweep_kernel<trs> + <res> + 3 x hb_cipm_step_kernel")
+            # multi-kernel driver (cipm_kernels.cu): 3 launches up front, then k_max rounds of factorisation, forward, step, trs, step, res, step
+            split = os.environ.get("HPMPC_B200_IPM_SV2", "1") != "0" and os.environ.get("HPMPC_B200_IPM_LIGHT", "1") != "0" and h.sz.ipm_fast_variant == 0
+            n_launch, kern = 3 + (7 if split else 6) * k_max, ("multi-kernel driver, k_max rounds enqueued: hb_cipm_sv2_kernel<24,11> (factorisation, two instances per warp; "
+                                                               "~50 % of an iteration) + hb_cipm_sweep_kernel<forward> + <trs> + <res> (16 warps/SM) + 3 x hb_cipm_step_kernel")
             try:
                 ipm_traffic_wave = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("hb_cipm_sv2_bytes_per_launch") if h.sz.ipm_fast_variant == 0 else None
             except Exception:
