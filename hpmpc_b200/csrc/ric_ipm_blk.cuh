@@ -27,6 +27,11 @@ struct hbi2_cfg
 	typedef hbk_cfg<C::NX, C::NU, 16, 2> K;
 	static constexpr int PW = hbi_cfg<C>::PER_WARP;                    /* one instance's region: the layout of hbi_ctx */
 	static constexpr int PER_WARP = 2*PW;
+	/* factorisation-only kernel (the forward sweep runs elsewhere): stage inputs / W, ONE factor buffer, the x-columns of the
+	 * previous stage's factor, Lxx'b -- 21 instead of 27 KB per instance, five warps per SM */
+	static constexpr int XC = K::xOff(C::NX);
+	static constexpr int PWS = C::even(C::INB) + C::LBUF + XC + C::XS;
+	static constexpr int PER_WARP_SLIM = 8 + 2*PWS;
 	static_assert(K::uOff(C::NU)==C::colOff(C::NU) && K::uOff(C::NU)+K::xOff(C::NX-1)==C::colOff(C::NUX-1), "column layouts must agree");
 	static_assert(C::BAB>=K::NZ*K::NX, "W (leading dimension NX) must fit over [B A b]'");
 	static_assert(K::RO==K::GR && K::E>0, "every lane slot owns a row; the gradient row is column-owned");
@@ -380,20 +385,21 @@ __device__ __forceinline__ void hbi2_factor(const hbk_lane<K> &ln, hbk_tile<K> &
 /* ---- the sweep: two instances per warp.  wbase: the warp's shared memory, two regions of hbi2_cfg::PW doubles in the layout of
  *      hbi_ctx (so the forward sweep of ric_ipm_fast.cuh can follow on either region); every pointer argument is the lane's own
  *      instance's (lanes 0-15: instance 0, lanes 16-31: instance 1), null rqv / bv per instance allowed ---- */
-template<class C>
+template<class C, bool SLIM = false>
 struct hbi2_ctx
 	{
+	static constexpr int RS = SLIM ? hbi2_cfg<C>::PWS : hbi2_cfg<C>::PW;    /* distance between the two instances' regions */
 	int lane, l, g, N;
 	uint64_t *bar;
 	uint32_t ph;
-	double *wbase, *io, *Lb0, *Lb1, *tmp;
+	double *wbase, *io, *Lb0, *Lb1, *tmp, *xp;
 	int o_in1, s_in, o_inN;
 	__device__ __forceinline__ void init(double *wbase_, int lane_, const hb_dims &d)
 		{
 		lane = lane_; l = lane_&15; g = lane_>>4; N = d.N; wbase = wbase_;
-		double *own = wbase_ + (size_t)g*hbi2_cfg<C>::PW;
-		io = own + 8; Lb0 = io + C::IOB; Lb1 = Lb0 + C::LBUF;
-		tmp = Lb1 + C::LBUF + C::even(C::NU) + 2*C::XS;
+		io = wbase_ + 8 + (size_t)g*RS;
+		if(SLIM) { Lb0 = io + C::even(C::INB); Lb1 = Lb0; xp = Lb0 + C::LBUF; tmp = xp + hbi2_cfg<C>::XC; }
+		else { Lb0 = io + C::IOB; Lb1 = Lb0 + C::LBUF; xp = nullptr; tmp = Lb1 + C::LBUF + C::even(C::NU) + 2*C::XS; }
 		bar = reinterpret_cast<uint64_t*>(wbase_) + 4;            /* slots 0..3 belong to the hbi_ctx of region 0 */
 		ph = 0;
 		o_in1 = d.st[1].off_BAbt; s_in = d.st[2].off_BAbt - d.st[1].off_BAbt; o_inN = d.st[N].off_BAbt;
@@ -404,12 +410,12 @@ struct hbi2_ctx
 	__device__ __forceinline__ int off_ux(int n) const { return (n==0) ? 0 : C::NU + (n-1)*C::NUX; }
 	};
 
-template<class C>
-__device__ void hbi2_backward(hbi2_ctx<C> &c, const hb_dims &d, const double *__restrict__ in_inst, double *__restrict__ Lst,
+template<class C, bool SLIM>
+__device__ void hbi2_backward(hbi2_ctx<C, SLIM> &c, const hb_dims &d, const double *__restrict__ in_inst, double *__restrict__ Lst,
 		const double *bv, const double *rqv, const double *Qx, const double *qx, double *Pb)
 	{
 	typedef typename hbi2_cfg<C>::K K;
-	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF, BAB = C::BAB, PW = hbi2_cfg<C>::PW;
+	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF, BAB = C::BAB, PW = hbi2_ctx<C, SLIM>::RS;
 	const int lane = c.lane, l = c.l, N = c.N;
 	hbk_lane<K> ln; ln.init(l);
 	int co[2] = {0, 0};                                                  /* offsets of the two factor columns this lane finishes */
@@ -451,6 +457,7 @@ __device__ void hbi2_backward(hbi2_ctx<C> &c, const hb_dims &d, const double *__
 		const int nux = (n==0) ? NU : (n==N ? NX : NUX), brow = (n==0) ? NU : NUX;
 		double *Lc = (n&1) ? c.Lb1 : c.Lb0;
 		const double *Lp = (n&1) ? c.Lb0 : c.Lb1;
+		const double *xc = SLIM ? c.xp : Lp + C::colOff(NU);             /* x-columns of the factor of stage n+1 */
 		hbf_mbar_wait(c.bar, c.ph&1); c.ph ^= 1u;
 		/* ---- hooks: new right-hand sides, barrier terms of the IPM (all global loads first: one round trip, not two) ---- */
 		{
@@ -480,9 +487,9 @@ __device__ void hbi2_backward(hbi2_ctx<C> &c, const hb_dims &d, const double *__
 		}
 		__syncwarp();
 		hbk_tile<K> T;
-		if(n==N) hbi2_assemble<K, HBF_LAST>(ln, c.io, sQ, Lp + C::colOff(NU), T, c.tmp);
-		else if(n==0) hbi2_assemble<K, HBF_FIRST>(ln, c.io, sQ, Lp + C::colOff(NU), T, c.tmp);
-		else hbi2_assemble<K, HBF_MID>(ln, c.io, sQ, Lp + C::colOff(NU), T, c.tmp);
+		if(n==N) hbi2_assemble<K, HBF_LAST>(ln, c.io, sQ, xc, T, c.tmp);
+		else if(n==0) hbi2_assemble<K, HBF_FIRST>(ln, c.io, sQ, xc, T, c.tmp);
+		else hbi2_assemble<K, HBF_MID>(ln, c.io, sQ, xc, T, c.tmp);
 		/* ---- Pb_n = Lxx (Lxx' b) with Lxx of stage n+1; Lxx' b came out of the assembly (the b-row of W before l_x is added) ---- */
 		if(n<N && Pb!=nullptr)
 			{
@@ -496,15 +503,16 @@ __device__ void hbi2_backward(hbi2_ctx<C> &c, const hb_dims &d, const double *__
 					#pragma unroll
 					for(int cc=0; cc<NX; cc+=2)
 						{
-						if(cc<=r) p0 = fma(Lp[C::colOff(NU+cc) + (r-cc)], c.tmp[cc], p0);
-						if(cc+1<=r) p1 = fma(Lp[C::colOff(NU+cc+1) + (r-cc-1)], c.tmp[cc+1], p1);
+						if(cc<=r) p0 = fma(xc[K::xOff(cc) + (r-cc)], c.tmp[cc], p0);
+						if(cc+1<=r) p1 = fma(xc[K::xOff(cc+1) + (r-cc-1)], c.tmp[cc+1], p1);
 						}
 					Pb[n*NX+r] = p0 + p1;
 					}
 				}
 			}
 		if(n>0) issue(n-1);
-		if(lane==0) hbf_bulk_wait_read<1>();
+		/* the factor buffer about to be overwritten must have left for HBM: the store before last (two buffers), the last one (one) */
+		if(lane==0) { if(SLIM) hbf_bulk_wait_read<0>(); else hbf_bulk_wait_read<1>(); }
 		__syncwarp();
 		hbi2_factor<C, K>(ln, T, Lc, co);
 		hbf_fence_async();
@@ -515,6 +523,13 @@ __device__ void hbi2_backward(hbi2_ctx<C> &c, const hb_dims &d, const double *__
 			hbf_bulk_s2g(Lst + (long long)n*LBUF, io0 + lo, 8u*LBUF);
 			hbf_bulk_s2g(Lst_o + (long long)n*LBUF, io1 + lo, 8u*LBUF);
 			hbf_bulk_commit();
+			}
+		if(SLIM && n>0)
+			{
+			/* the next stage needs the x-columns only: keep a copy, the factor buffer is reused */
+			const double *src = Lc + C::colOff(NU);
+			for(int i=2*l; i<hbi2_cfg<C>::XC; i+=32) *reinterpret_cast<double2*>(c.xp + i) = *reinterpret_cast<const double2*>(src + i);
+			__syncwarp();
 			}
 		}
 	if(lane==0) hbf_bulk_wait_all<0>();
