@@ -30,7 +30,12 @@ struct hbi2_cfg
 	/* factorisation-only kernel (the forward sweep runs elsewhere): stage inputs / W, ONE factor buffer, the x-columns of the
 	 * previous stage's factor, Lxx'b -- 21 instead of 27 KB per instance, five warps per SM */
 	static constexpr int XC = K::xOff(C::NX);
-	static constexpr int PWS = C::even(C::INB) + C::LBUF + XC + C::XS;
+	/* W with leading dimension NX+2: the one-row-per-lane LDS.128 / STS.128 of the own rows are conflict-free (192-byte rows put
+	 * four lanes of a quarter-warp on the same banks); W then runs past [B A b]', so the Hessian is fetched behind it */
+	static constexpr int LDWS = ((C::even(C::NX)/2)%2==0) ? C::even(C::NX)+2 : C::even(C::NX);
+	static constexpr int QOFF = C::even(K::NZ*LDWS);
+	static constexpr int IOS = QOFF + C::even(HB_TRI(C::NUX)+C::NUX);
+	static constexpr int PWS = IOS + C::LBUF + XC + C::XS;
 	static constexpr int PER_WARP_SLIM = 8 + 2*PWS;
 	static_assert(K::uOff(C::NU)==C::colOff(C::NU) && K::uOff(C::NU)+K::xOff(C::NX-1)==C::colOff(C::NUX-1), "column layouts must agree");
 	static_assert(C::BAB>=K::NZ*K::NX, "W (leading dimension NX) must fit over [B A b]'");
@@ -38,7 +43,7 @@ struct hbi2_cfg
 	};
 
 /* ---- H <- RSQrq_n + W W',  W = [B A b]'_n Lxx_{n+1}.  sBW: [B A b]' in, W (ld NX) out; sQ: RSQrq, NOT overlapping W ---- */
-template<class K, int KIND>
+template<class K, int KIND, int LDW>
 __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__restrict__ sBW, const double *__restrict__ sQ,
 		const double *__restrict__ xc, hbk_tile<K> &T, double *__restrict__ lxb /* out: Lxx' b (NX), needs E > 0 */)
 	{
@@ -107,7 +112,7 @@ __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__r
 				if(v<NX)
 					{
 					#pragma unroll
-					for(int e=0; e<E; e++) sBW[(RO+e)*NX + v] = wx[e][s];
+					for(int e=0; e<E; e++) sBW[(RO+e)*LDW + v] = wx[e][s];
 					}
 				}
 			}
@@ -143,7 +148,7 @@ __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__r
 					}
 				}
 			#pragma unroll
-			for(int s=0; s<R; s++) *reinterpret_cast<double2*>(sBW + (l+s*G)*NX + j) = make_double2(wj[s][0], wj[s][1]);
+			for(int s=0; s<R; s++) *reinterpret_cast<double2*>(sBW + (l+s*G)*LDW + j) = make_double2(wj[s][0], wj[s][1]);
 			}
 		}
 	/* ---- H <- RSQrq ---- */
@@ -207,7 +212,7 @@ __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__r
 		#pragma unroll
 		for(int s=0; s<R; s++)
 			{
-			wo[s] = *reinterpret_cast<const double2*>(sW + (l+s*G)*NX + m);
+			wo[s] = *reinterpret_cast<const double2*>(sW + (l+s*G)*LDW + m);
 			T.hd[s] = fma(wo[s].x, wo[s].x, T.hd[s]);
 			T.hd[s] = fma(wo[s].y, wo[s].y, T.hd[s]);
 			}
@@ -216,7 +221,7 @@ __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__r
 			{
 			double2 t[4];
 			#pragma unroll
-			for(int q=0; q<4; q++) if(k4+q<K::KS) t[q] = *reinterpret_cast<const double2*>(sW + (k4+q)*NX + m);
+			for(int q=0; q<4; q++) if(k4+q<K::KS) t[q] = *reinterpret_cast<const double2*>(sW + (k4+q)*LDW + m);
 			#pragma unroll
 			for(int q=0; q<4; q++)
 				#pragma unroll
@@ -232,7 +237,7 @@ __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__r
 			{
 			double2 te[E>0 ? E : 1];
 			#pragma unroll
-			for(int e=0; e<E; e++) te[e] = *reinterpret_cast<const double2*>(sW + (RO+e)*NX + m);
+			for(int e=0; e<E; e++) te[e] = *reinterpret_cast<const double2*>(sW + (RO+e)*LDW + m);
 			#pragma unroll
 			for(int e=0; e<E; e++)
 				{
@@ -398,7 +403,7 @@ struct hbi2_ctx
 		{
 		lane = lane_; l = lane_&15; g = lane_>>4; N = d.N; wbase = wbase_;
 		io = wbase_ + 8 + (size_t)g*RS;
-		if(SLIM) { Lb0 = io + C::even(C::INB); Lb1 = Lb0; xp = Lb0 + C::LBUF; tmp = xp + hbi2_cfg<C>::XC; }
+		if(SLIM) { Lb0 = io + hbi2_cfg<C>::IOS; Lb1 = Lb0; xp = Lb0 + C::LBUF; tmp = xp + hbi2_cfg<C>::XC; }
 		else { Lb0 = io + C::IOB; Lb1 = Lb0 + C::LBUF; xp = nullptr; tmp = Lb1 + C::LBUF + C::even(C::NU) + 2*C::XS; }
 		bar = reinterpret_cast<uint64_t*>(wbase_) + 4;            /* slots 0..3 belong to the hbi_ctx of region 0 */
 		ph = 0;
@@ -416,6 +421,7 @@ __device__ void hbi2_backward(hbi2_ctx<C, SLIM> &c, const hb_dims &d, const doub
 	{
 	typedef typename hbi2_cfg<C>::K K;
 	constexpr int NX = C::NX, NU = C::NU, NUX = C::NUX, LBUF = C::LBUF, BAB = C::BAB, PW = hbi2_ctx<C, SLIM>::RS;
+	constexpr int LDW = SLIM ? hbi2_cfg<C>::LDWS : NX, QO = SLIM ? hbi2_cfg<C>::QOFF : BAB;      /* W's leading dimension, where RSQrq sits in io */
 	const int lane = c.lane, l = c.l, N = c.N;
 	hbk_lane<K> ln; ln.init(l);
 	int co[2] = {0, 0};                                                  /* offsets of the two factor columns this lane finishes */
@@ -435,14 +441,21 @@ __device__ void hbi2_backward(hbi2_ctx<C, SLIM> &c, const hb_dims &d, const doub
 			{
 			const uint32_t bB = hbi_bytes_BAbt<C>(true), bQ = hbi_bytes_RSQ<C>(HBF_FIRST);
 			hbf_mbar_expect(c.bar, 2u*(bB+bQ));
-			hbf_bulk_g2s(io0, in_inst + off, bB, c.bar); hbf_bulk_g2s(io0 + BAB, in_inst + off + bB/8, bQ, c.bar);
-			hbf_bulk_g2s(io1, in_o + off, bB, c.bar); hbf_bulk_g2s(io1 + BAB, in_o + off + bB/8, bQ, c.bar);
+			hbf_bulk_g2s(io0, in_inst + off, bB, c.bar); hbf_bulk_g2s(io0 + QO, in_inst + off + bB/8, bQ, c.bar);
+			hbf_bulk_g2s(io1, in_o + off, bB, c.bar); hbf_bulk_g2s(io1 + QO, in_o + off + bB/8, bQ, c.bar);
 			}
 		else if(n==N)
 			{
 			const uint32_t bQ = hbi_bytes_RSQ<C>(HBF_LAST);
 			hbf_mbar_expect(c.bar, 2u*bQ);
-			hbf_bulk_g2s(io0 + BAB, in_inst + off, bQ, c.bar); hbf_bulk_g2s(io1 + BAB, in_o + off, bQ, c.bar);
+			hbf_bulk_g2s(io0 + QO, in_inst + off, bQ, c.bar); hbf_bulk_g2s(io1 + QO, in_o + off, bQ, c.bar);
+			}
+		else if(SLIM)
+			{
+			const uint32_t bB = 8u*(uint32_t)BAB, bQ = 8u*(uint32_t)(C::INB-BAB);
+			hbf_mbar_expect(c.bar, 2u*(bB+bQ));
+			hbf_bulk_g2s(io0, in_inst + off, bB, c.bar); hbf_bulk_g2s(io0 + QO, in_inst + off + BAB, bQ, c.bar);
+			hbf_bulk_g2s(io1, in_o + off, bB, c.bar); hbf_bulk_g2s(io1 + QO, in_o + off + BAB, bQ, c.bar);
 			}
 		else
 			{
@@ -450,7 +463,7 @@ __device__ void hbi2_backward(hbi2_ctx<C, SLIM> &c, const hb_dims &d, const doub
 			hbf_bulk_g2s(io0, in_inst + off, 8u*C::INB, c.bar); hbf_bulk_g2s(io1, in_o + off, 8u*C::INB, c.bar);
 			}
 		};
-	double *sQ = c.io + BAB;
+	double *sQ = c.io + QO;
 	issue(N);
 	for(int n=N; n>=0; n--)
 		{
@@ -487,9 +500,9 @@ __device__ void hbi2_backward(hbi2_ctx<C, SLIM> &c, const hb_dims &d, const doub
 		}
 		__syncwarp();
 		hbk_tile<K> T;
-		if(n==N) hbi2_assemble<K, HBF_LAST>(ln, c.io, sQ, xc, T, c.tmp);
-		else if(n==0) hbi2_assemble<K, HBF_FIRST>(ln, c.io, sQ, xc, T, c.tmp);
-		else hbi2_assemble<K, HBF_MID>(ln, c.io, sQ, xc, T, c.tmp);
+		if(n==N) hbi2_assemble<K, HBF_LAST, LDW>(ln, c.io, sQ, xc, T, c.tmp);
+		else if(n==0) hbi2_assemble<K, HBF_FIRST, LDW>(ln, c.io, sQ, xc, T, c.tmp);
+		else hbi2_assemble<K, HBF_MID, LDW>(ln, c.io, sQ, xc, T, c.tmp);
 		/* ---- Pb_n = Lxx (Lxx' b) with Lxx of stage n+1; Lxx' b came out of the assembly (the b-row of W before l_x is added) ---- */
 		if(n<N && Pb!=nullptr)
 			{
