@@ -42,6 +42,8 @@ struct hbi2_cfg
 	static_assert(K::RO==K::GR && K::E>0, "every lane slot owns a row; the gradient row is column-owned");
 	};
 
+__device__ __forceinline__ void hbi2_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
 /* ---- H <- RSQrq_n + W W',  W = [B A b]'_n Lxx_{n+1}.  sBW: [B A b]' in, W (ld NX) out; sQ: RSQrq, NOT overlapping W ---- */
 template<class K, int KIND, int LDW>
 __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__restrict__ sBW, const double *__restrict__ sQ,
@@ -82,18 +84,26 @@ __device__ __forceinline__ void hbi2_assemble(const hbk_lane<K> &ln, double *__r
 				if(s*G<NX)
 					{
 					const double *col = xc + ln.xo[s] - (j<NX ? j : 0);      /* col[k] = Lxx[k][j], k >= j */
+					/* two accumulators per entry and the extra rows two columns at a time: eight independent chains */
+					double wy[E>0 ? E : 1];
 					#pragma unroll
-					for(int k=s*G; k<NX; k++)
+					for(int e=0; e<E; e++) wy[e] = 0.0;
+					#pragma unroll
+					for(int k=s*G; k<NX; k+=2)
 						{
-						const double lkj = (j<NX && k>=j) ? col[k] : 0.0;
+						const double l0 = (j<NX && k>=j) ? col[k] : 0.0, l1 = (j<NX && k+1>=j) ? col[k+1] : 0.0;
 						#pragma unroll
 						for(int e=0; e<E; e++)
 							{
 							const int ae = hbk_arow<K, KIND>(RO+e);
-							const double b = (ae>=0) ? sB[ae*NX + k] : 0.0;
-							wx[e][s] = fma(b, lkj, wx[e][s]);
+							double2 b = make_double2(0.0, 0.0);
+							if(ae>=0) b = *reinterpret_cast<const double2*>(sB + ae*NX + k);
+							wx[e][s] = fma(b.x, l0, wx[e][s]);
+							wy[e] = fma(b.y, l1, wy[e]);
 							}
 						}
+					#pragma unroll
+					for(int e=0; e<E; e++) wx[e][s] += wy[e];
 					if(j<NX)
 						{
 						lxb[j] = wx[E-1][s];                                 /* Lxx' b: the first half of Pb = Lxx (Lxx' b) */
@@ -489,6 +499,16 @@ __device__ void hbi2_backward(hbi2_ctx<C, SLIM> &c, const hb_dims &d, const doub
 			}
 		if(rqv!=nullptr) for(int i=l; i<nux; i+=16) sQ[HB_TRI(nux)+i] = rqv[c.off_ux(n)+i];
 		if(bv!=nullptr && n<N) for(int j=l; j<NX; j+=16) c.io[brow*NX+j] = bv[n*NX+j];
+		if(n>0)
+			{
+			/* the next stage's hook vectors into L1 now: with one warp per scheduler nothing else hides their latency later */
+			const hb_stage s1 = d.st[n-1];
+			const int o1 = 16*l;                                             /* one 128-byte line per lane */
+			if(Qx!=nullptr && o1<s1.nb) hbi2_prefetch_l1(Qx + s1.off_c + o1);
+			if(qx!=nullptr && o1<s1.nb) hbi2_prefetch_l1(qx + s1.off_c + o1);
+			if(rqv!=nullptr && o1<NUX) hbi2_prefetch_l1(rqv + c.off_ux(n-1) + o1);
+			if(bv!=nullptr && o1<NX) hbi2_prefetch_l1(bv + (n-1)*NX + o1);
+			}
 		__syncwarp();
 		#pragma unroll
 		for(int t=0; t<3; t++)
