@@ -54,6 +54,7 @@ struct hbi_ctx
 		__syncwarp();
 		}
 	__device__ __forceinline__ void wait(int b) { hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b); }
+	__device__ __forceinline__ void kick(int) {}            /* the copies are already in flight (see hbi_ctx1) */
 	__device__ __forceinline__ void load(int b, double *dst, const double *src, uint32_t bytes)
 		{
 		if(lane==0) { hbf_mbar_expect(&bars[b], bytes); hbf_bulk_g2s(dst, src, bytes, &bars[b]); }
@@ -85,7 +86,7 @@ struct hbi_ctx1
 	uint32_t phase;
 	int o_in1, s_in, o_inN;
 	const double *p_src0, *p_src1, *p_src2, *p_src3;    /* recorded requests, one per barrier */
-	uint32_t p_b0, p_b1, p_b2, p_b3;
+	uint32_t p_b0, p_b1, p_b2, p_b3, issued;
 	__device__ __forceinline__ void init(double *wbase, int lane_, const hb_dims &d)
 		{
 		lane = lane_; N = d.N;
@@ -95,7 +96,7 @@ struct hbi_ctx1
 		va = tmp + C::XS; vb = va + hbi_cfg1<C>::VZ; vc = vb + hbi_cfg1<C>::VZ;
 		phase = 0;
 		o_in1 = d.st[1].off_BAbt; s_in = d.st[2].off_BAbt - d.st[1].off_BAbt; o_inN = d.st[N].off_BAbt;
-		p_src0 = p_src1 = p_src2 = p_src3 = nullptr; p_b0 = p_b1 = p_b2 = p_b3 = 0;
+		p_src0 = p_src1 = p_src2 = p_src3 = nullptr; p_b0 = p_b1 = p_b2 = p_b3 = 0; issued = 0;
 		if(lane==0)
 			{
 			for(int b=0; b<4; b++) hbf_mbar_init(&bars[b], 1);
@@ -108,13 +109,22 @@ struct hbi_ctx1
 		if(b==0) { p_src0 = src; p_b0 = bytes; } else if(b==1) { p_src1 = src; p_b1 = bytes; }
 		else if(b==2) { p_src2 = src; p_b2 = bytes; } else { p_src3 = src; p_b3 = bytes; }
 		}
-	__device__ __forceinline__ void wait(int b)
+	/* issue the recorded copy of barrier b now (the data it replaces must be dead): a sweep calls this at the top of a stage, before
+	 * it fetches the stage's vectors from global memory, so that the two latencies overlap; wait() issues it if nobody did */
+	__device__ __forceinline__ void kick(int b)
 		{
+		if((issued>>b)&1u) return;
 		const double *src = (b==0) ? p_src0 : (b==1 ? p_src1 : (b==2 ? p_src2 : p_src3));
 		const uint32_t bytes = (b==0) ? p_b0 : (b==1 ? p_b1 : (b==2 ? p_b2 : p_b3));
 		__syncwarp();                                   /* every lane is done with the data this copy replaces */
 		if(lane==0) { hbf_mbar_expect(&bars[b], bytes); hbf_bulk_g2s(b<2 ? io : Lb0, src, bytes, &bars[b]); }
+		issued |= (1u<<b);
+		}
+	__device__ __forceinline__ void wait(int b)
+		{
+		kick(b);
 		hbf_mbar_wait(&bars[b], (phase>>b)&1); phase ^= (1u<<b);
+		issued &= ~(1u<<b);
 		}
 	__device__ __forceinline__ int off_in(int n) const { return (n==0) ? 0 : (n==N ? o_inN : o_in1 + (n-1)*s_in); }
 	__device__ __forceinline__ int off_ux(int n) const { return (n==0) ? 0 : C::NU + (n-1)*C::NUX; }
@@ -359,6 +369,9 @@ __device__ void hbi_trs_backward(X &c, const hb_dims &d, const double *__restric
 	__syncwarp();
 	if(qx!=nullptr) for(int j=l; j<s.nb; j+=32) wv[o+d.idxb[s.off_c+j]] += qx[s.off_c+j];
 	__syncwarp();
+	/* the x-part of w_{n+1} travels to the next stage through shared memory (vc), not through the global array it is stored in */
+	if(l<NX) c.vc[l] = wv[o+l];
+	__syncwarp();
 	}
 	for(int n=N-1; n>=0; n--)
 		{
@@ -367,8 +380,9 @@ __device__ void hbi_trs_backward(X &c, const hb_dims &d, const double *__restric
 		const double *sB = c.io + (n&1)*X::SB;
 		const int nux = first ? NU : NUX, o = c.off_ux(n), o1 = c.off_ux(n+1) + ((n+1<N) ? NU : 0);
 		const hb_stage s = d.st[n];
+		c.kick(2+(n&1)); c.kick(n&1);
 		for(int i=l; i<nux; i+=32) c.va[i] = rqv[o+i];
-		if(l<NX) c.vb[l] = Pb[n*NX+l] + wv[o1+l];
+		if(l<NX) c.vb[l] = Pb[n*NX+l] + c.vc[l];
 		__syncwarp();
 		if(qx!=nullptr) for(int j=l; j<s.nb; j+=32) c.va[d.idxb[s.off_c+j]] += qx[s.off_c+j];
 		__syncwarp();
@@ -410,6 +424,12 @@ __device__ void hbi_trs_backward(X &c, const hb_dims &d, const double *__restric
 			}
 		if(l<nux) wv[o+l] = v0;
 		if(NUX>32 && l+32<nux) wv[o+l+32] = v1;
+		if(!first)
+			{
+			/* x-part of w_n = entries NU.. of this stage's vector */
+			if(l>=NU && l<nux) c.vc[l-NU] = v0;
+			if(NUX>32 && l+32<nux) c.vc[l+32-NU] = v1;
+			}
 		__syncwarp();
 		if(n-2>=0) { issue_L(n-2); issue_B(n-2); }
 		}
@@ -594,6 +614,7 @@ __device__ void hbi_residuals(X &c, const hb_dims &d, const double *__restrict__
 		const double *sB = c.io + (n&1)*X::SB;
 		const double *H = (n&1) ? c.Lb1 : c.Lb0;
 		const hb_stage s = d.st[n];
+		c.kick(2+(n&1)); if(n<N) c.kick(n&1);
 		for(int i=l; i<nux; i+=32)
 			{
 			c.va[i] = ux[o+i];
