@@ -131,6 +131,13 @@ struct hbi_ctx1
 	__device__ __forceinline__ void sync() { __syncwarp(); }
 	};
 
+/* one 128-byte line per lane of a vector of n doubles into L1 (the sweeps fetch the NEXT stage's vectors a stage ahead: in the
+ * single-slot sweeps a warp has nothing else in flight while it waits for them) */
+__device__ __forceinline__ void hbi_prefetch_vec(const double *p, int n, int lane)
+	{
+	if(p!=nullptr && 16*lane<n) asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 16*lane));
+	}
+
 template<class C> __device__ __forceinline__ constexpr uint32_t hbi_bytes_BAbt(bool first)
 	{ return 8u*(uint32_t)(first ? C::even((C::NU+1)*C::NX) : C::BAB); }
 template<class C> __device__ __forceinline__ constexpr uint32_t hbi_bytes_RSQ(int kind)
@@ -255,8 +262,11 @@ __device__ void hbi_forward(X &c, const double *__restrict__ in_inst, const doub
 		const double *xs = (n&1) ? c.xs1 : c.xs0;
 		double *xo = (n&1) ? c.xs0 : c.xs1;
 		const int brow = first ? NU : NUX;
+		c.kick(2+(n&1)); c.kick(n&1);
+		if(n+1<N) { hbi_prefetch_vec(bv!=nullptr ? bv + (n+1)*NX : nullptr, NX, l); if(TRS) hbi_prefetch_vec(w + c.off_ux(n+1), NUX, l); }
+		const double bvl = (bv!=nullptr && l<NX) ? bv[n*NX+l] : 0.0;            /* in flight while the stage's matrices arrive */
 		c.wait(2+(n&1)); c.wait(n&1);
-		if(bv!=nullptr) { if(l<NX) sB[brow*NX+l] = bv[n*NX+l]; __syncwarp(); }
+		if(bv!=nullptr) { if(l<NX) sB[brow*NX+l] = bvl; __syncwarp(); }
 		const int o_ux = c.off_ux(n), o_ux1 = c.off_ux(n+1) + ((n+1<N) ? NU : 0);
 		/* ---- phase A ---- */
 		double t = 0.0;
@@ -381,6 +391,12 @@ __device__ void hbi_trs_backward(X &c, const hb_dims &d, const double *__restric
 		const int nux = first ? NU : NUX, o = c.off_ux(n), o1 = c.off_ux(n+1) + ((n+1<N) ? NU : 0);
 		const hb_stage s = d.st[n];
 		c.kick(2+(n&1)); c.kick(n&1);
+		if(n>0)
+			{
+			const hb_stage sp = d.st[n-1];
+			hbi_prefetch_vec(rqv + c.off_ux(n-1), NUX, l); hbi_prefetch_vec(Pb + (n-1)*NX, NX, l);
+			hbi_prefetch_vec(qx!=nullptr ? qx + sp.off_c : nullptr, sp.nb, l);
+			}
 		for(int i=l; i<nux; i+=32) c.va[i] = rqv[o+i];
 		if(l<NX) c.vb[l] = Pb[n*NX+l] + c.vc[l];
 		__syncwarp();
@@ -615,6 +631,12 @@ __device__ void hbi_residuals(X &c, const hb_dims &d, const double *__restrict__
 		const double *H = (n&1) ? c.Lb1 : c.Lb0;
 		const hb_stage s = d.st[n];
 		c.kick(2+(n&1)); if(n<N) c.kick(n&1);
+		if(n<N)
+			{
+			const hb_stage sn = d.st[n+1];
+			hbi_prefetch_vec(ux + c.off_ux(n+1), NUX, l); hbi_prefetch_vec(rq0 + c.off_ux(n+1), NUX, l); hbi_prefetch_vec(pi + n*NX, 2*NX, l);
+			hbi_prefetch_vec(lam_lo + sn.off_c, sn.nb, l); hbi_prefetch_vec(lam_up + sn.off_c, sn.nb, l); hbi_prefetch_vec(b0 + n*NX, NX, l);
+			}
 		for(int i=l; i<nux; i+=32)
 			{
 			c.va[i] = ux[o+i];
