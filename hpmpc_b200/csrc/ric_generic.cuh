@@ -63,6 +63,214 @@ __device__ __forceinline__ void hb_chol(const hb_ctx &c, double *L, int m, int n
 		}
 	}
 
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* Register-tiled stage routines (round 2).  The row-per-lane loops above and below need two shared-memory loads per DFMA  */
+/* and leave the lanes beyond the row count idle; here the warp is 16 row slots x 2: lane (rt, h) owns rows rt, rt+16,     */
+/* rt+32, rt+48 (R of them, R = ceil(m/16)) and four columns at a time, i.e. an R x 4 register tile fed by R + 4 loads per  */
+/* k.  Rows 16 apart keep the row operand conflict-free both in the odd-stride W rows and in the packed triangle           */
+/* (i(i+1)/2 mod 16 is a permutation of 0..15 over 16 consecutive i).                                                       */
+/* ---------------------------------------------------------------------------------------------------------------- */
+
+/* W <- W * Lxx_{n+1} in place (m x nx1, Lxx lower nx1 x nx1 inside the packed prev); h picks the column tile of a round.
+ * W[i][j] = sum_{k>=j} W[i][k] Lxx[k][j]: a round reads columns >= its own tiles only, and a lane's reads of its partner's
+ * tile happen before the barrier that precedes the writes */
+template<int R>
+__device__ __noinline__ void hbg_trmm(double *sW, int ld, int lane, int m, int nx1, const double *prev, int nu1)
+	{
+	const int rt = lane>>1, h = lane&1;
+	int row[R];
+#pragma unroll
+	for(int r=0; r<R; r++) { int i = rt + 16*r; row[r] = (i<m ? i : m-1)*ld; }
+	const int ntile = (nx1+3)>>2;
+	for(int t0=0; t0<ntile; t0+=2)
+		{
+		const int t = t0 + h, j0 = 4*t;
+		double acc[R][4];
+#pragma unroll
+		for(int r=0; r<R; r++) { acc[r][0] = 0.0; acc[r][1] = 0.0; acc[r][2] = 0.0; acc[r][3] = 0.0; }
+		if(t<ntile)
+			{
+#pragma unroll
+			for(int kk=0; kk<4; kk++)
+				{
+				const int k = j0 + kk;
+				if(k<nx1)
+					{
+					const double *lk = prev + HB_TRI(nu1+k) + nu1 + j0;
+					double a[R];
+#pragma unroll
+					for(int r=0; r<R; r++) a[r] = sW[row[r]+k];
+#pragma unroll
+					for(int cc=0; cc<=kk; cc++)
+						{
+						const double b = lk[cc];
+#pragma unroll
+						for(int r=0; r<R; r++) acc[r][cc] = fma(a[r], b, acc[r][cc]);
+						}
+					}
+				}
+#pragma unroll 2
+			for(int k=j0+4; k<nx1; k++)
+				{
+				const double *lk = prev + HB_TRI(nu1+k) + nu1 + j0;
+				const double b0 = lk[0], b1 = lk[1], b2 = lk[2], b3 = lk[3];
+#pragma unroll
+				for(int r=0; r<R; r++)
+					{
+					const double a = sW[row[r]+k];
+					acc[r][0] = fma(a, b0, acc[r][0]); acc[r][1] = fma(a, b1, acc[r][1]);
+					acc[r][2] = fma(a, b2, acc[r][2]); acc[r][3] = fma(a, b3, acc[r][3]);
+					}
+				}
+			}
+		__syncwarp();
+		if(t<ntile)
+			{
+#pragma unroll
+			for(int r=0; r<R; r++)
+				if(rt+16*r<m)
+					{
+#pragma unroll
+					for(int cc=0; cc<4; cc++) if(j0+cc<nx1) sW[row[r]+j0+cc] = acc[r][cc];
+					}
+			}
+		__syncwarp();
+		}
+	}
+
+/* cur <- chol_mn(cur + W W') by panels of four columns, left-looking: the panel's entries are accumulated in registers over
+ * the nx1 columns of W and over the columns of L already done (h splits both sums by the parity of k, one shuffle joins them),
+ * the 4 x 4 diagonal block is factorised by every lane on its own, the panel is scaled and stored.  Pivot rule of
+ * kernel/c99/kernel_dpotrf_c99_lib4.c:553-640 as in hb_chol.  m = nux (+1 with the gradient row, which is row nux of W and of
+ * the packed cur) */
+template<int R>
+__device__ __noinline__ void hbg_syrk_chol(double *cur, const double *sW, int ld, int lane, int m, int nux, int nx1)
+	{
+	const int rt = lane>>1, h = lane&1;
+	int irow[R], wrow[R], lrow[R];
+#pragma unroll
+	for(int r=0; r<R; r++) { int i = rt + 16*r; i = i<m ? i : m-1; irow[r] = i; wrow[r] = i*ld; lrow[r] = HB_TRI(i); }
+	double *dinv = cur + HB_TRI(nux) + nux;
+	for(int jb=0; jb<nux; jb+=4)
+		{
+		int wj[4], lj[4];
+#pragma unroll
+		for(int cc=0; cc<4; cc++) { int j = jb+cc; j = j<nux ? j : nux-1; wj[cc] = j*ld; lj[cc] = HB_TRI(j); }
+		const int rlo = jb>>4;
+		double acc[R][4];
+#pragma unroll
+		for(int r=0; r<R; r++) { acc[r][0] = 0.0; acc[r][1] = 0.0; acc[r][2] = 0.0; acc[r][3] = 0.0; }
+#pragma unroll 2
+		for(int k=h; k<nx1; k+=2)
+			{
+			const double b0 = sW[wj[0]+k], b1 = sW[wj[1]+k], b2 = sW[wj[2]+k], b3 = sW[wj[3]+k];
+#pragma unroll
+			for(int r=0; r<R; r++)
+				if(r>=rlo)
+					{
+					const double a = sW[wrow[r]+k];
+					acc[r][0] = fma(a, b0, acc[r][0]); acc[r][1] = fma(a, b1, acc[r][1]);
+					acc[r][2] = fma(a, b2, acc[r][2]); acc[r][3] = fma(a, b3, acc[r][3]);
+					}
+			}
+#pragma unroll 2
+		for(int k=h; k<jb; k+=2)
+			{
+			const double b0 = cur[lj[0]+k], b1 = cur[lj[1]+k], b2 = cur[lj[2]+k], b3 = cur[lj[3]+k];
+#pragma unroll
+			for(int r=0; r<R; r++)
+				if(r>=rlo)
+					{
+					const double a = -cur[lrow[r]+k];
+					acc[r][0] = fma(a, b0, acc[r][0]); acc[r][1] = fma(a, b1, acc[r][1]);
+					acc[r][2] = fma(a, b2, acc[r][2]); acc[r][3] = fma(a, b3, acc[r][3]);
+					}
+			}
+		/* join the two halves, add the entries of H, park the panel so that the diagonal block can be read by every lane */
+#pragma unroll
+		for(int r=0; r<R; r++)
+			if(r>=rlo)
+				{
+#pragma unroll
+				for(int cc=0; cc<4; cc++)
+					{
+					double v = acc[r][cc] + __shfl_xor_sync(HB_FULL, acc[r][cc], 1);
+					if((jb+cc<nux) && (jb+cc<=irow[r])) v += cur[lrow[r]+jb+cc];
+					acc[r][cc] = v;
+					}
+				}
+		__syncwarp();
+#pragma unroll
+		for(int r=0; r<R; r++)
+			if(r>=rlo && h==0 && irow[r]<jb+4)                                  /* only the rows of the diagonal block are read back */
+				{
+#pragma unroll
+				for(int cc=0; cc<4; cc++) if((jb+cc<nux) && (jb+cc<=irow[r])) cur[lrow[r]+jb+cc] = acc[r][cc];
+				}
+		__syncwarp();
+		double D[4][4], dd[4], iv[4];
+#pragma unroll
+		for(int cc=0; cc<4; cc++)
+#pragma unroll
+			for(int c2=0; c2<=cc; c2++)
+				D[cc][c2] = (jb+cc<nux) ? cur[lj[cc]+jb+c2] : (c2==cc ? 1.0 : 0.0);
+#pragma unroll
+		for(int cc=0; cc<4; cc++)
+			{
+			const double piv = D[cc][cc];
+			double d, inv;
+			if(piv>1e-15) { d = sqrt(piv); inv = 1.0/d; }
+			else { d = 0.0; inv = 0.0; }
+			dd[cc] = d; iv[cc] = inv;
+#pragma unroll
+			for(int c2=cc+1; c2<4; c2++) D[c2][cc] *= inv;
+#pragma unroll
+			for(int c2=cc+1; c2<4; c2++)
+#pragma unroll
+				for(int c3=cc+1; c3<=c2; c3++) D[c2][c3] = fma(-D[c2][cc], D[c3][cc], D[c2][c3]);
+			}
+		__syncwarp();
+#pragma unroll
+		for(int r=0; r<R; r++)
+			if(r>=rlo)
+				{
+				double x[4];
+#pragma unroll
+				for(int cc=0; cc<4; cc++)
+					{
+					double v = acc[r][cc];
+#pragma unroll
+					for(int c2=0; c2<cc; c2++) v = fma(-x[c2], D[cc][c2], v);
+					x[cc] = v*iv[cc];
+					}
+				if(rt+16*r<m)
+					{
+#pragma unroll
+					for(int cc=0; cc<4; cc++)
+						if((cc>>1)==h && jb+cc<nux && jb+cc<=irow[r])
+							cur[lrow[r]+jb+cc] = (irow[r]==jb+cc) ? dd[cc] : x[cc];
+					}
+				}
+		if(lane<4 && jb+lane<nux) dinv[jb+lane] = lane==0 ? iv[0] : lane==1 ? iv[1] : lane==2 ? iv[2] : iv[3];
+		__syncwarp();
+		}
+	}
+
+__device__ __forceinline__ void hbg_trmm_any(const hb_ctx &c, int m, int nx1, const double *prev, int nu1)
+	{
+	if(m<=16) hbg_trmm<1>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
+	else if(m<=32) hbg_trmm<2>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
+	else if(m<=48) hbg_trmm<3>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
+	else hbg_trmm<4>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
+	}
+__device__ __forceinline__ void hbg_syrk_chol_any(const hb_ctx &c, double *cur, int m, int nux, int nx1)
+	{
+	if(m<=16) hbg_syrk_chol<1>(cur, c.sW, c.ldW, c.lane, m, nux, nx1);
+	else if(m<=32) hbg_syrk_chol<2>(cur, c.sW, c.ldW, c.lane, m, nux, nx1);
+	else if(m<=48) hbg_syrk_chol<3>(cur, c.sW, c.ldW, c.lane, m, nux, nx1);
+	else hbg_syrk_chol<4>(cur, c.sW, c.ldW, c.lane, m, nux, nx1);
+	}
+
 /* one backward stage: cur <- chol_mn( RSQrq_n (+Qx,qx) + W W' ),  W = [B A b]'_n Lxx_{n+1}  */
 template<bool GRAD>
 __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage &s, int nu1,
@@ -133,14 +341,21 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 		{
 		double *sW = c.sW; const int ldW = c.ldW;
 		const double *gb = in_inst + s.off_BAbt;
-		for(int e=lane; e<m*nx1; e+=32)
+		{
+		int i = 0, j = lane;
+		const int tot = m*nx1;
+#pragma unroll 4
+		for(int e=lane; e<tot; e+=32)
 			{
-			int i = e/nx1, j = e - i*nx1;
+			while(j>=nx1) { j -= nx1; i++; }
 			double v = gb[e];
 			if(GRAD && bvec!=nullptr && i==nux) v = bvec[s.off_pi+j];
 			sW[i*ldW+j] = v;
+			j += 32;
 			}
+		}
 		__syncwarp();
+#ifdef HB_GENERIC_ROWWISE
 		/* W = [B A b]' * Lxx_{n+1}, in place, row per lane */
 		for(int i=lane; i<m; i+=32)
 			{
@@ -153,6 +368,9 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 				}
 			}
 		__syncwarp();
+#else
+		hbg_trmm_any(c, m, nx1, prev, nu1);
+#endif
 		if(GRAD)
 			{
 			const double *wl = sW + nux*ldW;
@@ -167,6 +385,7 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 			for(int j=lane; j<nx1; j+=32) sW[nux*ldW+j] += prev[HB_TRI(nu1+nx1)+nu1+j];
 			__syncwarp();
 			}
+#ifdef HB_GENERIC_ROWWISE
 		/* H += W W' (lower), row per lane */
 		for(int i=lane; i<m; i+=32)
 			{
@@ -182,8 +401,13 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 				}
 			}
 		__syncwarp();
+#endif
 		}
+#ifdef HB_GENERIC_ROWWISE
 	hb_chol(c, cur, m, nux);
+#else
+	hbg_syrk_chol_any(c, cur, m, nux, nx1);           /* H + W W' is formed panel by panel inside the factorisation */
+#endif
 	}
 
 /* copy a packed factor between smem and the stash (global) */

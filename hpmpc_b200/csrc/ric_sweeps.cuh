@@ -30,6 +30,13 @@ __host__ __device__ inline int hb_smem_doubles_per_warp(int nzM, int nxM)
 	return 2*lsz + HB_EVEN(nzM*(nxM|1)) + 192;
 	}
 
+/* the any-size sweeps fetch a stage with ordinary loads, a few in flight per lane: pull the NEXT stage's data towards the SM (L2)
+ * while the current stage is being worked on, one 128-byte line per lane and step */
+__device__ __forceinline__ void hb_prefetch_l2(const double *p, int n, int lane)
+	{
+	for(int o=16*lane; o<n; o+=512) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + o));
+	}
+
 /* backward sweep n = N..0 ; factor of every stage is written to Lst (global) */
 template<bool GRAD>
 __device__ void hb_backward(const hb_ctx &c, const hb_dims &d, const double *in_inst, double *Lst,
@@ -40,6 +47,11 @@ __device__ void hb_backward(const hb_ctx &c, const hb_dims &d, const double *in_
 		{
 		const hb_stage s = d.st[n];
 		const int nu1 = (n<d.N) ? d.st[n+1].nu : 0;
+		if(n>0)
+			{
+			const hb_stage sp = d.st[n-1];                                   /* [B A b]' and RSQrq of a stage are contiguous */
+			hb_prefetch_l2(in_inst + sp.off_BAbt, HB_EVEN((sp.nu+sp.nx+1)*sp.nx1) + HB_TRI(sp.nu+sp.nx) + sp.nu+sp.nx, c.lane);
+			}
 		hb_stage_factor<GRAD>(c, s, nu1, in_inst, bvec, rqvec, Qx, qx, d.idxb, Pb, cur, prev);
 		hb_copy(c, Lst + s.off_L, cur, HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx));
 		double *t = cur; cur = prev; prev = t;
@@ -60,6 +72,12 @@ static __device__ void hb_forward(const hb_ctx &c, const hb_dims &d, const doubl
 		{
 		const hb_stage s = d.st[n];
 		const hb_stage s1 = d.st[n+1];
+		if(n+2<=d.N)
+			{
+			const hb_stage s2 = d.st[n+2];
+			hb_prefetch_l2(Lst + s2.off_L, HB_TRI(s2.nu+s2.nx) + 2*(s2.nu+s2.nx), c.lane);
+			if(n+1<d.N) hb_prefetch_l2(in_inst + s1.off_BAbt, (s1.nu+s1.nx+1)*s1.nx1, c.lane);
+			}
 		hb_copy(c, b, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
 		hb_load_BAbt(c, s, in_inst);
 		__syncwarp();
@@ -96,6 +114,12 @@ static __device__ void hb_trs_backward(const hb_ctx &c, const hb_dims &d, const 
 		{
 		const hb_stage s = d.st[n];
 		const hb_stage s1 = d.st[n+1];
+		if(n>0)
+			{
+			const hb_stage sp = d.st[n-1];
+			hb_prefetch_l2(Lst + sp.off_L, HB_TRI(sp.nu+sp.nx) + 2*(sp.nu+sp.nx), lane);
+			hb_prefetch_l2(in_inst + sp.off_BAbt, (sp.nu+sp.nx+1)*sp.nx1, lane);
+			}
 		hb_copy(c, c.bufA, Lst + s.off_L, HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx));
 		if(compute_Pb) hb_copy(c, c.bufB, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
 		hb_load_BAbt(c, s, in_inst);
