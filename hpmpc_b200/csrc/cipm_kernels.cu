@@ -23,6 +23,7 @@
 #include "launch_util.cuh"
 #include "ipm_sweeps.cuh"
 #include "ric_ipm_blk.cuh"
+#include "ric_team.cuh"
 
 enum { CS_INIT=0, CS_P1_SV, CS_P1_A, CS_P1_TRS, CS_P1_B, CS_P2_SV, CS_P2_A, CS_P2_TRS, CS_P2_B,
        CS_RES_ENTER /* residuals wanted before phase 2 starts */, CS_RES_ITER /* ... at the end of a phase-2 iteration */,
@@ -416,6 +417,62 @@ template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 		const int grid = (int)(need<sms ? (need<1 ? 1 : need) : sms);
 		if(fwd) hb_cipm_sv2_kernel<C, true><<<grid, w*32, smem(), st>>>(a);
 		else hb_cipm_sv2_kernel<C, false><<<grid, w*32, smem_slim(), st>>>(a);
+		}
+	};
+
+/* any-size patterns: factor + solve (predictor) with four warps per instance (ric_team.cuh): one CTA per instance, handed out by an
+ * atomic counter; the forward sweep that follows is warp 0's */
+__global__ void __launch_bounds__(HBT_THREADS) hb_cipm_team_sv_kernel(hb_cipm_args a)
+	{
+	typedef hb_sweeps_generic S;
+	const hb_dims &d = a.d;
+	const int tid = threadIdx.x;
+	const long long n_items = a.act ? (long long)*a.n_act : a.n_inst;
+	if(n_items==0) return;
+	hb_ctx c = hb_make_ctx(d, hb_smem, tid&31);
+	__shared__ int s_it;
+	for(;;)
+		{
+		if(tid==0) s_it = atomicAdd(a.wq, 1);
+		__syncthreads();
+		const long long it = s_it;
+		__syncthreads();
+		if(it>=n_items) break;
+		const long long inst = a.act ? a.act[it] : it;
+		const int st = a.si[inst*CIPM_I];
+		if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
+		const bool p2 = (st==CS_P2_SV);
+		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst*a.work_stride);
+		const double *in_inst = a.in + inst*d.in_stride;
+		hbt_backward<true>(c, tid, d, in_inst, w.L, p2 ? w.res_b : nullptr, p2 ? w.res_q : w.rq0, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
+		if(tid<32)
+			{
+			S::forward_sv(c, d, in_inst, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
+			__syncwarp();
+			if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_A : CS_P1_A;
+			}
+		__syncthreads();
+		}
+	}
+template<> struct hb_cipm_sv<hb_sweeps_generic>
+	{
+	/* the kernel has a static shared word of its own (the queue ticket), so the dynamic maximum is set below the architectural one */
+	static int prep(int)
+		{
+		HB_CK(cudaFuncSetAttribute(hb_cipm_team_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
+		return 0;
+		}
+	/* HPMPC_B200_TEAM=0 keeps the one-warp-per-instance sweep (A/B runs) */
+	static bool use() { const char *e = getenv("HPMPC_B200_TEAM"); return !(e && e[0]=='0'); }
+	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st, bool)
+		{
+		const int smem = hb_smem_bytes_per_warp(&a.d);
+		int per_sm = 233472/(smem + 1024);
+		if(per_sm>16) per_sm = 16;
+		if(per_sm<1) per_sm = 1;
+		long long g = (long long)sms*per_sm;
+		if(g>a.n_inst) g = a.n_inst;
+		hb_cipm_team_sv_kernel<<<(int)(g<1 ? 1 : g), HBT_THREADS, smem, st>>>(a);
 		}
 	};
 

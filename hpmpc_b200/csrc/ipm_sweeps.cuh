@@ -42,8 +42,8 @@ static __device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const
 		const hb_stage s = d.st[n];
 		const int nu = s.nu, nx = s.nx, nux = nu+nx, nx1 = s.nx1;
 		double *H = c.bufA;
-		hb_copy(c, H, in_inst + s.off_RSQ, HB_TRI(nux));
-		if(nx1>0) hb_load_BAbt(c, s, in_inst);
+		hb_g2s(lane, H, in_inst + s.off_RSQ, HB_TRI(nux));
+		if(nx1>0) hb_load_BAbt_async(c, s, in_inst);
 		for(int i=lane; i<nux; i+=32) xs[i] = ux[s.off_ux+i];
 		for(int j=lane; j<nx1; j+=32) ps[j] = pi[s.off_pi+j];
 		/* rq = rq0 - pi_{n-1} (x part) + (lam_up - lam_lo)[idxb] */
@@ -71,6 +71,8 @@ static __device__ void hb_ipm_residuals(const hb_ctx &c, const hb_dims &d, const
 				}
 			__syncwarp();
 			}
+		hb_g2s_wait();
+		__syncwarp();
 		for(int i=lane; i<nux; i+=32)
 			{
 			double acc = w.res_q[s.off_ux+i];

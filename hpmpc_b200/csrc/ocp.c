@@ -700,8 +700,15 @@ static int ipm_multi_wanted(const hpmpc_b200_ocp *p, long long n_inst, int k_max
 	if(p->dims.nbtot<=0 || k_max<1 || warm_start==2) return 0;
 	if(e) return atoi(e)==0;
 	/* measured on B200 (profiles/r02_ipm_multi_kernel.txt): config 3 (size-specialised sweeps) 67.4 -> 82.9 K solves/s; config 4
-	 * (run-time-size sweeps, whose kernels are latency-bound whatever drives them) 71.2 -> 64.4 K, so those stay fused */
-	return p->ipm_fast_id>=0 && n_inst >= 2LL*p->i_grid*p->i_warps;
+	 * (run-time-size sweeps, one warp per instance in every kernel) 71.2 -> 64.4 K; with the four-warps-per-instance factorisation
+	 * kernel (ric_team.cuh), which only the multi-kernel driver has, the any-size patterns go there too */
+	if(p->ipm_fast_id<0)
+		{
+		const char *t = getenv("HPMPC_B200_TEAM");
+		if(t && t[0]=='0') return 0;
+		return n_inst >= 64;
+		}
+	return n_inst >= 2LL*p->i_grid*p->i_warps;
 	}
 
 static int ipm_multi(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, int k_max, double mu0, double mu_tol, double alpha_min,

@@ -32,6 +32,45 @@ struct hb_ctx
 
 __device__ __forceinline__ int hb_Lsize(int nux) { return HB_EVEN(HB_TRI(nux) + 2*nux); }
 
+/* global -> shared staging without a register round trip (LDGSTS): a lane puts ALL its 8-byte copies of a stage in flight at once
+ * (the plain `dst[e] = src[e]` loops keep ~4 loads per lane in flight, which at one warp per scheduler is ~1 KB per warp against
+ * a ~700-cycle round trip); hb_g2s_wait() + __syncwarp() before the data is used */
+__device__ __forceinline__ void hb_cp8(double *dst_smem, const double *src)
+	{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+	}
+__device__ __forceinline__ void hb_g2s_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void hb_g2s(int lane, double *dst_smem, const double *__restrict__ src, int n)
+	{
+	for(int e=lane; e<n; e+=32) hb_cp8(dst_smem + e, src + e);
+	}
+/* rows of nx1 doubles to rows of ld doubles */
+__device__ __forceinline__ void hb_g2s_rows(int lane, double *dst_smem, int ld, const double *__restrict__ src, int nrow, int nx1)
+	{
+	int i = 0, j = lane;
+	const int tot = nrow*nx1;
+	for(int e=lane; e<tot; e+=32)
+		{
+		while(j>=nx1) { j -= nx1; i++; }
+		hb_cp8(dst_smem + i*ld + j, src + e);
+		j += 32;
+		}
+	}
+
+/* 1/sqrt(p): hardware seed (MUFU.RSQ64H) and two coupled Goldschmidt steps, as in the size-specialised kernels (ric_blk.cuh) */
+__device__ __forceinline__ double hbg_rsqrt(double p)
+	{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+	const double hp = 0.5*p;
+	double g = hp*y;
+	double r = fma(-g, y, 0.5);
+	g = fma(g, r, g); y = fma(y, r, y);
+	r = fma(-g, y, 0.5);
+	y = fma(y, r, y);
+	return y;
+	}
+
 /* left-looking Cholesky of the packed m x nux trapezoid in smem; dinv written after the trapezoid */
 __device__ __forceinline__ void hb_chol(const hb_ctx &c, double *L, int m, int nux)
 	{
@@ -218,10 +257,8 @@ __device__ __noinline__ void hbg_syrk_chol(double *cur, const double *sW, int ld
 		for(int cc=0; cc<4; cc++)
 			{
 			const double piv = D[cc][cc];
-			double d, inv;
-			if(piv>1e-15) { d = sqrt(piv); inv = 1.0/d; }
-			else { d = 0.0; inv = 0.0; }
-			dd[cc] = d; iv[cc] = inv;
+			const double inv = (piv>1e-15) ? hbg_rsqrt(piv) : 0.0;
+			dd[cc] = piv*inv; iv[cc] = inv;
 #pragma unroll
 			for(int c2=cc+1; c2<4; c2++) D[c2][cc] *= inv;
 #pragma unroll
@@ -251,7 +288,13 @@ __device__ __noinline__ void hbg_syrk_chol(double *cur, const double *sW, int ld
 							cur[lrow[r]+jb+cc] = (irow[r]==jb+cc) ? dd[cc] : x[cc];
 					}
 				}
-		if(lane<4 && jb+lane<nux) dinv[jb+lane] = lane==0 ? iv[0] : lane==1 ? iv[1] : lane==2 ? iv[2] : iv[3];
+		if(lane==0)
+			{
+			dinv[jb] = iv[0];
+			if(jb+1<nux) dinv[jb+1] = iv[1];
+			if(jb+2<nux) dinv[jb+2] = iv[2];
+			if(jb+3<nux) dinv[jb+3] = iv[3];
+			}
 		__syncwarp();
 		}
 	}
@@ -283,7 +326,9 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 	const int m = GRAD ? nux+1 : nux;
 	const int ntri = HB_TRI(nux) + (GRAD ? nux : 0);
 	const double *g = in_inst + s.off_RSQ;
-	for(int e=lane; e<ntri; e+=32) cur[e] = g[e];
+	hb_g2s(lane, cur, g, ntri);
+	if(nx1>0) hb_g2s_rows(lane, c.sW, c.ldW, in_inst + s.off_BAbt, m, nx1);
+	hb_g2s_wait();
 	__syncwarp();
 	if(GRAD && rqvec!=nullptr)
 		{
@@ -340,21 +385,11 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 	if(nx1>0)
 		{
 		double *sW = c.sW; const int ldW = c.ldW;
-		const double *gb = in_inst + s.off_BAbt;
-		{
-		int i = 0, j = lane;
-		const int tot = m*nx1;
-#pragma unroll 4
-		for(int e=lane; e<tot; e+=32)
+		if(GRAD && bvec!=nullptr)
 			{
-			while(j>=nx1) { j -= nx1; i++; }
-			double v = gb[e];
-			if(GRAD && bvec!=nullptr && i==nux) v = bvec[s.off_pi+j];
-			sW[i*ldW+j] = v;
-			j += 32;
+			for(int j=lane; j<nx1; j+=32) sW[nux*ldW+j] = bvec[s.off_pi+j];
+			__syncwarp();
 			}
-		}
-		__syncwarp();
 #ifdef HB_GENERIC_ROWWISE
 		/* W = [B A b]' * Lxx_{n+1}, in place, row per lane */
 		for(int i=lane; i<m; i+=32)
@@ -414,6 +449,12 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 __device__ __forceinline__ void hb_copy(const hb_ctx &c, double *dst, const double *src, int n)
 	{
 	for(int e=c.lane; e<n; e+=32) dst[e] = src[e];
+	}
+
+/* the same, asynchronous: hb_g2s_wait() + __syncwarp() before use */
+__device__ __forceinline__ void hb_load_BAbt_async(const hb_ctx &c, const hb_stage &s, const double *__restrict__ in_inst)
+	{
+	hb_g2s_rows(c.lane, c.sW, c.ldW, in_inst + s.off_BAbt, s.nu+s.nx+1, s.nx1);
 	}
 
 /* load [B A b]'_n into sW (all nux+1 rows) */

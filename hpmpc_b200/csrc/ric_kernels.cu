@@ -14,6 +14,7 @@
 #include "launch_util.cuh"
 #include "layout.h"
 #include "ric_sweeps.cuh"
+#include "ric_team.cuh"
 #include "ric_tree.cuh"
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -53,6 +54,34 @@ __global__ void hb_ric_trf_kernel(hb_dims d, long long n_inst, const double *__r
 		hb_backward<false>(c, d, in + inst*d.in_stride, L + inst*d.L_stride, nullptr, nullptr, Qx!=nullptr ? Qx + inst*d.nbtot : nullptr, nullptr, nullptr);
 		__syncwarp();
 		}
+	}
+
+/* the same two kernels with four warps per instance (ric_team.cuh): one CTA of 128 threads works on one instance at a time, the
+ * factor stash is one slot per CTA; the forward sweep is warp 0's */
+__global__ void __launch_bounds__(HBT_THREADS) hbt_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+		double *__restrict__ ux, double *__restrict__ pi, double *__restrict__ Pb, double *__restrict__ stash,
+		const double *__restrict__ Qx, const double *__restrict__ qx)
+	{
+	const int tid = threadIdx.x;
+	hb_ctx c = hb_make_ctx(d, hb_smem, tid&31);
+	double *Lst = stash + (long long)blockIdx.x*d.L_stride;
+	for(long long inst=blockIdx.x; inst<n_inst; inst+=gridDim.x)
+		{
+		const double *in_inst = in + inst*d.in_stride;
+		hbt_backward<true>(c, tid, d, in_inst, Lst, nullptr, nullptr, Qx!=nullptr ? Qx + inst*d.nbtot : nullptr,
+				qx!=nullptr ? qx + inst*d.nbtot : nullptr, Pb!=nullptr ? Pb + inst*d.pi_stride : nullptr);
+		if(tid<32) hb_forward(c, d, in_inst, Lst, nullptr, nullptr, false, ux + inst*d.ux_stride, pi + inst*d.pi_stride, true);
+		hbt_sync();
+		}
+	}
+
+__global__ void __launch_bounds__(HBT_THREADS) hbt_ric_trf_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, double *__restrict__ L,
+		const double *__restrict__ Qx)
+	{
+	const int tid = threadIdx.x;
+	hb_ctx c = hb_make_ctx(d, hb_smem, tid&31);
+	for(long long inst=blockIdx.x; inst<n_inst; inst+=gridDim.x)
+		hbt_backward<false>(c, tid, d, in + inst*d.in_stride, L + inst*d.L_stride, nullptr, nullptr, Qx!=nullptr ? Qx + inst*d.nbtot : nullptr, nullptr, nullptr);
 	}
 
 /* solve with the stored factor; b and [r q] are taken from the instance block (new right-hand sides are
@@ -270,11 +299,39 @@ extern "C" int hb_device_sm_count(int device)
 	return n;
 	}
 
+/* launch shape of the four-warps-per-instance kernels: CTAs of one instance, as many per SM as the shared memory holds.
+ * HPMPC_B200_TEAM=0 keeps the one-warp-per-instance kernels (A/B runs) */
+static int hbt_grid(const hb_dims *d, long long n_inst, int max_ctas)
+	{
+	const char *e = getenv("HPMPC_B200_TEAM");
+	if(e && e[0]=='0') return 0;
+	int dev = 0, sms = 0;
+	if(cudaGetDevice(&dev)!=cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)!=cudaSuccess) return 0;
+	int per_sm = 233472/(hb_smem_bytes_per_warp(d) + 1024);
+	if(per_sm>16) per_sm = 16;
+	if(per_sm<1) return 0;
+	long long g = (long long)sms*per_sm;
+	if(g>n_inst) g = n_inst;
+	if(max_ctas>0 && g>max_ctas) g = max_ctas;
+	return (int)(g<1 ? 1 : g);
+	}
+
 extern "C" int hb_launch_ric_sv(const hb_dims *d, long long n_inst, const double *in, double *ux, double *pi, double *Pb,
 		double *stash, int n_slots, int grid, int warps, void *stream, const double *Qx, const double *qx)
 	{
 	if(d->nzM>64) { fprintf(stderr, "hpmpc_b200: nu+nx+1 > 64 not supported\n"); return -2; }
 	if(grid*warps>n_slots) return -3;
+	{
+	const int tg = hbt_grid(d, n_inst, n_slots);
+	if(tg>0)
+		{
+		const int tsmem = hb_smem_bytes_per_warp(d);
+		if(hb_prep(hbt_ric_sv_kernel, tsmem)) return -1;
+		hbt_ric_sv_kernel<<<tg, HBT_THREADS, tsmem, (cudaStream_t)stream>>>(*d, n_inst, in, ux, pi, Pb, stash, Qx, qx);
+		HB_CK(cudaGetLastError());
+		return 0;
+		}
+	}
 	int smem = warps*hb_smem_bytes_per_warp(d);
 	if(hb_prep(hb_ric_sv_kernel, smem)) return -1;
 	hb_ric_sv_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, ux, pi, Pb, stash, Qx, qx);
@@ -286,6 +343,17 @@ extern "C" int hb_launch_ric_trf(const hb_dims *d, long long n_inst, const doubl
 		const double *Qx)
 	{
 	if(d->nzM>64) return -2;
+	{
+	const int tg = hbt_grid(d, n_inst, 0);
+	if(tg>0)
+		{
+		const int tsmem = hb_smem_bytes_per_warp(d);
+		if(hb_prep(hbt_ric_trf_kernel, tsmem)) return -1;
+		hbt_ric_trf_kernel<<<tg, HBT_THREADS, tsmem, (cudaStream_t)stream>>>(*d, n_inst, in, L, Qx);
+		HB_CK(cudaGetLastError());
+		return 0;
+		}
+	}
 	int smem = warps*hb_smem_bytes_per_warp(d);
 	if(hb_prep(hb_ric_trf_kernel, smem)) return -1;
 	hb_ric_trf_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, L, Qx);

@@ -66,7 +66,7 @@ static __device__ void hb_forward(const hb_ctx &c, const hb_dims &d, const doubl
 	double *a = c.bufA, *b = c.bufB;
 	{
 	const hb_stage s0 = d.st[0];
-	hb_copy(c, a, Lst + s0.off_L, HB_TRI(s0.nu+s0.nx) + 2*(s0.nu+s0.nx));
+	hb_g2s(c.lane, a, Lst + s0.off_L, HB_TRI(s0.nu+s0.nx) + 2*(s0.nu+s0.nx));
 	}
 	for(int n=0; n<d.N; n++)
 		{
@@ -78,8 +78,9 @@ static __device__ void hb_forward(const hb_ctx &c, const hb_dims &d, const doubl
 			hb_prefetch_l2(Lst + s2.off_L, HB_TRI(s2.nu+s2.nx) + 2*(s2.nu+s2.nx), c.lane);
 			if(n+1<d.N) hb_prefetch_l2(in_inst + s1.off_BAbt, (s1.nu+s1.nx+1)*s1.nx1, c.lane);
 			}
-		hb_copy(c, b, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
-		hb_load_BAbt(c, s, in_inst);
+		hb_g2s(c.lane, b, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
+		hb_load_BAbt_async(c, s, in_inst);
+		hb_g2s_wait();
 		__syncwarp();
 		hb_stage_forward(c, s, s1, n, a, b, lrow, bvec, trs, ux, pi, compute_pi);
 		double *t = a; a = b; b = t;
@@ -120,9 +121,10 @@ static __device__ void hb_trs_backward(const hb_ctx &c, const hb_dims &d, const 
 			hb_prefetch_l2(Lst + sp.off_L, HB_TRI(sp.nu+sp.nx) + 2*(sp.nu+sp.nx), lane);
 			hb_prefetch_l2(in_inst + sp.off_BAbt, (sp.nu+sp.nx+1)*sp.nx1, lane);
 			}
-		hb_copy(c, c.bufA, Lst + s.off_L, HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx));
-		if(compute_Pb) hb_copy(c, c.bufB, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
-		hb_load_BAbt(c, s, in_inst);
+		hb_g2s(lane, c.bufA, Lst + s.off_L, HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx));
+		if(compute_Pb) hb_g2s(lane, c.bufB, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
+		hb_load_BAbt_async(c, s, in_inst);
+		hb_g2s_wait();
 		__syncwarp();
 		hb_trs_stage_back(c, s, s1, n, c.bufA, c.bufB, bvec, rqvec, qx, d.idxb, ux, Pb, compute_Pb, in_inst);
 		}

@@ -1,0 +1,258 @@
+/*
+ * ric_team.cuh -- any-size backward (factorisation) sweep with FOUR warps per instance.
+ *
+ * The one-warp-per-instance sweeps of ric_sweeps.cuh keep [B A b]' and two packed factors of an instance in shared memory
+ * (38 KB at nu+nx+1 = 49), so an SM holds five or six instances -- and with one warp each that is one warp per scheduler: every
+ * dependent instruction pays its full latency (ncu, config 4: 5.7 cycles per warp instruction, FP64 pipe 10 % busy).  Here the
+ * same shared-memory footprint is worked on by a CTA of 128 threads: warp w owns rows 16w .. 16w+15 of W / H / L (lane = (row
+ * slot, half) as in ric_generic.cuh, one row per lane), so an SM runs 20-24 warps and an instance's stage takes a quarter of
+ * the dependent steps.  The forward sweep of the same instance follows on warp 0 (hb_forward) or in a kernel of its own
+ * (multi-kernel IPM driver).
+ *
+ * Restates the same reference lines as hb_stage_factor (lqcp_solvers/d_back_ric_rec.c:236-333; readable twin
+ * d_back_ric_rec_libstr.c:125-181 / :229-305); the stage routine is kept operation-for-operation equal to the one-warp
+ * version's register-tiled path (same sums in the same order), so both give the same bits.
+ */
+#pragma once
+#include "ric_sweeps.cuh"
+
+#define HBT_WARPS 4
+#define HBT_THREADS (32*HBT_WARPS)
+
+__device__ __forceinline__ void hbt_sync() { __syncthreads(); }
+
+/* one 4-column panel of cur <- chol_mn(cur + W W') on the 16 rows of this warp (row0 .. row0+15); see hbg_syrk_chol.
+ * Dblk: 16 doubles of shared scratch for the diagonal block */
+__device__ __forceinline__ void hbt_panel_acc(double *cur, const double *sW, int ld, int lane, int row0, int m, int nux, int nx1, int jb,
+		double (&acc)[4], int &irow_out, bool &valid_out)
+	{
+	const int rt = lane>>1, h = lane&1;
+	int i = row0 + rt;
+	const bool valid = i<m;
+	i = valid ? i : m-1;
+	const int wrow = i*ld, lrow = HB_TRI(i);
+	int wj[4], lj[4];
+#pragma unroll
+	for(int cc=0; cc<4; cc++) { int j = jb+cc; j = j<nux ? j : nux-1; wj[cc] = j*ld; lj[cc] = HB_TRI(j); }
+	acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 0.0;
+#pragma unroll 4
+	for(int k=h; k<nx1; k+=2)
+		{
+		const double b0 = sW[wj[0]+k], b1 = sW[wj[1]+k], b2 = sW[wj[2]+k], b3 = sW[wj[3]+k];
+		const double a = sW[wrow+k];
+		acc[0] = fma(a, b0, acc[0]); acc[1] = fma(a, b1, acc[1]);
+		acc[2] = fma(a, b2, acc[2]); acc[3] = fma(a, b3, acc[3]);
+		}
+#pragma unroll 4
+	for(int k=h; k<jb; k+=2)
+		{
+		const double b0 = cur[lj[0]+k], b1 = cur[lj[1]+k], b2 = cur[lj[2]+k], b3 = cur[lj[3]+k];
+		const double a = -cur[lrow+k];
+		acc[0] = fma(a, b0, acc[0]); acc[1] = fma(a, b1, acc[1]);
+		acc[2] = fma(a, b2, acc[2]); acc[3] = fma(a, b3, acc[3]);
+		}
+#pragma unroll
+	for(int cc=0; cc<4; cc++)
+		{
+		double v = acc[cc] + __shfl_xor_sync(HB_FULL, acc[cc], 1);
+		if((jb+cc<nux) && (jb+cc<=i)) v += cur[lrow+jb+cc];
+		acc[cc] = v;
+		}
+	irow_out = i; valid_out = valid;
+	}
+
+/* the whole factorisation of one stage by the team: cur <- chol_mn(cur + W W'), W in sW (m x nx1), Dblk 16 doubles */
+__device__ __forceinline__ void hbt_syrk_chol(double *cur, const double *sW, int ld, int tid, int m, int nux, int nx1, double *Dblk)
+	{
+	const int warp = tid>>5, lane = tid&31, h = lane&1;
+	const int row0 = 16*warp;
+	double *dinv = cur + HB_TRI(nux) + nux;
+	for(int jb=0; jb<nux; jb+=4)
+		{
+		const bool active = (row0+15>=jb) && (row0<m);                 /* warp-uniform */
+		double acc[4]; int i = 0; bool valid = false;
+		if(active)
+			{
+			hbt_panel_acc(cur, sW, ld, lane, row0, m, nux, nx1, jb, acc, i, valid);
+			if(valid && h==0 && i>=jb && i<jb+4)
+				{
+#pragma unroll
+				for(int cc=0; cc<4; cc++) if(jb+cc<=i) Dblk[4*(i-jb)+cc] = acc[cc];
+				}
+			}
+		hbt_sync();
+		if(active)
+			{
+			double D[4][4], dd[4], iv[4];
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+#pragma unroll
+				for(int c2=0; c2<=cc; c2++)
+					D[cc][c2] = (jb+cc<nux) ? Dblk[4*cc+c2] : (c2==cc ? 1.0 : 0.0);
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+				{
+				const double piv = D[cc][cc];
+				const double inv = (piv>1e-15) ? hbg_rsqrt(piv) : 0.0;
+				dd[cc] = piv*inv; iv[cc] = inv;
+#pragma unroll
+				for(int c2=cc+1; c2<4; c2++) D[c2][cc] *= inv;
+#pragma unroll
+				for(int c2=cc+1; c2<4; c2++)
+#pragma unroll
+					for(int c3=cc+1; c3<=c2; c3++) D[c2][c3] = fma(-D[c2][cc], D[c3][cc], D[c2][c3]);
+				}
+			double x[4];
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+				{
+				double v = acc[cc];
+#pragma unroll
+				for(int c2=0; c2<cc; c2++) v = fma(-x[c2], D[cc][c2], v);
+				x[cc] = v*iv[cc];
+				}
+			if(valid)
+				{
+				const int lrow = HB_TRI(i);
+#pragma unroll
+				for(int cc=0; cc<4; cc++)
+					if((cc>>1)==h && jb+cc<nux && jb+cc<=i)
+						cur[lrow+jb+cc] = (i==jb+cc) ? dd[cc] : x[cc];
+				}
+			if(lane==0 && (jb>>4)==warp)
+				{
+				dinv[jb] = iv[0];
+				if(jb+1<nux) dinv[jb+1] = iv[1];
+				if(jb+2<nux) dinv[jb+2] = iv[2];
+				if(jb+3<nux) dinv[jb+3] = iv[3];
+				}
+			}
+		hbt_sync();
+		}
+	}
+
+/* one backward stage by the team (the arguments of hb_stage_factor; c.lane is not used, tid is) */
+template<bool GRAD>
+__device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const hb_stage &s, int nu1,
+		const double *__restrict__ in_inst, const double *bvec, const double *rqvec,
+		const double *Qx, const double *qx, const int *__restrict__ idxb, double *Pb,
+		double *cur, const double *prev)
+	{
+	const int warp = tid>>5, lane = tid&31;
+	const int nux = s.nu + s.nx, nx1 = s.nx1;
+	const int m = GRAD ? nux+1 : nux;
+	const int ntri = HB_TRI(nux) + (GRAD ? nux : 0);
+	double *sW = c.sW; const int ldW = c.ldW;
+	{
+	const double *g = in_inst + s.off_RSQ;
+	for(int e=tid; e<ntri; e+=HBT_THREADS) hb_cp8(cur + e, g + e);
+	if(nx1>0)
+		{
+		const double *gb = in_inst + s.off_BAbt;
+		const int tot = m*nx1;
+		int i = tid/nx1, j = tid - i*nx1;
+		for(int e=tid; e<tot; e+=HBT_THREADS)
+			{
+			hb_cp8(sW + i*ldW + j, gb + e);
+			j += HBT_THREADS;
+			while(j>=nx1) { j -= nx1; i++; }
+			}
+		}
+	hb_g2s_wait();
+	}
+	hbt_sync();
+	if(GRAD && rqvec!=nullptr)
+		for(int e=tid; e<nux; e+=HBT_THREADS) cur[HB_TRI(nux)+e] = rqvec[s.off_ux+e];
+	if(GRAD && bvec!=nullptr && nx1>0)
+		for(int j=tid; j<nx1; j+=HBT_THREADS) sW[nux*ldW+j] = bvec[s.off_pi+j];
+	hbt_sync();
+	if(Qx!=nullptr && s.nb>0)
+		{
+		for(int j=tid; j<s.nb; j+=HBT_THREADS)
+			{
+			int id = idxb[s.off_c+j];
+			cur[HB_TRI(id)+id] += Qx[s.off_c+j];
+			if(GRAD && qx!=nullptr) cur[HB_TRI(nux)+id] += qx[s.off_c+j];
+			}
+		}
+	if(Qx!=nullptr && s.ng>0)
+		{
+		/* general constraints (see hb_stage_factor); rows over the team's threads */
+		hbt_sync();
+		const int ng = s.ng;
+		const double *G = in_inst + s.off_DCt;
+		const double *Qg = Qx + s.off_c + s.nb;
+		for(int i=tid; i<m; i+=HBT_THREADS)
+			{
+			double *hi = cur + HB_TRI(i);
+			if(i<nux)
+				{
+				const double *gi = G + i*ng;
+				for(int k=0; k<=i; k++)
+					{
+					const double *gk = G + k*ng;
+					double acc = 0.0;
+					for(int j=0; j<ng; j++) acc += gi[j]*Qg[j]*gk[j];
+					hi[k] += acc;
+					}
+				}
+			else if(qx!=nullptr)
+				{
+				const double *qg = qx + s.off_c + s.nb;
+				for(int k=0; k<nux; k++)
+					{
+					const double *gk = G + k*ng;
+					double acc = 0.0;
+					for(int j=0; j<ng; j++) acc += qg[j]*gk[j];
+					hi[k] += acc;
+					}
+				}
+			}
+		}
+	hbt_sync();
+	if(nx1>0)
+		{
+		/* W = [B A b]' Lxx_{n+1}: rows are independent, every warp does its own 16 */
+		if(16*warp<m) hbg_trmm<1>(sW + 16*warp*ldW, ldW, lane, m - 16*warp, nx1, prev, nu1);
+		hbt_sync();
+		if(GRAD)
+			{
+			const double *wl = sW + nux*ldW;
+			if(Pb!=nullptr)
+				for(int i=tid; i<nx1; i+=HBT_THREADS)
+					{
+					double acc = 0.0;
+					for(int k=0; k<=i; k++) acc += prev[HB_TRI(nu1+i)+nu1+k]*wl[k];
+					Pb[s.off_pi+i] = acc;
+					}
+			hbt_sync();
+			for(int j=tid; j<nx1; j+=HBT_THREADS) sW[nux*ldW+j] += prev[HB_TRI(nu1+nx1)+nu1+j];
+			hbt_sync();
+			}
+		}
+	hbt_syrk_chol(cur, sW, ldW, tid, m, nux, nx1, c.sV);
+	}
+
+/* backward sweep n = N..0 by the team; the factor of every stage goes to Lst (global) */
+template<bool GRAD>
+__device__ void hbt_backward(const hb_ctx &c, int tid, const hb_dims &d, const double *in_inst, double *Lst,
+		const double *bvec, const double *rqvec, const double *Qx, const double *qx, double *Pb)
+	{
+	double *cur = c.bufA, *prev = c.bufB;
+	for(int n=d.N; n>=0; n--)
+		{
+		const hb_stage s = d.st[n];
+		const int nu1 = (n<d.N) ? d.st[n+1].nu : 0;
+		if(n>0 && tid<32)
+			{
+			const hb_stage sp = d.st[n-1];
+			hb_prefetch_l2(in_inst + sp.off_BAbt, HB_EVEN((sp.nu+sp.nx+1)*sp.nx1) + HB_TRI(sp.nu+sp.nx) + sp.nu+sp.nx, tid);
+			}
+		hbt_stage_factor<GRAD>(c, tid, s, nu1, in_inst, bvec, rqvec, Qx, qx, d.idxb, Pb, cur, prev);
+		const int nL = HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx);
+		double *dst = Lst + s.off_L;
+		for(int e=tid; e<nL; e+=HBT_THREADS) dst[e] = cur[e];
+		double *t = cur; cur = prev; prev = t;
+		hbt_sync();
+		}
+	}
