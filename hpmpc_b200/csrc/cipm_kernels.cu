@@ -399,7 +399,9 @@ template<class S> struct hb_cipm_sv
 	{
 	static int prep(int) { return 0; }
 	static bool use() { return false; }
+	static bool has_trs() { return false; }
 	static void launch(const hb_cipm_args &, int, cudaStream_t, bool) {}
+	static void launch_trs(const hb_cipm_args &, int, cudaStream_t) {}
 	};
 template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 	{
@@ -410,6 +412,8 @@ template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 	static int prep(int) { return hb_prep(hb_cipm_sv2_kernel<C, true>, smem()) || hb_prep(hb_cipm_sv2_kernel<C, false>, smem_slim()); }
 	/* HPMPC_B200_IPM_SV2=0 keeps the one-instance-per-warp sweep (A/B runs) */
 	static bool use() { const char *e = getenv("HPMPC_B200_IPM_SV2"); return !(e && e[0]=='0'); }
+	static bool has_trs() { return false; }
+	static void launch_trs(const hb_cipm_args &, int, cudaStream_t) {}
 	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st, bool fwd)
 		{
 		const int w = fwd ? WARPS : WARPS_SLIM;
@@ -420,9 +424,11 @@ template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 		}
 	};
 
-/* any-size patterns: factor + solve (predictor) with four warps per instance (ric_team.cuh): one CTA per instance, handed out by an
- * atomic counter; the forward sweep that follows is warp 0's */
-__global__ void __launch_bounds__(HBT_THREADS) hb_cipm_team_sv_kernel(hb_cipm_args a)
+/* any-size patterns: the sweeps with four warps per instance (ric_team.cuh), one CTA per instance.  WHICH 0: factor + solve
+ * (predictor), instances handed out by an atomic counter; 1: solve with the stored factor (corrector) */
+extern "C" int hbt_smem_bytes(const hb_dims *d);
+template<int WHICH>
+__global__ void __launch_bounds__(HBT_THREADS) hb_cipm_team_kernel(hb_cipm_args a)
 	{
 	typedef hb_sweeps_generic S;
 	const hb_dims &d = a.d;
@@ -430,49 +436,74 @@ __global__ void __launch_bounds__(HBT_THREADS) hb_cipm_team_sv_kernel(hb_cipm_ar
 	const long long n_items = a.act ? (long long)*a.n_act : a.n_inst;
 	if(n_items==0) return;
 	hb_ctx c = hb_make_ctx(d, hb_smem, tid&31);
+	double *P = hb_smem + hb_smem_doubles_per_warp(d.nzM, d.nxM);
 	__shared__ int s_it;
+	long long it = (long long)blockIdx.x - gridDim.x;
 	for(;;)
 		{
-		if(tid==0) s_it = atomicAdd(a.wq, 1);
-		__syncthreads();
-		const long long it = s_it;
-		__syncthreads();
+		if(WHICH==0)
+			{
+			if(tid==0) s_it = atomicAdd(a.wq, 1);
+			__syncthreads();
+			it = s_it;
+			__syncthreads();
+			}
+		else it += gridDim.x;
 		if(it>=n_items) break;
 		const long long inst = a.act ? a.act[it] : it;
 		const int st = a.si[inst*CIPM_I];
-		if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
-		const bool p2 = (st==CS_P2_SV);
 		const hb_ipm_ws w = hb_ipm_make_ws<S>(d, a.work + inst*a.work_stride);
 		const double *in_inst = a.in + inst*d.in_stride;
-		hbt_backward<true>(c, tid, d, in_inst, w.L, p2 ? w.res_b : nullptr, p2 ? w.res_q : w.rq0, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
-		if(tid<32)
+		if(WHICH==0)
 			{
-			S::forward_sv(c, d, in_inst, w, p2 ? w.res_b : nullptr, w.dux, w.dpi);
-			__syncwarp();
+			if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
+			const bool p2 = (st==CS_P2_SV);
+			hbt_backward<true>(c, tid, d, in_inst, w.L, p2 ? w.res_b : nullptr, p2 ? w.res_q : w.rq0, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
+			hbt_forward(c, tid, P, d, in_inst, w.L, nullptr, p2 ? w.res_b : nullptr, false, w.dux, w.dpi, true);
 			if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_A : CS_P1_A;
+			}
+		else
+			{
+			if(st!=CS_P1_TRS && st!=CS_P2_TRS) continue;
+			const bool p2 = (st==CS_P2_TRS);
+			const double *bv = p2 ? w.res_b : w.b0, *rqv = p2 ? w.res_q : w.rq0;
+			hbt_trs_backward(c, tid, P, d, in_inst, w.L, bv, rqv, w.v(CV_QXG), w.dux, w.Pb, false);
+			hbt_forward(c, tid, P, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
+			if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_B : CS_P1_B;
 			}
 		__syncthreads();
 		}
 	}
 template<> struct hb_cipm_sv<hb_sweeps_generic>
 	{
-	/* the kernel has a static shared word of its own (the queue ticket), so the dynamic maximum is set below the architectural one */
+	/* the kernels have a static shared word of their own (the queue ticket), so the dynamic maximum is set below the architectural one */
 	static int prep(int)
 		{
-		HB_CK(cudaFuncSetAttribute(hb_cipm_team_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
+		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
+		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
 		return 0;
 		}
-	/* HPMPC_B200_TEAM=0 keeps the one-warp-per-instance sweep (A/B runs) */
+	/* HPMPC_B200_TEAM=0 keeps the one-warp-per-instance sweeps (A/B runs, bit-identical to the fused kernel) */
 	static bool use() { const char *e = getenv("HPMPC_B200_TEAM"); return !(e && e[0]=='0'); }
-	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st, bool)
+	static bool has_trs() { return true; }
+	static int grid(const hb_cipm_args &a, int sms, int smem)
 		{
-		const int smem = hb_smem_bytes_per_warp(&a.d);
-		int per_sm = 233472/(smem + 1024);
+		int per_sm = 232448/(smem + 1024);
 		if(per_sm>16) per_sm = 16;
 		if(per_sm<1) per_sm = 1;
 		long long g = (long long)sms*per_sm;
 		if(g>a.n_inst) g = a.n_inst;
-		hb_cipm_team_sv_kernel<<<(int)(g<1 ? 1 : g), HBT_THREADS, smem, st>>>(a);
+		return (int)(g<1 ? 1 : g);
+		}
+	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st, bool)
+		{
+		const int smem = hbt_smem_bytes(&a.d);
+		hb_cipm_team_kernel<0><<<grid(a, sms, smem), HBT_THREADS, smem, st>>>(a);
+		}
+	static void launch_trs(const hb_cipm_args &a, int sms, cudaStream_t st)
+		{
+		const int smem = hbt_smem_bytes(&a.d);
+		hb_cipm_team_kernel<1><<<grid(a, sms, smem), HBT_THREADS, smem, st>>>(a);
 		}
 	};
 
@@ -538,7 +569,8 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 		else hb_cipm_sweep_kernel<S, 0><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		if(split_fw) hb_cipm_sweep_kernel<S1, 3><<<grid_l, warps_l*32, smem_l, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
-		if(light) hb_cipm_sweep_kernel<S1, 1><<<grid_l, warps_l*32, smem_l, st>>>(a);
+		if(sv2 && hb_cipm_sv<S>::has_trs()) hb_cipm_sv<S>::launch_trs(a, sms, st);
+		else if(light) hb_cipm_sweep_kernel<S1, 1><<<grid_l, warps_l*32, smem_l, st>>>(a);
 		else hb_cipm_sweep_kernel<S, 1><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
 		if(light) hb_cipm_sweep_kernel<S1, 2><<<grid_l, warps_l*32, smem_l, st>>>(a);

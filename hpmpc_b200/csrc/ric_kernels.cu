@@ -64,13 +64,40 @@ __global__ void __launch_bounds__(HBT_THREADS) hbt_ric_sv_kernel(hb_dims d, long
 	{
 	const int tid = threadIdx.x;
 	hb_ctx c = hb_make_ctx(d, hb_smem, tid&31);
+	double *P = hb_smem + hb_smem_doubles_per_warp(d.nzM, d.nxM);
 	double *Lst = stash + (long long)blockIdx.x*d.L_stride;
 	for(long long inst=blockIdx.x; inst<n_inst; inst+=gridDim.x)
 		{
 		const double *in_inst = in + inst*d.in_stride;
 		hbt_backward<true>(c, tid, d, in_inst, Lst, nullptr, nullptr, Qx!=nullptr ? Qx + inst*d.nbtot : nullptr,
 				qx!=nullptr ? qx + inst*d.nbtot : nullptr, Pb!=nullptr ? Pb + inst*d.pi_stride : nullptr);
-		if(tid<32) hb_forward(c, d, in_inst, Lst, nullptr, nullptr, false, ux + inst*d.ux_stride, pi + inst*d.pi_stride, true);
+		hbt_forward(c, tid, P, d, in_inst, Lst, nullptr, nullptr, false, ux + inst*d.ux_stride, pi + inst*d.pi_stride, true);
+		hbt_sync();
+		}
+	}
+
+/* solve with the stored factor by the team (hb_ric_trs_kernel) */
+__global__ void __launch_bounds__(HBT_THREADS) hbt_ric_trs_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, const double *__restrict__ L,
+		double *__restrict__ ux, double *__restrict__ pi, double *__restrict__ work, const double *__restrict__ qx)
+	{
+	const int tid = threadIdx.x;
+	hb_ctx c = hb_make_ctx(d, hb_smem, tid&31);
+	double *P = hb_smem + hb_smem_doubles_per_warp(d.nzM, d.nxM);
+	double *rq = work + (long long)blockIdx.x*(d.ux_stride + 2*d.pi_stride), *bv = rq + d.ux_stride, *Pb = bv + d.pi_stride;
+	for(long long inst=blockIdx.x; inst<n_inst; inst+=gridDim.x)
+		{
+		const double *in_inst = in + inst*d.in_stride;
+		for(int n=0; n<=d.N; n++)
+			{
+			const hb_stage s = d.st[n];
+			const int nux = s.nu+s.nx;
+			for(int i=tid; i<nux; i+=HBT_THREADS) rq[s.off_ux+i] = in_inst[s.off_RSQ+HB_TRI(nux)+i];
+			for(int j=tid; j<s.nx1; j+=HBT_THREADS) bv[s.off_pi+j] = in_inst[s.off_BAbt+nux*s.nx1+j];
+			}
+		hbt_sync();
+		double *uxi = ux + inst*d.ux_stride;
+		hbt_trs_backward(c, tid, P, d, in_inst, L + inst*d.L_stride, bv, rq, qx!=nullptr ? qx + inst*d.nbtot : nullptr, uxi, Pb, true);
+		hbt_forward(c, tid, P, d, in_inst, L + inst*d.L_stride, uxi, bv, true, uxi, pi + inst*d.pi_stride, true);
 		hbt_sync();
 		}
 	}
@@ -299,6 +326,8 @@ extern "C" int hb_device_sm_count(int device)
 	return n;
 	}
 
+extern "C" int hbt_smem_bytes(const hb_dims *d) { return (int)sizeof(double)*hbt_smem_doubles(d->nzM, d->nxM); }
+
 /* launch shape of the four-warps-per-instance kernels: CTAs of one instance, as many per SM as the shared memory holds.
  * HPMPC_B200_TEAM=0 keeps the one-warp-per-instance kernels (A/B runs) */
 static int hbt_grid(const hb_dims *d, long long n_inst, int max_ctas)
@@ -307,7 +336,7 @@ static int hbt_grid(const hb_dims *d, long long n_inst, int max_ctas)
 	if(e && e[0]=='0') return 0;
 	int dev = 0, sms = 0;
 	if(cudaGetDevice(&dev)!=cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)!=cudaSuccess) return 0;
-	int per_sm = 233472/(hb_smem_bytes_per_warp(d) + 1024);
+	int per_sm = 233472/(hbt_smem_bytes(d) + 1024);
 	if(per_sm>16) per_sm = 16;
 	if(per_sm<1) return 0;
 	long long g = (long long)sms*per_sm;
@@ -325,7 +354,7 @@ extern "C" int hb_launch_ric_sv(const hb_dims *d, long long n_inst, const double
 	const int tg = hbt_grid(d, n_inst, n_slots);
 	if(tg>0)
 		{
-		const int tsmem = hb_smem_bytes_per_warp(d);
+		const int tsmem = hbt_smem_bytes(d);
 		if(hb_prep(hbt_ric_sv_kernel, tsmem)) return -1;
 		hbt_ric_sv_kernel<<<tg, HBT_THREADS, tsmem, (cudaStream_t)stream>>>(*d, n_inst, in, ux, pi, Pb, stash, Qx, qx);
 		HB_CK(cudaGetLastError());
@@ -347,7 +376,7 @@ extern "C" int hb_launch_ric_trf(const hb_dims *d, long long n_inst, const doubl
 	const int tg = hbt_grid(d, n_inst, 0);
 	if(tg>0)
 		{
-		const int tsmem = hb_smem_bytes_per_warp(d);
+		const int tsmem = hbt_smem_bytes(d);
 		if(hb_prep(hbt_ric_trf_kernel, tsmem)) return -1;
 		hbt_ric_trf_kernel<<<tg, HBT_THREADS, tsmem, (cudaStream_t)stream>>>(*d, n_inst, in, L, Qx);
 		HB_CK(cudaGetLastError());
@@ -366,6 +395,17 @@ extern "C" int hb_launch_ric_trs(const hb_dims *d, long long n_inst, const doubl
 	{
 	if(d->nzM>64) return -2;
 	if(grid*warps>n_slots) return -3;
+	{
+	const int tg = hbt_grid(d, n_inst, n_slots);
+	if(tg>0)
+		{
+		const int tsmem = hbt_smem_bytes(d);
+		if(hb_prep(hbt_ric_trs_kernel, tsmem)) return -1;
+		hbt_ric_trs_kernel<<<tg, HBT_THREADS, tsmem, (cudaStream_t)stream>>>(*d, n_inst, in, L, ux, pi, work, qx);
+		HB_CK(cudaGetLastError());
+		return 0;
+		}
+	}
 	int smem = warps*hb_smem_bytes_per_warp(d);
 	if(hb_prep(hb_ric_trs_kernel, smem)) return -1;
 	hb_ric_trs_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in, L, ux, pi, work, qx);

@@ -256,3 +256,230 @@ __device__ void hbt_backward(const hb_ctx &c, int tid, const hb_dims &d, const d
 		hbt_sync();
 		}
 	}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* Solve sweeps by the team.  A stage of the forward / solve-only backward sweep is a handful of matrix-vector products with  */
+/* 40-50 terms per entry; on one warp each is a dependent chain of that length, run twice when there are more than 32 entries.  */
+/* Here warp q takes the terms k = k0 + q, k0 + q + 4, ... of every entry, the four partial sums meet in shared memory         */
+/* (P: 4 x 64 doubles behind the one-warp layout).  The sums are therefore ordered differently from the one-warp sweeps:        */
+/* results agree to rounding (tests/test_team.py: 1e-9 and identical IPM iteration counts), not bit for bit.                    */
+/* ---------------------------------------------------------------------------------------------------------------- */
+#define HBT_P_DOUBLES 256
+
+__host__ __device__ inline int hbt_smem_doubles(int nzM, int nxM) { return hb_smem_doubles_per_warp(nzM, nxM) + HBT_P_DOUBLES; }
+
+/* out(o, sum_{k0(o) <= k < k1(o)} a(o,k)*b(o,k)) for o < n_out <= 64; ends with a team barrier */
+template<class K0, class K1, class A, class B, class FIN>
+__device__ __forceinline__ void hbt_dot(int tid, int n_out, double *P, K0 k0, K1 k1, A a, B b, FIN fin)
+	{
+	const int q = tid>>5, lane = tid&31;
+	for(int o=lane; o<n_out; o+=32)
+		{
+		double acc = 0.0;
+		const int ke = k1(o);
+#pragma unroll 4
+		for(int k=k0(o)+q; k<ke; k+=4) acc = fma(a(o, k), b(o, k), acc);
+		P[64*q+o] = acc;
+		}
+	hbt_sync();
+	for(int o=tid; o<n_out; o+=HBT_THREADS) fin(o, (P[o] + P[64+o]) + (P[128+o] + P[192+o]));
+	hbt_sync();
+	}
+
+/* one forward stage by the team: the arguments and the algebra of hb_stage_forward (lqcp_solvers/d_back_ric_rec.c:341-397 sv,
+ * :737-789 trs); the triangular solve with the ks x ks corner stays on warp 0 */
+__device__ __forceinline__ void hbt_stage_forward(const hb_ctx &c, int tid, double *P, const hb_stage &s, const hb_stage &s1, int n,
+		const double *Ln, const double *Ln1, const double *lrow, const double *bvec, bool trs,
+		double *ux, double *pi, bool compute_pi)
+	{
+	const int lane = tid&31;
+	const int nu = s.nu, nux = s.nu+s.nx, nx1 = s.nx1, nu1 = s1.nu, nux1 = s1.nu+s1.nx;
+	const int ks = (n==0) ? nux : nu;
+	const int ld = c.ldW;
+	const double *dinv = Ln + HB_TRI(nux) + nux;
+	const double *sW = c.sW;
+	double *v = c.sV, *xs = c.sV + 64, *tmp = c.sV + 128;
+	for(int i=tid; i<nux; i+=HBT_THREADS)
+		v[i] = (i<ks) ? -(lrow!=nullptr ? lrow[s.off_ux+i] : Ln[HB_TRI(nux)+i]) : ux[s.off_ux+i];
+	hbt_sync();
+	if(ks<nux)
+		hbt_dot(tid, ks, P, [&](int) { return ks; }, [&](int) { return nux; },
+				[&](int o, int k) { return Ln[HB_TRI(k)+o]; }, [&](int, int k) { return v[k]; },
+				[&](int o, double sum) { v[o] -= sum; });
+	if(tid<32)
+		for(int j=ks-1; j>=0; j--)
+			{
+			if(lane==(j&31)) v[j] *= dinv[j];
+			__syncwarp();
+			const double vj = v[j];
+			for(int i=lane; i<j; i+=32) v[i] -= Ln[HB_TRI(j)+i]*vj;
+			__syncwarp();
+			}
+	hbt_sync();
+	for(int i=tid; i<ks; i+=HBT_THREADS) ux[s.off_ux+i] = v[i];
+	hbt_dot(tid, nx1, P, [&](int) { return 0; }, [&](int) { return nux; },
+			[&](int o, int k) { return sW[k*ld+o]; }, [&](int, int k) { return v[k]; },
+			[&](int o, double sum)
+				{
+				const double acc = (bvec!=nullptr ? bvec[s.off_pi+o] : sW[nux*ld+o]) + sum;
+				if(trs && compute_pi) pi[s.off_pi+o] = ux[s1.off_ux+nu1+o];
+				ux[s1.off_ux+nu1+o] = acc;
+				xs[o] = acc;
+				});
+	if(compute_pi)
+		{
+		hbt_dot(tid, nx1, P, [&](int o) { return o; }, [&](int) { return nx1; },
+				[&](int o, int k) { return Ln1[HB_TRI(nu1+k)+nu1+o]; }, [&](int, int k) { return xs[k]; },
+				[&](int o, double sum) { tmp[o] = (trs ? 0.0 : Ln1[HB_TRI(nux1)+nu1+o]) + sum; });
+		hbt_dot(tid, nx1, P, [&](int) { return 0; }, [&](int o) { return o+1; },
+				[&](int o, int k) { return Ln1[HB_TRI(nu1+o)+nu1+k]; }, [&](int, int k) { return tmp[k]; },
+				[&](int o, double sum) { pi[s.off_pi+o] = (trs ? pi[s.off_pi+o] : 0.0) + sum; });
+		}
+	}
+
+/* stage data of the team's solve sweeps: packed factor(s) and [B A b]' by all threads (LDGSTS) */
+__device__ __forceinline__ void hbt_g2s(int tid, double *dst_smem, const double *__restrict__ src, int n)
+	{
+	for(int e=tid; e<n; e+=HBT_THREADS) hb_cp8(dst_smem + e, src + e);
+	}
+__device__ __forceinline__ void hbt_load_BAbt(const hb_ctx &c, int tid, const hb_stage &s, const double *__restrict__ in_inst)
+	{
+	const int nx1 = s.nx1, tot = (s.nu+s.nx+1)*nx1;
+	if(nx1<=0) return;
+	const double *gb = in_inst + s.off_BAbt;
+	int i = tid/nx1, j = tid - i*nx1;
+	for(int e=tid; e<tot; e+=HBT_THREADS)
+		{
+		hb_cp8(c.sW + i*c.ldW + j, gb + e);
+		j += HBT_THREADS;
+		while(j>=nx1) { j -= nx1; i++; }
+		}
+	}
+
+/* forward sweep n = 0..N-1 by the team (hb_forward) */
+static __device__ void hbt_forward(const hb_ctx &c, int tid, double *P, const hb_dims &d, const double *in_inst, const double *Lst,
+		const double *lrow, const double *bvec, bool trs, double *ux, double *pi, bool compute_pi)
+	{
+	double *a = c.bufA, *b = c.bufB;
+	{
+	const hb_stage s0 = d.st[0];
+	hbt_g2s(tid, a, Lst + s0.off_L, HB_TRI(s0.nu+s0.nx) + 2*(s0.nu+s0.nx));
+	}
+	for(int n=0; n<d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		const hb_stage s1 = d.st[n+1];
+		if(n+2<=d.N && tid<32)
+			{
+			const hb_stage s2 = d.st[n+2];
+			hb_prefetch_l2(Lst + s2.off_L, HB_TRI(s2.nu+s2.nx) + 2*(s2.nu+s2.nx), tid);
+			if(n+1<d.N) hb_prefetch_l2(in_inst + s1.off_BAbt, (s1.nu+s1.nx+1)*s1.nx1, tid);
+			}
+		hbt_g2s(tid, b, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
+		hbt_load_BAbt(c, tid, s, in_inst);
+		hb_g2s_wait();
+		hbt_sync();
+		hbt_stage_forward(c, tid, P, s, s1, n, a, b, lrow, bvec, trs, ux, pi, compute_pi);
+		double *t = a; a = b; b = t;
+		}
+	}
+
+/* one backward stage of the solve-only sweep by the team (hb_trs_stage_back; lqcp_solvers/d_back_ric_rec.c:628-732) */
+__device__ __forceinline__ void hbt_trs_stage_back(const hb_ctx &c, int tid, double *P, const hb_stage &s, const hb_stage &s1, int n,
+		const double *Ln, const double *Ln1, const double *bvec, const double *rqvec, const double *qx,
+		const int *__restrict__ idxb, double *ux, double *Pb, bool compute_Pb, const double *__restrict__ in_inst)
+	{
+	const int lane = tid&31;
+	const int nu = s.nu, nux = s.nu+s.nx, nx1 = s.nx1, nu1 = s1.nu;
+	const int ks = (n==0) ? nux : nu;
+	const int ld = c.ldW;
+	const double *dinv = Ln + HB_TRI(nux) + nux;
+	const double *sW = c.sW;
+	double *v = c.sV, *tmp = c.sV + 64, *t2 = c.sV + 128;
+	if(compute_Pb)
+		{
+		hbt_dot(tid, nx1, P, [&](int o) { return o; }, [&](int) { return nx1; },
+				[&](int o, int k) { return Ln1[HB_TRI(nu1+k)+nu1+o]; }, [&](int, int k) { return bvec[s.off_pi+k]; },
+				[&](int o, double sum) { t2[o] = sum; });
+		hbt_dot(tid, nx1, P, [&](int) { return 0; }, [&](int o) { return o+1; },
+				[&](int o, int k) { return Ln1[HB_TRI(nu1+o)+nu1+k]; }, [&](int, int k) { return t2[k]; },
+				[&](int o, double sum) { Pb[s.off_pi+o] = sum; });
+		}
+	for(int i=tid; i<nux; i+=HBT_THREADS) v[i] = rqvec[s.off_ux+i];
+	for(int j=tid; j<nx1; j+=HBT_THREADS) tmp[j] = Pb[s.off_pi+j] + ux[s1.off_ux+nu1+j];
+	hbt_sync();
+	if(qx!=nullptr && s.nb>0)
+		{
+		for(int j=tid; j<s.nb; j+=HBT_THREADS) v[idxb[s.off_c+j]] += qx[s.off_c+j];
+		hbt_sync();
+		}
+	if(qx!=nullptr && s.ng>0 && in_inst!=nullptr)
+		{
+		const double *G = in_inst + s.off_DCt, *qg = qx + s.off_c + s.nb;
+		for(int i=tid; i<nux; i+=HBT_THREADS)
+			{
+			double acc = v[i];
+			for(int j=0; j<s.ng; j++) acc += G[i*s.ng+j]*qg[j];
+			v[i] = acc;
+			}
+		hbt_sync();
+		}
+	hbt_dot(tid, nux, P, [&](int) { return 0; }, [&](int) { return nx1; },
+			[&](int o, int k) { return sW[o*ld+k]; }, [&](int, int k) { return tmp[k]; },
+			[&](int o, double sum) { v[o] += sum; });
+	if(tid<32)
+		for(int j=0; j<ks; j++)
+			{
+			if(lane==(j&31)) v[j] *= dinv[j];
+			__syncwarp();
+			const double vj = v[j];
+			for(int i=j+1+lane; i<nux; i+=32) v[i] -= Ln[HB_TRI(i)+j]*vj;
+			__syncwarp();
+			}
+	hbt_sync();
+	for(int i=tid; i<nux; i+=HBT_THREADS) ux[s.off_ux+i] = v[i];
+	hbt_sync();
+	(void)nu;
+	}
+
+/* solve-only backward vector sweep by the team; w is kept in ux (hb_trs_backward) */
+static __device__ void hbt_trs_backward(const hb_ctx &c, int tid, double *P, const hb_dims &d, const double *in_inst, const double *Lst,
+		const double *bvec, const double *rqvec, const double *qx, double *ux, double *Pb, bool compute_Pb)
+	{
+	{
+	const hb_stage s = d.st[d.N];
+	const int nux = s.nu+s.nx;
+	for(int i=tid; i<nux; i+=HBT_THREADS) ux[s.off_ux+i] = rqvec[s.off_ux+i];
+	hbt_sync();
+	if(qx!=nullptr) for(int j=tid; j<s.nb; j+=HBT_THREADS) ux[s.off_ux+d.idxb[s.off_c+j]] += qx[s.off_c+j];
+	hbt_sync();
+	if(qx!=nullptr && s.ng>0)
+		{
+		const double *G = in_inst + s.off_DCt, *qg = qx + s.off_c + s.nb;
+		for(int i=tid; i<nux; i+=HBT_THREADS)
+			{
+			double acc = ux[s.off_ux+i];
+			for(int j=0; j<s.ng; j++) acc += G[i*s.ng+j]*qg[j];
+			ux[s.off_ux+i] = acc;
+			}
+		hbt_sync();
+		}
+	}
+	for(int n=d.N-1; n>=0; n--)
+		{
+		const hb_stage s = d.st[n];
+		const hb_stage s1 = d.st[n+1];
+		if(n>0 && tid<32)
+			{
+			const hb_stage sp = d.st[n-1];
+			hb_prefetch_l2(Lst + sp.off_L, HB_TRI(sp.nu+sp.nx) + 2*(sp.nu+sp.nx), tid);
+			hb_prefetch_l2(in_inst + sp.off_BAbt, (sp.nu+sp.nx+1)*sp.nx1, tid);
+			}
+		hbt_g2s(tid, c.bufA, Lst + s.off_L, HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx));
+		if(compute_Pb) hbt_g2s(tid, c.bufB, Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx));
+		hbt_load_BAbt(c, tid, s, in_inst);
+		hb_g2s_wait();
+		hbt_sync();
+		hbt_trs_stage_back(c, tid, P, s, s1, n, c.bufA, c.bufB, bvec, rqvec, qx, d.idxb, ux, Pb, compute_Pb, in_inst);
+		}
+	}

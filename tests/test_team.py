@@ -1,6 +1,8 @@
-"""Four-warps-per-instance factorisation sweep of the any-size kernels (hpmpc_b200/csrc/ric_team.cuh) against the one-warp-per-instance
-sweep it replaces (HPMPC_B200_TEAM=0): the stage routine performs the same sums in the same order, so factor, solution and IPM
-iterates must be BIT-identical; and against the oracle (the reference's algorithm, lqcp_solvers/d_back_ric_rec.c:236-397)."""
+"""Four-warps-per-instance sweeps of the any-size kernels (hpmpc_b200/csrc/ric_team.cuh) against the one-warp-per-instance sweeps
+they replace (HPMPC_B200_TEAM=0).  The factorisation performs the same sums in the same order, so the factor must be BIT-identical;
+the solve sweeps split every dot product over the four warps, so solutions agree to rounding (1e-11 here, 1e-9 is the bar) and the
+IPM must take the same number of iterations; and against the oracle (the reference's algorithm,
+lqcp_solvers/d_back_ric_rec.c:236-397)."""
 import os
 
 import numpy as np
@@ -24,6 +26,11 @@ def _with_team(flag, fn):
         os.environ.pop("HPMPC_B200_TEAM", None)
 
 
+def _close(x, y):
+    xa, ya = x.cpu().numpy(), y.cpu().numpy()
+    return float(np.max(np.abs(xa - ya) / np.maximum(1.0, np.abs(ya))))
+
+
 def _batch(mk, n, first):
     import torch
     probs = [mk(tuple(x)) for x in problems.instance_xi(n, first=first)]
@@ -38,7 +45,7 @@ def _batch(mk, n, first):
     ("wide", lambda xi: problems.mass_spring_ocp(30, 12, 6, bounds=False, xi=xi), 40),             # 43 rows
     ("tiny", lambda xi: problems.mass_spring_ocp(2, 1, 3, bounds=False, xi=xi), 17),
 ])
-def test_team_sv_and_trf_equal_one_warp_bit_for_bit(name, mk, n):
+def test_team_sv_trf_trs_equal_one_warp(name, mk, n):
     import torch
     L = capi.product()
     probs, h, blk = _batch(mk, n, 900)
@@ -57,7 +64,7 @@ def test_team_sv_and_trf_equal_one_warp_bit_for_bit(name, mk, n):
         return Lf
 
     a, b = _with_team(True, sv), _with_team(False, sv)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert _close(a[0], b[0]) < 1e-11 and _close(a[1], b[1]) < 1e-11
     fa, fb = _with_team(True, trf), _with_team(False, trf)
     # a stage's block of the factor is [triangle | gradient row | inverse diagonal]; trf leaves the gradient row undefined
     p0 = probs[0]
@@ -69,6 +76,16 @@ def test_team_sv_and_trf_equal_one_warp_bit_for_bit(name, mk, n):
         mask[o + nux * (nux + 1) // 2 + nux:o + nux * (nux + 1) // 2 + 2 * nux] = True
     mk_t = torch.from_numpy(mask).cuda()
     assert torch.equal(fa[:, mk_t], fb[:, mk_t])
+
+    # solve with the stored factor (trs): b, q, r taken from the block
+    def trs():
+        ux, pi = z(h.sz.ux_stride), z(h.sz.pi_stride)
+        assert L.hpmpc_b200_d_back_ric_rec_trs_batch(h.h, n, blk.data_ptr(), fa.data_ptr(), ux.data_ptr(), pi.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        return ux, pi
+    ta, tb = _with_team(True, trs), _with_team(False, trs)
+    assert _close(ta[0], tb[0]) < 1e-11 and _close(ta[1], tb[1]) < 1e-11
+    assert _close(ta[0], a[0]) < 1e-9 and _close(ta[1], a[1]) < 1e-9
     for i in (0, n // 2, n - 1):
         o = oracle.ric(probs[i], mode="sv")
         u, x = h.split_ux(a[0][i].cpu().numpy())
@@ -81,9 +98,9 @@ def test_team_sv_and_trf_equal_one_warp_bit_for_bit(name, mk, n):
     ("cfg4", lambda xi: problems.make("cfg4", xi=xi), 96),
     ("general", lambda xi: problems.general_test_problem(8, 3, 10, xi=xi), 80),
 ])
-def test_team_ipm_equals_one_warp_bit_for_bit(name, mk, n):
-    """The multi-kernel IPM driver with the team factorisation kernel (default for any-size patterns) against the fused one-warp
-    kernel: same bits, same iteration counts."""
+def test_team_ipm_equals_one_warp(name, mk, n):
+    """The multi-kernel IPM driver with the team kernels (default for any-size patterns) against the fused one-warp kernel: same
+    iteration counts and status, every output within 1e-9."""
     import torch
     L = capi.product()
     probs, h, blk = _batch(mk, n, 1300)
@@ -97,9 +114,11 @@ def test_team_ipm_equals_one_warp_bit_for_bit(name, mk, n):
         return out
 
     a, b = _with_team(True, ipm), _with_team(False, ipm)
-    for x, y, nm in zip(a, b, ("ux", "pi", "lam", "t", "info")):
-        assert torch.equal(x, y), nm
-    info = a[4].cpu().numpy()
+    info, info_b = a[4].cpu().numpy(), b[4].cpu().numpy()
+    assert np.array_equal(info[:, :2], info_b[:, :2])                   # iteration counts and status
+    ok = torch.from_numpy(info[:, 1] == 0).cuda()                       # an instance that stops short of convergence is ill-conditioned by then
+    for x, y, nm in zip(a[:4], b[:4], ("ux", "pi", "lam", "t")):
+        assert _close(x[ok], y[ok]) < 1e-9, nm
     assert np.mean(info[:, 1] == 0) > 0.9
     o = oracle.ipm(probs[0], k_max=k_max)
     assert int(info[0, 0]) == o["kk"]
