@@ -702,6 +702,31 @@ def run_ours(args):
                                                   "padded_vs_any_size": res_u["padded_into_12_5"]["solves_per_s"] / res_u["any_size_kernels"]["solves_per_s"]}
             except Exception as e:      # noqa: BLE001
                 out["extra"]["unlisted_shape_error"] = repr(e)
+            # BASELINE config 4: time-varying variable-nx OCP on the any-size kernels (four warps per instance, ric_team.cuh)
+            torch.cuda.empty_cache()
+            try:
+                import importlib.util
+                sp4 = importlib.util.spec_from_file_location("bench_cfg4", os.path.join(ROOT, "tools", "bench_cfg4.py"))
+                mod4 = importlib.util.module_from_spec(sp4)
+                sp4.loader.exec_module(mod4)
+                r4 = mod4.measure(8192, 3)
+                w4 = algorithmic_work(r4.pop("problem"))
+                ach_sv = w4["B_sv"] * r4["n_inst"] / (r4["sv_ms"] * 1e-3) / 1e9
+                ach_ipm = w4["B_it"] * r4["mean_kk"] * r4["n_inst"] / (r4["ipm_ms"] * 1e-3) / 1e9
+                out["extra"]["cfg4"] = {
+                    "workload": "time-varying variable-nx OCP (nx 40 -> 4, nu=8, N=20, box bounds), 8192 instances, any-size kernels, FP64",
+                    "sv": {"metric": "lqcp_riccati_solves_per_s", "value": r4["sv_solves_per_s"], "unit": "solves/s", "ms_per_step": r4["sv_ms"],
+                           "roofline": {"bound": "hbm", "achieved": ach_sv, "peak": hbm_peak, "unit": "GB/s", "frac": ach_sv / hbm_peak, "traffic": None,
+                                        "kernel": "hbt_ric_sv_kernel", "algorithmic_bytes_per_solve": w4["B_sv"],
+                                        "fp64_tflops": w4["F_sv"] * r4["sv_solves_per_s"] / 1e12}},
+                    "ipm": {"metric": "box_ipm_qp_solves_per_s", "value": r4["ipm_solves_per_s"], "unit": "solves/s", "ms_per_step": r4["ipm_ms"],
+                            "mean_iterations": r4["mean_kk"], "converged": r4["converged"],
+                            "roofline": {"bound": "hbm", "achieved": ach_ipm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_ipm / hbm_peak, "traffic": None,
+                                         "kernel": "multi-kernel driver: hb_cipm_team_kernel<0> (factor + solve) + hb_cipm_team_kernel<1> (solve) + "
+                                                   "hb_cipm_sweep_kernel<generic,2> (residuals) + hb_cipm_step_kernel",
+                                         "bytes_per_iteration_model": w4["B_it"], "fp64_tflops": w4["F_it"] * r4["mean_kk"] * r4["ipm_solves_per_s"] / 1e12}}}
+            except Exception as e:      # noqa: BLE001
+                out["extra"]["cfg4_error"] = repr(e)
             # the IPM's last KKT system solved again for a new right-hand side (cfg 3 shapes, 4096 instances)
             torch.cuda.empty_cache()
             try:

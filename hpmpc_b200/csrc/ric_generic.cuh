@@ -113,17 +113,20 @@ __device__ __forceinline__ void hb_chol(const hb_ctx &c, double *L, int m, int n
 /* W <- W * Lxx_{n+1} in place (m x nx1, Lxx lower nx1 x nx1 inside the packed prev); h picks the column tile of a round.
  * W[i][j] = sum_{k>=j} W[i][k] Lxx[k][j]: a round reads columns >= its own tiles only, and a lane's reads of its partner's
  * tile happen before the barrier that precedes the writes */
-template<int R>
-__device__ __noinline__ void hbg_trmm(double *sW, int ld, int lane, int m, int nx1, const double *prev, int nu1)
+/* TEAM: called by all 128 threads of a four-warp team (ric_team.cuh): a round is eight column tiles, one per (warp, h) */
+template<bool TEAM> __device__ __forceinline__ void hbg_sync() { if(TEAM) __syncthreads(); else __syncwarp(); }
+template<int R, bool TEAM>
+__device__ __noinline__ void hbg_trmm(double *sW, int ld, int tid, int m, int nx1, const double *prev, int nu1)
 	{
-	const int rt = lane>>1, h = lane&1;
+	const int lane = tid&31, rt = lane>>1, h = lane&1;
+	const int slot = TEAM ? 2*(tid>>5) + h : h, nslot = TEAM ? 8 : 2;
 	int row[R];
 #pragma unroll
 	for(int r=0; r<R; r++) { int i = rt + 16*r; row[r] = (i<m ? i : m-1)*ld; }
 	const int ntile = (nx1+3)>>2;
-	for(int t0=0; t0<ntile; t0+=2)
+	for(int t0=0; t0<ntile; t0+=nslot)
 		{
-		const int t = t0 + h, j0 = 4*t;
+		const int t = t0 + slot, j0 = 4*t;
 		double acc[R][4];
 #pragma unroll
 		for(int r=0; r<R; r++) { acc[r][0] = 0.0; acc[r][1] = 0.0; acc[r][2] = 0.0; acc[r][3] = 0.0; }
@@ -162,7 +165,7 @@ __device__ __noinline__ void hbg_trmm(double *sW, int ld, int lane, int m, int n
 					}
 				}
 			}
-		__syncwarp();
+		hbg_sync<TEAM>();
 		if(t<ntile)
 			{
 #pragma unroll
@@ -173,7 +176,7 @@ __device__ __noinline__ void hbg_trmm(double *sW, int ld, int lane, int m, int n
 					for(int cc=0; cc<4; cc++) if(j0+cc<nx1) sW[row[r]+j0+cc] = acc[r][cc];
 					}
 			}
-		__syncwarp();
+		hbg_sync<TEAM>();
 		}
 	}
 
@@ -212,6 +215,22 @@ __device__ __noinline__ void hbg_syrk_chol(double *cur, const double *sW, int ld
 					acc[r][2] = fma(a, b2, acc[r][2]); acc[r][3] = fma(a, b3, acc[r][3]);
 					}
 			}
+		/* the W part: its two halves joined and added to the entries of H (the team version does this in a pass of its own and
+		 * stores the sum, hbt_syrk: same operations in the same order) */
+		double hw[R][4];
+#pragma unroll
+		for(int r=0; r<R; r++)
+			if(r>=rlo)
+				{
+#pragma unroll
+				for(int cc=0; cc<4; cc++)
+					{
+					double v = acc[r][cc] + __shfl_xor_sync(HB_FULL, acc[r][cc], 1);
+					if((jb+cc<nux) && (jb+cc<=irow[r])) v += cur[lrow[r]+jb+cc];
+					hw[r][cc] = v;
+					acc[r][cc] = 0.0;
+					}
+				}
 #pragma unroll 2
 		for(int k=h; k<jb; k+=2)
 			{
@@ -225,18 +244,14 @@ __device__ __noinline__ void hbg_syrk_chol(double *cur, const double *sW, int ld
 					acc[r][2] = fma(a, b2, acc[r][2]); acc[r][3] = fma(a, b3, acc[r][3]);
 					}
 			}
-		/* join the two halves, add the entries of H, park the panel so that the diagonal block can be read by every lane */
+		/* join the two halves of the L part, add, park the panel so that the diagonal block can be read by every lane */
 #pragma unroll
 		for(int r=0; r<R; r++)
 			if(r>=rlo)
 				{
 #pragma unroll
 				for(int cc=0; cc<4; cc++)
-					{
-					double v = acc[r][cc] + __shfl_xor_sync(HB_FULL, acc[r][cc], 1);
-					if((jb+cc<nux) && (jb+cc<=irow[r])) v += cur[lrow[r]+jb+cc];
-					acc[r][cc] = v;
-					}
+					acc[r][cc] = (acc[r][cc] + __shfl_xor_sync(HB_FULL, acc[r][cc], 1)) + hw[r][cc];
 				}
 		__syncwarp();
 #pragma unroll
@@ -299,12 +314,13 @@ __device__ __noinline__ void hbg_syrk_chol(double *cur, const double *sW, int ld
 		}
 	}
 
-__device__ __forceinline__ void hbg_trmm_any(const hb_ctx &c, int m, int nx1, const double *prev, int nu1)
+template<bool TEAM>
+__device__ __forceinline__ void hbg_trmm_any(double *sW, int ld, int tid, int m, int nx1, const double *prev, int nu1)
 	{
-	if(m<=16) hbg_trmm<1>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
-	else if(m<=32) hbg_trmm<2>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
-	else if(m<=48) hbg_trmm<3>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
-	else hbg_trmm<4>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
+	if(m<=16) hbg_trmm<1, TEAM>(sW, ld, tid, m, nx1, prev, nu1);
+	else if(m<=32) hbg_trmm<2, TEAM>(sW, ld, tid, m, nx1, prev, nu1);
+	else if(m<=48) hbg_trmm<3, TEAM>(sW, ld, tid, m, nx1, prev, nu1);
+	else hbg_trmm<4, TEAM>(sW, ld, tid, m, nx1, prev, nu1);
 	}
 __device__ __forceinline__ void hbg_syrk_chol_any(const hb_ctx &c, double *cur, int m, int nux, int nx1)
 	{
@@ -404,7 +420,7 @@ __device__ __forceinline__ void hb_stage_factor(const hb_ctx &c, const hb_stage 
 			}
 		__syncwarp();
 #else
-		hbg_trmm_any(c, m, nx1, prev, nu1);
+		hbg_trmm_any<false>(c.sW, c.ldW, c.lane, m, nx1, prev, nu1);
 #endif
 		if(GRAD)
 			{

@@ -58,7 +58,7 @@ __global__ void hb_ric_trf_kernel(hb_dims d, long long n_inst, const double *__r
 
 /* the same two kernels with four warps per instance (ric_team.cuh): one CTA of 128 threads works on one instance at a time, the
  * factor stash is one slot per CTA; the forward sweep is warp 0's */
-__global__ void __launch_bounds__(HBT_THREADS) hbt_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
+__global__ void __launch_bounds__(HBT_THREADS, 5) hbt_ric_sv_kernel(hb_dims d, long long n_inst, const double *__restrict__ in,
 		double *__restrict__ ux, double *__restrict__ pi, double *__restrict__ Pb, double *__restrict__ stash,
 		const double *__restrict__ Qx, const double *__restrict__ qx)
 	{
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(HBT_THREADS) hbt_ric_trs_kernel(hb_dims d, lon
 		}
 	}
 
-__global__ void __launch_bounds__(HBT_THREADS) hbt_ric_trf_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, double *__restrict__ L,
+__global__ void __launch_bounds__(HBT_THREADS, 5) hbt_ric_trf_kernel(hb_dims d, long long n_inst, const double *__restrict__ in, double *__restrict__ L,
 		const double *__restrict__ Qx)
 	{
 	const int tid = threadIdx.x;
@@ -325,6 +325,18 @@ extern "C" int hb_device_sm_count(int device)
 	if(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device)!=cudaSuccess) return -1;
 	return n;
 	}
+
+#ifdef HBT_TIMING
+/* phase clocks of block 0 (lane 0 of each of the four warps), then reset */
+extern "C" int hbt_timing_read(long long *out48)
+	{
+	HB_CK(cudaDeviceSynchronize());
+	HB_CK(cudaMemcpyFromSymbol(out48, hbt_tm_g, sizeof(long long)*48));
+	long long z[48]; memset(z, 0, sizeof(z));
+	HB_CK(cudaMemcpyToSymbol(hbt_tm_g, z, sizeof(z)));
+	return 0;
+	}
+#endif
 
 extern "C" int hbt_smem_bytes(const hb_dims *d) { return (int)sizeof(double)*hbt_smem_doubles(d->nzM, d->nxM); }
 

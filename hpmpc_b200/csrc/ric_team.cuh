@@ -21,7 +21,17 @@
 
 __device__ __forceinline__ void hbt_sync() { __syncthreads(); }
 
-/* one 4-column panel of cur <- chol_mn(cur + W W') on the 16 rows of this warp (row0 .. row0+15); see hbg_syrk_chol.
+/* -DHBT_TIMING: block 0 accumulates clock64() per phase of the backward sweep, lane 0 of every warp (tools/phase_timing_team.py) */
+#ifdef HBT_TIMING
+__device__ long long hbt_tm_g[4*12];
+#define HBT_T0 long long hbt_t0_ = clock64();
+#define HBT_T(idx) do { if(blockIdx.x==0 && (tid&31)==0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&hbt_tm_g[12*(tid>>5)+(idx)], (unsigned long long)(t_-hbt_t0_)); hbt_t0_ = t_; } } while(0)
+#else
+#define HBT_T0
+#define HBT_T(idx)
+#endif
+
+/* one 4-column panel (W part, then L part)  of cur <- chol_mn(cur) on the 16 rows of this warp (row0 .. row0+15); see hbg_syrk_chol.
  * Dblk: 16 doubles of shared scratch for the diagonal block */
 __device__ __forceinline__ void hbt_panel_acc(double *cur, const double *sW, int ld, int lane, int row0, int m, int nux, int nx1, int jb,
 		double (&acc)[4], int &irow_out, bool &valid_out)
@@ -35,6 +45,7 @@ __device__ __forceinline__ void hbt_panel_acc(double *cur, const double *sW, int
 #pragma unroll
 	for(int cc=0; cc<4; cc++) { int j = jb+cc; j = j<nux ? j : nux-1; wj[cc] = j*ld; lj[cc] = HB_TRI(j); }
 	acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 0.0;
+	double hw[4];
 #pragma unroll 4
 	for(int k=h; k<nx1; k+=2)
 		{
@@ -42,6 +53,14 @@ __device__ __forceinline__ void hbt_panel_acc(double *cur, const double *sW, int
 		const double a = sW[wrow+k];
 		acc[0] = fma(a, b0, acc[0]); acc[1] = fma(a, b1, acc[1]);
 		acc[2] = fma(a, b2, acc[2]); acc[3] = fma(a, b3, acc[3]);
+		}
+#pragma unroll
+	for(int cc=0; cc<4; cc++)
+		{
+		double v = acc[cc] + __shfl_xor_sync(HB_FULL, acc[cc], 1);
+		if((jb+cc<nux) && (jb+cc<=i)) v += cur[lrow+jb+cc];
+		hw[cc] = v;
+		acc[cc] = 0.0;
 		}
 #pragma unroll 4
 	for(int k=h; k<jb; k+=2)
@@ -52,17 +71,16 @@ __device__ __forceinline__ void hbt_panel_acc(double *cur, const double *sW, int
 		acc[2] = fma(a, b2, acc[2]); acc[3] = fma(a, b3, acc[3]);
 		}
 #pragma unroll
-	for(int cc=0; cc<4; cc++)
-		{
-		double v = acc[cc] + __shfl_xor_sync(HB_FULL, acc[cc], 1);
-		if((jb+cc<nux) && (jb+cc<=i)) v += cur[lrow+jb+cc];
-		acc[cc] = v;
-		}
+	for(int cc=0; cc<4; cc++) acc[cc] = (acc[cc] + __shfl_xor_sync(HB_FULL, acc[cc], 1)) + hw[cc];
 	irow_out = i; valid_out = valid;
 	}
 
 /* the whole factorisation of one stage by the team: cur <- chol_mn(cur + W W'), W in sW (m x nx1), Dblk 16 doubles */
-__device__ __forceinline__ void hbt_syrk_chol(double *cur, const double *sW, int ld, int tid, int m, int nux, int nx1, double *Dblk)
+__device__ __forceinline__ void hbt_syrk_chol(double *cur, const double *sW, int ld, int tid, int m, int nux, int nx1, double *Dblk
+#ifdef HBT_TIMING
+		, long long &hbt_t0_
+#endif
+		)
 	{
 	const int warp = tid>>5, lane = tid&31, h = lane&1;
 	const int row0 = 16*warp;
@@ -71,6 +89,7 @@ __device__ __forceinline__ void hbt_syrk_chol(double *cur, const double *sW, int
 		{
 		const bool active = (row0+15>=jb) && (row0<m);                 /* warp-uniform */
 		double acc[4]; int i = 0; bool valid = false;
+		HBT_T(8);
 		if(active)
 			{
 			hbt_panel_acc(cur, sW, ld, lane, row0, m, nux, nx1, jb, acc, i, valid);
@@ -80,7 +99,9 @@ __device__ __forceinline__ void hbt_syrk_chol(double *cur, const double *sW, int
 				for(int cc=0; cc<4; cc++) if(jb+cc<=i) Dblk[4*(i-jb)+cc] = acc[cc];
 				}
 			}
+		HBT_T(4);
 		hbt_sync();
+		HBT_T(5);
 		if(active)
 			{
 			double D[4][4], dd[4], iv[4];
@@ -127,7 +148,9 @@ __device__ __forceinline__ void hbt_syrk_chol(double *cur, const double *sW, int
 				if(jb+3<nux) dinv[jb+3] = iv[3];
 				}
 			}
+		HBT_T(6);
 		hbt_sync();
+		HBT_T(7);
 		}
 	}
 
@@ -143,6 +166,7 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 	const int m = GRAD ? nux+1 : nux;
 	const int ntri = HB_TRI(nux) + (GRAD ? nux : 0);
 	double *sW = c.sW; const int ldW = c.ldW;
+	HBT_T0
 	{
 	const double *g = in_inst + s.off_RSQ;
 	for(int e=tid; e<ntri; e+=HBT_THREADS) hb_cp8(cur + e, g + e);
@@ -161,6 +185,7 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 	hb_g2s_wait();
 	}
 	hbt_sync();
+	HBT_T(0);
 	if(GRAD && rqvec!=nullptr)
 		for(int e=tid; e<nux; e+=HBT_THREADS) cur[HB_TRI(nux)+e] = rqvec[s.off_ux+e];
 	if(GRAD && bvec!=nullptr && nx1>0)
@@ -210,11 +235,12 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 			}
 		}
 	hbt_sync();
+	HBT_T(1);
 	if(nx1>0)
 		{
-		/* W = [B A b]' Lxx_{n+1}: rows are independent, every warp does its own 16 */
-		if(16*warp<m) hbg_trmm<1>(sW + 16*warp*ldW, ldW, lane, m - 16*warp, nx1, prev, nu1);
-		hbt_sync();
+		/* W = [B A b]' Lxx_{n+1}: eight column tiles per round, one per (warp, h), all rows of a tile in one lane set */
+		hbg_trmm_any<true>(sW, ldW, tid, m, nx1, prev, nu1);
+		HBT_T(2);
 		if(GRAD)
 			{
 			const double *wl = sW + nux*ldW;
@@ -230,7 +256,14 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 			hbt_sync();
 			}
 		}
+	HBT_T(3);
+	/* a separate W W' pass on R-row tiles, panels dealt to the warps (hbt_syrk), was measured and is slower than accumulating the W part
+	 * inside the panel loop (342 K against ~110 K cycles per factorisation at config 4, tools/phase_timing_team.py) */
+#ifdef HBT_TIMING
+	hbt_syrk_chol(cur, sW, ldW, tid, m, nux, nx1, c.sV, hbt_t0_);
+#else
 	hbt_syrk_chol(cur, sW, ldW, tid, m, nux, nx1, c.sV);
+#endif
 	}
 
 /* backward sweep n = N..0 by the team; the factor of every stage goes to Lst (global) */
