@@ -402,6 +402,7 @@ template<class S> struct hb_cipm_sv
 	static bool has_trs() { return false; }
 	static void launch(const hb_cipm_args &, int, cudaStream_t, bool) {}
 	static void launch_trs(const hb_cipm_args &, int, cudaStream_t) {}
+	static void launch_res(const hb_cipm_args &, int, cudaStream_t) {}
 	};
 template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 	{
@@ -414,6 +415,7 @@ template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 	static bool use() { const char *e = getenv("HPMPC_B200_IPM_SV2"); return !(e && e[0]=='0'); }
 	static bool has_trs() { return false; }
 	static void launch_trs(const hb_cipm_args &, int, cudaStream_t) {}
+	static void launch_res(const hb_cipm_args &, int, cudaStream_t) {}
 	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st, bool fwd)
 		{
 		const int w = fwd ? WARPS : WARPS_SLIM;
@@ -424,11 +426,93 @@ template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 		}
 	};
 
+/* residuals by the four-warp team: hb_ipm_residuals (mpc_solvers/c99/d_res_ip_res_hard.c:39-319, exit norms of
+ * interfaces/c/fortran_order_interface.c:616-652) with the two matrix-vector products of a stage split over the warps (hbt_dot) and
+ * the constraint loops over all 128 threads; mu and the norms are reduced warp by warp, then over the four warps in a fixed order */
+static __device__ void hbt_ipm_residuals(const hb_ctx &c, int tid, double *P, const hb_dims &d, const double *in_inst, const hb_ipm_ws &w,
+		const double *ux, const double *pi, double *mu, double *norms)
+	{
+	const int ld = c.ldW;
+	double nq = 0.0, nb_ = 0.0, nd = 0.0, mu2 = 0.0;
+	const double *lam_lo = w.v(CV_LAM_LO), *lam_up = w.v(CV_LAM_UP);
+	if(d.ngtot>0)
+		{
+		hb_gen_values_part(tid, HBT_THREADS, d, in_inst, w, ux);
+		hbt_sync();
+		}
+	hb_ipm_residuals_bounds_part(tid, HBT_THREADS, d, w, ux, mu2, nd);
+	double *xs = c.sV, *ps = c.sV + 64;
+	double *H = c.bufA;
+	const double *sW = c.sW;
+	for(int n=0; n<=d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		const int nu = s.nu, nux = s.nu+s.nx, nx1 = s.nx1;
+		hbt_g2s(tid, H, in_inst + s.off_RSQ, HB_TRI(nux));
+		hbt_load_BAbt(c, tid, s, in_inst);
+		for(int i=tid; i<nux; i+=HBT_THREADS) xs[i] = ux[s.off_ux+i];
+		for(int j=tid; j<nx1; j+=HBT_THREADS) ps[j] = pi[s.off_pi+j];
+		for(int i=tid; i<nux; i+=HBT_THREADS)
+			{
+			double v = w.rq0[s.off_ux+i];
+			if(n>0 && i>=nu) v -= pi[d.st[n-1].off_pi + (i-nu)];
+			w.res_q[s.off_ux+i] = v;
+			}
+		hbt_sync();
+		for(int j=tid; j<s.nb; j+=HBT_THREADS)
+			w.res_q[s.off_ux+d.idxb[s.off_c+j]] += -lam_lo[s.off_c+j] + lam_up[s.off_c+j];
+		if(s.ng>0)
+			{
+			hbt_sync();
+			const double *G = in_inst + s.off_DCt;
+			const int cg = s.off_c + s.nb;
+			for(int i=tid; i<nux; i+=HBT_THREADS)
+				{
+				double acc = w.res_q[s.off_ux+i];
+				for(int j=0; j<s.ng; j++) acc += G[i*s.ng+j]*(lam_up[cg+j] - lam_lo[cg+j]);
+				w.res_q[s.off_ux+i] = acc;
+				}
+			}
+		hb_g2s_wait();
+		hbt_sync();
+		hbt_dot(tid, nux, P, [&](int) { return 0; }, [&](int) { return nux + nx1; },
+				[&](int o, int k) { return k<nux ? (k<=o ? H[HB_TRI(o)+k] : H[HB_TRI(k)+o]) : sW[o*ld + (k-nux)]; },
+				[&](int, int k) { return k<nux ? xs[k] : ps[k-nux]; },
+				[&](int o, double sum)
+					{
+					const double acc = w.res_q[s.off_ux+o] + sum;
+					w.res_q[s.off_ux+o] = acc;
+					nq = fmax(nq, fabs(acc));
+					});
+		if(nx1>0)
+			{
+			const hb_stage s1 = d.st[n+1];
+			hbt_dot(tid, nx1, P, [&](int) { return 0; }, [&](int) { return nux; },
+					[&](int o, int k) { return sW[k*ld+o]; }, [&](int, int k) { return xs[k]; },
+					[&](int o, double sum)
+						{
+						const double acc = (w.b0[s.off_pi+o] - ux[s1.off_ux+s1.nu+o]) + sum;
+						w.res_b[s.off_pi+o] = acc;
+						nb_ = fmax(nb_, fabs(acc));
+						});
+			}
+		}
+	/* warp results, then the four warps in order */
+	mu2 = hb_warp_sum(mu2); nq = hb_warp_max(nq); nb_ = hb_warp_max(nb_); nd = hb_warp_max(nd);
+	if((tid&31)==0) { P[4*(tid>>5)] = mu2; P[4*(tid>>5)+1] = nq; P[4*(tid>>5)+2] = nb_; P[4*(tid>>5)+3] = nd; }
+	hbt_sync();
+	if(d.nbtot>0) *mu = ((P[0] + P[4]) + (P[8] + P[12]))/(2.0*d.nbtot);
+	norms[0] = fmax(fmax(P[1], P[5]), fmax(P[9], P[13]));
+	norms[1] = fmax(fmax(P[2], P[6]), fmax(P[10], P[14]));
+	norms[2] = fmax(fmax(P[3], P[7]), fmax(P[11], P[15]));
+	hbt_sync();
+	}
+
 /* any-size patterns: the sweeps with four warps per instance (ric_team.cuh), one CTA per instance.  WHICH 0: factor + solve
- * (predictor), instances handed out by an atomic counter; 1: solve with the stored factor (corrector) */
+ * (predictor), instances handed out by an atomic counter; 1: solve with the stored factor (corrector); 2: residuals */
 extern "C" int hbt_smem_bytes(const hb_dims *d);
 template<int WHICH>
-__global__ void __launch_bounds__(HBT_THREADS) hb_cipm_team_kernel(hb_cipm_args a)
+__global__ void __launch_bounds__(HBT_THREADS, 5) hb_cipm_team_kernel(hb_cipm_args a)
 	{
 	typedef hb_sweeps_generic S;
 	const hb_dims &d = a.d;
@@ -462,7 +546,7 @@ __global__ void __launch_bounds__(HBT_THREADS) hb_cipm_team_kernel(hb_cipm_args 
 			hbt_forward(c, tid, P, d, in_inst, w.L, nullptr, p2 ? w.res_b : nullptr, false, w.dux, w.dpi, true);
 			if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_A : CS_P1_A;
 			}
-		else
+		else if(WHICH==1)
 			{
 			if(st!=CS_P1_TRS && st!=CS_P2_TRS) continue;
 			const bool p2 = (st==CS_P2_TRS);
@@ -470,6 +554,18 @@ __global__ void __launch_bounds__(HBT_THREADS) hb_cipm_team_kernel(hb_cipm_args 
 			hbt_trs_backward(c, tid, P, d, in_inst, w.L, bv, rqv, w.v(CV_QXG), w.dux, w.Pb, false);
 			hbt_forward(c, tid, P, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
 			if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_B : CS_P1_B;
+			}
+		else
+			{
+			if(st!=CS_RES_ENTER && st!=CS_RES_ITER) continue;
+			double *sd = a.sd + inst*CIPM_D;
+			double mu = sd[0], norms[3] = {0.0, 0.0, 0.0};
+			hbt_ipm_residuals(c, tid, P, d, in_inst, w, a.ux + inst*d.ux_stride, a.pi + inst*d.pi_stride, &mu, norms);
+			if(tid==0)
+				{
+				sd[0] = mu; sd[3] = norms[0]; sd[4] = norms[1]; sd[5] = norms[2];
+				a.si[inst*CIPM_I] = (st==CS_RES_ENTER) ? CS_RES_ENTER_DONE : CS_RES_ITER_DONE;
+				}
 			}
 		__syncthreads();
 		}
@@ -481,6 +577,7 @@ template<> struct hb_cipm_sv<hb_sweeps_generic>
 		{
 		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
 		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
+		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
 		return 0;
 		}
 	/* HPMPC_B200_TEAM=0 keeps the one-warp-per-instance sweeps (A/B runs, bit-identical to the fused kernel) */
@@ -504,6 +601,11 @@ template<> struct hb_cipm_sv<hb_sweeps_generic>
 		{
 		const int smem = hbt_smem_bytes(&a.d);
 		hb_cipm_team_kernel<1><<<grid(a, sms, smem), HBT_THREADS, smem, st>>>(a);
+		}
+	static void launch_res(const hb_cipm_args &a, int sms, cudaStream_t st)
+		{
+		const int smem = hbt_smem_bytes(&a.d);
+		hb_cipm_team_kernel<2><<<grid(a, sms, smem), HBT_THREADS, smem, st>>>(a);
 		}
 	};
 
@@ -558,7 +660,9 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 	hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
 	/* instances whose first loop test already fails (mu0 below the phase-1 threshold) want residuals before anything else */
 	a.act = act[0]; a.n_act = cnt[0]; a.act_next = nullptr; a.n_act_next = nullptr;
-	if(light) hb_cipm_sweep_kernel<S1, 2><<<grid_l, warps_l*32, smem_l, st>>>(a);
+	const bool team_res = sv2 && hb_cipm_sv<S>::has_trs();
+	if(team_res) hb_cipm_sv<S>::launch_res(a, sms, st);
+	else if(light) hb_cipm_sweep_kernel<S1, 2><<<grid_l, warps_l*32, smem_l, st>>>(a);
 	else hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 	hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
 	for(int r=0; r<a.k_max; r++)
@@ -573,7 +677,8 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 		else if(light) hb_cipm_sweep_kernel<S1, 1><<<grid_l, warps_l*32, smem_l, st>>>(a);
 		else hb_cipm_sweep_kernel<S, 1><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		hb_cipm_step_kernel<S><<<grid_step, step_warps*32, 0, st>>>(a);
-		if(light) hb_cipm_sweep_kernel<S1, 2><<<grid_l, warps_l*32, smem_l, st>>>(a);
+		if(team_res) hb_cipm_sv<S>::launch_res(a, sms, st);
+		else if(light) hb_cipm_sweep_kernel<S1, 2><<<grid_l, warps_l*32, smem_l, st>>>(a);
 		else hb_cipm_sweep_kernel<S, 2><<<grid_sweep, warps_sweep*32, smem_sweep, st>>>(a);
 		HB_CK(cudaMemsetAsync(cnt[nxt], 0, sizeof(int), st));
 		a.act_next = act[nxt]; a.n_act_next = cnt[nxt];
