@@ -47,13 +47,15 @@ __device__ __forceinline__ void hb_g2s(int lane, double *dst_smem, const double 
 /* rows of nx1 doubles to rows of ld doubles */
 __device__ __forceinline__ void hb_g2s_rows(int lane, double *dst_smem, int ld, const double *__restrict__ src, int nrow, int nx1)
 	{
-	int i = 0, j = lane;
+	if(nx1<=0) return;
+	int i = lane/nx1, j = lane - i*nx1;
+	const int di = 32/nx1, dj = 32 - di*nx1;                              /* one step of 32 elements in (row, column) */
 	const int tot = nrow*nx1;
 	for(int e=lane; e<tot; e+=32)
 		{
-		while(j>=nx1) { j -= nx1; i++; }
 		hb_cp8(dst_smem + i*ld + j, src + e);
-		j += 32;
+		i += di; j += dj;
+		if(j>=nx1) { j -= nx1; i++; }
 		}
 	}
 

@@ -175,11 +175,12 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 		const double *gb = in_inst + s.off_BAbt;
 		const int tot = m*nx1;
 		int i = tid/nx1, j = tid - i*nx1;
+		const int di = HBT_THREADS/nx1, dj = HBT_THREADS - di*nx1;         /* one step of 128 elements in (row, column) */
 		for(int e=tid; e<tot; e+=HBT_THREADS)
 			{
 			hb_cp8(sW + i*ldW + j, gb + e);
-			j += HBT_THREADS;
-			while(j>=nx1) { j -= nx1; i++; }
+			i += di; j += dj;
+			if(j>=nx1) { j -= nx1; i++; }
 			}
 		}
 	hb_g2s_wait();
@@ -381,11 +382,12 @@ __device__ __forceinline__ void hbt_load_BAbt(const hb_ctx &c, int tid, const hb
 	if(nx1<=0) return;
 	const double *gb = in_inst + s.off_BAbt;
 	int i = tid/nx1, j = tid - i*nx1;
+	const int di = HBT_THREADS/nx1, dj = HBT_THREADS - di*nx1;
 	for(int e=tid; e<tot; e+=HBT_THREADS)
 		{
 		hb_cp8(c.sW + i*c.ldW + j, gb + e);
-		j += HBT_THREADS;
-		while(j>=nx1) { j -= nx1; i++; }
+		i += di; j += dj;
+		if(j>=nx1) { j -= nx1; i++; }
 		}
 	}
 
