@@ -20,6 +20,9 @@
 #include "layout.h"
 
 #define HB_FULL 0xffffffffu
+/* leading dimension of the shared-memory W / [B A b]' rows: odd (row-per-lane accesses are conflict-free) and at least nx rounded up
+ * to a multiple of 4 (the FP64 tensor-core path of ric_team.cuh pads the k range of a stage with zero columns) */
+#define HB_LDW(nxM) (((((nxM)+3)&~3))|1)
 
 struct hb_ctx
 	{

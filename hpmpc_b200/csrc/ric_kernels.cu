@@ -263,7 +263,7 @@ __global__ void hb_tree_kernel(hb_tdims d, long long n_trees, const double *__re
 	{
 	double *smem_warp = hb_smem + (size_t)warp*hb_smem_doubles_per_warp(d.nzM, d.nxM);
 	int lsz = HB_EVEN(HB_TRI(d.nzM) + 2*d.nzM);
-	c.lane = lane; c.ldW = d.nxM | 1;
+	c.lane = lane; c.ldW = HB_LDW(d.nxM);
 	c.bufA = smem_warp; c.bufB = c.bufA + lsz; c.sW = c.bufB + lsz; c.sV = c.sW + HB_EVEN(d.nzM*c.ldW);
 	}
 	if(skip!=nullptr && skip[n_trees*8]==0.0) return;          /* tree IPM driver: every tree has finished */

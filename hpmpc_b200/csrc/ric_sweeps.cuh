@@ -15,7 +15,7 @@ __device__ __forceinline__ hb_ctx hb_make_ctx(const hb_dims &d, double *smem_war
 	{
 	hb_ctx c;
 	c.lane = lane;
-	c.ldW = d.nxM | 1;
+	c.ldW = HB_LDW(d.nxM);
 	int lsz = HB_EVEN(HB_TRI(d.nzM) + 2*d.nzM);
 	c.bufA = smem_warp;
 	c.bufB = c.bufA + lsz;
@@ -27,7 +27,7 @@ __device__ __forceinline__ hb_ctx hb_make_ctx(const hb_dims &d, double *smem_war
 __host__ __device__ inline int hb_smem_doubles_per_warp(int nzM, int nxM)
 	{
 	int lsz = HB_EVEN(HB_TRI(nzM) + 2*nzM);
-	return 2*lsz + HB_EVEN(nzM*(nxM|1)) + 192;
+	return 2*lsz + HB_EVEN(nzM*HB_LDW(nxM)) + 192;
 	}
 
 /* the any-size sweeps fetch a stage with ordinary loads, a few in flight per lane: pull the NEXT stage's data towards the SM (L2)

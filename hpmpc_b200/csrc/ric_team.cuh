@@ -154,6 +154,230 @@ __device__ __forceinline__ void hbt_syrk_chol(double *cur, const double *sW, int
 		}
 	}
 
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* FP64 tensor-core path (mma.sync.m8n8k4.f64).  ncu on the FMA version of this sweep (profiles/r02_ncu_cipm_team_sv.txt): issue  */
+/* slots 47 % and the shared-memory pipe 48 % busy with the FP64 pipe at 16 % -- a one-row-per-lane panel spends 10 LDS and 8 DFMA  */
+/* (plus their address arithmetic) on 256 multiply-adds; one DMMA does them from two fragment loads.  DMMA runs on the same pipe at */
+/* the same rate (tools/microbench_dmma.cu: 4.0 SM-cycles per warp-DMMA = 64 FMA/clk/SM, 26 cycles dependent latency), so the gain  */
+/* is in issue slots and shared-memory wavefronts, which is what bounds this kernel.                                              */
+/* Fragments (PTX ISA, m8n8k4): A row-major 8x4, lane l holds A[l>>2][l&3]; B col-major 4x8, lane l holds B[l&3][l>>2]; C 8x8, lane l   */
+/* holds C[l>>2][2(l&3)], C[l>>2][2(l&3)+1].                                                                                       */
+/* ---------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void hbt_dmma(double &c0, double &c1, double a, double b)
+	{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+	}
+
+/* W <- W * Lxx_{n+1} in place by the team on 8 x 8 tiles.  A warp owns the row tiles rt = warp, warp+4 and computes ALL their column
+ * tiles (tile (rt, ct) sums over k >= 8ct) before it stores any: it reads and writes its own rows only, so the warps do not meet
+ * until W is complete.  One pass over k serves every column tile at or before k (a B fragment per column tile, an A fragment per row
+ * tile; up to 16 independent DMMA chains).  The k range is padded to a multiple of 4: columns nx1 .. nx1p-1 of W hold zeros
+ * (hbt_stage_factor), the matching rows of Lxx are taken as zero */
+template<int NCT>
+__device__ __noinline__ void hbt_trmm_mma_t(double *sW, int ld, int tid, int m, int nx1, const double *prev, int nu1)
+	{
+	const int warp = tid>>5, lane = tid&31, g = lane>>2, q = lane&3;
+	const int n_rt = (m+7)>>3, n_ct = (nx1+7)>>3, nx1p = (nx1+3)&~3;
+	if(warp<n_rt)
+		{
+		const bool two = warp+4<n_rt;
+		int r0 = 8*warp + g, r1 = 8*(warp+4) + g;
+		const int ra0 = r0<m ? r0 : m-1, ra1 = r1<m ? r1 : m-1;
+		const double *pa0 = sW + ra0*ld + q, *pa1 = sW + ra1*ld + q;
+		double acc0[NCT][2], acc1[NCT][2];
+#pragma unroll
+		for(int ct=0; ct<NCT; ct++) { acc0[ct][0] = 0.0; acc0[ct][1] = 0.0; acc1[ct][0] = 0.0; acc1[ct][1] = 0.0; }
+		for(int k0=0; k0<nx1p; k0+=4)
+			{
+			const int kr = k0 + q;
+			const double a0 = pa0[k0], a1 = pa1[k0];
+			const double *pb = prev + HB_TRI(nu1+kr) + nu1 + g;
+			const bool kin = kr<nx1;
+#pragma unroll
+			for(int ct=0; ct<NCT; ct++)
+				if(8*ct<=k0 && ct<n_ct)                                      /* warp-uniform */
+					{
+					const int col = 8*ct + g;
+					const double b = (kin && kr>=col) ? pb[8*ct] : 0.0;          /* kr >= col and kr < nx1 imply col < nx1 */
+					hbt_dmma(acc0[ct][0], acc0[ct][1], a0, b);
+					if(two) hbt_dmma(acc1[ct][0], acc1[ct][1], a1, b);
+					}
+			}
+		__syncwarp();
+#pragma unroll
+		for(int ct=0; ct<NCT; ct++)
+			if(ct<n_ct)
+				{
+				const int cc = 8*ct + 2*q;
+				if(r0<m)
+					{
+					if(cc<nx1) sW[r0*ld+cc] = acc0[ct][0];
+					if(cc+1<nx1) sW[r0*ld+cc+1] = acc0[ct][1];
+					}
+				if(two && r1<m)
+					{
+					if(cc<nx1) sW[r1*ld+cc] = acc1[ct][0];
+					if(cc+1<nx1) sW[r1*ld+cc+1] = acc1[ct][1];
+					}
+				}
+		}
+	hbt_sync();
+	}
+
+__device__ __forceinline__ void hbt_trmm_mma(double *sW, int ld, int tid, int m, int nx1, const double *prev, int nu1)
+	{
+	if(nx1<=16) hbt_trmm_mma_t<2>(sW, ld, tid, m, nx1, prev, nu1);
+	else if(nx1<=32) hbt_trmm_mma_t<4>(sW, ld, tid, m, nx1, prev, nu1);
+	else if(nx1<=48) hbt_trmm_mma_t<6>(sW, ld, tid, m, nx1, prev, nu1);
+	else hbt_trmm_mma_t<8>(sW, ld, tid, m, nx1, prev, nu1);
+	}
+
+/* cur <- chol_mn(cur + W W') by the team, left-looking by panels of EIGHT columns: the panel's 8 x 8 row tiles (rows at or below the
+ * panel) are dealt to the warps and accumulated by DMMA over the columns of W and over the finished columns of L, added to the
+ * entries of H in place; warp 0 factorises the 8 x 8 diagonal block (pivot rule of kernel/c99/kernel_dpotrf_c99_lib4.c:553-640 as in
+ * hb_chol) into scratch S (80 doubles), then the rows are handed to one thread each, which scales its row and stores it */
+__device__ __forceinline__ void hbt_syrk_chol_mma(double *cur, const double *sW, int ld, int tid, int m, int nux, int nx1, double *S
+#ifdef HBT_TIMING
+		, long long &hbt_t0_
+#endif
+		)
+	{
+	const int warp = tid>>5, lane = tid&31, g = lane>>2, q = lane&3;
+	const int n_rt = (m+7)>>3, nx1p = (nx1+3)&~3;
+	double *dinv = cur + HB_TRI(nux) + nux;
+	for(int jb=0; jb<nux; jb+=8)
+		{
+		HBT_T(8);
+		const int ncol = nux-jb<8 ? nux-jb : 8;
+		int rb = jb + g; rb = rb<nux ? rb : nux-1;                              /* row of W / L behind column jb+g of the panel */
+		const double *pbw = sW + rb*ld + q, *pbl = cur + HB_TRI(rb) + q;
+		for(int t=(jb>>3)+warp; t<n_rt; t+=4)
+			{
+			int ra = 8*t + g; ra = ra<m ? ra : m-1;
+			const double *paw = sW + ra*ld + q, *pal = cur + HB_TRI(ra) + q;
+			double c0 = 0.0, c1 = 0.0;
+#pragma unroll 2
+			for(int k0=0; k0<nx1p; k0+=4) hbt_dmma(c0, c1, paw[k0], pbw[k0]);
+#pragma unroll 2
+			for(int k0=0; k0<jb; k0+=4) hbt_dmma(c0, c1, -pal[k0], pbl[k0]);
+			const int r = 8*t + g, cc = jb + 2*q;
+			if(r<m)
+				{
+				/* the tile on the diagonal also leaves its entries in scratch: the rows of the diagonal block are overwritten by their
+				 * threads while threads of other warps still need the block */
+				double *h = cur + HB_TRI(r);
+				const bool dg = (t==(jb>>3));
+				if(cc<nux && cc<=r) { const double nv = h[cc] + c0; h[cc] = nv; if(dg) S[8*g+2*q] = nv; }
+				if(cc+1<nux && cc+1<=r) { const double nv = h[cc+1] + c1; h[cc+1] = nv; if(dg) S[8*g+2*q+1] = nv; }
+				}
+			}
+		HBT_T(4);
+		hbt_sync();
+		HBT_T(5);
+		/* one thread per row of the panel (rows jb .. m-1).  The 8 x 8 diagonal block [D11 0; D21 D22] is taken in two 4 x 4 steps, each
+		 * factorised by every thread for itself in registers (no exchange, four dependent pivots): columns jb..jb+3 of all rows first;
+		 * then, with L21 (rows jb+4..jb+7 of those columns) read back, D22 - L21 L21' and columns jb+4..jb+7 */
+		const int r = jb + tid;
+		const bool mine = r<m;
+		double v[8];
+		if(mine)
+			{
+			const double *h = cur + HB_TRI(r) + jb;
+#pragma unroll
+			for(int cc=0; cc<8; cc++) v[cc] = (cc<ncol && jb+cc<=r) ? h[cc] : 0.0;
+			double D[4][4], iv[4];
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+#pragma unroll
+				for(int c2=0; c2<=cc; c2++)
+					D[cc][c2] = (cc<ncol) ? S[8*cc+c2] : (c2==cc ? 1.0 : 0.0);
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+				{
+				const double piv = D[cc][cc];
+				const double inv = (piv>1e-15) ? hbg_rsqrt(piv) : 0.0;
+				D[cc][cc] = piv*inv; iv[cc] = inv;
+#pragma unroll
+				for(int c2=cc+1; c2<4; c2++) D[c2][cc] *= inv;
+#pragma unroll
+				for(int c2=cc+1; c2<4; c2++)
+#pragma unroll
+					for(int c3=cc+1; c3<=c2; c3++) D[c2][c3] = fma(-D[c2][cc], D[c3][cc], D[c2][c3]);
+				}
+			double *hs = cur + HB_TRI(r) + jb;
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+				{
+				double y = v[cc];
+#pragma unroll
+				for(int c2=0; c2<cc; c2++) y = fma(-v[c2], D[cc][c2], y);
+				v[cc] = y*iv[cc];
+				if(cc<ncol && jb+cc<=r) hs[cc] = (r==jb+cc) ? D[cc][cc] : v[cc];
+				}
+			if(tid==0)
+				{
+#pragma unroll
+				for(int cc=0; cc<4; cc++) if(cc<ncol) dinv[jb+cc] = iv[cc];
+				}
+			}
+		hbt_sync();
+		if(mine && ncol>4 && r>=jb+4)
+			{
+			double L21[4][4], D2[4][4], iv[4];
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+#pragma unroll
+				for(int c2=0; c2<4; c2++)
+					{
+					L21[cc][c2] = (cc+4<ncol) ? cur[HB_TRI(jb+4+cc)+jb+c2] : 0.0;
+					if(c2<=cc) D2[cc][c2] = (cc+4<ncol) ? S[8*(cc+4)+4+c2] : (c2==cc ? 1.0 : 0.0);
+					}
+			/* D22 - L21 L21' (lower), own entries - x[0..3] L21' */
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+				{
+#pragma unroll
+				for(int c2=0; c2<=cc; c2++)
+#pragma unroll
+					for(int k=0; k<4; k++) D2[cc][c2] = fma(-L21[cc][k], L21[c2][k], D2[cc][c2]);
+#pragma unroll
+				for(int k=0; k<4; k++) v[4+cc] = fma(-v[k], L21[cc][k], v[4+cc]);
+				}
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+				{
+				const double piv = D2[cc][cc];
+				const double inv = (piv>1e-15) ? hbg_rsqrt(piv) : 0.0;
+				D2[cc][cc] = piv*inv; iv[cc] = inv;
+#pragma unroll
+				for(int c2=cc+1; c2<4; c2++) D2[c2][cc] *= inv;
+#pragma unroll
+				for(int c2=cc+1; c2<4; c2++)
+#pragma unroll
+					for(int c3=cc+1; c3<=c2; c3++) D2[c2][c3] = fma(-D2[c2][cc], D2[c3][cc], D2[c2][c3]);
+				}
+			double *hs = cur + HB_TRI(r) + jb + 4;
+#pragma unroll
+			for(int cc=0; cc<4; cc++)
+				{
+				double y = v[4+cc];
+#pragma unroll
+				for(int c2=0; c2<cc; c2++) y = fma(-v[4+c2], D2[cc][c2], y);
+				v[4+cc] = y*iv[cc];
+				if(cc+4<ncol && jb+4+cc<=r) hs[cc] = (r==jb+4+cc) ? D2[cc][cc] : v[4+cc];
+				}
+			if(tid==4)
+				{
+#pragma unroll
+				for(int cc=0; cc<4; cc++) if(cc+4<ncol) dinv[jb+4+cc] = iv[cc];
+				}
+			}
+		HBT_T(6);
+		hbt_sync();
+		HBT_T(7);
+		}
+	}
+
 /* one backward stage by the team (the arguments of hb_stage_factor; c.lane is not used, tid is) */
 template<bool GRAD>
 __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const hb_stage &s, int nu1,
@@ -187,6 +411,13 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 	}
 	hbt_sync();
 	HBT_T(0);
+#ifndef HBT_FMA_PANELS
+	{
+	/* zero columns nx1 .. nx1p-1 of W: the DMMA k range is a multiple of 4 */
+	const int npad = ((nx1+3)&~3) - nx1;
+	if(npad>0) for(int e=tid; e<m*npad; e+=HBT_THREADS) { const int i = e/npad, j = e - i*npad; sW[i*ldW + nx1 + j] = 0.0; }
+	}
+#endif
 	if(GRAD && rqvec!=nullptr)
 		for(int e=tid; e<nux; e+=HBT_THREADS) cur[HB_TRI(nux)+e] = rqvec[s.off_ux+e];
 	if(GRAD && bvec!=nullptr && nx1>0)
@@ -240,7 +471,11 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 	if(nx1>0)
 		{
 		/* W = [B A b]' Lxx_{n+1}: eight column tiles per round, one per (warp, h), all rows of a tile in one lane set */
+#ifdef HBT_FMA_PANELS
 		hbg_trmm_any<true>(sW, ldW, tid, m, nx1, prev, nu1);
+#else
+		hbt_trmm_mma(sW, ldW, tid, m, nx1, prev, nu1);
+#endif
 		HBT_T(2);
 		if(GRAD)
 			{
@@ -260,10 +495,18 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 	HBT_T(3);
 	/* a separate W W' pass on R-row tiles, panels dealt to the warps (hbt_syrk), was measured and is slower than accumulating the W part
 	 * inside the panel loop (342 K against ~110 K cycles per factorisation at config 4, tools/phase_timing_team.py) */
+#ifdef HBT_FMA_PANELS
 #ifdef HBT_TIMING
 	hbt_syrk_chol(cur, sW, ldW, tid, m, nux, nx1, c.sV, hbt_t0_);
 #else
 	hbt_syrk_chol(cur, sW, ldW, tid, m, nux, nx1, c.sV);
+#endif
+#else
+#ifdef HBT_TIMING
+	hbt_syrk_chol_mma(cur, sW, ldW, tid, m, nux, nx1, c.sV, hbt_t0_);
+#else
+	hbt_syrk_chol_mma(cur, sW, ldW, tid, m, nux, nx1, c.sV);
+#endif
 #endif
 	}
 
