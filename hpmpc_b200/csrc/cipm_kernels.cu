@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128, 1) hb_cipm_sv2_kernel(hb_cipm_args a)
 template<class S> struct hb_cipm_sv
 	{
 	static int prep(int) { return 0; }
-	static bool use() { return false; }
+	static bool use(const hb_dims &) { return false; }
 	static bool has_trs() { return false; }
 	static void launch(const hb_cipm_args &, int, cudaStream_t, bool) {}
 	static void launch_trs(const hb_cipm_args &, int, cudaStream_t) {}
@@ -412,7 +412,7 @@ template<> struct hb_cipm_sv<hb_sweeps_fast<hbi_v0> >
 	static int smem_slim() { return WARPS_SLIM*(int)sizeof(double)*hbi2_cfg<C>::PER_WARP_SLIM; }
 	static int prep(int) { return hb_prep(hb_cipm_sv2_kernel<C, true>, smem()) || hb_prep(hb_cipm_sv2_kernel<C, false>, smem_slim()); }
 	/* HPMPC_B200_IPM_SV2=0 keeps the one-instance-per-warp sweep (A/B runs) */
-	static bool use() { const char *e = getenv("HPMPC_B200_IPM_SV2"); return !(e && e[0]=='0'); }
+	static bool use(const hb_dims &) { const char *e = getenv("HPMPC_B200_IPM_SV2"); return !(e && e[0]=='0'); }
 	static bool has_trs() { return false; }
 	static void launch_trs(const hb_cipm_args &, int, cudaStream_t) {}
 	static void launch_res(const hb_cipm_args &, int, cudaStream_t) {}
@@ -511,6 +511,7 @@ static __device__ void hbt_ipm_residuals(const hb_ctx &c, int tid, double *P, co
 /* any-size patterns: the sweeps with four warps per instance (ric_team.cuh), one CTA per instance.  WHICH 0: factor + solve
  * (predictor), instances handed out by an atomic counter; 1: solve with the stored factor (corrector); 2: residuals */
 extern "C" int hbt_smem_bytes(const hb_dims *d);
+extern "C" int hbt_wanted(const hb_dims *d);
 template<int WHICH>
 __global__ void __launch_bounds__(HBT_THREADS, 5) hb_cipm_team_kernel(hb_cipm_args a)
 	{
@@ -580,8 +581,9 @@ template<> struct hb_cipm_sv<hb_sweeps_generic>
 		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
 		return 0;
 		}
-	/* HPMPC_B200_TEAM=0 keeps the one-warp-per-instance sweeps (A/B runs, bit-identical to the fused kernel) */
-	static bool use() { const char *e = getenv("HPMPC_B200_TEAM"); return !(e && e[0]=='0'); }
+	/* HPMPC_B200_TEAM=0 keeps the one-warp-per-instance sweeps (A/B runs, bit-identical to the fused kernel); small stages stay there
+	 * by default (hbt_wanted, ric_kernels.cu) */
+	static bool use(const hb_dims &d) { return hbt_wanted(&d)!=0; }
 	static bool has_trs() { return true; }
 	static int grid(const hb_cipm_args &a, int sms, int smem)
 		{
@@ -637,7 +639,7 @@ template<class S> static int hb_cipm_run(int smem_sweep, const hb_cipm_args &bas
 	long long need = (n + step_warps - 1)/step_warps;
 	const int grid_step = (int)(need < (long long)sms*8 ? (need<1 ? 1 : need) : (long long)sms*8);
 	if(hb_prep(hb_cipm_sweep_kernel<S, 0>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 1>, smem_sweep) || hb_prep(hb_cipm_sweep_kernel<S, 2>, smem_sweep)) return -1;
-	const bool sv2 = hb_cipm_sv<S>::use();
+	const bool sv2 = hb_cipm_sv<S>::use(a.d);
 	if(sv2 && hb_cipm_sv<S>::prep(0)) return -1;
 	typedef typename hb_cipm_light<S>::type S1;
 	const bool light = hb_cipm_light<S>::use();

@@ -694,6 +694,7 @@ static int ipm_waves(hpmpc_b200_ocp *p, long long n_inst, const double *d_in, in
  * so the batch is cut into chunks whose state fits `cap` bytes (HPMPC_B200_IPM_STATE_GB, default 16 GiB); small batches (less than
  * two waves of the fused kernel), k_max < 1 and unconstrained patterns stay on the fused one-kernel path.  HPMPC_B200_IPM_FUSED=1
  * forces the fused path, =0 forces the multi-kernel one.  Both give the same bits (tests/test_cipm.py). */
+int hbt_wanted(const hb_dims *d);
 static int ipm_multi_wanted(const hpmpc_b200_ocp *p, long long n_inst, int k_max, int warm_start)
 	{
 	const char *e = getenv("HPMPC_B200_IPM_FUSED");
@@ -702,12 +703,7 @@ static int ipm_multi_wanted(const hpmpc_b200_ocp *p, long long n_inst, int k_max
 	/* measured on B200 (profiles/r02_ipm_multi_kernel.txt): config 3 (size-specialised sweeps) 67.4 -> 82.9 K solves/s; config 4
 	 * (run-time-size sweeps, one warp per instance in every kernel) 71.2 -> 64.4 K; with the four-warps-per-instance factorisation
 	 * kernel (ric_team.cuh), which only the multi-kernel driver has, the any-size patterns go there too */
-	if(p->ipm_fast_id<0)
-		{
-		const char *t = getenv("HPMPC_B200_TEAM");
-		if(t && t[0]=='0') return 0;
-		return n_inst >= 64;
-		}
+	if(p->ipm_fast_id<0) return hbt_wanted(&p->dims) && n_inst >= 64;
 	return n_inst >= 2LL*p->i_grid*p->i_warps;
 	}
 

@@ -342,10 +342,20 @@ extern "C" int hbt_smem_bytes(const hb_dims *d) { return (int)sizeof(double)*hbt
 
 /* launch shape of the four-warps-per-instance kernels: CTAs of one instance, as many per SM as the shared memory holds.
  * HPMPC_B200_TEAM=0 keeps the one-warp-per-instance kernels (A/B runs) */
-static int hbt_grid(const hb_dims *d, long long n_inst, int max_ctas)
+/* which kernel set serves an any-size pattern: the team pays off when a stage has more rows than one warp's 16 row slots; small
+ * stages (nu+nx+1 < 20) keep one warp per instance, of which an SM then holds many (measured: nx=10 nu=4 N=25 4.7 M solves/s on one
+ * warp against 3.0 M on the team; nx=12 nu=10 ng=6 (23 rows) 104 K against 119 K IPM solves/s).  HPMPC_B200_TEAM=0 / =1 force one */
+extern "C" int hbt_wanted(const hb_dims *d)
 	{
 	const char *e = getenv("HPMPC_B200_TEAM");
 	if(e && e[0]=='0') return 0;
+	if(e && e[0]=='1') return 1;
+	return d->nzM>=20;
+	}
+
+static int hbt_grid(const hb_dims *d, long long n_inst, int max_ctas)
+	{
+	if(!hbt_wanted(d)) return 0;
 	int dev = 0, sms = 0;
 	if(cudaGetDevice(&dev)!=cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)!=cudaSuccess) return 0;
 	int per_sm = 233472/(hbt_smem_bytes(d) + 1024);

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 def _with_team(flag, fn):
     if flag:
-        os.environ.pop("HPMPC_B200_TEAM", None)
+        os.environ["HPMPC_B200_TEAM"] = "1"        # forced: by default stages with fewer than 20 rows stay on one warp
     else:
         os.environ["HPMPC_B200_TEAM"] = "0"
     try:
