@@ -1,5 +1,5 @@
 """Per-kernel SASS evidence of the built library: registers / spills / stack (cuobjdump -res-usage) and counts of the mnemonics that
-matter on this path -- DFMA/DMUL/DADD (FP64 pipe), MUFU.RSQ64H (pivot), UBLKCP (1-D bulk async copies, both directions), SYNCS
+matter on this path -- DFMA/DMUL/DADD (FP64 pipe), DMMA (FP64 tensor-core tiles of the any-size team kernels), LDGSTS (cp.async staging), MUFU.RSQ64H (pivot), UBLKCP (1-D bulk async copies, both directions), SYNCS
 (mbarrier), LDS/STS, LDG/STG, SHFL, ATOM/RED, CCTL/discard, LDL/STL (local memory = spills).  No GPU needed.
 usage: python tools/sass_summary.py [lib.so] > profiles/rNN_sass_summary.md"""
 import collections, os, re, subprocess, sys
@@ -20,7 +20,7 @@ for line in res.splitlines():
 sass = subprocess.run([CUOBJ, "-sass", lib], capture_output=True, text=True).stdout
 counts = collections.OrderedDict()
 cur = None
-KEYS = ["DFMA", "DMUL", "DADD", "MUFU.RSQ64H", "MUFU.RCP64H", "UBLKCP", "SYNCS", "LDS", "STS", "LDG", "STG", "SHFL", "ATOM", "RED", "CCTL", "LDL", "STL", "BAR"]
+KEYS = ["DFMA", "DMMA", "LDGSTS", "DMUL", "DADD", "MUFU.RSQ64H", "MUFU.RCP64H", "UBLKCP", "SYNCS", "LDS", "STS", "LDG", "STG", "SHFL", "ATOM", "RED", "CCTL", "LDL", "STL", "BAR"]
 for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
     if m:
