@@ -40,13 +40,13 @@ def demangle(names):
 
 dm = demangle(list(counts))
 print(f"# SASS summary of `{os.path.relpath(lib, ROOT)}` (sm_100a; `cuobjdump -res-usage` and `-sass`, mnemonic counts are static)\n")
-print("| kernel | regs | stack B | smem B (static) | instr | DFMA | DMUL+DADD | RSQ64H | UBLKCP | SYNCS | LDS | STS | LDG | STG | SHFL | ATOM/RED | CCTL | LDL/STL |")
-print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+print("| kernel | regs | stack B | smem B (static) | instr | DFMA | DMMA | LDGSTS | DMUL+DADD | RSQ64H | UBLKCP | SYNCS | LDS | STS | LDG | STG | SHFL | ATOM/RED | CCTL | LDL/STL |")
+print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
 for k, c in counts.items():
     u = usage.get(k, {})
     name = dm.get(k, k)
     name = re.sub(r"^void ", "", name); name = re.sub(r"\(.*$", "", name)
-    print(f"| `{name}` | {u.get('REG', '?')} | {u.get('STACK', '?')} | {u.get('SHARED', '?')} | {c['_total']} | {c['DFMA']} | {c['DMUL'] + c['DADD']} | "
+    print(f"| `{name}` | {u.get('REG', '?')} | {u.get('STACK', '?')} | {u.get('SHARED', '?')} | {c['_total']} | {c['DFMA']} | {c['DMMA']} | {c['LDGSTS']} | {c['DMUL'] + c['DADD']} | "
           f"{c['MUFU.RSQ64H']} | {c['UBLKCP']} | {c['SYNCS']} | {c['LDS']} | {c['STS']} | {c['LDG']} | {c['STG']} | {c['SHFL']} | {c['ATOM'] + c['RED']} | {c['CCTL']} | {c['LDL'] + c['STL']} |")
-print("\nUBLKCP = `cp.async.bulk` (global<->shared 1-D bulk copies issued by one lane, completion on an mbarrier = SYNCS); a non-zero "
+print("\nDMMA = `mma.sync.m8n8k4.f64` (FP64 tensor-core tiles; the counts of a kernel include the device functions it calls, which cuobjdump lists inside the kernel's section); LDGSTS = `cp.async`. UBLKCP = `cp.async.bulk` (global<->shared 1-D bulk copies issued by one lane, completion on an mbarrier = SYNCS); a non-zero "
       "LDL/STL column is local-memory traffic (spills or indexed private arrays).")
