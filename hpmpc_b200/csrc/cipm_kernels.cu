@@ -45,6 +45,7 @@ struct hb_cipm_args
 	const int *act; const int *n_act;       /* active list of this launch (act == nullptr: all instances 0..n_inst-1) */
 	int *act_next; int *n_act_next;         /* step kernel, end of a round: the list it builds (nullptr: none) */
 	int *wq;                                /* factorisation kernel: work-queue counter (pairs of list entries), zeroed before the launch */
+	int team_fwd;                           /* any-size team kernel <0>: 1 = the forward sweep follows in the same kernel, 0 = factorisation only */
 	};
 
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -509,19 +510,21 @@ static __device__ void hbt_ipm_residuals(const hb_ctx &c, int tid, double *P, co
 	}
 
 /* any-size patterns: the sweeps with four warps per instance (ric_team.cuh), one CTA per instance.  WHICH 0: factor + solve
- * (predictor), instances handed out by an atomic counter; 1: solve with the stored factor (corrector); 2: residuals */
+ * (predictor) or factorisation only, instances handed out by an atomic counter; 1: solve with the stored factor (corrector);
+ * 2: residuals; 3: the predictor's forward sweep behind a factorisation-only <0> */
 extern "C" int hbt_smem_bytes(const hb_dims *d);
 extern "C" int hbt_wanted(const hb_dims *d);
 template<int WHICH>
-__global__ void __launch_bounds__(HBT_THREADS, 5) hb_cipm_team_kernel(hb_cipm_args a)
+__global__ void __launch_bounds__(HBT_THREADS, WHICH==0 ? 5 : 7) hb_cipm_team_kernel(hb_cipm_args a)
 	{
 	typedef hb_sweeps_generic S;
 	const hb_dims &d = a.d;
 	const int tid = threadIdx.x;
 	const long long n_items = a.act ? (long long)*a.n_act : a.n_inst;
 	if(n_items==0) return;
-	hb_ctx c = hb_make_ctx(d, hb_smem, tid&31);
+	/* the kernels that do not factorise keep one factor buffer (30 KB instead of 41 KB of stage data: more CTAs per SM) */
 	double *P = hb_smem + hb_smem_doubles_per_warp(d.nzM, d.nxM);
+	hb_ctx c = (WHICH==0) ? hb_make_ctx(d, hb_smem, tid&31) : hbt_make_ctx1(d, hb_smem, tid&31, P);
 	__shared__ int s_it;
 	long long it = (long long)blockIdx.x - gridDim.x;
 	for(;;)
@@ -544,7 +547,18 @@ __global__ void __launch_bounds__(HBT_THREADS, 5) hb_cipm_team_kernel(hb_cipm_ar
 			if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
 			const bool p2 = (st==CS_P2_SV);
 			hbt_backward<true>(c, tid, d, in_inst, w.L, p2 ? w.res_b : nullptr, p2 ? w.res_q : w.rq0, w.v(CV_QXD), w.v(CV_QXG), w.Pb);
-			hbt_forward(c, tid, P, d, in_inst, w.L, nullptr, p2 ? w.res_b : nullptr, false, w.dux, w.dpi, true);
+			if(a.team_fwd)
+				{
+				hbt_forward(c, tid, P, d, in_inst, w.L, nullptr, p2 ? w.res_b : nullptr, false, w.dux, w.dpi, true);
+				if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_A : CS_P1_A;
+				}
+			/* else: the state stays *_SV and hb_cipm_team_kernel<3> (one factor buffer, seven CTAs per SM) picks the instance up */
+			}
+		else if(WHICH==3)
+			{
+			if(st!=CS_P1_SV && st!=CS_P2_SV) continue;
+			const bool p2 = (st==CS_P2_SV);
+			hbt_forward1(c, tid, P, d, in_inst, w.L, nullptr, p2 ? w.res_b : nullptr, false, w.dux, w.dpi, true);
 			if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_A : CS_P1_A;
 			}
 		else if(WHICH==1)
@@ -553,7 +567,7 @@ __global__ void __launch_bounds__(HBT_THREADS, 5) hb_cipm_team_kernel(hb_cipm_ar
 			const bool p2 = (st==CS_P2_TRS);
 			const double *bv = p2 ? w.res_b : w.b0, *rqv = p2 ? w.res_q : w.rq0;
 			hbt_trs_backward(c, tid, P, d, in_inst, w.L, bv, rqv, w.v(CV_QXG), w.dux, w.Pb, false);
-			hbt_forward(c, tid, P, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
+			hbt_forward1(c, tid, P, d, in_inst, w.L, w.dux, bv, true, w.dux, w.dpi, true);
 			if(tid==0) a.si[inst*CIPM_I] = p2 ? CS_P2_B : CS_P1_B;
 			}
 		else
@@ -579,6 +593,7 @@ template<> struct hb_cipm_sv<hb_sweeps_generic>
 		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
 		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
 		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
+		HB_CK(cudaFuncSetAttribute(hb_cipm_team_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226*1024));
 		return 0;
 		}
 	/* HPMPC_B200_TEAM=0 keeps the one-warp-per-instance sweeps (A/B runs, bit-identical to the fused kernel); small stages stay there
@@ -594,19 +609,28 @@ template<> struct hb_cipm_sv<hb_sweeps_generic>
 		if(g>a.n_inst) g = a.n_inst;
 		return (int)(g<1 ? 1 : g);
 		}
-	static void launch(const hb_cipm_args &a, int sms, cudaStream_t st, bool)
+	/* HPMPC_B200_TEAM_FWD=1 keeps the predictor's forward sweep inside the factorisation kernel (A/B runs) */
+	static void launch(const hb_cipm_args &a0, int sms, cudaStream_t st, bool)
 		{
+		hb_cipm_args a = a0;
+		const char *e = getenv("HPMPC_B200_TEAM_FWD");
+		a.team_fwd = (e && e[0]=='1') ? 1 : 0;
 		const int smem = hbt_smem_bytes(&a.d);
 		hb_cipm_team_kernel<0><<<grid(a, sms, smem), HBT_THREADS, smem, st>>>(a);
+		if(!a.team_fwd)
+			{
+			const int smem1 = (int)sizeof(double)*hbt_smem1_doubles(a.d.nzM, a.d.nxM);
+			hb_cipm_team_kernel<3><<<grid(a, sms, smem1), HBT_THREADS, smem1, st>>>(a);
+			}
 		}
 	static void launch_trs(const hb_cipm_args &a, int sms, cudaStream_t st)
 		{
-		const int smem = hbt_smem_bytes(&a.d);
+		const int smem = (int)sizeof(double)*hbt_smem1_doubles(a.d.nzM, a.d.nxM);
 		hb_cipm_team_kernel<1><<<grid(a, sms, smem), HBT_THREADS, smem, st>>>(a);
 		}
 	static void launch_res(const hb_cipm_args &a, int sms, cudaStream_t st)
 		{
-		const int smem = hbt_smem_bytes(&a.d);
+		const int smem = (int)sizeof(double)*hbt_smem1_doubles(a.d.nzM, a.d.nxM);
 		hb_cipm_team_kernel<2><<<grid(a, sms, smem), HBT_THREADS, smem, st>>>(a);
 		}
 	};
@@ -711,7 +735,7 @@ extern "C" int hb_launch_cipm(const hb_dims *d, long long n_inst, const double *
 	a.si = ip; ip += CIPM_I*n_inst;
 	int *lists = ip; ip += 2*n_inst;
 	int *counters = ip;
-	a.act = nullptr; a.n_act = nullptr; a.act_next = nullptr; a.n_act_next = nullptr;
+	a.act = nullptr; a.n_act = nullptr; a.act_next = nullptr; a.n_act_next = nullptr; a.team_fwd = 1;
 	long long need = (n_inst + warps - 1)/warps;
 	if(need<grid) grid = (int)(need<1 ? 1 : need);
 	switch(fast_id)

@@ -563,7 +563,20 @@ __device__ __forceinline__ void hbt_dot(int tid, int n_out, double *P, K0 k0, K1
 	hbt_sync();
 	}
 
-/* one forward stage by the team: the arguments and the algebra of hb_stage_forward (lqcp_solvers/d_back_ric_rec.c:341-397 sv,
+/* pi of a stage from x_{n+1} (in c.sV + 64, left there by hbt_stage_forward) and the factor of stage n+1 (nx1, nu1, nux1: its sizes):
+ * pi = (trs ? pi : 0) + Lxx (Lxx' x + (trs ? 0 : gradient row)) */
+__device__ __forceinline__ void hbt_stage_pi(const hb_ctx &c, int tid, double *P, int nx1, int nu1, int nux1, const double *Ln1, bool trs, double *pi_n)
+	{
+	double *xs = c.sV + 64, *tmp = c.sV + 128;
+	hbt_dot(tid, nx1, P, [&](int o) { return o; }, [&](int) { return nx1; },
+			[&](int o, int k) { return Ln1[HB_TRI(nu1+k)+nu1+o]; }, [&](int, int k) { return xs[k]; },
+			[&](int o, double sum) { tmp[o] = (trs ? 0.0 : Ln1[HB_TRI(nux1)+nu1+o]) + sum; });
+	hbt_dot(tid, nx1, P, [&](int) { return 0; }, [&](int o) { return o+1; },
+			[&](int o, int k) { return Ln1[HB_TRI(nu1+o)+nu1+k]; }, [&](int, int k) { return tmp[k]; },
+			[&](int o, double sum) { pi_n[o] = (trs ? pi_n[o] : 0.0) + sum; });
+	}
+
+/* one forward stage by the team: the arguments and the algebra of hb_stage_forward (Ln1 == nullptr: pi is left to the caller) (lqcp_solvers/d_back_ric_rec.c:341-397 sv,
  * :737-789 trs); the triangular solve with the ks x ks corner stays on warp 0 */
 __device__ __forceinline__ void hbt_stage_forward(const hb_ctx &c, int tid, double *P, const hb_stage &s, const hb_stage &s1, int n,
 		const double *Ln, const double *Ln1, const double *lrow, const double *bvec, bool trs,
@@ -575,7 +588,7 @@ __device__ __forceinline__ void hbt_stage_forward(const hb_ctx &c, int tid, doub
 	const int ld = c.ldW;
 	const double *dinv = Ln + HB_TRI(nux) + nux;
 	const double *sW = c.sW;
-	double *v = c.sV, *xs = c.sV + 64, *tmp = c.sV + 128;
+	double *v = c.sV, *xs = c.sV + 64;
 	for(int i=tid; i<nux; i+=HBT_THREADS)
 		v[i] = (i<ks) ? -(lrow!=nullptr ? lrow[s.off_ux+i] : Ln[HB_TRI(nux)+i]) : ux[s.off_ux+i];
 	hbt_sync();
@@ -603,15 +616,7 @@ __device__ __forceinline__ void hbt_stage_forward(const hb_ctx &c, int tid, doub
 				ux[s1.off_ux+nu1+o] = acc;
 				xs[o] = acc;
 				});
-	if(compute_pi)
-		{
-		hbt_dot(tid, nx1, P, [&](int o) { return o; }, [&](int) { return nx1; },
-				[&](int o, int k) { return Ln1[HB_TRI(nu1+k)+nu1+o]; }, [&](int, int k) { return xs[k]; },
-				[&](int o, double sum) { tmp[o] = (trs ? 0.0 : Ln1[HB_TRI(nux1)+nu1+o]) + sum; });
-		hbt_dot(tid, nx1, P, [&](int) { return 0; }, [&](int o) { return o+1; },
-				[&](int o, int k) { return Ln1[HB_TRI(nu1+o)+nu1+k]; }, [&](int, int k) { return tmp[k]; },
-				[&](int o, double sum) { pi[s.off_pi+o] = (trs ? pi[s.off_pi+o] : 0.0) + sum; });
-		}
+	if(compute_pi && Ln1!=nullptr) hbt_stage_pi(c, tid, P, nx1, nu1, nux1, Ln1, trs, pi + s.off_pi);
 	}
 
 /* stage data of the team's solve sweeps: packed factor(s) and [B A b]' by all threads (LDGSTS) */
@@ -660,6 +665,58 @@ static __device__ void hbt_forward(const hb_ctx &c, int tid, double *P, const hb
 		hbt_stage_forward(c, tid, P, s, s1, n, a, b, lrow, bvec, trs, ux, pi, compute_pi);
 		double *t = a; a = b; b = t;
 		}
+	}
+
+/* forward sweep with ONE factor buffer: stage n needs L_n only when pi_{n-1} = f(L_n, x_n) is taken at stage n instead of stage n-1
+ * (and pi_{N-1} after the loop, behind a last load of L_N).  With [B A b]' that is 30 KB of stage data per instance instead of 41:
+ * seven CTAs per SM instead of five for the kernels that do not factorise.  Same operations in the same order per entry as
+ * hbt_forward */
+static __device__ void hbt_forward1(const hb_ctx &c, int tid, double *P, const hb_dims &d, const double *in_inst, const double *Lst,
+		const double *lrow, const double *bvec, bool trs, double *ux, double *pi, bool compute_pi)
+	{
+	double *a = c.bufA;
+	for(int n=0; n<d.N; n++)
+		{
+		const hb_stage s = d.st[n];
+		const hb_stage s1 = d.st[n+1];
+		if(tid<32)
+			{
+			hb_prefetch_l2(Lst + s1.off_L, HB_TRI(s1.nu+s1.nx) + 2*(s1.nu+s1.nx), tid);
+			if(n+1<d.N) hb_prefetch_l2(in_inst + s1.off_BAbt, (s1.nu+s1.nx+1)*s1.nx1, tid);
+			}
+		hbt_g2s(tid, a, Lst + s.off_L, HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx));
+		hbt_load_BAbt(c, tid, s, in_inst);
+		hb_g2s_wait();
+		hbt_sync();
+		if(n>0 && compute_pi) hbt_stage_pi(c, tid, P, s.nx, s.nu, s.nu+s.nx, a, trs, pi + d.st[n-1].off_pi);
+		hbt_stage_forward(c, tid, P, s, s1, n, a, nullptr, lrow, bvec, trs, ux, pi, compute_pi);
+		}
+	if(compute_pi && d.N>0)
+		{
+		const hb_stage s = d.st[d.N];
+		hbt_g2s(tid, a, Lst + s.off_L, HB_TRI(s.nu+s.nx) + 2*(s.nu+s.nx));
+		hb_g2s_wait();
+		hbt_sync();
+		hbt_stage_pi(c, tid, P, s.nx, s.nu, s.nu+s.nx, a, trs, pi + d.st[d.N-1].off_pi);
+		}
+	}
+
+/* the layout of the kernels that keep one factor buffer: [L | W | vectors | P] */
+__host__ __device__ inline int hbt_smem1_doubles(int nzM, int nxM)
+	{
+	return HB_EVEN(HB_TRI(nzM) + 2*nzM) + HB_EVEN(nzM*HB_LDW(nxM)) + 192 + HBT_P_DOUBLES;
+	}
+__device__ __forceinline__ hb_ctx hbt_make_ctx1(const hb_dims &d, double *smem, int lane, double *&P)
+	{
+	hb_ctx c;
+	c.lane = lane;
+	c.ldW = HB_LDW(d.nxM);
+	c.bufA = smem;
+	c.bufB = smem;                                                     /* not used by these kernels */
+	c.sW = smem + HB_EVEN(HB_TRI(d.nzM) + 2*d.nzM);
+	c.sV = c.sW + HB_EVEN(d.nzM*c.ldW);
+	P = c.sV + 192;
+	return c;
 	}
 
 /* one backward stage of the solve-only sweep by the team (hb_trs_stage_back; lqcp_solvers/d_back_ric_rec.c:628-732) */
