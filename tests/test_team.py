@@ -44,6 +44,7 @@ def _batch(mk, n, first):
     ("small", lambda xi: problems.mass_spring_ocp(10, 3, 7, bounds=False, xi=xi), 64),             # nu+nx+1 = 14: one warp of the team
     ("wide", lambda xi: problems.mass_spring_ocp(30, 12, 6, bounds=False, xi=xi), 40),             # 43 rows
     ("tiny", lambda xi: problems.mass_spring_ocp(2, 1, 3, bounds=False, xi=xi), 17),
+    ("limit", lambda xi: problems.mass_spring_ocp(50, 13, 4, bounds=False, xi=xi), 24),           # nu+nx+1 = 64: eight row tiles, eight column tiles
 ])
 def test_team_sv_trf_trs_equal_one_warp(name, mk, n):
     import torch
