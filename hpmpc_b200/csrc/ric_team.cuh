@@ -434,35 +434,51 @@ __device__ __forceinline__ void hbt_stage_factor(const hb_ctx &c, int tid, const
 		}
 	if(Qx!=nullptr && s.ng>0)
 		{
-		/* general constraints (see hb_stage_factor); rows over the team's threads */
+		/* general constraints: H += [D C]' diag(Qx_g) [D C] (see hb_stage_factor) on 8 x 8 DMMA tiles of the lower triangle, the
+		 * fragments taken from the instance block (row-major nux x ng, L2-resident after the stage's loads); the gradient row
+		 * += [D C]' qx_g with one thread per column */
 		hbt_sync();
-		const int ng = s.ng;
+		const int ng = s.ng, ngp = (ng+3)&~3;
 		const double *G = in_inst + s.off_DCt;
 		const double *Qg = Qx + s.off_c + s.nb;
-		for(int i=tid; i<m; i+=HBT_THREADS)
+		{
+		const int lane = tid&31, g = lane>>2, q = lane&3;
+		const int n_t = (nux+7)>>3, ntile = n_t*(n_t+1)/2;
+		for(int idx=warp; idx<ntile; idx+=HBT_WARPS)
 			{
-			double *hi = cur + HB_TRI(i);
-			if(i<nux)
+			int t = 0, rem = idx;                                           /* tile idx -> (row tile t, column tile p <= t) */
+			while(rem>t) { rem -= t+1; t++; }
+			const int p = rem;
+			const int ra = 8*t + g, rb = 8*p + g;
+			const double *pa = G + (ra<nux ? ra : nux-1)*ng, *pb = G + (rb<nux ? rb : nux-1)*ng;
+			double c0 = 0.0, c1 = 0.0;
+			for(int k0=0; k0<ngp; k0+=4)
 				{
-				const double *gi = G + i*ng;
-				for(int k=0; k<=i; k++)
-					{
-					const double *gk = G + k*ng;
-					double acc = 0.0;
-					for(int j=0; j<ng; j++) acc += gi[j]*Qg[j]*gk[j];
-					hi[k] += acc;
-					}
+				const int kj = k0 + q;
+				const bool in = kj<ng;
+				const double a = in ? pa[kj] : 0.0;
+				const double b = in ? pb[kj]*Qg[kj] : 0.0;
+				hbt_dmma(c0, c1, a, b);
 				}
-			else if(qx!=nullptr)
+			const int cc = 8*p + 2*q;
+			if(ra<nux)
 				{
-				const double *qg = qx + s.off_c + s.nb;
-				for(int k=0; k<nux; k++)
-					{
-					const double *gk = G + k*ng;
-					double acc = 0.0;
-					for(int j=0; j<ng; j++) acc += qg[j]*gk[j];
-					hi[k] += acc;
-					}
+				double *h = cur + HB_TRI(ra);
+				if(cc<=ra) h[cc] += c0;
+				if(cc+1<=ra) h[cc+1] += c1;
+				}
+			}
+		}
+		if(GRAD && qx!=nullptr)
+			{
+			const double *qg = qx + s.off_c + s.nb;
+			double *hi = cur + HB_TRI(nux);
+			for(int k=tid; k<nux; k+=HBT_THREADS)
+				{
+				const double *gk = G + k*ng;
+				double acc = 0.0;
+				for(int j=0; j<ng; j++) acc += qg[j]*gk[j];
+				hi[k] += acc;
 				}
 			}
 		}
