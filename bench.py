@@ -419,7 +419,7 @@ def run_ours(args):
                "workload": "SHARED DYNAMICS (not the headline workload): config-2 matrices stored once per batch, per-instance b, q, r; factor once + batched solve with the stored factor",
                "roofline": {"bound": "hbm", "achieved": bytes_inst * n / (float(np.mean(per)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": bytes_inst * n / (float(np.mean(per)) * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                            "kernel": "hb_ric_trs_shared_kernel (+ hb_ric_trf_kernel once)", "algorithmic_bytes_per_solve": bytes_inst}}
+                            "kernel": ("hb_ric_trs_shared_kernel" if os.environ.get("HPMPC_B200_SHARED_GENERIC") else "hb_ric_trs_shared_tpi_kernel<12,5>") + " (+ hb_ric_trf_kernel once)", "algorithmic_bytes_per_solve": bytes_inst}}
         pin = lambda m: torch.empty((n, m), dtype=torch.float64, pin_memory=True)
         h_vec, h_ux, h_pi = pin(vs), pin(h.sz.ux_stride), pin(h.sz.pi_stride)
         h_vec.copy_(d_vec)
@@ -611,6 +611,12 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    if args.workload == "shared":
+        sh = bench_shared(max(args.steps, 3), max(args.warmup, 3))
+        if rank == 0:
+            print(json.dumps(sh))
+        return
+
     if args.workload == "ipm":
         ipm = bench_ipm(args.steps, args.warmup)
         if rank == 0:
@@ -789,7 +795,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ric", choices=["ric", "ipm", "tree", "tree_ipm"])
+    ap.add_argument("--workload", default="ric", choices=["ric", "ipm", "tree", "tree_ipm", "shared"])
     ap.add_argument("--n-trees", type=int, default=0)
     ap.add_argument("--n-inst", type=int, default=0)
     ap.add_argument("--n-inst-ipm", type=int, default=0)

@@ -1012,7 +1012,11 @@ int hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(hpmpc_b200_ocp *p, long long 
 	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
 	CK(cudaSetDevice(p->device));
 	const long long vs = p->dims.ux_stride + p->dims.pi_stride;
-	long long cs = (256LL<<20)/(long long)(sizeof(double)*vs);
+	/* chunk: 128 MB of vectors (the solve of a chunk is far shorter than its copies, so the pipeline's fill and drain -- one
+	 * chunk's H2D and one chunk's D2H -- is what small chunks save); HPMPC_B200_SHARED_CHUNK_MB overrides */
+	long long chunk_mb = 128;
+	{ const char *e = getenv("HPMPC_B200_SHARED_CHUNK_MB"); if(e && atoll(e)>0) chunk_mb = atoll(e); }
+	long long cs = (chunk_mb<<20)/(long long)(sizeof(double)*vs);
 	if(cs<1) cs = 1;
 	if(cs>n_inst) cs = n_inst;
 	int grid, warps, smem, resident, k = 0;

@@ -16,6 +16,7 @@
 #include "ric_sweeps.cuh"
 #include "ric_team.cuh"
 #include "ric_tree.cuh"
+#include "ric_shared_tpi.cuh"
 
 /* ------------------------------------------------------------------------------------------------ */
 /* Riccati kernels                                                                                   */
@@ -230,6 +231,13 @@ __global__ void __launch_bounds__(256) hb_ric_trs_shared_kernel(hb_dims d, long 
 
 extern "C" long long hb_trs_shared_smem_bytes(const hb_dims *d, const hb_stage *st_host, int warps, int *resident)
 	{
+	/* size patterns with a thread-per-instance kernel (ric_shared_tpi.cuh): *resident = 16 + 2 variant + (nx_0 != 0);
+	 * HPMPC_B200_SHARED_GENERIC=1 keeps the warp-per-instance kernel */
+	{
+	int nx0 = 0;
+	const int var = getenv("HPMPC_B200_SHARED_GENERIC")!=NULL ? -1 : hb_tpi_variant(d, st_host, &nx0);
+	if(var>=0 && hb_tpi_smem_bytes(d, st_host)<=113*1024) { *resident = 16 + 2*var + (nx0!=0); return hb_tpi_smem_bytes(d, st_host); }
+	}
 	const int ldW = d->nxM | 1;
 	long long B = HB_EVEN((d->N+2+1)/2);
 	for(int n=0; n<d->N; n++) B += HB_EVEN((st_host[n].nu + st_host[n].nx + 1)*ldW);
@@ -245,6 +253,27 @@ extern "C" int hb_launch_ric_trs_shared(const hb_dims *d, long long n_inst, cons
 	{
 	if(d->nzM>64) return -2;
 	if(warps>8) return -3;
+	if(resident>=16)
+		{
+		/* one thread per instance, warps take blocks of 32 instances from a queue (its counter: the first 8 bytes of `work`) */
+		const int var = (resident-16)>>1, nx0 = ((resident-16)&1) ? d->nxM : 0;
+		const long long need = (n_inst + 255)/256;
+		if(need<grid) grid = (int)need;
+		unsigned long long *queue = reinterpret_cast<unsigned long long*>(work);
+		HB_CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+		if(var==0)
+			{
+			if(hb_prep(hb_ric_trs_shared_tpi_kernel<12, 5>, smem)) return -1;
+			hb_ric_trs_shared_tpi_kernel<12, 5><<<grid, 256, smem, (cudaStream_t)stream>>>(*d, n_inst, in_shared, L_shared, vec, ux, pi, queue, nx0);
+			}
+		else
+			{
+			if(hb_prep(hb_ric_trs_shared_tpi_kernel<8, 3>, smem)) return -1;
+			hb_ric_trs_shared_tpi_kernel<8, 3><<<grid, 256, smem, (cudaStream_t)stream>>>(*d, n_inst, in_shared, L_shared, vec, ux, pi, queue, nx0);
+			}
+		HB_CK(cudaGetLastError());
+		return 0;
+		}
 	if(hb_prep(hb_ric_trs_shared_kernel, smem)) return -1;
 	hb_ric_trs_shared_kernel<<<grid, warps*32, smem, (cudaStream_t)stream>>>(*d, n_inst, in_shared, L_shared, vec, ux, pi, work, resident);
 	HB_CK(cudaGetLastError());

@@ -80,3 +80,41 @@ def test_shared_dynamics_device_and_host_paths(cfg):
     np.testing.assert_array_equal(hux[:, :n_ux], uxh[:, :n_ux])
     np.testing.assert_array_equal(hpi, pih)
     h.close()
+
+
+@pytest.mark.parametrize("shape", [dict(nx=12, nu=5, N=30), dict(nx=12, nu=5, N=7, free_x0=True), dict(nx=8, nu=3, N=10),
+                                   dict(nx=8, nu=3, N=4, free_x0=True)])
+def test_thread_per_instance_kernel_equals_warp_per_instance_kernel(shape, monkeypatch):
+    """The size-specialised shared-dynamics kernel (one thread per instance, csrc/ric_shared_tpi.cuh) against the any-size one
+    (one warp per instance, HPMPC_B200_SHARED_GENERIC=1) and the oracle: nx_0 = 0 and nx_0 = nx, a ragged last warp."""
+    import torch
+    L = _api()
+    base = problems.mass_spring_ocp(shape["nx"], shape["nu"], shape["N"], free_x0=shape.get("free_x0", False))
+    h = capi.BatchOcp(base, device=0)
+    n = 32 * 70 + 13
+    probs = shared_batch(base, n, seed=11)
+    blk = h.pack(base)
+    vec = np.stack([vec_of(h, p) for p in probs])
+    d_blk, d_vec = torch.from_numpy(blk).cuda(), torch.from_numpy(vec).cuda()
+    d_L = torch.zeros(L.hpmpc_b200_shared_factor_doubles(h.h) + 8, dtype=torch.float64, device="cuda")
+    assert L.hpmpc_b200_d_back_ric_rec_trf_shared(h.h, d_blk.data_ptr(), d_L.data_ptr(), None) == 0
+    out = {}
+    for mode in ("tpi", "generic"):
+        if mode == "generic":
+            monkeypatch.setenv("HPMPC_B200_SHARED_GENERIC", "1")
+        else:
+            monkeypatch.delenv("HPMPC_B200_SHARED_GENERIC", raising=False)
+        ux = torch.full((n, h.sz.ux_stride), np.nan, dtype=torch.float64, device="cuda")
+        pi = torch.full((n, h.sz.pi_stride), np.nan, dtype=torch.float64, device="cuda")
+        assert L.hpmpc_b200_d_back_ric_rec_trs_shared_batch(h.h, n, d_blk.data_ptr(), d_L.data_ptr(), d_vec.data_ptr(), ux.data_ptr(), pi.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        out[mode] = (ux.cpu().numpy(), pi.cpu().numpy())
+    n_ux, n_pi = sum(base.nx) + sum(base.nu), sum(base.nx[1:])
+    a, b = out["tpi"], out["generic"]
+    assert np.isfinite(a[0][:, :n_ux]).all() and np.isfinite(a[1][:, :n_pi]).all()
+    assert rel_err(a[0][:, :n_ux], b[0][:, :n_ux]) < 1e-12 and rel_err(a[1][:, :n_pi], b[1][:, :n_pi]) < 1e-12
+    for i in (0, 31, 32, n - 1):
+        o = oracle.ric(probs[i], "sv")
+        u, x = h.split_ux(a[0][i])
+        assert rel_err(u, o["u"]) < TOL and rel_err(x, o["x"]) < TOL and rel_err(h.split_pi(a[1][i]), o["pi"]) < TOL, i
+    h.close()
