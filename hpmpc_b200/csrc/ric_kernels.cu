@@ -257,7 +257,8 @@ extern "C" int hb_launch_ric_trs_shared(const hb_dims *d, long long n_inst, cons
 		{
 		/* one thread per instance, warps take blocks of 32 instances from a queue (its counter: the first 8 bytes of `work`) */
 		const int var = (resident-16)>>1, nx0 = ((resident-16)&1) ? d->nxM : 0;
-		const long long need = (n_inst + 255)/256;
+		/* one CTA per SM slot as soon as there are that many blocks of 32 instances: the queue then spreads the blocks evenly */
+		const long long need = (n_inst + 31)/32;
 		if(need<grid) grid = (int)need;
 		unsigned long long *queue = reinterpret_cast<unsigned long long*>(work);
 		HB_CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), (cudaStream_t)stream));

@@ -16,6 +16,11 @@
  * forward sweep reads w back, writes u, x and pi: 8 x (2(nu+nx) + nx + (nu+nx) + (nu+nx) + nx) bytes -- the vectors' own
  * sizes; nothing else crosses HBM.  A thread's accesses to one stage are a contiguous run of (nu+nx) or nx doubles, so the
  * sectors a warp touches are used completely (through L1) although neighbouring lanes are an instance stride apart.
+ *
+ * Measured alternative (not kept): the vectors staged through a per-warp 32 x 29 shared-memory buffer with warp-coalesced copies,
+ * one 16-warp CTA per SM.  Global LSU wavefronts fell from 73 M to 19 M per 65 536 instances, shared-memory wavefronts rose from
+ * 44 M to 98 M (row stores + loads, 18 M bank conflicts of the copies), the LSU data pipe stayed at 60-63 % of its peak and the
+ * rate at 262 144 instances was the same (83.7 vs 83.8 M solves/s; +10 % at 65 536) -- profiles/r02_ncu_shared_tpi.txt.
  */
 #pragma once
 #include "layout.h"
@@ -49,10 +54,11 @@ __device__ __forceinline__ void tpi_LLt(const double *__restrict__ Ln1, const do
 	}
 
 /* one backward stage (n < N).  NUX = nu_n + nx_n, KS = columns eliminated (nu_n, or NUX at n = 0), NU1 = nu_{n+1}.
- * wx: in = x-part of w_{n+1}, out = x-part of w_n (when the stage has one) */
+ * wx: in = x-part of w_{n+1}, out = x-part of w_n (when the stage has one).  rq / b are read before the first fence and w_out is
+ * written after the last one, so w_out may be the memory rq came from */
 template<int NX, int NU, int NUX, int KS, int NU1>
 __device__ __forceinline__ void tpi_back(const double *__restrict__ Ln, const double *__restrict__ Ln1, const double *__restrict__ W,
-		const double *__restrict__ rq, const double *__restrict__ b, double *__restrict__ w_out, double (&wx)[NX])
+		const double *rq, const double *b, double *w_out, double (&wx)[NX])
 	{
 	double bb[NX], zero[NX], Pb[NX], tmp[NX], v[NUX];
 	#pragma unroll
@@ -91,7 +97,7 @@ __device__ __forceinline__ void tpi_back(const double *__restrict__ Ln, const do
  * ux_n: w_n in, u_n (and at n = 0 x_0) out; ux_n1x: x-part of w_{n+1} in, x_{n+1} out */
 template<int NX, int NU, int NUX, int KS, int NU1>
 __device__ __forceinline__ void tpi_fwd(const double *__restrict__ Ln, const double *__restrict__ Ln1, const double *__restrict__ W,
-		const double *__restrict__ b, double *__restrict__ ux_n, double *__restrict__ ux_n1x, double *__restrict__ pi_n, double (&xs)[NX])
+		const double *b, double *ux_n, double *ux_n1x, double *pi_n, double (&xs)[NX])
 	{
 	double v[NUX], pin[NX], pout[NX];
 	#pragma unroll
@@ -228,3 +234,4 @@ static long long hb_tpi_smem_bytes(const hb_dims *d, const hb_stage *st_host)
 	const int N = d->N, NU = st_host[0].nu, NX = st_host[1].nx, nux0 = NU + st_host[0].nx;
 	return 8LL*(HB_EVEN(d->L_stride) + HB_EVEN(nux0*NX) + (long long)(N-1)*HB_EVEN((NU+NX)*NX));
 	}
+
