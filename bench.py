@@ -527,7 +527,10 @@ def run_ours(args):
                "config": {"workload": f"scenario-tree Riccati factor+solve (d_tree_back_ric_rec_sv), {n} trees, md=4 Nr=3 Nh=20 nx=12 nu=5 (1173 nodes), FP64",
                           "parallelism": f"16 depth-2 subtrees sharded over {world} GPU(s), 5 nodes above replicated, one NCCL all-gather of subtree-root factor blocks per solve, issued inside the C library (hpmpc_b200_d_tree_back_ric_rec_sv_batch_mg)"},
                "roofline": {"bound": "hbm", "achieved": Bt * n / (float(np.mean(per)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": Bt * n / (float(np.mean(per)) * 1e-3) / 1e9 / hbm_peak, "traffic": None, "kernel": "hb_tree_kernel (3 launches)",
+                            "frac": Bt * n / (float(np.mean(per)) * 1e-3) / 1e9 / hbm_peak, "traffic": 9.63e6 * n / world,
+                            "traffic_source": "static: profiles/r02_tree_traffic.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum of the 8 launches of one solve, "
+                                              "1024 trees on one GPU: 9.63 MB per tree; the tail kernels run at 3.8 / 6.3 TB/s of DRAM traffic)",
+                            "kernel": "hbk_tail_kernel (backward, forward) + 6 x hbk_top_kernel",
                             "algorithmic_bytes_per_tree": Bt, "algorithmic_flops_per_tree": F},
                "gpu_launches": 8 * steps}
         if world > 1:
