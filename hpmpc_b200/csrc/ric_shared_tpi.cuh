@@ -21,6 +21,11 @@
  * one 16-warp CTA per SM.  Global LSU wavefronts fell from 73 M to 19 M per 65 536 instances, shared-memory wavefronts rose from
  * 44 M to 98 M (row stores + loads, 18 M bank conflicts of the copies), the LSU data pipe stayed at 60-63 % of its peak and the
  * rate at 262 144 instances was the same (83.7 vs 83.8 M solves/s; +10 % at 65 536) -- profiles/r02_ncu_shared_tpi.txt.
+ * Second measured alternative (not kept): two instances per lane (each broadcast load serves 64 instances; 255 registers, 8 warps
+ * per SM): 85.6 vs 83.8 M solves/s.  Three kernels with different LSU / shared-memory / occupancy profiles tie, so the common
+ * factor is what limits them: the vectors' layout in HBM -- per stage a warp touches 32 runs of 96-136 bytes that are an instance
+ * stride (7 KB) apart, and DRAM delivers 2.0 TB/s on that pattern.  A stage-major layout of the vectors (one 4 KB run per warp and
+ * stage) is the next step; it changes this mode's buffer format.
  */
 #pragma once
 #include "layout.h"

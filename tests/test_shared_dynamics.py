@@ -84,14 +84,14 @@ def test_shared_dynamics_device_and_host_paths(cfg):
 
 @pytest.mark.parametrize("shape", [dict(nx=12, nu=5, N=30), dict(nx=12, nu=5, N=7, free_x0=True), dict(nx=8, nu=3, N=10),
                                    dict(nx=8, nu=3, N=4, free_x0=True)])
-def test_thread_per_instance_kernel_equals_warp_per_instance_kernel(shape, monkeypatch):
+@pytest.mark.parametrize("n", [32 * 70 + 13, 64 * 9 + 45])
+def test_thread_per_instance_kernel_equals_warp_per_instance_kernel(shape, n, monkeypatch):
     """The size-specialised shared-dynamics kernel (one thread per instance, csrc/ric_shared_tpi.cuh) against the any-size one
     (one warp per instance, HPMPC_B200_SHARED_GENERIC=1) and the oracle: nx_0 = 0 and nx_0 = nx, a ragged last warp."""
     import torch
     L = _api()
     base = problems.mass_spring_ocp(shape["nx"], shape["nu"], shape["N"], free_x0=shape.get("free_x0", False))
     h = capi.BatchOcp(base, device=0)
-    n = 32 * 70 + 13
     probs = shared_batch(base, n, seed=11)
     blk = h.pack(base)
     vec = np.stack([vec_of(h, p) for p in probs])
