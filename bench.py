@@ -671,7 +671,7 @@ def run_ours(args):
             args.n_trees, args.no_cpu = args.n_trees or 4096, True          # the same 4096 trees at every N: strong scaling
             tr = bench_tree(3, 2)
             if rank == 0:
-                out["extra"]["tree"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "gpu_launches", "scaling", "n_gpus")} | \
+                out["extra"]["tree"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "gpu_launches", "scaling", "n_gpus", "roofline")} | \
                     {"workload": tr["config"]["workload"], "parallelism": tr["config"]["parallelism"]}
             args.n_trees = saved[0] or 1024                # per GPU (weak)
             ti = bench_tree_ipm(2, 1)
