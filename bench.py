@@ -420,6 +420,21 @@ def run_ours(args):
                "roofline": {"bound": "hbm", "achieved": bytes_inst * n / (float(np.mean(per)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": bytes_inst * n / (float(np.mean(per)) * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                             "kernel": ("hb_ric_trs_shared_kernel" if os.environ.get("HPMPC_B200_SHARED_GENERIC") else "hb_ric_trs_shared_tpi_kernel<12,5>") + " (+ hb_ric_trf_kernel once)", "algorithmic_bytes_per_solve": bytes_inst}}
+        # the same solve on STAGE-MAJOR vectors (random data of the same shape: the layout, not the values, is what is measured)
+        try:
+            L.hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 6
+
+            def launch_sm():
+                assert L.hpmpc_b200_d_back_ric_rec_trf_shared(h.h, d_blk.data_ptr(), d_L.data_ptr(), st) == 0
+                assert L.hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major(h.h, n, d_blk.data_ptr(), d_L.data_ptr(), d_vec.data_ptr(), ux.data_ptr(), pi.data_ptr(), st) == 0
+            tot_sm, per_sm = time_steps(launch_sm, steps, warmup, stream, barrier)
+            tot_sm = reduce_max_time(tot_sm, dev)
+            out["stage_major_vectors"] = {"value": world * n * steps / (tot_sm * 1e-3), "unit": "solves/s", "ms_per_step": tot_sm / steps,
+                                          "frac": bytes_inst * n / (float(np.mean(per_sm)) * 1e-3) / 1e9 / hbm_peak,
+                                          "entry": "hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major"}
+            launch(); torch.cuda.synchronize()          # ux, pi back in the instance-major layout for the e2e check below
+        except Exception as e:      # noqa: BLE001
+            out["stage_major_vectors"] = {"error": repr(e)}
         pin = lambda m: torch.empty((n, m), dtype=torch.float64, pin_memory=True)
         h_vec, h_ux, h_pi = pin(vs), pin(h.sz.ux_stride), pin(h.sz.pi_stride)
         h_vec.copy_(d_vec)

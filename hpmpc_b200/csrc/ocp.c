@@ -1003,6 +1003,24 @@ int hpmpc_b200_d_back_ric_rec_trs_shared_batch(hpmpc_b200_ocp *p, long long n_in
 	return call_end(p, stream, hb_launch_ric_trs_shared(&p->dims, n_inst, d_in_shared, d_L_shared, d_vec, d_ux, d_pi, p->scratch, grid, warps, smem, resident, stream));
 	}
 
+/* the same with STAGE-MAJOR vectors (thread-per-instance shapes only, -2 otherwise): the part of a vector that belongs to stage n --
+ * offset o_n in the instance-major layout, K_n doubles -- is one array [n_inst][K_n] at o_n * n_inst; d_vec: [r q] parts
+ * (ux offsets, nu_n + nx_n doubles), then from ux_stride * n_inst on the b parts (pi offsets, nx_{n+1} doubles); d_ux, d_pi alike.
+ * A warp's 32 instances then touch one contiguous run per stage, which is what DRAM wants. */
+int hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major(hpmpc_b200_ocp *p, long long n_inst, const double *d_in_shared, const double *d_L_shared,
+		const double *d_vec, double *d_ux, double *d_pi, void *stream)
+	{
+	if(n_inst<=0) return 0;
+	if(p->device<0) { fprintf(stderr, "hpmpc_b200: host-only handle (device < 0) cannot solve; there is no CPU fallback\n"); return -4; }
+	CK(cudaSetDevice(p->device));
+	int grid, warps, smem, resident;
+	if(trs_shared_shape(p, n_inst, &grid, &warps, &smem, &resident)) return -2;
+	if(resident<16) { fprintf(stderr, "hpmpc_b200: stage-major shared-dynamics solve: no thread-per-instance kernel for this size pattern\n"); return -2; }
+	if(call_begin(p, stream)) return -1;
+	if(ensure_scratch(p, sizeof(double)*(size_t)grid*warps*p->dims.pi_stride)) return -1;
+	return call_end(p, stream, hb_launch_ric_trs_shared(&p->dims, n_inst, d_in_shared, d_L_shared, d_vec, d_ux, d_pi, p->scratch, grid, warps, smem, resident + 64, stream));
+	}
+
 /* the same from host buffers: the shared block goes over once and is factorised once, then the vectors stream through in chunks
  * (H2D of chunk k+1 overlaps the solve / D2H of chunk k) */
 int hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in_shared, const double *h_vec,

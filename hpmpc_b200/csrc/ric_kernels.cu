@@ -256,22 +256,20 @@ extern "C" int hb_launch_ric_trs_shared(const hb_dims *d, long long n_inst, cons
 	if(resident>=16)
 		{
 		/* one thread per instance, warps take blocks of 32 instances from a queue (its counter: the first 8 bytes of `work`) */
+		/* + 64: stage-major vectors (hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major) */
+		const int stage_major = resident>=64;
+		if(stage_major) resident -= 64;
 		const int var = (resident-16)>>1, nx0 = ((resident-16)&1) ? d->nxM : 0;
 		/* one CTA per SM slot as soon as there are that many blocks of 32 instances: the queue then spreads the blocks evenly */
 		const long long need = (n_inst + 31)/32;
 		if(need<grid) grid = (int)need;
 		unsigned long long *queue = reinterpret_cast<unsigned long long*>(work);
 		HB_CK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), (cudaStream_t)stream));
-		if(var==0)
-			{
-			if(hb_prep(hb_ric_trs_shared_tpi_kernel<12, 5>, smem)) return -1;
-			hb_ric_trs_shared_tpi_kernel<12, 5><<<grid, 256, smem, (cudaStream_t)stream>>>(*d, n_inst, in_shared, L_shared, vec, ux, pi, queue, nx0);
-			}
-		else
-			{
-			if(hb_prep(hb_ric_trs_shared_tpi_kernel<8, 3>, smem)) return -1;
-			hb_ric_trs_shared_tpi_kernel<8, 3><<<grid, 256, smem, (cudaStream_t)stream>>>(*d, n_inst, in_shared, L_shared, vec, ux, pi, queue, nx0);
-			}
+#define HB_TPI_LAUNCH(NX_, NU_, SM_) do { if(hb_prep(hb_ric_trs_shared_tpi_kernel<NX_, NU_, SM_>, smem)) return -1; \
+		hb_ric_trs_shared_tpi_kernel<NX_, NU_, SM_><<<grid, 256, smem, (cudaStream_t)stream>>>(*d, n_inst, in_shared, L_shared, vec, ux, pi, queue, nx0); } while(0)
+		if(var==0) { if(stage_major) HB_TPI_LAUNCH(12, 5, true); else HB_TPI_LAUNCH(12, 5, false); }
+		else       { if(stage_major) HB_TPI_LAUNCH(8, 3, true);  else HB_TPI_LAUNCH(8, 3, false); }
+#undef HB_TPI_LAUNCH
 		HB_CK(cudaGetLastError());
 		return 0;
 		}

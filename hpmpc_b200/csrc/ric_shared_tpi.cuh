@@ -147,13 +147,16 @@ __device__ __forceinline__ void tpi_fwd(const double *__restrict__ Ln, const dou
 	for(int i=0; i<NX; i++) pi_n[i] = pout[i];
 	}
 
-/* shared memory: [factor of the horizon, L_stride doubles | [B A]' of stage 0 .. N-1, rows of exactly nx doubles] */
-template<int NX, int NU>
+/* shared memory: [factor of the horizon, L_stride doubles | [B A]' of stage 0 .. N-1, rows of exactly nx doubles].
+ * SM: STAGE-MAJOR vectors -- the part of a vector that belongs to stage n (offset o_n, K_n doubles per instance) is one array
+ * [n_inst][K_n] at o_n * n_inst, so the 32 instances of a warp touch ONE run of 32 K_n doubles per stage instead of 32 runs an
+ * instance stride apart (the b part of vec starts at ux_stride * n_inst). */
+template<int NX, int NU, bool SM>
 __global__ void __launch_bounds__(256, 2) hb_ric_trs_shared_tpi_kernel(hb_dims d, long long n_inst, const double *__restrict__ in_shared,
 		const double *__restrict__ L_shared, const double *__restrict__ vec, double *__restrict__ ux_all, double *__restrict__ pi_all,
 		unsigned long long *__restrict__ queue, int nx0)
 	{
-	extern __shared__ __align__(16) double tpi_smem[];
+	extern __shared__ double tpi_smem[];
 	const int N = d.N, lane = threadIdx.x&31;
 	constexpr int NZ = NU+NX;
 	const int nux0 = NU + nx0;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(256, 2) hb_ric_trs_shared_tpi_kernel(hb_dims d
 		for(int e=threadIdx.x; e<cnt; e+=blockDim.x) dst[e] = gb[e];
 		}
 	__syncthreads();
-	const long long vs = d.ux_stride + d.pi_stride;
+	const long long vs = d.ux_stride + d.pi_stride, us = d.ux_stride, ps = d.pi_stride;
 	const hb_stage *__restrict__ st = d.st;
 	for(;;)
 		{
@@ -178,44 +181,48 @@ __global__ void __launch_bounds__(256, 2) hb_ric_trs_shared_tpi_kernel(hb_dims d
 		if((long long)(blk*32ULL)>=n_inst) break;
 		const long long inst = (long long)(blk*32ULL) + lane;
 		if(inst>=n_inst) continue;                      /* nothing below talks to the other lanes */
-		const double *rq = vec + inst*vs, *bv = rq + d.ux_stride;
-		double *ux = ux_all + inst*d.ux_stride, *pi = pi_all + inst*d.pi_stride;
+		/* the instance's part of stage s in [r q], b, ux, pi */
+		auto RQ = [&](const hb_stage &s) { return SM ? vec + (long long)s.off_ux*n_inst + inst*(s.nu+s.nx) : vec + inst*vs + s.off_ux; };
+		auto BV = [&](const hb_stage &s) { return SM ? vec + (us + s.off_pi)*n_inst + inst*NX : vec + inst*vs + us + s.off_pi; };
+		auto UX = [&](const hb_stage &s) { return SM ? ux_all + (long long)s.off_ux*n_inst + inst*(s.nu+s.nx) : ux_all + inst*us + s.off_ux; };
+		auto PI = [&](const hb_stage &s) { return SM ? pi_all + (long long)s.off_pi*n_inst + inst*NX : pi_all + inst*ps + s.off_pi; };
 		double wx[NX];
 		{
-		const int o = st[N].off_ux;
+		const hb_stage s = st[N];
+		const double *q = RQ(s); double *u = UX(s);
 		#pragma unroll
-		for(int j=0; j<NX; j++) { wx[j] = rq[o+j]; ux[o+j] = wx[j]; }
+		for(int j=0; j<NX; j++) { wx[j] = q[j]; u[j] = wx[j]; }
 		}
 		/* backward: stage N-1 looks at a stage N without inputs, stage 0 eliminates everything it has */
 		{
 		const hb_stage s = st[N-1];
-		tpi_back<NX, NU, NZ, NU, 0>(Lsm + s.off_L, Lsm + st[N].off_L, Bsm + szB0 + (N-2)*szB, rq + s.off_ux, bv + s.off_pi, ux + s.off_ux, wx);
+		tpi_back<NX, NU, NZ, NU, 0>(Lsm + s.off_L, Lsm + st[N].off_L, Bsm + szB0 + (N-2)*szB, RQ(s), BV(s), UX(s), wx);
 		}
 		for(int n=N-2; n>=1; n--)
 			{
 			const hb_stage s = st[n];
-			tpi_back<NX, NU, NZ, NU, NU>(Lsm + s.off_L, Lsm + st[n+1].off_L, Bsm + szB0 + (n-1)*szB, rq + s.off_ux, bv + s.off_pi, ux + s.off_ux, wx);
+			tpi_back<NX, NU, NZ, NU, NU>(Lsm + s.off_L, Lsm + st[n+1].off_L, Bsm + szB0 + (n-1)*szB, RQ(s), BV(s), UX(s), wx);
 			}
 		{
 		const hb_stage s = st[0];
-		if(nx0==0) tpi_back<NX, NU, NU, NU, NU>(Lsm + s.off_L, Lsm + st[1].off_L, Bsm, rq + s.off_ux, bv + s.off_pi, ux + s.off_ux, wx);
-		else       tpi_back<NX, NU, NZ, NZ, NU>(Lsm + s.off_L, Lsm + st[1].off_L, Bsm, rq + s.off_ux, bv + s.off_pi, ux + s.off_ux, wx);
+		if(nx0==0) tpi_back<NX, NU, NU, NU, NU>(Lsm + s.off_L, Lsm + st[1].off_L, Bsm, RQ(s), BV(s), UX(s), wx);
+		else       tpi_back<NX, NU, NZ, NZ, NU>(Lsm + s.off_L, Lsm + st[1].off_L, Bsm, RQ(s), BV(s), UX(s), wx);
 		}
 		/* forward */
 		double xs[NX];
 		{
 		const hb_stage s = st[0], s1 = st[1];
-		if(nx0==0) tpi_fwd<NX, NU, NU, NU, NU>(Lsm + s.off_L, Lsm + s1.off_L, Bsm, bv + s.off_pi, ux + s.off_ux, ux + s1.off_ux + NU, pi + s.off_pi, xs);
-		else       tpi_fwd<NX, NU, NZ, NZ, NU>(Lsm + s.off_L, Lsm + s1.off_L, Bsm, bv + s.off_pi, ux + s.off_ux, ux + s1.off_ux + NU, pi + s.off_pi, xs);
+		if(nx0==0) tpi_fwd<NX, NU, NU, NU, NU>(Lsm + s.off_L, Lsm + s1.off_L, Bsm, BV(s), UX(s), UX(s1) + NU, PI(s), xs);
+		else       tpi_fwd<NX, NU, NZ, NZ, NU>(Lsm + s.off_L, Lsm + s1.off_L, Bsm, BV(s), UX(s), UX(s1) + NU, PI(s), xs);
 		}
 		for(int n=1; n<N-1; n++)
 			{
 			const hb_stage s = st[n], s1 = st[n+1];
-			tpi_fwd<NX, NU, NZ, NU, NU>(Lsm + s.off_L, Lsm + s1.off_L, Bsm + szB0 + (n-1)*szB, bv + s.off_pi, ux + s.off_ux, ux + s1.off_ux + NU, pi + s.off_pi, xs);
+			tpi_fwd<NX, NU, NZ, NU, NU>(Lsm + s.off_L, Lsm + s1.off_L, Bsm + szB0 + (n-1)*szB, BV(s), UX(s), UX(s1) + NU, PI(s), xs);
 			}
 		{
 		const hb_stage s = st[N-1], s1 = st[N];
-		tpi_fwd<NX, NU, NZ, NU, 0>(Lsm + s.off_L, Lsm + s1.off_L, Bsm + szB0 + (N-2)*szB, bv + s.off_pi, ux + s.off_ux, ux + s1.off_ux, pi + s.off_pi, xs);
+		tpi_fwd<NX, NU, NZ, NU, 0>(Lsm + s.off_L, Lsm + s1.off_L, Bsm + szB0 + (N-2)*szB, BV(s), UX(s), UX(s1), PI(s), xs);
 		}
 		}
 	}

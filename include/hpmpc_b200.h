@@ -141,6 +141,10 @@ long long hpmpc_b200_shared_factor_doubles(const hpmpc_b200_ocp *p);
 int hpmpc_b200_d_back_ric_rec_trf_shared(hpmpc_b200_ocp *p, const double *d_in_shared, double *d_L_shared, void *stream);
 int hpmpc_b200_d_back_ric_rec_trs_shared_batch(hpmpc_b200_ocp *p, long long n_inst, const double *d_in_shared, const double *d_L_shared,
                                                const double *d_vec, double *d_ux, double *d_pi, void *stream);
+/* stage-major vectors (uniform (12,5) / (8,3) patterns only, -2 otherwise): the part of a vector that belongs to stage n (offset
+ * o_n in the layout above, K_n doubles) is one array [n_inst][K_n] at o_n * n_inst; b parts start at ux_stride * n_inst */
+int hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major(hpmpc_b200_ocp *p, long long n_inst, const double *d_in_shared, const double *d_L_shared,
+                                               const double *d_vec, double *d_ux, double *d_pi, void *stream);
 int hpmpc_b200_d_back_ric_rec_sv_shared_batch_host(hpmpc_b200_ocp *p, long long n_inst, const double *h_in_shared, const double *h_vec,
                                                    double *h_ux, double *h_pi);
 

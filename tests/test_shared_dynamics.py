@@ -48,6 +48,7 @@ def _api():
     L.hpmpc_b200_d_back_ric_rec_trf_shared.argtypes = [C.c_void_p] * 4
     L.hpmpc_b200_d_back_ric_rec_trs_shared_batch.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 6
     L.hpmpc_b200_d_back_ric_rec_sv_shared_batch_host.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
+    L.hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 6
     return L
 
 
@@ -118,3 +119,49 @@ def test_thread_per_instance_kernel_equals_warp_per_instance_kernel(shape, n, mo
         u, x = h.split_ux(a[0][i])
         assert rel_err(u, o["u"]) < TOL and rel_err(x, o["x"]) < TOL and rel_err(h.split_pi(a[1][i]), o["pi"]) < TOL, i
     h.close()
+
+
+def _to_stage_major(a, parts, n):
+    """a: (n, stride) instance-major; parts: [(offset, K)] -> flat array with part (o, K) as an [n][K] array at o * n."""
+    out = np.zeros(a.shape[0] * a.shape[1])
+    for o, K in parts:
+        out[o * n:o * n + n * K] = a[:, o:o + K].reshape(-1)
+    return out
+
+
+@pytest.mark.parametrize("shape", [dict(nx=12, nu=5, N=30), dict(nx=8, nu=3, N=6, free_x0=True)])
+def test_stage_major_vectors_give_the_same_bits(shape):
+    """hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major: the same kernel arithmetic on vectors stored stage by stage."""
+    import torch
+    L = _api()
+    base = problems.mass_spring_ocp(shape["nx"], shape["nu"], shape["N"], free_x0=shape.get("free_x0", False))
+    h = capi.BatchOcp(base, device=0)
+    n = 32 * 21 + 7
+    probs = shared_batch(base, n, seed=5)
+    blk = h.pack(base)
+    vec = np.stack([vec_of(h, p) for p in probs])
+    us, ps = h.sz.ux_stride, h.sz.pi_stride
+    ux_parts = [(h.off[s]["ux"], base.nu[s] + base.nx[s]) for s in range(base.N + 1)]
+    pi_parts = [(h.off[s]["pi"], base.nx[s + 1]) for s in range(base.N)]
+    vec_sm = np.concatenate([_to_stage_major(vec[:, :us], ux_parts, n), _to_stage_major(vec[:, us:], pi_parts, n)])
+    d_blk = torch.from_numpy(blk).cuda()
+    d_L = torch.zeros(L.hpmpc_b200_shared_factor_doubles(h.h) + 8, dtype=torch.float64, device="cuda")
+    assert L.hpmpc_b200_d_back_ric_rec_trf_shared(h.h, d_blk.data_ptr(), d_L.data_ptr(), None) == 0
+    d_vec, d_vec_sm = torch.from_numpy(vec).cuda(), torch.from_numpy(vec_sm).cuda()
+    ux = torch.zeros((n, us), dtype=torch.float64, device="cuda"); pi = torch.zeros((n, ps), dtype=torch.float64, device="cuda")
+    ux_sm = torch.zeros(n * us, dtype=torch.float64, device="cuda"); pi_sm = torch.zeros(n * ps, dtype=torch.float64, device="cuda")
+    assert L.hpmpc_b200_d_back_ric_rec_trs_shared_batch(h.h, n, d_blk.data_ptr(), d_L.data_ptr(), d_vec.data_ptr(), ux.data_ptr(), pi.data_ptr(), None) == 0
+    assert L.hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major(h.h, n, d_blk.data_ptr(), d_L.data_ptr(), d_vec_sm.data_ptr(), ux_sm.data_ptr(),
+                                                                   pi_sm.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ux_sm.cpu().numpy(), _to_stage_major(ux.cpu().numpy(), ux_parts, n))
+    np.testing.assert_array_equal(pi_sm.cpu().numpy(), _to_stage_major(pi.cpu().numpy(), pi_parts, n))
+    o = oracle.ric(probs[n - 1], "sv")
+    u, x = h.split_ux(ux.cpu().numpy()[n - 1])
+    assert rel_err(u, o["u"]) < TOL and rel_err(x, o["x"]) < TOL
+    h.close()
+    # a pattern without a thread-per-instance kernel is refused, not served by something else
+    h2 = capi.BatchOcp(problems.mass_spring_ocp(10, 4, 8), device=0)
+    assert L.hpmpc_b200_d_back_ric_rec_trs_shared_batch_stage_major(h2.h, 4, d_blk.data_ptr(), d_L.data_ptr(), d_vec_sm.data_ptr(), ux_sm.data_ptr(),
+                                                                    pi_sm.data_ptr(), None) == -2
+    h2.close()
