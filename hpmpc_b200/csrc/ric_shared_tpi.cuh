@@ -182,10 +182,14 @@ __global__ void __launch_bounds__(256, 2) hb_ric_trs_shared_tpi_kernel(hb_dims d
 		const long long inst = (long long)(blk*32ULL) + lane;
 		if(inst>=n_inst) continue;                      /* nothing below talks to the other lanes */
 		/* the instance's part of stage s in [r q], b, ux, pi */
-		auto RQ = [&](const hb_stage &s) { return SM ? vec + (long long)s.off_ux*n_inst + inst*(s.nu+s.nx) : vec + inst*vs + s.off_ux; };
-		auto BV = [&](const hb_stage &s) { return SM ? vec + (us + s.off_pi)*n_inst + inst*NX : vec + inst*vs + us + s.off_pi; };
-		auto UX = [&](const hb_stage &s) { return SM ? ux_all + (long long)s.off_ux*n_inst + inst*(s.nu+s.nx) : ux_all + inst*us + s.off_ux; };
-		auto PI = [&](const hb_stage &s) { return SM ? pi_all + (long long)s.off_pi*n_inst + inst*NX : pi_all + inst*ps + s.off_pi; };
+		const double *const rq0 = vec + inst*vs, *const bv0 = rq0 + us;          /* instance-major bases */
+		double *const ux0 = ux_all + inst*us, *const pi0 = pi_all + inst*ps;
+		const double *const bsm = vec + us*n_inst + inst*NX;                      /* stage-major: + off_pi * n_inst */
+		double *const psm = pi_all + inst*NX;
+		auto RQ = [&](const hb_stage &s) { return SM ? vec + (long long)s.off_ux*n_inst + inst*(s.nu+s.nx) : rq0 + s.off_ux; };
+		auto BV = [&](const hb_stage &s) { return SM ? bsm + (long long)s.off_pi*n_inst : bv0 + s.off_pi; };
+		auto UX = [&](const hb_stage &s) { return SM ? ux_all + (long long)s.off_ux*n_inst + inst*(s.nu+s.nx) : ux0 + s.off_ux; };
+		auto PI = [&](const hb_stage &s) { return SM ? psm + (long long)s.off_pi*n_inst : pi0 + s.off_pi; };
 		double wx[NX];
 		{
 		const hb_stage s = st[N];
